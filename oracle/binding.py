@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for the two CPU checkers.
+
+* ``Oracle``    -> oracle/liboracle.so   (the C restatement, smem_oracle.c)
+* ``Reference`` -> oracle/_ref/libbwaref.so (the reference's own objects + ref_harness.c);
+  present only where ``make -C oracle ref`` ran or where the prebuilt file travelled.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SRC = "/root/reference/software"
+
+
+class SeedOpt(C.Structure):
+    """mem_opt_t seeding fields (bwamem.h:33-60), defaults from mem_opt_init (bwamem.c:45-75)."""
+    _fields_ = [("min_seed_len", C.c_int), ("split_factor", C.c_double), ("split_width", C.c_int), ("start_width", C.c_int)]
+
+    def __init__(self, min_seed_len=19, split_factor=1.5, split_width=10, start_width=1):
+        super().__init__(min_seed_len, split_factor, split_width, start_width)
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("extends", "blocks", "smem1_calls", "steps", "intervals", "max_curr", "max_mem")]
+
+    def asdict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class _OrcIndex(C.Structure):
+    _fields_ = [("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64), ("bwt_size", C.c_uint64),
+                ("bwt", C.c_void_p)]
+
+
+def build_oracle() -> str:
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    return os.path.join(HERE, "liboracle.so")
+
+
+def build_reference() -> "str | None":
+    """Compile the reference where its sources lie; returns the .so path or None if unavailable."""
+    so = os.path.join(HERE, "_ref", "libbwaref.so")
+    if os.path.isdir(REF_SRC):
+        subprocess.run(["make", "-s", "-C", HERE, "ref", "-j8"], check=True)
+    return so if os.path.exists(so) else None
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class _Base:
+    """Shared flat-array plumbing: both checkers expose the same collect/smem1/time signatures."""
+
+    def _collect(self, fn, handle, seq, offs, opt, nthreads, extra=()):
+        n = len(offs) - 1
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        cap = max(64, 24 * n)
+        read_off = np.zeros(n + 1, np.int64)
+        n_steps = np.zeros(max(n, 1), np.int32)
+        last = np.zeros(max(n, 1), np.int32)
+        while True:
+            intv = np.zeros((cap, 4), np.uint64)
+            step = np.zeros(cap, np.uint16)
+            tot = fn(handle, C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64), C.byref(opt), nthreads, _p(intv, C.c_uint64), C.c_int64(cap),
+                     _p(read_off, C.c_int64), _p(step, C.c_uint16), _p(n_steps, C.c_int32), _p(last, C.c_int32), *extra)
+            if tot <= cap:
+                return dict(intv=intv[:tot], read_off=read_off, step=step[:tot], n_steps=n_steps[:n], last_start=last[:n])
+            cap = int(tot)
+
+    def _smem1(self, fn, handle, seq, offs, x, min_intv):
+        n = len(offs) - 1
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        x = np.ascontiguousarray(x, np.int32)
+        mi = np.ascontiguousarray(min_intv, np.int32)
+        cap = max(64, 32 * n)
+        read_off = np.zeros(n + 1, np.int64)
+        ret = np.zeros(max(n, 1), np.int32)
+        while True:
+            intv = np.zeros((cap, 4), np.uint64)
+            tot = fn(handle, C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64), _p(x, C.c_int32), _p(mi, C.c_int32),
+                     _p(intv, C.c_uint64), C.c_int64(cap), _p(read_off, C.c_int64), _p(ret, C.c_int32))
+            if tot <= cap:
+                return dict(intv=intv[:tot], read_off=read_off, ret=ret[:n])
+            cap = int(tot)
+
+    def _time(self, fn, handle, seq, offs, opt, nthreads):
+        n = len(offs) - 1
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        ck = C.c_uint64(0)
+        ni = C.c_int64(0)
+        sec = fn(handle, C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64), C.byref(opt), nthreads, C.byref(ck), C.byref(ni))
+        return dict(seconds=float(sec), checksum=int(ck.value), n_intervals=int(ni.value), reads_per_s=n / sec if sec > 0 else 0.0)
+
+
+class Oracle(_Base):
+    """The C restatement.  ``index`` is any object with primary/L2/seq_len/bwt_size/words_numpy()."""
+
+    def __init__(self, index):
+        self.lib = C.CDLL(build_oracle())
+        self.words = np.ascontiguousarray(index.words_numpy(), np.uint32)
+        self.ix = _OrcIndex(int(index.primary), (C.c_uint64 * 5)(*[int(v) for v in index.L2]), int(index.seq_len),
+                            int(index.bwt_size), self.words.ctypes.data)
+        L = self.lib
+        L.orc_collect.restype = C.c_int64
+        L.orc_smem1.restype = C.c_int64
+        L.orc_time_collect.restype = C.c_double
+        L.orc_checksum.restype = C.c_uint64
+
+    def collect(self, seq, offs, opt=None, nthreads=1, stats=False):
+        opt = opt or SeedOpt()
+        st = Stats()
+        out = self._collect(self.lib.orc_collect, C.byref(self.ix), seq, offs, opt, C.c_int(nthreads), (C.byref(st) if stats else None,))
+        if stats:
+            out["stats"] = st.asdict()
+        return out
+
+    def smem1(self, seq, offs, x, min_intv):
+        return self._smem1(self.lib.orc_smem1, C.byref(self.ix), seq, offs, x, min_intv)
+
+    def time_collect(self, seq, offs, opt=None, nthreads=1):
+        return self._time(self.lib.orc_time_collect, C.byref(self.ix), seq, offs, opt or SeedOpt(), C.c_int(nthreads))
+
+    def occ4(self, k: int):
+        cnt = (C.c_uint64 * 4)()
+        self.lib.orc_occ4(C.byref(self.ix), C.c_uint64(k & 0xFFFFFFFFFFFFFFFF), cnt)
+        return [int(v) for v in cnt]
+
+    def extend(self, ik3, is_back: int):
+        ok = (C.c_uint64 * 12)()
+        self.lib.orc_extend(C.byref(self.ix), (C.c_uint64 * 3)(*[int(v) for v in ik3]), C.c_int(is_back), ok)
+        return np.array(list(ok), dtype=np.uint64).reshape(4, 3)
+
+    def checksum(self, intv, read_off):
+        intv = np.ascontiguousarray(intv, np.uint64)
+        read_off = np.ascontiguousarray(read_off, np.int64)
+        return int(self.lib.orc_checksum(C.c_int64(len(read_off) - 1), _p(intv, C.c_uint64), _p(read_off, C.c_int64)))
+
+
+class Reference(_Base):
+    """The reference's own compiled objects.  Raises FileNotFoundError when they are not available."""
+
+    def __init__(self, index=None, path: "str | None" = None):
+        so = build_reference()
+        if so is None:
+            raise FileNotFoundError("oracle/_ref/libbwaref.so is not built and /root/reference is absent")
+        self.lib = L = C.CDLL(so)
+        L.ref_bwt_load.restype = C.c_void_p
+        L.ref_bwt_view.restype = C.c_void_p
+        L.ref_collect.restype = C.c_int64
+        L.ref_smem1.restype = C.c_int64
+        L.ref_time_collect.restype = C.c_double
+        self._view = path is None
+        if path is not None:
+            self.h = C.c_void_p(L.ref_bwt_load(path.encode()))
+        else:
+            self.words = np.ascontiguousarray(index.words_numpy(), np.uint32)
+            self.h = C.c_void_p(L.ref_bwt_view(C.c_uint64(int(index.primary)), (C.c_uint64 * 5)(*[int(v) for v in index.L2]),
+                                               C.c_uint64(int(index.seq_len)), C.c_uint64(int(index.bwt_size)),
+                                               C.c_void_p(self.words.ctypes.data)))
+
+    def __del__(self):
+        try:
+            (self.lib.ref_bwt_free_view if self._view else self.lib.ref_bwt_free)(self.h)
+        except Exception:
+            pass
+
+    def collect(self, seq, offs, opt=None, nthreads=1):
+        return self._collect(self.lib.ref_collect, self.h, seq, offs, opt or SeedOpt(), C.c_int(nthreads))
+
+    def smem1(self, seq, offs, x, min_intv):
+        return self._smem1(self.lib.ref_smem1, self.h, seq, offs, x, min_intv)
+
+    def time_collect(self, seq, offs, opt=None, nthreads=1):
+        return self._time(self.lib.ref_time_collect, self.h, seq, offs, opt or SeedOpt(), C.c_int(nthreads))
+
+    def occ4(self, k: int):
+        cnt = (C.c_uint64 * 4)()
+        self.lib.ref_occ4(self.h, C.c_uint64(k & 0xFFFFFFFFFFFFFFFF), cnt)
+        return [int(v) for v in cnt]
+
+    def extend(self, ik3, is_back: int):
+        ok = (C.c_uint64 * 12)()
+        self.lib.ref_extend(self.h, (C.c_uint64 * 3)(*[int(v) for v in ik3]), C.c_int(is_back), ok)
+        return np.array(list(ok), dtype=np.uint64).reshape(4, 3)

@@ -1,0 +1,377 @@
+/* TEST INFRASTRUCTURE ONLY -- see smem_oracle.h.  Parity status: PINNED against oracle/_ref.
+ *
+ * A from-scratch CPU restatement of BWA-MEM 0.7.8's SMEM seeding as found in the reference:
+ *   orc_occ4     <- bwt_occ4        bwt.c:187-204   (popcount on bit planes instead of the LUT)
+ *   extend       <- bwt_extend      bwt.c:416-429   (bwt_2occ4 = two occ4, bwt.c:213-214)
+ *   smem1        <- bwt_smem1       bwt.c:776-835
+ *   next2        <- smem_next2      bwamem.c:244-305 (0.7.8 re-seed + ordered merge)
+ *   collect_read <- mem_insert_seed bwamem.c:453-460 (enumeration loop only)
+ */
+#include "smem_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <time.h>
+
+typedef struct { uint64_t x0, x1, x2, info; } iv_t;
+typedef struct { iv_t *a; int n, m; } ivv_t;
+
+static void ivv_push(ivv_t *v, iv_t e)
+{
+	if (v->n == v->m) { v->m = v->m ? v->m * 2 : 16; v->a = (iv_t *)realloc(v->a, sizeof(iv_t) * (size_t)v->m); }
+	v->a[v->n++] = e;
+}
+static void ivv_reverse(ivv_t *v)
+{
+	int i, j;
+	for (i = 0, j = v->n - 1; i < j; ++i, --j) { iv_t t = v->a[i]; v->a[i] = v->a[j]; v->a[j] = t; }
+}
+
+/* Occurrences of A,C,G,T in BWT[0..k] (inclusive); k counts the '$' row, hence the primary shift
+ * (bwt.c:194).  Block = 16 words per 128 symbols: 4 x uint64 counts, then 8 words of 16 symbols,
+ * first symbol in bits 31:30 (bwtindex.c:101,137-143). */
+void orc_occ4(const orc_index_t *ix, uint64_t k, uint64_t cnt[4])
+{
+	const uint32_t *blk;
+	uint64_t base[4];
+	unsigned rem, w;
+	uint32_t c1 = 0, c2 = 0, c3 = 0;
+	if (k == (uint64_t)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; return; }
+	k -= (k >= ix->primary);
+	blk = ix->bwt + ((k >> 7) << 4);
+	memcpy(base, blk, 32);
+	rem = (unsigned)(k & 127) + 1; /* symbols of this block to count */
+	for (w = 0; rem > 0; ++w) {
+		unsigned take = rem < 16 ? rem : 16;
+		uint32_t v = blk[8 + w];
+		uint32_t keep = take == 16 ? 0x55555555u : (0x55555555u & ~((1u << (2 * (16 - take))) - 1));
+		uint32_t hi = (v >> 1) & keep, lo = v & keep;
+		c3 += (uint32_t)__builtin_popcount(hi & lo);
+		c2 += (uint32_t)__builtin_popcount(hi & ~lo);
+		c1 += (uint32_t)__builtin_popcount(~hi & lo);
+		rem -= take;
+	}
+	cnt[1] = base[1] + c1; cnt[2] = base[2] + c2; cnt[3] = base[3] + c3;
+	cnt[0] = base[0] + ((unsigned)(k & 127) + 1 - c1 - c2 - c3);
+}
+
+static inline void extend(const orc_index_t *ix, const iv_t *ik, int is_back, iv_t ok[4], orc_stats_t *st)
+{
+	uint64_t tk[4], tl[4], a = is_back ? ik->x0 : ik->x1, b = is_back ? ik->x1 : ik->x0; /* a = x[!is_back] */
+	uint64_t k = a - 1, l = a - 1 + ik->x2, acc;
+	int c;
+	orc_occ4(ix, k, tk);
+	orc_occ4(ix, l, tl);
+	if (st) {
+		uint64_t kk = k - (k >= ix->primary), ll = l - (l >= ix->primary);
+		st->extends++;
+		st->blocks += (kk >> 7) == (ll >> 7) ? 1 : 2;
+	}
+	/* the other strand's start: bases are laid out T,G,C,A after the (possible) '$' (bwt.c:425-428) */
+	acc = b + (a <= ix->primary && a + ik->x2 - 1 >= ix->primary);
+	for (c = 3; c >= 0; --c) {
+		uint64_t na = ix->L2[c] + 1 + tk[c], sz = tl[c] - tk[c];
+		ok[c].x2 = sz;
+		if (is_back) { ok[c].x0 = na; ok[c].x1 = acc; } else { ok[c].x1 = na; ok[c].x0 = acc; }
+		acc += sz;
+	}
+}
+
+typedef struct { ivv_t prev, curr, mem, sub, merged; } scratch_t;
+
+/* bwt_smem1, bwt.c:776-835.  Writes the SMEM candidates through x into `mem`, returns ret. */
+static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int min_intv, ivv_t *mem,
+                 ivv_t *prev, ivv_t *curr, orc_stats_t *st)
+{
+	iv_t ik, ok[4];
+	int i, j, ret;
+	ivv_t *t;
+	mem->n = 0;
+	if (q[x] > 3) return x + 1;
+	if (min_intv < 1) min_intv = 1;
+	if (st) st->smem1_calls++;
+	ik.x0 = ix->L2[q[x]] + 1; ik.x1 = ix->L2[3 - q[x]] + 1; ik.x2 = ix->L2[q[x] + 1] - ix->L2[q[x]];
+	ik.info = (uint64_t)(x + 1);
+	curr->n = 0;
+	for (i = x + 1; i < len; ++i) { /* forward: extend with the complement on the reverse strand */
+		int c;
+		if (q[i] > 3) { ivv_push(curr, ik); break; }
+		c = 3 - q[i];
+		extend(ix, &ik, 0, ok, st);
+		if (ok[c].x2 != ik.x2) {
+			ivv_push(curr, ik);
+			if (ok[c].x2 < (uint64_t)min_intv) break;
+		}
+		ik = ok[c]; ik.info = (uint64_t)(i + 1);
+	}
+	if (i == len) ivv_push(curr, ik);
+	ivv_reverse(curr); /* longest match first */
+	ret = (int)curr->a[0].info;
+	if (st && (uint64_t)curr->n > st->max_curr) st->max_curr = (uint64_t)curr->n;
+	t = prev; prev = curr; curr = t;
+	for (i = x - 1; i >= -1; --i) { /* backward */
+		int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
+		curr->n = 0;
+		for (j = 0; j < prev->n; ++j) {
+			iv_t *p = &prev->a[j];
+			extend(ix, p, 1, ok, st);
+			if (c < 0 || ok[c].x2 < (uint64_t)min_intv) {
+				if (curr->n == 0 && (mem->n == 0 || (uint64_t)(i + 1) < (mem->a[mem->n - 1].info >> 32))) {
+					iv_t e = *p;
+					e.info |= (uint64_t)(i + 1) << 32;
+					ivv_push(mem, e);
+				}
+			} else if (curr->n == 0 || ok[c].x2 != curr->a[curr->n - 1].x2) {
+				ok[c].info = p->info;
+				ivv_push(curr, ok[c]);
+			}
+		}
+		if (curr->n == 0) break;
+		t = prev; prev = curr; curr = t;
+	}
+	ivv_reverse(mem); /* ascending start */
+	if (st && (uint64_t)mem->n > st->max_mem) st->max_mem = (uint64_t)mem->n;
+	return ret;
+}
+
+static inline int iv_len(const iv_t *p) { return (int)((uint32_t)p->info - (uint32_t)(p->info >> 32)); }
+
+/* smem_next2, bwamem.c:244-305.  Returns 0 when exhausted, else 1 with the step's list in s->mem. */
+static int next2(const orc_index_t *ix, int len, const uint8_t *q, int *start, int split_len, int split_width,
+                 int start_width, scratch_t *s, orc_stats_t *st)
+{
+	int i, max = 0, max_i = 0, ori_start;
+	s->mem.n = s->sub.n = 0;
+	if (*start >= len || *start < 0) return 0;
+	while (*start < len && q[*start] > 3) ++*start;
+	if (*start == len) return 0;
+	ori_start = *start;
+	*start = smem1(ix, len, q, ori_start, start_width, &s->mem, &s->prev, &s->curr, st);
+	if (s->mem.n == 0) return 1;
+	for (i = 0; i < s->mem.n; ++i) { /* first maximum wins (bwamem.c:266-270) */
+		int l = iv_len(&s->mem.a[i]);
+		if (max < l) { max = l; max_i = i; }
+	}
+	if (split_len > 0 && max >= split_len && s->mem.a[max_i].x2 <= (uint64_t)split_width) {
+		const iv_t *p = &s->mem.a[max_i];
+		int j, mid = (int)(((uint32_t)p->info + (uint32_t)(p->info >> 32)) >> 1);
+		ivv_t *a = &s->merged;
+		smem1(ix, len, q, mid, (int)(p->x2 + 1), &s->sub, &s->prev, &s->curr, st);
+		a->n = 0;
+		i = j = 0;
+#define KEY(e) ((int64_t)(((e).info >> 32 << 32) | (uint32_t)(len - (int)(uint32_t)(e).info)))
+#define KEEP(e) (iv_len(&(e)) >= (max >> 1) && (int)(uint32_t)(e).info > ori_start)
+		while (i < s->mem.n && j < s->sub.n) {
+			if (KEY(s->mem.a[i]) < KEY(s->sub.a[j])) ivv_push(a, s->mem.a[i++]);
+			else { if (KEEP(s->sub.a[j])) ivv_push(a, s->sub.a[j]); ++j; }
+		}
+		for (; i < s->mem.n; ++i) ivv_push(a, s->mem.a[i]);
+		for (; j < s->sub.n; ++j) if (KEEP(s->sub.a[j])) ivv_push(a, s->sub.a[j]);
+#undef KEY
+#undef KEEP
+		s->mem.n = 0;
+		for (i = 0; i < a->n; ++i) ivv_push(&s->mem, a->a[i]);
+	}
+	return 1;
+}
+
+typedef void (*emit_fn)(void *ctx, const iv_t *e, int step);
+
+static void collect_read(const orc_index_t *ix, int len, const uint8_t *q, const orc_seed_opt_t *o, scratch_t *s,
+                         orc_stats_t *st, emit_fn emit, void *ctx, int32_t *n_steps, int32_t *last_start)
+{
+	int split_len = (int)(o->min_seed_len * o->split_factor + .499), start = 0, step = 0, i;
+	if (split_len > len) split_len = len;
+	while (next2(ix, len, q, &start, split_len, o->split_width, o->start_width, s, st)) {
+		for (i = 0; i < s->mem.n; ++i) emit(ctx, &s->mem.a[i], step);
+		if (st) { st->steps++; st->intervals += (uint64_t)s->mem.n; }
+		++step;
+	}
+	if (n_steps) *n_steps = step;
+	if (last_start) *last_start = start;
+}
+
+static void scratch_free(scratch_t *s) { free(s->prev.a); free(s->curr.a); free(s->mem.a); free(s->sub.a); free(s->merged.a); }
+
+/* ------------------------------------------------------------------ flat APIs */
+void orc_extend(const orc_index_t *ix, const uint64_t ik3[3], int is_back, uint64_t ok12[12])
+{
+	iv_t ik, ok[4];
+	int c;
+	ik.x0 = ik3[0]; ik.x1 = ik3[1]; ik.x2 = ik3[2]; ik.info = 0;
+	extend(ix, &ik, is_back, ok, 0);
+	for (c = 0; c < 4; ++c) { ok12[3*c] = ok[c].x0; ok12[3*c+1] = ok[c].x1; ok12[3*c+2] = ok[c].x2; }
+}
+
+int64_t orc_smem1(const orc_index_t *ix, int64_t n, const uint8_t *seq, const int64_t *offs, const int32_t *x,
+                  const int32_t *min_intv, uint64_t *intv, int64_t cap, int64_t *read_off, int32_t *ret)
+{
+	scratch_t s;
+	int64_t i, total = 0;
+	int k;
+	memset(&s, 0, sizeof(s));
+	read_off[0] = 0;
+	for (i = 0; i < n; ++i) {
+		ret[i] = smem1(ix, (int)(offs[i+1] - offs[i]), seq + offs[i], x[i], min_intv[i], &s.mem, &s.prev, &s.curr, 0);
+		for (k = 0; k < s.mem.n; ++k, ++total)
+			if (total < cap) memcpy(intv + 4 * total, &s.mem.a[k], 32);
+		read_off[i+1] = total;
+	}
+	scratch_free(&s);
+	return total;
+}
+
+typedef struct { uint64_t *v; uint16_t *step; int64_t n, m; } flat_t;
+static void flat_emit(void *ctx, const iv_t *e, int step)
+{
+	flat_t *f = (flat_t *)ctx;
+	if (f->n == f->m) {
+		f->m = f->m ? f->m * 2 : 1024;
+		f->v = (uint64_t *)realloc(f->v, (size_t)f->m * 32);
+		f->step = (uint16_t *)realloc(f->step, (size_t)f->m * 2);
+	}
+	memcpy(f->v + 4 * f->n, e, 32);
+	f->step[f->n++] = (uint16_t)step;
+}
+
+typedef struct {
+	const orc_index_t *ix; const uint8_t *seq; const int64_t *offs; orc_seed_opt_t opt;
+	int64_t lo, hi; flat_t out; int64_t *cnt; int32_t *n_steps, *last_start; orc_stats_t st; int want_stats;
+} job_t;
+
+static void *collect_worker(void *data)
+{
+	job_t *j = (job_t *)data;
+	scratch_t s;
+	int64_t i;
+	memset(&s, 0, sizeof(s));
+	for (i = j->lo; i < j->hi; ++i) {
+		int64_t n0 = j->out.n;
+		collect_read(j->ix, (int)(j->offs[i+1] - j->offs[i]), j->seq + j->offs[i], &j->opt, &s, j->want_stats ? &j->st : 0,
+		             flat_emit, &j->out, j->n_steps ? &j->n_steps[i] : 0, j->last_start ? &j->last_start[i] : 0);
+		j->cnt[i - j->lo] = j->out.n - n0;
+	}
+	scratch_free(&s);
+	return 0;
+}
+
+int64_t orc_collect(const orc_index_t *ix, int64_t n, const uint8_t *seq, const int64_t *offs, const orc_seed_opt_t *opt,
+                    int nthreads, uint64_t *intv, int64_t cap, int64_t *read_off, uint16_t *step,
+                    int32_t *n_steps, int32_t *last_start, orc_stats_t *stats)
+{
+	job_t *jobs;
+	pthread_t *tid;
+	int t;
+	int64_t total = 0, i, per, pos = 0;
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > n) nthreads = n > 0 ? (int)n : 1;
+	jobs = (job_t *)calloc((size_t)nthreads, sizeof(job_t));
+	tid = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+	per = (n + nthreads - 1) / nthreads;
+	for (t = 0; t < nthreads; ++t) {
+		job_t *j = &jobs[t];
+		j->ix = ix; j->seq = seq; j->offs = offs; j->opt = *opt; j->want_stats = stats != 0;
+		j->lo = t * per < n ? t * per : n; j->hi = (t + 1) * per < n ? (t + 1) * per : n;
+		j->cnt = (int64_t *)calloc((size_t)(j->hi - j->lo + 1), sizeof(int64_t));
+		j->n_steps = n_steps; j->last_start = last_start;
+		pthread_create(&tid[t], 0, collect_worker, j);
+	}
+	for (t = 0; t < nthreads; ++t) pthread_join(tid[t], 0);
+	read_off[0] = 0;
+	if (stats) memset(stats, 0, sizeof(*stats));
+	for (t = 0; t < nthreads; ++t) {
+		for (i = jobs[t].lo; i < jobs[t].hi; ++i) { total += jobs[t].cnt[i - jobs[t].lo]; read_off[i+1] = total; }
+		if (stats) {
+			stats->extends += jobs[t].st.extends; stats->blocks += jobs[t].st.blocks;
+			stats->smem1_calls += jobs[t].st.smem1_calls; stats->steps += jobs[t].st.steps;
+			stats->intervals += jobs[t].st.intervals;
+			if (jobs[t].st.max_curr > stats->max_curr) stats->max_curr = jobs[t].st.max_curr;
+			if (jobs[t].st.max_mem > stats->max_mem) stats->max_mem = jobs[t].st.max_mem;
+		}
+	}
+	if (total <= cap)
+		for (t = 0; t < nthreads; ++t) {
+			if (jobs[t].out.n) {
+				memcpy(intv + 4 * pos, jobs[t].out.v, (size_t)jobs[t].out.n * 32);
+				if (step) memcpy(step + pos, jobs[t].out.step, (size_t)jobs[t].out.n * 2);
+			}
+			pos += jobs[t].out.n;
+		}
+	for (t = 0; t < nthreads; ++t) { free(jobs[t].out.v); free(jobs[t].out.step); free(jobs[t].cnt); }
+	free(jobs); free(tid);
+	return total;
+}
+
+/* ------------------------------------------------------------------ checksum + timing arm */
+#define FNV_BASIS 0xcbf29ce484222325ull
+#define FNV_PRIME 0x100000001b3ull
+
+uint64_t orc_checksum(int64_t n, const uint64_t *intv, const int64_t *read_off)
+{
+	uint64_t sum = 0;
+	int64_t i, k;
+	for (i = 0; i < n; ++i) {
+		uint64_t h = FNV_BASIS ^ (uint64_t)i;
+		for (k = 4 * read_off[i]; k < 4 * read_off[i+1]; ++k) h = (h ^ intv[k]) * FNV_PRIME;
+		sum += h;
+	}
+	return sum;
+}
+
+typedef struct { uint64_t h; int64_t n; } hash_ctx_t;
+static void hash_emit(void *ctx, const iv_t *e, int step)
+{
+	hash_ctx_t *c = (hash_ctx_t *)ctx;
+	(void)step;
+	c->h = (c->h ^ e->x0) * FNV_PRIME; c->h = (c->h ^ e->x1) * FNV_PRIME;
+	c->h = (c->h ^ e->x2) * FNV_PRIME; c->h = (c->h ^ e->info) * FNV_PRIME;
+	c->n++;
+}
+
+typedef struct {
+	const orc_index_t *ix; const uint8_t *seq; const int64_t *offs; orc_seed_opt_t opt;
+	int64_t n; volatile int64_t *next; uint64_t sum; int64_t cnt;
+} tjob_t;
+
+static void *time_worker(void *data)
+{
+	tjob_t *j = (tjob_t *)data;
+	scratch_t s;
+	memset(&s, 0, sizeof(s));
+	for (;;) { /* dynamic chunks of 256 reads, like kt_for's stealing (kthread.c:17-38) */
+		int64_t lo = __sync_fetch_and_add(j->next, 256), hi = lo + 256 < j->n ? lo + 256 : j->n, i;
+		if (lo >= j->n) break;
+		for (i = lo; i < hi; ++i) {
+			hash_ctx_t c;
+			c.h = FNV_BASIS ^ (uint64_t)i; c.n = 0;
+			collect_read(j->ix, (int)(j->offs[i+1] - j->offs[i]), j->seq + j->offs[i], &j->opt, &s, 0, hash_emit, &c, 0, 0);
+			j->sum += c.h; j->cnt += c.n;
+		}
+	}
+	scratch_free(&s);
+	return 0;
+}
+
+double orc_time_collect(const orc_index_t *ix, int64_t n, const uint8_t *seq, const int64_t *offs,
+                        const orc_seed_opt_t *opt, int nthreads, uint64_t *checksum, int64_t *n_intervals)
+{
+	tjob_t *jobs;
+	pthread_t *tid;
+	volatile int64_t next = 0;
+	struct timespec t0, t1;
+	int t;
+	if (nthreads < 1) nthreads = 1;
+	jobs = (tjob_t *)calloc((size_t)nthreads, sizeof(tjob_t));
+	tid = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (t = 0; t < nthreads; ++t) {
+		jobs[t].ix = ix; jobs[t].seq = seq; jobs[t].offs = offs; jobs[t].opt = *opt; jobs[t].n = n; jobs[t].next = &next;
+		pthread_create(&tid[t], 0, time_worker, &jobs[t]);
+	}
+	for (t = 0; t < nthreads; ++t) pthread_join(tid[t], 0);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	*checksum = 0; *n_intervals = 0;
+	for (t = 0; t < nthreads; ++t) { *checksum += jobs[t].sum; *n_intervals += jobs[t].cnt; }
+	free(jobs); free(tid);
+	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
