@@ -1,0 +1,590 @@
+// smem_gpu.cu -- host side of the C ABI declared in include/smem_gpu.h.
+//
+// Replaces, for the SMEM path only, the reference's accelerator plumbing:
+//   HelloALINLB.cpp:309-451 (service + workspace allocation, CSR programming)  -> smem_gpu_create
+//   bwa.c:289-301           (index memcpy into the workspace + handshake 2)    -> smem_gpu_upload_index
+//   bwt.c:559-749 + fastmap.c:335-420 (pack, handshake, manager copy, unpack)  -> stage / run / fetch
+// No CPU fallback exists here: every failure is an error code.
+#include "../../include/smem_gpu.h"
+#include "smem_kernels.cuh"
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct CastI2L { __host__ __device__ long long operator()(const int &v) const { return (long long)v; } };
+typedef thrust::transform_iterator<CastI2L, const int *, long long> CountIter;
+
+struct DeviceCtx {
+	int dev = 0, sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+	// index
+	uint4 *d_index = nullptr;
+	size_t index_bytes = 0;
+	DevIndex ix{};
+	bool has_index = false;
+	// batch buffers (capacity fixed at create)
+	int64_t read_cap = 0;
+	size_t seq_cap = 0;
+	uint8_t *d_seq = nullptr;
+	long long *d_offs = nullptr;
+	int *d_x = nullptr, *d_mi = nullptr, *d_ret = nullptr;
+	int *d_counts = nullptr, *d_overflow = nullptr, *d_status = nullptr;
+	long long *d_off = nullptr;
+	Intv *d_slots = nullptr;
+	int slots_cap_alloc = 0;
+	Intv *d_scratch = nullptr;
+	size_t scratch_entries = 0;
+	Intv *d_out = nullptr;
+	unsigned short *d_step = nullptr;
+	size_t out_cap = 0;
+	void *d_tmp = nullptr;
+	size_t tmp_bytes = 0;
+	Intv *d_big = nullptr;
+	size_t big_entries = 0;
+	int *d_counts_k = nullptr;
+	size_t counts_k_cap = 0;
+	int *h_status = nullptr;          // pinned: [0..3] status, then 2 x int64 total
+	// current shard
+	int64_t lo = 0, hi = 0, n = 0;
+	long long seq_base = 0;
+	long long total = 0;
+	int mode = MODE_COLLECT;
+	// last-run measurements
+	float seed_ms = 0, total_ms = 0;
+	int64_t launches = 0, overflow = 0;
+	std::string err;
+	int rc = 0;
+};
+
+} // namespace
+
+struct smem_gpu {
+	std::vector<DeviceCtx> devs;
+	int64_t max_batch = 0;
+	int max_len = 0;
+	int64_t staged = -1;
+	bool ran = false;
+	int block_threads = SEED_BLOCK, blocks_per_sm = 4, slot_cap = 32;
+	int64_t hot_min_intv = 0;
+	int64_t h2d_bytes = 0, d2h_bytes = 0;
+	std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                          \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) {                                                                          \
+			char b_[512];                                                                                 \
+			snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+			d.err = b_;                                                                                   \
+			return e_ == cudaErrorMemoryAllocation ? SMEM_GPU_E_NOMEM : SMEM_GPU_E_CUDA;                 \
+		}                                                                                                 \
+	} while (0)
+
+template <typename T> int dev_alloc(DeviceCtx &d, T **p, size_t count)
+{
+	CK(cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)));
+	return 0;
+}
+
+int ctx_init(DeviceCtx &d, int dev, int64_t read_cap, int max_len, int slot_cap)
+{
+	d.dev = dev;
+	CK(cudaSetDevice(dev));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, dev));
+	d.sm_count = prop.multiProcessorCount;
+	CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&d.ev0)); CK(cudaEventCreate(&d.ev1)); CK(cudaEventCreate(&d.ev2));
+	d.read_cap = read_cap;
+	d.seq_cap = (size_t)read_cap * (size_t)max_len + 64;
+	int rc;
+	if ((rc = dev_alloc(d, &d.d_seq, d.seq_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_offs, (size_t)read_cap + 1))) return rc;
+	if ((rc = dev_alloc(d, &d.d_x, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_mi, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_ret, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_counts, (size_t)read_cap + 1))) return rc;
+	if ((rc = dev_alloc(d, &d.d_overflow, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_status, 8))) return rc;
+	if ((rc = dev_alloc(d, &d.d_off, (size_t)read_cap + 1))) return rc;
+	if ((rc = dev_alloc(d, &d.d_slots, (size_t)read_cap * slot_cap))) return rc;
+	d.slots_cap_alloc = slot_cap;
+	d.out_cap = (size_t)read_cap * 16 + 1024;
+	if ((rc = dev_alloc(d, &d.d_out, d.out_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_step, d.out_cap))) return rc;
+	CK(cudaMallocHost((void **)&d.h_status, 64));
+	// CUB temp storage for the counts -> offsets scan
+	CountIter it((const int *)d.d_counts, CastI2L());
+	size_t tb = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, d.d_off, (int)std::min<int64_t>(read_cap + 1, 0x7fffffff), d.stream));
+	d.tmp_bytes = tb + 256;
+	CK(cudaMalloc(&d.d_tmp, d.tmp_bytes));
+	return 0;
+}
+
+void ctx_free(DeviceCtx &d)
+{
+	cudaSetDevice(d.dev);
+	cudaFree(d.d_index); cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
+	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
+	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
+	if (d.h_status) cudaFreeHost(d.h_status);
+	if (d.ev0) cudaEventDestroy(d.ev0);
+	if (d.ev1) cudaEventDestroy(d.ev1);
+	if (d.ev2) cudaEventDestroy(d.ev2);
+	if (d.stream) cudaStreamDestroy(d.stream);
+}
+
+// The copy in HBM is padded to whole 64-byte blocks plus one spare block so that the two
+// 32-byte sector loads of the last (truncated, bwtindex.c:145-147) block never leave the allocation.
+int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
+{
+	CK(cudaSetDevice(d.dev));
+	const size_t bytes = (size_t)ix->bwt_size * 4;
+	const size_t padded = ((bytes + 63) / 64 + 1) * 64;
+	if (d.d_index) { CK(cudaFree(d.d_index)); d.d_index = nullptr; }
+	CK(cudaMalloc((void **)&d.d_index, padded));
+	CK(cudaMemsetAsync((char *)d.d_index + (padded - 128), 0, 128, d.stream));
+	if (src_device < 0) CK(cudaMemcpyAsync(d.d_index, ix->bwt, bytes, cudaMemcpyHostToDevice, d.stream));
+	else if (src_device == d.dev) CK(cudaMemcpyAsync(d.d_index, ix->bwt, bytes, cudaMemcpyDeviceToDevice, d.stream));
+	else CK(cudaMemcpyPeerAsync(d.d_index, d.dev, ix->bwt, src_device, bytes, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	d.index_bytes = bytes;
+	d.ix.blk = d.d_index;
+	d.ix.primary = ix->primary;
+	for (int i = 0; i < 5; ++i) d.ix.L2[i] = ix->L2[i];
+	d.ix.seq_len = ix->seq_len;
+	d.has_index = true;
+	return 0;
+}
+
+int ctx_stage(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
+{
+	CK(cudaSetDevice(d.dev));
+	d.n = d.hi - d.lo;
+	d.total = 0;
+	if (d.n == 0) return 0;
+	d.seq_base = offs[d.lo];
+	const size_t nbytes = (size_t)(offs[d.hi] - offs[d.lo]);
+	if (nbytes > d.seq_cap || d.n > d.read_cap) { d.err = "batch exceeds the capacity given to smem_gpu_create"; return SMEM_GPU_E_CAPACITY; }
+	if (nbytes) CK(cudaMemcpyAsync(d.d_seq, seq + d.seq_base, nbytes, cudaMemcpyHostToDevice, d.stream));
+	CK(cudaMemcpyAsync(d.d_offs, offs + d.lo, (size_t)(d.n + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+	if (x) {
+		CK(cudaMemcpyAsync(d.d_x, x + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
+		CK(cudaMemcpyAsync(d.d_mi, mi + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
+	}
+	CK(cudaStreamSynchronize(d.stream));
+	return 0;
+}
+
+template <int MODE>
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid)
+{
+	switch (blocks_per_sm) {
+	case 4: seed_kernel<MODE, 4><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	case 5: seed_kernel<MODE, 5><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	case 6: seed_kernel<MODE, 6><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	case 8: seed_kernel<MODE, 8><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	case 10: seed_kernel<MODE, 10><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	case 12: seed_kernel<MODE, 12><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	default: seed_kernel<MODE, 3><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	}
+	CK(cudaGetLastError());
+	++d.launches;
+	return 0;
+}
+
+int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *opt)
+{
+	CK(cudaSetDevice(d.dev));
+	d.mode = mode; d.launches = 0; d.overflow = 0; d.seed_ms = d.total_ms = 0; d.total = 0;
+	if (d.n == 0) return 0;
+	if (!d.has_index) { d.err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
+	const int bps = h.blocks_per_sm;
+	const int max_grid = d.sm_count * bps;
+	const int grid = (int)std::min<int64_t>(max_grid, (d.n + SEED_BLOCK - 1) / SEED_BLOCK);
+	const int scratch_cap = h.max_len + 2;
+	const size_t need = (size_t)max_grid * SEED_BLOCK * 4 * scratch_cap;
+	if (need > d.scratch_entries) {
+		if (d.d_scratch) CK(cudaFree(d.d_scratch));
+		d.d_scratch = nullptr; d.scratch_entries = 0;
+		CK(cudaMalloc((void **)&d.d_scratch, need * sizeof(Intv)));
+		d.scratch_entries = need;
+	}
+	if (h.slot_cap > d.slots_cap_alloc) {
+		CK(cudaFree(d.d_slots)); d.d_slots = nullptr;
+		CK(cudaMalloc((void **)&d.d_slots, (size_t)d.read_cap * h.slot_cap * sizeof(Intv)));
+		d.slots_cap_alloc = h.slot_cap;
+	}
+	SeedParams p{};
+	p.ix = d.ix;
+	p.seq = d.d_seq - d.seq_base;
+	p.offs = d.d_offs;
+	p.n = d.n;
+	p.list = nullptr;
+	p.xs = d.d_x; p.min_intvs = d.d_mi; p.ret = d.d_ret;
+	p.slots = d.d_slots; p.slot_cap = h.slot_cap;
+	p.counts = d.d_counts; p.overflow_list = d.d_overflow; p.status = d.d_status;
+	p.scratch = d.d_scratch; p.scratch_cap = scratch_cap;
+	if (opt) {
+		p.split_len_init = (int)(opt->min_seed_len * opt->split_factor + .499);   // bwamem.c:456, the path's only FP
+		p.split_width = opt->split_width; p.start_width = opt->start_width;
+	}
+	p.hot_min_intv = (u64)h.hot_min_intv;
+
+	CK(cudaEventRecord(d.ev0, d.stream));
+	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
+	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid) : launch_seed<MODE_SMEM1>(d, p, bps, grid);
+	if (rc) return rc;
+	CK(cudaEventRecord(d.ev1, d.stream));
+	CountIter it((const int *)d.d_counts, CastI2L());
+	size_t tb = d.tmp_bytes;
+	CK(cub::DeviceScan::ExclusiveSum(d.d_tmp, tb, it, d.d_off, (int)(d.n + 1), d.stream));
+	d.launches += 1;
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status + 4, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
+	memcpy(&d.total, d.h_status + 4, 8);
+	const int n_over = d.h_status[1];
+	d.overflow = n_over;
+	if ((size_t)d.total > d.out_cap) {
+		CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); d.d_out = nullptr; d.d_step = nullptr;
+		d.out_cap = (size_t)d.total + (size_t)d.total / 8 + 1024;
+		CK(cudaMalloc((void **)&d.d_out, d.out_cap * sizeof(Intv)));
+		CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
+	}
+	{
+		const long long threads = (long long)d.n * h.slot_cap;
+		compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
+		                                                                        d.d_out, d.d_step);
+		CK(cudaGetLastError());
+		++d.launches;
+	}
+	if (n_over > 0) {
+		// Reads whose interval list outgrew their slot are seeded again into slots of the worst-case
+		// size a read of max_len bases can produce per the counts just measured.
+		std::vector<int> list(n_over), cnt(n_over);
+		CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
+		CK(cudaStreamSynchronize(d.stream));
+		std::sort(list.begin(), list.end());
+		int big_cap = 0;
+		for (int k = 0; k < n_over; ++k) {
+			CK(cudaMemcpyAsync(&cnt[k], d.d_counts + list[k], 4, cudaMemcpyDeviceToHost, d.stream));
+		}
+		CK(cudaStreamSynchronize(d.stream));
+		for (int k = 0; k < n_over; ++k) big_cap = std::max(big_cap, cnt[k]);
+		const size_t need_big = (size_t)n_over * big_cap;
+		if (need_big > d.big_entries) {
+			if (d.d_big) CK(cudaFree(d.d_big));
+			d.d_big = nullptr; d.big_entries = 0;
+			CK(cudaMalloc((void **)&d.d_big, need_big * sizeof(Intv)));
+			d.big_entries = need_big;
+		}
+		if ((size_t)n_over > d.counts_k_cap) {
+			if (d.d_counts_k) CK(cudaFree(d.d_counts_k));
+			d.d_counts_k = nullptr; d.counts_k_cap = 0;
+			CK(cudaMalloc((void **)&d.d_counts_k, (size_t)n_over * 4));
+			d.counts_k_cap = n_over;
+		}
+		CK(cudaMemcpyAsync(d.d_overflow, list.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, d.stream));
+		CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+		SeedParams p2 = p;
+		p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
+		p2.overflow_list = d.d_overflow + n_over;   // unused: big_cap is exact
+		const int grid2 = (int)std::min<int64_t>(max_grid, (n_over + SEED_BLOCK - 1) / SEED_BLOCK);
+		rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2);
+		if (rc) return rc;
+		const long long threads = (long long)n_over * big_cap;
+		compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
+		                                                                             d.d_off, d.d_out, d.d_step);
+		CK(cudaGetLastError());
+		++d.launches;
+		CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+		CK(cudaStreamSynchronize(d.stream));
+		if (d.h_status[2] != 0) { d.err = "device guard tripped in the overflow re-run"; return SMEM_GPU_E_INTERNAL; }
+	}
+	CK(cudaEventRecord(d.ev2, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	CK(cudaEventElapsedTime(&d.seed_ms, d.ev0, d.ev1));
+	CK(cudaEventElapsedTime(&d.total_ms, d.ev0, d.ev2));
+	return 0;
+}
+
+int ctx_fetch(DeviceCtx &d, smem_intv_t *intv_out, int64_t *read_off, uint16_t *step_out, int32_t *ret, long long base)
+{
+	CK(cudaSetDevice(d.dev));
+	if (d.n == 0) return 0;
+	CK(cudaMemcpyAsync(read_off + d.lo, d.d_off, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));   // read_off[n] is set by the caller
+	if (intv_out && d.total) CK(cudaMemcpyAsync(intv_out + base, d.d_out, (size_t)d.total * sizeof(Intv), cudaMemcpyDeviceToHost, d.stream));
+	if (step_out && d.total) CK(cudaMemcpyAsync(step_out + base, d.d_step, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream));
+	if (ret) CK(cudaMemcpyAsync(ret + d.lo, d.d_ret, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	if (base) for (int64_t i = d.lo; i < d.hi; ++i) read_off[i] += base;
+	return 0;
+}
+
+template <typename F> int for_each_device(smem_gpu *h, F f)
+{
+	if (h->devs.size() == 1) { h->devs[0].rc = f(h->devs[0]); }
+	else {
+		std::vector<std::thread> th;
+		for (auto &d : h->devs) th.emplace_back([&d, &f]() { d.rc = f(d); });
+		for (auto &t : th) t.join();
+	}
+	for (auto &d : h->devs) if (d.rc) { h->err = "device " + std::to_string(d.dev) + ": " + d.err; return d.rc; }
+	return 0;
+}
+
+void shard(smem_gpu *h, int64_t n)
+{
+	const int g = (int)h->devs.size();
+	const int64_t per = (n + g - 1) / g;
+	for (int k = 0; k < g; ++k) {
+		h->devs[k].lo = std::min<int64_t>(n, k * per);
+		h->devs[k].hi = std::min<int64_t>(n, (k + 1) * per);
+	}
+}
+
+int do_stage(smem_gpu *h, int64_t n, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
+{
+	if (!h || n < 0 || (n > 0 && (!seq || !offs))) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
+	if (n > h->max_batch) { h->err = "batch larger than max_batch_reads"; return SMEM_GPU_E_CAPACITY; }
+	shard(h, n);
+	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_stage(d, seq, offs, x, mi); });
+	if (rc) return rc;
+	h->staged = n; h->ran = false;
+	h->h2d_bytes = n ? (offs[n] - offs[0]) + (n + (int64_t)h->devs.size()) * 8 + (x ? n * 8 : 0) : 0;
+	return 0;
+}
+
+int do_run(smem_gpu *h, int mode, const smem_seed_opt_t *opt, int64_t *total_out)
+{
+	if (h->staged < 0) { h->err = "nothing staged"; return SMEM_GPU_E_ARG; }
+	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_run(d, *h, mode, opt); });
+	if (rc) return rc;
+	int64_t tot = 0;
+	for (auto &d : h->devs) tot += d.total;
+	if (total_out) *total_out = tot;
+	h->ran = true;
+	return 0;
+}
+
+int do_fetch(smem_gpu *h, smem_intv_t *intv_out, int64_t cap, int64_t *read_off, uint16_t *step_out, int32_t *ret, int64_t *total_out)
+{
+	if (!h->ran) { h->err = "no results: call a run function first"; return SMEM_GPU_E_ARG; }
+	if (!read_off) { h->err = "read_off is required"; return SMEM_GPU_E_ARG; }
+	int64_t tot = 0;
+	std::vector<long long> base(h->devs.size());
+	for (size_t k = 0; k < h->devs.size(); ++k) { base[k] = tot; tot += h->devs[k].total; }
+	if (total_out) *total_out = tot;
+	const bool fits = tot <= cap && (intv_out || tot == 0);
+	read_off[0] = 0;
+	int rc = for_each_device(h, [&](DeviceCtx &d) {
+		const size_t k = &d - &h->devs[0];
+		return ctx_fetch(d, fits ? intv_out : nullptr, read_off, fits ? step_out : nullptr, ret, base[k]);
+	});
+	if (rc) return rc;
+	read_off[h->staged] = tot;
+	h->d2h_bytes = (h->staged + (int64_t)h->devs.size()) * 8 + (fits ? tot * (32 + (step_out ? 2 : 0)) : 0) + (ret ? h->staged * 4 : 0);
+	if (!fits) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	return 0;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int smem_gpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int64_t max_batch_reads, int max_read_len)
+{
+	if (!out || n_devices < 1 || n_devices > 64 || max_batch_reads < 1 || max_read_len < 1 || max_read_len > 65535) return SMEM_GPU_E_ARG;
+	*out = nullptr;
+	if (smem_gpu_device_count() < 1) return SMEM_GPU_E_NODEVICE;
+	smem_gpu *h = new (std::nothrow) smem_gpu();
+	if (!h) return SMEM_GPU_E_NOMEM;
+	h->max_batch = max_batch_reads; h->max_len = max_read_len;
+	h->devs.resize(n_devices);
+	const int64_t per = (max_batch_reads + n_devices - 1) / n_devices;
+	for (int k = 0; k < n_devices; ++k) {
+		int rc = ctx_init(h->devs[k], device_ids ? device_ids[k] : k, per, max_read_len, h->slot_cap);
+		if (rc) {
+			fprintf(stderr, "[smem_gpu] create failed on device %d: %s\n", h->devs[k].dev, h->devs[k].err.c_str());
+			for (auto &d : h->devs) ctx_free(d);
+			delete h;
+			return rc;
+		}
+	}
+	*out = h;
+	return 0;
+}
+
+int smem_gpu_destroy(smem_gpu_t *h)
+{
+	if (!h) return SMEM_GPU_E_ARG;
+	for (auto &d : h->devs) ctx_free(d);
+	delete h;
+	return 0;
+}
+
+int smem_gpu_upload_index(smem_gpu_t *h, const smem_index_desc_t *ix)
+{
+	if (!h || !ix || !ix->bwt || ix->bwt_size < 16) return SMEM_GPU_E_ARG;
+	return for_each_device(h, [&](DeviceCtx &d) { return ctx_upload_index(d, ix, -1); });
+}
+
+int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device)
+{
+	if (!h || !ix || !ix->bwt || ix->bwt_size < 16 || src_device < 0) return SMEM_GPU_E_ARG;
+	return for_each_device(h, [&](DeviceCtx &d) { return ctx_upload_index(d, ix, src_device); });
+}
+
+int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs)
+{
+	return do_stage(h, n_reads, seq, offs, nullptr, nullptr);
+}
+
+int smem_gpu_run_collect(smem_gpu_t *h, const smem_seed_opt_t *opt, int64_t *total_out)
+{
+	if (!h || !opt) return SMEM_GPU_E_ARG;
+	return do_run(h, MODE_COLLECT, opt, total_out);
+}
+
+int smem_gpu_fetch(smem_gpu_t *h, smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, uint16_t *step_out, int64_t *total_out)
+{
+	if (!h) return SMEM_GPU_E_ARG;
+	return do_fetch(h, intv_out, intv_cap, read_off, step_out, nullptr, total_out);
+}
+
+int smem_gpu_collect(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const smem_seed_opt_t *opt,
+                     smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, uint16_t *step_out, int64_t *total_out)
+{
+	if (!h || !opt || !read_off) return SMEM_GPU_E_ARG;
+	int rc = do_stage(h, n_reads, seq, offs, nullptr, nullptr);
+	if (rc) return rc;
+	if ((rc = do_run(h, MODE_COLLECT, opt, nullptr))) return rc;
+	return do_fetch(h, intv_out, intv_cap, read_off, step_out, nullptr, total_out);
+}
+
+int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *min_intv,
+                   smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, int32_t *ret, int64_t *total_out)
+{
+	if (!h || !read_off || !ret || (n_reads > 0 && (!x || !min_intv))) return SMEM_GPU_E_ARG;
+	int rc = do_stage(h, n_reads, seq, offs, x, min_intv);
+	if (rc) return rc;
+	if ((rc = do_run(h, MODE_SMEM1, nullptr, nullptr))) return rc;
+	return do_fetch(h, intv_out, intv_cap, read_off, nullptr, ret, total_out);
+}
+
+int smem_gpu_host_alloc(void **ptr, size_t bytes)
+{
+	if (!ptr) return SMEM_GPU_E_ARG;
+	return cudaMallocHost(ptr, bytes ? bytes : 1) == cudaSuccess ? 0 : SMEM_GPU_E_NOMEM;
+}
+int smem_gpu_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? 0 : SMEM_GPU_E_CUDA; }
+
+int smem_gpu_last_timing(const smem_gpu_t *h, smem_gpu_timing_t *t)
+{
+	if (!h || !t) return SMEM_GPU_E_ARG;
+	memset(t, 0, sizeof *t);
+	for (auto &d : h->devs) {
+		t->seed_kernel_ms = std::max<double>(t->seed_kernel_ms, d.seed_ms);
+		t->total_device_ms = std::max<double>(t->total_device_ms, d.total_ms);
+		t->kernel_launches += d.launches;
+		t->overflow_reads += d.overflow;
+	}
+	t->h2d_bytes = h->h2d_bytes; t->d2h_bytes = h->d2h_bytes;
+	return 0;
+}
+
+int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
+{
+	if (!h || !name) return SMEM_GPU_E_ARG;
+	if (!strcmp(name, "blocks_per_sm")) {
+		static const int ok[] = {3, 4, 5, 6, 8, 10, 12};
+		for (int k : ok) if (k == v) { h->blocks_per_sm = (int)v; return 0; }
+		return SMEM_GPU_E_ARG;
+	}
+	if (!strcmp(name, "slot_cap")) { if (v < 1 || v > 4096) return SMEM_GPU_E_ARG; h->slot_cap = (int)v; return 0; }
+	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
+	return SMEM_GPU_E_ARG;
+}
+
+int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
+{
+	if (!h || !name) return SMEM_GPU_E_ARG;
+	if (!strcmp(name, "block_threads")) return h->block_threads;
+	if (!strcmp(name, "blocks_per_sm")) return h->blocks_per_sm;
+	if (!strcmp(name, "slot_cap")) return h->slot_cap;
+	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
+	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
+	if (!strcmp(name, "n_devices")) return (int64_t)h->devs.size();
+	return SMEM_GPU_E_ARG;
+}
+
+int smem_gpu_gather_roofline(smem_gpu_t *h, int block_bytes, uint64_t span_bytes, int chains_per_sm, int steps, double *gbps_out)
+{
+	if (!h || !gbps_out || (block_bytes != 32 && block_bytes != 64) || chains_per_sm < 256 || steps < 1) return SMEM_GPU_E_ARG;
+	DeviceCtx &d = h->devs[0];
+	if (!d.has_index) { h->err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
+	auto body = [&]() -> int {
+		CK(cudaSetDevice(d.dev));
+		if (span_bytes == 0 || span_bytes > d.index_bytes) span_bytes = d.index_bytes;
+		const u64 units = span_bytes / block_bytes;
+		const int grid = d.sm_count * (chains_per_sm / 256);
+		u64 *sink = (u64 *)d.d_status;
+		for (int rep = 0; rep < 2; ++rep) {   // first pass warms the TLB / instruction cache
+			CK(cudaEventRecord(d.ev0, d.stream));
+			if (block_bytes == 64) gather_probe_kernel<64><<<grid, 256, 0, d.stream>>>(d.d_index, units, steps, sink);
+			else gather_probe_kernel<32><<<grid, 256, 0, d.stream>>>(d.d_index, units, steps, sink);
+			CK(cudaGetLastError());
+			CK(cudaEventRecord(d.ev1, d.stream));
+			CK(cudaStreamSynchronize(d.stream));
+		}
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+		*gbps_out = (double)grid * 256.0 * steps * block_bytes / (ms * 1e-3) / 1e9;
+		return 0;
+	};
+	int rc = body();
+	if (rc) h->err = d.err;
+	return rc;
+}
+
+const char *smem_gpu_strerror(int code)
+{
+	switch (code) {
+	case SMEM_GPU_OK: return "ok";
+	case SMEM_GPU_E_ARG: return "bad argument";
+	case SMEM_GPU_E_CUDA: return "CUDA runtime error";
+	case SMEM_GPU_E_NOMEM: return "out of memory";
+	case SMEM_GPU_E_NOINDEX: return "no index uploaded";
+	case SMEM_GPU_E_CAPACITY: return "capacity exceeded";
+	case SMEM_GPU_E_INTERNAL: return "device-side guard tripped";
+	case SMEM_GPU_E_NODEVICE: return "no CUDA device";
+	default: return "unknown error";
+	}
+}
+
+const char *smem_gpu_last_error(const smem_gpu_t *h) { return h ? h->err.c_str() : "null handle"; }
+
+} // extern "C"

@@ -1,0 +1,231 @@
+"""ctypes binding of the C-ABI CUDA library (include/smem_gpu.h) -- the host-side mirror used by
+tests/ and bench.py.  There is deliberately no CPU fallback: if ``libsmem_gpu.so`` is missing or
+no CUDA device is usable, constructing :class:`SmemGpu` raises.
+
+Mirrors the reference interface for the path:
+  * ``SmemGpu.upload_index``   <- bwa_idx_load_bwt's upload step (bwa.c:289-301)
+  * ``SmemGpu.collect``        <- mem_insert_seed's enumeration loop over smem_next2 (bwamem.c:453-460)
+  * ``SmemGpu.smem1``          <- one DO call of bwt_smem1_batched / bwt_smem1 (bwt.c:444, bwt.c:776)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
+
+EXPORTS = [
+    "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
+    "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
+    "smem_gpu_device_count",
+]
+
+
+class SeedOpt(C.Structure):
+    """smem_seed_opt_t == seeding fields of mem_opt_t (bwamem.h:33-60; defaults bwamem.c:45-75)."""
+    _fields_ = [("min_seed_len", C.c_int), ("split_factor", C.c_double), ("split_width", C.c_int), ("start_width", C.c_int)]
+
+    def __init__(self, min_seed_len=19, split_factor=1.5, split_width=10, start_width=1):
+        super().__init__(min_seed_len, split_factor, split_width, start_width)
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64), ("bwt_size", C.c_uint64),
+                ("bwt", C.c_void_p)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("seed_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("kernel_launches", C.c_int64),
+                ("overflow_reads", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SmemGpuError(RuntimeError):
+    def __init__(self, code, what, detail=""):
+        super().__init__(f"smem_gpu: {what} ({code}){': ' + detail if detail else ''}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/ for sm_100a with nvcc (in-tree .so, travels to the GPU box)."""
+    if force or not os.path.exists(LIB_PATH) or any(
+            os.path.getmtime(os.path.join(HERE, "csrc", f)) > os.path.getmtime(LIB_PATH)
+            for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh"))):
+        subprocess.run(["make", "-s", "-C", os.path.join(HERE, "csrc")], check=True)
+    return LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    lib.smem_gpu_strerror.restype = C.c_char_p
+    lib.smem_gpu_last_error.restype = C.c_char_p
+    lib.smem_gpu_get_param.restype = C.c_int64
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (smem_gpu_host_alloc)."""
+
+    def __init__(self, lib, shape, dtype):
+        self.lib = lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = C.c_void_p()
+        rc = lib.smem_gpu_host_alloc(C.byref(self.ptr), C.c_size_t(max(self.nbytes, 1)))
+        if rc:
+            raise SmemGpuError(rc, "host_alloc failed")
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.smem_gpu_host_free(self.ptr)
+            self.ptr = None
+
+
+class SmemGpu:
+    def __init__(self, max_batch_reads: int, max_read_len: int, devices: "list[int] | None" = None):
+        self.lib = load_library()
+        n_avail = self.lib.smem_gpu_device_count()
+        if n_avail < 1:
+            raise SmemGpuError(-7, "no CUDA device visible; the seeding path has no CPU fallback")
+        devices = list(devices) if devices is not None else [0]
+        self.h = C.c_void_p()
+        ids = (C.c_int * len(devices))(*devices)
+        rc = self.lib.smem_gpu_create(C.byref(self.h), len(devices), ids, C.c_int64(max_batch_reads), C.c_int(max_read_len))
+        if rc:
+            raise SmemGpuError(rc, self.lib.smem_gpu_strerror(rc).decode())
+        self.max_batch = max_batch_reads
+        self.devices = devices
+        self._keep = None
+
+    # -- helpers
+    def _check(self, rc):
+        if rc:
+            raise SmemGpuError(rc, self.lib.smem_gpu_strerror(rc).decode(), self.lib.smem_gpu_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.smem_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_param(self, name: str, value: int):
+        self._check(self.lib.smem_gpu_set_param(self.h, name.encode(), C.c_int64(value)))
+
+    def get_param(self, name: str) -> int:
+        return int(self.lib.smem_gpu_get_param(self.h, name.encode()))
+
+    def timing(self) -> dict:
+        t = Timing()
+        self._check(self.lib.smem_gpu_last_timing(self.h, C.byref(t)))
+        return t.asdict()
+
+    # -- index
+    def upload_index(self, index):
+        """``index``: object with primary / L2 / seq_len / bwt_size / bwt (numpy array or torch tensor)."""
+        bwt = index.bwt
+        desc = IndexDesc(int(index.primary), (C.c_uint64 * 5)(*[int(v) for v in index.L2]), int(index.seq_len),
+                         int(index.bwt_size), None)
+        if hasattr(bwt, "is_cuda") and bwt.is_cuda:
+            desc.bwt = bwt.data_ptr()
+            import torch
+            torch.cuda.synchronize(bwt.device)
+            self._check(self.lib.smem_gpu_upload_index_device(self.h, C.byref(desc), C.c_int(bwt.device.index or 0)))
+        else:
+            words = np.ascontiguousarray(index.words_numpy(), np.uint32)
+            desc.bwt = words.ctypes.data
+            self._check(self.lib.smem_gpu_upload_index(self.h, C.byref(desc)))
+
+    # -- one-call forms (host buffers in, host buffers out)
+    def collect(self, seq, offs, opt: "SeedOpt | None" = None, want_step=True, cap_hint: "int | None" = None):
+        opt = opt or SeedOpt()
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        n = len(offs) - 1
+        cap = cap_hint or max(64, 16 * n)
+        read_off = np.zeros(n + 1, np.int64)
+        tot = C.c_int64(0)
+        while True:
+            intv = np.empty((cap, 4), np.uint64)
+            step = np.empty(cap, np.uint16) if want_step else None
+            rc = self.lib.smem_gpu_collect(self.h, C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64), C.byref(opt),
+                                           _p(intv, C.c_uint64), C.c_int64(cap), _p(read_off, C.c_int64),
+                                           _p(step, C.c_uint16), C.byref(tot))
+            if rc == -5 and tot.value > cap:
+                cap = int(tot.value)
+                continue
+            self._check(rc)
+            t = int(tot.value)
+            return dict(intv=intv[:t], read_off=read_off, step=step[:t] if want_step else None)
+
+    def smem1(self, seq, offs, x, min_intv):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        x = np.ascontiguousarray(x, np.int32)
+        mi = np.ascontiguousarray(min_intv, np.int32)
+        n = len(offs) - 1
+        cap = max(64, 16 * n)
+        read_off = np.zeros(n + 1, np.int64)
+        ret = np.zeros(max(n, 1), np.int32)
+        tot = C.c_int64(0)
+        while True:
+            intv = np.empty((cap, 4), np.uint64)
+            rc = self.lib.smem_gpu_smem1(self.h, C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64), _p(x, C.c_int32),
+                                         _p(mi, C.c_int32), _p(intv, C.c_uint64), C.c_int64(cap), _p(read_off, C.c_int64),
+                                         _p(ret, C.c_int32), C.byref(tot))
+            if rc == -5 and tot.value > cap:
+                cap = int(tot.value)
+                continue
+            self._check(rc)
+            return dict(intv=intv[:int(tot.value)], read_off=read_off, ret=ret[:n])
+
+    # -- split form (device-resident timing)
+    def stage(self, seq, offs):
+        seq = np.ascontiguousarray(seq, np.uint8) if not isinstance(seq, np.ndarray) or not seq.flags.c_contiguous else seq
+        offs = np.ascontiguousarray(offs, np.int64)
+        self._keep = (seq, offs)
+        self._n = len(offs) - 1
+        self._check(self.lib.smem_gpu_stage_reads(self.h, C.c_int64(self._n), _p(seq, C.c_uint8), _p(offs, C.c_int64)))
+
+    def run_collect(self, opt: "SeedOpt | None" = None) -> int:
+        opt = opt or SeedOpt()
+        tot = C.c_int64(0)
+        self._check(self.lib.smem_gpu_run_collect(self.h, C.byref(opt), C.byref(tot)))
+        return int(tot.value)
+
+    def fetch(self, total: int, want_step=False, intv=None, read_off=None):
+        n = self._n
+        intv = intv if intv is not None else np.empty((max(total, 1), 4), np.uint64)
+        read_off = read_off if read_off is not None else np.zeros(n + 1, np.int64)
+        step = np.empty(max(total, 1), np.uint16) if want_step else None
+        tot = C.c_int64(0)
+        self._check(self.lib.smem_gpu_fetch(self.h, _p(intv, C.c_uint64), C.c_int64(intv.shape[0]), _p(read_off, C.c_int64),
+                                            _p(step, C.c_uint16), C.byref(tot)))
+        t = int(tot.value)
+        return dict(intv=intv[:t], read_off=read_off, step=step[:t] if want_step else None)
+
+    def gather_roofline(self, block_bytes=64, span_bytes=0, chains_per_sm=2048, steps=2000) -> float:
+        g = C.c_double(0)
+        self._check(self.lib.smem_gpu_gather_roofline(self.h, C.c_int(block_bytes), C.c_uint64(span_bytes), C.c_int(chains_per_sm),
+                                                      C.c_int(steps), C.byref(g)))
+        return float(g.value)

@@ -1,0 +1,135 @@
+/* smem_gpu.h -- C ABI of the B200 SMEM-seeding service.
+ *
+ * This is the drop-in boundary that replaces the Intel AAL/MPF FPGA service of the reference
+ * (HelloALINLB.cpp:254-482 bring-up, bwa.c:289-307 index upload, fastmap.c:320-429 manager thread,
+ * bwt.c:444-774 bwt_smem1_batched pack/handshake/unpack).  Plain C: pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SMEM_GPU_E_* code; nothing aborts, nothing
+ *     falls back to the CPU (the reference's reject->CPU path, bwt.c:651-717, has no equivalent);
+ *   - the caller owns all host arrays; the library owns device memory;
+ *   - a handle may span 1..8 GPUs of one box: the index is replicated, reads are sharded
+ *     contiguously, results land in caller order (no collective on the path);
+ *   - a handle is used by one host thread at a time (the link-compatible adapter in
+ *     host/bwt_smem1_batched_gpu.c serialises the reference's worker threads onto it).
+ *
+ * Read batch:   seq  uint8, one base per byte, 0..3 = A,C,G,T, >3 ambiguous (bwamem.c:1403-1406)
+ *               offs int64[n+1]; read i = seq[offs[i] .. offs[i+1])
+ * Result:       intv smem_intv_t[total] (== bwtintv_t, bwt.h:60-62), grouped by read in batch order,
+ *               read_off int64[n+1] (CSR), each read's intervals in the order the reference's
+ *               iterator yields them (per step: sorted by start, bwt.c:829 / bwamem.c:281-301).
+ */
+#ifndef SMEM_GPU_H
+#define SMEM_GPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smem_gpu smem_gpu_t;
+
+/* == bwtintv_t (bwt.h:60-62): x[0] forward SA start, x[1] reverse-strand SA start, x[2] size,
+ * info = query_begin<<32 | query_end (end exclusive). */
+typedef struct { uint64_t x[3], info; } smem_intv_t;
+
+/* The fields of bwt_t (bwt.h:46-58) that the path reads.  `bwt` is bwt_t::bwt: 64-byte blocks of
+ * 4 x uint64 occ checkpoints + 8 x uint32 words of 16 two-bit symbols (bwtindex.c:128-150). */
+typedef struct {
+	uint64_t primary;
+	uint64_t L2[5];
+	uint64_t seq_len;
+	uint64_t bwt_size;      /* in uint32 words */
+	const uint32_t *bwt;
+} smem_index_desc_t;
+
+/* Seeding fields of mem_opt_t (bwamem.h:33-60); defaults mem_opt_init (bwamem.c:45-75):
+ * min_seed_len 19, split_factor 1.5, split_width 10, start_width = MEM_F_NO_EXACT ? 2 : 1. */
+typedef struct {
+	int min_seed_len;
+	double split_factor;
+	int split_width;
+	int start_width;
+} smem_seed_opt_t;
+
+enum {
+	SMEM_GPU_OK = 0,
+	SMEM_GPU_E_ARG = -1,        /* bad argument */
+	SMEM_GPU_E_CUDA = -2,       /* CUDA runtime error, see smem_gpu_last_error */
+	SMEM_GPU_E_NOMEM = -3,      /* host or device allocation failed */
+	SMEM_GPU_E_NOINDEX = -4,    /* no index uploaded */
+	SMEM_GPU_E_CAPACITY = -5,   /* batch larger than the handle was created for / output cap too small */
+	SMEM_GPU_E_INTERNAL = -6,   /* device-side guard tripped */
+	SMEM_GPU_E_NODEVICE = -7    /* no usable CUDA device */
+};
+
+/* Replaces HelloALINLBApp::run's service/buffer allocation (HelloALINLB.cpp:309-380).
+ * device_ids may be NULL (= 0..n_devices-1). max_batch_reads / max_read_len size the device
+ * buffers (per handle, split across devices). */
+int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int64_t max_batch_reads, int max_read_len);
+int smem_gpu_destroy(smem_gpu_t *h);
+
+/* Replaces the memcpy into SPL_BWT_ref + handshake `2` of bwa_idx_load_bwt (bwa.c:289-301):
+ * copies bwt->bwt, primary, L2, seq_len to every GPU of the handle, once. */
+int smem_gpu_upload_index(smem_gpu_t *h, const smem_index_desc_t *ix);
+/* Same, but ix->bwt is a device pointer on CUDA device `src_device` (index built on the GPU). */
+int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device);
+
+/* Whole-read seeding == the enumeration loop of mem_insert_seed (bwamem.c:453-460):
+ * smem_next2 (bwamem.c:244-305: pass 1, 0.7.8 re-seed of the longest SMEM, ordered merge) to
+ * exhaustion for every read.  step_out (nullable) receives, per interval, the index of the
+ * smem_next2 call that produced it.  *total_out = number of intervals; if it exceeds intv_cap the
+ * call returns SMEM_GPU_E_CAPACITY with read_off and *total_out valid and intv_out untouched. */
+int smem_gpu_collect(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs,
+                     const smem_seed_opt_t *opt, smem_intv_t *intv_out, int64_t intv_cap,
+                     int64_t *read_off, uint16_t *step_out, int64_t *total_out);
+
+/* One raw bwt_smem1 call per read (bwt.c:776-835) == one DO call of bwt_smem1_batched
+ * (bwt.c:444): position x[i], minimum interval size min_intv[i] (clamped to >= 1);
+ * ret[i] = end of the longest forward match (itr->start after pass 1). */
+int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs,
+                   const int32_t *x, const int32_t *min_intv, smem_intv_t *intv_out, int64_t intv_cap,
+                   int64_t *read_off, int32_t *ret, int64_t *total_out);
+
+/* Split form of smem_gpu_collect, so that seeding can be timed with inputs resident in HBM:
+ * stage (H2D) -> run (kernels only, may be repeated) -> fetch (D2H). */
+int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs);
+int smem_gpu_run_collect(smem_gpu_t *h, const smem_seed_opt_t *opt, int64_t *total_out);
+int smem_gpu_fetch(smem_gpu_t *h, smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off,
+                   uint16_t *step_out, int64_t *total_out);
+
+/* Pinned host memory for the caller's batches (replaces the MPF-VTP workspace buffers). */
+int smem_gpu_host_alloc(void **ptr, size_t bytes);
+int smem_gpu_host_free(void *ptr);
+
+/* Measurement hooks (CUDA events on the library's own streams; max over the handle's devices). */
+typedef struct {
+	double seed_kernel_ms;     /* the SMEM kernel(s) of the last run */
+	double total_device_ms;    /* seed kernel + scan + compaction (+ overflow re-run) */
+	int64_t kernel_launches;   /* kernels launched by the last run, all devices */
+	int64_t overflow_reads;    /* reads that needed the large-slot re-run */
+	int64_t h2d_bytes, d2h_bytes;  /* bytes copied by the last stage / fetch */
+} smem_gpu_timing_t;
+int smem_gpu_last_timing(const smem_gpu_t *h, smem_gpu_timing_t *t);
+
+/* Tuning knobs: "block_threads", "blocks_per_sm", "slot_cap", "l2_hot_min_intv" (0 = off:
+ * occ-block loads for intervals of size >= value carry an L2 evict_last hint). */
+int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t value);
+int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name);
+
+/* Random-access roofline micro-benchmark: dependent chains of aligned
+ * `block_bytes` (32 or 64) gathers, uniform over the first `span_bytes` of the uploaded index
+ * (0 = all of it), `chains_per_sm` chains in flight per SM, `steps` gathers per chain.
+ * *gbps_out = bytes gathered / CUDA-event time on device 0 of the handle. */
+int smem_gpu_gather_roofline(smem_gpu_t *h, int block_bytes, uint64_t span_bytes, int chains_per_sm,
+                             int steps, double *gbps_out);
+
+const char *smem_gpu_strerror(int code);
+const char *smem_gpu_last_error(const smem_gpu_t *h);   /* detail of the last failure on this handle */
+int smem_gpu_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

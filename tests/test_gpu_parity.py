@@ -1,0 +1,164 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: bit-exact intervals.
+
+Everything here calls libsmem_gpu.so through ctypes (include/smem_gpu.h); the oracle is only the checker.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, OPT_KEYS, GoldenIndex, pkg, same_result
+from oracle.binding import Oracle, SeedOpt as OSeedOpt
+
+pytestmark = pytest.mark.gpu
+
+
+def gopt(o):
+    sg = pkg("smem_gpu")
+    return sg.SeedOpt(int(o[0]), float(o[1]), int(o[2]), int(o[3]))
+
+
+@pytest.fixture(scope="module")
+def sg():
+    m = pkg("smem_gpu")
+    m.load_library()
+    return m
+
+
+@pytest.fixture(scope="module")
+def world(fm, synth, sg):
+    """1 Mbp random reference with planted repeats, its index, the oracle and a GPU handle."""
+    ref = synth.make_reference(1_000_000, 77)
+    ref[50_000:52_000] = ref[10_000:12_000]
+    ref[400_000:400_300] = 1
+    ix = fm.build_index(ref)
+    g = sg.SmemGpu(max_batch_reads=40_000, max_read_len=260)
+    g.upload_index(ix)
+    return ref, ix, Oracle(ix), g
+
+
+@pytest.mark.parametrize("key", OPT_KEYS)
+def test_golden_collect(golden, sg, key):
+    name, z, ix = golden
+    g = sg.SmemGpu(max_batch_reads=1024, max_read_len=160)
+    g.upload_index(ix)
+    r = g.collect(z["seq"], z["offs"], gopt(z[f"opt_{key}"]))
+    for k in ("intv", "read_off", "step"):
+        assert np.array_equal(r[k], z[f"collect_{key}_{k}"]), (name, key, k)
+    g.close()
+
+
+@pytest.mark.parametrize("rep", [0, 1, 2])
+def test_golden_smem1(golden, sg, rep):
+    name, z, ix = golden
+    g = sg.SmemGpu(max_batch_reads=1024, max_read_len=160)
+    g.upload_index(ix)
+    r = g.smem1(z["smem1_seq"], z["smem1_offs"], z[f"smem1_{rep}_x"], z[f"smem1_{rep}_min_intv"])
+    for k in ("intv", "read_off", "ret"):
+        assert np.array_equal(r[k], z[f"smem1_{rep}_{k}"]), (name, rep, k)
+    g.close()
+
+
+@pytest.mark.parametrize("n,L,err,nfrac,opt", [
+    (20000, 101, 0.01, 0.06, (19, 1.5, 10, 1)),
+    (6000, 250, 0.02, 0.06, (19, 1.5, 10, 1)),       # BASELINE config 4 shape: re-seeding on
+    (5000, 101, 0.01, 0.0, (19, 1.5, 10, 2)),        # MEM_F_NO_EXACT
+    (5000, 60, 0.05, 0.3, (10, 1.2, 20, 1)),
+    (3000, 150, 0.0, 0.0, (19, 1.5, 0, 1)),          # split_width 0: never re-seeds
+    (3000, 36, 0.1, 0.0, (19, 1.5, 10, 1)),
+])
+def test_collect_vs_oracle(world, synth, n, L, err, nfrac, opt):
+    ref, ix, o, g = world
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, n, L, err, seed=n + L, n_frac=nfrac))
+    a = o.collect(seq, offs, OSeedOpt(*opt), nthreads=8)
+    b = g.collect(seq, offs, gopt(opt))
+    same_result(a, b, ("read_off", "intv", "step"))
+    t = g.timing()
+    assert t["kernel_launches"] >= 3 and t["seed_kernel_ms"] > 0
+
+
+def test_smem1_vs_oracle(world, synth):
+    ref, ix, o, g = world
+    n = 12000
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, n, 101, 0.02, seed=5, n_frac=0.1))
+    rng = np.random.default_rng(8)
+    x = rng.integers(0, 101, n).astype(np.int32)
+    mi = rng.integers(0, 5, n).astype(np.int32)
+    a, b = o.smem1(seq, offs, x, mi), g.smem1(seq, offs, x, mi)
+    same_result(a, b, ("read_off", "intv", "ret"))
+
+
+def test_ragged_and_degenerate_reads(world, synth):
+    ref, ix, o, g = world
+    rng = np.random.default_rng(2)
+    refn = ref.numpy()
+    reads = [np.zeros(0, np.uint8), np.array([4], np.uint8), np.array([3], np.uint8), np.full(50, 4, np.uint8),
+             refn[400_000:400_200].copy(), refn[10_000:10_250].copy(), np.zeros(120, np.uint8)]
+    for _ in range(500):
+        L = int(rng.integers(1, 256))
+        p = int(rng.integers(0, len(refn) - L))
+        r = refn[p:p + L].copy()
+        if rng.random() < 0.3:
+            r[rng.integers(0, L, 3)] = 4
+        if rng.random() < 0.5:
+            r = (3 - np.minimum(r, 3))[::-1].copy() if r.max(initial=0) < 4 else r
+        reads.append(r)
+    seq, offs = synth.to_batch(reads)
+    a = o.collect(seq, offs, OSeedOpt(), nthreads=4)
+    b = g.collect(seq, offs)
+    same_result(a, b, ("read_off", "intv", "step"))
+    # empty batch
+    e = g.collect(np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    assert len(e["intv"]) == 0 and list(e["read_off"]) == [0]
+
+
+def test_slot_overflow_rerun_and_knobs(world, synth):
+    """Results must not depend on launch geometry, slot capacity (forces the overflow re-run) or L2 hints."""
+    ref, ix, o, g = world
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 4000, 101, 0.03, seed=31, n_frac=0.05))
+    a = o.collect(seq, offs, OSeedOpt(), nthreads=8)
+    try:
+        for name, val in [("slot_cap", 2), ("slot_cap", 32), ("blocks_per_sm", 3), ("blocks_per_sm", 8), ("blocks_per_sm", 4),
+                          ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0)]:
+            g.set_param(name, val)
+            b = g.collect(seq, offs)
+            same_result(a, b, ("read_off", "intv", "step"))
+            if name == "slot_cap" and val == 2:
+                assert g.timing()["overflow_reads"] > 0
+    finally:
+        g.set_param("slot_cap", 32); g.set_param("blocks_per_sm", 4); g.set_param("l2_hot_min_intv", 0)
+
+
+def test_staged_run_is_idempotent_and_capacity_error(world, synth, sg):
+    ref, ix, o, g = world
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 3000, 101, 0.01, seed=1))
+    a = o.collect(seq, offs, OSeedOpt(), nthreads=4)
+    g.stage(seq, offs)
+    t1 = g.run_collect()
+    t2 = g.run_collect()
+    assert t1 == t2 == len(a["intv"])
+    b = g.fetch(t2, want_step=True)
+    same_result(a, b, ("read_off", "intv", "step"))
+    assert o.checksum(b["intv"], b["read_off"]) == o.checksum(a["intv"], a["read_off"])
+    # too-small output buffer -> SMEM_GPU_E_CAPACITY with counts still reported
+    with pytest.raises(sg.SmemGpuError) as ei:
+        g.fetch(t2, intv=np.empty((10, 4), np.uint64))
+    assert ei.value.code == -5
+    with pytest.raises(sg.SmemGpuError):
+        g.stage(np.zeros(50_000 * 10, np.uint8), np.arange(50_001, dtype=np.int64) * 10)   # > max_batch_reads
+
+
+def test_exact_reads_give_full_length_smem(world, synth):
+    """Size-independent property: an error-free read has one SMEM spanning it, with x[2] >= 1."""
+    ref, ix, o, g = world
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 5000, 101, 0.0, seed=99))
+    b = g.collect(seq, offs)
+    ro = b["read_off"]
+    for i in range(0, 5000, 7):
+        iv = b["intv"][ro[i]:ro[i + 1]]
+        full = [(int(v[3]) >> 32, int(v[3]) & 0xFFFFFFFF) for v in iv]
+        assert (0, 101) in full
+        assert all(int(v[2]) >= 1 for v in iv)
+        starts = [s for s, _ in full]
+        # per step the list is sorted by start; across steps starts never decrease below the previous step's first
+        assert all(0 <= s < e <= 101 for s, e in full)
