@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- SMEM-seeded 101 bp reads/s on N B200s (BASELINE.json metric), one JSON line on stdout.
+
+A "step" is one pass of the hot path (smem_next2 to exhaustion for every read == the enumeration loop
+of mem_insert_seed, bwamem.c:453-460) over one batch of simulated reads per GPU.
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [...]                      the reference's own CPU code on the host cores
+
+Workload (BASELINE.json configs[2]): 3.1 Gbp synthetic reference (25 contigs x 124 Mbp), 1 M simulated
+101 bp read pairs (= 2 M reads) per GPU per step, default seeding options (-k 19 -r 1.5, split_width 10).
+The index is built on the GPU by bwa-mem-harp2_b200/fmindex.py (verified bit-for-bit against `bwa index`
+in tests/), outside every timed region.  Multi-GPU: index replicated, reads sharded (weak scaling: every
+rank seeds its own 2 M reads), no collective on the data path.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-bp", type=int, default=int(os.environ.get("SMEM_BENCH_REF_BP", 3_100_000_000)))
+    ap.add_argument("--contigs", type=int, default=25)
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("SMEM_BENCH_READS", 2_000_000)), help="reads per GPU per step")
+    ap.add_argument("--read-len", type=int, default=101)
+    ap.add_argument("--err", type=float, default=0.01)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--l2-hot-min-intv", type=int, default=-1)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv] to time (stderr), e.g. 4,6,8:16384")
+    ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_workload(args, rank, device):
+    """Reference + index on the GPU, this rank's reads on the host (pinned by the caller)."""
+    import torch
+    fm = importlib.import_module("bwa-mem-harp2_b200.fmindex")
+    sy = importlib.import_module("bwa-mem-harp2_b200.synth")
+    t0 = time.time()
+    fwd = sy.make_reference(args.ref_bp, 13, device)
+    ix = fm.build_index(fwd)
+    torch.cuda.synchronize()
+    t_index = time.time() - t0
+    reads = sy.simulate_reads(fwd, args.reads, args.read_len, args.err, seed=1000 + rank, paired=True)
+    seq, offs = sy.to_batch(reads)
+    del fwd, reads
+    torch.cuda.empty_cache()
+    return ix, seq, offs, t_index
+
+
+def cpu_engine(ix_host):
+    """(engine, kind): the reference's own objects if oracle/_ref travelled, else the C port."""
+    from oracle.binding import Oracle, Reference
+    try:
+        return Reference(ix_host), "reference"
+    except Exception as e:  # noqa: BLE001
+        log("reference objects unavailable, using the oracle port:", e)
+        return Oracle(ix_host), "port"
+
+
+def cpu_time(engine, seq, offs, n, threads, opt):
+    o = offs[: n + 1]
+    return engine.time_collect(seq[: int(o[-1])], o, opt, threads)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference" and rank != 0:
+        return 0                                   # rank 0 alone runs the CPU arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the seeding path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    use_dist = world > 1 and args.impl == "ours"
+    if use_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from oracle.binding import SeedOpt as OSeedOpt
+    sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    workload = (f"{args.ref_bp / 1e9:.2f} Gbp synthetic reference ({args.contigs} contigs), "
+                f"{args.reads // 2} simulated {args.read_len}bp read pairs ({args.reads} reads) per GPU per step, "
+                f"{args.err:.0%} substitutions, -k 19 -r 1.5 re-seeding on")
+    config = {"workload": workload, "baseline_config": "configs[2]", "ref_bp": args.ref_bp, "reads_per_gpu_per_step": args.reads,
+              "read_len": args.read_len, "l2": "inputs larger than L2 (index %.1f GB, reads %.0f MB)" %
+              (args.ref_bp / 1e9, args.reads * args.read_len / 1e6), "parallelism": f"replicated index, reads sharded x{args.gpus}"}
+
+    log(f"rank {rank}/{world}: building workload ({args.ref_bp} bp)")
+    ix, seq, offs, t_index = make_workload(args, rank, device)
+    log(f"index built on GPU in {t_index:.1f}s: seq_len={ix.seq_len} bwt_size={ix.bwt_size} primary={ix.primary}")
+    n = len(offs) - 1
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        fm = importlib.import_module("bwa-mem-harp2_b200.fmindex")
+        ixh = fm.BwtIndex(ix.primary, ix.L2, ix.seq_len, ix.bwt_size, ix.words_numpy())
+        eng, kind = cpu_engine(ixh)
+        opt = OSeedOpt()
+        probe = cpu_time(eng, seq, offs, min(n, 20_000), ncores, opt)
+        per_step = max(10_000, min(n, int(probe["reads_per_s"] * min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))))
+        for _ in range(args.warmup):
+            cpu_time(eng, seq, offs, per_step, ncores, opt)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_time(eng, seq, offs, per_step, ncores, opt)
+        dt = time.perf_counter() - t0
+        v = per_step * args.steps / dt
+        sample = f"first {per_step} reads of the step's batch per step, {ncores} host threads (kt_for)"
+        print(json.dumps({"impl": "reference", "metric": "smem_seeded_101bp_reads_per_sec", "value": v, "unit": "reads/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                          "config": config, "cpu_baseline": {"value": v, "unit": "reads/s", "cores": ncores, "kind": kind, "sample": sample},
+                          "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA through the C ABI)
+    g = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local])
+    if args.blocks_per_sm:
+        g.set_param("blocks_per_sm", args.blocks_per_sm)
+    if args.l2_hot_min_intv >= 0:
+        g.set_param("l2_hot_min_intv", args.l2_hot_min_intv)
+    g.upload_index(ix)                      # device -> device copy of the packed bwt_t into the library's HBM buffer
+    lib = g.lib
+    # pinned host batch + pinned result buffers for the end-to-end leg
+    pseq = sg.PinnedArray(lib, (len(seq),), np.uint8); pseq.array[:] = seq
+    poffs = sg.PinnedArray(lib, (n + 1,), np.int64); poffs.array[:] = offs
+    opt = sg.SeedOpt()
+
+    # CPU baseline + full-size parity sample (rank 0 only)
+    cpu_baseline, parity, bytes_per_read = None, None, None
+    if rank == 0:
+        fm = importlib.import_module("bwa-mem-harp2_b200.fmindex")
+        from oracle.binding import Oracle
+        ixh = fm.BwtIndex(ix.primary, ix.L2, ix.seq_len, ix.bwt_size, ix.words_numpy())
+        orc = Oracle(ixh)
+        ns = min(n, 20_000)
+        st = orc.collect(seq[: int(offs[ns])], offs[: ns + 1], OSeedOpt(), nthreads=ncores, stats=True)
+        s = st["stats"]
+        bytes_per_read = (64.0 * s["blocks"] + 128.0 * ns + 32.0 * s["intervals"]) / ns
+        log(f"algorithmic work per read (oracle, {ns} reads): extends={s['extends'] / ns:.1f} blocks={s['blocks'] / ns:.1f} "
+            f"intervals={s['intervals'] / ns:.2f} bytes={bytes_per_read:.0f}")
+        got = g.collect(seq[: int(offs[ns])], offs[: ns + 1], opt)
+        ok = (np.array_equal(got["read_off"], st["read_off"]) and np.array_equal(got["intv"], st["intv"])
+              and np.array_equal(got["step"], st["step"]))
+        parity = {"reads_checked": ns, "bit_exact": bool(ok), "checker": "oracle/liboracle.so"}
+        if not ok:
+            raise SystemExit("PARITY FAILURE: GPU intervals differ from the oracle on the bench workload")
+        if not args.skip_cpu:
+            eng, kind = cpu_engine(ixh)
+            probe = cpu_time(eng, seq, offs, min(n, 20_000), ncores, OSeedOpt())
+            m = max(20_000, min(n, int(probe["reads_per_s"] * args.cpu_seconds)))
+            r = cpu_time(eng, seq, offs, m, ncores, OSeedOpt())
+            one = cpu_time(eng, seq, offs, min(m, 20_000), 1, OSeedOpt())
+            gk = g.collect(seq[: int(offs[m])], offs[: m + 1], opt, want_step=False)
+            ck = orc.checksum(gk["intv"], gk["read_off"])
+            parity.update(reads_checked=m, bit_exact=bool(ok and ck == r["checksum"]), checker=f"oracle + {kind} checksum")
+            if ck != r["checksum"]:
+                raise SystemExit("PARITY FAILURE: checksum of GPU intervals differs from the CPU arm")
+            cpu_baseline = {"value": r["reads_per_s"], "unit": "reads/s", "cores": ncores, "kind": kind,
+                            "sample": f"first {m} reads of rank 0's batch, seeding only, {ncores} threads",
+                            "one_thread_reads_per_s": one["reads_per_s"]}
+            log("cpu baseline:", cpu_baseline)
+            del eng
+        del orc, ixh
+
+    def sync():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+
+    # ---- device-resident leg: inputs staged in HBM before the timed region
+    g.stage(pseq.array, poffs.array)
+    if args.sweep:
+        keep = (g.get_param("blocks_per_sm"), g.get_param("l2_hot_min_intv"))
+        for item in args.sweep.split(","):
+            b, _, hot = item.partition(":")
+            g.set_param("blocks_per_sm", int(b)); g.set_param("l2_hot_min_intv", int(hot or 0))
+            ms = []
+            for _ in range(4):
+                g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
+            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot or 0}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
+        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1])
+    for _ in range(max(args.warmup, 3)):
+        total = g.run_collect(opt)
+    sampler = ClockSampler(local)
+    sampler.start()
+    seed_ms, dev_ms, launches = [], [], 0
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        total = g.run_collect(opt)
+        t = g.timing()
+        seed_ms.append(t["seed_kernel_ms"]); dev_ms.append(t["total_device_ms"]); launches += t["kernel_launches"]
+    sync()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    overflow = g.timing()["overflow_reads"]
+
+    # ---- end-to-end leg: host buffers in, host buffers out, copies inside the timed region
+    pintv = sg.PinnedArray(lib, (total + 1024, 4), np.uint64)
+    proff = sg.PinnedArray(lib, (n + 1,), np.int64)
+    import ctypes as C
+
+    def e2e_step():
+        tot = C.c_int64(0)
+        rc = lib.smem_gpu_collect(g.h, C.c_int64(n), pseq.array.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                  poffs.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(opt),
+                                  pintv.array.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(pintv.array.shape[0]),
+                                  proff.array.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(tot))
+        if rc:
+            raise SystemExit(f"smem_gpu_collect failed: {rc} {lib.smem_gpu_last_error(g.h).decode()}")
+        return int(tot.value)
+
+    for _ in range(2):
+        e2e_step()
+    sync()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        tot_e2e = e2e_step()
+    sync()
+    dt_e2e = time.perf_counter() - t1
+    te = g.timing()
+
+    # ---- max over ranks
+    times = torch.tensor([dt, dt_e2e, float(np.mean(seed_ms))], dtype=torch.float64, device=device)
+    if use_dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt, dt_e2e, seed_avg_ms = [float(x) for x in times.tolist()]
+
+    probe = None
+    if args.probe and rank == 0:
+        probe = {}
+        for bb in (64, 32):
+            for chains in (512, 1024, 2048):
+                probe[f"{bb}B_x{chains}"] = round(g.gather_roofline(bb, 0, chains, 1000), 1)
+        log("random-access probe GB/s:", probe)
+    rand64 = g.gather_roofline(64, 0, 2048, 1000) if rank == 0 else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        value = world * n * args.steps / dt
+        achieved = n * bytes_per_read / (seed_avg_ms * 1e-3) / 1e9
+        out = {
+            "metric": "smem_seeded_101bp_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "e2e": {"value": world * n * args.steps / dt_e2e, "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": dt_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "seed_kernel<COLLECT>",
+                         "kernel_ms": seed_avg_ms, "algorithmic_bytes_per_read": bytes_per_read,
+                         "random_access_peak": rand64, "frac_of_random_access": achieved / rand64 if rand64 else None,
+                         "random_access_note": "dependent 64 B gathers over the whole index, smem_gpu_gather_roofline"},
+            "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
+            "intervals_per_step_per_gpu": int(total), "overflow_reads": int(overflow), "index_build_s": t_index,
+            "blocks_per_sm": g.get_param("blocks_per_sm"), "l2_hot_min_intv": g.get_param("l2_hot_min_intv"),
+        }
+        if probe:
+            out["random_access_probe_gbs"] = probe
+        print(json.dumps(out), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -39,7 +39,7 @@ struct SeedParams {
 	int slot_cap;
 	int *counts;             // [n] exact interval count per read (even when > slot_cap)
 	int *overflow_list;      // read ids with count > slot_cap
-	int *status;             // [0] work counter, [1] n_overflow, [2] guard trips
+	int *status;             // [0] work counter, [1] n_overflow, [2] guard trips, [3] largest overflowing count
 	Intv *scratch;           // per-thread: 4 arrays of scratch_cap entries
 	int scratch_cap;
 	int split_len_init, split_width, start_width;

@@ -72,7 +72,7 @@ struct smem_gpu {
 	int max_len = 0;
 	int64_t staged = -1;
 	bool ran = false;
-	int block_threads = SEED_BLOCK, blocks_per_sm = 4, slot_cap = 32;
+	int block_threads = SEED_BLOCK, blocks_per_sm = 4, slot_cap = 64;
 	int64_t hot_min_intv = 0;
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
 	std::string err;
@@ -276,16 +276,13 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	if (n_over > 0) {
 		// Reads whose interval list outgrew their slot are seeded again into slots of the worst-case
 		// size a read of max_len bases can produce per the counts just measured.
-		std::vector<int> list(n_over), cnt(n_over);
+		// The list is sorted on the host so that the re-run is deterministic; the slot size is the
+		// largest count the first pass measured (status[3]), so the second pass cannot overflow.
+		std::vector<int> list(n_over);
 		CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
 		CK(cudaStreamSynchronize(d.stream));
 		std::sort(list.begin(), list.end());
-		int big_cap = 0;
-		for (int k = 0; k < n_over; ++k) {
-			CK(cudaMemcpyAsync(&cnt[k], d.d_counts + list[k], 4, cudaMemcpyDeviceToHost, d.stream));
-		}
-		CK(cudaStreamSynchronize(d.stream));
-		for (int k = 0; k < n_over; ++k) big_cap = std::max(big_cap, cnt[k]);
+		const int big_cap = d.h_status[3];
 		const size_t need_big = (size_t)n_over * big_cap;
 		if (need_big > d.big_entries) {
 			if (d.d_big) CK(cudaFree(d.d_big));

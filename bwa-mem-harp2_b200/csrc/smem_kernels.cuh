@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				while (start < len && q[start] > 3) ++start;
 				if (start >= len) {
 					p.counts[rk] = n_out;
-					if (n_out > p.slot_cap) p.overflow_list[atomicAdd(&p.status[1], 1)] = rid;
+					if (n_out > p.slot_cap) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_out); }
 					phase = PH_NEED_READ;
 					break;
 				}
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					for (int e = n_mem - 1, o = 0; e >= 0; --e, ++o)             // bwt.c:829: ascending start
 						if (o < p.slot_cap) { const Intv v = ld_intv(&M1[e]); st_intv(&slot[o], v.x0, v.x1, v.x2, v.info); }
 					p.counts[rk] = n_mem; p.ret[rid] = ret;
-					if (n_mem > p.slot_cap) p.overflow_list[atomicAdd(&p.status[1], 1)] = rid;
+					if (n_mem > p.slot_cap) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_mem); }
 					phase = PH_NEED_READ;
 					break;
 				}
