@@ -1,16 +1,25 @@
 // smem_device.cuh -- device side of the SMEM seeding path (sm_100a).
 //
 // What is computed (bit-exact with the reference's CPU code, see oracle/smem_oracle.c):
-//   occ_in_block  <- bwt_occ4      bwt.c:187-204
-//   extend        <- bwt_extend    bwt.c:416-429 (bwt_2occ4 = two occ4, bwt.c:213-214)
+//   occ_half      <- bwt_occ4      bwt.c:187-204
+//   extend_pair   <- bwt_extend    bwt.c:416-429 (bwt_2occ4 = two occ4, bwt.c:213-214)
 //   seed_kernel   <- bwt_smem1     bwt.c:776-835, smem_next2 bwamem.c:244-305,
 //                    enumeration loop of mem_insert_seed bwamem.c:453-460
 //
-// How: one read per thread, but written as a *state machine whose every iteration performs
-// exactly one bwt_extend*.  All lanes of a warp therefore re-converge on the expensive part
-// (two 64-byte occ-block gathers + popcounts) no matter which read / pass / direction each lane
-// is in; only the cheap bookkeeping between extends diverges.  Threads are persistent and pull
-// read indices from a global counter (the AFU's free-PE dispatch, afu_core.v:3375-3440).
+// Hardware facts this design follows (measured with smem_gpu_gather_roofline):
+//   * random gathers over the 3.1 GB index are bound by the NUMBER of DRAM-missing requests
+//     (~38 G/s on a B200) and not by their size up to 128 B: a 64-byte occ block fetched as two
+//     per-lane 32-byte loads costs two requests (1.23 TB/s), fetched by two adjacent lanes in one
+//     instruction it costs one (2.45 TB/s);
+//   * so one read is carried by a PAIR of lanes, each loading one 32-byte sector of the same
+//     64-byte block in the same LDG.256: one request per block, one or two blocks per bwt_extend.
+//
+// Device layout of the index ("split bit-plane" block, produced by repack_kernel at upload from the
+// unmodified bwt_t::bwt): per 128 symbols still one 64-byte block, but arranged so that both lanes of
+// a pair do half of the popcount work and nothing has to be shifted into place:
+//   sector h (h = 0,1) = { uint64 cnt[2h], uint64 cnt[2h+1],      checkpoints of bases 2h, 2h+1
+//                          uint32 hi[2], uint32 lo[2] }            bit planes of symbols 64h .. 64h+63
+//   (symbol i of the half lives in bit 31-(i&31) of word i>>5; hi = bit 1, lo = bit 0 of the 2-bit code).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -18,8 +27,10 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
+#define FULL_MASK 0xffffffffu
+
 struct DevIndex {
-	const uint4 *blk;   // bwt_t::bwt viewed as 64-byte occ blocks (padded copy in HBM)
+	const uint4 *blk;   // re-packed 64-byte occ blocks in HBM
 	u64 primary;
 	u64 L2[5];
 	u64 seq_len;
@@ -40,8 +51,11 @@ struct SeedParams {
 	int *counts;             // [n] exact interval count per read (even when > slot_cap)
 	int *overflow_list;      // read ids with count > slot_cap
 	int *status;             // [0] work counter, [1] n_overflow, [2] guard trips, [3] largest overflowing count
-	Intv *scratch;           // per-thread: 4 arrays of scratch_cap entries
+	Intv *scratch;           // per lane pair: M1, M2, BX arrays of scratch_cap entries each (global, L2-resident)
 	int scratch_cap;
+	int b_cap;               // entries of the prev/curr array kept in shared memory per read (rest spills to BX)
+	int q_stride;            // bytes of shared memory per staged query (multiple of 16)
+	int pair_stride;         // bytes of shared memory per lane pair
 	int split_len_init, split_width, start_width;
 	u64 hot_min_intv;        // 0 = off; L2 evict_last hint for occ blocks of intervals >= this size
 };
@@ -49,28 +63,19 @@ struct SeedParams {
 // ---------------------------------------------------------------------------------------------
 // memory helpers
 
-// One 64-byte occ block as two 32-byte sectors (256-bit loads, new on sm_100), read-only path,
-// no L1 allocation: these lines are never re-used by the same SM before eviction.
-struct OccBlock { u32 w[16]; };
-
-__device__ __forceinline__ void ld_block(OccBlock &b, const uint4 *p)
+// One 32-byte sector of an occ block per lane: 256-bit load (new on sm_100), read-only path, no L1
+// allocation (a block is never re-used by the same SM before eviction).
+__device__ __forceinline__ void ld_sector(u32 (&w)[8], const uint4 *p)
 {
 	asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
+	             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
 	             : "l"(p));
-	asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=r"(b.w[8]), "=r"(b.w[9]), "=r"(b.w[10]), "=r"(b.w[11]), "=r"(b.w[12]), "=r"(b.w[13]), "=r"(b.w[14]), "=r"(b.w[15])
-	             : "l"(p + 2));
 }
-
-__device__ __forceinline__ void ld_block_hot(OccBlock &b, const uint4 *p, u64 policy)
+__device__ __forceinline__ void ld_sector_hot(u32 (&w)[8], const uint4 *p, u64 policy)
 {
 	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-	             : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
+	             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
 	             : "l"(p), "l"(policy));
-	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-	             : "=r"(b.w[8]), "=r"(b.w[9]), "=r"(b.w[10]), "=r"(b.w[11]), "=r"(b.w[12]), "=r"(b.w[13]), "=r"(b.w[14]), "=r"(b.w[15])
-	             : "l"(p + 2), "l"(policy));
 }
 
 __device__ __forceinline__ Intv ld_intv(const Intv *p)
@@ -88,71 +93,113 @@ __device__ __forceinline__ void st_intv(Intv *p, u64 x0, u64 x1, u64 x2, u64 inf
 	q[1] = make_ulonglong2(x2, info);
 }
 
-// ---------------------------------------------------------------------------------------------
-// occ: counts of C,G,T (and by difference A) among the first r symbols (1..128) of a block.
-// Two words are merged before each popcount (the bit planes only occupy even bit positions),
-// so a block costs 12 POPC instead of the LUT walk of bwt.c:200-203.
-struct Cnt4 { u32 c[4]; };
-
-__device__ __forceinline__ Cnt4 occ_in_block(const OccBlock &b, u32 r)
+// Shared memory through 32-bit shared-space addresses (keeps the generic->shared window arithmetic
+// out of the hot loop).
+__device__ __forceinline__ u32 lds_u8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds_i32(u32 a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_i32(u32 a, int v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(u32 a)
 {
-	u32 nh = 0, nl = 0, nt = 0;
-#pragma unroll
-	for (int j = 0; j < 8; j += 2) {
-		int ta = (int)r - 16 * j, tb = ta - 16;
-		ta = max(min(ta, 16), 0); tb = max(min(tb, 16), 0);
-		// mask keeping the top `t` symbols of a word (first symbol lives in bits 31:30)
-		u32 ma = __funnelshift_rc(0u, 0xffffffffu, 2 * ta), mb = __funnelshift_rc(0u, 0xffffffffu, 2 * tb);
-		u32 va = b.w[8 + j] & ma, vb = b.w[9 + j] & mb;
-		u32 ha = (va >> 1) & 0x55555555u, la = va & 0x55555555u;
-		u32 hb = vb & 0xaaaaaaaau, lb = (vb << 1) & 0xaaaaaaaau;
-		nh += __popc(ha | hb);
-		nl += __popc(la | lb);
-		nt += __popc((ha & la) | (hb & lb));
-	}
-	Cnt4 o;
-	o.c[3] = nt; o.c[2] = nh - nt; o.c[1] = nl - nt; o.c[0] = r - nh - nl + nt;
-	return o;
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void sts_v4(u32 a, uint4 v)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ __forceinline__ u64 blk_base(const OccBlock &b, int c) { return (u64)b.w[2 * c] | ((u64)b.w[2 * c + 1] << 32); }
+// prev/curr entries in shared memory: 16 bytes when every coordinate fits 36 bits (seq_len < 2^36,
+// i.e. any genome bwa can index in practice) and the read is shorter than 2^20, else 32 bytes.
+template <bool WIDE> struct BEntry;
+template <> struct BEntry<false> {
+	static const int BYTES = 16;
+	static __device__ __forceinline__ void put(u32 addr, u64 x0, u64 x1, u64 x2, u32 end)
+	{
+		sts_v4(addr, make_uint4((u32)x0, (u32)x1, (u32)x2,
+		                        ((u32)(x0 >> 32) & 15u) | (((u32)(x1 >> 32) & 15u) << 4) | (((u32)(x2 >> 32) & 15u) << 8) | (end << 12)));
+	}
+	static __device__ __forceinline__ void get(u32 addr, u64 &x0, u64 &x1, u64 &x2, u32 &end)
+	{
+		const uint4 t = lds_v4(addr);
+		x0 = (u64)t.x | ((u64)(t.w & 15u) << 32);
+		x1 = (u64)t.y | ((u64)((t.w >> 4) & 15u) << 32);
+		x2 = (u64)t.z | ((u64)((t.w >> 8) & 15u) << 32);
+		end = t.w >> 12;
+	}
+};
+template <> struct BEntry<true> {
+	static const int BYTES = 32;
+	static __device__ __forceinline__ void put(u32 addr, u64 x0, u64 x1, u64 x2, u32 end)
+	{
+		sts_v4(addr, make_uint4((u32)x0, (u32)(x0 >> 32), (u32)x1, (u32)(x1 >> 32)));
+		sts_v4(addr + 16, make_uint4((u32)x2, (u32)(x2 >> 32), end, 0u));
+	}
+	static __device__ __forceinline__ void get(u32 addr, u64 &x0, u64 &x1, u64 &x2, u32 &end)
+	{
+		const uint4 lo = lds_v4(addr), hi = lds_v4(addr + 16);
+		x0 = (u64)lo.x | ((u64)lo.y << 32);
+		x1 = (u64)lo.z | ((u64)lo.w << 32);
+		x2 = (u64)hi.x | ((u64)hi.y << 32);
+		end = hi.z;
+	}
+};
 
-// Result of extending an interval by base c (only the chosen base is materialised).
+// ---------------------------------------------------------------------------------------------
+// occ: counts of A,C,G,T among the first r (0..64) symbols of this lane's half block, packed one
+// byte per base.  w[4..5] = hi plane, w[6..7] = lo plane.  6 POPC, no shifting of data.
+__device__ __forceinline__ u32 occ_half(const u32 (&w)[8], int r)
+{
+	const u32 m0 = __funnelshift_rc(0u, 0xffffffffu, r);                 // top min(r,32) bits
+	const u32 m1 = __funnelshift_rc(0u, 0xffffffffu, max(r - 32, 0));
+	const u32 h0 = w[4] & m0, h1 = w[5] & m1, l0 = w[6] & m0, l1 = w[7] & m1;
+	const u32 nh = __popc(h0) + __popc(h1), nl = __popc(l0) + __popc(l1), nt = __popc(h0 & l0) + __popc(h1 & l1);
+	// T = hi&lo, G = hi&~lo, C = ~hi&lo, A = the rest of the r symbols
+	return ((u32)r - nh - nl + nt) | ((nl - nt) << 8) | ((nh - nt) << 16) | (nt << 24);
+}
+
 struct Ext { u64 a, b, s; };   // a = x[!is_back], b = x[is_back], s = x[2]
 
-// bwt_extend for one chosen base c: in (a = x[!is_back], b = x[is_back], s = x[2]).
-__device__ __forceinline__ Ext extend(const DevIndex &ix, u64 a, u64 b, u64 s, int c, u64 hot_min, u64 policy)
+// bwt_extend for one chosen base c, executed by a converged warp of lane pairs (half = lane & 1).
+// in: (a = x[!is_back], b = x[is_back], s = x[2], c) identical in both lanes of a pair; out likewise.
+__device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 policy)
 {
-	u64 k = a - 1, l = a - 1 + s;
-	u64 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);   // '$' is not stored (bwt.c:194)
-	u64 bk = kk >> 7, bl = ll >> 7;
-	OccBlock K, L;
+	const u64 k = a - 1, l = a - 1 + s;
+	const u64 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);   // '$' is not stored (bwt.c:194)
+	const u64 bk = kk >> 7, bl = ll >> 7;
 	const bool same = bk == bl;
+	u32 w[8], v[8];
+	const uint4 *pk = ix.blk + bk * 4 + half * 2, *pl = ix.blk + bl * 4 + half * 2;
 	if (hot_min && s >= hot_min) {
-		ld_block_hot(K, ix.blk + bk * 4, policy);
-		if (!same) ld_block_hot(L, ix.blk + bl * 4, policy);
+		ld_sector_hot(w, pk, policy);
+		if (!same) ld_sector_hot(v, pl, policy);
 	} else {
-		ld_block(K, ix.blk + bk * 4);
-		if (!same) ld_block(L, ix.blk + bl * 4);
+		ld_sector(w, pk);
+		if (!same) ld_sector(v, pl);
 	}
-	Cnt4 ck = occ_in_block(K, (u32)(kk & 127) + 1);
-	if (same) L = K;
-	Cnt4 cl = occ_in_block(L, (u32)(ll & 127) + 1);
-	u64 sz[4], tk_c = 0;
+	if (same) {
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		u64 tk = blk_base(K, j) + ck.c[j], tl = blk_base(L, j) + cl.c[j];
-		sz[j] = tl - tk;
-		if (j == c) tk_c = tk;
+		for (int j = 0; j < 8; ++j) v[j] = w[j];
 	}
+	// symbols 0..kk&127 (inclusive) of the block count; this lane owns symbols 64*half .. 64*half+63
+	const int rk = min(max((int)(kk & 127) + 1 - 64 * half, 0), 64), rl = min(max((int)(ll & 127) + 1 - 64 * half, 0), 64);
+	u32 ck = occ_half(w, rk), cl = occ_half(v, rl);
+	ck += __shfl_xor_sync(FULL_MASK, ck, 1);          // whole-block counts (each byte <= 128)
+	cl += __shfl_xor_sync(FULL_MASK, cl, 1);
+	// this lane owns bases j0 = 2*half and j0 + 1
+	const int j0 = 2 * half;
+	const u64 tk0 = ((u64)w[0] | ((u64)w[1] << 32)) + ((ck >> (8 * j0)) & 0xffu), tk1 = ((u64)w[2] | ((u64)w[3] << 32)) + ((ck >> (8 * j0 + 8)) & 0xffu);
+	const u64 tl0 = ((u64)v[0] | ((u64)v[1] << 32)) + ((cl >> (8 * j0)) & 0xffu), tl1 = ((u64)v[2] | ((u64)v[3] << 32)) + ((cl >> (8 * j0 + 8)) & 0xffu);
+	const u64 sz0 = tl0 - tk0, sz1 = tl1 - tk1;
+	// other strand: bases are laid out T,G,C,A after the optional '$' (bwt.c:425-428): sum the sizes of bases > c
+	u64 acc = (j0 > c ? sz0 : 0) + (j0 + 1 > c ? sz1 : 0);
+	acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+	const u64 tkc = (c & 1) ? tk1 : tk0, szc = (c & 1) ? sz1 : sz0;       // valid in the lane that owns base c
+	const int owner = (lane & ~1) | (c >> 1);
 	Ext o;
-	// other strand: bases are laid out T,G,C,A after the optional '$' (bwt.c:425-428)
-	u64 acc = b + ((a <= ix.primary && a + s - 1 >= ix.primary) ? 1 : 0);
-	if (c < 3) acc += sz[3];
-	if (c < 2) acc += sz[2];
-	if (c < 1) acc += sz[1];
-	o.b = acc;
-	o.s = c == 0 ? sz[0] : c == 1 ? sz[1] : c == 2 ? sz[2] : sz[3];
-	o.a = ix.L2[c] + 1 + tk_c;
+	o.a = ix.L2[c] + 1 + __shfl_sync(FULL_MASK, tkc, owner);
+	o.s = __shfl_sync(FULL_MASK, szc, owner);
+	o.b = b + ((a <= ix.primary && a + s - 1 >= ix.primary) ? 1 : 0) + acc;
 	return o;
 }

@@ -23,6 +23,7 @@ typedef thrust::transform_iterator<CastI2L, const int *, long long> CountIter;
 
 struct DeviceCtx {
 	int dev = 0, sm_count = 0;
+	size_t smem_per_sm = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 	// index
@@ -72,8 +73,10 @@ struct smem_gpu {
 	int max_len = 0;
 	int64_t staged = -1;
 	bool ran = false;
-	int block_threads = SEED_BLOCK, blocks_per_sm = 4, slot_cap = 64;
+	int block_threads = SEED_BLOCK, blocks_per_sm = 8, slot_cap = 64, b_cap = 20;
 	int64_t hot_min_intv = 0;
+	int probe_variant = 0;
+	int force_wide = 0;
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
 	std::string err;
 };
@@ -104,6 +107,7 @@ int ctx_init(DeviceCtx &d, int dev, int64_t read_cap, int max_len, int slot_cap)
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, dev));
 	d.sm_count = prop.multiProcessorCount;
+	d.smem_per_sm = prop.sharedMemPerMultiprocessor;
 	CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&d.ev0)); CK(cudaEventCreate(&d.ev1)); CK(cudaEventCreate(&d.ev2));
 	d.read_cap = read_cap;
@@ -146,21 +150,34 @@ void ctx_free(DeviceCtx &d)
 	if (d.stream) cudaStreamDestroy(d.stream);
 }
 
-// The copy in HBM is padded to whole 64-byte blocks plus one spare block so that the two
-// 32-byte sector loads of the last (truncated, bwtindex.c:145-147) block never leave the allocation.
+// The index lives in HBM as re-packed 64-byte blocks (see smem_device.cuh); the packed bwt_t::bwt the
+// caller hands over is staged in a temporary device buffer and re-arranged by repack_kernel, once.
 int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 {
 	CK(cudaSetDevice(d.dev));
+	const u64 n_blocks = (ix->seq_len + 127) / 128;
+	const u64 last_words = ((ix->seq_len - (n_blocks - 1) * 128) + 15) / 16;
+	if (ix->seq_len == 0 || ix->bwt_size < (n_blocks - 1) * 16 + 8 + last_words) { d.err = "bwt_size is inconsistent with seq_len"; return SMEM_GPU_E_ARG; }
 	const size_t bytes = (size_t)ix->bwt_size * 4;
-	const size_t padded = ((bytes + 63) / 64 + 1) * 64;
+	const size_t out_bytes = (size_t)(n_blocks + 1) * 64;            // one spare block keeps idle lanes in bounds
 	if (d.d_index) { CK(cudaFree(d.d_index)); d.d_index = nullptr; }
-	CK(cudaMalloc((void **)&d.d_index, padded));
-	CK(cudaMemsetAsync((char *)d.d_index + (padded - 128), 0, 128, d.stream));
-	if (src_device < 0) CK(cudaMemcpyAsync(d.d_index, ix->bwt, bytes, cudaMemcpyHostToDevice, d.stream));
-	else if (src_device == d.dev) CK(cudaMemcpyAsync(d.d_index, ix->bwt, bytes, cudaMemcpyDeviceToDevice, d.stream));
-	else CK(cudaMemcpyPeerAsync(d.d_index, d.dev, ix->bwt, src_device, bytes, d.stream));
+	d.has_index = false;
+	CK(cudaMalloc((void **)&d.d_index, out_bytes));
+	CK(cudaMemsetAsync((char *)d.d_index + out_bytes - 64, 0, 64, d.stream));
+	const u32 *src = nullptr;
+	u32 *tmp = nullptr;
+	if (src_device == d.dev) src = ix->bwt;
+	else {
+		CK(cudaMalloc((void **)&tmp, bytes + 64));
+		if (src_device < 0) CK(cudaMemcpyAsync(tmp, ix->bwt, bytes, cudaMemcpyHostToDevice, d.stream));
+		else CK(cudaMemcpyPeerAsync(tmp, d.dev, ix->bwt, src_device, bytes, d.stream));
+		src = tmp;
+	}
+	repack_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, d.stream>>>(src, n_blocks, ix->seq_len, d.d_index);
+	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(d.stream));
-	d.index_bytes = bytes;
+	if (tmp) CK(cudaFree(tmp));
+	d.index_bytes = (size_t)n_blocks * 64;
 	d.ix.blk = d.d_index;
 	d.ix.primary = ix->primary;
 	for (int i = 0; i < 5; ++i) d.ix.L2[i] = ix->L2[i];
@@ -188,21 +205,33 @@ int ctx_stage(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32
 	return 0;
 }
 
-template <int MODE>
-int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid)
+template <int MODE, bool WIDE>
+int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem)
 {
+#define LAUNCH(B)                                                                                                        \
+	do {                                                                                                                 \
+		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+		seed_kernel<MODE, B, WIDE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
+	} while (0)
 	switch (blocks_per_sm) {
-	case 4: seed_kernel<MODE, 4><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
-	case 5: seed_kernel<MODE, 5><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
-	case 6: seed_kernel<MODE, 6><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
-	case 8: seed_kernel<MODE, 8><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
-	case 10: seed_kernel<MODE, 10><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
-	case 12: seed_kernel<MODE, 12><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
-	default: seed_kernel<MODE, 3><<<grid, SEED_BLOCK, 0, d.stream>>>(p); break;
+	case 4: LAUNCH(4); break;
+	case 5: LAUNCH(5); break;
+	case 6: LAUNCH(6); break;
+	case 8: LAUNCH(8); break;
+	case 10: LAUNCH(10); break;
+	case 12: LAUNCH(12); break;
+	default: LAUNCH(3); break;
 	}
+#undef LAUNCH
 	CK(cudaGetLastError());
 	++d.launches;
 	return 0;
+}
+
+template <int MODE>
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide)
+{
+	return wide ? launch_seed_w<MODE, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false>(d, p, blocks_per_sm, grid, smem);
 }
 
 int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *opt)
@@ -213,9 +242,23 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	if (!d.has_index) { d.err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
 	const int bps = h.blocks_per_sm;
 	const int max_grid = d.sm_count * bps;
-	const int grid = (int)std::min<int64_t>(max_grid, (d.n + SEED_BLOCK - 1) / SEED_BLOCK);
+	const int pairs_per_cta = SEED_BLOCK / 2;
+	const int grid = (int)std::min<int64_t>(max_grid, (d.n + pairs_per_cta - 1) / pairs_per_cta);
 	const int scratch_cap = h.max_len + 2;
-	const size_t need = (size_t)max_grid * SEED_BLOCK * 4 * scratch_cap;
+	const size_t need = (size_t)max_grid * pairs_per_cta * 3 * scratch_cap;
+	// 16-byte packed prev/curr entries need every SA coordinate < 2^36 and read positions < 2^20
+	const bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
+	const int q_stride = (h.max_len + 15) / 16 * 16;
+	const size_t smem_budget = (size_t)(d.smem_per_sm / bps) - 1024;            // per CTA, leaving the driver's reserve
+	const size_t entry = wide ? 32 : 16;
+	int b_cap = h.b_cap;
+	if ((size_t)pairs_per_cta * (COLD_BYTES + b_cap * entry + q_stride) > smem_budget) {
+		const long long fit = ((long long)(smem_budget / pairs_per_cta) - q_stride - COLD_BYTES) / (long long)entry;
+		if (fit < 2) { d.err = "read length too large for the shared-memory staging at this blocks_per_sm"; return SMEM_GPU_E_CAPACITY; }
+		b_cap = (int)fit;
+	}
+	const int pair_stride = (int)(COLD_BYTES + q_stride + b_cap * entry);
+	const size_t smem = (size_t)pairs_per_cta * pair_stride;
 	if (need > d.scratch_entries) {
 		if (d.d_scratch) CK(cudaFree(d.d_scratch));
 		d.d_scratch = nullptr; d.scratch_entries = 0;
@@ -237,6 +280,7 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	p.slots = d.d_slots; p.slot_cap = h.slot_cap;
 	p.counts = d.d_counts; p.overflow_list = d.d_overflow; p.status = d.d_status;
 	p.scratch = d.d_scratch; p.scratch_cap = scratch_cap;
+	p.b_cap = b_cap; p.q_stride = q_stride; p.pair_stride = pair_stride;
 	if (opt) {
 		p.split_len_init = (int)(opt->min_seed_len * opt->split_factor + .499);   // bwamem.c:456, the path's only FP
 		p.split_width = opt->split_width; p.start_width = opt->start_width;
@@ -246,7 +290,7 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	CK(cudaEventRecord(d.ev0, d.stream));
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
-	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid) : launch_seed<MODE_SMEM1>(d, p, bps, grid);
+	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
 	CountIter it((const int *)d.d_counts, CastI2L());
@@ -301,8 +345,8 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 		SeedParams p2 = p;
 		p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
 		p2.overflow_list = d.d_overflow + n_over;   // unused: big_cap is exact
-		const int grid2 = (int)std::min<int64_t>(max_grid, (n_over + SEED_BLOCK - 1) / SEED_BLOCK);
-		rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2);
+		const int grid2 = (int)std::min<int64_t>(max_grid, (n_over + pairs_per_cta - 1) / pairs_per_cta);
+		rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide);
 		if (rc) return rc;
 		const long long threads = (long long)n_over * big_cap;
 		compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
@@ -522,7 +566,15 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 		return SMEM_GPU_E_ARG;
 	}
 	if (!strcmp(name, "slot_cap")) { if (v < 1 || v > 4096) return SMEM_GPU_E_ARG; h->slot_cap = (int)v; return 0; }
+	if (!strcmp(name, "force_wide")) { h->force_wide = v != 0; return 0; }
+	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
+	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
+	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
+		if (v != 32 && v != 64 && v != 128) return SMEM_GPU_E_ARG;
+		for (auto &d : h->devs) { cudaSetDevice(d.dev); if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) != cudaSuccess) return SMEM_GPU_E_CUDA; }
+		return 0;
+	}
 	return SMEM_GPU_E_ARG;
 }
 
@@ -532,15 +584,17 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "block_threads")) return h->block_threads;
 	if (!strcmp(name, "blocks_per_sm")) return h->blocks_per_sm;
 	if (!strcmp(name, "slot_cap")) return h->slot_cap;
+	if (!strcmp(name, "b_cap")) return h->b_cap;
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
+	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }
 	if (!strcmp(name, "n_devices")) return (int64_t)h->devs.size();
 	return SMEM_GPU_E_ARG;
 }
 
 int smem_gpu_gather_roofline(smem_gpu_t *h, int block_bytes, uint64_t span_bytes, int chains_per_sm, int steps, double *gbps_out)
 {
-	if (!h || !gbps_out || (block_bytes != 32 && block_bytes != 64) || chains_per_sm < 256 || steps < 1) return SMEM_GPU_E_ARG;
+	if (!h || !gbps_out || (block_bytes != 32 && block_bytes != 64 && block_bytes != 128) || chains_per_sm < 256 || steps < 1) return SMEM_GPU_E_ARG;
 	DeviceCtx &d = h->devs[0];
 	if (!d.has_index) { h->err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
 	auto body = [&]() -> int {
@@ -551,15 +605,34 @@ int smem_gpu_gather_roofline(smem_gpu_t *h, int block_bytes, uint64_t span_bytes
 		u64 *sink = (u64 *)d.d_status;
 		for (int rep = 0; rep < 2; ++rep) {   // first pass warms the TLB / instruction cache
 			CK(cudaEventRecord(d.ev0, d.stream));
-			if (block_bytes == 64) gather_probe_kernel<64><<<grid, 256, 0, d.stream>>>(d.d_index, units, steps, sink);
-			else gather_probe_kernel<32><<<grid, 256, 0, d.stream>>>(d.d_index, units, steps, sink);
+#define PROBE(B, V) gather_probe_kernel<B, V><<<grid, 256, 0, d.stream>>>(d.d_index, units, steps, sink)
+#define PROBE_B(V) (block_bytes == 32 ? PROBE(32, V) : block_bytes == 64 ? PROBE(64, V) : PROBE(128, V))
+#define COOP(L, W) gather_probe_coop_kernel<L, W><<<grid, 256, 0, d.stream>>>(d.d_index, span_bytes / (L * W), steps, sink)
+			switch (h->probe_variant) {
+			case 10: COOP(2, 32); break;    // 64 B units, 2 lanes x 256-bit
+			case 11: COOP(4, 16); break;    // 64 B units, 4 lanes x 128-bit
+			case 12: COOP(4, 32); break;    // 128 B units
+			case 13: COOP(8, 16); break;    // 128 B units
+			case 14: COOP(2, 16); break;    // 32 B units
+			case 15: COOP(8, 32); break;    // 256 B units
+			case 1: PROBE_B(1); break;
+			case 2: PROBE_B(2); break;
+			case 3: PROBE_B(3); break;
+			case 4: PROBE_B(4); break;
+			default: PROBE_B(0); break;
+			}
+#undef PROBE_B
+#undef COOP
+#undef PROBE
 			CK(cudaGetLastError());
 			CK(cudaEventRecord(d.ev1, d.stream));
 			CK(cudaStreamSynchronize(d.stream));
 		}
 		float ms = 0;
 		CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
-		*gbps_out = (double)grid * 256.0 * steps * block_bytes / (ms * 1e-3) / 1e9;
+		double per_thread = block_bytes;
+		switch (h->probe_variant) { case 10: case 12: case 15: per_thread = 32; break; case 11: case 13: case 14: per_thread = 16; break; default: break; }
+		*gbps_out = (double)grid * 256.0 * steps * per_thread / (ms * 1e-3) / 1e9;
 		return 0;
 	};
 	int rc = body();

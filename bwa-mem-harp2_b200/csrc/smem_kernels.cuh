@@ -3,225 +3,293 @@
 #include "smem_device.cuh"
 
 enum { MODE_COLLECT = 0, MODE_SMEM1 = 1 };
-enum { PH_NEED_READ = 0, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD, PH_FWD_DONE, PH_BWD, PH_CALL_DONE, PH_EXIT };
+// hot phases first: the main loop only ever extends in PH_FWD / PH_BWD
+enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
 
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index rides in info bits 48..63
-#define SEED_BLOCK 128       // threads per CTA of the seeding kernel
+#define SEED_BLOCK 128       // threads per CTA of the seeding kernel (= 64 lane pairs = 64 reads in flight)
 
-// One persistent thread = one read at a time.  Per-thread scratch (global, L1/L2 cached):
-//   B0, B1 : prev/curr ping-pong of bwt_smem1 (B0 also receives the forward pass' pushes)
-//   M1, M2 : `matches` / `sub` of smem_next2 in emission order (descending start)
-// each of `scratch_cap` = max_read_len + 2 entries, which bounds every list of bwt.c:776-835
-// (forward pushes <= len - x, backward emissions <= x + 2), so there is no overflow path.
-template <int MODE, int MIN_BLOCKS>
+// per-pair shared memory: [cold state | query bytes | B entries]
+enum { CS_RK = 0, CS_RID = 4, CS_START = 8, CS_STEP = 12, CS_ORI = 16, CS_SPLIT = 20, CS_NOUT = 24, CS_PASS = 28, CS_X = 32,
+       CS_NMEM = 36, CS_LMS = 40, CS_NM1 = 44, CS_KEEP = 48, CS_MAXLEN = 52, CS_MAXSTART = 56, CS_MAXEND = 60, CS_MAXS_LO = 64,
+       CS_MAXS_HI = 68, CS_RET = 72, COLD_BYTES = 80 };
+
+// One persistent LANE PAIR = one read at a time (see smem_device.cuh for why a pair).  Both lanes run
+// the same state machine on identical state; they differ only in which sector of an occ block they
+// load and which two bases they account for.  Every trip of the main loop performs exactly one
+// bwt_extend for every pair of the warp, whatever read / pass / direction each pair is in; rare
+// transitions (next read, next smem_next2 step, call set-up, merge) run in a divergent cold section
+// whose state lives in shared memory so that the hot loop stays small.
+//
+// Per-read storage:
+//   shared : cold state, q[len] (the staged query), B[b_cap] = prev/curr of bwt_smem1 compacted IN
+//            PLACE (curr[n] is written at or behind the prev[j] just consumed, so one array serves both,
+//            bwt.c:810-828) and addressed from its top so that "reverse curr" (bwt.c:807) costs nothing;
+//   global : M1, M2 = `matches` / `sub` of smem_next2 in emission order (descending start),
+//            BX = spill of B beyond b_cap (not touched on random references: <= 18 live intervals);
+//            each of scratch_cap = max_read_len + 2 entries, which bounds every list of bwt.c:776-835.
+template <int MODE, int MIN_BLOCKS, bool WIDE>
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
-	const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-	Intv *const B0 = p.scratch + (size_t)gtid * 4 * p.scratch_cap;
-	Intv *const B1 = B0 + p.scratch_cap, *const M1 = B1 + p.scratch_cap, *const M2 = M1 + p.scratch_cap;
+	typedef BEntry<WIDE> BE;
+	extern __shared__ uint4 smem_raw[];
+	const int lane = threadIdx.x & 31, half = lane & 1;
+	const int pair = threadIdx.x >> 1;
+	const int gpair = blockIdx.x * (SEED_BLOCK / 2) + pair;
+	const u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;   // this pair's shared memory
+	const u32 sq = sp + COLD_BYTES, sb = sq + (u32)p.q_stride;
+	Intv *const M1 = p.scratch + (size_t)gpair * 3 * p.scratch_cap;
+	Intv *const BX = M1 + 2 * p.scratch_cap;
 
 	u64 policy = 0;
 	if (p.hot_min_intv) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
 
+	auto b_put = [&](int idx, u64 x0, u64 x1, u64 x2, u32 end) {
+		if (idx < p.b_cap) BE::put(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		else st_intv(&BX[idx], x0, x1, x2, (u64)end);
+	};
+	auto b_get = [&](int idx, u64 &x0, u64 &x1, u64 &x2, u32 &end) {
+		if (idx < p.b_cap) BE::get(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		else { const Intv t = ld_intv(&BX[idx]); x0 = t.x0; x1 = t.x1; x2 = t.x2; end = (u32)t.info; }
+	};
+	// bwt.c:815-820: a hit that cannot be extended is recorded unless a longer match already covers it
+	auto emit = [&](u64 x0, u64 x1, u64 x2, u32 end, int st) {
+		const int n_mem = lds_i32(sp + CS_NMEM);
+		if (n_mem == 0 || st < lds_i32(sp + CS_LMS)) {
+			Intv *M = M1 + (size_t)lds_i32(sp + CS_PASS) * p.scratch_cap;
+			st_intv(&M[n_mem], x0, x1, x2, (u64)end | ((u64)st << 32));
+			sts_i32(sp + CS_NMEM, n_mem + 1);
+			sts_i32(sp + CS_LMS, st);
+			const int l = (int)end - st;
+			if (l >= lds_i32(sp + CS_MAXLEN)) {          // ">=": the first maximum in ascending start order wins (bwamem.c:266-270)
+				sts_i32(sp + CS_MAXLEN, l); sts_i32(sp + CS_MAXSTART, st); sts_i32(sp + CS_MAXEND, (int)end);
+				sts_i32(sp + CS_MAXS_LO, (int)(u32)x2); sts_i32(sp + CS_MAXS_HI, (int)(u32)(x2 >> 32));
+			}
+		}
+	};
+
+	// ---- hot state (registers)
 	int phase = PH_NEED_READ;
-	// ---- per-read state
-	int rk = 0, rid = 0;                 // position in the work list, read id
-	const uint8_t *q = nullptr;
-	int len = 0, start = 0, step = 0, ori_start = 0, split_len = 0, n_out = 0;
-	Intv *slot = nullptr;
-	// ---- per-call state (one bwt_smem1)
-	int pass = 0, x = 0, i = 0, j = 0, n_prev = 0, n_curr = 0, n_mem = 0, ret = 0, cb = -1;
-	u64 min_intv = 1;
-	bool prev_rev = false;
-	Intv *prev = B0, *curr = B1, *M = M1;
-	u64 ka = 0, kb = 0, ks = 0;          // forward ik kept as (a = x[1], b = x[0], s = x[2]): is_back = 0 walks x[1]
-	int kend = 0;
-	u64 last_curr_s = 0;
-	int last_mem_start = 0;
-	int n_m1 = 0, keep_len = 0;          // |matches| and its longest length once pass 0 finished
-	int max_len = 0, max_start = 0, max_end = 0;   // longest SMEM of this call (first max in start order)
-	u64 max_s = 0;
-	Intv pe;                             // current backward element prev[j]
-	pe.x0 = pe.x1 = pe.x2 = pe.info = 0;
-	int guard = 0;
+	u64 a = 1, b = 1, s = 1;             // FWD: ik as (a = x[1], b = x[0]); BWD: prev[j] as (a = x[0], b = x[1])
+	u32 end = 0;                         // info of that interval (query end)
+	int c = 0;                           // base of the pending extend
+	int i = 0, j = 0, n0 = 0, n_prev = 0, n_curr = 0, len = 0, guard = 0;
+	u64 min_intv = 1, last_s = 0;
 
 	for (;;) {
-		// ============================================================== bookkeeping (divergent, cheap)
-		bool req = false;
-		while (!req && phase != PH_EXIT) {
+		__syncwarp();
+		// ============================================================== cold section (divergent between pairs)
+		while (phase > PH_IDLE) {
 			switch (phase) {
 			case PH_NEED_READ: {
-				rk = atomicAdd(&p.status[0], 1);
-				if ((long long)rk >= p.n) { phase = PH_EXIT; break; }
-				rid = p.list ? p.list[rk] : rk;
+				int rk = 0;
+				if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(sp + CS_RK, rk); }
+				__syncwarp(3u << (lane & ~1));
+				rk = lds_i32(sp + CS_RK);
+				if ((long long)rk >= p.n) { phase = PH_IDLE; break; }
+				const int rid = p.list ? p.list[rk] : rk;
 				const long long o0 = p.offs[rid];
-				q = p.seq + o0;
+				const uint8_t *q = p.seq + o0;
 				len = (int)(p.offs[rid + 1] - o0);
-				slot = p.slots + (size_t)rk * p.slot_cap;
-				n_out = 0; start = 0; step = 0;
+				for (int t = half; t < len; t += 2) sts_u8(sq + t, q[t]);     // stage the query in shared memory
+				__syncwarp(3u << (lane & ~1));
+				sts_i32(sp + CS_RID, rid); sts_i32(sp + CS_NOUT, 0); sts_i32(sp + CS_START, 0); sts_i32(sp + CS_STEP, 0);
 				if (MODE == MODE_COLLECT) {
-					split_len = p.split_len_init < len ? p.split_len_init : len;     // bwamem.c:458
+					sts_i32(sp + CS_SPLIT, p.split_len_init < len ? p.split_len_init : len);     // bwamem.c:458
 					phase = PH_NEXT_STEP;
 				} else {
-					x = p.xs[rid];
-					const int mi = p.min_intvs[rid];
-					min_intv = mi < 1 ? 1 : (u64)mi;                                 // bwt.c:784
-					pass = 0; M = M1;
-					if (x < 0 || x >= len || q[x] > 3) {                              // bwt.c:783
+					const int x = p.xs[rid], mi = p.min_intvs[rid];
+					min_intv = mi < 1 ? 1 : (u64)mi;                                              // bwt.c:784
+					sts_i32(sp + CS_PASS, 0); sts_i32(sp + CS_X, x);
+					if (x < 0 || x >= len || lds_u8(sq + x) > 3) {                                // bwt.c:783
 						p.ret[rid] = x + 1; p.counts[rk] = 0; phase = PH_NEED_READ;
 					} else phase = PH_INIT_CALL;
 				}
 			} break;
 			case PH_NEXT_STEP: {     // head of smem_next2, bwamem.c:249-258
-				while (start < len && q[start] > 3) ++start;
+				int start = lds_i32(sp + CS_START);
+				while (start < len && lds_u8(sq + start) > 3) ++start;
 				if (start >= len) {
+					const int rk = lds_i32(sp + CS_RK), n_out = lds_i32(sp + CS_NOUT);
 					p.counts[rk] = n_out;
-					if (n_out > p.slot_cap) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_out); }
+					if (n_out > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sp + CS_RID); atomicMax(&p.status[3], n_out); }
 					phase = PH_NEED_READ;
 					break;
 				}
-				ori_start = start; x = start; pass = 0; M = M1;
+				sts_i32(sp + CS_START, start); sts_i32(sp + CS_ORI, start); sts_i32(sp + CS_X, start); sts_i32(sp + CS_PASS, 0);
 				min_intv = p.start_width < 1 ? 1 : (u64)p.start_width;
 				phase = PH_INIT_CALL;
 			} break;
-			case PH_INIT_CALL: {     // bwt_set_intv, bwt.c:788-789
-				const int c0 = q[x];
-				ka = p.ix.L2[3 - c0] + 1;
-				kb = p.ix.L2[c0] + 1;
-				ks = p.ix.L2[c0 + 1] - p.ix.L2[c0];
-				kend = x + 1;
-				i = x + 1; n_curr = 0; n_mem = 0;
-				max_len = 0; max_start = max_end = 0; max_s = 0;
+			case PH_INIT_CALL: {     // bwt_set_intv, bwt.c:788-789, then the head of the forward loop
+				const int x = lds_i32(sp + CS_X);
+				const int c0 = (int)lds_u8(sq + x);
+				a = p.ix.L2[3 - c0] + 1;             // is_back = 0 walks x[1]
+				b = p.ix.L2[c0] + 1;
+				s = p.ix.L2[c0 + 1] - p.ix.L2[c0];
+				end = (u32)(x + 1);
+				i = x + 1; n_curr = 0;
+				sts_i32(sp + CS_NMEM, 0); sts_i32(sp + CS_MAXLEN, 0); sts_i32(sp + CS_MAXSTART, 0); sts_i32(sp + CS_MAXEND, 0);
+				sts_i32(sp + CS_MAXS_LO, 0); sts_i32(sp + CS_MAXS_HI, 0);
 				guard = 2 * (len + 2) * (len + 2) + 64;   // > every extend one bwt_smem1 can issue
-				phase = PH_FWD;
-			} break;
-			case PH_FWD: {
-				if (i == len || q[i] > 3) {              // bwt.c:800-803 (ambiguous base) / :806 (end of read)
-					st_intv(&B0[n_curr++], kb, ka, ks, (u64)kend);
-					ret = kend;
+				const u32 qv = i < len ? lds_u8(sq + i) : 4u;
+				if (qv > 3) {                             // bwt.c:800-803 (ambiguous base) / :806 (end of read)
+					b_put(n_curr++, b, a, s, end);
+					sts_i32(sp + CS_RET, (int)end);
 					phase = PH_FWD_DONE;
-				} else req = true;
+				} else { c = 3 - (int)qv; phase = PH_FWD; }   // bwt.c:793: forward extension uses the complement
 			} break;
-			case PH_FWD_DONE: {      // bwt.c:807-809: "reverse curr" == walk B0 from its tail
-				if (MODE == MODE_COLLECT && pass == 0) start = ret;   // bwamem.c:262; pass 2 leaves start alone
-				prev = B0; curr = B1; prev_rev = true; n_prev = n_curr; n_curr = 0;
-				i = x - 1; j = 0;
-				cb = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
-				phase = PH_BWD;
+			case PH_FWD_DONE: {      // bwt.c:807-809: "reverse curr" == address B from its top (n0 - 1 - j)
+				if (MODE == MODE_COLLECT && lds_i32(sp + CS_PASS) == 0) sts_i32(sp + CS_START, lds_i32(sp + CS_RET));   // bwamem.c:262
+				n0 = n_curr; n_prev = n_curr; n_curr = 0;
+				i = lds_i32(sp + CS_X) - 1; j = 0;
+				c = i < 0 ? -1 : (int)lds_u8(sq + i);
+				if (c > 3) c = -1;
+				b_get(n0 - 1, a, b, s, end);
+				phase = c < 0 ? PH_BWD_LAST : PH_BWD;
 			} break;
-			case PH_BWD: {
-				pe = ld_intv(&prev[prev_rev ? n_prev - 1 - j : j]);
-				if (cb < 0) {
-					// bwt.c:815-821 with c == -1 (read start or ambiguous base): nothing can enter curr and
-					// only prev[0] can pass the containment test, so the round collapses to this.
-					if (n_mem == 0 || i + 1 < last_mem_start) {
-						st_intv(&M[n_mem++], pe.x0, pe.x1, pe.x2, pe.info | ((u64)(i + 1) << 32));
-						last_mem_start = i + 1;
-						const int l = (int)pe.info - (i + 1);
-						if (l >= max_len) { max_len = l; max_start = i + 1; max_end = (int)pe.info; max_s = pe.x2; }
-					}
-					phase = PH_CALL_DONE;
-				} else req = true;
+			case PH_BWD_LAST: {
+				// bwt.c:815-821 with c == -1 (read start or ambiguous base): nothing can enter curr and only
+				// prev[0] can pass the containment test, so the round collapses to one emission test.
+				emit(a, b, s, end, i + 1);
+				phase = PH_CALL_DONE;
 			} break;
 			case PH_CALL_DONE: {
+				const int rk = lds_i32(sp + CS_RK), n_mem = lds_i32(sp + CS_NMEM);
+				Intv *const slot = p.slots + (size_t)rk * p.slot_cap;
+				const Intv *const M2 = M1 + p.scratch_cap;
 				if (MODE == MODE_SMEM1) {
+					const int rid = lds_i32(sp + CS_RID);
 					for (int e = n_mem - 1, o = 0; e >= 0; --e, ++o)             // bwt.c:829: ascending start
-						if (o < p.slot_cap) { const Intv v = ld_intv(&M1[e]); st_intv(&slot[o], v.x0, v.x1, v.x2, v.info); }
-					p.counts[rk] = n_mem; p.ret[rid] = ret;
-					if (n_mem > p.slot_cap) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_mem); }
+						if (o < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[o], t.x0, t.x1, t.x2, t.info); }
+					p.counts[rk] = n_mem; p.ret[rid] = lds_i32(sp + CS_RET);
+					if (n_mem > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_mem); }
 					phase = PH_NEED_READ;
 					break;
 				}
+				const int step = lds_i32(sp + CS_STEP);
 				const u64 tag = (u64)step << STEP_SHIFT;
-				if (pass == 0) {
-					n_m1 = n_mem; keep_len = max_len;
+				int n_out = lds_i32(sp + CS_NOUT);
+				if (lds_i32(sp + CS_PASS) == 0) {
+					const int max_len = lds_i32(sp + CS_MAXLEN), split_len = lds_i32(sp + CS_SPLIT);
+					const u64 max_s = (u64)(u32)lds_i32(sp + CS_MAXS_LO) | ((u64)(u32)lds_i32(sp + CS_MAXS_HI) << 32);
 					// bwamem.c:272: re-seed from the middle of the longest SMEM if it is long and (nearly) unique
 					if (n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width) {
-						pass = 1; M = M2;
-						x = (max_end + max_start) >> 1;
+						sts_i32(sp + CS_NM1, n_mem); sts_i32(sp + CS_KEEP, max_len); sts_i32(sp + CS_PASS, 1);
+						sts_i32(sp + CS_X, (lds_i32(sp + CS_MAXEND) + lds_i32(sp + CS_MAXSTART)) >> 1);
 						min_intv = max_s + 1;
 						phase = PH_INIT_CALL;
 						break;
 					}
-					for (int e = n_m1 - 1; e >= 0; --e) {
-						if (n_out < p.slot_cap) { const Intv v = ld_intv(&M1[e]); st_intv(&slot[n_out], v.x0, v.x1, v.x2, v.info | tag); }
+					for (int e = n_mem - 1; e >= 0; --e) {
+						if (n_out < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[n_out], t.x0, t.x1, t.x2, t.info | tag); }
 						++n_out;
 					}
 				} else {
 					// ordered merge, bwamem.c:281-301; both lists are walked in ascending start = reverse emission
-					int a = n_m1 - 1, b = n_mem - 1;
-					const int half = keep_len >> 1;
+					int ia = lds_i32(sp + CS_NM1) - 1, ib = n_mem - 1;
+					const int half_len = lds_i32(sp + CS_KEEP) >> 1, ori_start = lds_i32(sp + CS_ORI);
 					Intv va, vb;
 					va.x0 = va.x1 = va.x2 = va.info = 0; vb = va;
 					bool have_a = false, have_b = false;
-					while (a >= 0 || b >= 0) {
-						if (a >= 0 && !have_a) { va = ld_intv(&M1[a]); have_a = true; }
-						if (b >= 0 && !have_b) { vb = ld_intv(&M2[b]); have_b = true; }
+					while (ia >= 0 || ib >= 0) {
+						if (ia >= 0 && !have_a) { va = ld_intv(&M1[ia]); have_a = true; }
+						if (ib >= 0 && !have_b) { vb = ld_intv(&M2[ib]); have_b = true; }
 						bool take_a;
-						if (a >= 0 && b >= 0) {
+						if (ia >= 0 && ib >= 0) {
 							const long long xa = (long long)((va.info >> 32 << 32) | (u32)(len - (int)(u32)va.info));
 							const long long xb = (long long)((vb.info >> 32 << 32) | (u32)(len - (int)(u32)vb.info));
 							take_a = xa < xb;
-						} else take_a = a >= 0;
+						} else take_a = ia >= 0;
 						if (take_a) {
 							if (n_out < p.slot_cap) st_intv(&slot[n_out], va.x0, va.x1, va.x2, va.info | tag);
-							++n_out; --a; have_a = false;
+							++n_out; --ia; have_a = false;
 						} else {
 							const int sl = (int)(u32)vb.info - (int)(vb.info >> 32);
-							if (sl >= half && (int)(u32)vb.info > ori_start) {
+							if (sl >= half_len && (int)(u32)vb.info > ori_start) {
 								if (n_out < p.slot_cap) st_intv(&slot[n_out], vb.x0, vb.x1, vb.x2, vb.info | tag);
 								++n_out;
 							}
-							--b; have_b = false;
+							--ib; have_b = false;
 						}
 					}
 				}
-				++step;
+				sts_i32(sp + CS_NOUT, n_out); sts_i32(sp + CS_STEP, step + 1);
 				phase = PH_NEXT_STEP;
 			} break;
 			default: break;
 			}
 		}
-		if (phase == PH_EXIT) break;
+		__syncwarp();
+		if (__all_sync(FULL_MASK, phase == PH_IDLE)) break;
 
-		// ============================================================== one bwt_extend (warp re-converges here)
-		Ext ok;
-		if (phase == PH_FWD) ok = extend(p.ix, ka, kb, ks, 3 - (int)q[i], p.hot_min_intv, policy);   // bwt.c:793
-		else                 ok = extend(p.ix, pe.x0, pe.x1, pe.x2, cb, p.hot_min_intv, policy);     // bwt.c:812
-		if (--guard < 0) { atomicAdd(&p.status[2], 1); p.counts[rk] = 0; phase = PH_NEED_READ; continue; }
+		// ============================================================== one bwt_extend per pair (warp converged)
+		// idle pairs ride along on the interval (1,1,1): its block is hot in L2 and the result is dropped
+		const Ext ok = extend_pair(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, policy);
+		if (phase == PH_IDLE) continue;
+		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sp + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 
-		// ============================================================== consume the result
+		// ============================================================== consume the result, set up the next extend
 		if (phase == PH_FWD) {                               // bwt.c:794-799
-			if (ok.s != ks) {
-				st_intv(&B0[n_curr++], kb, ka, ks, (u64)kend);
-				ret = kend;
+			if (ok.s != s) {
+				b_put(n_curr++, b, a, s, end);
+				sts_i32(sp + CS_RET, (int)end);
 				if (ok.s < min_intv) { phase = PH_FWD_DONE; continue; }
 			}
-			ka = ok.a; kb = ok.b; ks = ok.s; kend = i + 1;
+			a = ok.a; b = ok.b; s = ok.s; end = (u32)(i + 1);
 			++i;
+			const u32 qv = i < len ? lds_u8(sq + i) : 4u;
+			if (qv > 3) {                                    // bwt.c:800-803 / :806
+				b_put(n_curr++, b, a, s, end);
+				sts_i32(sp + CS_RET, (int)end);
+				phase = PH_FWD_DONE;
+			} else c = 3 - (int)qv;
 		} else {                                             // bwt.c:813-824
 			if (ok.s < min_intv) {
-				if (n_curr == 0 && (n_mem == 0 || i + 1 < last_mem_start)) {
-					st_intv(&M[n_mem++], pe.x0, pe.x1, pe.x2, pe.info | ((u64)(i + 1) << 32));
-					last_mem_start = i + 1;
-					const int l = (int)pe.info - (i + 1);
-					if (l >= max_len) { max_len = l; max_start = i + 1; max_end = (int)pe.info; max_s = pe.x2; }
-				}
-			} else if (n_curr == 0 || ok.s != last_curr_s) {
-				st_intv(&curr[n_curr++], ok.a, ok.b, ok.s, pe.info);
-				last_curr_s = ok.s;
+				if (n_curr == 0) emit(a, b, s, end, i + 1);
+			} else if (n_curr == 0 || ok.s != last_s) {
+				b_put(n0 - 1 - n_curr, ok.a, ok.b, ok.s, end);    // n_curr <= j: lands at or behind the slot just read
+				++n_curr;
+				last_s = ok.s;
 			}
 			if (++j == n_prev) {                             // bwt.c:826-827
-				if (n_curr == 0) phase = PH_CALL_DONE;
-				else {
-					Intv *t = prev; prev = curr; curr = t;
-					prev_rev = false;
-					n_prev = n_curr; n_curr = 0; j = 0; --i;
-					cb = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
-				}
+				if (n_curr == 0) { phase = PH_CALL_DONE; continue; }
+				n_prev = n_curr; n_curr = 0; j = 0; --i;
+				c = i < 0 ? -1 : (int)lds_u8(sq + i);
+				if (c > 3) c = -1;
+				if (c < 0) phase = PH_BWD_LAST;
 			}
+			b_get(n0 - 1 - j, a, b, s, end);
 		}
 	}
+}
+
+// Upload-time re-pack of bwt_t::bwt (bwtindex.c:128-150: per 128 symbols 4 x uint64 checkpoints + 8 words of
+// 16 two-bit symbols, first symbol in the top bits; last block truncated) into the split bit-plane block
+// described in smem_device.cuh.  One thread per block.
+__global__ void repack_kernel(const u32 *__restrict__ src, u64 n_blocks, u64 seq_len, uint4 *__restrict__ dst)
+{
+	const u64 bidx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (bidx >= n_blocks) return;
+	const u32 *s = src + bidx * 16;
+	const u64 rem = seq_len - bidx * 128;                         // symbols in this block
+	const int nw = rem >= 128 ? 8 : (int)((rem + 15) >> 4);        // symbol words actually present
+	u32 cnt[8], hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int k = 0; k < 8; ++k) cnt[k] = s[k];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const u32 w = k < nw ? s[8 + k] : 0u;
+		u32 h = 0, l = 0;                                          // compress the odd / even bits of w into 16 bits
+#pragma unroll
+		for (int t = 0; t < 16; ++t) { h |= ((w >> (2 * t + 1)) & 1u) << t; l |= ((w >> (2 * t)) & 1u) << t; }
+		hi[k >> 1] |= h << (16 * (1 - (k & 1)));
+		lo[k >> 1] |= l << (16 * (1 - (k & 1)));
+	}
+	uint4 *d = dst + bidx * 4;
+	d[0] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);             // sector 0: checkpoints A, C
+	d[1] = make_uint4(hi[0], hi[1], lo[0], lo[1]);                 //           planes of symbols 0..63
+	d[2] = make_uint4(cnt[4], cnt[5], cnt[6], cnt[7]);             // sector 1: checkpoints G, T
+	d[3] = make_uint4(hi[2], hi[3], lo[2], lo[3]);                 //           planes of symbols 64..127
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,26 +335,76 @@ __global__ void add_base_kernel(long long *off, long long n, long long base)
 // Random-access roofline probe: every thread walks a dependent chain of
 // aligned BYTES-sized gathers over `n_units` units; the next address is a hash of the data just
 // loaded, so nothing can be prefetched or coalesced -- the access pattern of bwt_occ4.
-template <int BYTES>
+// VARIANT selects the load flavour so that the best the memory system can do is what gets reported:
+//   0: 256-bit ld.global.nc.L1::no_allocate   1: 128-bit ld.global.nc.L1::no_allocate
+//   2: 256-bit plain ld.global (L1 allocating) 3: 128-bit ld.global.cg   4: 128-bit ld.global.nc + L2::evict_first
+template <int VARIANT>
+__device__ __forceinline__ u32 probe_load32(const uint4 *ptr, u64 pol)
+{
+	u32 w[8];
+	if (VARIANT == 0) {
+		asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr));
+	} else if (VARIANT == 2) {
+		asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr));
+	} else if (VARIANT == 1) {
+		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(ptr));
+		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr + 1));
+	} else if (VARIANT == 3) {
+		asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(ptr));
+		asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr + 1));
+	} else {
+		asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(ptr), "l"(pol));
+		asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr + 1), "l"(pol));
+	}
+	return w[0] ^ w[1] ^ w[2] ^ w[3] ^ w[4] ^ w[5] ^ w[6] ^ w[7];
+}
+
+template <int BYTES, int VARIANT>
 __global__ void __launch_bounds__(256) gather_probe_kernel(const uint4 *__restrict__ base, u64 n_units, int steps, u64 *sink)
 {
 	u64 s = (u64)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+	u64 acc = 0, pol = 0;
+	if (VARIANT == 4) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	for (int it = 0; it < steps; ++it) {
+		s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
+		const u64 u = __umul64hi(s, n_units);          // uniform in [0, n_units) without a 64-bit modulo
+		const uint4 *ptr = base + u * (BYTES / 16);
+		u32 f = probe_load32<VARIANT>(ptr, pol);
+		if (BYTES >= 64) f ^= probe_load32<VARIANT>(ptr + 2, pol);
+		if (BYTES >= 128) { f ^= probe_load32<VARIANT>(ptr + 4, pol); f ^= probe_load32<VARIANT>(ptr + 6, pol); }
+		acc += f;
+		s += f;          // the chain: next unit depends on the bytes just gathered
+	}
+	if (acc == 0x7fffffffffffffffull) *sink = acc;
+}
+
+// Cooperative flavour of the probe: LANES adjacent lanes share one chain and fetch one aligned
+// (LANES * WIDTH)-byte unit with a single load instruction (WIDTH = 16 or 32 bytes per lane), the
+// access shape of a sub-warp-per-read kernel.  Chains per SM = resident threads / LANES.
+template <int LANES, int WIDTH>
+__global__ void __launch_bounds__(256) gather_probe_coop_kernel(const uint4 *__restrict__ base, u64 n_units, int steps, u64 *sink)
+{
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int sub = tid % LANES;
+	u64 s = (u64)(tid / LANES) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
 	u64 acc = 0;
 	for (int it = 0; it < steps; ++it) {
 		s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
-		const u64 u = s % n_units;
-		const uint4 *ptr = base + u * (BYTES / 16);
-		u32 w[16];
-		asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(ptr));
-		u32 f = w[0] ^ w[1] ^ w[2] ^ w[3] ^ w[4] ^ w[5] ^ w[6] ^ w[7];
-		if (BYTES == 64) {
-			asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-			             : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(ptr + 2));
-			f ^= w[8] ^ w[9] ^ w[10] ^ w[11] ^ w[12] ^ w[13] ^ w[14] ^ w[15];
+		const u64 u = __umul64hi(s, n_units);
+		const uint4 *ptr = base + u * (LANES * WIDTH / 16) + sub * (WIDTH / 16);
+		u32 f;
+		if (WIDTH == 32) f = probe_load32<0>(ptr, 0);
+		else {
+			u32 a, b, c, d;
+			asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(ptr));
+			f = a ^ b ^ c ^ d;
 		}
+#pragma unroll
+		for (int m = 1; m < LANES; m <<= 1) f ^= __shfl_xor_sync(0xffffffffu, f, m);
 		acc += f;
-		s += f;          // the chain: next unit depends on the bytes just gathered
+		s += f;
 	}
 	if (acc == 0x7fffffffffffffffull) *sink = acc;
 }
