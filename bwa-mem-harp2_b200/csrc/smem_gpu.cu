@@ -23,7 +23,7 @@ typedef thrust::transform_iterator<CastI2L, const int *, long long> CountIter;
 
 struct DeviceCtx {
 	int dev = 0, sm_count = 0;
-	size_t smem_per_sm = 0;
+	size_t smem_per_sm = 0, smem_per_block_optin = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 	// index
@@ -73,7 +73,7 @@ struct smem_gpu {
 	int max_len = 0;
 	int64_t staged = -1;
 	bool ran = false;
-	int block_threads = SEED_BLOCK, blocks_per_sm = 8, slot_cap = 64, b_cap = 20;
+	int block_threads = SEED_BLOCK, blocks_per_sm = 6, slot_cap = 64, b_cap = 20;
 	int64_t hot_min_intv = 0;
 	int probe_variant = 0;
 	int force_wide = 0;
@@ -108,6 +108,7 @@ int ctx_init(DeviceCtx &d, int dev, int64_t read_cap, int max_len, int slot_cap)
 	CK(cudaGetDeviceProperties(&prop, dev));
 	d.sm_count = prop.multiProcessorCount;
 	d.smem_per_sm = prop.sharedMemPerMultiprocessor;
+	d.smem_per_block_optin = prop.sharedMemPerBlockOptin;
 	CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&d.ev0)); CK(cudaEventCreate(&d.ev1)); CK(cudaEventCreate(&d.ev2));
 	d.read_cap = read_cap;
@@ -205,15 +206,16 @@ int ctx_stage(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32
 	return 0;
 }
 
-template <int MODE, bool WIDE>
+template <int MODE, bool WIDE, bool BGLOBAL>
 int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem)
 {
-#define LAUNCH(B)                                                                                                        \
-	do {                                                                                                                 \
-		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-		seed_kernel<MODE, B, WIDE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
+#define LAUNCH(B)                                                                                                                 \
+	do {                                                                                                                          \
+		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, BGLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+		seed_kernel<MODE, B, WIDE, BGLOBAL><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
 	} while (0)
-	switch (blocks_per_sm) {
+	if (BGLOBAL) LAUNCH(4);            // the rare re-run: one instantiation is enough
+	else switch (blocks_per_sm) {
 	case 4: LAUNCH(4); break;
 	case 5: LAUNCH(5); break;
 	case 6: LAUNCH(6); break;
@@ -229,9 +231,10 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 }
 
 template <int MODE>
-int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide)
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide, bool bglobal)
 {
-	return wide ? launch_seed_w<MODE, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false>(d, p, blocks_per_sm, grid, smem);
+	if (bglobal) return wide ? launch_seed_w<MODE, true, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, true>(d, p, blocks_per_sm, grid, smem);
+	return wide ? launch_seed_w<MODE, true, false>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, false>(d, p, blocks_per_sm, grid, smem);
 }
 
 int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *opt)
@@ -249,12 +252,14 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	// 16-byte packed prev/curr entries need every SA coordinate < 2^36 and read positions < 2^20
 	const bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
 	const int q_stride = (h.max_len + 15) / 16 * 16;
-	const size_t smem_budget = (size_t)(d.smem_per_sm / bps) - 1024;            // per CTA, leaving the driver's reserve
+	// b_cap is honoured even if that leaves room for fewer CTAs per SM than blocks_per_sm asks for (the
+	// hardware then simply runs fewer); it only shrinks when a single CTA would not fit at all.
+	const size_t smem_budget = d.smem_per_block_optin;
 	const size_t entry = wide ? 32 : 16;
 	int b_cap = h.b_cap;
 	if ((size_t)pairs_per_cta * (COLD_BYTES + b_cap * entry + q_stride) > smem_budget) {
 		const long long fit = ((long long)(smem_budget / pairs_per_cta) - q_stride - COLD_BYTES) / (long long)entry;
-		if (fit < 2) { d.err = "read length too large for the shared-memory staging at this blocks_per_sm"; return SMEM_GPU_E_CAPACITY; }
+		if (fit < 2) { d.err = "read length too large for the shared-memory staging of one CTA"; return SMEM_GPU_E_CAPACITY; }
 		b_cap = (int)fit;
 	}
 	const int pair_stride = (int)(COLD_BYTES + q_stride + b_cap * entry);
@@ -290,20 +295,66 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	CK(cudaEventRecord(d.ev0, d.stream));
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
-	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide);
+	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, false) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, false);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
+	const int n_over = d.h_status[1];
+	d.overflow = n_over;
+	int big_cap = 0;
+	if (n_over > 0) {
+		// Reads that outgrew their result slot (exact count known) or their shared-memory prev/curr array
+		// (count unknown) are seeded again, B in global memory, into slots sized from what was measured;
+		// a second round with the then exact maximum follows if a slot is still too small.
+		std::vector<int> list(n_over);
+		CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
+		CK(cudaStreamSynchronize(d.stream));
+		std::sort(list.begin(), list.end());       // deterministic re-run order
+		if ((size_t)n_over > d.counts_k_cap) {
+			if (d.d_counts_k) CK(cudaFree(d.d_counts_k));
+			d.d_counts_k = nullptr; d.counts_k_cap = 0;
+			CK(cudaMalloc((void **)&d.d_counts_k, (size_t)n_over * 2 * 4));       // counts + this pass' overflow list
+			d.counts_k_cap = n_over;
+		}
+		CK(cudaMemcpyAsync(d.d_overflow, list.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, d.stream));
+		big_cap = std::max(d.h_status[3], 4 * h.slot_cap);
+		for (int round = 0; round < 3; ++round) {
+			const size_t need_big = (size_t)n_over * big_cap;
+			if (need_big > d.big_entries) {
+				if (d.d_big) CK(cudaFree(d.d_big));
+				d.d_big = nullptr; d.big_entries = 0;
+				CK(cudaMalloc((void **)&d.d_big, need_big * sizeof(Intv)));
+				d.big_entries = need_big;
+			}
+			CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+			SeedParams p2 = p;
+			p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
+			p2.overflow_list = d.d_counts_k + n_over;
+			p2.b_cap = 0; p2.pair_stride = COLD_BYTES + q_stride;
+			const size_t smem2 = (size_t)pairs_per_cta * p2.pair_stride;
+			const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
+			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem2, wide, true) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem2, wide, true);
+			if (rc) return rc;
+			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+			CK(cudaStreamSynchronize(d.stream));
+			if (d.h_status[2] != 0) { d.err = "device guard tripped in the overflow re-run"; return SMEM_GPU_E_INTERNAL; }
+			if (d.h_status[1] == 0) break;
+			if (round == 2) { d.err = "overflow re-run did not converge"; return SMEM_GPU_E_INTERNAL; }
+			big_cap = d.h_status[3];               // exact now: nothing was abandoned with B in global memory
+		}
+		scatter_counts_kernel<<<(n_over + 255) / 256, 256, 0, d.stream>>>(d.d_counts_k, d.d_overflow, n_over, d.d_counts);
+		CK(cudaGetLastError());
+		++d.launches;
+	}
 	CountIter it((const int *)d.d_counts, CastI2L());
 	size_t tb = d.tmp_bytes;
 	CK(cub::DeviceScan::ExclusiveSum(d.d_tmp, tb, it, d.d_off, (int)(d.n + 1), d.stream));
 	d.launches += 1;
-	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaMemcpyAsync(d.h_status + 4, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
-	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
 	memcpy(&d.total, d.h_status + 4, 8);
-	const int n_over = d.h_status[1];
-	d.overflow = n_over;
 	if ((size_t)d.total > d.out_cap) {
 		CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); d.d_out = nullptr; d.d_step = nullptr;
 		d.out_cap = (size_t)d.total + (size_t)d.total / 8 + 1024;
@@ -318,44 +369,11 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 		++d.launches;
 	}
 	if (n_over > 0) {
-		// Reads whose interval list outgrew their slot are seeded again into slots of the worst-case
-		// size a read of max_len bases can produce per the counts just measured.
-		// The list is sorted on the host so that the re-run is deterministic; the slot size is the
-		// largest count the first pass measured (status[3]), so the second pass cannot overflow.
-		std::vector<int> list(n_over);
-		CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
-		CK(cudaStreamSynchronize(d.stream));
-		std::sort(list.begin(), list.end());
-		const int big_cap = d.h_status[3];
-		const size_t need_big = (size_t)n_over * big_cap;
-		if (need_big > d.big_entries) {
-			if (d.d_big) CK(cudaFree(d.d_big));
-			d.d_big = nullptr; d.big_entries = 0;
-			CK(cudaMalloc((void **)&d.d_big, need_big * sizeof(Intv)));
-			d.big_entries = need_big;
-		}
-		if ((size_t)n_over > d.counts_k_cap) {
-			if (d.d_counts_k) CK(cudaFree(d.d_counts_k));
-			d.d_counts_k = nullptr; d.counts_k_cap = 0;
-			CK(cudaMalloc((void **)&d.d_counts_k, (size_t)n_over * 4));
-			d.counts_k_cap = n_over;
-		}
-		CK(cudaMemcpyAsync(d.d_overflow, list.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, d.stream));
-		CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
-		SeedParams p2 = p;
-		p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
-		p2.overflow_list = d.d_overflow + n_over;   // unused: big_cap is exact
-		const int grid2 = (int)std::min<int64_t>(max_grid, (n_over + pairs_per_cta - 1) / pairs_per_cta);
-		rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide);
-		if (rc) return rc;
 		const long long threads = (long long)n_over * big_cap;
 		compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
 		                                                                             d.d_off, d.d_out, d.d_step);
 		CK(cudaGetLastError());
 		++d.launches;
-		CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-		CK(cudaStreamSynchronize(d.stream));
-		if (d.h_status[2] != 0) { d.err = "device guard tripped in the overflow re-run"; return SMEM_GPU_E_INTERNAL; }
 	}
 	CK(cudaEventRecord(d.ev2, d.stream));
 	CK(cudaStreamSynchronize(d.stream));

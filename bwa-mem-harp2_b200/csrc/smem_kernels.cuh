@@ -4,7 +4,7 @@
 
 enum { MODE_COLLECT = 0, MODE_SMEM1 = 1 };
 // hot phases first: the main loop only ever extends in PH_FWD / PH_BWD
-enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
+enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
 
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index rides in info bits 48..63
 #define SEED_BLOCK 128       // threads per CTA of the seeding kernel (= 64 lane pairs = 64 reads in flight)
@@ -12,7 +12,7 @@ enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_I
 // per-pair shared memory: [cold state | query bytes | B entries]
 enum { CS_RK = 0, CS_RID = 4, CS_START = 8, CS_STEP = 12, CS_ORI = 16, CS_SPLIT = 20, CS_NOUT = 24, CS_PASS = 28, CS_X = 32,
        CS_NMEM = 36, CS_LMS = 40, CS_NM1 = 44, CS_KEEP = 48, CS_MAXLEN = 52, CS_MAXSTART = 56, CS_MAXEND = 60, CS_MAXS_LO = 64,
-       CS_MAXS_HI = 68, CS_RET = 72, COLD_BYTES = 80 };
+       CS_MAXS_HI = 68, CS_RET = 72, CS_ABORT = 76, COLD_BYTES = 80 };
 
 // One persistent LANE PAIR = one read at a time (see smem_device.cuh for why a pair).  Both lanes run
 // the same state machine on identical state; they differ only in which sector of an occ block they
@@ -25,10 +25,12 @@ enum { CS_RK = 0, CS_RID = 4, CS_START = 8, CS_STEP = 12, CS_ORI = 16, CS_SPLIT 
 //   shared : cold state, q[len] (the staged query), B[b_cap] = prev/curr of bwt_smem1 compacted IN
 //            PLACE (curr[n] is written at or behind the prev[j] just consumed, so one array serves both,
 //            bwt.c:810-828) and addressed from its top so that "reverse curr" (bwt.c:807) costs nothing;
-//   global : M1, M2 = `matches` / `sub` of smem_next2 in emission order (descending start),
-//            BX = spill of B beyond b_cap (not touched on random references: <= 18 live intervals);
-//            each of scratch_cap = max_read_len + 2 entries, which bounds every list of bwt.c:776-835.
-template <int MODE, int MIN_BLOCKS, bool WIDE>
+//   global : M1, M2 = `matches` / `sub` of smem_next2 in emission order (descending start), each of
+//            scratch_cap = max_read_len + 2 entries, which bounds every list of bwt.c:776-835.
+// A read whose forward pass needs more than b_cap live intervals (never on random references: <= 18;
+// repeats can) is abandoned, put on the overflow list and seeded again by the BGLOBAL instantiation,
+// which keeps B in global memory (BX, scratch_cap entries) -- correctness never depends on b_cap.
+template <int MODE, int MIN_BLOCKS, bool WIDE, bool BGLOBAL>
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
 	typedef BEntry<WIDE> BE;
@@ -45,12 +47,19 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	if (p.hot_min_intv) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
 
 	auto b_put = [&](int idx, u64 x0, u64 x1, u64 x2, u32 end) {
-		if (idx < p.b_cap) BE::put(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		if (!BGLOBAL) BE::put(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
 		else st_intv(&BX[idx], x0, x1, x2, (u64)end);
 	};
 	auto b_get = [&](int idx, u64 &x0, u64 &x1, u64 &x2, u32 &end) {
-		if (idx < p.b_cap) BE::get(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		if (!BGLOBAL) BE::get(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
 		else { const Intv t = ld_intv(&BX[idx]); x0 = t.x0; x1 = t.x1; x2 = t.x2; end = (u32)t.info; }
+	};
+	const int b_lim = BGLOBAL ? p.scratch_cap : p.b_cap;
+	// give up on this read in this launch: the host re-runs it with B in global memory
+	auto abandon = [&]() {
+		const int rk = lds_i32(sp + CS_RK);
+		p.counts[rk] = 0;
+		if (!half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sp + CS_RID); atomicMax(&p.status[3], 1); }
 	};
 	// bwt.c:815-820: a hit that cannot be extended is recorded unless a longer match already covers it
 	auto emit = [&](u64 x0, u64 x1, u64 x2, u32 end, int st) {
@@ -132,19 +141,22 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				sts_i32(sp + CS_MAXS_LO, 0); sts_i32(sp + CS_MAXS_HI, 0);
 				guard = 2 * (len + 2) * (len + 2) + 64;   // > every extend one bwt_smem1 can issue
 				const u32 qv = i < len ? lds_u8(sq + i) : 4u;
-				if (qv > 3) {                             // bwt.c:800-803 (ambiguous base) / :806 (end of read)
-					b_put(n_curr++, b, a, s, end);
-					sts_i32(sp + CS_RET, (int)end);
-					phase = PH_FWD_DONE;
-				} else { c = 3 - (int)qv; phase = PH_FWD; }   // bwt.c:793: forward extension uses the complement
+				if (qv > 3) phase = PH_FWD_END;
+				else { c = 3 - (int)qv; phase = PH_FWD; }     // bwt.c:793: forward extension uses the complement
+			} break;
+			case PH_FWD_END: {       // bwt.c:800-803 (ambiguous base) / :806 (end of read): push the last interval
+				if (n_curr >= b_lim) { abandon(); phase = PH_NEED_READ; break; }
+				b_put(n_curr++, b, a, s, end);
+				phase = PH_FWD_DONE;
 			} break;
 			case PH_FWD_DONE: {      // bwt.c:807-809: "reverse curr" == address B from its top (n0 - 1 - j)
-				if (MODE == MODE_COLLECT && lds_i32(sp + CS_PASS) == 0) sts_i32(sp + CS_START, lds_i32(sp + CS_RET));   // bwamem.c:262
 				n0 = n_curr; n_prev = n_curr; n_curr = 0;
 				i = lds_i32(sp + CS_X) - 1; j = 0;
 				c = i < 0 ? -1 : (int)lds_u8(sq + i);
 				if (c > 3) c = -1;
-				b_get(n0 - 1, a, b, s, end);
+				b_get(n0 - 1, a, b, s, end);             // prev[0] = the last push; its info is bwt_smem1's return value
+				sts_i32(sp + CS_RET, (int)end);
+				if (MODE == MODE_COLLECT && lds_i32(sp + CS_PASS) == 0) sts_i32(sp + CS_START, (int)end);   // bwamem.c:262
 				phase = c < 0 ? PH_BWD_LAST : PH_BWD;
 			} break;
 			case PH_BWD_LAST: {
@@ -229,28 +241,29 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sp + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 
 		// ============================================================== consume the result, set up the next extend
-		if (phase == PH_FWD) {                               // bwt.c:794-799
-			if (ok.s != s) {
-				b_put(n_curr++, b, a, s, end);
-				sts_i32(sp + CS_RET, (int)end);
-				if (ok.s < min_intv) { phase = PH_FWD_DONE; continue; }
-			}
+		// (forward: bwt.c:794-799, backward: bwt.c:813-824; written once for both so that the warp does not
+		//  run two divergent copies of the push / advance code)
+		const bool fwd = phase == PH_FWD;
+		const bool small = ok.s < min_intv;
+		const bool diff = ok.s != (fwd ? s : last_s);
+		const bool push = fwd ? diff : (!small && (n_curr == 0 || diff));
+		if (!fwd && small && n_curr == 0) emit(a, b, s, end, i + 1);
+		if (push) {
+			// forward pushes the interval it leaves (ik), backward the one it arrives at (ok[c], info inherited)
+			const int idx = fwd ? n_curr : n0 - 1 - n_curr;      // backward: n_curr <= j, lands at or behind the slot just read
+			if (idx >= b_lim) { abandon(); phase = PH_NEED_READ; continue; }
+			b_put(idx, fwd ? b : ok.a, fwd ? a : ok.b, fwd ? s : ok.s, end);
+			++n_curr;
+			last_s = ok.s;
+		}
+		if (fwd) {
+			if (diff && small) { phase = PH_FWD_DONE; continue; }
 			a = ok.a; b = ok.b; s = ok.s; end = (u32)(i + 1);
 			++i;
 			const u32 qv = i < len ? lds_u8(sq + i) : 4u;
-			if (qv > 3) {                                    // bwt.c:800-803 / :806
-				b_put(n_curr++, b, a, s, end);
-				sts_i32(sp + CS_RET, (int)end);
-				phase = PH_FWD_DONE;
-			} else c = 3 - (int)qv;
-		} else {                                             // bwt.c:813-824
-			if (ok.s < min_intv) {
-				if (n_curr == 0) emit(a, b, s, end, i + 1);
-			} else if (n_curr == 0 || ok.s != last_s) {
-				b_put(n0 - 1 - n_curr, ok.a, ok.b, ok.s, end);    // n_curr <= j: lands at or behind the slot just read
-				++n_curr;
-				last_s = ok.s;
-			}
+			if (qv > 3) phase = PH_FWD_END;
+			else c = 3 - (int)qv;
+		} else {
 			if (++j == n_prev) {                             // bwt.c:826-827
 				if (n_curr == 0) { phase = PH_CALL_DONE; continue; }
 				n_prev = n_curr; n_curr = 0; j = 0; --i;
@@ -261,6 +274,13 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			b_get(n0 - 1 - j, a, b, s, end);
 		}
 	}
+}
+
+// counts of the re-run (list order) -> counts[read id]
+__global__ void scatter_counts_kernel(const int *__restrict__ counts_k, const int *__restrict__ list, int n_list, int *__restrict__ counts)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n_list) counts[list[k]] = counts_k[k];
 }
 
 // Upload-time re-pack of bwt_t::bwt (bwtindex.c:128-150: per 128 symbols 4 x uint64 checkpoints + 8 words of

@@ -127,7 +127,7 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
             if name == "slot_cap" and val == 2:
                 assert g.timing()["overflow_reads"] > 0
     finally:
-        g.set_param("slot_cap", 64); g.set_param("blocks_per_sm", 8); g.set_param("l2_hot_min_intv", 0)
+        g.set_param("slot_cap", 64); g.set_param("blocks_per_sm", 6); g.set_param("l2_hot_min_intv", 0)
         g.set_param("b_cap", 20); g.set_param("force_wide", 0)
 
 
