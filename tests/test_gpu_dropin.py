@@ -1,0 +1,47 @@
+"""Drop-in boundary, end to end: the reference's own `bwa mem` with ONLY bwt_smem1_batched replaced by the
+GPU adapter (oracle/_ref/bwa_gpu, see oracle/Makefile `gpu`) must print the same SAM as the reference's CPU
+path (`-b 1` never offloads).  The binaries are prebuilt in the build container and
+travel with the snapshot; nothing here reads /root/reference."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pkg
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(ROOT, "oracle", "_ref", "bwa_ref")
+GPU = os.path.join(ROOT, "oracle", "_ref", "bwa_gpu")
+
+
+def sam_body(txt):
+    return [l for l in txt.splitlines() if not l.startswith("@PG")]
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)), reason="oracle/_ref binaries were not built")
+@pytest.mark.parametrize("paired", [False, True])
+def test_bwa_mem_sam_identical(tmp_path, paired):
+    sy = pkg("synth")
+    ref = sy.make_reference(300_000, 42)
+    refn = ref.numpy()
+    refn[40_000:41_000] = refn[5_000:6_000]
+    fa = str(tmp_path / "g.fa")
+    sy.write_fasta(fa, [("chrA", refn[:180_000]), ("chrB", refn[180_000:])])
+    subprocess.run([REF, "index", fa], check=True, capture_output=True, cwd=tmp_path)
+    n = 3000
+    reads = sy.simulate_reads(ref, n, 101, 0.02, seed=7, n_frac=0.05, paired=paired).numpy()
+    fqs = []
+    if paired:
+        sy.write_fastq(str(tmp_path / "r1.fq"), reads[0::2]); sy.write_fastq(str(tmp_path / "r2.fq"), reads[1::2])
+        fqs = [str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")]
+    else:
+        sy.write_fastq(str(tmp_path / "r.fq"), reads)
+        fqs = [str(tmp_path / "r.fq")]
+    cpu = subprocess.run([REF, "mem", "-t", "2", "-b", "1", fa] + fqs, check=True, capture_output=True, cwd=tmp_path, text=True)
+    env = dict(os.environ, SMEM_GPU_MAX_READ_LEN="256", SMEM_GPU_MAX_BATCH="4096")
+    gpu = subprocess.run([GPU, "mem", "-t", "2", "-b", "64", fa] + fqs, check=True, capture_output=True, cwd=tmp_path, text=True,
+                         env=env, timeout=600)
+    a, b = sam_body(cpu.stdout), sam_body(gpu.stdout)
+    assert len(a) == len(b) and len(a) > n
+    assert a == b
