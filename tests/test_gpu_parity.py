@@ -164,3 +164,22 @@ def test_exact_reads_give_full_length_smem(world, synth):
         starts = [s for s, _ in full]
         # per step the list is sorted by start; across steps starts never decrease below the previous step's first
         assert all(0 <= s < e <= 101 for s, e in full)
+
+
+def test_two_gpu_handle_matches_single(world, synth, sg):
+    """One handle spanning 2 GPUs (index replicated, reads sharded, host gather) == single GPU == oracle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ref, ix, o, g = world
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 9001, 101, 0.02, seed=77, n_frac=0.05))
+    a = o.collect(seq, offs, OSeedOpt(), nthreads=8)
+    g2 = sg.SmemGpu(max_batch_reads=10_000, max_read_len=128, devices=[0, 1])
+    g2.upload_index(ix)
+    b = g2.collect(seq, offs)
+    same_result(a, b, ("read_off", "intv", "step"))
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 101, 9001).astype(np.int32)
+    mi = rng.integers(0, 4, 9001).astype(np.int32)
+    same_result(o.smem1(seq, offs, x, mi), g2.smem1(seq, offs, x, mi), ("read_off", "intv", "ret"))
+    g2.close()
