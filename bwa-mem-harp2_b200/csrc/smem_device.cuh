@@ -50,7 +50,7 @@ struct SeedParams {
 	int slot_cap;
 	int *counts;             // [n] exact interval count per read (even when > slot_cap)
 	int *overflow_list;      // read ids with count > slot_cap
-	int *status;             // [0] work counter, [1] n_overflow, [2] guard trips, [3] largest overflowing count
+	int *status;             // [0] work counter, [1] n_overflow, [2] guard trips, [3] largest overflowing count, [4] largest count
 	Intv *scratch;           // per lane pair: M1, M2, BX arrays of scratch_cap entries each (global, L2-resident)
 	int scratch_cap;
 	int b_cap;               // entries of the prev/curr array kept in shared memory per read (rest spills to BX)

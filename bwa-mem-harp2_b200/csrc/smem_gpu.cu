@@ -52,7 +52,7 @@ struct DeviceCtx {
 	size_t big_entries = 0;
 	int *d_counts_k = nullptr;
 	size_t counts_k_cap = 0;
-	int *h_status = nullptr;          // pinned: [0..3] status, then 2 x int64 total
+	int *h_status = nullptr;          // pinned: [0..4] status, [6..7] int64 total
 	// current shard
 	int64_t lo = 0, hi = 0, n = 0;
 	long long seq_base = 0;
@@ -73,7 +73,7 @@ struct smem_gpu {
 	int max_len = 0;
 	int64_t staged = -1;
 	bool ran = false;
-	int block_threads = SEED_BLOCK, blocks_per_sm = 6, slot_cap = 64, b_cap = 20;
+	int block_threads = SEED_BLOCK, blocks_per_sm = 6, slot_cap = 128, b_cap = 24;
 	int64_t hot_min_intv = 0;
 	int probe_variant = 0;
 	int force_wide = 0;
@@ -298,9 +298,10 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, false) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, false);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
-	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 5 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
 	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
+	const int width = std::max(1, std::min(h.slot_cap, d.h_status[4]));
 	const int n_over = d.h_status[1];
 	d.overflow = n_over;
 	int big_cap = 0;
@@ -352,9 +353,9 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	size_t tb = d.tmp_bytes;
 	CK(cub::DeviceScan::ExclusiveSum(d.d_tmp, tb, it, d.d_off, (int)(d.n + 1), d.stream));
 	d.launches += 1;
-	CK(cudaMemcpyAsync(d.h_status + 4, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status + 6, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
-	memcpy(&d.total, d.h_status + 4, 8);
+	memcpy(&d.total, d.h_status + 6, 8);
 	if ((size_t)d.total > d.out_cap) {
 		CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); d.d_out = nullptr; d.d_step = nullptr;
 		d.out_cap = (size_t)d.total + (size_t)d.total / 8 + 1024;
@@ -362,8 +363,8 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 		CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
 	}
 	{
-		const long long threads = (long long)d.n * h.slot_cap;
-		compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
+		const long long threads = (long long)d.n * width;
+		compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_slots, h.slot_cap, width, d.d_counts, d.d_off, d.n,
 		                                                                        d.d_out, d.d_step);
 		CK(cudaGetLastError());
 		++d.launches;

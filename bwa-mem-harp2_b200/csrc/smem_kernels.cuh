@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	u32 end = 0;                         // info of that interval (query end)
 	int c = 0;                           // base of the pending extend
 	int i = 0, j = 0, n0 = 0, n_prev = 0, n_curr = 0, len = 0, guard = 0;
+	int max_count = 0;                   // largest per-read interval count this pair produced (sizes the compaction grid)
 	u64 min_intv = 1, last_s = 0;
 
 	for (;;) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(sp + CS_RK, rk); }
 				__syncwarp(3u << (lane & ~1));
 				rk = lds_i32(sp + CS_RK);
-				if ((long long)rk >= p.n) { phase = PH_IDLE; break; }
+				if ((long long)rk >= p.n) { if (!half && max_count > 0) atomicMax(&p.status[4], max_count); phase = PH_IDLE; break; }
 				const int rid = p.list ? p.list[rk] : rk;
 				const long long o0 = p.offs[rid];
 				const uint8_t *q = p.seq + o0;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				if (start >= len) {
 					const int rk = lds_i32(sp + CS_RK), n_out = lds_i32(sp + CS_NOUT);
 					p.counts[rk] = n_out;
+					max_count = max(max_count, n_out);
 					if (n_out > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sp + CS_RID); atomicMax(&p.status[3], n_out); }
 					phase = PH_NEED_READ;
 					break;
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					for (int e = n_mem - 1, o = 0; e >= 0; --e, ++o)             // bwt.c:829: ascending start
 						if (o < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[o], t.x0, t.x1, t.x2, t.info); }
 					p.counts[rk] = n_mem; p.ret[rid] = lds_i32(sp + CS_RET);
+					max_count = max(max_count, n_mem);
 					if (n_mem > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_mem); }
 					phase = PH_NEED_READ;
 					break;
@@ -315,13 +318,14 @@ __global__ void repack_kernel(const u32 *__restrict__ src, u64 n_blocks, u64 seq
 // ---------------------------------------------------------------------------------------------
 // counts -> CSR offsets is done with one CUB exclusive scan on the host side (plumbing).
 // Compaction: slots[n][slot_cap] -> dense intv[total] (+ optional step array), info restored.
-__global__ void compact_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
+__global__ void compact_kernel(const Intv *__restrict__ slots, int slot_cap, int width, const int *__restrict__ counts,
                                const long long *__restrict__ off, long long n, Intv *__restrict__ out,
                                unsigned short *__restrict__ step_out)
 {
+	// `width` = min(slot_cap, largest count of the batch): one thread per (read, entry < width)
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const long long r = t / slot_cap;
-	const int e = (int)(t - r * slot_cap);
+	const long long r = t / width;
+	const int e = (int)(t - r * width);
 	if (r >= n) return;
 	const int c = counts[r];
 	if (e >= c) return;          // entries beyond slot_cap are filled in by the overflow re-run

@@ -118,8 +118,8 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
     seq, offs = synth.to_batch(synth.simulate_reads(ref, 4000, 101, 0.03, seed=31, n_frac=0.05))
     a = o.collect(seq, offs, OSeedOpt(), nthreads=8)
     try:
-        for name, val in [("slot_cap", 2), ("slot_cap", 64), ("blocks_per_sm", 3), ("blocks_per_sm", 12), ("blocks_per_sm", 6),
-                          ("b_cap", 2), ("b_cap", 7), ("force_wide", 1), ("b_cap", 20), ("force_wide", 0),
+        for name, val in [("slot_cap", 2), ("slot_cap", 128), ("blocks_per_sm", 3), ("blocks_per_sm", 12), ("blocks_per_sm", 6),
+                          ("b_cap", 2), ("b_cap", 7), ("force_wide", 1), ("b_cap", 24), ("force_wide", 0),
                           ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0)]:
             g.set_param(name, val)
             b = g.collect(seq, offs)
@@ -127,8 +127,8 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
             if name == "slot_cap" and val == 2:
                 assert g.timing()["overflow_reads"] > 0
     finally:
-        g.set_param("slot_cap", 64); g.set_param("blocks_per_sm", 6); g.set_param("l2_hot_min_intv", 0)
-        g.set_param("b_cap", 20); g.set_param("force_wide", 0)
+        g.set_param("slot_cap", 128); g.set_param("blocks_per_sm", 6); g.set_param("l2_hot_min_intv", 0)
+        g.set_param("b_cap", 24); g.set_param("force_wide", 0)
 
 
 def test_staged_run_is_idempotent_and_capacity_error(world, synth, sg):
