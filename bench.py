@@ -47,8 +47,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--l2-hot-min-intv", type=int, default=-1)
+    ap.add_argument("--lanes", type=int, default=4, help="pipeline lanes per GPU of the end-to-end handle")
+    ap.add_argument("--spare-sms", type=int, default=-1)
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv] to time (stderr), e.g. 4,6,8:16384")
+    ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
     return ap.parse_args()
 
@@ -244,15 +246,17 @@ def main():
     # ---- device-resident leg: inputs staged in HBM before the timed region
     g.stage(pseq.array, poffs.array)
     if args.sweep:
-        keep = (g.get_param("blocks_per_sm"), g.get_param("l2_hot_min_intv"))
+        keep = (g.get_param("blocks_per_sm"), g.get_param("l2_hot_min_intv"), g.get_param("b_cap"))
         for item in args.sweep.split(","):
-            b, _, hot = item.partition(":")
-            g.set_param("blocks_per_sm", int(b)); g.set_param("l2_hot_min_intv", int(hot or 0))
+            f = item.split(":")
+            b, hot = f[0], (f[1] if len(f) > 1 and f[1] else "0")
+            g.set_param("blocks_per_sm", int(b)); g.set_param("l2_hot_min_intv", int(hot))
+            g.set_param("b_cap", int(f[2]) if len(f) > 2 else keep[2])
             ms = []
             for _ in range(4):
                 g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
-            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot or 0}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
-        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1])
+            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
+        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2])
     for _ in range(max(args.warmup, 3)):
         total = g.run_collect(opt)
     sampler = ClockSampler(local)
@@ -269,7 +273,16 @@ def main():
     clocks = sampler.stop()
     overflow = g.timing()["overflow_reads"]
 
-    # ---- end-to-end leg: host buffers in, host buffers out, copies inside the timed region
+    # ---- end-to-end leg: host buffers in, host buffers out, copies inside the timed region.  The public call is
+    # smem_gpu_collect on a handle with `--lanes` pipeline lanes on this GPU (shards overlap H2D / kernels / D2H).
+    if args.lanes > 1:
+        g.close()
+        g = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local] * args.lanes)
+        if args.blocks_per_sm:
+            g.set_param("blocks_per_sm", args.blocks_per_sm)
+        if args.spare_sms >= 0:
+            g.set_param("spare_sms", args.spare_sms)
+        g.upload_index(ix)
     pintv = sg.PinnedArray(lib, (total + 1024, 4), np.uint64)
     proff = sg.PinnedArray(lib, (n + 1,), np.int64)
     import ctypes as C
@@ -308,6 +321,7 @@ def main():
                 probe[f"{bb}B_x{chains}"] = round(g.gather_roofline(bb, 0, chains, 1000), 1)
         log("random-access probe GB/s:", probe)
     rand64 = rand64_split = None
+    e2e_overflow = g.timing()["overflow_reads"]
     if rank == 0:
         # the roofline of the access pattern: dependent 64 B gathers over the whole index, one coalesced request
         # per block (lane pair, 2 x 32 B) -- and, for reference, the same gathers issued as two per-lane requests
@@ -329,7 +343,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": world * n * args.steps / dt_e2e, "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": dt_e2e / args.steps * 1e3},
+                    "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "pipeline_lanes_per_gpu": args.lanes, "intervals": int(tot_e2e)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "seed_kernel<COLLECT>",

@@ -54,7 +54,7 @@ struct SeedParams {
 	Intv *scratch;           // per lane pair: M1, M2, BX arrays of scratch_cap entries each (global, L2-resident)
 	int scratch_cap;
 	int b_cap;               // entries of the prev/curr array kept in shared memory per read (rest spills to BX)
-	int q_stride;            // bytes of shared memory per staged query (multiple of 16)
+	int q_stride;            // bytes of shared memory per staged query (two bases per byte)
 	int pair_stride;         // bytes of shared memory per lane pair
 	int split_len_init, split_width, start_width;
 	u64 hot_min_intv;        // 0 = off; L2 evict_last hint for occ blocks of intervals >= this size
@@ -98,6 +98,8 @@ __device__ __forceinline__ void st_intv(Intv *p, u64 x0, u64 x1, u64 x2, u64 inf
 __device__ __forceinline__ u32 lds_u8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ int lds_i32(u32 a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_u16(u32 a) { u32 v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ void sts_u16(u32 a, int v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_i32(u32 a, int v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds_v4(u32 a)
 {

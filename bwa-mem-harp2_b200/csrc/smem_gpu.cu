@@ -7,19 +7,19 @@
 // No CPU fallback exists here: every failure is an error code.
 #include "../../include/smem_gpu.h"
 #include "smem_kernels.cuh"
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/transform_iterator.h>
+#include <condition_variable>
+#include <mutex>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 namespace {
-
-struct CastI2L { __host__ __device__ long long operator()(const int &v) const { return (long long)v; } };
-typedef thrust::transform_iterator<CastI2L, const int *, long long> CountIter;
 
 struct DeviceCtx {
 	int dev = 0, sm_count = 0;
@@ -31,6 +31,12 @@ struct DeviceCtx {
 	size_t index_bytes = 0;
 	DevIndex ix{};
 	bool has_index = false;
+	bool owns_index = true;          // false: d_index aliases the copy of an earlier context on the same GPU
+	int lane = 0, lanes_on_dev = 1;  // pipeline lane of this context on its GPU
+	DeviceCtx *prev_lane = nullptr;  // the lane whose seed kernel runs right before this one's
+	struct smem_gpu *owner = nullptr;
+	uint64_t seed_issued = 0;        // epoch of the last run whose seed kernel + ev1 have been enqueued (guarded by smem_gpu::lane_mu)
+	uint64_t stage_issued = 0;       // epoch of the last staging whose H2D copies have been enqueued (same guard)
 	// batch buffers (capacity fixed at create)
 	int64_t read_cap = 0;
 	size_t seq_cap = 0;
@@ -73,11 +79,17 @@ struct smem_gpu {
 	int max_len = 0;
 	int64_t staged = -1;
 	bool ran = false;
-	int block_threads = SEED_BLOCK, blocks_per_sm = 6, slot_cap = 128, b_cap = 24;
+	int block_threads = SEED_BLOCK, blocks_per_sm = 9, slot_cap = 128, b_cap = 17;
 	int64_t hot_min_intv = 0;
 	int probe_variant = 0;
 	int force_wide = 0;
+	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
+	int chain_lanes = 0;             // 1: lane k's seed kernel waits for lane k-1's (no tail overlap)
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
+	uint64_t epoch = 0;              // bumped per run; orders the lanes' seed kernels
+	uint64_t stage_epoch = 0;        // bumped per staging; orders the lanes' H2D copies
+	std::mutex lane_mu;
+	std::condition_variable lane_cv;
 	std::string err;
 };
 
@@ -100,7 +112,7 @@ template <typename T> int dev_alloc(DeviceCtx &d, T **p, size_t count)
 	return 0;
 }
 
-int ctx_init(DeviceCtx &d, int dev, int64_t read_cap, int max_len, int slot_cap)
+int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int slot_cap)
 {
 	d.dev = dev;
 	CK(cudaSetDevice(dev));
@@ -109,7 +121,15 @@ int ctx_init(DeviceCtx &d, int dev, int64_t read_cap, int max_len, int slot_cap)
 	d.sm_count = prop.multiProcessorCount;
 	d.smem_per_sm = prop.sharedMemPerMultiprocessor;
 	d.smem_per_block_optin = prop.sharedMemPerBlockOptin;
-	CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+	{
+		// lanes of one GPU: earlier lane = higher stream priority.  Pending seed kernels then start in lane order
+		// (the next lane's CTAs fill the tail of the previous one) and a finished lane's scan / compaction kernels
+		// are scheduled ahead of the following lanes' persistent CTAs (measured: with equal priorities they starve
+		// until every seed kernel has drained), so its D2H copy overlaps the next lane's kernel.
+		int lo = 0, hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = least (numerically largest), hi = greatest
+		CK(cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, std::min(lo, hi + lane)));
+	}
 	CK(cudaEventCreate(&d.ev0)); CK(cudaEventCreate(&d.ev1)); CK(cudaEventCreate(&d.ev2));
 	d.read_cap = read_cap;
 	d.seq_cap = (size_t)read_cap * (size_t)max_len + 64;
@@ -129,11 +149,12 @@ int ctx_init(DeviceCtx &d, int dev, int64_t read_cap, int max_len, int slot_cap)
 	if ((rc = dev_alloc(d, &d.d_out, d.out_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_step, d.out_cap))) return rc;
 	CK(cudaMallocHost((void **)&d.h_status, 64));
-	// CUB temp storage for the counts -> offsets scan
-	CountIter it((const int *)d.d_counts, CastI2L());
-	size_t tb = 0;
-	CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, d.d_off, (int)std::min<int64_t>(read_cap + 1, 0x7fffffff), d.stream));
-	d.tmp_bytes = tb + 256;
+	// per-pair scratch for the default launch geometry (re-grown in ctx_run if blocks_per_sm is raised): allocating
+	// it lazily would delay the first lane's first kernel by a cudaMalloc
+	d.scratch_entries = (size_t)d.sm_count * 9 * (SEED_BLOCK / 2) * 3 * (size_t)(max_len + 2);
+	CK(cudaMalloc((void **)&d.d_scratch, d.scratch_entries * sizeof(Intv)));
+	// block sums of the counts -> offsets scan
+	d.tmp_bytes = ((size_t)(read_cap + 1) / SCAN_PER_BLOCK + 2) * sizeof(long long);
 	CK(cudaMalloc(&d.d_tmp, d.tmp_bytes));
 	return 0;
 }
@@ -141,7 +162,8 @@ int ctx_init(DeviceCtx &d, int dev, int64_t read_cap, int max_len, int slot_cap)
 void ctx_free(DeviceCtx &d)
 {
 	cudaSetDevice(d.dev);
-	cudaFree(d.d_index); cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
+	if (d.owns_index) cudaFree(d.d_index);
+	cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
 	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
 	if (d.h_status) cudaFreeHost(d.h_status);
@@ -161,7 +183,8 @@ int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 	if (ix->seq_len == 0 || ix->bwt_size < (n_blocks - 1) * 16 + 8 + last_words) { d.err = "bwt_size is inconsistent with seq_len"; return SMEM_GPU_E_ARG; }
 	const size_t bytes = (size_t)ix->bwt_size * 4;
 	const size_t out_bytes = (size_t)(n_blocks + 1) * 64;            // one spare block keeps idle lanes in bounds
-	if (d.d_index) { CK(cudaFree(d.d_index)); d.d_index = nullptr; }
+	if (d.d_index && d.owns_index) CK(cudaFree(d.d_index));
+	d.d_index = nullptr; d.owns_index = true;
 	d.has_index = false;
 	CK(cudaMalloc((void **)&d.d_index, out_bytes));
 	CK(cudaMemsetAsync((char *)d.d_index + out_bytes - 64, 0, 64, d.stream));
@@ -187,7 +210,22 @@ int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 	return 0;
 }
 
-int ctx_stage(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
+int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi);
+
+// Lanes of one GPU enqueue their H2D copies in lane order (the copy engine is FIFO), so lane 0's reads land
+// first and the seed kernels become ready in priority order.
+int ctx_stage(DeviceCtx &d, smem_gpu &h, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
+{
+	if (d.prev_lane) {
+		std::unique_lock<std::mutex> lk(h.lane_mu);
+		h.lane_cv.wait(lk, [&] { return d.prev_lane->stage_issued == h.stage_epoch; });
+	}
+	const int rc = ctx_stage_inner(d, seq, offs, x, mi);
+	if (d.stage_issued != h.stage_epoch) { std::lock_guard<std::mutex> lk(h.lane_mu); d.stage_issued = h.stage_epoch; h.lane_cv.notify_all(); }
+	return rc;
+}
+
+int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
 {
 	CK(cudaSetDevice(d.dev));
 	d.n = d.hi - d.lo;
@@ -202,24 +240,26 @@ int ctx_stage(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32
 		CK(cudaMemcpyAsync(d.d_x, x + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
 		CK(cudaMemcpyAsync(d.d_mi, mi + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
 	}
+	{ std::lock_guard<std::mutex> lk(d.owner->lane_mu); d.stage_issued = d.owner->stage_epoch; d.owner->lane_cv.notify_all(); }
 	CK(cudaStreamSynchronize(d.stream));
 	return 0;
 }
 
-template <int MODE, bool WIDE, bool BGLOBAL>
+template <int MODE, bool WIDE>
 int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem)
 {
-#define LAUNCH(B)                                                                                                                 \
-	do {                                                                                                                          \
-		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, BGLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-		seed_kernel<MODE, B, WIDE, BGLOBAL><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
+#define LAUNCH(B)                                                                                                        \
+	do {                                                                                                                 \
+		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+		seed_kernel<MODE, B, WIDE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
 	} while (0)
-	if (BGLOBAL) LAUNCH(4);            // the rare re-run: one instantiation is enough
-	else switch (blocks_per_sm) {
+	switch (blocks_per_sm) {
 	case 4: LAUNCH(4); break;
 	case 5: LAUNCH(5); break;
 	case 6: LAUNCH(6); break;
+	case 7: LAUNCH(7); break;
 	case 8: LAUNCH(8); break;
+	case 9: LAUNCH(9); break;
 	case 10: LAUNCH(10); break;
 	case 12: LAUNCH(12); break;
 	default: LAUNCH(3); break;
@@ -231,27 +271,52 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 }
 
 template <int MODE>
-int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide, bool bglobal)
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide)
 {
-	if (bglobal) return wide ? launch_seed_w<MODE, true, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, true>(d, p, blocks_per_sm, grid, smem);
-	return wide ? launch_seed_w<MODE, true, false>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, false>(d, p, blocks_per_sm, grid, smem);
+	return wide ? launch_seed_w<MODE, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false>(d, p, blocks_per_sm, grid, smem);
 }
 
-int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *opt)
+// Lanes of one GPU run their seed kernels strictly in lane order: lane k waits (on the device) for lane k-1's
+// seed kernel of the same epoch.  The host-side hand-shake only makes sure the event was recorded before it is waited on.
+void lane_mark_issued(DeviceCtx &d, smem_gpu &h)
+{
+	std::lock_guard<std::mutex> lk(h.lane_mu);
+	d.seed_issued = h.epoch;
+	h.lane_cv.notify_all();
+}
+
+int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *opt);
+
+int ctx_run(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *opt)
+{
+	const int rc = ctx_run_inner(d, h, mode, opt);
+	if (d.seed_issued != h.epoch) {           // early return (no reads / error): never leave the next lane waiting
+		cudaSetDevice(d.dev);
+		cudaEventRecord(d.ev1, d.stream);
+		lane_mark_issued(d, h);
+	}
+	return rc;
+}
+
+int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *opt)
 {
 	CK(cudaSetDevice(d.dev));
 	d.mode = mode; d.launches = 0; d.overflow = 0; d.seed_ms = d.total_ms = 0; d.total = 0;
 	if (d.n == 0) return 0;
 	if (!d.has_index) { d.err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
 	const int bps = h.blocks_per_sm;
+	// several lanes on this GPU: the persistent seed kernel leaves `spare_sms` SMs empty, so that the finished
+	// lane's scan / compaction kernels run next to the following lane's seed kernel (measured: with every SM
+	// occupied they wait for it to drain, even when CTA slots are free)
+	const int spare = d.lanes_on_dev > 1 ? std::min(h.spare_sms, d.sm_count / 4) : 0;
 	const int max_grid = d.sm_count * bps;
 	const int pairs_per_cta = SEED_BLOCK / 2;
-	const int grid = (int)std::min<int64_t>(max_grid, (d.n + pairs_per_cta - 1) / pairs_per_cta);
+	const int grid = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * bps, (d.n + pairs_per_cta - 1) / pairs_per_cta);
 	const int scratch_cap = h.max_len + 2;
 	const size_t need = (size_t)max_grid * pairs_per_cta * 3 * scratch_cap;
 	// 16-byte packed prev/curr entries need every SA coordinate < 2^36 and read positions < 2^20
 	const bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
-	const int q_stride = (h.max_len + 15) / 16 * 16;
+	const int q_stride = ((h.max_len + 1) / 2 + 15) / 16 * 16;      // two bases per byte; keeps pair_stride a multiple of 16
 	// b_cap is honoured even if that leaves room for fewer CTAs per SM than blocks_per_sm asks for (the
 	// hardware then simply runs fewer); it only shrinks when a single CTA would not fit at all.
 	const size_t smem_budget = d.smem_per_block_optin;
@@ -263,7 +328,7 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 		b_cap = (int)fit;
 	}
 	const int pair_stride = (int)(COLD_BYTES + q_stride + b_cap * entry);
-	const size_t smem = (size_t)pairs_per_cta * pair_stride;
+	const size_t smem = (size_t)pairs_per_cta * pair_stride;   // (the grid, not shared memory, keeps the spare CTA slot free)
 	if (need > d.scratch_entries) {
 		if (d.d_scratch) CK(cudaFree(d.d_scratch));
 		d.d_scratch = nullptr; d.scratch_entries = 0;
@@ -295,20 +360,28 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	CK(cudaEventRecord(d.ev0, d.stream));
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
-	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, false) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, false);
+	if (d.prev_lane && h.chain_lanes) {
+		std::unique_lock<std::mutex> lk(h.lane_mu);
+		h.lane_cv.wait(lk, [&] { return d.prev_lane->seed_issued == h.epoch; });
+		lk.unlock();
+		CK(cudaStreamWaitEvent(d.stream, d.prev_lane->ev1, 0));
+	}
+	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
+	lane_mark_issued(d, h);
+	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
+	const auto tt0 = std::chrono::steady_clock::now();
+	auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 5 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
+	const double t_status = tms();
 	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
-	const int width = std::max(1, std::min(h.slot_cap, d.h_status[4]));
 	const int n_over = d.h_status[1];
 	d.overflow = n_over;
 	int big_cap = 0;
 	if (n_over > 0) {
-		// Reads that outgrew their result slot (exact count known) or their shared-memory prev/curr array
-		// (count unknown) are seeded again, B in global memory, into slots sized from what was measured;
-		// a second round with the then exact maximum follows if a slot is still too small.
+		// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
 		std::vector<int> list(n_over);
 		CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
 		CK(cudaStreamSynchronize(d.stream));
@@ -320,7 +393,7 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 			d.counts_k_cap = n_over;
 		}
 		CK(cudaMemcpyAsync(d.d_overflow, list.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, d.stream));
-		big_cap = std::max(d.h_status[3], 4 * h.slot_cap);
+		big_cap = d.h_status[3];
 		for (int round = 0; round < 3; ++round) {
 			const size_t need_big = (size_t)n_over * big_cap;
 			if (need_big > d.big_entries) {
@@ -333,10 +406,8 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 			SeedParams p2 = p;
 			p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
 			p2.overflow_list = d.d_counts_k + n_over;
-			p2.b_cap = 0; p2.pair_stride = COLD_BYTES + q_stride;
-			const size_t smem2 = (size_t)pairs_per_cta * p2.pair_stride;
 			const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
-			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem2, wide, true) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem2, wide, true);
+			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide);
 			if (rc) return rc;
 			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 			CK(cudaStreamSynchronize(d.stream));
@@ -349,12 +420,19 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 		CK(cudaGetLastError());
 		++d.launches;
 	}
-	CountIter it((const int *)d.d_counts, CastI2L());
-	size_t tb = d.tmp_bytes;
-	CK(cub::DeviceScan::ExclusiveSum(d.d_tmp, tb, it, d.d_off, (int)(d.n + 1), d.stream));
-	d.launches += 1;
+	{
+		const long long n1 = d.n + 1;                  // counts[n] = 0, so off[n] = total
+		const int nb = (int)((n1 + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
+		long long *bsum = (long long *)d.d_tmp;
+		scan_local_kernel<<<nb, SCAN_TPB, 0, d.stream>>>(d.d_counts, n1, d.d_off, bsum);
+		scan_bsum_kernel<<<1, SCAN_TPB, 0, d.stream>>>(bsum, nb);
+		scan_add_kernel<<<(unsigned)((n1 + SCAN_TPB - 1) / SCAN_TPB), SCAN_TPB, 0, d.stream>>>(d.d_off, n1, bsum);
+		CK(cudaGetLastError());
+		d.launches += 3;
+	}
 	CK(cudaMemcpyAsync(d.h_status + 6, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
+	const double t_scan = tms();
 	memcpy(&d.total, d.h_status + 6, 8);
 	if ((size_t)d.total > d.out_cap) {
 		CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); d.d_out = nullptr; d.d_step = nullptr;
@@ -363,8 +441,8 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 		CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
 	}
 	{
-		const long long threads = (long long)d.n * width;
-		compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_slots, h.slot_cap, width, d.d_counts, d.d_off, d.n,
+		const long long threads = (long long)d.n * 8;
+		compact_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
 		                                                                        d.d_out, d.d_step);
 		CK(cudaGetLastError());
 		++d.launches;
@@ -378,6 +456,7 @@ int ctx_run(DeviceCtx &d, const smem_gpu &h, int mode, const smem_seed_opt_t *op
 	}
 	CK(cudaEventRecord(d.ev2, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
+	if (trace) fprintf(stderr, "[smem_gpu trace]   lane %d run: status +%.2f scan +%.2f compact +%.2f ms after the seed launch\n", d.lane, t_status, t_scan, tms());
 	CK(cudaEventElapsedTime(&d.seed_ms, d.ev0, d.ev1));
 	CK(cudaEventElapsedTime(&d.total_ms, d.ev0, d.ev2));
 	return 0;
@@ -423,7 +502,8 @@ int do_stage(smem_gpu *h, int64_t n, const uint8_t *seq, const int64_t *offs, co
 	if (!h || n < 0 || (n > 0 && (!seq || !offs))) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
 	if (n > h->max_batch) { h->err = "batch larger than max_batch_reads"; return SMEM_GPU_E_CAPACITY; }
 	shard(h, n);
-	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_stage(d, seq, offs, x, mi); });
+	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->stage_epoch; }
+	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_stage(d, *h, seq, offs, x, mi); });
 	if (rc) return rc;
 	h->staged = n; h->ran = false;
 	h->h2d_bytes = n ? (offs[n] - offs[0]) + (n + (int64_t)h->devs.size()) * 8 + (x ? n * 8 : 0) : 0;
@@ -433,6 +513,7 @@ int do_stage(smem_gpu *h, int64_t n, const uint8_t *seq, const int64_t *offs, co
 int do_run(smem_gpu *h, int mode, const smem_seed_opt_t *opt, int64_t *total_out)
 {
 	if (h->staged < 0) { h->err = "nothing staged"; return SMEM_GPU_E_ARG; }
+	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; }
 	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_run(d, *h, mode, opt); });
 	if (rc) return rc;
 	int64_t tot = 0;
@@ -463,6 +544,62 @@ int do_fetch(smem_gpu *h, smem_intv_t *intv_out, int64_t cap, int64_t *read_off,
 	return 0;
 }
 
+// One-call form: every context (GPU, or pipeline lane of a GPU) runs stage -> run -> fetch for its shard on its own
+// host thread, so that one lane's copies overlap another lane's kernels.  A lane needs the interval totals of all
+// lanes before it to know where its results go; those finish first anyway (lanes run in order).
+int do_collect(smem_gpu *h, int mode, int64_t n, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi,
+               const smem_seed_opt_t *opt, smem_intv_t *intv_out, int64_t cap, int64_t *read_off, uint16_t *step_out, int32_t *ret,
+               int64_t *total_out)
+{
+	if (!h || n < 0 || (n > 0 && (!seq || !offs)) || !read_off) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
+	if (n > h->max_batch) { h->err = "batch larger than max_batch_reads"; return SMEM_GPU_E_CAPACITY; }
+	shard(h, n);
+	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; ++h->stage_epoch; }
+	const size_t G = h->devs.size();
+	std::vector<long long> totals(G, 0);
+	std::vector<char> ran(G, 0);
+	std::mutex mu;
+	std::condition_variable cv;
+	bool overflow = false;
+	read_off[0] = 0;
+	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
+	auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+	int rc = for_each_device(h, [&](DeviceCtx &d) {
+		const size_t k = &d - &h->devs[0];
+		const double ta = ms();
+		int r = ctx_stage(d, *h, seq, offs, x, mi);
+		const double tb = ms();
+		if (!r) r = ctx_run(d, *h, mode, opt);
+		const double tc = ms();
+		long long base = 0;
+		{
+			std::unique_lock<std::mutex> lk(mu);
+			totals[k] = r ? 0 : d.total; ran[k] = 1;
+			cv.notify_all();
+			cv.wait(lk, [&] { for (size_t j = 0; j < k; ++j) if (!ran[j]) return false; return true; });
+			for (size_t j = 0; j < k; ++j) base += totals[j];
+			if (!r && base + d.total > cap) overflow = true;
+		}
+		if (r) return r;
+		const bool fits = intv_out && base + d.total <= cap;
+		r = ctx_fetch(d, fits ? intv_out : nullptr, read_off, fits ? step_out : nullptr, ret, base);
+		if (trace) fprintf(stderr, "[smem_gpu trace] lane %zu: start %.2f staged %.2f ran %.2f (seed %.2f ms, dev %.2f ms) fetched %.2f\n", k, ta, tb, tc,
+		                   d.seed_ms, d.total_ms, ms());
+		return r;
+	});
+	h->staged = n; h->ran = rc == 0;
+	if (rc) return rc;
+	long long tot = 0;
+	for (auto t : totals) tot += t;
+	read_off[n] = tot;
+	if (total_out) *total_out = tot;
+	h->h2d_bytes = n ? (offs[n] - offs[0]) + (n + (int64_t)G) * 8 + (x ? n * 8 : 0) : 0;
+	h->d2h_bytes = n * 8 + (overflow ? 0 : tot * (32 + (step_out ? 2 : 0))) + (ret ? n * 4 : 0);
+	if (overflow || (tot > 0 && !intv_out)) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	return 0;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------- C ABI
@@ -486,7 +623,13 @@ int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int6
 	h->devs.resize(n_devices);
 	const int64_t per = (max_batch_reads + n_devices - 1) / n_devices;
 	for (int k = 0; k < n_devices; ++k) {
-		int rc = ctx_init(h->devs[k], device_ids ? device_ids[k] : k, per, max_read_len, h->slot_cap);
+		const int dev = device_ids ? device_ids[k] : k;
+		int lane = 0;
+		for (int j = 0; j < k; ++j) lane += (device_ids ? device_ids[j] : j) == dev;
+		h->devs[k].lane = lane;
+		h->devs[k].owner = h;
+		for (int j = k - 1; j >= 0; --j) if ((device_ids ? device_ids[j] : j) == dev) { h->devs[k].prev_lane = &h->devs[j]; break; }
+		int rc = ctx_init(h->devs[k], dev, lane, per, max_read_len, h->slot_cap);
 		if (rc) {
 			fprintf(stderr, "[smem_gpu] create failed on device %d: %s\n", h->devs[k].dev, h->devs[k].err.c_str());
 			for (auto &d : h->devs) ctx_free(d);
@@ -494,6 +637,7 @@ int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int6
 			return rc;
 		}
 	}
+	for (auto &d : h->devs) { d.lanes_on_dev = 0; for (auto &o : h->devs) d.lanes_on_dev += o.dev == d.dev; }
 	*out = h;
 	return 0;
 }
@@ -506,16 +650,37 @@ int smem_gpu_destroy(smem_gpu_t *h)
 	return 0;
 }
 
+// One copy of the index per physical GPU: contexts that share a device (several pipeline lanes on one GPU,
+// see smem_gpu_create) alias the first one's copy.
+static int upload_all(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device)
+{
+	int rc = for_each_device(h, [&](DeviceCtx &d) {
+		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
+		return ctx_upload_index(d, ix, src_device);
+	});
+	if (rc) return rc;
+	for (auto &d : h->devs)
+		for (auto &o : h->devs) {
+			if (&o == &d) break;
+			if (o.dev == d.dev) {
+				if (d.d_index && d.owns_index) { cudaSetDevice(d.dev); cudaFree(d.d_index); }
+				d.d_index = o.d_index; d.owns_index = false; d.index_bytes = o.index_bytes; d.ix = o.ix; d.has_index = true;
+				break;
+			}
+		}
+	return 0;
+}
+
 int smem_gpu_upload_index(smem_gpu_t *h, const smem_index_desc_t *ix)
 {
 	if (!h || !ix || !ix->bwt || ix->bwt_size < 16) return SMEM_GPU_E_ARG;
-	return for_each_device(h, [&](DeviceCtx &d) { return ctx_upload_index(d, ix, -1); });
+	return upload_all(h, ix, -1);
 }
 
 int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device)
 {
 	if (!h || !ix || !ix->bwt || ix->bwt_size < 16 || src_device < 0) return SMEM_GPU_E_ARG;
-	return for_each_device(h, [&](DeviceCtx &d) { return ctx_upload_index(d, ix, src_device); });
+	return upload_all(h, ix, src_device);
 }
 
 int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs)
@@ -539,20 +704,14 @@ int smem_gpu_collect(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const i
                      smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, uint16_t *step_out, int64_t *total_out)
 {
 	if (!h || !opt || !read_off) return SMEM_GPU_E_ARG;
-	int rc = do_stage(h, n_reads, seq, offs, nullptr, nullptr);
-	if (rc) return rc;
-	if ((rc = do_run(h, MODE_COLLECT, opt, nullptr))) return rc;
-	return do_fetch(h, intv_out, intv_cap, read_off, step_out, nullptr, total_out);
+	return do_collect(h, MODE_COLLECT, n_reads, seq, offs, nullptr, nullptr, opt, intv_out, intv_cap, read_off, step_out, nullptr, total_out);
 }
 
 int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *min_intv,
                    smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, int32_t *ret, int64_t *total_out)
 {
 	if (!h || !read_off || !ret || (n_reads > 0 && (!x || !min_intv))) return SMEM_GPU_E_ARG;
-	int rc = do_stage(h, n_reads, seq, offs, x, min_intv);
-	if (rc) return rc;
-	if ((rc = do_run(h, MODE_SMEM1, nullptr, nullptr))) return rc;
-	return do_fetch(h, intv_out, intv_cap, read_off, nullptr, ret, total_out);
+	return do_collect(h, MODE_SMEM1, n_reads, seq, offs, x, min_intv, nullptr, intv_out, intv_cap, read_off, nullptr, ret, total_out);
 }
 
 int smem_gpu_host_alloc(void **ptr, size_t bytes)
@@ -580,12 +739,14 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 {
 	if (!h || !name) return SMEM_GPU_E_ARG;
 	if (!strcmp(name, "blocks_per_sm")) {
-		static const int ok[] = {3, 4, 5, 6, 8, 10, 12};
+		static const int ok[] = {3, 4, 5, 6, 7, 8, 9, 10, 12};
 		for (int k : ok) if (k == v) { h->blocks_per_sm = (int)v; return 0; }
 		return SMEM_GPU_E_ARG;
 	}
 	if (!strcmp(name, "slot_cap")) { if (v < 1 || v > 4096) return SMEM_GPU_E_ARG; h->slot_cap = (int)v; return 0; }
 	if (!strcmp(name, "force_wide")) { h->force_wide = v != 0; return 0; }
+	if (!strcmp(name, "spare_sms")) { if (v < 0 || v > 64) return SMEM_GPU_E_ARG; h->spare_sms = (int)v; return 0; }
+	if (!strcmp(name, "chain_lanes")) { h->chain_lanes = v != 0; return 0; }
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
@@ -604,6 +765,8 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "blocks_per_sm")) return h->blocks_per_sm;
 	if (!strcmp(name, "slot_cap")) return h->slot_cap;
 	if (!strcmp(name, "b_cap")) return h->b_cap;
+	if (!strcmp(name, "spare_sms")) return h->spare_sms;
+	if (!strcmp(name, "chain_lanes")) return h->chain_lanes;
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
 	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }

@@ -9,10 +9,15 @@ enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_I
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index rides in info bits 48..63
 #define SEED_BLOCK 128       // threads per CTA of the seeding kernel (= 64 lane pairs = 64 reads in flight)
 
-// per-pair shared memory: [cold state | query bytes | B entries]
-enum { CS_RK = 0, CS_RID = 4, CS_START = 8, CS_STEP = 12, CS_ORI = 16, CS_SPLIT = 20, CS_NOUT = 24, CS_PASS = 28, CS_X = 32,
-       CS_NMEM = 36, CS_LMS = 40, CS_NM1 = 44, CS_KEEP = 48, CS_MAXLEN = 52, CS_MAXSTART = 56, CS_MAXEND = 60, CS_MAXS_LO = 64,
-       CS_MAXS_HI = 68, CS_RET = 72, CS_ABORT = 76, COLD_BYTES = 80 };
+// per-pair shared memory: [B entries | cold state | query, two bases per byte]
+// cold state: 32-bit rk, rid, n_out, max_s (2 words); everything else is a query position or a small count (16 bit)
+enum { CS_RK = 0, CS_RID = 4, CS_NOUT = 8, CS_MAXS_LO = 12, CS_MAXS_HI = 16,
+       CS_START = 20, CS_STEP = 22, CS_ORI = 24, CS_SPLIT = 26, CS_PASS = 28, CS_X = 30, CS_NMEM = 32, CS_LMS = 34, CS_NM1 = 36,
+       CS_KEEP = 38, CS_MAXLEN = 40, CS_MAXSTART = 42, CS_MAXEND = 44, CS_RET = 46, COLD_BYTES = 48 };
+
+__device__ __forceinline__ u32 qbase(u32 sq, int i) { return (lds_u8(sq + ((u32)i >> 1)) >> ((i & 1) * 4)) & 15u; }
+__device__ __noinline__ void bx_put(Intv *p, u64 x0, u64 x1, u64 x2, u32 end) { st_intv(p, x0, x1, x2, (u64)end); }
+__device__ __noinline__ Intv bx_get(const Intv *p) { return ld_intv(p); }
 
 // One persistent LANE PAIR = one read at a time (see smem_device.cuh for why a pair).  Both lanes run
 // the same state machine on identical state; they differ only in which sector of an occ block they
@@ -27,10 +32,8 @@ enum { CS_RK = 0, CS_RID = 4, CS_START = 8, CS_STEP = 12, CS_ORI = 16, CS_SPLIT 
 //            bwt.c:810-828) and addressed from its top so that "reverse curr" (bwt.c:807) costs nothing;
 //   global : M1, M2 = `matches` / `sub` of smem_next2 in emission order (descending start), each of
 //            scratch_cap = max_read_len + 2 entries, which bounds every list of bwt.c:776-835.
-// A read whose forward pass needs more than b_cap live intervals (never on random references: <= 18;
-// repeats can) is abandoned, put on the overflow list and seeded again by the BGLOBAL instantiation,
-// which keeps B in global memory (BX, scratch_cap entries) -- correctness never depends on b_cap.
-template <int MODE, int MIN_BLOCKS, bool WIDE, bool BGLOBAL>
+//            BX = the entries of B beyond b_cap (only the deepest forward passes reach them).
+template <int MODE, int MIN_BLOCKS, bool WIDE>
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
 	typedef BEntry<WIDE> BE;
@@ -39,40 +42,37 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	const int pair = threadIdx.x >> 1;
 	const int gpair = blockIdx.x * (SEED_BLOCK / 2) + pair;
 	const u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;   // this pair's shared memory
-	const u32 sq = sp + COLD_BYTES, sb = sq + (u32)p.q_stride;
+	const u32 sb = sp;                                       // B entries first (16-byte aligned)
+	const u32 sc = sp + (u32)p.b_cap * BE::BYTES;            // cold state
+	const u32 sq = sc + COLD_BYTES;                          // query, two bases per byte
 	Intv *const M1 = p.scratch + (size_t)gpair * 3 * p.scratch_cap;
 	Intv *const BX = M1 + 2 * p.scratch_cap;
 
 	u64 policy = 0;
 	if (p.hot_min_intv) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
 
+	// B beyond b_cap spills to global memory through an out-of-line slow path: one compare + a branch that is
+	// (almost) never taken on the hot path, and correctness never depends on b_cap
 	auto b_put = [&](int idx, u64 x0, u64 x1, u64 x2, u32 end) {
-		if (!BGLOBAL) BE::put(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
-		else st_intv(&BX[idx], x0, x1, x2, (u64)end);
+		if (__builtin_expect(idx < p.b_cap, 1)) BE::put(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		else bx_put(&BX[idx], x0, x1, x2, end);
 	};
 	auto b_get = [&](int idx, u64 &x0, u64 &x1, u64 &x2, u32 &end) {
-		if (!BGLOBAL) BE::get(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
-		else { const Intv t = ld_intv(&BX[idx]); x0 = t.x0; x1 = t.x1; x2 = t.x2; end = (u32)t.info; }
-	};
-	const int b_lim = BGLOBAL ? p.scratch_cap : p.b_cap;
-	// give up on this read in this launch: the host re-runs it with B in global memory
-	auto abandon = [&]() {
-		const int rk = lds_i32(sp + CS_RK);
-		p.counts[rk] = 0;
-		if (!half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sp + CS_RID); atomicMax(&p.status[3], 1); }
+		if (__builtin_expect(idx < p.b_cap, 1)) BE::get(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		else { const Intv t = bx_get(&BX[idx]); x0 = t.x0; x1 = t.x1; x2 = t.x2; end = (u32)t.info; }
 	};
 	// bwt.c:815-820: a hit that cannot be extended is recorded unless a longer match already covers it
 	auto emit = [&](u64 x0, u64 x1, u64 x2, u32 end, int st) {
-		const int n_mem = lds_i32(sp + CS_NMEM);
-		if (n_mem == 0 || st < lds_i32(sp + CS_LMS)) {
-			Intv *M = M1 + (size_t)lds_i32(sp + CS_PASS) * p.scratch_cap;
+		const int n_mem = lds_u16(sc + CS_NMEM);
+		if (n_mem == 0 || st < lds_u16(sc + CS_LMS)) {
+			Intv *M = M1 + (size_t)lds_u16(sc + CS_PASS) * p.scratch_cap;
 			st_intv(&M[n_mem], x0, x1, x2, (u64)end | ((u64)st << 32));
-			sts_i32(sp + CS_NMEM, n_mem + 1);
-			sts_i32(sp + CS_LMS, st);
+			sts_u16(sc + CS_NMEM, n_mem + 1);
+			sts_u16(sc + CS_LMS, st);
 			const int l = (int)end - st;
-			if (l >= lds_i32(sp + CS_MAXLEN)) {          // ">=": the first maximum in ascending start order wins (bwamem.c:266-270)
-				sts_i32(sp + CS_MAXLEN, l); sts_i32(sp + CS_MAXSTART, st); sts_i32(sp + CS_MAXEND, (int)end);
-				sts_i32(sp + CS_MAXS_LO, (int)(u32)x2); sts_i32(sp + CS_MAXS_HI, (int)(u32)(x2 >> 32));
+			if (l >= lds_u16(sc + CS_MAXLEN)) {          // ">=": the first maximum in ascending start order wins (bwamem.c:266-270)
+				sts_u16(sc + CS_MAXLEN, l); sts_u16(sc + CS_MAXSTART, st); sts_u16(sc + CS_MAXEND, (int)end);
+				sts_i32(sc + CS_MAXS_LO, (int)(u32)x2); sts_i32(sc + CS_MAXS_HI, (int)(u32)(x2 >> 32));
 			}
 		}
 	};
@@ -93,72 +93,74 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			switch (phase) {
 			case PH_NEED_READ: {
 				int rk = 0;
-				if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(sp + CS_RK, rk); }
+				if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(sc + CS_RK, rk); }
 				__syncwarp(3u << (lane & ~1));
-				rk = lds_i32(sp + CS_RK);
+				rk = lds_i32(sc + CS_RK);
 				if ((long long)rk >= p.n) { if (!half && max_count > 0) atomicMax(&p.status[4], max_count); phase = PH_IDLE; break; }
 				const int rid = p.list ? p.list[rk] : rk;
 				const long long o0 = p.offs[rid];
 				const uint8_t *q = p.seq + o0;
 				len = (int)(p.offs[rid + 1] - o0);
-				for (int t = half; t < len; t += 2) sts_u8(sq + t, q[t]);     // stage the query in shared memory
+				for (int t = half; 2 * t < len; t += 2) {                    // stage the query, two bases per byte (0..3, else 4)
+					const u32 b0 = min((u32)q[2 * t], 4u), b1 = 2 * t + 1 < len ? min((u32)q[2 * t + 1], 4u) : 4u;
+					sts_u8(sq + t, b0 | (b1 << 4));
+				}
 				__syncwarp(3u << (lane & ~1));
-				sts_i32(sp + CS_RID, rid); sts_i32(sp + CS_NOUT, 0); sts_i32(sp + CS_START, 0); sts_i32(sp + CS_STEP, 0);
+				sts_i32(sc + CS_RID, rid); sts_i32(sc + CS_NOUT, 0); sts_u16(sc + CS_START, 0); sts_u16(sc + CS_STEP, 0);
 				if (MODE == MODE_COLLECT) {
-					sts_i32(sp + CS_SPLIT, p.split_len_init < len ? p.split_len_init : len);     // bwamem.c:458
+					sts_u16(sc + CS_SPLIT, p.split_len_init < len ? p.split_len_init : len);     // bwamem.c:458
 					phase = PH_NEXT_STEP;
 				} else {
 					const int x = p.xs[rid], mi = p.min_intvs[rid];
 					min_intv = mi < 1 ? 1 : (u64)mi;                                              // bwt.c:784
-					sts_i32(sp + CS_PASS, 0); sts_i32(sp + CS_X, x);
-					if (x < 0 || x >= len || lds_u8(sq + x) > 3) {                                // bwt.c:783
+					sts_u16(sc + CS_PASS, 0); sts_u16(sc + CS_X, x);
+					if (x < 0 || x >= len || qbase(sq, x) > 3) {                                // bwt.c:783
 						p.ret[rid] = x + 1; p.counts[rk] = 0; phase = PH_NEED_READ;
 					} else phase = PH_INIT_CALL;
 				}
 			} break;
 			case PH_NEXT_STEP: {     // head of smem_next2, bwamem.c:249-258
-				int start = lds_i32(sp + CS_START);
-				while (start < len && lds_u8(sq + start) > 3) ++start;
+				int start = lds_u16(sc + CS_START);
+				while (start < len && qbase(sq, start) > 3) ++start;
 				if (start >= len) {
-					const int rk = lds_i32(sp + CS_RK), n_out = lds_i32(sp + CS_NOUT);
+					const int rk = lds_i32(sc + CS_RK), n_out = lds_i32(sc + CS_NOUT);
 					p.counts[rk] = n_out;
 					max_count = max(max_count, n_out);
-					if (n_out > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sp + CS_RID); atomicMax(&p.status[3], n_out); }
+					if (n_out > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sc + CS_RID); atomicMax(&p.status[3], n_out); }
 					phase = PH_NEED_READ;
 					break;
 				}
-				sts_i32(sp + CS_START, start); sts_i32(sp + CS_ORI, start); sts_i32(sp + CS_X, start); sts_i32(sp + CS_PASS, 0);
+				sts_u16(sc + CS_START, start); sts_u16(sc + CS_ORI, start); sts_u16(sc + CS_X, start); sts_u16(sc + CS_PASS, 0);
 				min_intv = p.start_width < 1 ? 1 : (u64)p.start_width;
 				phase = PH_INIT_CALL;
 			} break;
 			case PH_INIT_CALL: {     // bwt_set_intv, bwt.c:788-789, then the head of the forward loop
-				const int x = lds_i32(sp + CS_X);
-				const int c0 = (int)lds_u8(sq + x);
+				const int x = lds_u16(sc + CS_X);
+				const int c0 = (int)qbase(sq, x);
 				a = p.ix.L2[3 - c0] + 1;             // is_back = 0 walks x[1]
 				b = p.ix.L2[c0] + 1;
 				s = p.ix.L2[c0 + 1] - p.ix.L2[c0];
 				end = (u32)(x + 1);
 				i = x + 1; n_curr = 0;
-				sts_i32(sp + CS_NMEM, 0); sts_i32(sp + CS_MAXLEN, 0); sts_i32(sp + CS_MAXSTART, 0); sts_i32(sp + CS_MAXEND, 0);
-				sts_i32(sp + CS_MAXS_LO, 0); sts_i32(sp + CS_MAXS_HI, 0);
+				sts_u16(sc + CS_NMEM, 0); sts_u16(sc + CS_MAXLEN, 0); sts_u16(sc + CS_MAXSTART, 0); sts_u16(sc + CS_MAXEND, 0);
+				sts_i32(sc + CS_MAXS_LO, 0); sts_i32(sc + CS_MAXS_HI, 0);
 				guard = 2 * (len + 2) * (len + 2) + 64;   // > every extend one bwt_smem1 can issue
-				const u32 qv = i < len ? lds_u8(sq + i) : 4u;
+				const u32 qv = i < len ? qbase(sq, i) : 4u;
 				if (qv > 3) phase = PH_FWD_END;
 				else { c = 3 - (int)qv; phase = PH_FWD; }     // bwt.c:793: forward extension uses the complement
 			} break;
 			case PH_FWD_END: {       // bwt.c:800-803 (ambiguous base) / :806 (end of read): push the last interval
-				if (n_curr >= b_lim) { abandon(); phase = PH_NEED_READ; break; }
 				b_put(n_curr++, b, a, s, end);
 				phase = PH_FWD_DONE;
 			} break;
 			case PH_FWD_DONE: {      // bwt.c:807-809: "reverse curr" == address B from its top (n0 - 1 - j)
 				n0 = n_curr; n_prev = n_curr; n_curr = 0;
-				i = lds_i32(sp + CS_X) - 1; j = 0;
-				c = i < 0 ? -1 : (int)lds_u8(sq + i);
+				i = lds_u16(sc + CS_X) - 1; j = 0;
+				c = i < 0 ? -1 : (int)qbase(sq, i);
 				if (c > 3) c = -1;
 				b_get(n0 - 1, a, b, s, end);             // prev[0] = the last push; its info is bwt_smem1's return value
-				sts_i32(sp + CS_RET, (int)end);
-				if (MODE == MODE_COLLECT && lds_i32(sp + CS_PASS) == 0) sts_i32(sp + CS_START, (int)end);   // bwamem.c:262
+				sts_u16(sc + CS_RET, (int)end);
+				if (MODE == MODE_COLLECT && lds_u16(sc + CS_PASS) == 0) sts_u16(sc + CS_START, (int)end);   // bwamem.c:262
 				phase = c < 0 ? PH_BWD_LAST : PH_BWD;
 			} break;
 			case PH_BWD_LAST: {
@@ -168,29 +170,29 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				phase = PH_CALL_DONE;
 			} break;
 			case PH_CALL_DONE: {
-				const int rk = lds_i32(sp + CS_RK), n_mem = lds_i32(sp + CS_NMEM);
+				const int rk = lds_i32(sc + CS_RK), n_mem = lds_u16(sc + CS_NMEM);
 				Intv *const slot = p.slots + (size_t)rk * p.slot_cap;
 				const Intv *const M2 = M1 + p.scratch_cap;
 				if (MODE == MODE_SMEM1) {
-					const int rid = lds_i32(sp + CS_RID);
+					const int rid = lds_i32(sc + CS_RID);
 					for (int e = n_mem - 1, o = 0; e >= 0; --e, ++o)             // bwt.c:829: ascending start
 						if (o < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[o], t.x0, t.x1, t.x2, t.info); }
-					p.counts[rk] = n_mem; p.ret[rid] = lds_i32(sp + CS_RET);
+					p.counts[rk] = n_mem; p.ret[rid] = lds_u16(sc + CS_RET);
 					max_count = max(max_count, n_mem);
 					if (n_mem > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_mem); }
 					phase = PH_NEED_READ;
 					break;
 				}
-				const int step = lds_i32(sp + CS_STEP);
+				const int step = lds_u16(sc + CS_STEP);
 				const u64 tag = (u64)step << STEP_SHIFT;
-				int n_out = lds_i32(sp + CS_NOUT);
-				if (lds_i32(sp + CS_PASS) == 0) {
-					const int max_len = lds_i32(sp + CS_MAXLEN), split_len = lds_i32(sp + CS_SPLIT);
-					const u64 max_s = (u64)(u32)lds_i32(sp + CS_MAXS_LO) | ((u64)(u32)lds_i32(sp + CS_MAXS_HI) << 32);
+				int n_out = lds_i32(sc + CS_NOUT);
+				if (lds_u16(sc + CS_PASS) == 0) {
+					const int max_len = lds_u16(sc + CS_MAXLEN), split_len = lds_u16(sc + CS_SPLIT);
+					const u64 max_s = (u64)(u32)lds_i32(sc + CS_MAXS_LO) | ((u64)(u32)lds_i32(sc + CS_MAXS_HI) << 32);
 					// bwamem.c:272: re-seed from the middle of the longest SMEM if it is long and (nearly) unique
 					if (n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width) {
-						sts_i32(sp + CS_NM1, n_mem); sts_i32(sp + CS_KEEP, max_len); sts_i32(sp + CS_PASS, 1);
-						sts_i32(sp + CS_X, (lds_i32(sp + CS_MAXEND) + lds_i32(sp + CS_MAXSTART)) >> 1);
+						sts_u16(sc + CS_NM1, n_mem); sts_u16(sc + CS_KEEP, max_len); sts_u16(sc + CS_PASS, 1);
+						sts_u16(sc + CS_X, (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1);
 						min_intv = max_s + 1;
 						phase = PH_INIT_CALL;
 						break;
@@ -201,8 +203,8 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					}
 				} else {
 					// ordered merge, bwamem.c:281-301; both lists are walked in ascending start = reverse emission
-					int ia = lds_i32(sp + CS_NM1) - 1, ib = n_mem - 1;
-					const int half_len = lds_i32(sp + CS_KEEP) >> 1, ori_start = lds_i32(sp + CS_ORI);
+					int ia = lds_u16(sc + CS_NM1) - 1, ib = n_mem - 1;
+					const int half_len = lds_u16(sc + CS_KEEP) >> 1, ori_start = lds_u16(sc + CS_ORI);
 					Intv va, vb;
 					va.x0 = va.x1 = va.x2 = va.info = 0; vb = va;
 					bool have_a = false, have_b = false;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 						}
 					}
 				}
-				sts_i32(sp + CS_NOUT, n_out); sts_i32(sp + CS_STEP, step + 1);
+				sts_i32(sc + CS_NOUT, n_out); sts_u16(sc + CS_STEP, step + 1);
 				phase = PH_NEXT_STEP;
 			} break;
 			default: break;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// idle pairs ride along on the interval (1,1,1): its block is hot in L2 and the result is dropped
 		const Ext ok = extend_pair(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, policy);
 		if (phase == PH_IDLE) continue;
-		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sp + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
+		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 
 		// ============================================================== consume the result, set up the next extend
 		// (forward: bwt.c:794-799, backward: bwt.c:813-824; written once for both so that the warp does not
@@ -254,7 +256,6 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		if (push) {
 			// forward pushes the interval it leaves (ik), backward the one it arrives at (ok[c], info inherited)
 			const int idx = fwd ? n_curr : n0 - 1 - n_curr;      // backward: n_curr <= j, lands at or behind the slot just read
-			if (idx >= b_lim) { abandon(); phase = PH_NEED_READ; continue; }
 			b_put(idx, fwd ? b : ok.a, fwd ? a : ok.b, fwd ? s : ok.s, end);
 			++n_curr;
 			last_s = ok.s;
@@ -263,14 +264,14 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			if (diff && small) { phase = PH_FWD_DONE; continue; }
 			a = ok.a; b = ok.b; s = ok.s; end = (u32)(i + 1);
 			++i;
-			const u32 qv = i < len ? lds_u8(sq + i) : 4u;
+			const u32 qv = i < len ? qbase(sq, i) : 4u;
 			if (qv > 3) phase = PH_FWD_END;
 			else c = 3 - (int)qv;
 		} else {
 			if (++j == n_prev) {                             // bwt.c:826-827
 				if (n_curr == 0) { phase = PH_CALL_DONE; continue; }
 				n_prev = n_curr; n_curr = 0; j = 0; --i;
-				c = i < 0 ? -1 : (int)lds_u8(sq + i);
+				c = i < 0 ? -1 : (int)qbase(sq, i);
 				if (c > 3) c = -1;
 				if (c < 0) phase = PH_BWD_LAST;
 			}
@@ -316,23 +317,85 @@ __global__ void repack_kernel(const u32 *__restrict__ src, u64 n_blocks, u64 seq
 }
 
 // ---------------------------------------------------------------------------------------------
-// counts -> CSR offsets is done with one CUB exclusive scan on the host side (plumbing).
-// Compaction: slots[n][slot_cap] -> dense intv[total] (+ optional step array), info restored.
-__global__ void compact_kernel(const Intv *__restrict__ slots, int slot_cap, int width, const int *__restrict__ counts,
-                               const long long *__restrict__ off, long long n, Intv *__restrict__ out,
-                               unsigned short *__restrict__ step_out)
+// counts -> CSR offsets: a small three-kernel exclusive scan (int counts -> int64 offsets).  Hand-written
+// rather than a library scan so that its CTAs (128 threads, few registers, 32 B of shared memory) fit into
+// the slots a running persistent seed kernel leaves free: with several pipeline lanes on one GPU the scan and
+// compaction of a finished lane run next to the following lane's seed kernel.
+#define SCAN_TPB 128
+#define SCAN_PER_THREAD 8
+#define SCAN_PER_BLOCK (SCAN_TPB * SCAN_PER_THREAD)
+
+__global__ void __launch_bounds__(SCAN_TPB) scan_local_kernel(const int *__restrict__ counts, long long n, long long *__restrict__ off,
+                                                              long long *__restrict__ bsum)
 {
-	// `width` = min(slot_cap, largest count of the batch): one thread per (read, entry < width)
+	__shared__ long long wsum[SCAN_TPB / 32];
+	const long long base = (long long)blockIdx.x * SCAN_PER_BLOCK + (long long)threadIdx.x * SCAN_PER_THREAD;
+	int v[SCAN_PER_THREAD];
+	long long t = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_PER_THREAD; ++k) { v[k] = base + k < n ? counts[base + k] : 0; t += v[k]; }
+	long long incl = t;                                  // inclusive scan of the thread totals inside the warp
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const long long o = __shfl_up_sync(FULL_MASK, incl, d); if ((threadIdx.x & 31) >= d) incl += o; }
+	if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	long long woff = 0, total = 0;
+#pragma unroll
+	for (int w = 0; w < SCAN_TPB / 32; ++w) { if (w < (int)(threadIdx.x >> 5)) woff += wsum[w]; total += wsum[w]; }
+	long long run = woff + incl - t;
+#pragma unroll
+	for (int k = 0; k < SCAN_PER_THREAD; ++k) { if (base + k < n) off[base + k] = run; run += v[k]; }
+	if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+// exclusive scan of the block sums in place (one CTA; nb <= a few thousand)
+__global__ void __launch_bounds__(SCAN_TPB) scan_bsum_kernel(long long *__restrict__ bsum, int nb)
+{
+	__shared__ long long wsum[SCAN_TPB / 32];
+	__shared__ long long carry_s;
+	if (threadIdx.x == 0) carry_s = 0;
+	__syncthreads();
+	for (int b0 = 0; b0 < nb; b0 += SCAN_TPB) {
+		const int i = b0 + threadIdx.x;
+		const long long t = i < nb ? bsum[i] : 0;
+		long long incl = t;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const long long o = __shfl_up_sync(FULL_MASK, incl, d); if ((threadIdx.x & 31) >= d) incl += o; }
+		if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		long long woff = 0, total = 0;
+#pragma unroll
+		for (int w = 0; w < SCAN_TPB / 32; ++w) { if (w < (int)(threadIdx.x >> 5)) woff += wsum[w]; total += wsum[w]; }
+		const long long carry = carry_s;
+		if (i < nb) bsum[i] = carry + woff + incl - t;
+		__syncthreads();
+		if (threadIdx.x == 0) carry_s = carry + total;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) scan_add_kernel(long long *__restrict__ off, long long n, const long long *__restrict__ bsum)
+{
+	const long long i = (long long)blockIdx.x * SCAN_TPB + threadIdx.x;
+	if (i < n) off[i] += bsum[i / SCAN_PER_BLOCK];
+}
+
+// Compaction: slots[n][slot_cap] -> dense intv[total] (+ optional step array), info restored.
+// Eight lanes per read, each copying entries lane, lane+8, ... (most reads have <= 16 intervals).
+__global__ void __launch_bounds__(128) compact_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
+                                                      const long long *__restrict__ off, long long n, Intv *__restrict__ out,
+                                                      unsigned short *__restrict__ step_out)
+{
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const long long r = t / width;
-	const int e = (int)(t - r * width);
+	const long long r = t >> 3;
 	if (r >= n) return;
-	const int c = counts[r];
-	if (e >= c) return;          // entries beyond slot_cap are filled in by the overflow re-run
-	const Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
-	const long long o = off[r] + e;
-	st_intv(&out[o], v.x0, v.x1, v.x2, v.info & ((1ull << STEP_SHIFT) - 1));
-	if (step_out) step_out[o] = (unsigned short)(v.info >> STEP_SHIFT);
+	const int c = min(counts[r], slot_cap);      // entries beyond slot_cap are filled in by the overflow re-run
+	const long long o0 = off[r];
+	for (int e = (int)(t & 7); e < c; e += 8) {
+		const Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
+		st_intv(&out[o0 + e], v.x0, v.x1, v.x2, v.info & ((1ull << STEP_SHIFT) - 1));
+		if (step_out) step_out[o0 + e] = (unsigned short)(v.info >> STEP_SHIFT);
+	}
 }
 
 // Overflow re-run placement: big_slots[k][big_cap] of read list[k] -> dense output at off[list[k]].

@@ -66,7 +66,10 @@ enum {
 
 /* Replaces HelloALINLBApp::run's service/buffer allocation (HelloALINLB.cpp:309-380).
  * device_ids may be NULL (= 0..n_devices-1). max_batch_reads / max_read_len size the device
- * buffers (per handle, split across devices). */
+ * buffers (per handle, split across devices).  A device id may be listed several times: each
+ * occurrence is an independent pipeline lane (own stream, buffers and host thread) on that GPU, so
+ * that within one smem_gpu_collect the H2D copy, the kernels and the D2H copy of different
+ * shards overlap; lanes of one GPU share a single copy of the index. */
 int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int64_t max_batch_reads, int max_read_len);
 int smem_gpu_destroy(smem_gpu_t *h);
 

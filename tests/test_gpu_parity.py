@@ -119,7 +119,7 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
     a = o.collect(seq, offs, OSeedOpt(), nthreads=8)
     try:
         for name, val in [("slot_cap", 2), ("slot_cap", 128), ("blocks_per_sm", 3), ("blocks_per_sm", 12), ("blocks_per_sm", 6),
-                          ("b_cap", 2), ("b_cap", 7), ("force_wide", 1), ("b_cap", 24), ("force_wide", 0),
+                          ("b_cap", 2), ("b_cap", 7), ("force_wide", 1), ("b_cap", 19), ("force_wide", 0),
                           ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0)]:
             g.set_param(name, val)
             b = g.collect(seq, offs)
@@ -127,8 +127,8 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
             if name == "slot_cap" and val == 2:
                 assert g.timing()["overflow_reads"] > 0
     finally:
-        g.set_param("slot_cap", 128); g.set_param("blocks_per_sm", 6); g.set_param("l2_hot_min_intv", 0)
-        g.set_param("b_cap", 24); g.set_param("force_wide", 0)
+        g.set_param("slot_cap", 128); g.set_param("blocks_per_sm", 8); g.set_param("l2_hot_min_intv", 0)
+        g.set_param("b_cap", 19); g.set_param("force_wide", 0)
 
 
 def test_staged_run_is_idempotent_and_capacity_error(world, synth, sg):
@@ -183,3 +183,18 @@ def test_two_gpu_handle_matches_single(world, synth, sg):
     mi = rng.integers(0, 4, 9001).astype(np.int32)
     same_result(o.smem1(seq, offs, x, mi), g2.smem1(seq, offs, x, mi), ("read_off", "intv", "ret"))
     g2.close()
+
+
+def test_pipeline_lanes_on_one_gpu(world, synth, sg):
+    """A device listed several times = several pipeline lanes sharing one index copy; same results."""
+    ref, ix, o, g = world
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 7003, 101, 0.02, seed=123, n_frac=0.05))
+    a = o.collect(seq, offs, OSeedOpt(), nthreads=8)
+    g4 = sg.SmemGpu(max_batch_reads=8_000, max_read_len=128, devices=[0, 0, 0, 0])
+    g4.upload_index(ix)
+    for _ in range(2):
+        b = g4.collect(seq, offs)
+        same_result(a, b, ("read_off", "intv", "step"))
+    g4.upload_index(ix)            # re-upload must not leak or double-free the shared copy
+    same_result(a, g4.collect(seq, offs), ("read_off", "intv", "step"))
+    g4.close()
