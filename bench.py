@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
+    ap.add_argument("--batch-sweep", action="store_true", help="BASELINE config 5: latency/throughput of smem_gpu_collect for 64..1M reads per call, L2 hint off/on")
+    ap.add_argument("--full-compare", action="store_true", help="compare every interval of the step with the oracle (config 2)")
     return ap.parse_args()
 
 
@@ -172,7 +174,7 @@ def main():
         eng, kind = cpu_engine(ixh)
         opt = OSeedOpt()
         probe = cpu_time(eng, seq, offs, min(n, 20_000), ncores, opt)
-        per_step = max(10_000, min(n, int(probe["reads_per_s"] * min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))))
+        per_step = min(n, max(10_000, int(probe["reads_per_s"] * min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))))
         for _ in range(args.warmup):
             cpu_time(eng, seq, offs, per_step, ncores, opt)
         t0 = time.perf_counter()
@@ -223,7 +225,7 @@ def main():
         if not args.skip_cpu:
             eng, kind = cpu_engine(ixh)
             probe = cpu_time(eng, seq, offs, min(n, 20_000), ncores, OSeedOpt())
-            m = max(20_000, min(n, int(probe["reads_per_s"] * args.cpu_seconds)))
+            m = min(n, max(20_000, int(probe["reads_per_s"] * args.cpu_seconds)))
             r = cpu_time(eng, seq, offs, m, ncores, OSeedOpt())
             one = cpu_time(eng, seq, offs, min(m, 20_000), 1, OSeedOpt())
             gk = g.collect(seq[: int(offs[m])], offs[: m + 1], opt, want_step=False)
@@ -250,13 +252,14 @@ def main():
         for item in args.sweep.split(","):
             f = item.split(":")
             b, hot = f[0], (f[1] if len(f) > 1 and f[1] else "0")
+            g.set_param("prefetch", int(f[3]) if len(f) > 3 else 0)
             g.set_param("blocks_per_sm", int(b)); g.set_param("l2_hot_min_intv", int(hot))
             g.set_param("b_cap", int(f[2]) if len(f) > 2 else keep[2])
             ms = []
             for _ in range(4):
                 g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
-            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
-        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2])
+            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} prefetch={g.get_param('prefetch')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
+        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("prefetch", 0)
     for _ in range(max(args.warmup, 3)):
         total = g.run_collect(opt)
     sampler = ClockSampler(local)
@@ -307,6 +310,47 @@ def main():
     dt_e2e = time.perf_counter() - t1
     te = g.timing()
 
+    # ---- optional: every interval of the step against the oracle (BASELINE config 2)
+    if args.full_compare and rank == 0:
+        from oracle.binding import Oracle
+        fm = importlib.import_module("bwa-mem-harp2_b200.fmindex")
+        ixh = fm.BwtIndex(ix.primary, ix.L2, ix.seq_len, ix.bwt_size, ix.words_numpy())
+        t0c = time.time()
+        want = Oracle(ixh).collect(seq, offs, OSeedOpt(), nthreads=ncores)
+        same = (np.array_equal(want["read_off"], proff.array) and np.array_equal(want["intv"], pintv.array[:tot_e2e]))
+        log(f"full compare: {n} reads, {len(want['intv'])} intervals, bit_exact={same} (oracle {time.time() - t0c:.1f}s)")
+        parity = dict(parity or {}, full_compare_reads=n, full_compare_intervals=int(len(want["intv"])), full_compare_bit_exact=bool(same))
+        if not same:
+            raise SystemExit("PARITY FAILURE in --full-compare")
+
+    # ---- optional: batch-size sweep (BASELINE config 5): one smem_gpu_collect call of B reads, host buffers
+    batch_sweep = None
+    if args.batch_sweep and rank == 0:
+        batch_sweep = []
+        for hot in (0, 16384):
+            g.set_param("l2_hot_min_intv", hot)
+            for B in (64, 256, 1024, 4096, 16384, 65536, 262144, 1048576):
+                if B > n:
+                    continue
+                o = poffs.array[: B + 1]
+                s_ = pseq.array[: int(o[-1])]
+                def call():
+                    tot = C.c_int64(0)
+                    rc = lib.smem_gpu_collect(g.h, C.c_int64(B), s_.ctypes.data_as(C.POINTER(C.c_uint8)), o.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              C.byref(opt), pintv.array.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(pintv.array.shape[0]),
+                                              proff.array.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(tot))
+                    assert rc == 0, rc
+                for _ in range(3):
+                    call()
+                reps = 20 if B <= 16384 else 5
+                tb = time.perf_counter()
+                for _ in range(reps):
+                    call()
+                ms = (time.perf_counter() - tb) / reps * 1e3
+                batch_sweep.append({"reads_per_call": B, "l2_hot_min_intv": hot, "latency_ms": round(ms, 3), "reads_per_s": round(B / ms * 1e3)})
+                log(f"batch sweep B={B} l2_hot_min_intv={hot}: {ms:.3f} ms/call -> {B / ms / 1e3:.2f} M reads/s")
+        g.set_param("l2_hot_min_intv", 0)
+
     # ---- max over ranks
     times = torch.tensor([dt, dt_e2e, float(np.mean(seed_ms))], dtype=torch.float64, device=device)
     if use_dist:
@@ -336,6 +380,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        traffic = None
+        try:   # dram__bytes_read + dram__bytes_write of seed_kernel from the committed `ncu --set full` capture of this workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "seed_traffic.json")))
+            if tr.get("ref_bp") == args.ref_bp and tr.get("reads") == args.reads and tr.get("read_len") == args.read_len:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         value = world * n * args.steps / dt
         achieved = n * bytes_per_read / (seed_avg_ms * 1e-3) / 1e9
         out = {
@@ -347,7 +398,7 @@ def main():
                     "pipeline_lanes_per_gpu": args.lanes, "intervals": int(tot_e2e)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "seed_kernel<COLLECT>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "seed_kernel<COLLECT>",
                          "kernel_ms": seed_avg_ms, "algorithmic_bytes_per_read": bytes_per_read,
                          "random_access_peak": rand64, "frac_of_random_access": achieved / rand64 if rand64 else None,
                          "random_access_peak_two_requests": rand64_split,
@@ -359,6 +410,8 @@ def main():
         }
         if probe:
             out["random_access_probe_gbs"] = probe
+        if batch_sweep:
+            out["batch_sweep"] = batch_sweep
         print(json.dumps(out), flush=True)
     if use_dist:
         dist.barrier()

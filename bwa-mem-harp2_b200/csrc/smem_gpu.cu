@@ -85,6 +85,7 @@ struct smem_gpu {
 	int force_wide = 0;
 	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
 	int chain_lanes = 0;             // 1: lane k's seed kernel waits for lane k-1's (no tail overlap)
+	int prefetch = 0;                // L2 look-ahead for the backward sweep: measured 37 % SLOWER (adds DRAM requests), kept as a knob
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
 	uint64_t epoch = 0;              // bumped per run; orders the lanes' seed kernels
 	uint64_t stage_epoch = 0;        // bumped per staging; orders the lanes' H2D copies
@@ -245,13 +246,13 @@ int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const
 	return 0;
 }
 
-template <int MODE, bool WIDE>
+template <int MODE, bool WIDE, bool PREFETCH>
 int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem)
 {
-#define LAUNCH(B)                                                                                                        \
-	do {                                                                                                                 \
-		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-		seed_kernel<MODE, B, WIDE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
+#define LAUNCH(B)                                                                                                                  \
+	do {                                                                                                                           \
+		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+		seed_kernel<MODE, B, WIDE, PREFETCH><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
 	} while (0)
 	switch (blocks_per_sm) {
 	case 4: LAUNCH(4); break;
@@ -271,9 +272,10 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 }
 
 template <int MODE>
-int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide)
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide, bool prefetch)
 {
-	return wide ? launch_seed_w<MODE, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false>(d, p, blocks_per_sm, grid, smem);
+	if (prefetch) return wide ? launch_seed_w<MODE, true, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, true>(d, p, blocks_per_sm, grid, smem);
+	return wide ? launch_seed_w<MODE, true, false>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, false>(d, p, blocks_per_sm, grid, smem);
 }
 
 // Lanes of one GPU run their seed kernels strictly in lane order: lane k waits (on the device) for lane k-1's
@@ -366,7 +368,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		lk.unlock();
 		CK(cudaStreamWaitEvent(d.stream, d.prev_lane->ev1, 0));
 	}
-	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide);
+	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.prefetch != 0) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.prefetch != 0);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
 	lane_mark_issued(d, h);
@@ -407,7 +409,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
 			p2.overflow_list = d.d_counts_k + n_over;
 			const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
-			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide);
+			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide, h.prefetch != 0) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide, h.prefetch != 0);
 			if (rc) return rc;
 			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 			CK(cudaStreamSynchronize(d.stream));
@@ -620,6 +622,7 @@ int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int6
 	smem_gpu *h = new (std::nothrow) smem_gpu();
 	if (!h) return SMEM_GPU_E_NOMEM;
 	h->max_batch = max_batch_reads; h->max_len = max_read_len;
+	h->slot_cap = std::max(128, (max_read_len + 31) / 32 * 32);      // long reads emit more intervals (250 bp: 48 on average)
 	h->devs.resize(n_devices);
 	const int64_t per = (max_batch_reads + n_devices - 1) / n_devices;
 	for (int k = 0; k < n_devices; ++k) {
@@ -747,6 +750,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "force_wide")) { h->force_wide = v != 0; return 0; }
 	if (!strcmp(name, "spare_sms")) { if (v < 0 || v > 64) return SMEM_GPU_E_ARG; h->spare_sms = (int)v; return 0; }
 	if (!strcmp(name, "chain_lanes")) { h->chain_lanes = v != 0; return 0; }
+	if (!strcmp(name, "prefetch")) { h->prefetch = v != 0; return 0; }
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
@@ -767,6 +771,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "b_cap")) return h->b_cap;
 	if (!strcmp(name, "spare_sms")) return h->spare_sms;
 	if (!strcmp(name, "chain_lanes")) return h->chain_lanes;
+	if (!strcmp(name, "prefetch")) return h->prefetch;
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
 	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }

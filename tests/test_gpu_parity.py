@@ -120,7 +120,7 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
     try:
         for name, val in [("slot_cap", 2), ("slot_cap", 128), ("blocks_per_sm", 3), ("blocks_per_sm", 12), ("blocks_per_sm", 6),
                           ("b_cap", 2), ("b_cap", 7), ("force_wide", 1), ("b_cap", 19), ("force_wide", 0),
-                          ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0)]:
+                          ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0), ("prefetch", 1), ("prefetch", 0)]:
             g.set_param(name, val)
             b = g.collect(seq, offs)
             same_result(a, b, ("read_off", "intv", "step"))
