@@ -31,6 +31,8 @@ struct DeviceCtx {
 	size_t index_bytes = 0;
 	DevIndex ix{};
 	bool has_index = false;
+	u64 *d_sa = nullptr; bool owns_sa = true; int sa_shift = -1; u64 n_sa = 0;
+	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
 	bool owns_index = true;          // false: d_index aliases the copy of an earlier context on the same GPU
 	int lane = 0, lanes_on_dev = 1;  // pipeline lane of this context on its GPU
 	DeviceCtx *prev_lane = nullptr;  // the lane whose seed kernel runs right before this one's
@@ -164,6 +166,8 @@ void ctx_free(DeviceCtx &d)
 {
 	cudaSetDevice(d.dev);
 	if (d.owns_index) cudaFree(d.d_index);
+	if (d.owns_sa) cudaFree(d.d_sa);
+	cudaFree(d.d_k); cudaFree(d.d_kout);
 	cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
 	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
@@ -653,6 +657,45 @@ int smem_gpu_destroy(smem_gpu_t *h)
 	return 0;
 }
 
+int ctx_upload_sa(DeviceCtx &d, int sa_shift, u64 n_sa, const uint64_t *sa, int src_device)
+{
+	CK(cudaSetDevice(d.dev));
+	if (d.d_sa && d.owns_sa) CK(cudaFree(d.d_sa));
+	d.d_sa = nullptr; d.owns_sa = true; d.sa_shift = -1;
+	CK(cudaMalloc((void **)&d.d_sa, (size_t)n_sa * 8));
+	if (src_device < 0) CK(cudaMemcpyAsync(d.d_sa, sa, (size_t)n_sa * 8, cudaMemcpyHostToDevice, d.stream));
+	else if (src_device == d.dev) CK(cudaMemcpyAsync(d.d_sa, sa, (size_t)n_sa * 8, cudaMemcpyDeviceToDevice, d.stream));
+	else CK(cudaMemcpyPeerAsync(d.d_sa, d.dev, sa, src_device, (size_t)n_sa * 8, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	d.sa_shift = sa_shift; d.n_sa = n_sa;
+	return 0;
+}
+
+int ctx_sa(DeviceCtx &d, const uint64_t *k, uint64_t *out)
+{
+	CK(cudaSetDevice(d.dev));
+	const int64_t n = d.hi - d.lo;
+	if (n == 0) return 0;
+	if (!d.has_index || d.sa_shift < 0) { d.err = "index or suffix-array samples not uploaded"; return SMEM_GPU_E_NOINDEX; }
+	if ((size_t)n > d.k_cap) {
+		if (d.d_k) CK(cudaFree(d.d_k));
+		if (d.d_kout) CK(cudaFree(d.d_kout));
+		d.d_k = d.d_kout = nullptr; d.k_cap = 0;
+		CK(cudaMalloc((void **)&d.d_k, (size_t)n * 8)); CK(cudaMalloc((void **)&d.d_kout, (size_t)n * 8));
+		d.k_cap = (size_t)n;
+	}
+	CK(cudaMemcpyAsync(d.d_k, k + d.lo, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+	const int grid = (int)std::min<int64_t>((int64_t)d.sm_count * 8, (n + 63) / 64);
+	sa_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, n, d.d_k, d.d_kout, d.d_status);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out + d.lo, d.d_kout, (size_t)n * 8, cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	if (d.h_status[2] != 0) { d.err = "suffix-array walk did not terminate (corrupt index?)"; return SMEM_GPU_E_INTERNAL; }
+	return 0;
+}
+
 // One copy of the index per physical GPU: contexts that share a device (several pipeline lanes on one GPU,
 // see smem_gpu_create) alias the first one's copy.
 static int upload_all(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device)
@@ -684,6 +727,36 @@ int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int
 {
 	if (!h || !ix || !ix->bwt || ix->bwt_size < 16 || src_device < 0) return SMEM_GPU_E_ARG;
 	return upload_all(h, ix, src_device);
+}
+
+int smem_gpu_upload_sa(smem_gpu_t *h, int sa_intv, uint64_t n_sa, const uint64_t *sa, int src_device)
+{
+	if (!h || !sa || n_sa < 1 || sa_intv < 1 || (sa_intv & (sa_intv - 1))) return SMEM_GPU_E_ARG;   // power of two (bwt.c:85-86)
+	int shift = 0;
+	while ((1 << shift) < sa_intv) ++shift;
+	int rc = for_each_device(h, [&](DeviceCtx &d) {
+		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }
+		return ctx_upload_sa(d, shift, n_sa, sa, src_device);
+	});
+	if (rc) return rc;
+	for (auto &d : h->devs)
+		for (auto &o : h->devs) {
+			if (&o == &d) break;
+			if (o.dev == d.dev) {
+				if (d.d_sa && d.owns_sa) { cudaSetDevice(d.dev); cudaFree(d.d_sa); }
+				d.d_sa = o.d_sa; d.owns_sa = false; d.sa_shift = o.sa_shift; d.n_sa = o.n_sa;
+				break;
+			}
+		}
+	return 0;
+}
+
+int smem_gpu_sa(smem_gpu_t *h, int64_t n, const uint64_t *k, uint64_t *out)
+{
+	if (!h || n < 0 || (n > 0 && (!k || !out))) return SMEM_GPU_E_ARG;
+	shard(h, n);
+	h->staged = -1; h->ran = false;
+	return for_each_device(h, [&](DeviceCtx &d) { return ctx_sa(d, k, out); });
 }
 
 int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs)

@@ -432,6 +432,45 @@ __global__ void add_base_kernel(long long *off, long long n, long long base)
 }
 
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Seed -> reference position: bwt_sa (bwt.c:104-114) for a batch of suffix-array rows.
+// Each step is bwt_invPsi (bwt.c:71-77) = the symbol at the row + one bwt_occ (bwt.c:125-147): one occ block,
+// fetched by a lane pair with one request like everywhere else; the walk ends at a sampled row (expected
+// sa_intv steps).  `sa` are the samples of bwt_cal_sa (bwt.c:79-101), sa[0] = -1.
+__global__ void __launch_bounds__(128) sa_kernel(const DevIndex ix, const u64 *__restrict__ sa, int sa_shift, long long n,
+                                                 const u64 *__restrict__ ks, u64 *__restrict__ out, int *__restrict__ status)
+{
+	const int lane = threadIdx.x & 31, half = lane & 1;
+	const long long gpair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1, npairs = ((long long)gridDim.x * blockDim.x) >> 1;
+	const u64 mask = (1ull << sa_shift) - 1;
+	for (long long q0 = gpair; __any_sync(FULL_MASK, q0 < n); q0 += npairs) {
+		const bool have = q0 < n;
+		u64 k = have ? ks[q0] : 0, steps = 0;
+		while (__any_sync(FULL_MASK, have && (k & mask) != 0)) {
+			const bool act = have && (k & mask) != 0;
+			const bool at_primary = k == ix.primary;                       // bwt_invPsi returns 0 there (bwt.c:76)
+			const u64 kk = at_primary ? 0 : k - (k >= ix.primary);          // '$' is not stored (bwt.c:133); == k - (k > primary) here
+			u32 w[8];
+			ld_sector(w, ix.blk + (kk >> 7) * 4 + half * 2);
+			const int pos = (int)(kk & 127), bit = pos & 63, sh = 31 - (bit & 31);
+			const u32 hw = bit < 32 ? w[4] : w[5], lw = bit < 32 ? w[6] : w[7];
+			const int cm = (int)((((hw >> sh) & 1u) << 1) | ((lw >> sh) & 1u));       // bwt_B0 (bwt.h:78), valid in the half that owns pos
+			const int c = __shfl_sync(FULL_MASK, cm, (lane & ~1) | (pos >> 6));
+			const int r = min(max(pos + 1 - 64 * half, 0), 64);             // symbols of my half that count
+			const u32 m0 = __funnelshift_rc(0u, 0xffffffffu, r), m1 = __funnelshift_rc(0u, 0xffffffffu, max(r - 32, 0));
+			const u32 h0 = (c & 2) ? w[4] : ~w[4], h1 = (c & 2) ? w[5] : ~w[5], l0 = (c & 1) ? w[6] : ~w[6], l1 = (c & 1) ? w[7] : ~w[7];
+			u32 cnt = __popc(h0 & l0 & m0) + __popc(h1 & l1 & m1);
+			cnt += __shfl_xor_sync(FULL_MASK, cnt, 1);
+			const u64 base_mine = (c & 1) ? ((u64)w[2] | ((u64)w[3] << 32)) : ((u64)w[0] | ((u64)w[1] << 32));
+			const u64 base = __shfl_sync(FULL_MASK, base_mine, (lane & ~1) | (c >> 1));
+			const u64 kn = at_primary ? 0 : ix.L2[c] + base + cnt;
+			if (act) { k = kn; ++steps; }
+			if (steps > (1ull << 24)) { if (act && !half) atomicAdd(&status[2], 1); k = 0; }   // guard: corrupt index
+		}
+		if (have && !half) out[q0] = steps + sa[k >> sa_shift];
+	}
+}
+
 // Random-access roofline probe: every thread walks a dependent chain of
 // aligned BYTES-sized gathers over `n_units` units; the next address is a hash of the data just
 // loaded, so nothing can be prefetched or coalesced -- the access pattern of bwt_occ4.

@@ -37,6 +37,34 @@ class BwtIndex:
     seq_len: int
     bwt_size: int         # in uint32 words
     bwt: "np.ndarray | torch.Tensor"   # uint32/int32 words, length bwt_size
+    sa_intv: int = 0      # 0 = no suffix-array samples
+    sa: "np.ndarray | torch.Tensor | None" = None   # uint64/int64 [n_sa]: SA of every sa_intv-th row, sa[0] = -1 (bwt.c:79-101)
+
+    def sa_numpy(self) -> np.ndarray:
+        if isinstance(self.sa, torch.Tensor):
+            return self.sa.cpu().numpy().view(np.uint64)
+        return np.asarray(self.sa).view(np.uint64)
+
+    def save_sa(self, path: str) -> None:
+        """The reference's ``.sa`` file format (bwt_dump_sa, bwt.c:852-864)."""
+        with open(path, "wb") as f:
+            f.write(struct.pack("<Q", self.primary))
+            f.write(np.asarray(self.L2[1:5], dtype="<u8").tobytes())
+            f.write(struct.pack("<QQ", self.sa_intv, self.seq_len))
+            self.sa_numpy()[1:].tofile(f)
+
+    @staticmethod
+    def load_sa(path: str):
+        """Returns (sa_intv, sa uint64[n_sa]) from a reference ``.sa`` file (bwt_restore_sa, bwt.c:877-897)."""
+        with open(path, "rb") as f:
+            f.read(40)
+            intv, seq_len = struct.unpack("<QQ", f.read(16))
+            rest = np.fromfile(f, dtype=np.uint64)
+        sa = np.empty(rest.size + 1, dtype=np.uint64)
+        sa[0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        sa[1:] = rest
+        assert sa.size == (seq_len + intv) // intv
+        return int(intv), sa
 
     def words_numpy(self) -> np.ndarray:
         if isinstance(self.bwt, torch.Tensor):
@@ -130,8 +158,10 @@ def _refine_ties(P: torch.Tensor, pos: torch.Tensor, keys: torch.Tensor, n: int)
     return pos
 
 
-def bwt_string(T: torch.Tensor, bucket_syms: int | None = None) -> tuple[torch.Tensor, int]:
-    """BWT of T$ with the ``$`` removed (uint8 symbols) and ``primary`` (is_bwt / bwt_bwtgen semantics)."""
+def bwt_string(T: torch.Tensor, bucket_syms: int | None = None, sa_intv: int = 0):
+    """BWT of T$ with the ``$`` removed (uint8 symbols) and ``primary`` (is_bwt / bwt_bwtgen semantics).
+    With ``sa_intv`` also returns the suffix-array samples of bwt_cal_sa (bwt.c:79-101): SA of every
+    sa_intv-th row of the sorted rotations of T$ (row 0 = "$"), sa[0] = -1."""
     n = int(T.numel())
     dev = T.device
     if bucket_syms is None:
@@ -140,7 +170,12 @@ def bwt_string(T: torch.Tensor, bucket_syms: int | None = None) -> tuple[torch.T
     out = torch.empty(n, dtype=torch.uint8, device=dev)
     out[0] = T[n - 1]            # row 0 is the empty suffix "$"
     primary = -1
-    row = 1                      # next SA row to fill
+    row = 1                      # next output index to fill (= SA row until the '$' row is skipped)
+    sa_row = 1                   # SA row of the next sorted suffix
+    sa = None
+    if sa_intv:
+        sa = torch.zeros((n + sa_intv) // sa_intv, dtype=torch.int64, device=dev)
+        sa[0] = -1
     nb = 4 ** bucket_syms
     if bucket_syms:
         code = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -165,6 +200,12 @@ def bwt_string(T: torch.Tensor, bucket_syms: int | None = None) -> tuple[torch.T
         pos = _refine_ties(P, pos, keys, n)
         del keys
         m = int(pos.numel())
+        if sa_intv:
+            first = (-sa_row) % sa_intv
+            if first < m:
+                sel = torch.arange(first, m, sa_intv, device=dev, dtype=torch.int64)
+                sa[(sa_row + sel) // sa_intv] = pos[sel]
+        sa_row += m
         zero = torch.nonzero(pos == 0).view(-1)
         ch = T[torch.clamp(pos - 1, min=0)]
         if zero.numel():
@@ -178,6 +219,8 @@ def bwt_string(T: torch.Tensor, bucket_syms: int | None = None) -> tuple[torch.T
             row += m
         del pos, ch
     assert primary >= 0 and row == n
+    if sa_intv:
+        return out, primary, sa
     return out, primary
 
 
@@ -224,13 +267,18 @@ def pack_bwt(bstr: torch.Tensor, primary: int) -> BwtIndex:
     return BwtIndex(int(primary), l2, n, int(bwt_size), words)
 
 
-def build_index(fwd: "torch.Tensor | np.ndarray", device: "str | torch.device | None" = None) -> BwtIndex:
-    """Forward reference symbols (0..3, all contigs concatenated) -> packed FM-index."""
+def build_index(fwd: "torch.Tensor | np.ndarray", device: "str | torch.device | None" = None, sa_intv: int = 0) -> BwtIndex:
+    """Forward reference symbols (0..3, all contigs concatenated) -> packed FM-index (+ SA samples if sa_intv)."""
     if isinstance(fwd, np.ndarray):
         fwd = torch.from_numpy(np.ascontiguousarray(fwd, dtype=np.uint8))
     if device is not None:
         fwd = fwd.to(device)
     T = text_from_forward(fwd)
-    bstr, primary = bwt_string(T)
+    if sa_intv:
+        bstr, primary, sa = bwt_string(T, sa_intv=sa_intv)
+    else:
+        (bstr, primary), sa = bwt_string(T), None
     del T
-    return pack_bwt(bstr, primary)
+    ix = pack_bwt(bstr, primary)
+    ix.sa_intv, ix.sa = sa_intv, sa
+    return ix

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -155,6 +155,25 @@ class SmemGpu:
             words = np.ascontiguousarray(index.words_numpy(), np.uint32)
             desc.bwt = words.ctypes.data
             self._check(self.lib.smem_gpu_upload_index(self.h, C.byref(desc)))
+
+    def upload_sa(self, index):
+        """Suffix-array samples of ``index`` (sa_intv, sa) -> HBM, for :meth:`sa`."""
+        sa = index.sa
+        if hasattr(sa, "is_cuda") and sa.is_cuda:
+            import torch
+            torch.cuda.synchronize(sa.device)
+            self._check(self.lib.smem_gpu_upload_sa(self.h, C.c_int(int(index.sa_intv)), C.c_uint64(sa.numel()), C.c_void_p(sa.data_ptr()),
+                                                    C.c_int(sa.device.index or 0)))
+        else:
+            a = np.ascontiguousarray(index.sa_numpy(), np.uint64)
+            self._check(self.lib.smem_gpu_upload_sa(self.h, C.c_int(int(index.sa_intv)), C.c_uint64(a.size), C.c_void_p(a.ctypes.data), C.c_int(-1)))
+
+    def sa(self, k):
+        """bwt_sa (bwt.c:104) for a batch of suffix-array rows."""
+        k = np.ascontiguousarray(k, np.uint64)
+        out = np.zeros(len(k), np.uint64)
+        self._check(self.lib.smem_gpu_sa(self.h, C.c_int64(len(k)), _p(k, C.c_uint64), _p(out, C.c_uint64)))
+        return out
 
     # -- one-call forms (host buffers in, host buffers out)
     def collect(self, seq, offs, opt: "SeedOpt | None" = None, want_step=True, cap_hint: "int | None" = None):

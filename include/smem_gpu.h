@@ -95,6 +95,13 @@ int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int
                    const int32_t *x, const int32_t *min_intv, smem_intv_t *intv_out, int64_t intv_cap,
                    int64_t *read_off, int32_t *ret, int64_t *total_out);
 
+/* Seed -> reference position (the step right after the path; bwamem.c:420,474):
+ * upload the suffix-array samples of bwt_t (sa_intv, n_sa, sa; bwt.c:79-101, sa[0] = -1) once, then
+ * out[i] = bwt_sa(bwt, k[i]) (bwt.c:104-114) for a batch of suffix-array rows.  src_device < 0: `sa` is a host
+ * pointer, else a device pointer on that CUDA device. */
+int smem_gpu_upload_sa(smem_gpu_t *h, int sa_intv, uint64_t n_sa, const uint64_t *sa, int src_device);
+int smem_gpu_sa(smem_gpu_t *h, int64_t n, const uint64_t *k, uint64_t *out);
+
 /* Split form of smem_gpu_collect, so that seeding can be timed with inputs resident in HBM:
  * stage (H2D) -> run (kernels only, may be repeated) -> fetch (D2H). */
 int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs);

@@ -142,6 +142,14 @@ class Oracle(_Base):
         self.lib.orc_extend(C.byref(self.ix), (C.c_uint64 * 3)(*[int(v) for v in ik3]), C.c_int(is_back), ok)
         return np.array(list(ok), dtype=np.uint64).reshape(4, 3)
 
+    def sa(self, index, k):
+        """bwt_sa for every k; ``index`` carries sa_intv / sa samples."""
+        k = np.ascontiguousarray(k, np.uint64)
+        sa = np.ascontiguousarray(index.sa_numpy(), np.uint64)
+        out = np.zeros(len(k), np.uint64)
+        self.lib.orc_sa(C.byref(self.ix), C.c_int(int(index.sa_intv)), _p(sa, C.c_uint64), C.c_int64(len(k)), _p(k, C.c_uint64), _p(out, C.c_uint64))
+        return out
+
     def checksum(self, intv, read_off):
         intv = np.ascontiguousarray(intv, np.uint64)
         read_off = np.ascontiguousarray(read_off, np.int64)
@@ -189,6 +197,15 @@ class Reference(_Base):
         cnt = (C.c_uint64 * 4)()
         self.lib.ref_occ4(self.h, C.c_uint64(k & 0xFFFFFFFFFFFFFFFF), cnt)
         return [int(v) for v in cnt]
+
+    def sa(self, index, k):
+        k = np.ascontiguousarray(k, np.uint64)
+        sa = np.ascontiguousarray(index.sa_numpy(), np.uint64)
+        out = np.zeros(len(k), np.uint64)
+        self.lib.ref_bwt_set_sa(self.h, C.c_int(int(index.sa_intv)), C.c_uint64(len(sa)), C.c_void_p(sa.ctypes.data))
+        self.lib.ref_sa(self.h, C.c_int64(len(k)), _p(k, C.c_uint64), _p(out, C.c_uint64))
+        self.lib.ref_bwt_clear_sa(self.h)
+        return out
 
     def extend(self, ik3, is_back: int):
         ok = (C.c_uint64 * 12)()

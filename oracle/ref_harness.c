@@ -82,6 +82,19 @@ void ref_extend(const void *p, const uint64_t ik3[3], int is_back, uint64_t ok12
 	for (i = 0; i < 4; ++i) { ok12[3*i] = ok[i].x[0]; ok12[3*i+1] = ok[i].x[1]; ok12[3*i+2] = ok[i].x[2]; }
 }
 
+/* Attach caller-owned SA samples to a bwt_t (view or loaded) and call the reference's bwt_sa (bwt.c:104). */
+void ref_bwt_set_sa(void *p, int sa_intv, uint64_t n_sa, uint64_t *sa)
+{
+	bwt_t *b = (bwt_t *)p;
+	b->sa_intv = sa_intv; b->n_sa = n_sa; b->sa = sa;
+}
+void ref_bwt_clear_sa(void *p) { ((bwt_t *)p)->sa = 0; ((bwt_t *)p)->n_sa = 0; }
+void ref_sa(const void *p, int64_t n, const uint64_t *k, uint64_t *out)
+{
+	int64_t i;
+	for (i = 0; i < n; ++i) out[i] = bwt_sa((const bwt_t *)p, k[i]);
+}
+
 /* ---------------- growable flat result ---------------- */
 typedef struct { uint64_t *v; uint16_t *step; int64_t n, m; } flat_t;
 static void flat_push(flat_t *f, const bwtintv_t *p, int step)

@@ -302,6 +302,38 @@ int64_t orc_collect(const orc_index_t *ix, int64_t n, const uint8_t *seq, const 
 	return total;
 }
 
+/* ------------------------------------------------------------------ seed -> reference position */
+/* bwt_occ, bwt.c:125-147: occurrences of base c in BWT[0..k] */
+uint64_t orc_occ(const orc_index_t *ix, uint64_t k, int c)
+{
+	uint64_t cnt[4];
+	if (k == ix->seq_len) return ix->L2[c + 1] - ix->L2[c];
+	if (k == (uint64_t)-1) return 0;
+	orc_occ4(ix, k, cnt);
+	return cnt[c];
+}
+
+/* bwt_invPsi, bwt.c:71-77 */
+static uint64_t inv_psi(const orc_index_t *ix, uint64_t k)
+{
+	uint64_t x = k - (k > ix->primary);
+	int c = (int)((ix->bwt[((x >> 7) << 4) + 8 + ((x & 127) >> 4)] >> ((~x & 15) << 1)) & 3);   /* bwt_B0, bwt.h:78 */
+	uint64_t r = ix->L2[c] + orc_occ(ix, k, c);
+	return k == ix->primary ? 0 : r;
+}
+
+/* bwt_sa, bwt.c:104-114 */
+void orc_sa(const orc_index_t *ix, int sa_intv, const uint64_t *sa, int64_t n, const uint64_t *k, uint64_t *out)
+{
+	int64_t i;
+	const uint64_t mask = (uint64_t)sa_intv - 1;
+	for (i = 0; i < n; ++i) {
+		uint64_t kk = k[i], steps = 0;
+		while (kk & mask) { ++steps; kk = inv_psi(ix, kk); }
+		out[i] = steps + sa[kk / (uint64_t)sa_intv];
+	}
+}
+
 /* ------------------------------------------------------------------ checksum + timing arm */
 #define FNV_BASIS 0xcbf29ce484222325ull
 #define FNV_PRIME 0x100000001b3ull

@@ -52,6 +52,11 @@ int64_t orc_collect(const orc_index_t *ix, int64_t n, const uint8_t *seq, const 
 /* Timing arm ("kind": "port"): wall seconds, checksum as in ref_time_collect. */
 double orc_time_collect(const orc_index_t *ix, int64_t n, const uint8_t *seq, const int64_t *offs,
                         const orc_seed_opt_t *opt, int nthreads, uint64_t *checksum, int64_t *n_intervals);
+/* Seed -> reference position: bwt_sa (bwt.c:104-114) over bwt_invPsi (bwt.c:71-77)
+ * and bwt_occ (bwt.c:125-147).  sa = the samples of bwt_cal_sa (bwt.c:79-101), sa[0] = -1. */
+uint64_t orc_occ(const orc_index_t *ix, uint64_t k, int c);
+void orc_sa(const orc_index_t *ix, int sa_intv, const uint64_t *sa, int64_t n, const uint64_t *k, uint64_t *out);
+
 /* Order-independent-across-reads checksum of a flat result (same definition as the timing arms). */
 uint64_t orc_checksum(int64_t n, const uint64_t *intv, const int64_t *read_off);
 
