@@ -33,6 +33,8 @@ struct DeviceCtx {
 	bool has_index = false;
 	u64 *d_sa = nullptr; bool owns_sa = true; int sa_shift = -1; u64 n_sa = 0;
 	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
+	int *d_scnt = nullptr; long long *d_soff = nullptr, *d_sroff = nullptr; size_t s_cap = 0, sroff_cap = 0;
+	Seed *d_seeds = nullptr; size_t seeds_cap = 0; long long n_seeds = 0;
 	bool owns_index = true;          // false: d_index aliases the copy of an earlier context on the same GPU
 	int lane = 0, lanes_on_dev = 1;  // pipeline lane of this context on its GPU
 	DeviceCtx *prev_lane = nullptr;  // the lane whose seed kernel runs right before this one's
@@ -151,7 +153,7 @@ int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int
 	d.out_cap = (size_t)read_cap * 16 + 1024;
 	if ((rc = dev_alloc(d, &d.d_out, d.out_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_step, d.out_cap))) return rc;
-	CK(cudaMallocHost((void **)&d.h_status, 64));
+	CK(cudaMallocHost((void **)&d.h_status, 128));
 	// per-pair scratch for the default launch geometry (re-grown in ctx_run if blocks_per_sm is raised): allocating
 	// it lazily would delay the first lane's first kernel by a cudaMalloc
 	d.scratch_entries = (size_t)d.sm_count * 9 * (SEED_BLOCK / 2) * 3 * (size_t)(max_len + 2);
@@ -167,7 +169,7 @@ void ctx_free(DeviceCtx &d)
 	cudaSetDevice(d.dev);
 	if (d.owns_index) cudaFree(d.d_index);
 	if (d.owns_sa) cudaFree(d.d_sa);
-	cudaFree(d.d_k); cudaFree(d.d_kout);
+	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
 	cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
 	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
@@ -696,6 +698,84 @@ int ctx_sa(DeviceCtx &d, const uint64_t *k, uint64_t *out)
 	return 0;
 }
 
+// counts (int) -> exclusive offsets (int64) with the library's own three-kernel scan; n1 elements
+int run_scan(DeviceCtx &d, const int *counts, long long n1, long long *off)
+{
+	const int nb = (int)((n1 + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
+	if ((size_t)(nb + 2) * sizeof(long long) > d.tmp_bytes) {
+		CK(cudaFree(d.d_tmp)); d.d_tmp = nullptr;
+		d.tmp_bytes = (size_t)(nb + 2) * sizeof(long long) * 2;
+		CK(cudaMalloc(&d.d_tmp, d.tmp_bytes));
+	}
+	long long *bsum = (long long *)d.d_tmp;
+	scan_local_kernel<<<nb, SCAN_TPB, 0, d.stream>>>(counts, n1, off, bsum);
+	scan_bsum_kernel<<<1, SCAN_TPB, 0, d.stream>>>(bsum, nb);
+	scan_add_kernel<<<(unsigned)((n1 + SCAN_TPB - 1) / SCAN_TPB), SCAN_TPB, 0, d.stream>>>(off, n1, bsum);
+	CK(cudaGetLastError());
+	d.launches += 3;
+	return 0;
+}
+
+// intervals of the last run (d_out, d_off) -> seeds in HBM; d.n_seeds
+int ctx_seeds_run(DeviceCtx &d, int min_seed_len, u64 max_occ)
+{
+	CK(cudaSetDevice(d.dev));
+	d.n_seeds = 0;
+	if (d.n == 0) return 0;
+	if (d.sa_shift < 0) { d.err = "suffix-array samples not uploaded"; return SMEM_GPU_E_NOINDEX; }
+	const long long total = d.total;
+	if ((size_t)total + 1 > d.s_cap) {
+		if (d.d_scnt) CK(cudaFree(d.d_scnt));
+		if (d.d_soff) CK(cudaFree(d.d_soff));
+		d.d_scnt = nullptr; d.d_soff = nullptr; d.s_cap = 0;
+		const size_t cap = (size_t)total + (size_t)total / 8 + 1024;
+		CK(cudaMalloc((void **)&d.d_scnt, cap * sizeof(int))); CK(cudaMalloc((void **)&d.d_soff, cap * sizeof(long long)));
+		d.s_cap = cap;
+	}
+	if ((size_t)d.n + 1 > d.sroff_cap) {
+		if (d.d_sroff) CK(cudaFree(d.d_sroff));
+		d.d_sroff = nullptr; d.sroff_cap = 0;
+		CK(cudaMalloc((void **)&d.d_sroff, ((size_t)d.n + 1) * sizeof(long long)));
+		d.sroff_cap = (size_t)d.n + 1;
+	}
+	seed_count_kernel<<<(unsigned)((total + 1 + 255) / 256), 256, 0, d.stream>>>(d.d_out, total, min_seed_len, max_occ, d.d_scnt);
+	CK(cudaGetLastError());
+	int rc = run_scan(d, d.d_scnt, total + 1, d.d_soff);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(d.h_status + 8, d.d_soff + total, 8, cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	memcpy(&d.n_seeds, d.h_status + 8, 8);
+	if ((size_t)d.n_seeds > d.seeds_cap) {
+		if (d.d_seeds) CK(cudaFree(d.d_seeds));
+		d.d_seeds = nullptr; d.seeds_cap = 0;
+		const size_t cap = (size_t)d.n_seeds + (size_t)d.n_seeds / 8 + 1024;
+		CK(cudaMalloc((void **)&d.d_seeds, cap * sizeof(Seed)));
+		d.seeds_cap = cap;
+	}
+	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+	if (d.n_seeds > 0 && total > 0) {
+		const int grid = (int)std::min<int64_t>((int64_t)d.sm_count * 8, (d.n_seeds + 63) / 64);
+		seed_expand_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, d.d_out, total, d.d_soff, d.n_seeds, d.d_seeds, d.d_status);
+		CK(cudaGetLastError());
+	}
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	if (d.h_status[2] != 0) { d.err = "suffix-array walk did not terminate (corrupt index?)"; return SMEM_GPU_E_INTERNAL; }
+	return 0;
+}
+
+int ctx_seeds_fetch(DeviceCtx &d, smem_seed_t *seeds_out, int64_t *seed_off, long long base)
+{
+	CK(cudaSetDevice(d.dev));
+	if (d.n == 0) return 0;
+	seed_read_off_kernel<<<(unsigned)((d.n + 1 + 255) / 256), 256, 0, d.stream>>>(d.d_off, d.d_soff, d.n, base, d.d_sroff);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(seed_off + d.lo, d.d_sroff, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));
+	if (seeds_out && d.n_seeds) CK(cudaMemcpyAsync(seeds_out + base, d.d_seeds, (size_t)d.n_seeds * sizeof(Seed), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	return 0;
+}
+
 // One copy of the index per physical GPU: contexts that share a device (several pipeline lanes on one GPU,
 // see smem_gpu_create) alias the first one's copy.
 static int upload_all(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device)
@@ -757,6 +837,26 @@ int smem_gpu_sa(smem_gpu_t *h, int64_t n, const uint64_t *k, uint64_t *out)
 	shard(h, n);
 	h->staged = -1; h->ran = false;
 	return for_each_device(h, [&](DeviceCtx &d) { return ctx_sa(d, k, out); });
+}
+
+int smem_gpu_seeds(smem_gpu_t *h, int min_seed_len, int64_t max_occ, smem_seed_t *seeds_out, int64_t seeds_cap, int64_t *seed_off,
+                   int64_t *total_out)
+{
+	if (!h || !seed_off || max_occ < 0) return SMEM_GPU_E_ARG;
+	if (!h->ran || h->staged < 0) { h->err = "no resident results: run smem_gpu_collect or smem_gpu_run_collect first"; return SMEM_GPU_E_ARG; }
+	static_assert(sizeof(Seed) == sizeof(smem_seed_t), "seed layout");
+	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_seeds_run(d, min_seed_len, (u64)max_occ); });
+	if (rc) return rc;
+	long long tot = 0;
+	std::vector<long long> base(h->devs.size());
+	for (size_t k = 0; k < h->devs.size(); ++k) { base[k] = tot; tot += h->devs[k].n_seeds; }
+	if (total_out) *total_out = tot;
+	const bool fits = tot <= seeds_cap && (seeds_out || tot == 0);
+	rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_seeds_fetch(d, fits ? seeds_out : nullptr, seed_off, base[&d - &h->devs[0]]); });
+	if (rc) return rc;
+	seed_off[h->staged] = tot;
+	if (!fits) { h->err = "seeds_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	return 0;
 }
 
 int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs)

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -174,6 +174,23 @@ class SmemGpu:
         out = np.zeros(len(k), np.uint64)
         self._check(self.lib.smem_gpu_sa(self.h, C.c_int64(len(k)), _p(k, C.c_uint64), _p(out, C.c_uint64)))
         return out
+
+    SEED_DTYPE = np.dtype([("rbeg", np.int64), ("qbeg", np.int32), ("len", np.int32)])
+
+    def seeds(self, n_reads: int, min_seed_len=19, max_occ=10000):
+        """mem_seed_t list of the last run's intervals (bwamem.c:408-424): structured array + CSR offsets per read."""
+        seed_off = np.zeros(n_reads + 1, np.int64)
+        tot = C.c_int64(0)
+        cap = max(64, 4 * n_reads)
+        while True:
+            out = np.zeros(cap, self.SEED_DTYPE)
+            rc = self.lib.smem_gpu_seeds(self.h, C.c_int(min_seed_len), C.c_int64(max_occ), C.c_void_p(out.ctypes.data), C.c_int64(cap),
+                                         _p(seed_off, C.c_int64), C.byref(tot))
+            if rc == -5 and tot.value > cap:
+                cap = int(tot.value)
+                continue
+            self._check(rc)
+            return dict(seeds=out[:int(tot.value)], seed_off=seed_off)
 
     # -- one-call forms (host buffers in, host buffers out)
     def collect(self, seq, offs, opt: "SeedOpt | None" = None, want_step=True, cap_hint: "int | None" = None):

@@ -102,6 +102,17 @@ int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int
 int smem_gpu_upload_sa(smem_gpu_t *h, int sa_intv, uint64_t n_sa, const uint64_t *sa, int src_device);
 int smem_gpu_sa(smem_gpu_t *h, int64_t n, const uint64_t *k, uint64_t *out);
 
+/* == mem_seed_t (bwamem.c:316-319) */
+typedef struct { int64_t rbeg; int32_t qbeg, len; } smem_seed_t;
+
+/* Intervals -> seeds, on the results of the last run that are still resident in HBM (smem_gpu_collect or
+ * smem_gpu_run_collect): every interval with seed length >= min_seed_len and x[2] <= max_occ (the filter of
+ * bwamem.c:412,467) is expanded into its x[2] seeds {rbeg = bwt_sa(x[0] + t), qbeg, len} (bwamem.c:420-424,
+ * 474-476), in interval order, then t.  seed_off = int64[n_reads + 1], CSR per read.  Needs smem_gpu_upload_sa.
+ * The reference's later per-seed tests (forward/reverse boundary, bwamem.c:426,478) are left to the caller. */
+int smem_gpu_seeds(smem_gpu_t *h, int min_seed_len, int64_t max_occ, smem_seed_t *seeds_out, int64_t seeds_cap,
+                   int64_t *seed_off, int64_t *total_out);
+
 /* Split form of smem_gpu_collect, so that seeding can be timed with inputs resident in HBM:
  * stage (H2D) -> run (kernels only, may be repeated) -> fetch (D2H). */
 int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs);

@@ -67,3 +67,31 @@ def test_gpu_sa_vs_oracle_and_seed_positions(world_sa, synth):
         hit[i] |= int(r) == int(pos[i])
     assert hit.all()
     g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_seeds_vs_oracle(world_sa, synth):
+    """smem_gpu_seeds == the seed loop of mem_insert_seed (bwamem.c:462-476) rebuilt from oracle intervals + oracle bwt_sa."""
+    sg = pkg("smem_gpu")
+    ref, ix, o = world_sa
+    refn = ref.numpy().copy()
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 6001, 101, 0.02, seed=11, n_frac=0.05))
+    for devices, (min_seed_len, max_occ) in (([0], (19, 10000)), ([0, 0, 0], (25, 3))):
+        g = sg.SmemGpu(max_batch_reads=8192, max_read_len=128, devices=devices)
+        g.upload_index(ix); g.upload_sa(ix)
+        res = g.collect(seq, offs)
+        got = g.seeds(len(offs) - 1, min_seed_len, max_occ)
+        want = o.collect(seq, offs, SeedOpt(), nthreads=4)
+        rows, qb, ln, cnt = [], [], [], np.zeros(len(offs) - 1, np.int64)
+        for i in range(len(offs) - 1):
+            for iv in want["intv"][want["read_off"][i]:want["read_off"][i + 1]]:
+                s, e = int(iv[3]) >> 32, int(iv[3]) & 0xFFFFFFFF
+                if e - s < min_seed_len or int(iv[2]) > max_occ:
+                    continue
+                for t in range(int(iv[2])):
+                    rows.append(int(iv[0]) + t); qb.append(s); ln.append(e - s); cnt[i] += 1
+        rbeg = o.sa(ix, np.array(rows, np.uint64)).astype(np.int64)
+        assert np.array_equal(got["seed_off"], np.concatenate([[0], np.cumsum(cnt)]))
+        assert np.array_equal(got["seeds"]["rbeg"], rbeg)
+        assert np.array_equal(got["seeds"]["qbeg"], np.array(qb, np.int32)) and np.array_equal(got["seeds"]["len"], np.array(ln, np.int32))
+        g.close()
