@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
     ap.add_argument("--batch-sweep", action="store_true", help="BASELINE config 5: latency/throughput of smem_gpu_collect for 64..1M reads per call, L2 hint off/on")
+    ap.add_argument("--seeds", action="store_true", help="also time collect + smem_gpu_seeds (section 8f-1: intervals -> mem_seed_t on device)")
     ap.add_argument("--full-compare", action="store_true", help="compare every interval of the step with the oracle (config 2)")
     return ap.parse_args()
 
@@ -110,7 +111,7 @@ def make_workload(args, rank, device):
     sy = importlib.import_module("bwa-mem-harp2_b200.synth")
     t0 = time.time()
     fwd = sy.make_reference(args.ref_bp, 13, device)
-    ix = fm.build_index(fwd)
+    ix = fm.build_index(fwd, sa_intv=32 if getattr(args, 'seeds', False) else 0)
     torch.cuda.synchronize()
     t_index = time.time() - t0
     reads = sy.simulate_reads(fwd, args.reads, args.read_len, args.err, seed=1000 + rank, paired=True)
@@ -310,6 +311,32 @@ def main():
     dt_e2e = time.perf_counter() - t1
     te = g.timing()
 
+    # ---- optional: the seed-level API (section 8f-1): stage -> collect -> seeds -> D2H of mem_seed_t only
+    seeds_leg = None
+    if args.seeds:
+        g.upload_sa(ix)
+        seed_off = sg.PinnedArray(lib, (n + 1,), np.int64)
+        pseeds = sg.PinnedArray(lib, (8 * n, 2), np.int64)
+        def seeds_step():
+            g.stage(pseq.array, poffs.array)
+            g.run_collect(opt)
+            tot = C.c_int64(0)
+            rc = lib.smem_gpu_seeds(g.h, C.c_int(19), C.c_int64(10000), C.c_void_p(pseeds.array.ctypes.data), C.c_int64(pseeds.array.shape[0]),
+                                    seed_off.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(tot))
+            assert rc == 0, (rc, lib.smem_gpu_last_error(g.h))
+            return int(tot.value)
+        for _ in range(2):
+            seeds_step()
+        sync()
+        ts = time.perf_counter()
+        for _ in range(args.steps):
+            n_seeds = seeds_step()
+        sync()
+        dts = time.perf_counter() - ts
+        seeds_leg = {"value": world * n * args.steps / dts, "unit": "reads/s", "ms_per_step": dts / args.steps * 1e3, "seeds_per_step_per_gpu": n_seeds,
+                     "d2h_bytes_per_step": n_seeds * 16 + (n + 1) * 8, "note": "host reads in -> mem_seed_t {rbeg,qbeg,len} out (min_seed_len 19, max_occ 10000)"}
+        log("seeds leg:", seeds_leg)
+
     # ---- optional: every interval of the step against the oracle (BASELINE config 2)
     if args.full_compare and rank == 0:
         from oracle.binding import Oracle
@@ -412,6 +439,8 @@ def main():
             out["random_access_probe_gbs"] = probe
         if batch_sweep:
             out["batch_sweep"] = batch_sweep
+        if seeds_leg:
+            out["seeds_api"] = seeds_leg
         print(json.dumps(out), flush=True)
     if use_dist:
         dist.barrier()

@@ -437,45 +437,49 @@ __global__ void add_base_kernel(long long *off, long long n, long long base)
 // Each step is bwt_invPsi (bwt.c:71-77) = the symbol at the row + one bwt_occ (bwt.c:125-147): one occ block,
 // fetched by a lane pair with one request like everywhere else; the walk ends at a sampled row (expected
 // sa_intv steps).  `sa` are the samples of bwt_cal_sa (bwt.c:79-101), sa[0] = -1.
-// The walk of one row, executed by a converged warp of lane pairs (`have` = this pair has a row).
-__device__ __forceinline__ u64 sa_walk(const DevIndex &ix, const u64 *__restrict__ sa, int sa_shift, u64 k, bool have, int half, int lane,
-                                       int *__restrict__ status)
+// One bwt_invPsi step (bwt.c:71-77), executed by a converged warp of lane pairs; pairs without work ride along.
+__device__ __forceinline__ u64 inv_psi_pair(const DevIndex &ix, u64 k, int half, int lane)
 {
-	const u64 mask = (1ull << sa_shift) - 1;
-	u64 steps = 0;
-	while (__any_sync(FULL_MASK, have && (k & mask) != 0)) {
-		const bool act = have && (k & mask) != 0;
-		const bool at_primary = k == ix.primary;                       // bwt_invPsi returns 0 there (bwt.c:76)
-		const u64 kk = at_primary ? 0 : k - (k >= ix.primary);          // '$' is not stored (bwt.c:133); == k - (k > primary) here
-		u32 w[8];
-		ld_sector(w, ix.blk + (kk >> 7) * 4 + half * 2);
-		const int pos = (int)(kk & 127), bit = pos & 63, sh = 31 - (bit & 31);
-		const u32 hw = bit < 32 ? w[4] : w[5], lw = bit < 32 ? w[6] : w[7];
-		const int cm = (int)((((hw >> sh) & 1u) << 1) | ((lw >> sh) & 1u));       // bwt_B0 (bwt.h:78), valid in the half that owns pos
-		const int c = __shfl_sync(FULL_MASK, cm, (lane & ~1) | (pos >> 6));
-		const int r = min(max(pos + 1 - 64 * half, 0), 64);             // symbols of my half that count
-		const u32 m0 = __funnelshift_rc(0u, 0xffffffffu, r), m1 = __funnelshift_rc(0u, 0xffffffffu, max(r - 32, 0));
-		const u32 h0 = (c & 2) ? w[4] : ~w[4], h1 = (c & 2) ? w[5] : ~w[5], l0 = (c & 1) ? w[6] : ~w[6], l1 = (c & 1) ? w[7] : ~w[7];
-		u32 cnt = __popc(h0 & l0 & m0) + __popc(h1 & l1 & m1);
-		cnt += __shfl_xor_sync(FULL_MASK, cnt, 1);
-		const u64 base_mine = (c & 1) ? ((u64)w[2] | ((u64)w[3] << 32)) : ((u64)w[0] | ((u64)w[1] << 32));
-		const u64 base = __shfl_sync(FULL_MASK, base_mine, (lane & ~1) | (c >> 1));
-		const u64 kn = at_primary ? 0 : ix.L2[c] + base + cnt;
-		if (act) { k = kn; ++steps; }
-		if (steps > (1ull << 24)) { if (act && !half) atomicAdd(&status[2], 1); k = 0; }   // guard: corrupt index
-	}
-	return have ? steps + sa[k >> sa_shift] : 0;
+	const bool at_primary = k == ix.primary;                       // bwt_invPsi returns 0 there (bwt.c:76)
+	const u64 kk = at_primary ? 0 : k - (k >= ix.primary);          // '$' is not stored (bwt.c:133); == k - (k > primary) here
+	u32 w[8];
+	ld_sector(w, ix.blk + (kk >> 7) * 4 + half * 2);
+	const int pos = (int)(kk & 127), bit = pos & 63, sh = 31 - (bit & 31);
+	const u32 hw = bit < 32 ? w[4] : w[5], lw = bit < 32 ? w[6] : w[7];
+	const int cm = (int)((((hw >> sh) & 1u) << 1) | ((lw >> sh) & 1u));       // bwt_B0 (bwt.h:78), valid in the half that owns pos
+	const int c = __shfl_sync(FULL_MASK, cm, (lane & ~1) | (pos >> 6));
+	const int r = min(max(pos + 1 - 64 * half, 0), 64);             // symbols of my half that count
+	const u32 m0 = __funnelshift_rc(0u, 0xffffffffu, r), m1 = __funnelshift_rc(0u, 0xffffffffu, max(r - 32, 0));
+	const u32 h0 = (c & 2) ? w[4] : ~w[4], h1 = (c & 2) ? w[5] : ~w[5], l0 = (c & 1) ? w[6] : ~w[6], l1 = (c & 1) ? w[7] : ~w[7];
+	u32 cnt = __popc(h0 & l0 & m0) + __popc(h1 & l1 & m1);
+	cnt += __shfl_xor_sync(FULL_MASK, cnt, 1);
+	const u64 base_mine = (c & 1) ? ((u64)w[2] | ((u64)w[3] << 32)) : ((u64)w[0] | ((u64)w[1] << 32));
+	const u64 base = __shfl_sync(FULL_MASK, base_mine, (lane & ~1) | (c >> 1));
+	return at_primary ? 0 : ix.L2[c] + base + cnt;
 }
 
+// Both walkers below are persistent: a pair retires its row when it reaches a sampled row and immediately takes
+// the next one, so that a warp never waits for its longest walk (walk lengths are geometric, mean sa_intv).
 __global__ void __launch_bounds__(128) sa_kernel(const DevIndex ix, const u64 *__restrict__ sa, int sa_shift, long long n,
                                                  const u64 *__restrict__ ks, u64 *__restrict__ out, int *__restrict__ status)
 {
 	const int lane = threadIdx.x & 31, half = lane & 1;
-	const long long gpair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1, npairs = ((long long)gridDim.x * blockDim.x) >> 1;
-	for (long long q0 = gpair; __any_sync(FULL_MASK, q0 < n); q0 += npairs) {
-		const bool have = q0 < n;
-		const u64 r = sa_walk(ix, sa, sa_shift, have ? ks[q0] : 0, have, half, lane, status);
-		if (have && !half) out[q0] = r;
+	const long long npairs = ((long long)gridDim.x * blockDim.x) >> 1;
+	long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1, cur = 0;
+	const u64 mask = (1ull << sa_shift) - 1;
+	bool have = false;
+	u64 k = 0, steps = 0;
+	for (;;) {
+		for (;;) {                                      // retire / refill (divergent between pairs)
+			if (!have) { if (q >= n) break; cur = q; q += npairs; k = ks[cur]; steps = 0; have = true; }
+			if ((k & mask) != 0) break;
+			if (!half) out[cur] = steps + sa[k >> sa_shift];
+			have = false;
+		}
+		__syncwarp();
+		if (!__any_sync(FULL_MASK, have)) break;
+		const u64 kn = inv_psi_pair(ix, k, half, lane);
+		if (have) { k = kn; if (++steps > (1ull << 24)) { if (!half) atomicAdd(&status[2], 1); k = 0; } }   // guard: corrupt index
 	}
 }
 
@@ -501,19 +505,32 @@ __global__ void __launch_bounds__(128) seed_expand_kernel(const DevIndex ix, con
                                                           Seed *__restrict__ out, int *__restrict__ status)
 {
 	const int lane = threadIdx.x & 31, half = lane & 1;
-	const long long gpair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1, npairs = ((long long)gridDim.x * blockDim.x) >> 1;
-	for (long long s0 = gpair; __any_sync(FULL_MASK, s0 < n_seeds); s0 += npairs) {
-		const bool have = s0 < n_seeds;
-		u64 row = 0; int qbeg = 0, len = 0;
-		if (have) {                                   // interval of seed s0: last i with soff[i] <= s0
-			long long lo = 0, hi = total - 1;
-			while (lo < hi) { const long long mid = (lo + hi + 1) >> 1; if (soff[mid] <= s0) lo = mid; else hi = mid - 1; }
-			const Intv v = ld_intv(&iv[lo]);
-			row = v.x0 + (u64)(s0 - soff[lo]);
-			qbeg = (int)(v.info >> 32); len = (int)(u32)v.info - qbeg;
+	const long long npairs = ((long long)gridDim.x * blockDim.x) >> 1;
+	long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1, cur = 0;
+	const u64 mask = (1ull << sa_shift) - 1;
+	bool have = false;
+	u64 k = 0, steps = 0;
+	int qbeg = 0, len = 0;
+	for (;;) {
+		for (;;) {                                      // retire / refill (divergent between pairs)
+			if (!have) {
+				if (q >= n_seeds) break;
+				cur = q; q += npairs;
+				long long lo = 0, hi = total - 1;           // interval of seed `cur`: last i with soff[i] <= cur
+				while (lo < hi) { const long long mid = (lo + hi + 1) >> 1; if (soff[mid] <= cur) lo = mid; else hi = mid - 1; }
+				const Intv v = ld_intv(&iv[lo]);
+				k = v.x0 + (u64)(cur - soff[lo]);           // bwamem.c:420: bwt_sa(bwt, p->x[0] + k)
+				qbeg = (int)(v.info >> 32); len = (int)(u32)v.info - qbeg;
+				steps = 0; have = true;
+			}
+			if ((k & mask) != 0) break;
+			if (!half) { Seed sd; sd.rbeg = (long long)(steps + sa[k >> sa_shift]); sd.qbeg = qbeg; sd.len = len; out[cur] = sd; }
+			have = false;
 		}
-		const u64 r = sa_walk(ix, sa, sa_shift, row, have, half, lane, status);
-		if (have && !half) { Seed sd; sd.rbeg = (long long)r; sd.qbeg = qbeg; sd.len = len; out[s0] = sd; }
+		__syncwarp();
+		if (!__any_sync(FULL_MASK, have)) break;
+		const u64 kn = inv_psi_pair(ix, k, half, lane);
+		if (have) { k = kn; if (++steps > (1ull << 24)) { if (!half) atomicAdd(&status[2], 1); k = 0; } }
 	}
 }
 
