@@ -253,14 +253,14 @@ def main():
         for item in args.sweep.split(","):
             f = item.split(":")
             b, hot = f[0], (f[1] if len(f) > 1 and f[1] else "0")
-            g.set_param("prefetch", int(f[3]) if len(f) > 3 else 0)
+            g.set_param("reuse", int(f[3]) if len(f) > 3 else 0)
             g.set_param("blocks_per_sm", int(b)); g.set_param("l2_hot_min_intv", int(hot))
             g.set_param("b_cap", int(f[2]) if len(f) > 2 else keep[2])
             ms = []
             for _ in range(4):
                 g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
-            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} prefetch={g.get_param('prefetch')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
-        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("prefetch", 0)
+            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} reuse={g.get_param('reuse')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
+        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("reuse", 0)
     for _ in range(max(args.warmup, 3)):
         total = g.run_collect(opt)
     sampler = ClockSampler(local)

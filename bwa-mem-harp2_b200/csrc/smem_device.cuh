@@ -165,25 +165,31 @@ struct Ext { u64 a, b, s; };   // a = x[!is_back], b = x[is_back], s = x[2]
 
 // bwt_extend for one chosen base c, executed by a converged warp of lane pairs (half = lane & 1).
 // in: (a = x[!is_back], b = x[is_back], s = x[2], c) identical in both lanes of a pair; out likewise.
-__device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 policy)
+// w / v hold this lane's sector of the K / L block across calls (last_bk / last_bl = their block numbers): in the
+// backward sweep consecutive prev[] elements are nested intervals, and the small ones sit in the same 128-row
+// block as their predecessor, so the gather is skipped when the block number repeats (REUSE).
+template <bool REUSE>
+__device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 policy,
+                                           u32 (&w)[8], u32 (&v)[8], u64 &last_bk, u64 &last_bl)
 {
 	const u64 k = a - 1, l = a - 1 + s;
 	const u64 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);   // '$' is not stored (bwt.c:194)
 	const u64 bk = kk >> 7, bl = ll >> 7;
 	const bool same = bk == bl;
-	u32 w[8], v[8];
+	const bool need_k = !REUSE || bk != last_bk, need_l = !same && (!REUSE || bl != last_bl);
 	const uint4 *pk = ix.blk + bk * 4 + half * 2, *pl = ix.blk + bl * 4 + half * 2;
 	if (hot_min && s >= hot_min) {
-		ld_sector_hot(w, pk, policy);
-		if (!same) ld_sector_hot(v, pl, policy);
+		if (need_k) ld_sector_hot(w, pk, policy);
+		if (need_l) ld_sector_hot(v, pl, policy);
 	} else {
-		ld_sector(w, pk);
-		if (!same) ld_sector(v, pl);
+		if (need_k) ld_sector(w, pk);
+		if (need_l) ld_sector(v, pl);
 	}
 	if (same) {
 #pragma unroll
 		for (int j = 0; j < 8; ++j) v[j] = w[j];
 	}
+	if (REUSE) { last_bk = bk; last_bl = bl; }
 	// symbols 0..kk&127 (inclusive) of the block count; this lane owns symbols 64*half .. 64*half+63
 	const int rk = min(max((int)(kk & 127) + 1 - 64 * half, 0), 64), rl = min(max((int)(ll & 127) + 1 - 64 * half, 0), 64);
 	u32 ck = occ_half(w, rk), cl = occ_half(v, rl);

@@ -89,7 +89,8 @@ struct smem_gpu {
 	int force_wide = 0;
 	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
 	int chain_lanes = 0;             // 1: lane k's seed kernel waits for lane k-1's (no tail overlap)
-	int prefetch = 0;                // L2 look-ahead for the backward sweep: measured 37 % SLOWER (adds DRAM requests), kept as a knob
+	int reuse = 0;                   // keep the last K/L occ sectors in registers and skip the gather when the block repeats:
+	                                 // +14 % at equal occupancy, but the 16 extra registers cost that occupancy (tie) -> off
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
 	uint64_t epoch = 0;              // bumped per run; orders the lanes' seed kernels
 	uint64_t stage_epoch = 0;        // bumped per staging; orders the lanes' H2D copies
@@ -241,6 +242,10 @@ int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const
 	d.seq_base = offs[d.lo];
 	const size_t nbytes = (size_t)(offs[d.hi] - offs[d.lo]);
 	if (nbytes > d.seq_cap || d.n > d.read_cap) { d.err = "batch exceeds the capacity given to smem_gpu_create"; return SMEM_GPU_E_CAPACITY; }
+	for (int64_t i = d.lo; i < d.hi; ++i) {          // every per-read buffer on the device is sized from max_read_len
+		const int64_t l = offs[i + 1] - offs[i];
+		if (l < 0 || l > d.owner->max_len) { d.err = "a read is longer than max_read_len (or offs is not monotone)"; return l < 0 ? SMEM_GPU_E_ARG : SMEM_GPU_E_CAPACITY; }
+	}
 	if (nbytes) CK(cudaMemcpyAsync(d.d_seq, seq + d.seq_base, nbytes, cudaMemcpyHostToDevice, d.stream));
 	CK(cudaMemcpyAsync(d.d_offs, offs + d.lo, (size_t)(d.n + 1) * 8, cudaMemcpyHostToDevice, d.stream));
 	if (x) {
@@ -252,13 +257,13 @@ int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const
 	return 0;
 }
 
-template <int MODE, bool WIDE, bool PREFETCH>
+template <int MODE, bool WIDE, bool REUSE>
 int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem)
 {
 #define LAUNCH(B)                                                                                                                  \
 	do {                                                                                                                           \
-		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-		seed_kernel<MODE, B, WIDE, PREFETCH><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
+		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+		seed_kernel<MODE, B, WIDE, REUSE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
 	} while (0)
 	switch (blocks_per_sm) {
 	case 4: LAUNCH(4); break;
@@ -278,9 +283,9 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 }
 
 template <int MODE>
-int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide, bool prefetch)
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide, bool reuse)
 {
-	if (prefetch) return wide ? launch_seed_w<MODE, true, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, true>(d, p, blocks_per_sm, grid, smem);
+	if (reuse) return wide ? launch_seed_w<MODE, true, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, true>(d, p, blocks_per_sm, grid, smem);
 	return wide ? launch_seed_w<MODE, true, false>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, false>(d, p, blocks_per_sm, grid, smem);
 }
 
@@ -374,7 +379,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		lk.unlock();
 		CK(cudaStreamWaitEvent(d.stream, d.prev_lane->ev1, 0));
 	}
-	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.prefetch != 0) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.prefetch != 0);
+	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.reuse != 0) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.reuse != 0);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
 	lane_mark_issued(d, h);
@@ -415,7 +420,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
 			p2.overflow_list = d.d_counts_k + n_over;
 			const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
-			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide, h.prefetch != 0) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide, h.prefetch != 0);
+			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide, h.reuse != 0) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide, h.reuse != 0);
 			if (rc) return rc;
 			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 			CK(cudaStreamSynchronize(d.stream));
@@ -923,7 +928,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "force_wide")) { h->force_wide = v != 0; return 0; }
 	if (!strcmp(name, "spare_sms")) { if (v < 0 || v > 64) return SMEM_GPU_E_ARG; h->spare_sms = (int)v; return 0; }
 	if (!strcmp(name, "chain_lanes")) { h->chain_lanes = v != 0; return 0; }
-	if (!strcmp(name, "prefetch")) { h->prefetch = v != 0; return 0; }
+	if (!strcmp(name, "reuse")) { h->reuse = v != 0; return 0; }
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
@@ -944,7 +949,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "b_cap")) return h->b_cap;
 	if (!strcmp(name, "spare_sms")) return h->spare_sms;
 	if (!strcmp(name, "chain_lanes")) return h->chain_lanes;
-	if (!strcmp(name, "prefetch")) return h->prefetch;
+	if (!strcmp(name, "reuse")) return h->reuse;
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
 	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }

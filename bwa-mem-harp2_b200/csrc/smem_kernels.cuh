@@ -33,7 +33,7 @@ __device__ __noinline__ Intv bx_get(const Intv *p) { return ld_intv(p); }
 //   global : M1, M2 = `matches` / `sub` of smem_next2 in emission order (descending start), each of
 //            scratch_cap = max_read_len + 2 entries, which bounds every list of bwt.c:776-835.
 //            BX = the entries of B beyond b_cap (only the deepest forward passes reach them).
-template <int MODE, int MIN_BLOCKS, bool WIDE, bool PREFETCH>
+template <int MODE, int MIN_BLOCKS, bool WIDE, bool REUSE /* keep the last occ sectors in registers, skip repeated gathers */>
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
 	typedef BEntry<WIDE> BE;
@@ -85,6 +85,10 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	int i = 0, j = 0, n0 = 0, n_prev = 0, n_curr = 0, len = 0, guard = 0;
 	int max_count = 0;                   // largest per-read interval count this pair produced (sizes the compaction grid)
 	u64 min_intv = 1, last_s = 0;
+	u32 blk_k[8], blk_l[8];              // this lane's sectors of the last K / L occ blocks (see extend_pair)
+	u64 last_bk = ~0ull, last_bl = ~0ull;
+#pragma unroll
+	for (int t = 0; t < 8; ++t) blk_k[t] = blk_l[t] = 0;
 
 	for (;;) {
 		__syncwarp();
@@ -239,22 +243,9 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		__syncwarp();
 		if (__all_sync(FULL_MASK, phase == PH_IDLE)) break;
 
-		// ============================================================== look-ahead for the backward sweep
-		// prev[j+1] is already known while prev[j] is being extended: touch its two occ blocks now (L2 prefetch, one
-		// per lane), so that the next trip's gathers hit L2 instead of waiting for DRAM.  MEASURED on B200: 37 % slower
-		// (52.3 vs 38.3 ms) -- the prefetches do not merge with the later loads, they add DRAM requests, and requests
-		// are the scarce resource.  Compiled in only for the `prefetch` knob, off by default.
-		if (PREFETCH && phase == PH_BWD && j + 1 < n_prev) {
-			u64 pa, pb, ps; u32 pend;
-			b_get(n0 - 2 - j, pa, pb, ps, pend);
-			const u64 pk = pa - 1 + (half ? ps : 0);                     // even lane: k, odd lane: l
-			const u64 pkk = pk - (pk >= p.ix.primary);
-			asm volatile("prefetch.global.L2 [%0];" :: "l"(p.ix.blk + (pkk >> 7) * 4));
-		}
-
 		// ============================================================== one bwt_extend per pair (warp converged)
 		// idle pairs ride along on the interval (1,1,1): its block is hot in L2 and the result is dropped
-		const Ext ok = extend_pair(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, policy);
+		const Ext ok = extend_pair<REUSE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, policy, blk_k, blk_l, last_bk, last_bl);
 		if (phase == PH_IDLE) continue;
 		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 

@@ -137,7 +137,8 @@ int smem_gpu_last_timing(const smem_gpu_t *h, smem_gpu_timing_t *t);
 /* Tuning knobs: "blocks_per_sm", "slot_cap", "b_cap" (prev/curr entries kept in shared
  * memory per read), "force_wide" (32-byte entries), "l2_fetch_granularity" (32|64|128, device-wide
  * cudaLimitMaxL2FetchGranularity hint), "probe_variant", "l2_hot_min_intv" (0 = off:
- * occ-block loads for intervals of size >= value carry an L2 evict_last hint). */
+ * occ-block loads for intervals of size >= value carry an L2 evict_last hint), "reuse" (keep the last occ sectors
+ * in registers), "spare_sms" / "chain_lanes" (scheduling of several pipeline lanes on one GPU). */
 int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t value);
 int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name);
 

@@ -120,7 +120,7 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
     try:
         for name, val in [("slot_cap", 2), ("slot_cap", 128), ("blocks_per_sm", 3), ("blocks_per_sm", 12), ("blocks_per_sm", 6),
                           ("b_cap", 2), ("b_cap", 7), ("force_wide", 1), ("b_cap", 19), ("force_wide", 0),
-                          ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0), ("prefetch", 1), ("prefetch", 0)]:
+                          ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0), ("reuse", 1), ("reuse", 0)]:
             g.set_param(name, val)
             b = g.collect(seq, offs)
             same_result(a, b, ("read_off", "intv", "step"))
@@ -148,6 +148,11 @@ def test_staged_run_is_idempotent_and_capacity_error(world, synth, sg):
     assert ei.value.code == -5
     with pytest.raises(sg.SmemGpuError):
         g.stage(np.zeros(50_000 * 10, np.uint8), np.arange(50_001, dtype=np.int64) * 10)   # > max_batch_reads
+    with pytest.raises(sg.SmemGpuError) as ei:                                             # one read longer than max_read_len
+        g.collect(np.zeros(400, np.uint8), np.array([0, 100, 400], np.int64))
+    assert ei.value.code == -5
+    with pytest.raises(sg.SmemGpuError):                                                   # offsets not monotone
+        g.collect(np.zeros(400, np.uint8), np.array([0, 200, 100], np.int64))
 
 
 def test_exact_reads_give_full_length_smem(world, synth):
