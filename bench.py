@@ -142,7 +142,22 @@ def cpu_time(engine, seq, offs, n, threads, opt):
     return engine.time_collect(seq[: int(o[-1])], o, opt, threads)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """The ONE JSON line goes to the process' original stdout; everything else (NCCL's version banner, library
+    chatter) was re-routed to stderr at start-up."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -190,7 +205,7 @@ def main():
         dt = time.perf_counter() - t0
         v = per_step * args.steps / dt
         sample = f"first {per_step} reads of the step's batch per step, {ncores} host threads (kt_for)"
-        print(json.dumps({"impl": "reference", "metric": "smem_seeded_101bp_reads_per_sec", "value": v, "unit": "reads/s",
+        emit(json.dumps({"impl": "reference", "metric": "smem_seeded_101bp_reads_per_sec", "value": v, "unit": "reads/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                           "config": config, "cpu_baseline": {"value": v, "unit": "reads/s", "cores": ncores, "kind": kind, "sample": sample},
@@ -447,7 +462,7 @@ def main():
             out["batch_sweep"] = batch_sweep
         if seeds_leg:
             out["seeds_api"] = seeds_leg
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
