@@ -54,7 +54,7 @@ struct DeviceCtx {
 	Intv *d_scratch = nullptr;
 	size_t scratch_entries = 0;
 	Intv *d_out = nullptr;
-	unsigned short *d_step = nullptr;
+	unsigned short *d_step = nullptr, *d_aux = nullptr;
 	size_t out_cap = 0;
 	void *d_tmp = nullptr;
 	size_t tmp_bytes = 0;
@@ -154,6 +154,7 @@ int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int
 	d.out_cap = (size_t)read_cap * 16 + 1024;
 	if ((rc = dev_alloc(d, &d.d_out, d.out_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_step, d.out_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_aux, d.out_cap))) return rc;
 	CK(cudaMallocHost((void **)&d.h_status, 128));
 	// per-pair scratch for the default launch geometry (re-grown in ctx_run if blocks_per_sm is raised): allocating
 	// it lazily would delay the first lane's first kernel by a cudaMalloc
@@ -173,7 +174,7 @@ void ctx_free(DeviceCtx &d)
 	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
 	cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
-	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
+	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_aux); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
 	if (d.h_status) cudaFreeHost(d.h_status);
 	if (d.ev0) cudaEventDestroy(d.ev0);
 	if (d.ev1) cudaEventDestroy(d.ev1);
@@ -379,7 +380,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		lk.unlock();
 		CK(cudaStreamWaitEvent(d.stream, d.prev_lane->ev1, 0));
 	}
-	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.reuse != 0) : launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.reuse != 0);
+	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.reuse != 0)
+	       : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.reuse != 0) : launch_seed<MODE_TRACE>(d, p, bps, grid, smem, wide, false);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
 	lane_mark_issued(d, h);
@@ -420,7 +422,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
 			p2.overflow_list = d.d_counts_k + n_over;
 			const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
-			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide, h.reuse != 0) : launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide, h.reuse != 0);
+			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide, h.reuse != 0)
+			   : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide, h.reuse != 0) : launch_seed<MODE_TRACE>(d, p2, bps, grid2, smem, wide, false);
 			if (rc) return rc;
 			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 			CK(cudaStreamSynchronize(d.stream));
@@ -448,22 +451,23 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const double t_scan = tms();
 	memcpy(&d.total, d.h_status + 6, 8);
 	if ((size_t)d.total > d.out_cap) {
-		CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); d.d_out = nullptr; d.d_step = nullptr;
+		CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); CK(cudaFree(d.d_aux)); d.d_out = nullptr; d.d_step = nullptr; d.d_aux = nullptr;
 		d.out_cap = (size_t)d.total + (size_t)d.total / 8 + 1024;
 		CK(cudaMalloc((void **)&d.d_out, d.out_cap * sizeof(Intv)));
 		CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
+		CK(cudaMalloc((void **)&d.d_aux, d.out_cap * sizeof(unsigned short)));
 	}
 	{
 		const long long threads = (long long)d.n * 8;
 		compact_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
-		                                                                        d.d_out, d.d_step);
+		                                                                        d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
 		CK(cudaGetLastError());
 		++d.launches;
 	}
 	if (n_over > 0) {
 		const long long threads = (long long)n_over * big_cap;
 		compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
-		                                                                             d.d_off, d.d_out, d.d_step);
+		                                                                             d.d_off, d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
 		CK(cudaGetLastError());
 		++d.launches;
 	}
@@ -475,13 +479,14 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	return 0;
 }
 
-int ctx_fetch(DeviceCtx &d, smem_intv_t *intv_out, int64_t *read_off, uint16_t *step_out, int32_t *ret, long long base)
+int ctx_fetch(DeviceCtx &d, smem_intv_t *intv_out, int64_t *read_off, uint16_t *step_out, int32_t *ret, long long base, uint16_t *aux_out = nullptr)
 {
 	CK(cudaSetDevice(d.dev));
 	if (d.n == 0) return 0;
 	CK(cudaMemcpyAsync(read_off + d.lo, d.d_off, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));   // read_off[n] is set by the caller
 	if (intv_out && d.total) CK(cudaMemcpyAsync(intv_out + base, d.d_out, (size_t)d.total * sizeof(Intv), cudaMemcpyDeviceToHost, d.stream));
 	if (step_out && d.total) CK(cudaMemcpyAsync(step_out + base, d.d_step, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream));
+	if (aux_out && d.total) CK(cudaMemcpyAsync(aux_out + base, d.d_aux, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream));
 	if (ret) CK(cudaMemcpyAsync(ret + d.lo, d.d_ret, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
 	if (base) for (int64_t i = d.lo; i < d.hi; ++i) read_off[i] += base;
@@ -562,7 +567,7 @@ int do_fetch(smem_gpu *h, smem_intv_t *intv_out, int64_t cap, int64_t *read_off,
 // lanes before it to know where its results go; those finish first anyway (lanes run in order).
 int do_collect(smem_gpu *h, int mode, int64_t n, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi,
                const smem_seed_opt_t *opt, smem_intv_t *intv_out, int64_t cap, int64_t *read_off, uint16_t *step_out, int32_t *ret,
-               int64_t *total_out)
+               int64_t *total_out, uint16_t *aux_out = nullptr)
 {
 	if (!h || n < 0 || (n > 0 && (!seq || !offs)) || !read_off) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
 	if (n > h->max_batch) { h->err = "batch larger than max_batch_reads"; return SMEM_GPU_E_CAPACITY; }
@@ -596,7 +601,7 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const uint8_t *seq, const int64
 		}
 		if (r) return r;
 		const bool fits = intv_out && base + d.total <= cap;
-		r = ctx_fetch(d, fits ? intv_out : nullptr, read_off, fits ? step_out : nullptr, ret, base);
+		r = ctx_fetch(d, fits ? intv_out : nullptr, read_off, fits ? step_out : nullptr, ret, base, fits ? aux_out : nullptr);
 		if (trace) fprintf(stderr, "[smem_gpu trace] lane %zu: start %.2f staged %.2f ran %.2f (seed %.2f ms, dev %.2f ms) fetched %.2f\n", k, ta, tb, tc,
 		                   d.seed_ms, d.total_ms, ms());
 		return r;
@@ -886,6 +891,13 @@ int smem_gpu_collect(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const i
 {
 	if (!h || !opt || !read_off) return SMEM_GPU_E_ARG;
 	return do_collect(h, MODE_COLLECT, n_reads, seq, offs, nullptr, nullptr, opt, intv_out, intv_cap, read_off, step_out, nullptr, total_out);
+}
+
+int smem_gpu_trace(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const smem_seed_opt_t *opt,
+                   smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, uint16_t *tag_out, uint16_t *ret_out, int64_t *total_out)
+{
+	if (!h || !opt || !read_off || !tag_out || !ret_out) return SMEM_GPU_E_ARG;
+	return do_collect(h, MODE_TRACE, n_reads, seq, offs, nullptr, nullptr, opt, intv_out, intv_cap, read_off, tag_out, nullptr, total_out, ret_out);
 }
 
 int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *min_intv,

@@ -2,11 +2,13 @@
 #pragma once
 #include "smem_device.cuh"
 
-enum { MODE_COLLECT = 0, MODE_SMEM1 = 1 };
+enum { MODE_COLLECT = 0, MODE_SMEM1 = 1, MODE_TRACE = 2 };   // TRACE: COLLECT's walk, but every bwt_smem1 call's raw list is kept
 // hot phases first: the main loop only ever extends in PH_FWD / PH_BWD
 enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
 
-#define STEP_SHIFT 48        // inside the slots the smem_next2 step index rides in info bits 48..63
+#define STEP_SHIFT 48        // inside the slots the smem_next2 step index (TRACE: step*2 + pass) rides in info bits 48..63
+#define AUX_SHIFT 16         // ... and, in TRACE mode, bwt_smem1's return value in bits 16..31 (query positions are < 2^16)
+#define INFO_MASK 0x0000ffff0000ffffull
 #define SEED_BLOCK 128       // threads per CTA of the seeding kernel (= 64 lane pairs = 64 reads in flight)
 
 // per-pair shared memory: [B entries | cold state | query, two bases per byte]
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				}
 				__syncwarp(3u << (lane & ~1));
 				sts_i32(sc + CS_RID, rid); sts_i32(sc + CS_NOUT, 0); sts_u16(sc + CS_START, 0); sts_u16(sc + CS_STEP, 0);
-				if (MODE == MODE_COLLECT) {
+				if (MODE != MODE_SMEM1) {
 					sts_u16(sc + CS_SPLIT, p.split_len_init < len ? p.split_len_init : len);     // bwamem.c:458
 					phase = PH_NEXT_STEP;
 				} else {
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				if (c > 3) c = -1;
 				b_get(n0 - 1, a, b, s, end);             // prev[0] = the last push; its info is bwt_smem1's return value
 				sts_u16(sc + CS_RET, (int)end);
-				if (MODE == MODE_COLLECT && lds_u16(sc + CS_PASS) == 0) sts_u16(sc + CS_START, (int)end);   // bwamem.c:262
+				if (MODE != MODE_SMEM1 && lds_u16(sc + CS_PASS) == 0) sts_u16(sc + CS_START, (int)end);   // bwamem.c:262
 				phase = c < 0 ? PH_BWD_LAST : PH_BWD;
 			} break;
 			case PH_BWD_LAST: {
@@ -188,8 +190,34 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					break;
 				}
 				const int step = lds_u16(sc + CS_STEP);
-				const u64 tag = (u64)step << STEP_SHIFT;
 				int n_out = lds_i32(sc + CS_NOUT);
+				if (MODE == MODE_TRACE) {
+					// what two successive DO calls of bwt_smem1_batched return (bwt.c:719-749): the raw list of this
+					// bwt_smem1 (ascending start) tagged step*2 + pass, with its return value alongside
+					const int pass = lds_u16(sc + CS_PASS);
+					const u64 ttag = ((u64)(step * 2 + pass) << STEP_SHIFT) | ((u64)(u32)lds_u16(sc + CS_RET) << AUX_SHIFT);
+					const Intv *const Mp = M1 + (size_t)pass * p.scratch_cap;
+					for (int e = n_mem - 1; e >= 0; --e) {
+						if (n_out < p.slot_cap) { const Intv t = ld_intv(&Mp[e]); st_intv(&slot[n_out], t.x0, t.x1, t.x2, t.info | ttag); }
+						++n_out;
+					}
+					sts_i32(sc + CS_NOUT, n_out);
+					if (pass == 0) {
+						const int max_len = lds_u16(sc + CS_MAXLEN), split_len = lds_u16(sc + CS_SPLIT);
+						const u64 max_s = (u64)(u32)lds_i32(sc + CS_MAXS_LO) | ((u64)(u32)lds_i32(sc + CS_MAXS_HI) << 32);
+						if (n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width) {   // bwamem.c:272
+							sts_u16(sc + CS_PASS, 1);
+							sts_u16(sc + CS_X, (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1);
+							min_intv = max_s + 1;
+							phase = PH_INIT_CALL;
+							break;
+						}
+					}
+					sts_u16(sc + CS_STEP, step + 1);
+					phase = PH_NEXT_STEP;
+					break;
+				}
+				const u64 tag = (u64)step << STEP_SHIFT;
 				if (lds_u16(sc + CS_PASS) == 0) {
 					const int max_len = lds_u16(sc + CS_MAXLEN), split_len = lds_u16(sc + CS_SPLIT);
 					const u64 max_s = (u64)(u32)lds_i32(sc + CS_MAXS_LO) | ((u64)(u32)lds_i32(sc + CS_MAXS_HI) << 32);
@@ -388,7 +416,7 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_add_kernel(long long *__restric
 // Eight lanes per read, each copying entries lane, lane+8, ... (most reads have <= 16 intervals).
 __global__ void __launch_bounds__(128) compact_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
                                                       const long long *__restrict__ off, long long n, Intv *__restrict__ out,
-                                                      unsigned short *__restrict__ step_out)
+                                                      unsigned short *__restrict__ step_out, unsigned short *__restrict__ aux_out)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long r = t >> 3;
@@ -397,23 +425,25 @@ __global__ void __launch_bounds__(128) compact_kernel(const Intv *__restrict__ s
 	const long long o0 = off[r];
 	for (int e = (int)(t & 7); e < c; e += 8) {
 		const Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
-		st_intv(&out[o0 + e], v.x0, v.x1, v.x2, v.info & ((1ull << STEP_SHIFT) - 1));
+		st_intv(&out[o0 + e], v.x0, v.x1, v.x2, v.info & INFO_MASK);
 		if (step_out) step_out[o0 + e] = (unsigned short)(v.info >> STEP_SHIFT);
+		if (aux_out) aux_out[o0 + e] = (unsigned short)(v.info >> AUX_SHIFT);
 	}
 }
 
 // Overflow re-run placement: big_slots[k][big_cap] of read list[k] -> dense output at off[list[k]].
 __global__ void compact_list_kernel(const Intv *__restrict__ big_slots, int big_cap, const int *__restrict__ list,
                                     const int *__restrict__ counts_k, int n_list, const long long *__restrict__ off,
-                                    Intv *__restrict__ out, unsigned short *__restrict__ step_out)
+                                    Intv *__restrict__ out, unsigned short *__restrict__ step_out, unsigned short *__restrict__ aux_out)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const int k = (int)(t / big_cap), e = (int)(t % big_cap);
 	if (k >= n_list || e >= counts_k[k]) return;
 	const Intv v = ld_intv(&big_slots[(size_t)k * big_cap + e]);
 	const long long o = off[list[k]] + e;
-	st_intv(&out[o], v.x0, v.x1, v.x2, v.info & ((1ull << STEP_SHIFT) - 1));
+	st_intv(&out[o], v.x0, v.x1, v.x2, v.info & INFO_MASK);
 	if (step_out) step_out[o] = (unsigned short)(v.info >> STEP_SHIFT);
+	if (aux_out) aux_out[o] = (unsigned short)(v.info >> AUX_SHIFT);
 }
 
 __global__ void add_base_kernel(long long *off, long long n, long long base)

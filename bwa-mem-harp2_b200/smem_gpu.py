@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_trace", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -213,6 +213,28 @@ class SmemGpu:
             self._check(rc)
             t = int(tot.value)
             return dict(intv=intv[:t], read_off=read_off, step=step[:t] if want_step else None)
+
+    def trace(self, seq, offs, opt: "SeedOpt | None" = None):
+        """Per-call raw lists of the whole iterator walk (smem_gpu_trace): intv, read_off, tag (2*step+pass), ret."""
+        opt = opt or SeedOpt()
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        n = len(offs) - 1
+        cap = max(64, 32 * n)
+        read_off = np.zeros(n + 1, np.int64)
+        tot = C.c_int64(0)
+        while True:
+            intv = np.empty((cap, 4), np.uint64)
+            tag = np.empty(cap, np.uint16)
+            ret = np.empty(cap, np.uint16)
+            rc = self.lib.smem_gpu_trace(self.h, C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64), C.byref(opt), _p(intv, C.c_uint64),
+                                         C.c_int64(cap), _p(read_off, C.c_int64), _p(tag, C.c_uint16), _p(ret, C.c_uint16), C.byref(tot))
+            if rc == -5 and tot.value > cap:
+                cap = int(tot.value)
+                continue
+            self._check(rc)
+            t = int(tot.value)
+            return dict(intv=intv[:t], read_off=read_off, tag=tag[:t], ret=ret[:t])
 
     def smem1(self, seq, offs, x, min_intv):
         seq = np.ascontiguousarray(seq, np.uint8)

@@ -102,6 +102,15 @@ int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int
 int smem_gpu_upload_sa(smem_gpu_t *h, int sa_intv, uint64_t n_sa, const uint64_t *sa, int src_device);
 int smem_gpu_sa(smem_gpu_t *h, int64_t n, const uint64_t *k, uint64_t *out);
 
+/* The same walk as smem_gpu_collect, but every bwt_smem1 call keeps its raw list: for each read and each
+ * smem_next2 step s the pass-1 list (tag 2s) and, if the iterator re-seeds, the pass-2 list (tag 2s+1), each in
+ * ascending start order, with ret_out = bwt_smem1's return value of that call.  This is what the successive DO calls
+ * of bwt_smem1_batched return for a batch (bwt.c:719-749), so an adapter can compute all rounds in one launch and
+ * serve the reference's per-round calls from the result. */
+int smem_gpu_trace(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const smem_seed_opt_t *opt,
+                   smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, uint16_t *tag_out, uint16_t *ret_out,
+                   int64_t *total_out);
+
 /* == mem_seed_t (bwamem.c:316-319) */
 typedef struct { int64_t rbeg; int32_t qbeg, len; } smem_seed_t;
 

@@ -203,3 +203,66 @@ def test_pipeline_lanes_on_one_gpu(world, synth, sg):
     g4.upload_index(ix)            # re-upload must not leak or double-free the shared copy
     same_result(a, g4.collect(seq, offs), ("read_off", "intv", "step"))
     g4.close()
+
+
+def test_trace_replays_to_collect_and_matches_raw_calls(world, synth):
+    """smem_gpu_trace: (a) every recorded call equals a raw bwt_smem1 of the oracle at the position / min_intv the
+    reference's smem_next2 would use, (b) re-doing smem_next2's merge on the host from the trace gives collect."""
+    ref, ix, o, g = world
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 1500, 101, 0.02, seed=17, n_frac=0.08))
+    opt = (19, 1.5, 10, 1)
+    tr = g.trace(seq, offs, gopt(opt))
+    want = o.collect(seq, offs, OSeedOpt(*opt), nthreads=8)
+    split_len0 = int(opt[0] * opt[1] + .499)
+    calls, merged_all, merged_off = [], [], [0]          # calls: (read, x, min_intv, expected list, expected ret)
+    for i in range(len(offs) - 1):
+        q = seq[offs[i]:offs[i + 1]]
+        L = len(q)
+        sl = tr["intv"][tr["read_off"][i]:tr["read_off"][i + 1]]
+        tg = tr["tag"][tr["read_off"][i]:tr["read_off"][i + 1]]
+        rt = tr["ret"][tr["read_off"][i]:tr["read_off"][i + 1]]
+        start, s = 0, 0
+        split_len = min(split_len0, L)
+        while True:
+            while start < L and q[start] > 3:
+                start += 1
+            if start >= L:
+                break
+            p1, r1 = sl[tg == 2 * s], rt[tg == 2 * s]
+            assert len(p1) >= 1 and (r1 == r1[0]).all()
+            calls.append((i, start, opt[3], p1, int(r1[0])))
+            lens = (p1[:, 3] & 0xFFFFFFFF).astype(np.int64) - (p1[:, 3] >> 32).astype(np.int64)
+            mi = int(np.argmax(lens))               # first maximum
+            mx = int(lens[mi])
+            out = [tuple(int(v) for v in e) for e in p1]
+            if split_len > 0 and mx >= split_len and int(p1[mi, 2]) <= opt[2]:
+                p2 = sl[tg == 2 * s + 1]
+                mid = (int(p1[mi, 3] & 0xFFFFFFFF) + int(p1[mi, 3] >> 32)) >> 1
+                calls.append((i, mid, int(p1[mi, 2]) + 1, p2, None))
+                key = lambda e: ((e[3] >> 32) << 32) | ((L - (e[3] & 0xFFFFFFFF)) & 0xFFFFFFFF)
+                keep = lambda e: ((e[3] & 0xFFFFFFFF) - (e[3] >> 32)) >= (mx >> 1) and (e[3] & 0xFFFFFFFF) > start
+                a, b, out, ia, ib = out, [tuple(int(v) for v in e) for e in p2], [], 0, 0
+                while ia < len(a) and ib < len(b):
+                    if key(a[ia]) < key(b[ib]):
+                        out.append(a[ia]); ia += 1
+                    else:
+                        if keep(b[ib]):
+                            out.append(b[ib])
+                        ib += 1
+                out += a[ia:] + [e for e in b[ib:] if keep(e)]
+            else:
+                assert not (tg == 2 * s + 1).any()
+            merged_all += out
+            start = int(r1[0])
+            s += 1
+        assert not (tg >= 2 * s).any()
+        merged_off.append(len(merged_all))
+    assert np.array_equal(np.array(merged_off), want["read_off"])
+    assert np.array_equal(np.array(merged_all, dtype=np.uint64).reshape(-1, 4), want["intv"])
+    # raw calls against the oracle's bwt_smem1
+    rseq, roffs = synth.to_batch([seq[offs[c[0]]:offs[c[0] + 1]] for c in calls])
+    raw = o.smem1(rseq, roffs, [c[1] for c in calls], [c[2] for c in calls])
+    for k, c in enumerate(calls):
+        assert np.array_equal(raw["intv"][raw["read_off"][k]:raw["read_off"][k + 1]], c[3]), k
+        if c[4] is not None:
+            assert int(raw["ret"][k]) == c[4]
