@@ -58,8 +58,10 @@ void bwt_smem1_batched(harp_smem_i **itr, int *ori_start, int *max_i, int start_
  * call from itr[0]->bwt).  devices: comma list in SMEM_GPU_DEVICES (default "0"). Returns 0 or SMEM_GPU_E_*. */
 int harp_gpu_service_start(const harp_bwt_t *bwt);
 void harp_gpu_service_stop(void);
-/* Counters for tests: DO calls served, reads seeded, intervals returned. */
-void harp_gpu_service_stats(uint64_t out[3]);
+/* Counters for tests: GPU calls, reads sent, intervals received, lists served from the whole-batch cache.
+ * Environment: SMEM_GPU_ADAPTER_CACHE=0 disables the cache; SMEM_GPU_SPLIT_LEN / SMEM_GPU_SPLIT_WIDTH tell it the
+ * caller's re-seeding options (default 28 / 10 = -k 19 -r 1.5); a mismatch only costs speed, never correctness. */
+void harp_gpu_service_stats(uint64_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -20,8 +20,8 @@ def sam_body(txt):
 
 
 @pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)), reason="oracle/_ref binaries were not built")
-@pytest.mark.parametrize("paired", [False, True])
-def test_bwa_mem_sam_identical(tmp_path, paired):
+@pytest.mark.parametrize("paired,batch,cache", [(False, 64, 1), (True, 64, 1), (False, 1000, 1), (False, 64, 0), (True, 2048, 1)])
+def test_bwa_mem_sam_identical(tmp_path, paired, batch, cache):
     sy = pkg("synth")
     ref = sy.make_reference(300_000, 42)
     refn = ref.numpy()
@@ -39,9 +39,16 @@ def test_bwa_mem_sam_identical(tmp_path, paired):
         sy.write_fastq(str(tmp_path / "r.fq"), reads)
         fqs = [str(tmp_path / "r.fq")]
     cpu = subprocess.run([REF, "mem", "-t", "2", "-b", "1", fa] + fqs, check=True, capture_output=True, cwd=tmp_path, text=True)
-    env = dict(os.environ, SMEM_GPU_MAX_READ_LEN="256", SMEM_GPU_MAX_BATCH="4096")
-    gpu = subprocess.run([GPU, "mem", "-t", "2", "-b", "64", fa] + fqs, check=True, capture_output=True, cwd=tmp_path, text=True,
+    env = dict(os.environ, SMEM_GPU_MAX_READ_LEN="256", SMEM_GPU_MAX_BATCH="4096", SMEM_GPU_ADAPTER_CACHE=str(cache), SMEM_GPU_ADAPTER_STATS="1")
+    gpu = subprocess.run([GPU, "mem", "-t", "2", "-b", str(batch), fa] + fqs, check=True, capture_output=True, cwd=tmp_path, text=True,
                          env=env, timeout=600)
     a, b = sam_body(cpu.stdout), sam_body(gpu.stdout)
     assert len(a) == len(b) and len(a) > n
     assert a == b
+    stats = [l for l in gpu.stderr.splitlines() if "lists_from_cache" in l]
+    assert stats, gpu.stderr[-2000:]
+    kv = dict(t.split("=") for t in stats[-1].split()[1:])
+    if cache:      # (nearly) every per-round call of the reference was served from the one-launch trace of its batch
+        assert int(kv["lists_from_cache"]) > 3 * n and int(kv["gpu_calls"]) <= 2 * (n // batch + 2) + 8, kv
+    else:
+        assert int(kv["lists_from_cache"]) == 0 and int(kv["gpu_calls"]) > 4 * (n // batch), kv
