@@ -52,3 +52,35 @@ def test_bwa_mem_sam_identical(tmp_path, paired, batch, cache):
         assert int(kv["lists_from_cache"]) > 3 * n and int(kv["gpu_calls"]) <= 2 * (n // batch + 2) + 8, kv
     else:
         assert int(kv["lists_from_cache"]) == 0 and int(kv["gpu_calls"]) > 4 * (n // batch), kv
+
+
+HARP = os.path.join(ROOT, "oracle", "_ref", "bwa_harp")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(HARP)), reason="oracle/_ref binaries were not built")
+@pytest.mark.parametrize("threads", [1, 2])
+def test_harp_wire_protocol_shim(tmp_path, threads):
+    """Section 8f-4: every reference object unmodified and built WITHOUT -DUSE_SW (real handshakes, its own record
+    packing and manager thread); only HelloALINLB.cpp is replaced by host/harp_shim.c, which plays the AFU on the GPU.
+    101 bp reads only -- the protocol's own limit (bwt.c:575)."""
+    sy = pkg("synth")
+    ref = sy.make_reference(250_000, 43)
+    fa = str(tmp_path / "g.fa")
+    sy.write_fasta(fa, [("chrA", ref.numpy())])
+    subprocess.run([REF, "index", fa], check=True, capture_output=True, cwd=tmp_path)
+    n = 1500
+    reads = sy.simulate_reads(ref, n, 101, 0.02, seed=9, n_frac=0.05).numpy()
+    sy.write_fastq(str(tmp_path / "r.fq"), reads)
+    cpu = subprocess.run([REF, "mem", "-t", str(threads), "-b", "1", fa, str(tmp_path / "r.fq")], check=True, capture_output=True,
+                         cwd=tmp_path, text=True)
+    env = dict(os.environ, HARP_SHIM_REF_MB="16")
+    hw = subprocess.run([HARP, "mem", "-t", str(threads), "-b", "64", fa, str(tmp_path / "r.fq")], check=True, capture_output=True,
+                        cwd=tmp_path, text=True, env=env, timeout=600)
+    a, b = sam_body(cpu.stdout), sam_body(hw.stdout)
+    assert len(a) == len(b) and a == b
+    stat = [l for l in hw.stderr.splitlines() if l.startswith("[harp_shim] requests=")]
+    assert stat, hw.stderr[-3000:]
+    kv = dict(t.split("=") for t in stat[-1].split()[1:])
+    assert int(kv["index_staged"]) == 1 and int(kv["requests"]) > 0
+    if threads == 1:      # nobody competes for the single in-flight request: (nearly) every call goes through the protocol
+        assert int(kv["reads"]) > 3 * n, kv
