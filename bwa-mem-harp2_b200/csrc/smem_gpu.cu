@@ -7,15 +7,14 @@
 // No CPU fallback exists here: every failure is an error code.
 #include "../../include/smem_gpu.h"
 #include "smem_kernels.cuh"
-#include <condition_variable>
-#include <mutex>
 #include <algorithm>
-#include <cstdio>
-#include <cstring>
-#include <string>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -31,11 +30,13 @@ struct DeviceCtx {
 	size_t index_bytes = 0;
 	DevIndex ix{};
 	bool has_index = false;
+	bool owns_index = true;          // false: d_index aliases the copy of an earlier context on the same GPU
+	// suffix-array samples and the seed-level API (section 8f-1)
 	u64 *d_sa = nullptr; bool owns_sa = true; int sa_shift = -1; u64 n_sa = 0;
 	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
 	int *d_scnt = nullptr; long long *d_soff = nullptr, *d_sroff = nullptr; size_t s_cap = 0, sroff_cap = 0;
 	Seed *d_seeds = nullptr; size_t seeds_cap = 0; long long n_seeds = 0;
-	bool owns_index = true;          // false: d_index aliases the copy of an earlier context on the same GPU
+	// pipeline lanes
 	int lane = 0, lanes_on_dev = 1;  // pipeline lane of this context on its GPU
 	DeviceCtx *prev_lane = nullptr;  // the lane whose seed kernel runs right before this one's
 	struct smem_gpu *owner = nullptr;
@@ -158,7 +159,7 @@ int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int
 	CK(cudaMallocHost((void **)&d.h_status, 128));
 	// per-pair scratch for the default launch geometry (re-grown in ctx_run if blocks_per_sm is raised): allocating
 	// it lazily would delay the first lane's first kernel by a cudaMalloc
-	d.scratch_entries = (size_t)d.sm_count * 9 * (SEED_BLOCK / 2) * 3 * (size_t)(max_len + 2);
+	d.scratch_entries = (size_t)d.sm_count * 9 * 64 * 3 * (size_t)(max_len + 2);
 	CK(cudaMalloc((void **)&d.d_scratch, d.scratch_entries * sizeof(Intv)));
 	// block sums of the counts -> offsets scan
 	d.tmp_bytes = ((size_t)(read_cap + 1) / SCAN_PER_BLOCK + 2) * sizeof(long long);
@@ -275,6 +276,11 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 	case 9: LAUNCH(9); break;
 	case 10: LAUNCH(10); break;
 	case 12: LAUNCH(12); break;
+#if SEED_BLOCK == 64
+	case 14: LAUNCH(14); break;
+	case 16: LAUNCH(16); break;
+	case 18: LAUNCH(18); break;
+#endif
 	default: LAUNCH(3); break;
 	}
 #undef LAUNCH
@@ -638,7 +644,7 @@ int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int6
 	smem_gpu *h = new (std::nothrow) smem_gpu();
 	if (!h) return SMEM_GPU_E_NOMEM;
 	h->max_batch = max_batch_reads; h->max_len = max_read_len;
-	h->slot_cap = std::max(128, (max_read_len + 31) / 32 * 32);      // long reads emit more intervals (250 bp: 48 on average)
+	h->slot_cap = std::min(256, std::max(128, (max_read_len + 31) / 32 * 32));   // long reads emit more intervals (250 bp: 48 on average); rarer, longer lists take the re-run
 	h->devs.resize(n_devices);
 	const int64_t per = (max_batch_reads + n_devices - 1) / n_devices;
 	for (int k = 0; k < n_devices; ++k) {
@@ -932,7 +938,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 {
 	if (!h || !name) return SMEM_GPU_E_ARG;
 	if (!strcmp(name, "blocks_per_sm")) {
-		static const int ok[] = {3, 4, 5, 6, 7, 8, 9, 10, 12};
+		static const int ok[] = {3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 18};
 		for (int k : ok) if (k == v) { h->blocks_per_sm = (int)v; return 0; }
 		return SMEM_GPU_E_ARG;
 	}

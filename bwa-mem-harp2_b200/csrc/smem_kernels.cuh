@@ -9,7 +9,9 @@ enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_I
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index (TRACE: step*2 + pass) rides in info bits 48..63
 #define AUX_SHIFT 16         // ... and, in TRACE mode, bwt_smem1's return value in bits 16..31 (query positions are < 2^16)
 #define INFO_MASK 0x0000ffff0000ffffull
+#ifndef SEED_BLOCK
 #define SEED_BLOCK 128       // threads per CTA of the seeding kernel (= 64 lane pairs = 64 reads in flight)
+#endif
 
 // per-pair shared memory: [B entries | cold state | query, two bases per byte]
 // cold state: 32-bit rk, rid, n_out, max_s (2 words); everything else is a query position or a small count (16 bit)
