@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--l2-hot-min-intv", type=int, default=-1)
     ap.add_argument("--lanes", type=int, default=4, help="pipeline lanes per GPU of the end-to-end handle")
+    ap.add_argument("--host-threads", type=int, default=2, help="host worker threads of the end-to-end leg, each with its own handle sharing one index (the reference's -t N pattern)")
     ap.add_argument("--spare-sms", type=int, default=-1)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap]] to time (stderr), e.g. 6,8:16384,9::17")
@@ -308,26 +309,54 @@ def main():
         if args.spare_sms >= 0:
             g.set_param("spare_sms", args.spare_sms)
         g.upload_index(ix)
-    pintv = sg.PinnedArray(lib, (total + 1024, 4), np.uint64)
-    proff = sg.PinnedArray(lib, (n + 1,), np.int64)
+    # Each of `--host-threads` worker threads owns a handle (sharing the first one's index copy, smem_gpu_share_index)
+    # and its own pinned result buffers, and makes the public call for the steps it is given: step k's copies overlap
+    # step k+1's kernels.  Every step still copies its inputs H2D and its results D2H inside the timed region.
     import ctypes as C
+    T = max(1, args.host_threads)
+    workers = [g]
+    for _ in range(1, T):
+        w = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local] * max(1, args.lanes))
+        if args.blocks_per_sm:
+            w.set_param("blocks_per_sm", args.blocks_per_sm)
+        w.share_index_from(g)
+        workers.append(w)
+    pintvs = [sg.PinnedArray(lib, (total + 1024, 4), np.uint64) for _ in range(T)]
+    proffs = [sg.PinnedArray(lib, (n + 1,), np.int64) for _ in range(T)]
+    pintv, proff = pintvs[0], proffs[0]
 
-    def e2e_step():
+    def e2e_step(t=0):
         tot = C.c_int64(0)
-        rc = lib.smem_gpu_collect(g.h, C.c_int64(n), pseq.array.ctypes.data_as(C.POINTER(C.c_uint8)),
+        rc = lib.smem_gpu_collect(workers[t].h, C.c_int64(n), pseq.array.ctypes.data_as(C.POINTER(C.c_uint8)),
                                   poffs.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(opt),
-                                  pintv.array.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(pintv.array.shape[0]),
-                                  proff.array.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(tot))
+                                  pintvs[t].array.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(pintvs[t].array.shape[0]),
+                                  proffs[t].array.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(tot))
         if rc:
-            raise SystemExit(f"smem_gpu_collect failed: {rc} {lib.smem_gpu_last_error(g.h).decode()}")
+            raise SystemExit(f"smem_gpu_collect failed: {rc} {lib.smem_gpu_last_error(workers[t].h).decode()}")
         return int(tot.value)
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(k_steps):
+        """k_steps calls of the public API spread over the worker threads; returns the interval count of a step."""
+        if T == 1:
+            r = 0
+            for _ in range(k_steps):
+                r = e2e_step(0)
+            return r
+        res = [0] * T
+        def work(t):
+            for _ in range(t, k_steps, T):
+                res[t] = e2e_step(t)
+        th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return max(res)
+
+    e2e_run(2 * T)
     sync()
     t1 = time.perf_counter()
-    for _ in range(args.steps):
-        tot_e2e = e2e_step()
+    tot_e2e = e2e_run(args.steps)
     sync()
     dt_e2e = time.perf_counter() - t1
     te = g.timing()
@@ -443,7 +472,7 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": world * n * args.steps / dt_e2e, "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
                     "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "pipeline_lanes_per_gpu": args.lanes, "intervals": int(tot_e2e)},
+                    "pipeline_lanes_per_gpu": args.lanes, "host_threads": T, "intervals": int(tot_e2e)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "seed_kernel<COLLECT>",

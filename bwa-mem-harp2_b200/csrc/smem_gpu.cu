@@ -825,6 +825,22 @@ int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int
 	return upload_all(h, ix, src_device);
 }
 
+int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src)
+{
+	if (!dst || !src || dst == src) return SMEM_GPU_E_ARG;
+	for (auto &d : dst->devs) {
+		const DeviceCtx *o = nullptr;
+		for (auto &c : src->devs) if (c.dev == d.dev && c.has_index) { o = &c; break; }
+		if (!o) { dst->err = "source handle has no index on device " + std::to_string(d.dev); return SMEM_GPU_E_NOINDEX; }
+		cudaSetDevice(d.dev);
+		if (d.d_index && d.owns_index) cudaFree(d.d_index);
+		if (d.d_sa && d.owns_sa) cudaFree(d.d_sa);
+		d.d_index = o->d_index; d.owns_index = false; d.index_bytes = o->index_bytes; d.ix = o->ix; d.has_index = true;
+		d.d_sa = o->d_sa; d.owns_sa = false; d.sa_shift = o->sa_shift; d.n_sa = o->n_sa;
+	}
+	return 0;
+}
+
 int smem_gpu_upload_sa(smem_gpu_t *h, int sa_intv, uint64_t n_sa, const uint64_t *sa, int src_device)
 {
 	if (!h || !sa || n_sa < 1 || sa_intv < 1 || (sa_intv & (sa_intv - 1))) return SMEM_GPU_E_ARG;   // power of two (bwt.c:85-86)

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_trace", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -155,6 +155,11 @@ class SmemGpu:
             words = np.ascontiguousarray(index.words_numpy(), np.uint32)
             desc.bwt = words.ctypes.data
             self._check(self.lib.smem_gpu_upload_index(self.h, C.byref(desc)))
+
+    def share_index_from(self, other: "SmemGpu"):
+        """Alias ``other``'s index / SA copies (one handle per host thread, one index per GPU)."""
+        self._check(self.lib.smem_gpu_share_index(self.h, other.h))
+        self._shared_from = other        # keep the owner alive
 
     def upload_sa(self, index):
         """Suffix-array samples of ``index`` (sa_intv, sa) -> HBM, for :meth:`sa`."""

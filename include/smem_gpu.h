@@ -79,6 +79,12 @@ int smem_gpu_upload_index(smem_gpu_t *h, const smem_index_desc_t *ix);
 /* Same, but ix->bwt is a device pointer on CUDA device `src_device` (index built on the GPU). */
 int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device);
 
+/* Several handles on the same GPU(s) -- one per host worker thread, the reference's `-t N` pattern -- can share
+ * ONE copy of the index (and of the suffix-array samples): dst's contexts alias src's device buffers.  Both handles
+ * must list the same devices; src must outlive dst and must not re-upload while dst is in use.  Calls on different
+ * handles may run concurrently from different threads, so one thread's copies overlap another thread's kernels. */
+int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src);
+
 /* Whole-read seeding == the enumeration loop of mem_insert_seed (bwamem.c:453-460):
  * smem_next2 (bwamem.c:244-305: pass 1, 0.7.8 re-seed of the longest SMEM, ordered merge) to
  * exhaustion for every read.  step_out (nullable) receives, per interval, the index of the
