@@ -7,6 +7,7 @@
 // No CPU fallback exists here: every failure is an error code.
 #include "../../include/smem_gpu.h"
 #include "smem_kernels.cuh"
+#include "smem_fast.cuh"
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -33,6 +34,10 @@ struct DeviceCtx {
 	bool owns_index = true;          // false: d_index aliases the copy of an earlier context on the same GPU
 	// suffix-array samples and the seed-level API (section 8f-1)
 	u64 *d_sa = nullptr; bool owns_sa = true; int sa_shift = -1; u64 n_sa = 0;
+	// k-mer count pyramid of the fast path (smem_fast.cuh)
+	FastTables ft{}; bool has_tables = false, owns_tables = true;
+	int *d_esc = nullptr;
+	int64_t escaped = 0;
 	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
 	int *d_scnt = nullptr; long long *d_soff = nullptr, *d_sroff = nullptr; size_t s_cap = 0, sroff_cap = 0;
 	Seed *d_seeds = nullptr; size_t seeds_cap = 0; long long n_seeds = 0;
@@ -90,6 +95,8 @@ struct smem_gpu {
 	int force_wide = 0;
 	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
 	int chain_lanes = 0;             // 1: lane k's seed kernel waits for lane k-1's (no tail overlap)
+	int fast = 1;                    // use the k-mer count pyramid for MODE_COLLECT when its tables are present
+	int fast_blocks_per_sm = 6, fast_b_cap = 6;
 	int reuse = 0;                   // keep the last K/L occ sectors in registers and skip the gather when the block repeats:
 	                                 // +14 % at equal occupancy, but the 16 extra registers cost that occupancy (tie) -> off
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -149,6 +156,7 @@ int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int
 	if ((rc = dev_alloc(d, &d.d_counts, (size_t)read_cap + 1))) return rc;
 	if ((rc = dev_alloc(d, &d.d_overflow, (size_t)read_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_status, 8))) return rc;
+	if ((rc = dev_alloc(d, &d.d_esc, (size_t)read_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_off, (size_t)read_cap + 1))) return rc;
 	if ((rc = dev_alloc(d, &d.d_slots, (size_t)read_cap * slot_cap))) return rc;
 	d.slots_cap_alloc = slot_cap;
@@ -172,6 +180,8 @@ void ctx_free(DeviceCtx &d)
 	cudaSetDevice(d.dev);
 	if (d.owns_index) cudaFree(d.d_index);
 	if (d.owns_sa) cudaFree(d.d_sa);
+	if (d.owns_tables && d.has_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
+	cudaFree(d.d_esc);
 	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
 	cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
@@ -217,6 +227,83 @@ int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 	for (int i = 0; i < 5; ++i) d.ix.L2[i] = ix->L2[i];
 	d.ix.seq_len = ix->seq_len;
 	d.has_index = true;
+	return 0;
+}
+
+
+// K-mer count pyramid (smem_fast.cuh) built on the device from the 2-bit forward text (`.pac` of the reference,
+// bntseq.c:268-273 doubles it with its reverse complement).  pac: (l_pac + 3) / 4 bytes on the host (src_device < 0)
+// or on CUDA device src_device.
+int ctx_build_tables(DeviceCtx &d, const uint8_t *pac, int64_t l_pac, int src_device, int DL)
+{
+	CK(cudaSetDevice(d.dev));
+	if (d.has_tables && d.owns_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
+	d.ft = FastTables{}; d.has_tables = false; d.owns_tables = true;
+	const int K = DL + 1, LP = DL + 4, D = DL + 5;
+	const long long n = 2 * l_pac;
+	const size_t pac_bytes = (size_t)((l_pac + 3) / 4);
+	uint8_t *d_pac = nullptr;
+	u64 *tw = nullptr, *bsum = nullptr;
+	u32 *cntK = nullptr, *cnt = nullptr;
+	u64 *cum = nullptr;
+	uint8_t *pyr = nullptr, *top = nullptr;
+	auto fail = [&](int rc) { cudaFree(d_pac == pac ? nullptr : d_pac); cudaFree(tw); cudaFree(bsum); cudaFree(cntK); cudaFree(cnt); cudaFree(cum); cudaFree(pyr); cudaFree(top); return rc; };
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); d.err = b_; return fail(e_ == cudaErrorMemoryAllocation ? SMEM_GPU_E_NOMEM : SMEM_GPU_E_CUDA); } } while (0)
+	if (src_device == d.dev) d_pac = const_cast<uint8_t *>(pac);
+	else {
+		CKT(cudaMalloc((void **)&d_pac, pac_bytes));
+		if (src_device < 0) CKT(cudaMemcpyAsync(d_pac, pac, pac_bytes, cudaMemcpyHostToDevice, d.stream));
+		else CKT(cudaMemcpyPeerAsync(d_pac, d.dev, pac, src_device, pac_bytes, d.stream));
+	}
+	// the last D symbols of T are the reverse complement of the first D symbols of the forward text
+	uint8_t head[8] = {0};
+	CKT(cudaMemcpyAsync(head, d_pac, std::min<size_t>(pac_bytes, 8), cudaMemcpyDeviceToHost, d.stream));
+	CKT(cudaStreamSynchronize(d.stream));
+	TailCodes tails{};
+	for (int a = 1; a <= D && a < 20; ++a) {
+		u64 code = 0;
+		for (int k = 0; k < a; ++k) { const int o = a - 1 - k; code = (code << 2) | (u64)(3 - ((head[o >> 2] >> ((~o & 3) << 1)) & 3)); }
+		tails.code[a] = code;
+	}
+	const long long n_words = (n + 31) / 32 + 2;
+	const size_t n_lvl = (size_t)lvl_off(K), n_cum = (size_t)lvl_off(K + 1);       // entries of levels 1..DL / 1..DL+1
+	CKT(cudaMalloc((void **)&tw, (size_t)n_words * 8));
+	CKT(cudaMalloc((void **)&cntK, ((size_t)1 << (2 * K)) * 4));
+	CKT(cudaMalloc((void **)&cnt, n_lvl * 4));
+	CKT(cudaMalloc((void **)&cum, n_cum * 8));
+	CKT(cudaMalloc((void **)&pyr, (size_t)1 << (2 * LP)));
+	CKT(cudaMalloc((void **)&top, (size_t)1 << (2 * D)));
+	const long long nbK = (((long long)1 << (2 * K)) + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK;
+	CKT(cudaMalloc((void **)&bsum, (size_t)(nbK + 2) * 8));
+	CKT(cudaMemsetAsync(cntK, 0, ((size_t)1 << (2 * K)) * 4, d.stream));
+	CKT(cudaMemsetAsync(pyr, 0, (size_t)1 << (2 * LP), d.stream));
+	CKT(cudaMemsetAsync(top, 0, (size_t)1 << (2 * D), d.stream));
+	pack_text_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, tw, n_words);
+	kmer_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(tw, n, DL, cntK, pyr, top);
+	CKT(cudaGetLastError());
+	// levels DL .. 1 by summing children; x[0] of every level by an exclusive scan
+	for (int L = K; L >= 1; --L) {
+		const long long nL = (long long)1 << (2 * L);
+		const u32 *src = L == K ? cntK : cnt + lvl_off(L);
+		if (L > 1) {
+			const long long np = nL / 4;
+			kmer_reduce_kernel<<<(unsigned)((np + 255) / 256), 256, 0, d.stream>>>(src, cnt + lvl_off(L - 1), np, tails.code[L - 1]);
+		}
+		const int nb = (int)((nL + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
+		cum_local_kernel<<<nb, SCAN_TPB, 0, d.stream>>>(src, nL, cum + lvl_off(L), bsum);
+		scan_bsum_kernel<<<1, SCAN_TPB, 0, d.stream>>>((long long *)bsum, nb);
+		cum_add_kernel<<<(unsigned)((nL + 255) / 256), 256, 0, d.stream>>>(cum + lvl_off(L), nL, bsum, L, tails);
+		CKT(cudaGetLastError());
+	}
+	// entries next to a suffix of T shorter than their level: unknown (see bwa-mem-harp2_b200/kmer_tables.py)
+	for (int a = K; a < LP; ++a) CKT(cudaMemsetAsync(pyr + (tails.code[a] << (2 * (LP - a))), 255, (size_t)1 << (2 * (LP - a)), d.stream));
+	CKT(cudaMemsetAsync(top + (tails.code[LP] << 2), 255, 4, d.stream));
+	CKT(cudaStreamSynchronize(d.stream));
+#undef CKT
+	if (d_pac != pac) cudaFree(d_pac);
+	cudaFree(tw); cudaFree(cntK); cudaFree(bsum);
+	d.ft.cnt = cnt; d.ft.cum = cum; d.ft.pyr = pyr; d.ft.top = top; d.ft.DL = DL;
+	d.has_tables = true;
 	return 0;
 }
 
@@ -386,20 +473,56 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		lk.unlock();
 		CK(cudaStreamWaitEvent(d.stream, d.prev_lane->ev1, 0));
 	}
-	int rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.reuse != 0)
-	       : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.reuse != 0) : launch_seed<MODE_TRACE>(d, p, bps, grid, smem, wide, false);
+	int rc = 0;
+	d.escaped = 0;
+	const bool use_fast = mode == MODE_COLLECT && h.fast && d.has_tables && !wide && h.max_len < 32768 && d.ft.DL + 5 <= 18;
+	if (use_fast) {
+		// k-mer count pyramid (smem_fast.cuh): the table-driven kernel, then the interval resolution; reads it gives up
+		// on (a table said "unknown") join the overflow list and are seeded by the FM kernel below
+		FastParams fp{};
+		fp.s = p; fp.t = d.ft; fp.esc = d.d_esc;
+		fp.q2_words = (h.max_len + 15) / 16 + 2;
+		fp.esc_cap = std::min(h.slot_cap, 32);
+		fp.s.b_cap = h.fast_b_cap;
+		fp.s.q_stride = (8 * fp.q2_words + 15) / 16 * 16;
+		const int q2_bytes = (4 * fp.q2_words + 15) / 16 * 16;
+		fp.s.pair_stride = (fp.s.b_cap * 16 + FS_BYTES + fp.s.q_stride + q2_bytes + 15) / 16 * 16;
+		const size_t smem_f = (size_t)pairs_per_cta * fp.s.pair_stride;
+		if (smem_f > smem_budget) { d.err = "read length too large for the shared-memory staging of one CTA"; return SMEM_GPU_E_CAPACITY; }
+		const int fb = h.fast_blocks_per_sm;
+		const int grid_f = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * fb, (d.n + pairs_per_cta - 1) / pairs_per_cta);
+		CK(cudaMemsetAsync(d.d_esc, 0, (size_t)d.n * sizeof(int), d.stream));
+#define LAUNCH_F(B) do { CK(cudaFuncSetAttribute(fast_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
+		fast_kernel<B><<<grid_f, SEED_BLOCK, smem_f, d.stream>>>(fp); } while (0)
+		switch (fb) {
+		case 3: LAUNCH_F(3); break;
+		case 4: LAUNCH_F(4); break;
+		case 5: LAUNCH_F(5); break;
+		case 7: LAUNCH_F(7); break;
+		case 8: LAUNCH_F(8); break;
+		default: LAUNCH_F(6); break;
+		}
+#undef LAUNCH_F
+		CK(cudaGetLastError());
+		const long long threads = (long long)d.n * 8;
+		resolve_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(fp);
+		CK(cudaGetLastError());
+		d.launches += 2;
+	} else
+		rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.reuse != 0)
+		   : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.reuse != 0) : launch_seed<MODE_TRACE>(d, p, bps, grid, smem, wide, false);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
 	lane_mark_issued(d, h);
 	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
 	const auto tt0 = std::chrono::steady_clock::now();
 	auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
-	CK(cudaMemcpyAsync(d.h_status, d.d_status, 5 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 6 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
 	const double t_status = tms();
 	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
 	const int n_over = d.h_status[1];
-	d.overflow = n_over;
+	d.overflow = n_over; d.escaped = use_fast ? d.h_status[5] : 0;
 	int big_cap = 0;
 	if (n_over > 0) {
 		// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
@@ -837,8 +960,45 @@ int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src)
 		if (d.d_sa && d.owns_sa) cudaFree(d.d_sa);
 		d.d_index = o->d_index; d.owns_index = false; d.index_bytes = o->index_bytes; d.ix = o->ix; d.has_index = true;
 		d.d_sa = o->d_sa; d.owns_sa = false; d.sa_shift = o->sa_shift; d.n_sa = o->n_sa;
+		if (d.has_tables && d.owns_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
+		d.ft = o->ft; d.has_tables = o->has_tables; d.owns_tables = false;
 	}
 	return 0;
+}
+
+int smem_gpu_build_kmer_tables(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int direct_levels)
+{
+	if (!h || !pac || l_pac < 32 || direct_levels < 2 || direct_levels > 13) return SMEM_GPU_E_ARG;
+	if (2 * l_pac <= direct_levels + 6) return SMEM_GPU_E_ARG;
+	int rc = for_each_device(h, [&](DeviceCtx &d) {
+		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
+		return ctx_build_tables(d, pac, l_pac, src_device, direct_levels);
+	});
+	if (rc) return rc;
+	for (auto &d : h->devs)
+		for (auto &o : h->devs) {
+			if (&o == &d) break;
+			if (o.dev == d.dev) { d.ft = o.ft; d.has_tables = o.has_tables; d.owns_tables = false; break; }
+		}
+	return 0;
+}
+
+int smem_gpu_get_kmer_table(smem_gpu_t *h, int which, int level, void *out, int64_t out_bytes)
+{
+	if (!h || !out) return SMEM_GPU_E_ARG;
+	DeviceCtx &d = h->devs[0];
+	if (!d.has_tables) { h->err = "no k-mer tables built"; return SMEM_GPU_E_NOINDEX; }
+	const int DL = d.ft.DL;
+	const void *src = nullptr;
+	size_t bytes = 0;
+	if (which == 0 && level >= 1 && level <= DL) { src = d.ft.cnt + lvl_off(level); bytes = ((size_t)1 << (2 * level)) * 4; }
+	else if (which == 1 && level >= 1 && level <= DL + 1) { src = d.ft.cum + lvl_off(level); bytes = ((size_t)1 << (2 * level)) * 8; }
+	else if (which == 2) { src = d.ft.pyr; bytes = (size_t)1 << (2 * (DL + 4)); }
+	else if (which == 3) { src = d.ft.top; bytes = (size_t)1 << (2 * (DL + 5)); }
+	else return SMEM_GPU_E_ARG;
+	if ((int64_t)bytes != out_bytes) { h->err = "table size mismatch"; return SMEM_GPU_E_ARG; }
+	cudaSetDevice(d.dev);
+	return cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : SMEM_GPU_E_CUDA;
 }
 
 int smem_gpu_upload_sa(smem_gpu_t *h, int sa_intv, uint64_t n_sa, const uint64_t *sa, int src_device)
@@ -963,6 +1123,9 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "spare_sms")) { if (v < 0 || v > 64) return SMEM_GPU_E_ARG; h->spare_sms = (int)v; return 0; }
 	if (!strcmp(name, "chain_lanes")) { h->chain_lanes = v != 0; return 0; }
 	if (!strcmp(name, "reuse")) { h->reuse = v != 0; return 0; }
+	if (!strcmp(name, "fast")) { h->fast = v != 0; return 0; }
+	if (!strcmp(name, "fast_blocks_per_sm")) { if (v < 3 || v > 8 || v == 9) return SMEM_GPU_E_ARG; h->fast_blocks_per_sm = (int)v; return 0; }
+	if (!strcmp(name, "fast_b_cap")) { if (v < 1 || v > 64) return SMEM_GPU_E_ARG; h->fast_b_cap = (int)v; return 0; }
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
@@ -984,6 +1147,11 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "spare_sms")) return h->spare_sms;
 	if (!strcmp(name, "chain_lanes")) return h->chain_lanes;
 	if (!strcmp(name, "reuse")) return h->reuse;
+	if (!strcmp(name, "fast")) return h->fast;
+	if (!strcmp(name, "fast_blocks_per_sm")) return h->fast_blocks_per_sm;
+	if (!strcmp(name, "fast_b_cap")) return h->fast_b_cap;
+	if (!strcmp(name, "has_kmer_tables")) return h->devs[0].has_tables ? 1 : 0;
+	if (!strcmp(name, "escaped_reads")) { int64_t e = 0; for (auto &d : h->devs) e += d.escaped; return e; }
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
 	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }

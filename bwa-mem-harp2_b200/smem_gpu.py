@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_kmer_tables", "smem_gpu_get_kmer_table", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -71,6 +71,28 @@ def load_library() -> C.CDLL:
     lib.smem_gpu_last_error.restype = C.c_char_p
     lib.smem_gpu_get_param.restype = C.c_int64
     return lib
+
+
+def pack_pac(fwd):
+    """Forward text (uint8 symbols 0..3; numpy or torch) -> the reference's 2-bit .pac layout: 4 bases per byte, first
+    base in the top bits (bntseq.c:_set_pac)."""
+    if hasattr(fwd, "is_cuda"):
+        import torch
+        n = fwd.numel()
+        out = torch.zeros((n + 3) // 4, dtype=torch.uint8, device=fwd.device)
+        step = 1 << 30
+        for s0 in range(0, n, step):
+            s1 = min(n, s0 + step)
+            seg = torch.zeros(((s1 - s0 + 3) // 4) * 4, dtype=torch.uint8, device=fwd.device)
+            seg[: s1 - s0] = fwd[s0:s1] & 3
+            q = seg.view(-1, 4)
+            out[s0 // 4: s0 // 4 + q.shape[0]] = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
+        return out
+    f = np.asarray(fwd, np.uint8) & 3
+    pad = np.zeros(((f.size + 3) // 4) * 4, np.uint8)
+    pad[: f.size] = f
+    q = pad.reshape(-1, 4)
+    return ((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).astype(np.uint8)
 
 
 def _p(a, t):
@@ -160,6 +182,29 @@ class SmemGpu:
         """Alias ``other``'s index / SA copies (one handle per host thread, one index per GPU)."""
         self._check(self.lib.smem_gpu_share_index(self.h, other.h))
         self._shared_from = other        # keep the owner alive
+
+    def build_kmer_tables(self, fwd, direct_levels: int):
+        """K-mer count pyramid of the fast path (smem_gpu_build_kmer_tables) from the forward text ``fwd``
+        (uint8 symbols 0..3, numpy array or torch tensor on any device); packs it to the reference's .pac layout first."""
+        pac = pack_pac(fwd)
+        l_pac = int(fwd.numel() if hasattr(fwd, "numel") else fwd.size)
+        if hasattr(pac, "is_cuda") and pac.is_cuda:
+            import torch
+            torch.cuda.synchronize(pac.device)
+            self._check(self.lib.smem_gpu_build_kmer_tables(self.h, C.c_void_p(pac.data_ptr()), C.c_int64(l_pac), C.c_int(pac.device.index or 0),
+                                                            C.c_int(direct_levels)))
+        else:
+            a = np.ascontiguousarray(pac.numpy() if hasattr(pac, "numpy") else pac, np.uint8)
+            self._check(self.lib.smem_gpu_build_kmer_tables(self.h, C.c_void_p(a.ctypes.data), C.c_int64(l_pac), C.c_int(-1), C.c_int(direct_levels)))
+        self.direct_levels = direct_levels
+
+    def kmer_table(self, which: int, level: int = 0) -> np.ndarray:
+        """Test hook: one table of the pyramid (0 cnt[level], 1 cum[level], 2 pyr, 3 top)."""
+        DL = self.direct_levels
+        n = 4 ** level if which < 2 else 4 ** (DL + 4 + (which == 3))
+        out = np.empty(n, [np.uint32, np.uint64, np.uint8, np.uint8][which])
+        self._check(self.lib.smem_gpu_get_kmer_table(self.h, C.c_int(which), C.c_int(level), C.c_void_p(out.ctypes.data), C.c_int64(out.nbytes)))
+        return out
 
     def upload_sa(self, index):
         """Suffix-array samples of ``index`` (sa_intv, sa) -> HBM, for :meth:`sa`."""

@@ -85,6 +85,20 @@ int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int
  * handles may run concurrently from different threads, so one thread's copies overlap another thread's kernels. */
 int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src);
 
+/* K-mer count pyramid of the indexed text -- optional accelerator tables of smem_gpu_collect.
+ * Most bwt_extend calls of bwt_smem1 (bwt.c:776-835) are made on patterns of at most ~17 bases and only their
+ * interval SIZES are looked at (bwt.c:794-799, 813-824); sizes and interval starts of short patterns are functions of
+ * the pattern alone and are tabulated here for every k-mer of up to direct_levels + 5 bases (12 + 5 on a 3.1 Gbp
+ * index: 25 GB of HBM).  Built on every GPU of the handle from the 2-bit forward text: `pac` is bwaidx_t::pac /
+ * the .pac file of the reference (bntseq.c:_get_pac: 4 bases per byte, first base in the top bits; the library appends
+ * the reverse complement itself, bntseq.c:268-273), l_pac = bntseq_t::l_pac; src_device < 0: host pointer, else the
+ * CUDA device holding it.  Results never depend on the tables: a read whose k-mers hit a saturated or otherwise
+ * unknown entry is seeded by the plain FM kernel.  smem_gpu_smem1 / smem_gpu_trace do not use the tables.
+ * Choose direct_levels so that 4^(direct_levels + 5) is a small multiple of the text length (3.1 Gbp: 12; 100 Mbp: 9). */
+int smem_gpu_build_kmer_tables(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int direct_levels);
+/* Test hook: copy one table to the host.  which: 0 = cnt[level] (uint32), 1 = cum[level] (uint64), 2 = pyr, 3 = top (uint8). */
+int smem_gpu_get_kmer_table(smem_gpu_t *h, int which, int level, void *out, int64_t out_bytes);
+
 /* Whole-read seeding == the enumeration loop of mem_insert_seed (bwamem.c:453-460):
  * smem_next2 (bwamem.c:244-305: pass 1, 0.7.8 re-seed of the longest SMEM, ordered merge) to
  * exhaustion for every read.  step_out (nullable) receives, per interval, the index of the
