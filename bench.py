@@ -47,9 +47,13 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--l2-hot-min-intv", type=int, default=-1)
-    ap.add_argument("--lanes", type=int, default=4, help="pipeline lanes per GPU of the end-to-end handle")
+    ap.add_argument("--lanes", type=int, default=1, help="pipeline lanes per GPU of the end-to-end handle")
     ap.add_argument("--host-threads", type=int, default=2, help="host worker threads of the end-to-end leg, each with its own handle sharing one index (the reference's -t N pattern)")
     ap.add_argument("--spare-sms", type=int, default=-1)
+    ap.add_argument("--fast", action="store_true", help="EXPERIMENTAL: build the k-mer count pyramid and seed through the table-driven kernel (DESIGN.md section 9)")
+    ap.add_argument("--direct-levels", type=int, default=-1, help="depth of the direct k-mer tables (pyramid reaches +5); -1 = from the text length")
+    ap.add_argument("--fast-blocks-per-sm", type=int, default=0)
+    ap.add_argument("--fast-slots", type=int, default=0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
@@ -123,9 +127,11 @@ def make_workload(args, rank, device):
     t_index = time.time() - t0
     reads = sy.simulate_reads(fwd, args.reads, args.read_len, args.err, seed=1000 + rank, paired=True)
     seq, offs = sy.to_batch(reads)
+    sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
+    pac = sg.pack_pac(fwd) if args.fast else None          # the reference's .pac layout of the forward text
     del fwd, reads
     torch.cuda.empty_cache()
-    return ix, seq, offs, t_index
+    return ix, seq, offs, t_index, pac
 
 
 def cpu_engine(ix_host):
@@ -186,7 +192,7 @@ def main():
               (args.ref_bp / 1e9, args.reads * args.read_len / 1e6), "parallelism": f"replicated index, reads sharded x{args.gpus}"}
 
     log(f"rank {rank}/{world}: building workload ({args.ref_bp} bp)")
-    ix, seq, offs, t_index = make_workload(args, rank, device)
+    ix, seq, offs, t_index, pac = make_workload(args, rank, device)
     log(f"index built on GPU in {t_index:.1f}s: seq_len={ix.seq_len} bwt_size={ix.bwt_size} primary={ix.primary}")
     n = len(offs) - 1
 
@@ -221,6 +227,27 @@ def main():
         g.set_param("l2_hot_min_intv", args.l2_hot_min_intv)
     g.upload_index(ix)                      # device -> device copy of the packed bwt_t into the library's HBM buffer
     lib = g.lib
+    fast_info = None
+    if pac is not None:
+        import ctypes as C
+        DL = args.direct_levels
+        if DL < 0:
+            DL = 2
+            while 4 ** (DL + 5) < 1.3 * ix.seq_len and DL < 13:
+                DL += 1
+        torch.cuda.synchronize()
+        tb0 = time.time()
+        g._check(lib.smem_gpu_build_kmer_tables(g.h, C.c_void_p(pac.data_ptr()), C.c_int64(args.ref_bp), C.c_int(local), C.c_int(DL)))
+        fast_info = {"direct_levels": DL, "deepest_level": DL + 5, "build_s": time.time() - tb0,
+                     "table_bytes": 4 ** (DL + 5) + 4 ** (DL + 4) + (4 ** (DL + 1) - 4) // 3 * 4 + (4 ** (DL + 2) - 4) // 3 * 8}
+        g.set_param("fast", 1)
+        if args.fast_blocks_per_sm:
+            g.set_param("fast_blocks_per_sm", args.fast_blocks_per_sm)
+        if args.fast_slots:
+            g.set_param("fast_slots", args.fast_slots)
+        log("k-mer count pyramid:", fast_info)
+        del pac
+        torch.cuda.empty_cache()
     # pinned host batch + pinned result buffers for the end-to-end leg
     pseq = sg.PinnedArray(lib, (len(seq),), np.uint8); pseq.array[:] = seq
     poffs = sg.PinnedArray(lib, (n + 1,), np.int64); poffs.array[:] = offs
@@ -301,14 +328,18 @@ def main():
 
     # ---- end-to-end leg: host buffers in, host buffers out, copies inside the timed region.  The public call is
     # smem_gpu_collect on a handle with `--lanes` pipeline lanes on this GPU (shards overlap H2D / kernels / D2H).
+    escaped = g.get_param("escaped_reads")
+    g_owner = g                             # owns the index and the tables; the end-to-end handles alias them
     if args.lanes > 1:
-        g.close()
         g = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local] * args.lanes)
         if args.blocks_per_sm:
             g.set_param("blocks_per_sm", args.blocks_per_sm)
         if args.spare_sms >= 0:
             g.set_param("spare_sms", args.spare_sms)
-        g.upload_index(ix)
+        if args.fast_blocks_per_sm:
+            g.set_param("fast_blocks_per_sm", args.fast_blocks_per_sm)
+        g.set_param("fast", 1 if args.fast else 0)
+        g.share_index_from(g_owner)
     # Each of `--host-threads` worker threads owns a handle (sharing the first one's index copy, smem_gpu_share_index)
     # and its own pinned result buffers, and makes the public call for the steps it is given: step k's copies overlap
     # step k+1's kernels.  Every step still copies its inputs H2D and its results D2H inside the timed region.
@@ -319,7 +350,10 @@ def main():
         w = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local] * max(1, args.lanes))
         if args.blocks_per_sm:
             w.set_param("blocks_per_sm", args.blocks_per_sm)
-        w.share_index_from(g)
+        if args.fast_blocks_per_sm:
+            w.set_param("fast_blocks_per_sm", args.fast_blocks_per_sm)
+        w.set_param("fast", 1 if args.fast else 0)
+        w.share_index_from(g_owner)
         workers.append(w)
     pintvs = [sg.PinnedArray(lib, (total + 1024, 4), np.uint64) for _ in range(T)]
     proffs = [sg.PinnedArray(lib, (n + 1,), np.int64) for _ in range(T)]
@@ -475,7 +509,8 @@ def main():
                     "pipeline_lanes_per_gpu": args.lanes, "host_threads": T, "intervals": int(tot_e2e)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "seed_kernel<COLLECT>",
+                         "traffic": traffic if not fast_info else None, "peak_source": peak_src,
+                         "kernel": "fast_kernel + resolve_kernel (k-mer count pyramid; FM re-run of escaped reads not included)" if fast_info else "seed_kernel<COLLECT>",
                          "kernel_ms": seed_avg_ms, "algorithmic_bytes_per_read": bytes_per_read,
                          "random_access_peak": rand64, "frac_of_random_access": achieved / rand64 if rand64 else None,
                          "random_access_peak_two_requests": rand64_split,
@@ -484,6 +519,8 @@ def main():
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "intervals_per_step_per_gpu": int(total), "overflow_reads": int(overflow), "index_build_s": t_index,
             "blocks_per_sm": g.get_param("blocks_per_sm"), "l2_hot_min_intv": g.get_param("l2_hot_min_intv"),
+            "fast_path": dict(fast_info, escaped_reads_per_step=int(escaped), blocks_per_sm=g.get_param("fast_blocks_per_sm")) if fast_info else None,
+            "device_ms_per_step": float(np.mean(dev_ms)),
         }
         if probe:
             out["random_access_probe_gbs"] = probe

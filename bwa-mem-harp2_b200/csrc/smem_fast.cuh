@@ -39,6 +39,7 @@ struct FastParams {
 	FastTables t;
 	int *esc;                // [n] 1 = the read is on the overflow / escape list (re-run by the FM kernel)
 	int q2_words;            // 32-bit words of the 2-bit staged query per pair (incl. 2 words of padding)
+	int n_slots;             // read slots per CTA (<= FAST_MAX_SLOTS)
 	int esc_cap;             // slot capacity assumed for the FM re-run of escaped reads (exact after its first round)
 };
 
@@ -82,25 +83,50 @@ __device__ __forceinline__ u64 window64(u32 sq2, int pos)
 	return ((u64)__funnelshift_l(w1, w0, off) << 32) | (u64)__funnelshift_l(w2, w1, off);
 }
 
+// Threads of a CTA are not tied to reads: the per-read state lives in shared-memory SLOTS, and a slot that waits for
+// memory is posted on the ready bitmap of its kind of operation (FM extend forward / backward / grown, table fetch
+// forward / round, GROW forward / backward).  Every warp, on its own and without CTA barriers, takes up to 16 slots
+// of ONE kind (the fullest bitmap), so that its lane pairs run the same code, performs the operation and the rare
+// transitions that follow, and posts the slots again.  (Measured on the way here: one read pinned to one lane pair
+// ran at 6.9 active lanes of 32; sorting the slots CTA-wide before every trip at 15 lanes but waiting at barriers.)
+#ifndef FAST_TPB
+#define FAST_TPB 256
+#endif
+#define FAST_MAX_SLOTS 192
+#define FAST_WORDS (FAST_MAX_SLOTS / 32)
+#define FAST_HDR 256                 // CTA header: ready bitmaps u32 [7][6] | idle-slot count
+enum { FH_BYTES = 64 };              // hot state of a slot (registers while a pair works on it)
+
 template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const FastParams fp)
+__global__ void __launch_bounds__(FAST_TPB, MIN_BLOCKS) fast_kernel(const FastParams fp)
 {
 	typedef BEntry<false> BE;
 	const SeedParams &p = fp.s;
 	const FastTables &T = fp.t;
 	extern __shared__ uint4 smem_raw[];
-	const int lane = threadIdx.x & 31, half = lane & 1;
+	const int tid = threadIdx.x, lane = tid & 31, half = lane & 1;
 	const u32 pm = 3u << (lane & ~1);                       // this pair's lanes
-	const int pair = threadIdx.x >> 1;
-	const int gpair = blockIdx.x * (SEED_BLOCK / 2) + pair;
-	const u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;
-	const u32 sb = sp;                                       // real entries
-	const u32 sc = sp + (u32)p.b_cap * BE::BYTES;            // cold state + sizes
-	const u32 ss = sc + FS_SIZES;                            // sizes[L], u32, L = 0..19
-	const u32 sq = sc + FS_BYTES;                            // query, two bases per byte
-	const u32 sq2 = sq + (u32)p.q_stride;                    // query, 2 bits per base, 16 bases per word
-	Intv *const M1 = p.scratch + (size_t)gpair * 3 * p.scratch_cap;
-	Intv *const BX = M1 + 2 * p.scratch_cap;
+	const int pair = tid >> 1;
+	const u32 s0 = (u32)__cvta_generic_to_shared(smem_raw);
+	const u32 s_slots = s0 + FAST_HDR;
+	u32 *const rdy = reinterpret_cast<u32 *>(smem_raw);                         // [FP_HOT_MAX][FAST_WORDS]
+	volatile u32 *const vrdy = rdy;
+	u32 *const n_idle = rdy + FP_HOT_MAX * FAST_WORDS + 2;
+	const int S = fp.n_slots;
+	u32 sh = 0, sb = 0, sc = 0, ss = 0, sq = 0, sq2 = 0;    // the slot this pair works on: hot state, real entries, cold state, sizes, query (x2)
+	Intv *M1 = nullptr, *BX = nullptr;
+	int slot = 0;
+	auto bind = [&](int sl) {
+		slot = sl;
+		sh = s_slots + (u32)sl * (u32)p.pair_stride;
+		sb = sh + FH_BYTES;
+		sc = sb + (u32)p.b_cap * BE::BYTES;
+		ss = sc + FS_SIZES;
+		sq = sc + FS_BYTES;
+		sq2 = sq + (u32)p.q_stride;
+		M1 = p.scratch + ((size_t)blockIdx.x * S + sl) * 3 * p.scratch_cap;
+		BX = M1 + 2 * p.scratch_cap;
+	};
 	const int DL = T.DL, K = DL + 1, LP = DL + 4, D = DL + 5;
 
 	auto b_put = [&](int idx, u64 x0, u64 x1, u64 x2, u32 end) {
@@ -137,7 +163,24 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 	u64 min_intv = 1, last_s = 0;
 	u32 E = 0;                           // virtual entries: bit b <-> end x + 1 + b
 	int tpos = 0, tlo = 0, thi = 0;      // pending table fetch: window start, lengths wanted
-	int gs = 0;                          // pending GROW: pattern q[gs .. gs + D)
+
+	auto load_state = [&]() {
+		const uint4 h0 = lds_v4(sh), h1 = lds_v4(sh + 16), h2 = lds_v4(sh + 32), h3 = lds_v4(sh + 48);
+		a = (u64)h0.x | ((u64)h0.y << 32); b = (u64)h0.z | ((u64)h0.w << 32);
+		s = (u64)h1.x | ((u64)h1.y << 32); last_s = (u64)h1.z | ((u64)h1.w << 32);
+		E = h2.x; min_intv = h2.y; phase = (int)(h2.z & 255u); c = (int)(signed char)((h2.z >> 8) & 255u); end = h2.z >> 16;
+		i = (int)(short)(h2.w & 0xffffu); j = (int)(h2.w >> 16);
+		n_prev = (int)(h3.x & 0xffffu); n_curr = (int)(h3.x >> 16); x = (int)(h3.y & 0xffffu); len = (int)(h3.y >> 16);
+		tpos = (int)(h3.z & 0xffffu); tlo = (int)((h3.z >> 16) & 255u); thi = (int)(h3.z >> 24); guard = (int)h3.w;
+	};
+	auto store_state = [&]() {
+		if (!half) {
+			sts_v4(sh, make_uint4((u32)a, (u32)(a >> 32), (u32)b, (u32)(b >> 32)));
+			sts_v4(sh + 16, make_uint4((u32)s, (u32)(s >> 32), (u32)last_s, (u32)(last_s >> 32)));
+			sts_v4(sh + 32, make_uint4(E, (u32)min_intv, (u32)phase | (((u32)c & 255u) << 8) | (end << 16), ((u32)i & 0xffffu) | ((u32)j << 16)));
+			sts_v4(sh + 48, make_uint4((u32)n_prev | ((u32)n_curr << 16), (u32)x | ((u32)len << 16), (u32)tpos | ((u32)tlo << 16) | ((u32)thi << 24), (u32)guard));
+		}
+	};
 
 	auto escape = [&]() {                // a table said "unknown": this read goes to the FM kernel
 		const int rk = lds_i32(sc + FS_RK);
@@ -151,9 +194,8 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 		phase = FP_NEED_READ;
 	};
 
-	for (;;) {
-		__syncwarp();
-		// ============================================================== cold section
+	// rare transitions of the per-read state machine; ends in a phase that waits for memory (or FP_IDLE)
+	auto cold = [&]() {
 		while (phase > FP_HOT_MAX) {
 			switch (phase) {
 			case FP_NEED_READ: {
@@ -247,7 +289,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 			} break;
 			case FP_ROUND_VIRT: {    // the real entries of this round are done; now the virtual ones
 				const int r = x - i, bg = D - r;
-				if (bg >= 0 && ((E >> bg) & 1u)) { gs = i + 1; phase = FP_BWD_GROW; }          // it reaches length D + 1: make it real
+				if (bg >= 0 && ((E >> bg) & 1u)) phase = FP_BWD_GROW;          // it reaches length D + 1: make it real
 				else if (E) { tpos = i; tlo = __ffs(E) + r; thi = 32 - __clz(E) + r; phase = FP_RND_TAB; }
 				else phase = FP_ROUND_END;
 			} break;
@@ -312,10 +354,86 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 			default: break;
 			}
 		}
+	};
+
+	// post the slot for its next operation (or retire it)
+	auto post = [&]() {
+		store_state();
+		__threadfence_block();
+		__syncwarp(pm);
+		if (!half) {
+			if (phase == FP_IDLE) atomicAdd(n_idle, 1u);
+			else atomicOr(&rdy[(phase - 1) * FAST_WORDS + (slot >> 5)], 1u << (slot & 31));
+		}
+	};
+
+	for (int t = tid; t < FAST_HDR / 4; t += FAST_TPB) rdy[t] = 0;
+	__syncthreads();
+	for (int sl = pair; sl < S; sl += FAST_TPB / 2) {
+		bind(sl);
+		phase = FP_NEED_READ;
+		cold();
+		post();
+	}
+	for (;;) {
 		__syncwarp();
-		if (__all_sync(FULL_MASK, phase == FP_IDLE)) break;
-		if (phase == FP_IDLE) continue;
-		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + FS_RK)] = 0; phase = FP_NEED_READ; continue; }
+		// ---- the kind of operation with the most ready slots ...
+		int cnt = 0;
+		if (lane < FP_HOT_MAX) {
+#pragma unroll
+			for (int wd = 0; wd < FAST_WORDS; ++wd) cnt += __popc(vrdy[lane * FAST_WORDS + wd]);
+		}
+		int best = cnt, bk = lane;
+#pragma unroll
+		for (int off = 4; off >= 1; off >>= 1) {
+			const int o = __shfl_down_sync(FULL_MASK, best, off), ok_ = __shfl_down_sync(FULL_MASK, bk, off);
+			if (o > best) { best = o; bk = ok_; }
+		}
+		best = __shfl_sync(FULL_MASK, best, 0); bk = __shfl_sync(FULL_MASK, bk, 0);
+		if (best == 0) {
+			u32 idle = 0;
+			if (lane == 0) idle = *(volatile u32 *)n_idle;
+			idle = __shfl_sync(FULL_MASK, idle, 0);
+			if (idle >= (u32)S) break;
+			__nanosleep(200);
+			continue;
+		}
+		// ---- ... up to 16 of them become this warp's (a bit seen set in the value atomicAnd returns is ours)
+		const u32 m = lane < FAST_WORDS ? vrdy[bk * FAST_WORDS + lane] : 0u;
+		const int c_ = __popc(m);
+		int pre = c_;
+#pragma unroll
+		for (int off = 1; off < 8; off <<= 1) { const int t_ = __shfl_up_sync(FULL_MASK, pre, off); if (lane >= off) pre += t_; }
+		pre -= c_;
+		const int take = min(max(16 - pre, 0), c_);
+		u32 rem = m;
+		for (int k = 0; k < take; ++k) rem &= rem - 1u;        // drop the lowest `take` set bits
+		const u32 bits = m ^ rem;
+		u32 got = 0;
+		if (bits) got = atomicAnd(&rdy[bk * FAST_WORDS + lane], ~bits) & bits;
+		const int g_ = __popc(got);
+		int gin = g_;
+#pragma unroll
+		for (int off = 1; off < 8; off <<= 1) { const int t_ = __shfl_up_sync(FULL_MASK, gin, off); if (lane >= off) gin += t_; }
+		const int total = __shfl_sync(FULL_MASK, gin, FAST_WORDS - 1);
+		const int pi = lane >> 1;
+		int my = -1;
+#pragma unroll
+		for (int wd = 0; wd < FAST_WORDS; ++wd) {
+			const u32 gw = __shfl_sync(FULL_MASK, got, wd);
+			const int ge = __shfl_sync(FULL_MASK, gin, wd) - __popc(gw);
+			if (pi >= ge && pi < ge + __popc(gw)) {
+				u32 t_ = gw;
+				for (int k = 0; k < pi - ge; ++k) t_ &= t_ - 1u;
+				my = 32 * wd + __ffs(t_) - 1;
+			}
+		}
+		if (total == 0 || my < 0) continue;
+		__threadfence_block();
+		bind(my);
+		load_state();
+		do {
+		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + FS_RK)] = 0; phase = FP_NEED_READ; break; }
 
 		// ============================================================== one memory round trip per pair
 		// (the warp is divergent by kind of operation, but the loads of all kinds are issued before any result is used)
@@ -345,7 +463,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 			if (thi >= D) v[7] = __ldg(reinterpret_cast<const u32 *>(T.top + ((W >> (64 - 2 * D)) & ~3ull)));
 		} else {
 			// GROW: lane 0 computes x[0] of the D-mer, lane 1 x[0] of its reverse complement (= x[1])
-			const u64 P = window64(sq2, gs) >> (64 - 2 * D);
+			const u64 P = window64(sq2, phase == FP_FWD_GROW ? x : i + 1) >> (64 - 2 * D);
 			W = half ? revcomp_code(P, D) : P;
 			const u64 c16 = W >> 2;
 			gcum = __ldg(T.cum + lvl_off(K) + (c16 >> 6));
@@ -380,7 +498,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 			if (phase == FP_FWD_FM) {                            // bwt.c:794-799
 				const bool diff = ok.s != s;
 				if (diff) b_put(n_curr++, b, a, s, end);
-				if (diff && small) { phase = FP_FWD_DONE; continue; }
+				if (diff && small) { phase = FP_FWD_DONE; break; }
 				a = ok.a; b = ok.b; s = ok.s; end = (u32)(i + 1);
 				++i;
 				const u32 qv = i < len ? qbase(sq, i) : 4u;
@@ -440,10 +558,10 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 					if (nx != prevn) { E |= 1u << (L - 1); if ((u64)nx < min_intv) { stop = true; break; } }
 					prevn = nx;
 				}
-				if (bad) { escape(); continue; }
+				if (bad) { escape(); break; }
 				if (stop) phase = FP_FWD_DONE;
 				else if (avail <= D) { E |= 1u << (Lend - 1); phase = FP_FWD_DONE; }
-				else { gs = x; phase = FP_FWD_GROW; }                 // the pattern outgrows the tables: FM from length D on
+				else phase = FP_FWD_GROW;                 // the pattern outgrows the tables: FM from length D on
 			} else {
 				// one backward round over all virtual entries (bwt.c:813-824 with sizes from the table)
 				const int r = x - i;
@@ -458,7 +576,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 					else if ((n_curr == 0 && E2 == 0) || (u64)n != last_s) { if (!E2) s_new = n; E2 |= 1u << bb; last_s = n; }
 					first = false;
 				}
-				if (bad) { escape(); continue; }
+				if (bad) { escape(); break; }
 				E = E2;
 				sts_i32(sc + FS_STOP, (int)s_new);
 				phase = FP_ROUND_END;
@@ -482,7 +600,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 			const u64 x0 = __shfl_sync(pm, sum, lane & ~1), x1 = __shfl_sync(pm, sum, lane | 1);
 			const u32 sz = __shfl_sync(pm, cnt, lane & ~1);
 			bad |= __shfl_xor_sync(pm, bad, 1);
-			if (bad) { escape(); continue; }
+			if (bad) { escape(); break; }
 			if (phase == FP_FWD_GROW) {
 				a = x1; b = x0; s = sz; end = (u32)(x + D); i = x + D;
 				const u32 qv = i < len ? qbase(sq, i) : 4u;       // (avail > D: this base is valid)
@@ -497,6 +615,9 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) fast_kernel(const Fast
 				phase = FP_GROWN_FM;
 			}
 		}
+		} while (0);
+		cold();
+		post();
 	}
 }
 

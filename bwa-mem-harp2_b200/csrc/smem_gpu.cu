@@ -38,6 +38,8 @@ struct DeviceCtx {
 	FastTables ft{}; bool has_tables = false, owns_tables = true;
 	int *d_esc = nullptr;
 	int64_t escaped = 0;
+	uint64_t turn_epoch = 0;         // epoch of the last run in which this lane took part in the kernel turn
+	bool holds_turn = false;         // this lane's seed kernel is part of the call that currently owns the GPU's kernel turn
 	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
 	int *d_scnt = nullptr; long long *d_soff = nullptr, *d_sroff = nullptr; size_t s_cap = 0, sroff_cap = 0;
 	Seed *d_seeds = nullptr; size_t seeds_cap = 0; long long n_seeds = 0;
@@ -95,8 +97,9 @@ struct smem_gpu {
 	int force_wide = 0;
 	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
 	int chain_lanes = 0;             // 1: lane k's seed kernel waits for lane k-1's (no tail overlap)
-	int fast = 1;                    // use the k-mer count pyramid for MODE_COLLECT when its tables are present
-	int fast_blocks_per_sm = 6, fast_b_cap = 6;
+	int fast = 0;                    // EXPERIMENTAL, opt-in: use the k-mer count pyramid for MODE_COLLECT when its tables are present
+	                                 // (bit-exact, but measured slower than the FM kernel so far: DESIGN.md section 9)
+	int fast_blocks_per_sm = 4, fast_b_cap = 4, fast_slots = 128;
 	int reuse = 0;                   // keep the last K/L occ sectors in registers and skip the gather when the block repeats:
 	                                 // +14 % at equal occupancy, but the 16 extra registers cost that occupancy (tie) -> off
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -383,6 +386,35 @@ int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, 
 	return wide ? launch_seed_w<MODE, true, false>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, false>(d, p, blocks_per_sm, grid, smem);
 }
 
+// Several handles on one GPU (one per host thread, smem_gpu_share_index): the seed kernels of ONE call run as a block.
+// Without this the lanes of concurrent calls interleave on the GPU, all calls finish together, and their copies
+// (H2D before, D2H after) find the GPU idle; with it call B stages its reads while call A's kernels run and starts
+// its kernels while call A's results travel back.
+struct DevTurn { std::mutex mu; std::condition_variable cv; const smem_gpu *owner = nullptr; int remaining = 0; };
+DevTurn g_turn[64];
+
+void turn_acquire(DeviceCtx &d, smem_gpu &h)
+{
+	DevTurn &t = g_turn[d.dev & 63];
+	std::unique_lock<std::mutex> lk(t.mu);
+	t.cv.wait(lk, [&] { return t.owner == nullptr || t.owner == &h; });
+	if (t.owner == nullptr) {
+		t.owner = &h; t.remaining = 0;
+		for (auto &o : h.devs) t.remaining += o.dev == d.dev && o.hi > o.lo;
+	}
+	d.holds_turn = true;
+	d.turn_epoch = h.epoch;
+}
+
+void turn_release(DeviceCtx &d)
+{
+	if (!d.holds_turn) return;
+	d.holds_turn = false;
+	DevTurn &t = g_turn[d.dev & 63];
+	std::lock_guard<std::mutex> lk(t.mu);
+	if (--t.remaining <= 0) { t.owner = nullptr; t.remaining = 0; t.cv.notify_all(); }
+}
+
 // Lanes of one GPU run their seed kernels strictly in lane order: lane k waits (on the device) for lane k-1's
 // seed kernel of the same epoch.  The host-side hand-shake only makes sure the event was recorded before it is waited on.
 void lane_mark_issued(DeviceCtx &d, smem_gpu &h)
@@ -397,6 +429,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 int ctx_run(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *opt)
 {
 	const int rc = ctx_run_inner(d, h, mode, opt);
+	turn_release(d);                          // (normally released right after the seed kernel; this covers the error paths)
+	if (rc && d.hi > d.lo && d.turn_epoch != h.epoch) { turn_acquire(d, h); turn_release(d); }   // failed before its turn: keep the lane count right
 	if (d.seed_issued != h.epoch) {           // early return (no reads / error): never leave the next lane waiting
 		cudaSetDevice(d.dev);
 		cudaEventRecord(d.ev1, d.stream);
@@ -464,6 +498,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	}
 	p.hot_min_intv = (u64)h.hot_min_intv;
 
+	turn_acquire(d, h);
 	CK(cudaEventRecord(d.ev0, d.stream));
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
@@ -486,21 +521,30 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		fp.s.b_cap = h.fast_b_cap;
 		fp.s.q_stride = (8 * fp.q2_words + 15) / 16 * 16;
 		const int q2_bytes = (4 * fp.q2_words + 15) / 16 * 16;
-		fp.s.pair_stride = (fp.s.b_cap * 16 + FS_BYTES + fp.s.q_stride + q2_bytes + 15) / 16 * 16;
-		const size_t smem_f = (size_t)pairs_per_cta * fp.s.pair_stride;
+		fp.s.pair_stride = (FH_BYTES + fp.s.b_cap * 16 + FS_BYTES + fp.s.q_stride + q2_bytes + 15) / 16 * 16;
+		fp.n_slots = h.fast_slots;
+		const size_t smem_f = FAST_HDR + (size_t)fp.n_slots * fp.s.pair_stride;
 		if (smem_f > smem_budget) { d.err = "read length too large for the shared-memory staging of one CTA"; return SMEM_GPU_E_CAPACITY; }
 		const int fb = h.fast_blocks_per_sm;
-		const int grid_f = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * fb, (d.n + pairs_per_cta - 1) / pairs_per_cta);
+		const int grid_f = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * fb, (d.n + fp.n_slots - 1) / fp.n_slots);
+		const size_t need_f = (size_t)d.sm_count * fb * fp.n_slots * 3 * scratch_cap;
+		if (need_f > d.scratch_entries) {
+			if (d.d_scratch) CK(cudaFree(d.d_scratch));
+			d.d_scratch = nullptr; d.scratch_entries = 0;
+			CK(cudaMalloc((void **)&d.d_scratch, need_f * sizeof(Intv)));
+			d.scratch_entries = need_f;
+			fp.s.scratch = d.d_scratch; p.scratch = d.d_scratch;
+		}
 		CK(cudaMemsetAsync(d.d_esc, 0, (size_t)d.n * sizeof(int), d.stream));
 #define LAUNCH_F(B) do { CK(cudaFuncSetAttribute(fast_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
-		fast_kernel<B><<<grid_f, SEED_BLOCK, smem_f, d.stream>>>(fp); } while (0)
+		fast_kernel<B><<<grid_f, FAST_TPB, smem_f, d.stream>>>(fp); } while (0)
 		switch (fb) {
-		case 3: LAUNCH_F(3); break;
+		case 2: LAUNCH_F(2); break;
 		case 4: LAUNCH_F(4); break;
 		case 5: LAUNCH_F(5); break;
-		case 7: LAUNCH_F(7); break;
+		case 6: LAUNCH_F(6); break;
 		case 8: LAUNCH_F(8); break;
-		default: LAUNCH_F(6); break;
+		default: LAUNCH_F(3); break;
 		}
 #undef LAUNCH_F
 		CK(cudaGetLastError());
@@ -601,6 +645,9 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		++d.launches;
 	}
 	CK(cudaEventRecord(d.ev2, d.stream));
+	// the scan / compaction kernels are queued ahead of whatever the next call launches: a persistent seed kernel that got
+	// there first would hold every SM and they would wait for it to drain
+	turn_release(d);
 	CK(cudaStreamSynchronize(d.stream));
 	if (trace) fprintf(stderr, "[smem_gpu trace]   lane %d run: status +%.2f scan +%.2f compact +%.2f ms after the seed launch\n", d.lane, t_status, t_scan, tms());
 	CK(cudaEventElapsedTime(&d.seed_ms, d.ev0, d.ev1));
@@ -718,6 +765,7 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const uint8_t *seq, const int64
 		int r = ctx_stage(d, *h, seq, offs, x, mi);
 		const double tb = ms();
 		if (!r) r = ctx_run(d, *h, mode, opt);
+		else if (d.hi > d.lo) { turn_acquire(d, *h); turn_release(d); }    // keep the turn's lane count right
 		const double tc = ms();
 		long long base = 0;
 		{
@@ -1124,8 +1172,9 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "chain_lanes")) { h->chain_lanes = v != 0; return 0; }
 	if (!strcmp(name, "reuse")) { h->reuse = v != 0; return 0; }
 	if (!strcmp(name, "fast")) { h->fast = v != 0; return 0; }
-	if (!strcmp(name, "fast_blocks_per_sm")) { if (v < 3 || v > 8 || v == 9) return SMEM_GPU_E_ARG; h->fast_blocks_per_sm = (int)v; return 0; }
+	if (!strcmp(name, "fast_blocks_per_sm")) { if (v < 2 || v > 8 || v == 7) return SMEM_GPU_E_ARG; h->fast_blocks_per_sm = (int)v; return 0; }
 	if (!strcmp(name, "fast_b_cap")) { if (v < 1 || v > 64) return SMEM_GPU_E_ARG; h->fast_b_cap = (int)v; return 0; }
+	if (!strcmp(name, "fast_slots")) { if (v < 16 || v > FAST_MAX_SLOTS) return SMEM_GPU_E_ARG; h->fast_slots = (int)v; return 0; }
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
@@ -1150,6 +1199,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "fast")) return h->fast;
 	if (!strcmp(name, "fast_blocks_per_sm")) return h->fast_blocks_per_sm;
 	if (!strcmp(name, "fast_b_cap")) return h->fast_b_cap;
+	if (!strcmp(name, "fast_slots")) return h->fast_slots;
 	if (!strcmp(name, "has_kmer_tables")) return h->devs[0].has_tables ? 1 : 0;
 	if (!strcmp(name, "escaped_reads")) { int64_t e = 0; for (auto &d : h->devs) e += d.escaped; return e; }
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;

@@ -35,6 +35,7 @@ def world(fm, synth, sg):
     g = sg.SmemGpu(max_batch_reads=40_000, max_read_len=260)
     g.upload_index(ix)
     g.build_kmer_tables(ref, 6)                      # tables up to 11-mers on a 2 Mbp text (4^11 = 4.2 M)
+    g.set_param("fast", 1)                           # the table-driven path is opt-in
     return ref, ix, Oracle(ix), g
 
 
@@ -109,7 +110,7 @@ def test_fast_small_slots_and_knobs(world, synth):
     seq, offs = synth.to_batch(synth.simulate_reads(ref, 4000, 150, 0.03, seed=12, n_frac=0.02))
     a = o.collect(seq, offs, OSeedOpt(), nthreads=8)
     old = g.get_param("slot_cap")
-    for name, val, back in (("slot_cap", 8, old), ("fast_b_cap", 1, 6), ("fast_blocks_per_sm", 4, 6), ("fast_blocks_per_sm", 8, 6)):
+    for name, val, back in (("slot_cap", 8, old), ("fast_b_cap", 1, 4), ("fast_blocks_per_sm", 2, 4), ("fast_slots", 40, 128)):
         g.set_param(name, val)
         b = g.collect(seq, offs)
         g.set_param(name, back)
