@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--fast-blocks-per-sm", type=int, default=0)
     ap.add_argument("--fast-slots", type=int, default=0)
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap]] to time (stderr), e.g. 6,8:16384,9::17")
+    ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap[:reuse[:l2_mode]]]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
     ap.add_argument("--batch-sweep", action="store_true", help="BASELINE config 5: latency/throughput of smem_gpu_collect for 64..1M reads per call, L2 hint off/on")
     ap.add_argument("--seeds", action="store_true", help="also time collect + smem_gpu_seeds (section 8f-1: intervals -> mem_seed_t on device)")
@@ -302,14 +302,15 @@ def main():
         for item in args.sweep.split(","):
             f = item.split(":")
             b, hot = f[0], (f[1] if len(f) > 1 and f[1] else "0")
-            g.set_param("reuse", int(f[3]) if len(f) > 3 else 0)
+            g.set_param("reuse", int(f[3]) if len(f) > 3 and f[3] else 0)
+            g.set_param("l2_mode", int(f[4]) if len(f) > 4 else 0)
             g.set_param("blocks_per_sm", int(b)); g.set_param("l2_hot_min_intv", int(hot))
-            g.set_param("b_cap", int(f[2]) if len(f) > 2 else keep[2])
+            g.set_param("b_cap", int(f[2]) if len(f) > 2 and f[2] else keep[2])
             ms = []
             for _ in range(4):
                 g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
-            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} reuse={g.get_param('reuse')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
-        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("reuse", 0)
+            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} reuse={g.get_param('reuse')} l2_mode={g.get_param('l2_mode')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
+        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("reuse", 0); g.set_param("l2_mode", 0)
     for _ in range(max(args.warmup, 3)):
         total = g.run_collect(opt)
     sampler = ClockSampler(local)

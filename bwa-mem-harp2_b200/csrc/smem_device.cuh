@@ -57,7 +57,9 @@ struct SeedParams {
 	int q_stride;            // bytes of shared memory per staged query (two bases per byte)
 	int pair_stride;         // bytes of shared memory per lane pair
 	int split_len_init, split_width, start_width;
-	u64 hot_min_intv;        // 0 = off; L2 evict_last hint for occ blocks of intervals >= this size
+	u64 hot_min_intv;        // 0 = off; occ blocks of intervals >= this size are "hot" (shallow levels, re-used across reads)
+	int l2_mode;             // L2 eviction hints when hot_min_intv != 0: 0 = hot evict_last / cold normal,
+	                         // 1 = hot normal / cold evict_first, 2 = hot evict_last / cold evict_first
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -169,7 +171,7 @@ struct Ext { u64 a, b, s; };   // a = x[!is_back], b = x[is_back], s = x[2]
 // backward sweep consecutive prev[] elements are nested intervals, and the small ones sit in the same 128-row
 // block as their predecessor, so the gather is skipped when the block number repeats (REUSE).
 template <bool REUSE>
-__device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 policy,
+__device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 pol_hot, u64 pol_cold,
                                            u32 (&w)[8], u32 (&v)[8], u64 &last_bk, u64 &last_bl)
 {
 	const u64 k = a - 1, l = a - 1 + s;
@@ -178,7 +180,8 @@ __device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64
 	const bool same = bk == bl;
 	const bool need_k = !REUSE || bk != last_bk, need_l = !same && (!REUSE || bl != last_bl);
 	const uint4 *pk = ix.blk + bk * 4 + half * 2, *pl = ix.blk + bl * 4 + half * 2;
-	if (hot_min && s >= hot_min) {
+	if (hot_min) {                       // uniform branch; ONE load site, the policy is a per-lane operand
+		const u64 policy = s >= hot_min ? pol_hot : pol_cold;
 		if (need_k) ld_sector_hot(w, pk, policy);
 		if (need_l) ld_sector_hot(v, pl, policy);
 	} else {

@@ -93,6 +93,7 @@ struct smem_gpu {
 	bool ran = false;
 	int block_threads = SEED_BLOCK, blocks_per_sm = 9, slot_cap = 128, b_cap = 17;
 	int64_t hot_min_intv = 0;
+	int l2_mode = 0;                 // see SeedParams::l2_mode
 	int probe_variant = 0;
 	int force_wide = 0;
 	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
@@ -497,6 +498,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		p.split_width = opt->split_width; p.start_width = opt->start_width;
 	}
 	p.hot_min_intv = (u64)h.hot_min_intv;
+	p.l2_mode = h.l2_mode;
 
 	turn_acquire(d, h);
 	CK(cudaEventRecord(d.ev0, d.stream));
@@ -1177,6 +1179,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "fast_slots")) { if (v < 16 || v > FAST_MAX_SLOTS) return SMEM_GPU_E_ARG; h->fast_slots = (int)v; return 0; }
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
+	if (!strcmp(name, "l2_mode")) { if (v < 0 || v > 2) return SMEM_GPU_E_ARG; h->l2_mode = (int)v; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
 		if (v != 32 && v != 64 && v != 128) return SMEM_GPU_E_ARG;
@@ -1203,6 +1206,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "has_kmer_tables")) return h->devs[0].has_tables ? 1 : 0;
 	if (!strcmp(name, "escaped_reads")) { int64_t e = 0; for (auto &d : h->devs) e += d.escaped; return e; }
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
+	if (!strcmp(name, "l2_mode")) return h->l2_mode;
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
 	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }
 	if (!strcmp(name, "n_devices")) return (int64_t)h->devs.size();

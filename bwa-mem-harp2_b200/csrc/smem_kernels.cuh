@@ -52,8 +52,13 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	Intv *const M1 = p.scratch + (size_t)gpair * 3 * p.scratch_cap;
 	Intv *const BX = M1 + 2 * p.scratch_cap;
 
-	u64 policy = 0;
-	if (p.hot_min_intv) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+	u64 pol_hot = 0, pol_cold = 0;
+	if (p.hot_min_intv) {
+		if (p.l2_mode == 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_hot));
+		else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
+		if (p.l2_mode == 0) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_cold));
+		else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
+	}
 
 	// B beyond b_cap spills to global memory through an out-of-line slow path: one compare + a branch that is
 	// (almost) never taken on the hot path, and correctness never depends on b_cap
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 
 		// ============================================================== one bwt_extend per pair (warp converged)
 		// idle pairs ride along on the interval (1,1,1): its block is hot in L2 and the result is dropped
-		const Ext ok = extend_pair<REUSE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, policy, blk_k, blk_l, last_bk, last_bl);
+		const Ext ok = extend_pair<REUSE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, last_bk, last_bl);
 		if (phase == PH_IDLE) continue;
 		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 

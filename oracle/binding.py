@@ -33,6 +33,22 @@ class Stats(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+SEED_DT = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])     # == mem_seed_t (bwamem.c:316-319)
+
+
+class ChainOpt(C.Structure):
+    """Chaining / chain-filter fields of mem_opt_t (bwamem.h:33-60), defaults from mem_opt_init (bwamem.c:45-75)."""
+    _fields_ = [("w", C.c_int), ("max_chain_gap", C.c_int), ("min_seed_len", C.c_int), ("mask_level", C.c_float), ("chain_drop_ratio", C.c_float)]
+
+    def __init__(self, w=100, max_chain_gap=10000, min_seed_len=19, mask_level=0.5, chain_drop_ratio=0.5):
+        super().__init__(w, max_chain_gap, min_seed_len, mask_level, chain_drop_ratio)
+
+
+class _RefChainOpt(C.Structure):
+    _fields_ = [("seed", SeedOpt), ("w", C.c_int), ("max_chain_gap", C.c_int), ("max_occ", C.c_int), ("mask_level", C.c_float),
+                ("chain_drop_ratio", C.c_float)]
+
+
 class _OrcIndex(C.Structure):
     _fields_ = [("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64), ("bwt_size", C.c_uint64),
                 ("bwt", C.c_void_p)]
@@ -150,6 +166,42 @@ class Oracle(_Base):
         self.lib.orc_sa(C.byref(self.ix), C.c_int(int(index.sa_intv)), _p(sa, C.c_uint64), C.c_int64(len(k)), _p(k, C.c_uint64), _p(out, C.c_uint64))
         return out
 
+    def seeds(self, index, intv, read_off, min_seed_len=19, max_occ=10000):
+        """Intervals -> seeds (bwamem.c:462-476); ``index`` carries the SA samples."""
+        intv = np.ascontiguousarray(intv, np.uint64)
+        read_off = np.ascontiguousarray(read_off, np.int64)
+        sa = np.ascontiguousarray(index.sa_numpy(), np.uint64)
+        n = len(read_off) - 1
+        seed_off = np.zeros(n + 1, np.int64)
+        self.lib.orc_seeds.restype = C.c_int64
+        cap = max(64, 4 * n)
+        while True:
+            seeds = np.zeros(cap, SEED_DT)
+            tot = self.lib.orc_seeds(C.byref(self.ix), C.c_int(int(index.sa_intv)), _p(sa, C.c_uint64), C.c_int64(n), _p(intv, C.c_uint64),
+                                     _p(read_off, C.c_int64), C.c_int(min_seed_len), C.c_int64(max_occ), C.c_void_p(seeds.ctypes.data),
+                                     C.c_int64(cap), _p(seed_off, C.c_int64))
+            if tot <= cap:
+                return dict(seeds=seeds[:tot], seed_off=seed_off)
+            cap = int(tot)
+
+    def chains(self, seeds, seed_off, l_pac, copt=None, flt=True):
+        """Seeds -> chains: mem_chain's insertion loop + (flt) mem_chain_flt."""
+        copt = copt or ChainOpt()
+        seeds = np.ascontiguousarray(seeds, SEED_DT)
+        seed_off = np.ascontiguousarray(seed_off, np.int64)
+        n = len(seed_off) - 1
+        self.lib.orc_chains.restype = C.c_int64
+        cap = max(len(seeds), 1)
+        chain_off = np.zeros(n + 1, np.int64)
+        chain = np.zeros((cap, 2), np.int64)
+        out = np.zeros(cap, SEED_DT)
+        ns = C.c_int64(0)
+        nc = self.lib.orc_chains(C.c_int64(n), C.c_void_p(seeds.ctypes.data), _p(seed_off, C.c_int64), C.c_int64(int(l_pac)), C.byref(copt),
+                                 C.c_int(int(flt)), _p(chain_off, C.c_int64), _p(chain, C.c_int64), C.c_int64(cap), C.c_void_p(out.ctypes.data),
+                                 C.c_int64(cap), C.byref(ns))
+        assert nc <= cap and ns.value <= cap
+        return dict(chain_off=chain_off, chain=chain[:nc], seeds=out[:ns.value])
+
     def checksum(self, intv, read_off):
         intv = np.ascontiguousarray(intv, np.uint64)
         read_off = np.ascontiguousarray(read_off, np.int64)
@@ -206,6 +258,33 @@ class Reference(_Base):
         self.lib.ref_sa(self.h, C.c_int64(len(k)), _p(k, C.c_uint64), _p(out, C.c_uint64))
         self.lib.ref_bwt_clear_sa(self.h)
         return out
+
+    def chains(self, index, seq, offs, opt=None, copt=None, max_occ=10000, flt=True):
+        """The reference's own mem_chain (+ mem_chain_flt) per read; ``index`` carries the SA samples."""
+        opt, copt = opt or SeedOpt(), copt or ChainOpt()
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        sa = np.ascontiguousarray(index.sa_numpy(), np.uint64)
+        n = len(offs) - 1
+        ro = _RefChainOpt(opt, copt.w, copt.max_chain_gap, max_occ, copt.mask_level, copt.chain_drop_ratio)
+        ro.seed.min_seed_len = copt.min_seed_len = opt.min_seed_len
+        self.lib.ref_chains.restype = C.c_int64
+        self.lib.ref_bwt_set_sa(self.h, C.c_int(int(index.sa_intv)), C.c_uint64(len(sa)), C.c_void_p(sa.ctypes.data))
+        ccap, scap = max(64, 4 * n), max(64, 8 * n)
+        chain_off = np.zeros(n + 1, np.int64)
+        try:
+            while True:
+                chain = np.zeros((ccap, 2), np.int64)
+                seeds = np.zeros(scap, SEED_DT)
+                ns = C.c_int64(0)
+                nc = self.lib.ref_chains(self.h, C.c_int64(int(index.seq_len) // 2), C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64),
+                                         C.byref(ro), C.c_int(int(flt)), _p(chain_off, C.c_int64), _p(chain, C.c_int64), C.c_int64(ccap),
+                                         C.c_void_p(seeds.ctypes.data), C.c_int64(scap), C.byref(ns))
+                if nc <= ccap and ns.value <= scap:
+                    return dict(chain_off=chain_off, chain=chain[:nc], seeds=seeds[:ns.value])
+                ccap, scap = max(ccap, int(nc)), max(scap, int(ns.value))
+        finally:
+            self.lib.ref_bwt_clear_sa(self.h)
 
     def extend(self, ik3, is_back: int):
         ok = (C.c_uint64 * 12)()

@@ -265,3 +265,51 @@ double ref_time_collect(const void *bwt, int64_t n, const uint8_t *seq, const in
 	free(j.itr); free(j.sum); free(j.cnt);
 	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---------------- chaining: the reference's own mem_chain + mem_chain_flt ---------------- */
+/* Calls mem_chain (bwamem.c:593-615: seeding, bwt_sa, kbtree insertion with test_and_merge bwamem.c:334-356, traversal in
+ * pos order) and optionally mem_chain_flt (bwamem.c:629-700) for every read; `bwt` must carry SA samples
+ * (ref_bwt_set_sa).  Flat result: chain_off int64[n+1] (CSR per read), chain int64[total][2] = {pos, n_seeds},
+ * seeds = mem_seed_t[] {int64 rbeg; int32 qbeg, len} grouped by chain in chain order.  Returns the chain total;
+ * *n_seeds_out = seed total; nothing but chain_off / the totals is complete when a cap is exceeded. */
+typedef struct { int64_t rbeg; int32_t qbeg, len; } h_seed_t;
+typedef struct { int n, m; int64_t pos; h_seed_t *seeds; } h_chain_t;
+typedef struct { size_t n, m; h_chain_t *a; } h_chain_v;
+h_chain_v mem_chain(const mem_opt_t *opt, const bwt_t *bwt, int64_t l_pac, int len, const uint8_t *seq);
+int mem_chain_flt(const mem_opt_t *opt, int n_chn, h_chain_t *chains);
+
+typedef struct {
+	ref_seed_opt_t seed;
+	int w, max_chain_gap, max_occ;
+	float mask_level, chain_drop_ratio;
+} ref_chain_opt_t;
+
+int64_t ref_chains(const void *bwt, int64_t l_pac, int64_t n, const uint8_t *seq, const int64_t *offs, const ref_chain_opt_t *o,
+                   int do_flt, int64_t *chain_off, int64_t *chain, int64_t chain_cap, h_seed_t *seeds, int64_t seed_cap,
+                   int64_t *n_seeds_out)
+{
+	mem_opt_t *opt = mem_opt_init();
+	int64_t i, nc = 0, ns = 0;
+	opt->min_seed_len = o->seed.min_seed_len; opt->split_factor = (float)o->seed.split_factor; opt->split_width = o->seed.split_width;
+	if (o->seed.start_width == 2) opt->flag |= MEM_F_NO_EXACT;
+	opt->w = o->w; opt->max_chain_gap = o->max_chain_gap; opt->max_occ = o->max_occ;
+	opt->mask_level = o->mask_level; opt->chain_drop_ratio = o->chain_drop_ratio;
+	chain_off[0] = 0;
+	for (i = 0; i < n; ++i) {
+		h_chain_v c = mem_chain(opt, (const bwt_t *)bwt, l_pac, (int)(offs[i+1] - offs[i]), seq + offs[i]);
+		size_t k;
+		if (do_flt) c.n = (size_t)mem_chain_flt(opt, (int)c.n, c.a);
+		for (k = 0; k < c.n; ++k) {
+			int t;
+			if (nc < chain_cap) { chain[2*nc] = c.a[k].pos; chain[2*nc+1] = c.a[k].n; }
+			++nc;
+			for (t = 0; t < c.a[k].n; ++t, ++ns) if (ns < seed_cap) seeds[ns] = c.a[k].seeds[t];
+			free(c.a[k].seeds);
+		}
+		free(c.a);
+		chain_off[i+1] = nc;
+	}
+	free(opt);
+	*n_seeds_out = ns;
+	return nc;
+}

@@ -407,3 +407,229 @@ double orc_time_collect(const orc_index_t *ix, int64_t n, const uint8_t *seq, co
 	free(jobs); free(tid);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------ seeds and chains */
+/* Intervals -> seeds: the seed loop of mem_insert_seed (bwamem.c:462-476): an interval of seed length >= min_seed_len with
+ * x[2] <= max_occ yields its x[2] seeds {bwt_sa(x[0] + k), qbeg, len}, in interval order then k.  (The forward/reverse
+ * boundary test of bwamem.c:478 belongs to chaining below.) */
+int64_t orc_seeds(const orc_index_t *ix, int sa_intv, const uint64_t *sa, int64_t n, const uint64_t *intv, const int64_t *read_off,
+                  int min_seed_len, int64_t max_occ, orc_seed_t *seeds, int64_t cap, int64_t *seed_off)
+{
+	int64_t r, e, tot = 0;
+	seed_off[0] = 0;
+	for (r = 0; r < n; ++r) {
+		for (e = read_off[r]; e < read_off[r + 1]; ++e) {
+			const uint64_t *p = intv + 4 * e;
+			const int qbeg = (int)(p[3] >> 32), slen = (int)(uint32_t)p[3] - qbeg;
+			uint64_t k;
+			if (slen < min_seed_len || p[2] > (uint64_t)max_occ) continue;
+			for (k = 0; k < p[2]; ++k, ++tot) {
+				if (tot < cap) {
+					uint64_t row = p[0] + k, pos;
+					orc_sa(ix, sa_intv, sa, 1, &row, &pos);
+					seeds[tot].rbeg = (int64_t)pos; seeds[tot].qbeg = qbeg; seeds[tot].len = slen;
+				}
+			}
+		}
+		seed_off[r + 1] = tot;
+	}
+	return tot;
+}
+
+typedef struct { int n, m; int64_t pos; orc_seed_t *seeds; } ochain_t;
+
+/* test_and_merge, bwamem.c:334-356: 1 = seed absorbed (contained, or appended to the chain), 0 = start a new chain */
+static int chain_absorbs(const orc_chain_opt_t *o, int64_t l_pac, ochain_t *c, const orc_seed_t *p)
+{
+	const orc_seed_t *first = &c->seeds[0], *last = &c->seeds[c->n - 1];
+	const int64_t qend = last->qbeg + last->len, rend = last->rbeg + last->len;
+	int64_t x, y;
+	if (p->qbeg >= first->qbeg && p->qbeg + p->len <= qend && p->rbeg >= first->rbeg && p->rbeg + p->len <= rend) return 1;
+	if ((last->rbeg < l_pac || first->rbeg < l_pac) && p->rbeg >= l_pac) return 0;      /* other strand */
+	x = p->qbeg - last->qbeg;
+	y = p->rbeg - last->rbeg;
+	if (y >= 0 && x - y <= o->w && y - x <= o->w && x - last->len < o->max_chain_gap && y - last->len < o->max_chain_gap) {
+		if (c->n == c->m) { c->m <<= 1; c->seeds = (orc_seed_t *)realloc(c->seeds, (size_t)c->m * sizeof(orc_seed_t)); }
+		c->seeds[c->n++] = *p;
+		return 1;
+	}
+	return 0;
+}
+
+/* mem_chain_weight, bwamem.c:502-521, including its second loop that keeps advancing `end` by QUERY coordinates */
+static int chain_weight(const ochain_t *c)
+{
+	int64_t end = 0;
+	int j, w = 0, tmp;
+	for (j = 0; j < c->n; ++j) {
+		const orc_seed_t *s = &c->seeds[j];
+		if (s->qbeg >= end) w += s->len;
+		else if (s->qbeg + s->len > end) w += (int)(s->qbeg + s->len - end);
+		if (s->qbeg + s->len > end) end = s->qbeg + s->len;
+	}
+	tmp = w;
+	for (j = 0, end = 0; j < c->n; ++j) {
+		const orc_seed_t *s = &c->seeds[j];
+		if (s->rbeg >= end) w += s->len;
+		else if (s->rbeg + s->len > end) w += (int)(s->rbeg + s->len - end);
+		if (s->qbeg + s->len > end) end = s->qbeg + s->len;
+	}
+	return w < tmp ? w : tmp;
+}
+
+typedef struct { int beg, end, w, p, p2; } flt_t;
+#define FLT_LT(a, b) ((a).w > (b).w)      /* bwamem.c:626: heavier chains first */
+
+static void flt_insertsort(flt_t *s, flt_t *t)   /* ksort.h __ks_insertsort: stable */
+{
+	flt_t *i, *j, tmp;
+	for (i = s + 1; i < t; ++i)
+		for (j = i; j > s && FLT_LT(*j, *(j - 1)); --j) { tmp = *j; *j = *(j - 1); *(j - 1) = tmp; }
+}
+
+static void flt_combsort(size_t n, flt_t *a)     /* ksort.h ks_combsort (introsort's depth-limit fallback) */
+{
+	const double shrink = 1.2473309501039786540366528676643;
+	int swapped;
+	size_t gap = n;
+	flt_t tmp, *i, *j;
+	do {
+		if (gap > 2) { gap = (size_t)((double)gap / shrink); if (gap == 9 || gap == 10) gap = 11; }
+		swapped = 0;
+		for (i = a; i < a + n - gap; ++i) {
+			j = i + gap;
+			if (FLT_LT(*j, *i)) { tmp = *i; *i = *j; *j = tmp; swapped = 1; }
+		}
+	} while (swapped || gap > 2);
+	if (gap != 1) flt_insertsort(a, a + n);
+}
+
+/* ks_introsort of ksort.h as instantiated at bwamem.c:627: the order of chains of EQUAL weight is whatever this exact
+ * procedure leaves (median-of-3 quicksort down to runs of <= 16, depth limit 2*ceil(log2 n) with combsort, one final
+ * insertion sort), so it is restated step by step. */
+static void flt_introsort(size_t n, flt_t *a)
+{
+	typedef struct { flt_t *left, *right; int depth; } frame_t;
+	frame_t stack[2 * 8 * sizeof(size_t) + 2], *top = stack;
+	flt_t *s, *t, *i, *j, *k, rp, tmp;
+	int d;
+	if (n < 1) return;
+	if (n == 2) { if (FLT_LT(a[1], a[0])) { tmp = a[0]; a[0] = a[1]; a[1] = tmp; } return; }
+	for (d = 2; (1ul << d) < n; ++d) {}
+	s = a; t = a + (n - 1); d <<= 1;
+	for (;;) {
+		if (s < t) {
+			if (--d == 0) { flt_combsort((size_t)(t - s) + 1, s); t = s; continue; }
+			i = s; j = t; k = i + ((j - i) >> 1) + 1;
+			if (FLT_LT(*k, *i)) { if (FLT_LT(*k, *j)) k = j; }
+			else k = FLT_LT(*j, *i) ? i : j;
+			rp = *k;
+			if (k != t) { tmp = *k; *k = *t; *t = tmp; }
+			for (;;) {
+				do ++i; while (FLT_LT(*i, rp));
+				do --j; while (i <= j && FLT_LT(rp, *j));
+				if (j <= i) break;
+				tmp = *i; *i = *j; *j = tmp;
+			}
+			tmp = *i; *i = *t; *t = tmp;
+			if (i - s > t - i) {
+				if (i - s > 16) { top->left = s; top->right = i - 1; top->depth = d; ++top; }
+				s = t - i > 16 ? i + 1 : t;
+			} else {
+				if (t - i > 16) { top->left = i + 1; top->right = t; top->depth = d; ++top; }
+				t = i - s > 16 ? i - 1 : s;
+			}
+		} else {
+			if (top == stack) { flt_insertsort(a, a + n); return; }
+			--top; s = top->left; t = top->right; d = top->depth;
+		}
+	}
+}
+
+/* mem_chain_flt, bwamem.c:629-700, on chain indices: order[] receives the kept chains in output order; returns how many */
+static int chain_filter(const orc_chain_opt_t *o, int n_chn, const ochain_t *chains, int *order)
+{
+	flt_t *a;
+	char *keep;
+	int i, j, n, n_out = 0;
+	if (n_chn <= 1) { for (i = 0; i < n_chn; ++i) order[i] = i; return n_chn; }
+	a = (flt_t *)malloc(sizeof(flt_t) * (size_t)n_chn);
+	keep = (char *)calloc((size_t)n_chn, 1);
+	for (i = 0; i < n_chn; ++i) {
+		const ochain_t *c = &chains[i];
+		a[i].beg = c->seeds[0].qbeg;
+		a[i].end = c->seeds[c->n - 1].qbeg + c->seeds[c->n - 1].len;
+		a[i].w = chain_weight(c); a[i].p = i; a[i].p2 = -1;
+	}
+	flt_introsort((size_t)n_chn, a);
+	for (i = 0; i < n_chn; ++i) { order[i] = a[i].p; a[i].p = i; }          /* best chain first; p = rank from here on */
+	for (i = 1, n = 1; i < n_chn; ++i) {
+		for (j = 0; j < n; ++j) {
+			const int b_max = a[j].beg > a[i].beg ? a[j].beg : a[i].beg;
+			const int e_min = a[j].end < a[i].end ? a[j].end : a[i].end;
+			if (e_min > b_max) {
+				const int li = a[i].end - a[i].beg, lj = a[j].end - a[j].beg, min_l = li < lj ? li : lj;
+				if (e_min - b_max >= min_l * o->mask_level) {                /* int vs float, as in the reference */
+					if (a[j].p2 < 0) a[j].p2 = a[i].p;
+					if (a[i].w < a[j].w * o->chain_drop_ratio && a[j].w - a[i].w >= o->min_seed_len << 1) break;
+				}
+			}
+		}
+		if (j == n) a[n++] = a[i];
+	}
+	for (i = 0; i < n; ++i) { keep[a[i].p] = 1; if (a[i].p2 >= 0) keep[a[i].p2] = 1; }
+	for (i = 0; i < n_chn; ++i) if (keep[i]) order[n_out++] = order[i];
+	free(a); free(keep);
+	return n_out;
+}
+
+/* mem_chain (bwamem.c:593-615) from the seed loop on (bwamem.c:478-496): per seed, the closest chain at or below its
+ * reference position (kb_intervalp lower bound) absorbs it or a new chain keyed by rbeg is inserted; chains leave in
+ * ascending pos (__kb_traverse).  The kbtree is restated as a sorted array; for EQUAL keys it follows what a kbtree
+ * leaf does (__kb_getp_aux: the FIRST equal key is found; __kb_putp_aux inserts right after it).  Then, optionally,
+ * mem_chain_flt.  Flat result as oracle/ref_harness.c:ref_chains. */
+int64_t orc_chains(int64_t n, const orc_seed_t *seeds, const int64_t *seed_off, int64_t l_pac, const orc_chain_opt_t *o, int do_flt,
+                   int64_t *chain_off, int64_t *chain, int64_t chain_cap, orc_seed_t *out_seeds, int64_t seed_cap, int64_t *n_seeds_out)
+{
+	int64_t r, nc = 0, ns = 0;
+	ochain_t *ch = 0;
+	int *order = 0, cap = 0;
+	chain_off[0] = 0;
+	for (r = 0; r < n; ++r) {
+		int nch = 0, k, n_out;
+		int64_t e;
+		for (e = seed_off[r]; e < seed_off[r + 1]; ++e) {
+			const orc_seed_t *s = &seeds[e];
+			int lo = 0, hi = nch, at;
+			if (s->rbeg < l_pac && l_pac < s->rbeg + s->len) continue;      /* bridges the forward/reverse boundary, bwamem.c:478 */
+			while (lo < hi) { const int mid = (lo + hi) >> 1; if (ch[mid].pos < s->rbeg) lo = mid + 1; else hi = mid; }
+			at = lo;                                                        /* first chain with pos >= rbeg */
+			if (at < nch && ch[at].pos == s->rbeg) { if (chain_absorbs(o, l_pac, &ch[at], s)) continue; ++at; }
+			else if (at > 0 && chain_absorbs(o, l_pac, &ch[at - 1], s)) continue;
+			if (nch == cap) {
+				cap = cap ? cap << 1 : 16;
+				ch = (ochain_t *)realloc(ch, sizeof(ochain_t) * (size_t)cap);
+				order = (int *)realloc(order, sizeof(int) * (size_t)cap);
+			}
+			memmove(&ch[at + 1], &ch[at], sizeof(ochain_t) * (size_t)(nch - at));
+			ch[at].n = 1; ch[at].m = 4; ch[at].pos = s->rbeg;
+			ch[at].seeds = (orc_seed_t *)calloc(4, sizeof(orc_seed_t));
+			ch[at].seeds[0] = *s;
+			++nch;
+		}
+		if (do_flt) n_out = chain_filter(o, nch, ch, order);
+		else for (n_out = 0; n_out < nch; ++n_out) order[n_out] = n_out;
+		for (k = 0; k < n_out; ++k) {
+			const ochain_t *c = &ch[order[k]];
+			int t;
+			if (nc < chain_cap) { chain[2 * nc] = c->pos; chain[2 * nc + 1] = c->n; }
+			++nc;
+			for (t = 0; t < c->n; ++t, ++ns) if (ns < seed_cap) out_seeds[ns] = c->seeds[t];
+		}
+		for (k = 0; k < nch; ++k) free(ch[k].seeds);
+		chain_off[r + 1] = nc;
+	}
+	free(ch); free(order);
+	*n_seeds_out = ns;
+	return nc;
+}

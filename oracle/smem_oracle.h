@@ -57,6 +57,17 @@ double orc_time_collect(const orc_index_t *ix, int64_t n, const uint8_t *seq, co
 uint64_t orc_occ(const orc_index_t *ix, uint64_t k, int c);
 void orc_sa(const orc_index_t *ix, int sa_intv, const uint64_t *sa, int64_t n, const uint64_t *k, uint64_t *out);
 
+/* Seeds and chains.  orc_seed_t == mem_seed_t (bwamem.c:316-319). */
+typedef struct { int64_t rbeg; int32_t qbeg, len; } orc_seed_t;
+/* chaining / chain-filter fields of mem_opt_t (bwamem.h:33-60; defaults w 100, max_chain_gap 10000, 0.5, 0.5) */
+typedef struct { int w, max_chain_gap, min_seed_len; float mask_level, chain_drop_ratio; } orc_chain_opt_t;
+int64_t orc_seeds(const orc_index_t *ix, int sa_intv, const uint64_t *sa, int64_t n, const uint64_t *intv, const int64_t *read_off,
+                  int min_seed_len, int64_t max_occ, orc_seed_t *seeds, int64_t cap, int64_t *seed_off);
+/* mem_chain's insertion loop (bwamem.c:478-496, test_and_merge :334-356) and, if do_flt, mem_chain_flt (bwamem.c:629-700).
+ * chain_off int64[n+1]; chain int64[total][2] = {pos, n_seeds}; out_seeds grouped by chain.  Returns the chain total. */
+int64_t orc_chains(int64_t n, const orc_seed_t *seeds, const int64_t *seed_off, int64_t l_pac, const orc_chain_opt_t *o, int do_flt,
+                   int64_t *chain_off, int64_t *chain, int64_t chain_cap, orc_seed_t *out_seeds, int64_t seed_cap, int64_t *n_seeds_out);
+
 /* Order-independent-across-reads checksum of a flat result (same definition as the timing arms). */
 uint64_t orc_checksum(int64_t n, const uint64_t *intv, const int64_t *read_off);
 

@@ -1,0 +1,75 @@
+"""Seeds -> chains: mem_chain's insertion loop (bwamem.c:478-496, test_and_merge :334-356) and
+mem_chain_flt (bwamem.c:629-700).  CPU: the C restatement vs the reference's own mem_chain / mem_chain_flt on a
+repeat-rich reference; GPU: smem_gpu_chains through the C ABI vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import pkg
+from oracle.binding import ChainOpt, Oracle, Reference, SeedOpt, build_reference
+
+
+def repeat_rich_reference(n_bp, seed):
+    """Random text with dispersed exact / mutated copies of segments and short tandem arrays: many multi-hit seeds, many
+    chains per read, chains of several seeds, equal-weight chains."""
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, 4, n_bp).astype(np.uint8)
+    for _ in range(n_bp // 4000):
+        ln = int(rng.integers(60, 900))
+        src, dst = (int(v) for v in rng.integers(0, n_bp - ln, 2))
+        seg = t[src:src + ln].copy()
+        mut = rng.random(ln) < rng.choice([0.0, 0.01, 0.04])
+        seg[mut] = (seg[mut] + rng.integers(1, 4, int(mut.sum()))) % 4
+        if rng.random() < 0.3:
+            seg = (3 - seg)[::-1]                      # reverse-complement copy
+        t[dst:dst + ln] = seg
+    for _ in range(n_bp // 20000):
+        unit = rng.integers(0, 4, int(rng.integers(2, 40))).astype(np.uint8)
+        reps = int(rng.integers(3, 30))
+        arr = np.tile(unit, reps)[:600]
+        dst = int(rng.integers(0, n_bp - len(arr)))
+        t[dst:dst + len(arr)] = arr
+    return torch.from_numpy(t)
+
+
+@pytest.fixture(scope="module")
+def world_chain(fm, synth):
+    ref = repeat_rich_reference(300_000, 77)
+    ix = fm.build_index(ref, sa_intv=32)
+    sets = {}
+    for name, (n, ln, err, s) in {"r101": (3000, 101, 0.01, 5), "r250": (1200, 250, 0.02, 6)}.items():
+        sets[name] = synth.to_batch(synth.simulate_reads(ref, n, ln, err, seed=s, n_frac=0.04))
+    return ref, ix, Oracle(ix), sets
+
+
+CASES = [("r101", SeedOpt(), ChainOpt(), 10000),
+         ("r250", SeedOpt(), ChainOpt(), 10000),
+         ("r101", SeedOpt(min_seed_len=15, split_factor=1.5, split_width=10), ChainOpt(w=20, max_chain_gap=60, mask_level=0.3, chain_drop_ratio=0.8), 50),
+         ("r250", SeedOpt(start_width=2), ChainOpt(w=5, max_chain_gap=10000), 3)]
+
+
+def oracle_chains(o, ix, seq, offs, opt, copt, max_occ, flt):
+    iv = o.collect(seq, offs, opt, nthreads=4)
+    sd = o.seeds(ix, iv["intv"], iv["read_off"], opt.min_seed_len, max_occ)
+    copt.min_seed_len = opt.min_seed_len
+    return sd, o.chains(sd["seeds"], sd["seed_off"], ix.seq_len // 2, copt, flt)
+
+
+@pytest.mark.skipif(build_reference() is None, reason="reference objects absent")
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_oracle_chains_match_reference(world_chain, case):
+    ref, ix, o, sets = world_chain
+    name, opt, copt, max_occ = CASES[case]
+    seq, offs = sets[name]
+    R = Reference(ix)
+    for flt in (False, True):
+        want = R.chains(ix, seq, offs, opt, copt, max_occ, flt)
+        sd, got = oracle_chains(o, ix, seq, offs, opt, copt, max_occ, flt)
+        assert np.array_equal(got["chain_off"], want["chain_off"])
+        assert np.array_equal(got["chain"], want["chain"])
+        assert np.array_equal(got["seeds"], want["seeds"])
+    # the set exercises what it is meant to: multi-seed chains, several chains per read, dropped chains
+    per_read = np.diff(want["chain_off"])
+    assert want["chain"][:, 1].max() >= 3 and (per_read.max() >= 4 or max_occ < 10)
+    _, unf = oracle_chains(o, ix, seq, offs, opt, copt, max_occ, False)
+    assert len(unf["chain"]) > len(want["chain"])
