@@ -8,6 +8,7 @@
 #include "../../include/smem_gpu.h"
 #include "smem_kernels.cuh"
 #include "smem_fast.cuh"
+#include "smem_chain.cuh"
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -43,6 +44,13 @@ struct DeviceCtx {
 	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
 	int *d_scnt = nullptr; long long *d_soff = nullptr, *d_sroff = nullptr; size_t s_cap = 0, sroff_cap = 0;
 	Seed *d_seeds = nullptr; size_t seeds_cap = 0; long long n_seeds = 0;
+	bool seeds_valid = false;        // d_seeds / d_soff describe the resident intervals (set by smem_gpu_seeds, cleared by a new run)
+	// chaining (section 8f-3): scratch per seed slot, outputs
+	int *d_cwork = nullptr; FltRec *d_flt = nullptr; unsigned char *d_keep = nullptr; size_t cwork_cap = 0;
+	int *d_nch = nullptr, *d_nkept = nullptr; long long *d_coff = nullptr, *d_koff = nullptr; size_t cread_cap = 0;
+	Chain *d_chains = nullptr; Seed *d_cseeds = nullptr; size_t chains_cap = 0;
+	long long n_chains = 0, n_cseeds = 0;
+	float chain_ms = 0;
 	// pipeline lanes
 	int lane = 0, lanes_on_dev = 1;  // pipeline lane of this context on its GPU
 	DeviceCtx *prev_lane = nullptr;  // the lane whose seed kernel runs right before this one's
@@ -187,6 +195,8 @@ void ctx_free(DeviceCtx &d)
 	if (d.owns_tables && d.has_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
 	cudaFree(d.d_esc);
 	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
+	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
+	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
 	cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
 	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_aux); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
@@ -444,6 +454,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 {
 	CK(cudaSetDevice(d.dev));
 	d.mode = mode; d.launches = 0; d.overflow = 0; d.seed_ms = d.total_ms = 0; d.total = 0;
+	d.seeds_valid = false;
 	if (d.n == 0) return 0;
 	if (!d.has_index) { d.err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
 	const int bps = h.blocks_per_sm;
@@ -910,7 +921,8 @@ int ctx_seeds_run(DeviceCtx &d, int min_seed_len, u64 max_occ)
 {
 	CK(cudaSetDevice(d.dev));
 	d.n_seeds = 0;
-	if (d.n == 0) return 0;
+	d.seeds_valid = false;
+	if (d.n == 0) { d.seeds_valid = true; return 0; }
 	if (d.sa_shift < 0) { d.err = "suffix-array samples not uploaded"; return SMEM_GPU_E_NOINDEX; }
 	const long long total = d.total;
 	if ((size_t)total + 1 > d.s_cap) {
@@ -950,6 +962,74 @@ int ctx_seeds_run(DeviceCtx &d, int min_seed_len, u64 max_occ)
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
 	if (d.h_status[2] != 0) { d.err = "suffix-array walk did not terminate (corrupt index?)"; return SMEM_GPU_E_INTERNAL; }
+	d.seeds_valid = true;
+	return 0;
+}
+
+// resident seeds of the last ctx_seeds_run -> chains in HBM (smem_chain.cuh); d.n_chains, d.n_cseeds
+int ctx_chains_run(DeviceCtx &d, const ChainOpt &o)
+{
+	CK(cudaSetDevice(d.dev));
+	d.n_chains = d.n_cseeds = 0; d.chain_ms = 0;
+	if (d.n == 0) return 0;
+	if (!d.seeds_valid) { d.err = "no resident seeds: call smem_gpu_seeds first"; return SMEM_GPU_E_ARG; }
+	const size_t need = (size_t)d.n_seeds + 1;
+	if (need > d.cwork_cap) {
+		cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_chains); cudaFree(d.d_cseeds);
+		d.d_cwork = nullptr; d.d_flt = nullptr; d.d_keep = nullptr; d.d_chains = nullptr; d.d_cseeds = nullptr; d.cwork_cap = 0;
+		const size_t cap = need + need / 8 + 1024;
+		CK(cudaMalloc((void **)&d.d_cwork, cap * 5 * sizeof(int)));
+		CK(cudaMalloc((void **)&d.d_flt, cap * sizeof(FltRec)));
+		CK(cudaMalloc((void **)&d.d_keep, cap));
+		CK(cudaMalloc((void **)&d.d_chains, cap * sizeof(Chain)));       // a chain has at least one seed
+		CK(cudaMalloc((void **)&d.d_cseeds, cap * sizeof(Seed)));
+		d.cwork_cap = cap;
+	}
+	if ((size_t)d.n + 1 > d.cread_cap) {
+		cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
+		d.d_nch = d.d_nkept = nullptr; d.d_coff = d.d_koff = nullptr; d.cread_cap = 0;
+		const size_t cap = (size_t)d.n + 1;
+		CK(cudaMalloc((void **)&d.d_nch, cap * sizeof(int))); CK(cudaMalloc((void **)&d.d_nkept, cap * sizeof(int)));
+		CK(cudaMalloc((void **)&d.d_coff, cap * sizeof(long long))); CK(cudaMalloc((void **)&d.d_koff, cap * sizeof(long long)));
+		d.cread_cap = cap;
+	}
+	ChainWork cw;
+	cw.seeds = d.d_seeds; cw.off = d.d_off; cw.soff = d.d_soff; cw.n = d.n;
+	cw.ord = d.d_cwork; cw.ord2 = cw.ord + d.cwork_cap; cw.c_last = cw.ord2 + d.cwork_cap; cw.c_n = cw.c_last + d.cwork_cap; cw.s_next = cw.c_n + d.cwork_cap;
+	cw.flt = d.d_flt; cw.keep = d.d_keep; cw.n_chains = d.d_nch; cw.n_kept = d.d_nkept;
+	const unsigned grid = (unsigned)(((d.n + 1) * 32 + CHAIN_TPB - 1) / CHAIN_TPB);
+	CK(cudaEventRecord(d.ev0, d.stream));
+	chain_build_kernel<<<grid, CHAIN_TPB, 0, d.stream>>>(cw, o);
+	CK(cudaGetLastError());
+	int rc = run_scan(d, d.d_nch, d.n + 1, d.d_coff);
+	if (rc) return rc;
+	rc = run_scan(d, d.d_nkept, d.n + 1, d.d_koff);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(d.h_status + 8, d.d_coff + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status + 10, d.d_koff + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
+	chain_emit_kernel<<<grid, CHAIN_TPB, 0, d.stream>>>(cw, d.d_coff, d.d_koff, 0, d.d_chains, d.d_cseeds);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(d.ev1, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	memcpy(&d.n_chains, d.h_status + 8, 8);
+	memcpy(&d.n_cseeds, d.h_status + 10, 8);
+	CK(cudaEventElapsedTime(&d.chain_ms, d.ev0, d.ev1));
+	d.launches += 2;
+	return 0;
+}
+
+// chain_off[lo .. hi) (+ chain_base), chains (+ seed_base in seed_first) and their seeds to the caller's arrays
+int ctx_chains_fetch(DeviceCtx &d, smem_chain_t *chains_out, smem_seed_t *seeds_out, int64_t *chain_off, long long chain_base, long long seed_base)
+{
+	CK(cudaSetDevice(d.dev));
+	if (d.n == 0) return 0;
+	std::vector<long long> off((size_t)d.n);
+	CK(cudaMemcpyAsync(off.data(), d.d_coff, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));
+	if (chains_out && d.n_chains) CK(cudaMemcpyAsync(chains_out + chain_base, d.d_chains, (size_t)d.n_chains * sizeof(Chain), cudaMemcpyDeviceToHost, d.stream));
+	if (seeds_out && d.n_cseeds) CK(cudaMemcpyAsync(seeds_out + seed_base, d.d_cseeds, (size_t)d.n_cseeds * sizeof(Seed), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaStreamSynchronize(d.stream));
+	for (int64_t i = 0; i < d.n; ++i) chain_off[d.lo + i] = off[(size_t)i] + chain_base;
+	if (chains_out && seed_base) for (long long k = 0; k < d.n_chains; ++k) chains_out[chain_base + k].seed_first += seed_base;
 	return 0;
 }
 
@@ -1098,6 +1178,33 @@ int smem_gpu_seeds(smem_gpu_t *h, int min_seed_len, int64_t max_occ, smem_seed_t
 	if (rc) return rc;
 	seed_off[h->staged] = tot;
 	if (!fits) { h->err = "seeds_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	return 0;
+}
+
+int smem_gpu_chains(smem_gpu_t *h, const smem_chain_opt_t *opt, int64_t l_pac, smem_chain_t *chains_out, int64_t chains_cap,
+                    smem_seed_t *seeds_out, int64_t seeds_cap, int64_t *chain_off, int64_t *n_chains_out, int64_t *n_seeds_out)
+{
+	if (!h || !opt || !chain_off || l_pac < 0) return SMEM_GPU_E_ARG;
+	if (!h->ran || h->staged < 0) { h->err = "no resident results: run smem_gpu_collect and smem_gpu_seeds first"; return SMEM_GPU_E_ARG; }
+	static_assert(sizeof(Chain) == sizeof(smem_chain_t), "chain layout");
+	ChainOpt o;
+	o.w = opt->w; o.max_chain_gap = opt->max_chain_gap; o.min_seed_len = opt->min_seed_len;
+	o.mask_level = opt->mask_level; o.chain_drop_ratio = opt->chain_drop_ratio; o.l_pac = l_pac; o.do_flt = opt->filter != 0;
+	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_chains_run(d, o); });
+	if (rc) return rc;
+	long long tc = 0, ts = 0;
+	std::vector<long long> cb(h->devs.size()), sb(h->devs.size());
+	for (size_t k = 0; k < h->devs.size(); ++k) { cb[k] = tc; sb[k] = ts; tc += h->devs[k].n_chains; ts += h->devs[k].n_cseeds; }
+	if (n_chains_out) *n_chains_out = tc;
+	if (n_seeds_out) *n_seeds_out = ts;
+	const bool fits = tc <= chains_cap && ts <= seeds_cap && (chains_out || tc == 0) && (seeds_out || ts == 0);
+	rc = for_each_device(h, [&](DeviceCtx &d) {
+		const size_t k = (size_t)(&d - &h->devs[0]);
+		return ctx_chains_fetch(d, fits ? chains_out : nullptr, fits ? seeds_out : nullptr, chain_off, cb[k], sb[k]);
+	});
+	if (rc) return rc;
+	chain_off[h->staged] = tc;
+	if (!fits) { h->err = "chains_cap / seeds_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
 	return 0;
 }
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_kmer_tables", "smem_gpu_get_kmer_table", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_chains", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_kmer_tables", "smem_gpu_get_kmer_table", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -52,6 +52,12 @@ class SmemGpuError(RuntimeError):
     def __init__(self, code, what, detail=""):
         super().__init__(f"smem_gpu: {what} ({code}){': ' + detail if detail else ''}")
         self.code = code
+
+
+class ChainOpt(C.Structure):
+    """smem_chain_opt_t: chaining fields of mem_opt_t (bwamem.h:33-60), defaults from mem_opt_init (bwamem.c:45-75)."""
+    _fields_ = [("w", C.c_int), ("max_chain_gap", C.c_int), ("min_seed_len", C.c_int), ("mask_level", C.c_float),
+                ("chain_drop_ratio", C.c_float), ("filter", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -241,6 +247,31 @@ class SmemGpu:
                 continue
             self._check(rc)
             return dict(seeds=out[:int(tot.value)], seed_off=seed_off)
+
+    CHAIN_DTYPE = np.dtype([("pos", np.int64), ("seed_first", np.int64), ("n_seeds", np.int32), ("weight", np.int32)])
+
+    def chains(self, n_reads: int, l_pac: int, w=100, max_chain_gap=10000, min_seed_len=19, mask_level=0.5, chain_drop_ratio=0.5,
+               flt=True, fetch=True):
+        """mem_chain [+ mem_chain_flt] (bwamem.c:593, 629) on the resident seeds of the last :meth:`seeds` call."""
+        opt = ChainOpt(w, max_chain_gap, min_seed_len, mask_level, chain_drop_ratio, int(flt))
+        chain_off = np.zeros(n_reads + 1, np.int64)
+        nc, ns = C.c_int64(0), C.c_int64(0)
+        ccap = scap = 0
+        chains = seeds = None
+        while True:
+            rc = self.lib.smem_gpu_chains(self.h, C.byref(opt), C.c_int64(int(l_pac)), C.c_void_p(chains.ctypes.data) if chains is not None else None,
+                                          C.c_int64(ccap), C.c_void_p(seeds.ctypes.data) if seeds is not None else None, C.c_int64(scap),
+                                          _p(chain_off, C.c_int64), C.byref(nc), C.byref(ns))
+            if rc == -5 and fetch and (nc.value > ccap or ns.value > scap):
+                ccap, scap = max(int(nc.value), 1), max(int(ns.value), 1)
+                chains, seeds = np.zeros(ccap, self.CHAIN_DTYPE), np.zeros(scap, self.SEED_DTYPE)
+                continue
+            if rc == -5 and not fetch:
+                return dict(chain_off=chain_off, n_chains=int(nc.value), n_seeds=int(ns.value))
+            self._check(rc)
+            if chains is None:
+                chains, seeds = np.zeros(0, self.CHAIN_DTYPE), np.zeros(0, self.SEED_DTYPE)
+            return dict(chain_off=chain_off, chains=chains[:int(nc.value)], seeds=seeds[:int(ns.value)])
 
     # -- one-call forms (host buffers in, host buffers out)
     def collect(self, seq, offs, opt: "SeedOpt | None" = None, want_step=True, cap_hint: "int | None" = None):

@@ -142,6 +142,28 @@ typedef struct { int64_t rbeg; int32_t qbeg, len; } smem_seed_t;
 int smem_gpu_seeds(smem_gpu_t *h, int min_seed_len, int64_t max_occ, smem_seed_t *seeds_out, int64_t seeds_cap,
                    int64_t *seed_off, int64_t *total_out);
 
+/* Seeds -> chains (the consumer of the seeds), on the seeds of the last smem_gpu_seeds call that are
+ * still resident in HBM.  Per read: the seed loop of mem_insert_seed from the boundary test on (bwamem.c:478-496) -- a seed
+ * bridging the forward/reverse boundary at l_pac is skipped, the closest chain at or below its reference position
+ * (kb_intervalp on the kbtree of mem_chain_t keyed by pos, bwamem.c:483) absorbs it through test_and_merge
+ * (bwamem.c:334-356) or it starts a new chain -- and the chains in ascending pos (__kb_traverse, bwamem.c:608-610); with
+ * `filter` != 0 then mem_chain_flt (bwamem.c:629-700): chains ordered by mem_chain_weight (bwamem.c:502-521) with the tie
+ * order of ks_introsort, shadowed light chains dropped.  == mem_chain (bwamem.c:593) [+ mem_chain_flt] per read.
+ * smem_chain_t mirrors mem_chain_t (bwamem.c:321-325) without the pointer: seeds of chain c are
+ * seeds_out[c.seed_first .. c.seed_first + c.n_seeds), in the chain's insertion order; chain_off = int64[n_reads + 1], CSR
+ * per read.  Chains whose keys are EQUAL follow a kbtree leaf (first equal key found, new key right after it).
+ * On SMEM_GPU_E_CAPACITY chain_off and the two totals are valid. */
+typedef struct { int64_t pos; int64_t seed_first; int32_t n_seeds; int32_t weight; } smem_chain_t;
+/* chaining fields of mem_opt_t (bwamem.h:33-60); defaults mem_opt_init (bwamem.c:45-75): w 100, max_chain_gap 10000,
+ * min_seed_len 19, mask_level 0.5, chain_drop_ratio 0.5. */
+typedef struct {
+	int w, max_chain_gap, min_seed_len;
+	float mask_level, chain_drop_ratio;
+	int filter;
+} smem_chain_opt_t;
+int smem_gpu_chains(smem_gpu_t *h, const smem_chain_opt_t *opt, int64_t l_pac, smem_chain_t *chains_out, int64_t chains_cap,
+                    smem_seed_t *seeds_out, int64_t seeds_cap, int64_t *chain_off, int64_t *n_chains_out, int64_t *n_seeds_out);
+
 /* Split form of smem_gpu_collect, so that seeding can be timed with inputs resident in HBM:
  * stage (H2D) -> run (kernels only, may be repeated) -> fetch (D2H). */
 int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs);

@@ -73,3 +73,61 @@ def test_oracle_chains_match_reference(world_chain, case):
     assert want["chain"][:, 1].max() >= 3 and (per_read.max() >= 4 or max_occ < 10)
     _, unf = oracle_chains(o, ix, seq, offs, opt, copt, max_occ, False)
     assert len(unf["chain"]) > len(want["chain"])
+
+
+def _weight(seeds):
+    """mem_chain_weight (bwamem.c:502-521): with its second loop as written the result is the query coverage."""
+    end = w = 0
+    for s in seeds:
+        q, ln = int(s["qbeg"]), int(s["len"])
+        w += ln if q >= end else max(q + ln - end, 0)
+        end = max(end, q + ln)
+    return w
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_gpu_chains_vs_oracle(world_chain, case):
+    sg = pkg("smem_gpu")
+    ref, ix, o, sets = world_chain
+    name, opt, copt, max_occ = CASES[case]
+    seq, offs = sets[name]
+    n = len(offs) - 1
+    for devices in ([0], [0, 0, 0]):
+        g = sg.SmemGpu(max_batch_reads=4096, max_read_len=256, devices=devices)
+        g.upload_index(ix); g.upload_sa(ix)
+        g.collect(seq, offs, sg.SeedOpt(opt.min_seed_len, opt.split_factor, opt.split_width, opt.start_width))
+        sd_gpu = g.seeds(n, opt.min_seed_len, max_occ)
+        for flt in (False, True):
+            sd, want = oracle_chains(o, ix, seq, offs, opt, copt, max_occ, flt)
+            assert np.array_equal(sd_gpu["seeds"], sd["seeds"])
+            got = g.chains(n, ix.seq_len // 2, copt.w, copt.max_chain_gap, opt.min_seed_len, copt.mask_level, copt.chain_drop_ratio, flt)
+            assert np.array_equal(got["chain_off"], want["chain_off"])
+            assert np.array_equal(got["chains"]["pos"], want["chain"][:, 0])
+            assert np.array_equal(got["chains"]["n_seeds"], want["chain"][:, 1])
+            assert np.array_equal(got["seeds"], want["seeds"])
+            first = np.concatenate([[0], np.cumsum(want["chain"][:, 1])[:-1]]) if len(want["chain"]) else np.zeros(0, np.int64)
+            assert np.array_equal(got["chains"]["seed_first"], first)
+            for c in got["chains"][:: max(1, len(got["chains"]) // 300)]:
+                assert int(c["weight"]) == _weight(got["seeds"][int(c["seed_first"]): int(c["seed_first"]) + int(c["n_seeds"])])
+        # capacity protocol: totals and chain_off without buffers
+        head = g.chains(n, ix.seq_len // 2, flt=True, fetch=False)
+        assert head["n_chains"] == head["chain_off"][-1] and head["n_seeds"] >= head["n_chains"]
+        g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_chains_need_seeds_and_handle_empty(world_chain, synth):
+    sg = pkg("smem_gpu")
+    ref, ix, o, sets = world_chain
+    g = sg.SmemGpu(max_batch_reads=1024, max_read_len=256)
+    g.upload_index(ix); g.upload_sa(ix)
+    seq, offs = synth.to_batch([np.zeros(0, np.uint8), np.full(30, 4, np.uint8), ref.numpy()[1000:1012], ref.numpy()[5000:5101]])
+    g.collect(seq, offs)
+    with pytest.raises(sg.SmemGpuError):
+        g.chains(4, ix.seq_len // 2)                 # seeds of this run not computed yet
+    g.seeds(4)
+    got = g.chains(4, ix.seq_len // 2)
+    assert list(np.diff(got["chain_off"])[:3]) == [0, 0, 0] and got["chain_off"][-1] >= 1
+    assert (got["chains"]["pos"] == 5000).any() or len(got["chains"]) > 1
+    g.close()
