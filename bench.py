@@ -421,6 +421,36 @@ def main():
         seeds_leg = {"value": world * n * args.steps / dts, "unit": "reads/s", "ms_per_step": dts / args.steps * 1e3, "seeds_per_step_per_gpu": n_seeds,
                      "d2h_bytes_per_step": n_seeds * 16 + (n + 1) * 8, "note": "host reads in -> mem_seed_t {rbeg,qbeg,len} out (min_seed_len 19, max_occ 10000)"}
         log("seeds leg:", seeds_leg)
+        # ---- section 8f-3: ... -> seeds -> chains (+ mem_chain_flt) on the device, D2H of chains and their seeds
+        chain_off = sg.PinnedArray(lib, (n + 1,), np.int64)
+        pchains = sg.PinnedArray(lib, (4 * n, 3), np.int64)
+        pcseeds = sg.PinnedArray(lib, (8 * n, 2), np.int64)
+        copt = sg.ChainOpt(100, 10000, 19, 0.5, 0.5, 1)
+        def chains_step():
+            g.stage(pseq.array, poffs.array)
+            g.run_collect(opt)
+            tot, nc, ns = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            rc = lib.smem_gpu_seeds(g.h, C.c_int(19), C.c_int64(10000), None, C.c_int64(0), seed_off.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(tot))
+            assert rc in (0, -5), (rc, lib.smem_gpu_last_error(g.h))          # seeds stay in HBM: only their count comes back
+            rc = lib.smem_gpu_chains(g.h, C.byref(copt), C.c_int64(int(ix.seq_len) // 2), C.c_void_p(pchains.array.ctypes.data), C.c_int64(pchains.array.shape[0]),
+                                     C.c_void_p(pcseeds.array.ctypes.data), C.c_int64(pcseeds.array.shape[0]),
+                                     chain_off.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nc), C.byref(ns))
+            assert rc == 0, (rc, lib.smem_gpu_last_error(g.h))
+            return int(nc.value), int(ns.value)
+        for _ in range(2):
+            chains_step()
+        sync()
+        ts = time.perf_counter()
+        for _ in range(args.steps):
+            n_chains, n_cseeds = chains_step()
+        sync()
+        dts = time.perf_counter() - ts
+        chains_leg = {"value": world * n * args.steps / dts, "unit": "reads/s", "ms_per_step": dts / args.steps * 1e3, "chains_per_step_per_gpu": n_chains,
+                      "chain_seeds_per_step_per_gpu": n_cseeds, "chain_kernels_ms": g.get_param("chain_kernels_us") / 1e3,
+                      "d2h_bytes_per_step": n_chains * 24 + n_cseeds * 16 + (n + 1) * 16,
+                      "note": "host reads in -> mem_chain_t after mem_chain_flt out (w 100, max_chain_gap 10000, mask_level 0.5, chain_drop_ratio 0.5)"}
+        log("chains leg:", chains_leg)
+        seeds_leg["chains"] = chains_leg
 
     # ---- optional: every interval of the step against the oracle (BASELINE config 2)
     if args.full_compare and rank == 0:

@@ -1314,6 +1314,8 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "escaped_reads")) { int64_t e = 0; for (auto &d : h->devs) e += d.escaped; return e; }
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "l2_mode")) return h->l2_mode;
+	if (!strcmp(name, "chain_kernels_us")) { float m = 0; for (auto &d : h->devs) m = std::max(m, d.chain_ms); return (int64_t)(m * 1000.0f); }
+	if (!strcmp(name, "n_chains")) { int64_t t = 0; for (auto &d : h->devs) t += d.n_chains; return t; }
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
 	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }
 	if (!strcmp(name, "n_devices")) return (int64_t)h->devs.size();
