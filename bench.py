@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--direct-levels", type=int, default=-1, help="depth of the direct k-mer tables (pyramid reaches +5); -1 = from the text length")
     ap.add_argument("--fast-blocks-per-sm", type=int, default=0)
     ap.add_argument("--fast-slots", type=int, default=0)
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="smem_gpu_set_param on the device-resident handle (repeatable)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap[:reuse[:l2_mode]]]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
@@ -223,6 +224,9 @@ def main():
     g = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local])
     if args.blocks_per_sm:
         g.set_param("blocks_per_sm", args.blocks_per_sm)
+    for kv in args.set:
+        k, v = kv.split("=")
+        g.set_param(k, int(v))
     if args.l2_hot_min_intv >= 0:
         g.set_param("l2_hot_min_intv", args.l2_hot_min_intv)
     g.upload_index(ix)                      # device -> device copy of the packed bwt_t into the library's HBM buffer

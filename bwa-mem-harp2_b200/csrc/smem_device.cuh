@@ -42,6 +42,7 @@ struct SeedParams {
 	DevIndex ix;
 	const uint8_t *seq;      // staged reads, one base per byte
 	const long long *offs;   // [n+1]
+	const uint4 *qpack;      // reads re-packed two bases per byte (0..3, else 4; padded with 4), q_stride bytes per read (pack_reads_kernel)
 	long long n;
 	const int *list;         // optional indirection (overflow re-run): read id = list[k]
 	const int *xs, *min_intvs; // smem1 mode inputs

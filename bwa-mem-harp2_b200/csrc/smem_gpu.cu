@@ -61,6 +61,7 @@ struct DeviceCtx {
 	int64_t read_cap = 0;
 	size_t seq_cap = 0;
 	uint8_t *d_seq = nullptr;
+	uint4 *d_qpack = nullptr; size_t qpack_bytes = 0;   // reads re-packed two bases per byte (pack_reads_kernel)
 	long long *d_offs = nullptr;
 	int *d_x = nullptr, *d_mi = nullptr, *d_ret = nullptr;
 	int *d_counts = nullptr, *d_overflow = nullptr, *d_status = nullptr;
@@ -197,7 +198,7 @@ void ctx_free(DeviceCtx &d)
 	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
 	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
 	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
-	cudaFree(d.d_seq); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
+	cudaFree(d.d_seq); cudaFree(d.d_qpack); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
 	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_aux); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
 	if (d.h_status) cudaFreeHost(d.h_status);
@@ -368,6 +369,10 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
 		seed_kernel<MODE, B, WIDE, REUSE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
 	} while (0)
+#ifdef SMEM_QUICK_BUILD          /* development builds (make QUICK=1): one launch-bounds variant only */
+	(void)blocks_per_sm;
+	LAUNCH(9);
+#else
 	switch (blocks_per_sm) {
 	case 4: LAUNCH(4); break;
 	case 5: LAUNCH(5); break;
@@ -384,6 +389,7 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 #endif
 	default: LAUNCH(3); break;
 	}
+#endif
 #undef LAUNCH
 	CK(cudaGetLastError());
 	++d.launches;
@@ -505,14 +511,31 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	p.scratch = d.d_scratch; p.scratch_cap = scratch_cap;
 	p.b_cap = b_cap; p.q_stride = q_stride; p.pair_stride = pair_stride;
 	if (opt) {
-		p.split_len_init = (int)(opt->min_seed_len * opt->split_factor + .499);   // bwamem.c:456, the path's only FP
+		// bwamem.c:456, the path's only FP: mem_opt_t::split_factor is a float, so the product is a float product
+		p.split_len_init = (int)((double)((float)opt->min_seed_len * (float)opt->split_factor) + .499);
 		p.split_width = opt->split_width; p.start_width = opt->start_width;
 	}
 	p.hot_min_intv = (u64)h.hot_min_intv;
 	p.l2_mode = h.l2_mode;
+	{
+		const size_t bytes = (size_t)d.read_cap * q_stride;
+		if (bytes > d.qpack_bytes) {
+			if (d.d_qpack) CK(cudaFree(d.d_qpack));
+			d.d_qpack = nullptr; d.qpack_bytes = 0;
+			CK(cudaMalloc((void **)&d.d_qpack, bytes));
+			d.qpack_bytes = bytes;
+		}
+		p.qpack = d.d_qpack;
+	}
 
 	turn_acquire(d, h);
 	CK(cudaEventRecord(d.ev0, d.stream));
+	{   // reads -> two bases per byte at a fixed stride (the seed kernels stage a read with 16-byte copies)
+		const long long chunks = (long long)d.n * (q_stride >> 4);
+		pack_reads_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, d.stream>>>(p.seq, p.offs, d.n, q_stride >> 4, d.d_qpack);
+		CK(cudaGetLastError());
+		++d.launches;
+	}
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
 	if (d.prev_lane && h.chain_lanes) {
@@ -551,6 +574,9 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		CK(cudaMemsetAsync(d.d_esc, 0, (size_t)d.n * sizeof(int), d.stream));
 #define LAUNCH_F(B) do { CK(cudaFuncSetAttribute(fast_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
 		fast_kernel<B><<<grid_f, FAST_TPB, smem_f, d.stream>>>(fp); } while (0)
+#ifdef SMEM_QUICK_BUILD
+		(void)fb; LAUNCH_F(4);
+#else
 		switch (fb) {
 		case 2: LAUNCH_F(2); break;
 		case 4: LAUNCH_F(4); break;
@@ -559,6 +585,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		case 8: LAUNCH_F(8); break;
 		default: LAUNCH_F(3); break;
 		}
+#endif
 #undef LAUNCH_F
 		CK(cudaGetLastError());
 		const long long threads = (long long)d.n * 8;

@@ -44,13 +44,12 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, half = lane & 1;
 	const int pair = threadIdx.x >> 1;
-	const int gpair = blockIdx.x * (SEED_BLOCK / 2) + pair;
 	const u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;   // this pair's shared memory
 	const u32 sb = sp;                                       // B entries first (16-byte aligned)
 	const u32 sc = sp + (u32)p.b_cap * BE::BYTES;            // cold state
 	const u32 sq = sc + COLD_BYTES;                          // query, two bases per byte
-	Intv *const M1 = p.scratch + (size_t)gpair * 3 * p.scratch_cap;
-	Intv *const BX = M1 + 2 * p.scratch_cap;
+	Intv *const M1s = p.scratch + (size_t)(blockIdx.x * (SEED_BLOCK / 2) + pair) * 3 * p.scratch_cap;
+	auto scratch_base = [&]() -> Intv * { return M1s; };   // (forcing this out of the main loop with volatile reads cost spills: slower)
 
 	u64 pol_hot = 0, pol_cold = 0;
 	if (p.hot_min_intv) {
@@ -64,17 +63,17 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	// (almost) never taken on the hot path, and correctness never depends on b_cap
 	auto b_put = [&](int idx, u64 x0, u64 x1, u64 x2, u32 end) {
 		if (__builtin_expect(idx < p.b_cap, 1)) BE::put(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
-		else bx_put(&BX[idx], x0, x1, x2, end);
+		else bx_put(scratch_base() + 2 * p.scratch_cap + idx, x0, x1, x2, end);
 	};
 	auto b_get = [&](int idx, u64 &x0, u64 &x1, u64 &x2, u32 &end) {
 		if (__builtin_expect(idx < p.b_cap, 1)) BE::get(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
-		else { const Intv t = bx_get(&BX[idx]); x0 = t.x0; x1 = t.x1; x2 = t.x2; end = (u32)t.info; }
+		else { const Intv t = bx_get(scratch_base() + 2 * p.scratch_cap + idx); x0 = t.x0; x1 = t.x1; x2 = t.x2; end = (u32)t.info; }
 	};
 	// bwt.c:815-820: a hit that cannot be extended is recorded unless a longer match already covers it
 	auto emit = [&](u64 x0, u64 x1, u64 x2, u32 end, int st) {
 		const int n_mem = lds_u16(sc + CS_NMEM);
 		if (n_mem == 0 || st < lds_u16(sc + CS_LMS)) {
-			Intv *M = M1 + (size_t)lds_u16(sc + CS_PASS) * p.scratch_cap;
+			Intv *M = scratch_base() + (size_t)lds_u16(sc + CS_PASS) * p.scratch_cap;
 			st_intv(&M[n_mem], x0, x1, x2, (u64)end | ((u64)st << 32));
 			sts_u16(sc + CS_NMEM, n_mem + 1);
 			sts_u16(sc + CS_LMS, st);
@@ -112,11 +111,10 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				if ((long long)rk >= p.n) { if (!half && max_count > 0) atomicMax(&p.status[4], max_count); phase = PH_IDLE; break; }
 				const int rid = p.list ? p.list[rk] : rk;
 				const long long o0 = p.offs[rid];
-				const uint8_t *q = p.seq + o0;
 				len = (int)(p.offs[rid + 1] - o0);
-				for (int t = half; 2 * t < len; t += 2) {                    // stage the query, two bases per byte (0..3, else 4)
-					const u32 b0 = min((u32)q[2 * t], 4u), b1 = 2 * t + 1 < len ? min((u32)q[2 * t + 1], 4u) : 4u;
-					sts_u8(sq + t, b0 | (b1 << 4));
+				{                                                            // staged by pack_reads_kernel: 16 bytes (32 bases) per copy
+					const uint4 *src = p.qpack + (size_t)rid * (size_t)(p.q_stride >> 4);
+					for (int t = half; 32 * t < len; t += 2) sts_v4(sq + 16 * t, __ldg(src + t));
 				}
 				__syncwarp(3u << (lane & ~1));
 				sts_i32(sc + CS_RID, rid); sts_i32(sc + CS_NOUT, 0); sts_u16(sc + CS_START, 0); sts_u16(sc + CS_STEP, 0);
@@ -185,6 +183,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			case PH_CALL_DONE: {
 				const int rk = lds_i32(sc + CS_RK), n_mem = lds_u16(sc + CS_NMEM);
 				Intv *const slot = p.slots + (size_t)rk * p.slot_cap;
+				const Intv *const M1 = scratch_base();
 				const Intv *const M2 = M1 + p.scratch_cap;
 				if (MODE == MODE_SMEM1) {
 					const int rid = lds_i32(sc + CS_RID);
@@ -317,6 +316,33 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			b_get(n0 - 1 - j, a, b, s, end);
 		}
 	}
+}
+
+// Reads (one base per byte, as the caller hands them over) -> two bases per byte at a fixed stride, so that a lane pair
+// stages its next read with a few 16-byte copies instead of a byte loop inside the divergent cold section.
+// One thread per 16-byte chunk (32 bases).
+__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t *__restrict__ seq, const long long *__restrict__ offs, long long n,
+                                                         int chunks_per_read, uint4 *__restrict__ qpack)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long r = t / chunks_per_read;
+	if (r >= n) return;
+	const int ch = (int)(t % chunks_per_read);
+	const long long o0 = offs[r];
+	const int len = (int)(offs[r + 1] - o0), base = 32 * ch;
+	u32 w[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		u32 v = 0;
+#pragma unroll
+		for (int b = 0; b < 8; ++b) {
+			const int pos = base + 8 * k + b;
+			const u32 c = pos < len ? min((u32)seq[o0 + pos], 4u) : 4u;
+			v |= c << (4 * b);
+		}
+		w[k] = v;
+	}
+	qpack[t] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // counts of the re-run (list order) -> counts[read id]

@@ -121,7 +121,7 @@ static void collect_one(smem_i *itr, const uint8_t *q, int len, const ref_seed_o
                         flat_t *out, int64_t *cnt, int32_t *n_steps, int32_t *last_start)
 {
 	const bwtintv_v *a;
-	int split_len = (int)(o->min_seed_len * o->split_factor + .499);
+	int split_len = (int)(o->min_seed_len * (float)o->split_factor + .499);   /* float product as with mem_opt_t (bwamem.c:456) */
 	int step = 0;
 	int64_t n0 = out->n;
 	split_len = split_len < len ? split_len : len;
@@ -228,7 +228,7 @@ static void time_worker(void *data, int ci, int tid)
 	for (i = lo; i < hi; ++i) {
 		const bwtintv_v *a;
 		int len = (int)(j->offs[i+1] - j->offs[i]);
-		int split_len = (int)(j->opt.min_seed_len * j->opt.split_factor + .499);
+		int split_len = (int)(j->opt.min_seed_len * (float)j->opt.split_factor + .499);
 		uint64_t h = FNV_BASIS ^ (uint64_t)i;
 		split_len = split_len < len ? split_len : len;
 		smem_set_query(itr, len, j->seq + j->offs[i]);

@@ -180,7 +180,8 @@ typedef void (*emit_fn)(void *ctx, const iv_t *e, int step);
 static void collect_read(const orc_index_t *ix, int len, const uint8_t *q, const orc_seed_opt_t *o, scratch_t *s,
                          orc_stats_t *st, emit_fn emit, void *ctx, int32_t *n_steps, int32_t *last_start)
 {
-	int split_len = (int)(o->min_seed_len * o->split_factor + .499), start = 0, step = 0, i;
+	/* mem_opt_t::split_factor is a float (bwamem.h:47): float product, then the double addition of bwamem.c:456 */
+	int split_len = (int)((double)((float)o->min_seed_len * (float)o->split_factor) + .499), start = 0, step = 0, i;
 	if (split_len > len) split_len = len;
 	while (next2(ix, len, q, &start, split_len, o->split_width, o->start_width, s, st)) {
 		for (i = 0; i < s->mem.n; ++i) emit(ctx, &s->mem.a[i], step);
