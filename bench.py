@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--fast-blocks-per-sm", type=int, default=0)
     ap.add_argument("--fast-slots", type=int, default=0)
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="smem_gpu_set_param on the device-resident handle (repeatable)")
+    ap.add_argument("--no-repeat-filter", action="store_true", help="do not build / use the repeat filter of the re-seeding pass (DESIGN.md section 10)")
+    ap.add_argument("--rf-kmer", type=int, default=0)
+    ap.add_argument("--rf-log2-bits", type=int, default=0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap[:reuse[:l2_mode]]]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
@@ -129,7 +132,7 @@ def make_workload(args, rank, device):
     reads = sy.simulate_reads(fwd, args.reads, args.read_len, args.err, seed=1000 + rank, paired=True)
     seq, offs = sy.to_batch(reads)
     sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
-    pac = sg.pack_pac(fwd) if args.fast else None          # the reference's .pac layout of the forward text
+    pac = sg.pack_pac(fwd) if (args.fast or not args.no_repeat_filter) else None          # the reference's .pac layout of the forward text
     del fwd, reads
     torch.cuda.empty_cache()
     return ix, seq, offs, t_index, pac
@@ -232,7 +235,15 @@ def main():
     g.upload_index(ix)                      # device -> device copy of the packed bwt_t into the library's HBM buffer
     lib = g.lib
     fast_info = None
-    if pac is not None:
+    rf_info = None
+    if pac is not None and not args.no_repeat_filter:
+        torch.cuda.synchronize()
+        tb0 = time.time()
+        g.build_repeat_filter((pac, args.ref_bp), args.rf_kmer, args.rf_log2_bits)
+        rf_info = {"kmer": g.get_param("rf_kmer"), "log2_bits": g.get_param("rf_log2_bits"), "bytes": 1 << (g.get_param("rf_log2_bits") - 3),
+                   "build_s": round(time.time() - tb0, 3)}
+        log("repeat filter:", rf_info)
+    if pac is not None and args.fast:
         import ctypes as C
         DL = args.direct_levels
         if DL < 0:
@@ -250,8 +261,8 @@ def main():
         if args.fast_slots:
             g.set_param("fast_slots", args.fast_slots)
         log("k-mer count pyramid:", fast_info)
-        del pac
-        torch.cuda.empty_cache()
+    pac = None
+    torch.cuda.empty_cache()
     # pinned host batch + pinned result buffers for the end-to-end leg
     pseq = sg.PinnedArray(lib, (len(seq),), np.uint8); pseq.array[:] = seq
     poffs = sg.PinnedArray(lib, (n + 1,), np.int64); poffs.array[:] = offs
@@ -330,6 +341,10 @@ def main():
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     overflow = g.timing()["overflow_reads"]
+    if rf_info:                                          # untimed: how many re-seeding passes the filter proved void
+        g.set_param("count_skips", 1); g.run_collect(opt)
+        rf_info["pass2_skipped_per_step"] = g.get_param("pass2_skipped")
+        g.set_param("count_skips", 0)
 
     # ---- end-to-end leg: host buffers in, host buffers out, copies inside the timed region.  The public call is
     # smem_gpu_collect on a handle with `--lanes` pipeline lanes on this GPU (shards overlap H2D / kernels / D2H).
@@ -554,6 +569,7 @@ def main():
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "intervals_per_step_per_gpu": int(total), "overflow_reads": int(overflow), "index_build_s": t_index,
             "blocks_per_sm": g.get_param("blocks_per_sm"), "l2_hot_min_intv": g.get_param("l2_hot_min_intv"),
+            "repeat_filter": rf_info,
             "fast_path": dict(fast_info, escaped_reads_per_step=int(escaped), blocks_per_sm=g.get_param("fast_blocks_per_sm")) if fast_info else None,
             "device_ms_per_step": float(np.mean(dev_ms)),
         }

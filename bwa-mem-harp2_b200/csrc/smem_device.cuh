@@ -58,6 +58,10 @@ struct SeedParams {
 	int q_stride;            // bytes of shared memory per staged query (two bases per byte)
 	int pair_stride;         // bytes of shared memory per lane pair
 	int split_len_init, split_width, start_width;
+	// repeat filter (smem_repeat.cuh): bit hash(w) is set for every rf_k-mer w that occurs more than once in the indexed text
+	const u32 *qflags;       // per read, per 32 window starts: bit set = that rf_k-mer window is not vouched for (pack_reads_kernel); nullptr = no filter
+	int rf_k;                // k-mer length (<= 32)
+	int count_skips;         // debug: status[6] counts the re-seeding passes the filter proved void
 	u64 hot_min_intv;        // 0 = off; occ blocks of intervals >= this size are "hot" (shallow levels, re-used across reads)
 	int l2_mode;             // L2 eviction hints when hot_min_intv != 0: 0 = hot evict_last / cold normal,
 	                         // 1 = hot normal / cold evict_first, 2 = hot evict_last / cold evict_first

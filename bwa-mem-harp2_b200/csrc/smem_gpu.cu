@@ -39,6 +39,9 @@ struct DeviceCtx {
 	FastTables ft{}; bool has_tables = false, owns_tables = true;
 	int *d_esc = nullptr;
 	int64_t escaped = 0;
+	// repeat filter of the re-seeding pass (smem_repeat.cuh)
+	u32 *d_rf = nullptr; bool owns_rf = true; int rf_k = 0, rf_log2 = 0;
+	int64_t pass2_skipped = 0;
 	uint64_t turn_epoch = 0;         // epoch of the last run in which this lane took part in the kernel turn
 	bool holds_turn = false;         // this lane's seed kernel is part of the call that currently owns the GPU's kernel turn
 	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
@@ -103,6 +106,8 @@ struct smem_gpu {
 	int block_threads = SEED_BLOCK, blocks_per_sm = 9, slot_cap = 128, b_cap = 17;
 	int64_t hot_min_intv = 0;
 	int l2_mode = 0;                 // see SeedParams::l2_mode
+	int repeat_filter = 1;           // use the repeat filter (if built) to skip void re-seeding passes in MODE_COLLECT
+	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
 	int probe_variant = 0;
 	int force_wide = 0;
 	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
@@ -195,6 +200,7 @@ void ctx_free(DeviceCtx &d)
 	if (d.owns_sa) cudaFree(d.d_sa);
 	if (d.owns_tables && d.has_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
 	cudaFree(d.d_esc);
+	if (d.owns_rf) cudaFree(d.d_rf);
 	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
 	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
 	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
@@ -319,6 +325,72 @@ int ctx_build_tables(DeviceCtx &d, const uint8_t *pac, int64_t l_pac, int src_de
 	cudaFree(tw); cudaFree(cntK); cudaFree(bsum);
 	d.ft.cnt = cnt; d.ft.cum = cum; d.ft.pyr = pyr; d.ft.top = top; d.ft.DL = DL;
 	d.has_tables = true;
+	return 0;
+}
+
+// Repeat filter (smem_repeat.cuh) from the 2-bit forward text: every K-mer of T = forward + reverse complement goes
+// through an open-addressing table, one hash group per pass so that the table stays small; a K-mer met twice sets its bit.
+int ctx_build_repeat_filter(DeviceCtx &d, const uint8_t *pac, long long l_pac, int src_device, int K, int log2_bits, bool auto_bits)
+{
+	CK(cudaSetDevice(d.dev));
+	if (d.d_rf && d.owns_rf) cudaFree(d.d_rf);
+	d.d_rf = nullptr; d.owns_rf = true; d.rf_k = 0; d.rf_log2 = 0;
+	const long long n = 2 * l_pac;
+	const size_t pac_bytes = (size_t)((l_pac + 3) / 4);
+	uint8_t *d_pac = nullptr;
+	u64 *tw = nullptr, *slots = nullptr;
+	u32 *bits = nullptr, *cur = nullptr, *nxt = nullptr;
+	auto fail = [&](int rc) { cudaFree(d_pac == pac ? nullptr : d_pac); cudaFree(tw); cudaFree(slots); cudaFree(bits); cudaFree(cur); cudaFree(nxt); return rc; };
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); d.err = b_; return fail(e_ == cudaErrorMemoryAllocation ? SMEM_GPU_E_NOMEM : SMEM_GPU_E_CUDA); } } while (0)
+	if (src_device == d.dev) d_pac = const_cast<uint8_t *>(pac);
+	else {
+		CKT(cudaMalloc((void **)&d_pac, pac_bytes));
+		if (src_device < 0) CKT(cudaMemcpyAsync(d_pac, pac, pac_bytes, cudaMemcpyHostToDevice, d.stream));
+		else CKT(cudaMemcpyPeerAsync(d_pac, d.dev, pac, src_device, pac_bytes, d.stream));
+	}
+	const long long n_words = (n + 31) / 32 + 2;
+	int log2_slots = 12;
+	while (log2_slots < 28 && (1ll << log2_slots) < 2 * n) ++log2_slots;          // <= 2 GB of slots
+	const unsigned G = (unsigned)((2 * n + (1ll << log2_slots) - 1) >> log2_slots);  // distinct k-mers per pass <= slots / 2
+	CKT(cudaMalloc((void **)&tw, (size_t)n_words * 8));
+	CKT(cudaMalloc((void **)&slots, (size_t)8 << log2_slots));
+	CKT(cudaMalloc((void **)&bits, (size_t)1 << (log2_bits - 3)));
+	CKT(cudaMemsetAsync(bits, 0, (size_t)1 << (log2_bits - 3), d.stream));
+	pack_text_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, tw, n_words);
+	CKT(cudaGetLastError());
+	for (unsigned g = 0; g < G; ++g) {
+		CKT(cudaMemsetAsync(slots, 0xff, (size_t)8 << log2_slots, d.stream));
+		rf_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(tw, n, K, G, g, slots, log2_slots, bits, log2_bits);
+		CKT(cudaGetLastError());
+	}
+	CKT(cudaStreamSynchronize(d.stream));
+	cudaFree(slots); slots = nullptr;
+	if (auto_bits) {
+		// fold down while the share of set bits stays <= 1/256 (and never below 2^16 bits)
+		cur = bits; bits = nullptr;
+		unsigned long long *d_pop = (unsigned long long *)tw, h_pop = 0;          // (the text words are no longer needed)
+		while (log2_bits > 16) {
+			const long long n_dst = 1ll << (log2_bits - 6);
+			if (!nxt) CKT(cudaMalloc((void **)&nxt, (size_t)n_dst * 4));
+			CKT(cudaMemsetAsync(d_pop, 0, 8, d.stream));
+			rf_fold_kernel<<<(unsigned)((n_dst + 255) / 256), 256, 0, d.stream>>>(cur, nxt, n_dst, d_pop);
+			CKT(cudaMemcpyAsync(&h_pop, d_pop, 8, cudaMemcpyDeviceToHost, d.stream));
+			CKT(cudaStreamSynchronize(d.stream));
+			if (h_pop * 256 > (1ull << (log2_bits - 1))) break;                   // too full: keep `cur`
+			std::swap(cur, nxt);                                                   // nxt now holds the larger table; its buffer is reused
+			--log2_bits;
+		}
+		cudaFree(nxt); nxt = nullptr;
+		// keep only as many bytes as the chosen size needs
+		CKT(cudaMalloc((void **)&bits, (size_t)1 << (log2_bits - 3)));
+		CKT(cudaMemcpyAsync(bits, cur, (size_t)1 << (log2_bits - 3), cudaMemcpyDeviceToDevice, d.stream));
+		CKT(cudaStreamSynchronize(d.stream));
+		cudaFree(cur); cur = nullptr;
+	}
+#undef CKT
+	if (d_pac != pac) cudaFree(d_pac);
+	cudaFree(tw);
+	d.d_rf = bits; d.rf_k = K; d.rf_log2 = log2_bits;
 	return 0;
 }
 
@@ -517,8 +589,10 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	}
 	p.hot_min_intv = (u64)h.hot_min_intv;
 	p.l2_mode = h.l2_mode;
+	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf;
+	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips;
 	{
-		const size_t bytes = (size_t)d.read_cap * q_stride;
+		const size_t bytes_q = (size_t)d.read_cap * q_stride, bytes = bytes_q + (size_t)d.read_cap * (q_stride >> 4) * 4;   // packed reads | window flags
 		if (bytes > d.qpack_bytes) {
 			if (d.d_qpack) CK(cudaFree(d.d_qpack));
 			d.d_qpack = nullptr; d.qpack_bytes = 0;
@@ -526,13 +600,15 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			d.qpack_bytes = bytes;
 		}
 		p.qpack = d.d_qpack;
+		if (use_rf) p.qflags = reinterpret_cast<u32 *>(reinterpret_cast<uint8_t *>(d.d_qpack) + bytes_q);
 	}
 
 	turn_acquire(d, h);
 	CK(cudaEventRecord(d.ev0, d.stream));
 	{   // reads -> two bases per byte at a fixed stride (the seed kernels stage a read with 16-byte copies)
 		const long long chunks = (long long)d.n * (q_stride >> 4);
-		pack_reads_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, d.stream>>>(p.seq, p.offs, d.n, q_stride >> 4, d.d_qpack);
+		pack_reads_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, d.stream>>>(p.seq, p.offs, d.n, q_stride >> 4, d.d_qpack,
+		                                                                          d.d_rf, d.rf_k, d.rf_log2, const_cast<u32 *>(p.qflags));
 		CK(cudaGetLastError());
 		++d.launches;
 	}
@@ -601,12 +677,13 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
 	const auto tt0 = std::chrono::steady_clock::now();
 	auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
-	CK(cudaMemcpyAsync(d.h_status, d.d_status, 6 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 7 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaStreamSynchronize(d.stream));
 	const double t_status = tms();
 	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
 	const int n_over = d.h_status[1];
 	d.overflow = n_over; d.escaped = use_fast ? d.h_status[5] : 0;
+	d.pass2_skipped = d.h_status[6];
 	int big_cap = 0;
 	if (n_over > 0) {
 		// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
@@ -1119,8 +1196,43 @@ int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src)
 		d.d_sa = o->d_sa; d.owns_sa = false; d.sa_shift = o->sa_shift; d.n_sa = o->n_sa;
 		if (d.has_tables && d.owns_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
 		d.ft = o->ft; d.has_tables = o->has_tables; d.owns_tables = false;
+		if (d.d_rf && d.owns_rf) cudaFree(d.d_rf);
+		d.d_rf = o->d_rf; d.owns_rf = false; d.rf_k = o->rf_k; d.rf_log2 = o->rf_log2;
 	}
 	return 0;
+}
+
+int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int kmer_len, int log2_bits)
+{
+	if (!h || !pac || l_pac < 32) return SMEM_GPU_E_ARG;
+	const long long n = 2 * l_pac;
+	int lg = 1;
+	while ((1ll << lg) < n) ++lg;                                  // ceil(log2 n)
+	if (kmer_len <= 0) kmer_len = (lg + 1) / 2 + 5;                // 4^K ~ 1000 x the text length: 22 on a 3.1 Gbp index
+	const bool auto_bits = log2_bits <= 0;                        // fill a table of 8 bits per text position, then fold it down (smem_repeat.cuh)
+	if (auto_bits) log2_bits = std::min(36, std::max(17, lg + 3));
+	if (kmer_len < 8 || kmer_len > 32 || n <= kmer_len || log2_bits < 10 || log2_bits > 40) return SMEM_GPU_E_ARG;
+	int rc = for_each_device(h, [&](DeviceCtx &d) {
+		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
+		return ctx_build_repeat_filter(d, pac, l_pac, src_device, kmer_len, log2_bits, auto_bits);
+	});
+	if (rc) return rc;
+	for (auto &d : h->devs)
+		for (auto &o : h->devs) {
+			if (&o == &d) break;
+			if (o.dev == d.dev) { d.d_rf = o.d_rf; d.owns_rf = false; d.rf_k = o.rf_k; d.rf_log2 = o.rf_log2; break; }
+		}
+	return 0;
+}
+
+int smem_gpu_get_repeat_filter(smem_gpu_t *h, uint32_t *out, int64_t out_words)
+{
+	if (!h || !out) return SMEM_GPU_E_ARG;
+	DeviceCtx &d = h->devs[0];
+	if (!d.d_rf) { h->err = "no repeat filter built"; return SMEM_GPU_E_NOINDEX; }
+	if (out_words != (int64_t)1 << (d.rf_log2 - 5)) return SMEM_GPU_E_ARG;
+	cudaSetDevice(d.dev);
+	return cudaMemcpy(out, d.d_rf, (size_t)out_words * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : SMEM_GPU_E_CUDA;
 }
 
 int smem_gpu_build_kmer_tables(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int direct_levels)
@@ -1314,6 +1426,8 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
 	if (!strcmp(name, "l2_mode")) { if (v < 0 || v > 2) return SMEM_GPU_E_ARG; h->l2_mode = (int)v; return 0; }
+	if (!strcmp(name, "repeat_filter")) { h->repeat_filter = v != 0; return 0; }
+	if (!strcmp(name, "count_skips")) { h->count_skips = v != 0; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
 		if (v != 32 && v != 64 && v != 128) return SMEM_GPU_E_ARG;
@@ -1341,6 +1455,12 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "escaped_reads")) { int64_t e = 0; for (auto &d : h->devs) e += d.escaped; return e; }
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "l2_mode")) return h->l2_mode;
+	if (!strcmp(name, "repeat_filter")) return h->repeat_filter;
+	if (!strcmp(name, "count_skips")) return h->count_skips;
+	if (!strcmp(name, "has_repeat_filter")) return h->devs[0].d_rf ? 1 : 0;
+	if (!strcmp(name, "rf_kmer")) return h->devs[0].rf_k;
+	if (!strcmp(name, "rf_log2_bits")) return h->devs[0].rf_log2;
+	if (!strcmp(name, "pass2_skipped")) { int64_t t = 0; for (auto &d : h->devs) t += d.pass2_skipped; return t; }
 	if (!strcmp(name, "chain_kernels_us")) { float m = 0; for (auto &d : h->devs) m = std::max(m, d.chain_ms); return (int64_t)(m * 1000.0f); }
 	if (!strcmp(name, "n_chains")) { int64_t t = 0; for (auto &d : h->devs) t += d.n_chains; return t; }
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;

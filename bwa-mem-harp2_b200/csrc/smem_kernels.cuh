@@ -1,6 +1,7 @@
 // smem_kernels.cuh -- the seeding kernel and its small companions (sm_100a).
 #pragma once
 #include "smem_device.cuh"
+#include "smem_repeat.cuh"
 
 enum { MODE_COLLECT = 0, MODE_SMEM1 = 1, MODE_TRACE = 2 };   // TRACE: COLLECT's walk, but every bwt_smem1 call's raw list is kept
 // hot phases first: the main loop only ever extends in PH_FWD / PH_BWD
@@ -227,8 +228,16 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				if (lds_u16(sc + CS_PASS) == 0) {
 					const int max_len = lds_u16(sc + CS_MAXLEN), split_len = lds_u16(sc + CS_SPLIT);
 					const u64 max_s = (u64)(u32)lds_i32(sc + CS_MAXS_LO) | ((u64)(u32)lds_i32(sc + CS_MAXS_HI) << 32);
-					// bwamem.c:272: re-seed from the middle of the longest SMEM if it is long and (nearly) unique
-					if (n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width) {
+					// bwamem.c:272: re-seed from the middle of the longest SMEM if it is long and (nearly) unique -- unless the
+					// repeat filter proves that the second pass cannot contribute (smem_repeat.cuh)
+					bool reseed = n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width;
+					if (reseed && p.qflags && (max_len >> 1) >= p.rf_k &&
+					    rf_range_is_clear(p.qflags + (size_t)lds_i32(sc + CS_RID) * (size_t)(p.q_stride >> 4), p.rf_k, len,
+					                      (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1)) {
+						reseed = false;
+						if (p.count_skips && !half) atomicAdd(&p.status[6], 1);
+					}
+					if (reseed) {
 						sts_u16(sc + CS_NM1, n_mem); sts_u16(sc + CS_KEEP, max_len); sts_u16(sc + CS_PASS, 1);
 						sts_u16(sc + CS_X, (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1);
 						min_intv = max_s + 1;
@@ -322,7 +331,8 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 // stages its next read with a few 16-byte copies instead of a byte loop inside the divergent cold section.
 // One thread per 16-byte chunk (32 bases).
 __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t *__restrict__ seq, const long long *__restrict__ offs, long long n,
-                                                         int chunks_per_read, uint4 *__restrict__ qpack)
+                                                         int chunks_per_read, uint4 *__restrict__ qpack,
+                                                         const u32 *__restrict__ rf_bits, int K, int log2_bits, u32 *__restrict__ qflags)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long r = t / chunks_per_read;
@@ -343,6 +353,36 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t *__restri
 		w[k] = v;
 	}
 	qpack[t] = make_uint4(w[0], w[1], w[2], w[3]);
+	if (!qflags) return;
+	// repeat-filter flags of the 32 windows that start in this chunk (smem_repeat.cuh): rolling K-mer code, `amb` = bases
+	// until the most recent ambiguous one leaves the window; eight independent table loads per round
+	u32 flags = 0;
+	u64 code = 0;
+	int amb = 0;
+	const u64 kmask = K == 32 ? ~0ull : (1ull << (2 * K)) - 1;
+	for (int k = 0; k < K - 1; ++k) {
+		const int pos = base + k;
+		const u32 c = pos < len ? (u32)seq[o0 + pos] : 4u;
+		code = ((code << 2) | (c & 3u)) & kmask;
+		amb = c > 3u ? K : max(amb - 1, 0);
+	}
+	for (int a0 = 0; a0 < 32; a0 += 8) {
+		u32 wd[8], sh[8], bad[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int pos = base + a0 + k + K - 1;                 // last base of the window starting at base + a0 + k
+			const u32 c = pos < len ? (u32)seq[o0 + pos] : 4u;
+			code = ((code << 2) | (c & 3u)) & kmask;
+			amb = c > 3u ? K : max(amb - 1, 0);
+			bad[k] = amb > 0;
+			const u64 b = rf_bit_index(code, log2_bits);
+			wd[k] = bad[k] ? 0u : __ldg(rf_bits + (b >> 5));
+			sh[k] = (u32)(b & 31);
+		}
+#pragma unroll
+		for (int k = 0; k < 8; ++k) flags |= (bad[k] | ((wd[k] >> sh[k]) & 1u)) << (a0 + k);
+	}
+	qflags[t] = flags;
 }
 
 // counts of the re-run (list order) -> counts[read id]

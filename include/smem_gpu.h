@@ -99,6 +99,23 @@ int smem_gpu_build_kmer_tables(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac,
 /* Test hook: copy one table to the host.  which: 0 = cnt[level] (uint32), 1 = cum[level] (uint64), 2 = pyr, 3 = top (uint8). */
 int smem_gpu_get_kmer_table(smem_gpu_t *h, int which, int level, void *out, int64_t out_bytes);
 
+/* Repeat filter of the re-seeding pass -- optional accelerator table of smem_gpu_collect.
+ * smem_next2 re-seeds from the middle x of a long, nearly unique SMEM with min_intv >= 2 (bwamem.c:272-278), and the
+ * merge keeps an entry of that pass only if its length is >= max >> 1 (bwamem.c:288,297).  Such an entry is a pattern
+ * through x that occurs at least twice in the indexed text, and it contains a kmer_len-mer window through x; so when
+ * max >> 1 >= kmer_len and every kmer_len-mer window of the read through x occurs at most once in the text, the pass
+ * cannot contribute and is skipped (about a third of all bwt_extend calls of a 101 bp read).  The table holds one bit per
+ * hash value: set <=> some kmer_len-mer with that hash occurs more than once in T = forward + reverse complement; hash
+ * collisions cost a skip, never a wrong one, and results never depend on the table.  Built on every GPU of the handle
+ * from the 2-bit forward text (`pac`, l_pac, src_device as for smem_gpu_build_kmer_tables).  kmer_len 0 = from the text
+ * length (22 on a 3.1 Gbp index; 4^kmer_len ~ 1000 x the text length), log2_bits 0 = the smallest power of two
+ * for which at most 1/256 of the bits are set (found by filling a table of 8 bits per text position and folding it down:
+ * 32-128 MB and L2-friendly on a repeat-poor text, gigabytes on a repeat-rich one).  smem_gpu_smem1 / smem_gpu_trace return raw bwt_smem1 lists and never skip.
+ * "repeat_filter" (smem_gpu_set_param) switches its use off and on; smem_gpu_share_index shares it. */
+int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int kmer_len, int log2_bits);
+/* Test hook: the bit table of device 0 (2^(log2_bits - 5) uint32 words; get_param "rf_kmer" / "rf_log2_bits"). */
+int smem_gpu_get_repeat_filter(smem_gpu_t *h, uint32_t *out, int64_t out_words);
+
 /* Whole-read seeding == the enumeration loop of mem_insert_seed (bwamem.c:453-460):
  * smem_next2 (bwamem.c:244-305: pass 1, 0.7.8 re-seed of the longest SMEM, ordered merge) to
  * exhaustion for every read.  step_out (nullable) receives, per interval, the index of the

@@ -136,6 +136,36 @@ static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int mi
 
 static inline int iv_len(const iv_t *p) { return (int)((uint32_t)p->info - (uint32_t)(p->info >> 32)); }
 
+/* MODEL of the device kernel's re-seeding shortcut, off unless orc_set_skip_kmer(D > 0) -- a test hook
+ * that lets the CPU suite check the argument behind it on real data:
+ *   the re-seeding pass (bwamem.c:272-300) only contributes entries of length >= max>>1 (the KEEP test of the merge), every
+ *   such entry is a pattern through `mid` occurring >= min_intv >= 2 times, and a pattern of length >= D through `mid`
+ *   contains a D-mer window through `mid`; so if max>>1 >= D and every D-mer window of the read through `mid` occurs at most
+ *   once in the text, the pass cannot contribute and smem_next2's result is its pass-1 list.
+ * Window counts here are exact (backward search); the device asks a conservative bit table ("may occur twice"). */
+static int orc_skip_kmer = 0;
+uint64_t orc_pass2_skipped = 0;
+void orc_set_skip_kmer(int D) { orc_skip_kmer = D; orc_pass2_skipped = 0; }
+uint64_t orc_get_pass2_skipped(void) { return orc_pass2_skipped; }
+
+static int pass2_is_void(const orc_index_t *ix, int len, const uint8_t *q, int mid, int max)
+{
+	const int D = orc_skip_kmer;
+	int a, lo, hi, k;
+	if (D <= 0 || (max >> 1) < D || len < D) return 0;
+	lo = mid - D + 1 < 0 ? 0 : mid - D + 1;
+	hi = mid < len - D ? mid : len - D;
+	for (k = lo; k < hi + D; ++k) if (q[k] > 3) return 0;          /* (the device does not bother with ambiguous bases either) */
+	for (a = lo; a <= hi; ++a) {
+		iv_t ik, ok[4];
+		int c = q[a + D - 1];
+		ik.x0 = ix->L2[c] + 1; ik.x2 = ix->L2[c + 1] - ix->L2[c]; ik.x1 = ix->L2[3 - c] + 1; ik.info = 0;
+		for (k = a + D - 2; k >= a && ik.x2 > 0; --k) { extend(ix, &ik, 1, ok, 0); ik = ok[q[k]]; }
+		if (ik.x2 > 1) return 0;
+	}
+	return 1;
+}
+
 /* smem_next2, bwamem.c:244-305.  Returns 0 when exhausted, else 1 with the step's list in s->mem. */
 static int next2(const orc_index_t *ix, int len, const uint8_t *q, int *start, int split_len, int split_width,
                  int start_width, scratch_t *s, orc_stats_t *st)
@@ -156,6 +186,7 @@ static int next2(const orc_index_t *ix, int len, const uint8_t *q, int *start, i
 		const iv_t *p = &s->mem.a[max_i];
 		int j, mid = (int)(((uint32_t)p->info + (uint32_t)(p->info >> 32)) >> 1);
 		ivv_t *a = &s->merged;
+		if (pass2_is_void(ix, len, q, mid, max)) { __sync_fetch_and_add(&orc_pass2_skipped, 1); return 1; }
 		smem1(ix, len, q, mid, (int)(p->x2 + 1), &s->sub, &s->prev, &s->curr, st);
 		a->n = 0;
 		i = j = 0;

@@ -1,0 +1,113 @@
+"""Repeat filter of the re-seeding pass (csrc/smem_repeat.cuh).
+CPU: the rule itself -- "if max>>1 >= K and every K-mer window through the re-seeding position occurs at most once, the
+second pass of smem_next2 contributes nothing" -- modelled in the oracle with exact counts and compared with the unmodified
+algorithm.  GPU: the device table against brute force, and seeding with the filter against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import pkg
+from oracle.binding import Oracle, SeedOpt
+from test_chains import repeat_rich_reference
+
+SETS = [(101, 0.01, SeedOpt()), (250, 0.02, SeedOpt()), (101, 0.03, SeedOpt(min_seed_len=15, split_factor=1.2, split_width=4)),
+        (151, 0.005, SeedOpt(start_width=2))]
+
+
+@pytest.fixture(scope="module")
+def worlds(fm, synth):
+    out = []
+    for name, ref in (("random", synth.make_reference(500_000, 21)), ("repeats", repeat_rich_reference(300_000, 77))):
+        ix = fm.build_index(ref)
+        out.append((name, ref, ix, Oracle(ix)))
+    return out
+
+
+def test_skip_rule_is_exact_on_cpu(worlds, synth):
+    for name, ref, ix, o in worlds:
+        o.lib.orc_get_pass2_skipped.restype = C.c_uint64
+        total_skipped = 0
+        for rl, err, opt in SETS:
+            seq, offs = synth.to_batch(synth.simulate_reads(ref, 1200, rl, err, seed=9, paired=True, n_frac=0.05))
+            o.lib.orc_set_skip_kmer(0)
+            want = o.collect(seq, offs, opt, nthreads=2)
+            for K in (12, 15, 19):
+                o.lib.orc_set_skip_kmer(K)
+                try:
+                    got = o.collect(seq, offs, opt, nthreads=2)
+                    total_skipped += o.lib.orc_get_pass2_skipped()
+                finally:
+                    o.lib.orc_set_skip_kmer(0)
+                for k in ("intv", "read_off", "step"):
+                    assert np.array_equal(got[k], want[k]), (name, rl, K, k)
+        assert total_skipped > 1000          # the rule fires (and is exercised) on these sets
+
+
+def _brute_bits(T, K, log2_bits):
+    n = len(T)
+    codes = np.zeros(n - K + 1, np.uint64)
+    for k in range(K):
+        codes = (codes << np.uint64(2)) | T[k:n - K + 1 + k].astype(np.uint64)
+    u, c = np.unique(codes, return_counts=True)
+    rep = u[c > 1]
+    idx = (rep * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(64 - log2_bits)
+    bits = np.zeros(1 << (log2_bits - 5), np.uint32)
+    np.bitwise_or.at(bits, (idx >> np.uint64(5)).astype(np.int64), (np.uint32(1) << (idx & np.uint64(31)).astype(np.uint32)))
+    return bits, len(rep)
+
+
+@pytest.mark.gpu
+def test_gpu_repeat_filter_table_vs_brute_force(fm):
+    sg = pkg("smem_gpu")
+    for seed, K, lb in ((1, 12, 20), (2, 9, 16), (3, 16, 22)):
+        ref = repeat_rich_reference(120_000, seed)
+        T = fm.text_from_forward(ref).numpy()
+        g = sg.SmemGpu(max_batch_reads=64, max_read_len=128)
+        g.build_repeat_filter(ref, K, lb)
+        assert g.get_param("rf_kmer") == K and g.get_param("rf_log2_bits") == lb
+        want, n_rep = _brute_bits(T, K, lb)
+        assert n_rep > 100
+        assert np.array_equal(g.repeat_filter_bits(), want)
+        # auto-sized: the table folded down from 8 bits per text position == the brute-force table of the size it chose,
+        # and at most 1/256 of its bits are set (or it is as large as it gets)
+        g.build_repeat_filter(ref, K, 0)
+        lb2 = g.get_param("rf_log2_bits")
+        got = g.repeat_filter_bits()
+        assert np.array_equal(got, _brute_bits(T, K, lb2)[0])
+        fill = sum(bin(int(w)).count("1") for w in got) / float(1 << lb2)
+        assert fill <= 1 / 256 or lb2 == 21, (lb2, fill)
+        g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_collect_with_repeat_filter_vs_oracle(worlds, synth):
+    sg = pkg("smem_gpu")
+    for name, ref, ix, o in worlds:
+        for devices in ([0], [0, 0]):
+            g = sg.SmemGpu(max_batch_reads=4096, max_read_len=256, devices=devices)
+            g.upload_index(ix)
+            g.build_repeat_filter(ref, 14, 0 if name == "random" else 24)      # auto-sized / explicit table
+            g.set_param("count_skips", 1)
+            skipped = 0
+            for rl, err, opt in SETS:
+                seq, offs = synth.to_batch(synth.simulate_reads(ref, 3000, rl, err, seed=19, paired=True, n_frac=0.05))
+                want = o.collect(seq, offs, opt, nthreads=4)
+                gopt = sg.SeedOpt(opt.min_seed_len, opt.split_factor, opt.split_width, opt.start_width)
+                got = g.collect(seq, offs, gopt)
+                skipped += g.get_param("pass2_skipped")
+                for k in ("intv", "read_off", "step"):
+                    assert np.array_equal(got[k], want[k]), (name, rl, k)
+                g.set_param("repeat_filter", 0)               # and the same answer with the filter switched off
+                off = g.collect(seq, offs, gopt)
+                assert g.get_param("pass2_skipped") == 0
+                g.set_param("repeat_filter", 1)
+                assert np.array_equal(off["intv"], want["intv"])
+                # raw bwt_smem1 lists are never shortened by the filter
+                tr = g.trace(seq[: offs[200]], offs[:201], gopt)
+                g.set_param("repeat_filter", 0)
+                tr0 = g.trace(seq[: offs[200]], offs[:201], gopt)
+                g.set_param("repeat_filter", 1)
+                assert all(np.array_equal(tr[k], tr0[k]) for k in tr0)
+            assert skipped > 2000
+            g.close()
