@@ -61,6 +61,7 @@ struct SeedParams {
 	// repeat filter (smem_repeat.cuh): bit hash(w) is set for every rf_k-mer w that occurs more than once in the indexed text
 	const u32 *qflags;       // per read, per 32 window starts: bit set = that rf_k-mer window is not vouched for (pack_reads_kernel); nullptr = no filter
 	int rf_k;                // k-mer length (<= 32)
+	int spec_walk;           // 1 = pass-1 calls that directly follow another walk their longest candidate back alone first (PH_SPEC)
 	int count_skips;         // debug: status[6] counts the re-seeding passes the filter proved void
 	u64 hot_min_intv;        // 0 = off; occ blocks of intervals >= this size are "hot" (shallow levels, re-used across reads)
 	int l2_mode;             // L2 eviction hints when hot_min_intv != 0: 0 = hot evict_last / cold normal,

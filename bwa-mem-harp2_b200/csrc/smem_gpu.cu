@@ -107,6 +107,7 @@ struct smem_gpu {
 	int64_t hot_min_intv = 0;
 	int l2_mode = 0;                 // see SeedParams::l2_mode
 	int repeat_filter = 1;           // use the repeat filter (if built) to skip void re-seeding passes in MODE_COLLECT
+	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
 	int probe_variant = 0;
 	int force_wide = 0;
@@ -590,7 +591,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	p.hot_min_intv = (u64)h.hot_min_intv;
 	p.l2_mode = h.l2_mode;
 	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf;
-	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips;
+	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips; p.spec_walk = h.spec_walk;
 	{
 		const size_t bytes_q = (size_t)d.read_cap * q_stride, bytes = bytes_q + (size_t)d.read_cap * (q_stride >> 4) * 4;   // packed reads | window flags
 		if (bytes > d.qpack_bytes) {
@@ -1428,6 +1429,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "l2_mode")) { if (v < 0 || v > 2) return SMEM_GPU_E_ARG; h->l2_mode = (int)v; return 0; }
 	if (!strcmp(name, "repeat_filter")) { h->repeat_filter = v != 0; return 0; }
 	if (!strcmp(name, "count_skips")) { h->count_skips = v != 0; return 0; }
+	if (!strcmp(name, "spec_walk")) { h->spec_walk = v != 0; return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
 		if (v != 32 && v != 64 && v != 128) return SMEM_GPU_E_ARG;
@@ -1457,6 +1459,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "l2_mode")) return h->l2_mode;
 	if (!strcmp(name, "repeat_filter")) return h->repeat_filter;
 	if (!strcmp(name, "count_skips")) return h->count_skips;
+	if (!strcmp(name, "spec_walk")) return h->spec_walk;
 	if (!strcmp(name, "has_repeat_filter")) return h->devs[0].d_rf ? 1 : 0;
 	if (!strcmp(name, "rf_kmer")) return h->devs[0].rf_k;
 	if (!strcmp(name, "rf_log2_bits")) return h->devs[0].rf_log2;

@@ -5,7 +5,7 @@
 
 enum { MODE_COLLECT = 0, MODE_SMEM1 = 1, MODE_TRACE = 2 };   // TRACE: COLLECT's walk, but every bwt_smem1 call's raw list is kept
 // hot phases first: the main loop only ever extends in PH_FWD / PH_BWD
-enum { PH_FWD = 0, PH_BWD = 1, PH_IDLE = 2, PH_NEED_READ = 3, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
+enum { PH_FWD = 0, PH_BWD = 1, PH_SPEC = 2 /* backward walk of the longest candidate alone */, PH_IDLE = 3, PH_NEED_READ = 4, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
 
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index (TRACE: step*2 + pass) rides in info bits 48..63
 #define AUX_SHIFT 16         // ... and, in TRACE mode, bwt_smem1's return value in bits 16..31 (query positions are < 2^16)
@@ -41,6 +41,7 @@ __device__ __noinline__ Intv bx_get(const Intv *p) { return ld_intv(p); }
 template <int MODE, int MIN_BLOCKS, bool WIDE, bool REUSE /* keep the last occ sectors in registers, skip repeated gathers */>
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
+	const bool SPEC = MODE != MODE_SMEM1 && p.spec_walk;     // speculative longest-only backward walk (PH_SPEC)
 	typedef BEntry<WIDE> BE;
 	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, half = lane & 1;
@@ -133,6 +134,9 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			} break;
 			case PH_NEXT_STEP: {     // head of smem_next2, bwamem.c:249-258
 				int start = lds_u16(sc + CS_START);
+				// Speculative walk (see PH_FWD_DONE): the previous pass-1 call at CS_ORI ended its forward sweep at `start` because
+				// q[CS_ORI .. start] occurs fewer than start_width times; that bounds the coming backward sweep at CS_ORI.
+				const int lim1 = (SPEC && lds_u16(sc + CS_STEP) > 0 && start < len && qbase(sq, start) <= 3) ? lds_u16(sc + CS_ORI) + 1 : 0;
 				while (start < len && qbase(sq, start) > 3) ++start;
 				if (start >= len) {
 					const int rk = lds_i32(sc + CS_RK), n_out = lds_i32(sc + CS_NOUT);
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					break;
 				}
 				sts_u16(sc + CS_START, start); sts_u16(sc + CS_ORI, start); sts_u16(sc + CS_X, start); sts_u16(sc + CS_PASS, 0);
+				if (SPEC) sts_u16(sc + CS_KEEP, lim1);       // (CS_KEEP is otherwise only used by the merge after a re-seeding pass)
 				min_intv = p.start_width < 1 ? 1 : (u64)p.start_width;
 				phase = PH_INIT_CALL;
 			} break;
@@ -174,6 +179,15 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				sts_u16(sc + CS_RET, (int)end);
 				if (MODE != MODE_SMEM1 && lds_u16(sc + CS_PASS) == 0) sts_u16(sc + CS_START, (int)end);   // bwamem.c:262
 				phase = c < 0 ? PH_BWD_LAST : PH_BWD;
+				// Every candidate of this sweep whose start reaches lim = CS_KEEP - 1 contains a pattern known to be too rare, so the
+				// sweep ends there with everything dead; and while the LONGEST candidate (a, b, s) lives nothing is emitted
+				// (bwt.c:815: curr->n != 0).  So walk it back alone: if it lives down to start lim + 1 (or to an ambiguous base /
+				// the read start, where everything dies too) it is the call's only result and the shorter candidates never needed
+				// extending; if it dies earlier the full sweep starts over (PH_SPEC in the main loop).  Model: oracle/smem_oracle.c.
+				if (SPEC && phase == PH_BWD && lds_u16(sc + CS_PASS) == 0 && lds_u16(sc + CS_KEEP) > 0) {
+					if (i < lds_u16(sc + CS_KEEP)) phase = PH_BWD_LAST;      // no round left before the limit: (i + 1, end) is the result
+					else phase = PH_SPEC;
+				}
 			} break;
 			case PH_BWD_LAST: {
 				// bwt.c:815-821 with c == -1 (read start or ambiguous base): nothing can enter curr and only
@@ -295,6 +309,21 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// ============================================================== consume the result, set up the next extend
 		// (forward: bwt.c:794-799, backward: bwt.c:813-824; written once for both so that the warp does not
 		//  run two divergent copies of the push / advance code)
+		if (SPEC && phase == PH_SPEC) {
+			if (ok.s < min_intv) {                               // died before the limit: the shorter candidates matter after all
+				i = lds_u16(sc + CS_X) - 1; j = 0; n_prev = n0; n_curr = 0;
+				c = (int)qbase(sq, i);                           // (valid: the walk started with it)
+				b_get(n0 - 1, a, b, s, end);
+				phase = PH_BWD;
+				continue;
+			}
+			a = ok.a; b = ok.b; s = ok.s;
+			--i;
+			c = i < 0 ? -1 : (int)qbase(sq, i);
+			if (c > 3) c = -1;
+			if (c < 0 || i < lds_u16(sc + CS_KEEP)) phase = PH_BWD_LAST;   // everything dies at the next round: emit (i + 1, end)
+			continue;
+		}
 		const bool fwd = phase == PH_FWD;
 		const bool small = ok.s < min_intv;
 		const bool diff = ok.s != (fwd ? s : last_s);

@@ -79,6 +79,20 @@ static inline void extend(const orc_index_t *ix, const iv_t *ik, int is_back, iv
 
 typedef struct { ivv_t prev, curr, mem, sub, merged; } scratch_t;
 
+/* MODEL of the device kernel's second shortcut, off unless orc_set_spec_walk(1) -- a test hook.
+ * When a pass-1 bwt_smem1 at x directly follows one at x_prev whose forward sweep ended at ret == x because the interval
+ * fell below min_intv, the pattern q[x_prev..x+1) occurs fewer than min_intv times; every candidate of the new call's
+ * backward sweep with start <= x_prev contains it, so the sweep ends at start x_prev with everything dead.  While the
+ * LONGEST candidate is alive nothing is emitted (bwt.c:815: curr->n != 0), so if it survives down to start x_prev + 1 (or to
+ * an ambiguous base / the read start, where everything dies as well) the call's result is that one candidate -- the
+ * shorter candidates never needed to be extended.  If it dies earlier by count, the full sweep is run after all. */
+static int orc_spec_walk = 0;
+static __thread int spec_lim = -1;          /* x_prev of the call about to be made, or -1 */
+uint64_t orc_spec_hits = 0, orc_spec_misses = 0;
+void orc_set_spec_walk(int on) { orc_spec_walk = on; orc_spec_hits = orc_spec_misses = 0; }
+uint64_t orc_get_spec_hits(void) { return orc_spec_hits; }
+uint64_t orc_get_spec_misses(void) { return orc_spec_misses; }
+
 /* bwt_smem1, bwt.c:776-835.  Writes the SMEM candidates through x into `mem`, returns ret. */
 static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int min_intv, ivv_t *mem,
                  ivv_t *prev, ivv_t *curr, orc_stats_t *st)
@@ -109,6 +123,24 @@ static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int mi
 	ret = (int)curr->a[0].info;
 	if (st && (uint64_t)curr->n > st->max_curr) st->max_curr = (uint64_t)curr->n;
 	t = prev; prev = curr; curr = t;
+	if (orc_spec_walk && spec_lim >= 0 && spec_lim < x) {
+		iv_t p = prev->a[0];
+		int ok_ = 1;
+		for (i = x - 1; i > spec_lim; --i) {
+			int c = q[i] < 4 ? q[i] : -1;
+			if (c < 0) break;                                   /* everything dies here: (i+1, end of the longest) */
+			extend(ix, &p, 1, ok, st);
+			if (ok[c].x2 < (uint64_t)min_intv) { ok_ = 0; break; } /* died by count before the limit: the others matter */
+			ok[c].info = p.info; p = ok[c];
+		}
+		if (ok_) {
+			p.info |= (uint64_t)(i + 1) << 32;
+			ivv_push(mem, p);
+			__sync_fetch_and_add(&orc_spec_hits, 1);
+			return ret;
+		}
+		__sync_fetch_and_add(&orc_spec_misses, 1);
+	}
 	for (i = x - 1; i >= -1; --i) { /* backward */
 		int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
 		curr->n = 0;
@@ -166,6 +198,8 @@ static int pass2_is_void(const orc_index_t *ix, int len, const uint8_t *q, int m
 	return 1;
 }
 
+static __thread int last_x = -1, last_ret = -1;   /* previous pass-1 call of the read being seeded (model of the second shortcut) */
+
 /* smem_next2, bwamem.c:244-305.  Returns 0 when exhausted, else 1 with the step's list in s->mem. */
 static int next2(const orc_index_t *ix, int len, const uint8_t *q, int *start, int split_len, int split_width,
                  int start_width, scratch_t *s, orc_stats_t *st)
@@ -176,7 +210,10 @@ static int next2(const orc_index_t *ix, int len, const uint8_t *q, int *start, i
 	while (*start < len && q[*start] > 3) ++*start;
 	if (*start == len) return 0;
 	ori_start = *start;
+	spec_lim = (last_x >= 0 && last_ret == ori_start) ? last_x : -1;      /* see the model above */
 	*start = smem1(ix, len, q, ori_start, start_width, &s->mem, &s->prev, &s->curr, st);
+	spec_lim = -1;
+	last_x = ori_start; last_ret = *start;
 	if (s->mem.n == 0) return 1;
 	for (i = 0; i < s->mem.n; ++i) { /* first maximum wins (bwamem.c:266-270) */
 		int l = iv_len(&s->mem.a[i]);
@@ -214,6 +251,7 @@ static void collect_read(const orc_index_t *ix, int len, const uint8_t *q, const
 	/* mem_opt_t::split_factor is a float (bwamem.h:47): float product, then the double addition of bwamem.c:456 */
 	int split_len = (int)((double)((float)o->min_seed_len * (float)o->split_factor) + .499), start = 0, step = 0, i;
 	if (split_len > len) split_len = len;
+	last_x = last_ret = -1;
 	while (next2(ix, len, q, &start, split_len, o->split_width, o->start_width, s, st)) {
 		for (i = 0; i < s->mem.n; ++i) emit(ctx, &s->mem.a[i], step);
 		if (st) { st->steps++; st->intervals += (uint64_t)s->mem.n; }

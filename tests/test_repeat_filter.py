@@ -1,4 +1,5 @@
-"""Repeat filter of the re-seeding pass (csrc/smem_repeat.cuh).
+"""The two exact shortcuts of the seeding kernel: the repeat filter of the re-seeding pass
+(csrc/smem_repeat.cuh) and the speculative longest-only backward walk (PH_SPEC, csrc/smem_kernels.cuh).
 CPU: the rule itself -- "if max>>1 >= K and every K-mer window through the re-seeding position occurs at most once, the
 second pass of smem_next2 contributes nothing" -- modelled in the oracle with exact counts and compared with the unmodified
 algorithm.  GPU: the device table against brute force, and seeding with the filter against the oracle."""
@@ -42,6 +43,28 @@ def test_skip_rule_is_exact_on_cpu(worlds, synth):
                 for k in ("intv", "read_off", "step"):
                     assert np.array_equal(got[k], want[k]), (name, rl, K, k)
         assert total_skipped > 1000          # the rule fires (and is exercised) on these sets
+
+
+def test_spec_walk_rule_is_exact_on_cpu(worlds, synth):
+    """Model of PH_SPEC in the oracle (smem_oracle.c, orc_set_spec_walk) against the unmodified algorithm, alone and
+    together with the pass-2 rule."""
+    for name, ref, ix, o in worlds:
+        o.lib.orc_get_spec_hits.restype = C.c_uint64
+        hits = 0
+        for rl, err, opt in SETS:
+            seq, offs = synth.to_batch(synth.simulate_reads(ref, 1200, rl, err, seed=29, paired=True, n_frac=0.05))
+            o.lib.orc_set_skip_kmer(0); o.lib.orc_set_spec_walk(0)
+            want = o.collect(seq, offs, opt, nthreads=2)
+            for K in (0, 15):
+                o.lib.orc_set_skip_kmer(K); o.lib.orc_set_spec_walk(1)
+                try:
+                    got = o.collect(seq, offs, opt, nthreads=2)
+                    hits += o.lib.orc_get_spec_hits()
+                finally:
+                    o.lib.orc_set_skip_kmer(0); o.lib.orc_set_spec_walk(0)
+                for k in ("intv", "read_off", "step", "n_steps", "last_start"):
+                    assert np.array_equal(got[k], want[k]), (name, rl, K, k)
+        assert hits > 1000
 
 
 def _brute_bits(T, K, log2_bits):
@@ -101,13 +124,14 @@ def test_gpu_collect_with_repeat_filter_vs_oracle(worlds, synth):
                 g.set_param("repeat_filter", 0)               # and the same answer with the filter switched off
                 off = g.collect(seq, offs, gopt)
                 assert g.get_param("pass2_skipped") == 0
-                g.set_param("repeat_filter", 1)
                 assert np.array_equal(off["intv"], want["intv"])
-                # raw bwt_smem1 lists are never shortened by the filter
-                tr = g.trace(seq[: offs[200]], offs[:201], gopt)
-                g.set_param("repeat_filter", 0)
+                g.set_param("spec_walk", 0)                   # ... and with both shortcuts off
+                off2 = g.collect(seq, offs, gopt)
+                assert np.array_equal(off2["intv"], want["intv"]) and np.array_equal(off2["step"], want["step"])
+                # raw bwt_smem1 lists (TRACE) are never shortened by the filter and are the same with and without the walk
                 tr0 = g.trace(seq[: offs[200]], offs[:201], gopt)
-                g.set_param("repeat_filter", 1)
+                g.set_param("repeat_filter", 1); g.set_param("spec_walk", 1)
+                tr = g.trace(seq[: offs[200]], offs[:201], gopt)
                 assert all(np.array_equal(tr[k], tr0[k]) for k in tr0)
             assert skipped > 2000
             g.close()
