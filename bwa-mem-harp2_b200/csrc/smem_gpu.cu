@@ -27,6 +27,7 @@ struct DeviceCtx {
 	size_t smem_per_sm = 0, smem_per_block_optin = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+	cudaEvent_t ev_sync = nullptr;   // blocking-sync event: host waits sleep instead of spinning (see stream_wait)
 	// index
 	uint4 *d_index = nullptr;
 	size_t index_bytes = 0;
@@ -97,6 +98,17 @@ struct DeviceCtx {
 
 } // namespace
 
+// Host wait for everything enqueued on the context's stream.  cudaStreamSynchronize spins a core; with one process per GPU
+// and several worker threads each (8 GPUs x 2 threads on a 16-core host) the spinning threads starve the ones that have
+// work, so such hosts can route the wait through a blocking-sync event and sleep ("blocking_sync" = 1; measured on this box: each wake-up costs ~1.5 ms, so it is off by default).
+static bool g_blocking_sync = false;
+static inline cudaError_t stream_wait(DeviceCtx &d)
+{
+	if (!g_blocking_sync) return cudaStreamSynchronize(d.stream);
+	cudaError_t e = cudaEventRecord(d.ev_sync, d.stream);
+	return e != cudaSuccess ? e : cudaEventSynchronize(d.ev_sync);
+}
+
 struct smem_gpu {
 	std::vector<DeviceCtx> devs;
 	int64_t max_batch = 0;
@@ -164,6 +176,7 @@ int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int
 		CK(cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, std::min(lo, hi + lane)));
 	}
 	CK(cudaEventCreate(&d.ev0)); CK(cudaEventCreate(&d.ev1)); CK(cudaEventCreate(&d.ev2));
+	CK(cudaEventCreateWithFlags(&d.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
 	d.read_cap = read_cap;
 	d.seq_cap = (size_t)read_cap * (size_t)max_len + 64;
 	int rc;
@@ -212,6 +225,7 @@ void ctx_free(DeviceCtx &d)
 	if (d.ev0) cudaEventDestroy(d.ev0);
 	if (d.ev1) cudaEventDestroy(d.ev1);
 	if (d.ev2) cudaEventDestroy(d.ev2);
+	if (d.ev_sync) cudaEventDestroy(d.ev_sync);
 	if (d.stream) cudaStreamDestroy(d.stream);
 }
 
@@ -241,7 +255,7 @@ int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 	}
 	repack_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, d.stream>>>(src, n_blocks, ix->seq_len, d.d_index);
 	CK(cudaGetLastError());
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	if (tmp) CK(cudaFree(tmp));
 	d.index_bytes = (size_t)n_blocks * 64;
 	d.ix.blk = d.d_index;
@@ -280,7 +294,7 @@ int ctx_build_tables(DeviceCtx &d, const uint8_t *pac, int64_t l_pac, int src_de
 	// the last D symbols of T are the reverse complement of the first D symbols of the forward text
 	uint8_t head[8] = {0};
 	CKT(cudaMemcpyAsync(head, d_pac, std::min<size_t>(pac_bytes, 8), cudaMemcpyDeviceToHost, d.stream));
-	CKT(cudaStreamSynchronize(d.stream));
+	CKT(stream_wait(d));
 	TailCodes tails{};
 	for (int a = 1; a <= D && a < 20; ++a) {
 		u64 code = 0;
@@ -320,7 +334,7 @@ int ctx_build_tables(DeviceCtx &d, const uint8_t *pac, int64_t l_pac, int src_de
 	// entries next to a suffix of T shorter than their level: unknown (see bwa-mem-harp2_b200/kmer_tables.py)
 	for (int a = K; a < LP; ++a) CKT(cudaMemsetAsync(pyr + (tails.code[a] << (2 * (LP - a))), 255, (size_t)1 << (2 * (LP - a)), d.stream));
 	CKT(cudaMemsetAsync(top + (tails.code[LP] << 2), 255, 4, d.stream));
-	CKT(cudaStreamSynchronize(d.stream));
+	CKT(stream_wait(d));
 #undef CKT
 	if (d_pac != pac) cudaFree(d_pac);
 	cudaFree(tw); cudaFree(cntK); cudaFree(bsum);
@@ -364,7 +378,7 @@ int ctx_build_repeat_filter(DeviceCtx &d, const uint8_t *pac, long long l_pac, i
 		rf_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(tw, n, K, G, g, slots, log2_slots, bits, log2_bits);
 		CKT(cudaGetLastError());
 	}
-	CKT(cudaStreamSynchronize(d.stream));
+	CKT(stream_wait(d));
 	cudaFree(slots); slots = nullptr;
 	if (auto_bits) {
 		// fold down while the share of set bits stays <= 1/256 (and never below 2^16 bits)
@@ -376,7 +390,7 @@ int ctx_build_repeat_filter(DeviceCtx &d, const uint8_t *pac, long long l_pac, i
 			CKT(cudaMemsetAsync(d_pop, 0, 8, d.stream));
 			rf_fold_kernel<<<(unsigned)((n_dst + 255) / 256), 256, 0, d.stream>>>(cur, nxt, n_dst, d_pop);
 			CKT(cudaMemcpyAsync(&h_pop, d_pop, 8, cudaMemcpyDeviceToHost, d.stream));
-			CKT(cudaStreamSynchronize(d.stream));
+			CKT(stream_wait(d));
 			if (h_pop * 256 > (1ull << (log2_bits - 1))) break;                   // too full: keep `cur`
 			std::swap(cur, nxt);                                                   // nxt now holds the larger table; its buffer is reused
 			--log2_bits;
@@ -385,7 +399,7 @@ int ctx_build_repeat_filter(DeviceCtx &d, const uint8_t *pac, long long l_pac, i
 		// keep only as many bytes as the chosen size needs
 		CKT(cudaMalloc((void **)&bits, (size_t)1 << (log2_bits - 3)));
 		CKT(cudaMemcpyAsync(bits, cur, (size_t)1 << (log2_bits - 3), cudaMemcpyDeviceToDevice, d.stream));
-		CKT(cudaStreamSynchronize(d.stream));
+		CKT(stream_wait(d));
 		cudaFree(cur); cur = nullptr;
 	}
 #undef CKT
@@ -430,7 +444,7 @@ int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const
 		CK(cudaMemcpyAsync(d.d_mi, mi + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
 	}
 	{ std::lock_guard<std::mutex> lk(d.owner->lane_mu); d.stage_issued = d.owner->stage_epoch; d.owner->lane_cv.notify_all(); }
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	return 0;
 }
 
@@ -679,7 +693,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const auto tt0 = std::chrono::steady_clock::now();
 	auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 7 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	const double t_status = tms();
 	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
 	const int n_over = d.h_status[1];
@@ -690,7 +704,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
 		std::vector<int> list(n_over);
 		CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
-		CK(cudaStreamSynchronize(d.stream));
+		CK(stream_wait(d));
 		std::sort(list.begin(), list.end());       // deterministic re-run order
 		if ((size_t)n_over > d.counts_k_cap) {
 			if (d.d_counts_k) CK(cudaFree(d.d_counts_k));
@@ -717,7 +731,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			   : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide, h.reuse != 0) : launch_seed<MODE_TRACE>(d, p2, bps, grid2, smem, wide, false);
 			if (rc) return rc;
 			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-			CK(cudaStreamSynchronize(d.stream));
+			CK(stream_wait(d));
 			if (d.h_status[2] != 0) { d.err = "device guard tripped in the overflow re-run"; return SMEM_GPU_E_INTERNAL; }
 			if (d.h_status[1] == 0) break;
 			if (round == 2) { d.err = "overflow re-run did not converge"; return SMEM_GPU_E_INTERNAL; }
@@ -738,7 +752,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		d.launches += 3;
 	}
 	CK(cudaMemcpyAsync(d.h_status + 6, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	const double t_scan = tms();
 	memcpy(&d.total, d.h_status + 6, 8);
 	if ((size_t)d.total > d.out_cap) {
@@ -766,7 +780,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	// the scan / compaction kernels are queued ahead of whatever the next call launches: a persistent seed kernel that got
 	// there first would hold every SM and they would wait for it to drain
 	turn_release(d);
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	if (trace) fprintf(stderr, "[smem_gpu trace]   lane %d run: status +%.2f scan +%.2f compact +%.2f ms after the seed launch\n", d.lane, t_status, t_scan, tms());
 	CK(cudaEventElapsedTime(&d.seed_ms, d.ev0, d.ev1));
 	CK(cudaEventElapsedTime(&d.total_ms, d.ev0, d.ev2));
@@ -782,7 +796,7 @@ int ctx_fetch(DeviceCtx &d, smem_intv_t *intv_out, int64_t *read_off, uint16_t *
 	if (step_out && d.total) CK(cudaMemcpyAsync(step_out + base, d.d_step, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream));
 	if (aux_out && d.total) CK(cudaMemcpyAsync(aux_out + base, d.d_aux, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream));
 	if (ret) CK(cudaMemcpyAsync(ret + d.lo, d.d_ret, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	if (base) for (int64_t i = d.lo; i < d.hi; ++i) read_off[i] += base;
 	return 0;
 }
@@ -973,7 +987,7 @@ int ctx_upload_sa(DeviceCtx &d, int sa_shift, u64 n_sa, const uint64_t *sa, int 
 	if (src_device < 0) CK(cudaMemcpyAsync(d.d_sa, sa, (size_t)n_sa * 8, cudaMemcpyHostToDevice, d.stream));
 	else if (src_device == d.dev) CK(cudaMemcpyAsync(d.d_sa, sa, (size_t)n_sa * 8, cudaMemcpyDeviceToDevice, d.stream));
 	else CK(cudaMemcpyPeerAsync(d.d_sa, d.dev, sa, src_device, (size_t)n_sa * 8, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	d.sa_shift = sa_shift; d.n_sa = n_sa;
 	return 0;
 }
@@ -998,7 +1012,7 @@ int ctx_sa(DeviceCtx &d, const uint64_t *k, uint64_t *out)
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(out + d.lo, d.d_kout, (size_t)n * 8, cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	if (d.h_status[2] != 0) { d.err = "suffix-array walk did not terminate (corrupt index?)"; return SMEM_GPU_E_INTERNAL; }
 	return 0;
 }
@@ -1049,7 +1063,7 @@ int ctx_seeds_run(DeviceCtx &d, int min_seed_len, u64 max_occ)
 	int rc = run_scan(d, d.d_scnt, total + 1, d.d_soff);
 	if (rc) return rc;
 	CK(cudaMemcpyAsync(d.h_status + 8, d.d_soff + total, 8, cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	memcpy(&d.n_seeds, d.h_status + 8, 8);
 	if ((size_t)d.n_seeds > d.seeds_cap) {
 		if (d.d_seeds) CK(cudaFree(d.d_seeds));
@@ -1065,7 +1079,7 @@ int ctx_seeds_run(DeviceCtx &d, int min_seed_len, u64 max_occ)
 		CK(cudaGetLastError());
 	}
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	if (d.h_status[2] != 0) { d.err = "suffix-array walk did not terminate (corrupt index?)"; return SMEM_GPU_E_INTERNAL; }
 	d.seeds_valid = true;
 	return 0;
@@ -1115,7 +1129,7 @@ int ctx_chains_run(DeviceCtx &d, const ChainOpt &o)
 	chain_emit_kernel<<<grid, CHAIN_TPB, 0, d.stream>>>(cw, d.d_coff, d.d_koff, 0, d.d_chains, d.d_cseeds);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(d.ev1, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	memcpy(&d.n_chains, d.h_status + 8, 8);
 	memcpy(&d.n_cseeds, d.h_status + 10, 8);
 	CK(cudaEventElapsedTime(&d.chain_ms, d.ev0, d.ev1));
@@ -1132,7 +1146,7 @@ int ctx_chains_fetch(DeviceCtx &d, smem_chain_t *chains_out, smem_seed_t *seeds_
 	CK(cudaMemcpyAsync(off.data(), d.d_coff, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));
 	if (chains_out && d.n_chains) CK(cudaMemcpyAsync(chains_out + chain_base, d.d_chains, (size_t)d.n_chains * sizeof(Chain), cudaMemcpyDeviceToHost, d.stream));
 	if (seeds_out && d.n_cseeds) CK(cudaMemcpyAsync(seeds_out + seed_base, d.d_cseeds, (size_t)d.n_cseeds * sizeof(Seed), cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	for (int64_t i = 0; i < d.n; ++i) chain_off[d.lo + i] = off[(size_t)i] + chain_base;
 	if (chains_out && seed_base) for (long long k = 0; k < d.n_chains; ++k) chains_out[chain_base + k].seed_first += seed_base;
 	return 0;
@@ -1146,7 +1160,7 @@ int ctx_seeds_fetch(DeviceCtx &d, smem_seed_t *seeds_out, int64_t *seed_off, lon
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(seed_off + d.lo, d.d_sroff, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));
 	if (seeds_out && d.n_seeds) CK(cudaMemcpyAsync(seeds_out + base, d.d_seeds, (size_t)d.n_seeds * sizeof(Seed), cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaStreamSynchronize(d.stream));
+	CK(stream_wait(d));
 	return 0;
 }
 
@@ -1430,6 +1444,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "repeat_filter")) { h->repeat_filter = v != 0; return 0; }
 	if (!strcmp(name, "count_skips")) { h->count_skips = v != 0; return 0; }
 	if (!strcmp(name, "spec_walk")) { h->spec_walk = v != 0; return 0; }
+	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
 		if (v != 32 && v != 64 && v != 128) return SMEM_GPU_E_ARG;
@@ -1460,6 +1475,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "repeat_filter")) return h->repeat_filter;
 	if (!strcmp(name, "count_skips")) return h->count_skips;
 	if (!strcmp(name, "spec_walk")) return h->spec_walk;
+	if (!strcmp(name, "blocking_sync")) return g_blocking_sync ? 1 : 0;
 	if (!strcmp(name, "has_repeat_filter")) return h->devs[0].d_rf ? 1 : 0;
 	if (!strcmp(name, "rf_kmer")) return h->devs[0].rf_k;
 	if (!strcmp(name, "rf_log2_bits")) return h->devs[0].rf_log2;
@@ -1506,7 +1522,7 @@ int smem_gpu_gather_roofline(smem_gpu_t *h, int block_bytes, uint64_t span_bytes
 #undef PROBE
 			CK(cudaGetLastError());
 			CK(cudaEventRecord(d.ev1, d.stream));
-			CK(cudaStreamSynchronize(d.stream));
+			CK(stream_wait(d));
 		}
 		float ms = 0;
 		CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
