@@ -135,3 +135,42 @@ def test_gpu_collect_with_repeat_filter_vs_oracle(worlds, synth):
                 assert all(np.array_equal(tr[k], tr0[k]) for k in tr0)
             assert skipped > 2000
             g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_repeat_filter_ragged_and_edge_reads(worlds, synth):
+    """Empty / shorter than the k-mer / exactly k / 2k-1 / 2k / long error-free reads, ambiguous bases next to the re-seeding
+    position, reads from both strands and across the forward/reverse junction -- filter and walk on, against the oracle."""
+    sg = pkg("smem_gpu")
+    name, ref, ix, o = worlds[0]
+    r = ref.numpy()
+    K = 13
+    rng = np.random.default_rng(3)
+    reads = [np.zeros(0, np.uint8), np.full(40, 4, np.uint8)]
+    for ln in (1, 5, K - 1, K, K + 1, 2 * K - 1, 2 * K, 2 * K + 1, 60, 101, 255, 256):
+        for _ in range(6):
+            p = int(rng.integers(0, len(r) - ln))
+            q = r[p:p + ln].copy()
+            if rng.random() < 0.5:
+                q = (3 - q)[::-1].copy()
+            reads.append(q)
+    for _ in range(40):                                   # one N close to the middle of a long exact match
+        p = int(rng.integers(0, len(r) - 120)); q = r[p:p + 120].copy(); q[60 + int(rng.integers(-K, K))] = 4; reads.append(q)
+    for _ in range(20):                                   # two substitutions K-ish apart
+        p = int(rng.integers(0, len(r) - 150)); q = r[p:p + 150].copy()
+        a = int(rng.integers(20, 100)); q[a] = (q[a] + 1) % 4; q[a + int(rng.integers(1, 2 * K))] ^= 1; reads.append(q)
+    T = np.concatenate([r, (3 - r)[::-1]])
+    for off in (-60, -30, -1, 0):                         # across the junction of forward text and reverse complement
+        reads.append(T[len(r) + off - 50: len(r) + off + 51].copy())
+    seq, offs = synth.to_batch(reads)
+    want = o.collect(seq, offs, SeedOpt(), nthreads=2)
+    for devices in ([0], [0, 0, 0]):
+        g = sg.SmemGpu(max_batch_reads=1024, max_read_len=256, devices=devices)
+        g.upload_index(ix)
+        g.build_repeat_filter(ref, K, 0)
+        g.set_param("count_skips", 1)
+        got = g.collect(seq, offs)
+        for k in ("intv", "read_off", "step"):
+            assert np.array_equal(got[k], want[k]), k
+        assert g.get_param("pass2_skipped") > 20
+        g.close()
