@@ -42,6 +42,7 @@ struct DeviceCtx {
 	int64_t escaped = 0;
 	// repeat filter of the re-seeding pass (smem_repeat.cuh)
 	u32 *d_rf = nullptr; bool owns_rf = true; int rf_k = 0, rf_log2 = 0;
+	u64 rf_text_len = 0;             // length of the text the filter was built from: it is only used with an index of that seq_len
 	int64_t pass2_skipped = 0;
 	uint64_t turn_epoch = 0;         // epoch of the last run in which this lane took part in the kernel turn
 	bool holds_turn = false;         // this lane's seed kernel is part of the call that currently owns the GPU's kernel turn
@@ -349,7 +350,7 @@ int ctx_build_repeat_filter(DeviceCtx &d, const uint8_t *pac, long long l_pac, i
 {
 	CK(cudaSetDevice(d.dev));
 	if (d.d_rf && d.owns_rf) cudaFree(d.d_rf);
-	d.d_rf = nullptr; d.owns_rf = true; d.rf_k = 0; d.rf_log2 = 0;
+	d.d_rf = nullptr; d.owns_rf = true; d.rf_k = 0; d.rf_log2 = 0; d.rf_text_len = 0;
 	const long long n = 2 * l_pac;
 	const size_t pac_bytes = (size_t)((l_pac + 3) / 4);
 	uint8_t *d_pac = nullptr;
@@ -405,7 +406,7 @@ int ctx_build_repeat_filter(DeviceCtx &d, const uint8_t *pac, long long l_pac, i
 #undef CKT
 	if (d_pac != pac) cudaFree(d_pac);
 	cudaFree(tw);
-	d.d_rf = bits; d.rf_k = K; d.rf_log2 = log2_bits;
+	d.d_rf = bits; d.rf_k = K; d.rf_log2 = log2_bits; d.rf_text_len = (u64)n;
 	return 0;
 }
 
@@ -604,7 +605,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	}
 	p.hot_min_intv = (u64)h.hot_min_intv;
 	p.l2_mode = h.l2_mode;
-	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf;
+	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf && d.rf_text_len == d.ix.seq_len;   // (a filter of another text is ignored)
 	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips; p.spec_walk = h.spec_walk;
 	{
 		const size_t bytes_q = (size_t)d.read_cap * q_stride, bytes = bytes_q + (size_t)d.read_cap * (q_stride >> 4) * 4;   // packed reads | window flags
@@ -1168,6 +1169,11 @@ int ctx_seeds_fetch(DeviceCtx &d, smem_seed_t *seeds_out, int64_t *seed_off, lon
 // see smem_gpu_create) alias the first one's copy.
 static int upload_all(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device)
 {
+	// a repeat filter belongs to the text of the index it was built next to: a new index drops it (build it after the upload)
+	for (auto &d : h->devs) {
+		if (d.d_rf && d.owns_rf) { cudaSetDevice(d.dev); cudaFree(d.d_rf); }
+		d.d_rf = nullptr; d.owns_rf = true; d.rf_k = d.rf_log2 = 0; d.rf_text_len = 0;
+	}
 	int rc = for_each_device(h, [&](DeviceCtx &d) {
 		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
 		return ctx_upload_index(d, ix, src_device);
@@ -1212,7 +1218,7 @@ int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src)
 		if (d.has_tables && d.owns_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
 		d.ft = o->ft; d.has_tables = o->has_tables; d.owns_tables = false;
 		if (d.d_rf && d.owns_rf) cudaFree(d.d_rf);
-		d.d_rf = o->d_rf; d.owns_rf = false; d.rf_k = o->rf_k; d.rf_log2 = o->rf_log2;
+		d.d_rf = o->d_rf; d.owns_rf = false; d.rf_k = o->rf_k; d.rf_log2 = o->rf_log2; d.rf_text_len = o->rf_text_len;
 	}
 	return 0;
 }
@@ -1227,6 +1233,8 @@ int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pa
 	const bool auto_bits = log2_bits <= 0;                        // fill a table of 8 bits per text position, then fold it down (smem_repeat.cuh)
 	if (auto_bits) log2_bits = std::min(36, std::max(17, lg + 3));
 	if (kmer_len < 8 || kmer_len > 32 || n <= kmer_len || log2_bits < 10 || log2_bits > 40) return SMEM_GPU_E_ARG;
+	for (auto &d : h->devs)
+		if (d.has_index && d.ix.seq_len != (u64)n) { h->err = "2 * l_pac differs from the seq_len of the uploaded index"; return SMEM_GPU_E_ARG; }
 	int rc = for_each_device(h, [&](DeviceCtx &d) {
 		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
 		return ctx_build_repeat_filter(d, pac, l_pac, src_device, kmer_len, log2_bits, auto_bits);
@@ -1235,7 +1243,7 @@ int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pa
 	for (auto &d : h->devs)
 		for (auto &o : h->devs) {
 			if (&o == &d) break;
-			if (o.dev == d.dev) { d.d_rf = o.d_rf; d.owns_rf = false; d.rf_k = o.rf_k; d.rf_log2 = o.rf_log2; break; }
+			if (o.dev == d.dev) { d.d_rf = o.d_rf; d.owns_rf = false; d.rf_k = o.rf_k; d.rf_log2 = o.rf_log2; d.rf_text_len = o.rf_text_len; break; }
 		}
 	return 0;
 }

@@ -111,7 +111,8 @@ int smem_gpu_get_kmer_table(smem_gpu_t *h, int which, int level, void *out, int6
  * length (22 on a 3.1 Gbp index; 4^kmer_len ~ 1000 x the text length), log2_bits 0 = the smallest power of two
  * for which at most 1/256 of the bits are set (found by filling a table of 8 bits per text position and folding it down:
  * 32-128 MB and L2-friendly on a repeat-poor text, gigabytes on a repeat-rich one).  smem_gpu_smem1 / smem_gpu_trace return raw bwt_smem1 lists and never skip.
- * "repeat_filter" (smem_gpu_set_param) switches its use off and on; smem_gpu_share_index shares it. */
+ * "repeat_filter" (smem_gpu_set_param) switches its use off and on; smem_gpu_share_index shares it.  Build it AFTER
+ * smem_gpu_upload_index (2 * l_pac must equal the index's seq_len; uploading another index drops the filter). */
 int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int kmer_len, int log2_bits);
 /* Test hook: the bit table of device 0 (2^(log2_bits - 5) uint32 words; get_param "rf_kmer" / "rf_log2_bits"). */
 int smem_gpu_get_repeat_filter(smem_gpu_t *h, uint32_t *out, int64_t out_words);

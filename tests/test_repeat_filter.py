@@ -174,3 +174,24 @@ def test_gpu_repeat_filter_ragged_and_edge_reads(worlds, synth):
             assert np.array_equal(got[k], want[k]), k
         assert g.get_param("pass2_skipped") > 20
         g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_repeat_filter_of_another_text_is_refused_or_ignored(worlds, synth, fm):
+    sg = pkg("smem_gpu")
+    name, ref, ix, o = worlds[0]
+    other = synth.make_reference(300_000, 99)
+    g = sg.SmemGpu(max_batch_reads=2048, max_read_len=128)
+    g.upload_index(ix)
+    with pytest.raises(sg.SmemGpuError):
+        g.build_repeat_filter(other, 13, 0)                   # text length differs from the uploaded index
+    g.build_repeat_filter(ref, 13, 0)
+    ix2 = fm.build_index(other)
+    g.upload_index(ix2)                                       # new index, old filter: must not be used
+    seq, offs = synth.to_batch(synth.simulate_reads(other, 1500, 101, 0.01, seed=5, paired=True))
+    g.set_param("count_skips", 1)
+    got = g.collect(seq, offs)
+    assert g.get_param("pass2_skipped") == 0
+    want = Oracle(ix2).collect(seq, offs, SeedOpt(), nthreads=2)
+    assert np.array_equal(got["intv"], want["intv"]) and np.array_equal(got["read_off"], want["read_off"])
+    g.close()
