@@ -164,7 +164,9 @@ def test_gpu_repeat_filter_ragged_and_edge_reads(worlds, synth):
         reads.append(T[len(r) + off - 50: len(r) + off + 51].copy())
     seq, offs = synth.to_batch(reads)
     want = o.collect(seq, offs, SeedOpt(), nthreads=2)
-    for devices in ([0], [0, 0, 0]):
+    import torch
+    two = [[0, 1]] if torch.cuda.device_count() >= 2 else []          # one handle over two GPUs: the filter is built on both
+    for devices in [[0], [0, 0, 0]] + two:
         g = sg.SmemGpu(max_batch_reads=1024, max_read_len=256, devices=devices)
         g.upload_index(ix)
         g.build_repeat_filter(ref, K, 0)
