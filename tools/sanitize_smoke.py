@@ -1,4 +1,4 @@
-"""Small end-to-end run for compute-sanitizer: collect, smem1, overflow re-run, spill path, sa, seeds."""
+"""Small end-to-end run for compute-sanitizer: collect, smem1, overflow re-run, spill path, sa, seeds, chains, repeat filter, trace."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -15,6 +15,7 @@ want = o.collect(seq, offs, SeedOpt(), nthreads=4)
 for devices in ([0], [0, 0]):
     g = sg.SmemGpu(max_batch_reads=1024, max_read_len=128, devices=devices)
     g.upload_index(ix); g.upload_sa(ix)
+    g.build_repeat_filter(ref, 12, 0)                  # filter + window flags + speculative walk are on from here
     for name, val in (("slot_cap", 128), ("slot_cap", 3), ("b_cap", 2), ("force_wide", 1), ("blocks_per_sm", 4)):
         g.set_param(name, val)
         got = g.collect(seq, offs)
@@ -24,6 +25,12 @@ for devices in ([0], [0, 0]):
     assert np.array_equal(s1["intv"], s2["intv"]) and np.array_equal(s1["ret"], s2["ret"])
     g.collect(seq, offs)
     sd = g.seeds(600)
+    ch = g.chains(600, ix.seq_len // 2)
+    assert ch["chain_off"][-1] == len(ch["chains"]) and ch["chains"]["n_seeds"].sum() == len(ch["seeds"])
+    tr = g.trace(seq, offs)
+    assert tr["read_off"][-1] == len(tr["intv"])
+    g.build_repeat_filter(ref, 16, 20)
+    assert np.array_equal(g.collect(seq, offs)["intv"], want["intv"])
     k = np.random.default_rng(2).integers(0, ix.seq_len + 1, 2000).astype(np.uint64)
     assert np.array_equal(g.sa(k), o.sa(ix, k))
     g.close()
