@@ -1143,12 +1143,14 @@ int ctx_chains_fetch(DeviceCtx &d, smem_chain_t *chains_out, smem_seed_t *seeds_
 {
 	CK(cudaSetDevice(d.dev));
 	if (d.n == 0) return 0;
-	std::vector<long long> off((size_t)d.n);
-	CK(cudaMemcpyAsync(off.data(), d.d_coff, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));
+	if (chain_base) {                        // offsets of this shard in the caller's numbering (d_coff is rebuilt by every run)
+		add_base_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, d.stream>>>(d.d_coff, d.n, chain_base);
+		CK(cudaGetLastError());
+	}
+	CK(cudaMemcpyAsync(chain_off + d.lo, d.d_coff, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));
 	if (chains_out && d.n_chains) CK(cudaMemcpyAsync(chains_out + chain_base, d.d_chains, (size_t)d.n_chains * sizeof(Chain), cudaMemcpyDeviceToHost, d.stream));
 	if (seeds_out && d.n_cseeds) CK(cudaMemcpyAsync(seeds_out + seed_base, d.d_cseeds, (size_t)d.n_cseeds * sizeof(Seed), cudaMemcpyDeviceToHost, d.stream));
 	CK(stream_wait(d));
-	for (int64_t i = 0; i < d.n; ++i) chain_off[d.lo + i] = off[(size_t)i] + chain_base;
 	if (chains_out && seed_base) for (long long k = 0; k < d.n_chains; ++k) chains_out[chain_base + k].seed_first += seed_base;
 	return 0;
 }
