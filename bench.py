@@ -563,6 +563,13 @@ def main():
             pass
         value = world * n * args.steps / dt
         achieved = n * bytes_per_read / (seed_avg_ms * 1e-3) / 1e9
+        # the bound that actually holds for this access pattern: DRAM-missing requests per second.
+        # requests of the kernel = ncu DRAM bytes / 64 (the sector pairs a lane pair gathers); ceiling = the coalesced 64 B probe
+        request_rate = None
+        if traffic and rand64 and not fast_info:
+            rq = traffic / 64.0 / (seed_avg_ms * 1e-3) / 1e9
+            request_rate = {"achieved_G_per_s": rq, "ceiling_G_per_s": rand64 / 64.0, "frac": rq / (rand64 / 64.0),
+                            "note": "DRAM requests of 64 B per second: ncu dram bytes of the committed capture / 64 / live kernel time, against the coalesced gather probe measured in this run"}
         out = {
             "metric": "smem_seeded_101bp_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -576,6 +583,7 @@ def main():
                          "kernel": "fast_kernel + resolve_kernel (k-mer count pyramid; FM re-run of escaped reads not included)" if fast_info else "seed_kernel<COLLECT>",
                          "kernel_ms": seed_avg_ms, "algorithmic_bytes_per_read": bytes_per_read, "executed": executed,
                          "achieved_note": "algorithmic bytes of the REFERENCE algorithm (SURVEY 8d) / kernel time; `executed` and `traffic` show what the kernel really touches",
+                         "request_rate": request_rate,
                          "random_access_peak": rand64, "frac_of_random_access": achieved / rand64 if rand64 else None,
                          "random_access_peak_two_requests": rand64_split,
                          "random_access_note": "dependent 64 B gathers over the whole index (smem_gpu_gather_roofline): one coalesced "
