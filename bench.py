@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-bp", type=int, default=int(os.environ.get("SMEM_BENCH_REF_BP", 3_100_000_000)))
     ap.add_argument("--contigs", type=int, default=25)
+    ap.add_argument("--repeat-frac", type=float, default=0.0, help="robustness runs: overwrite this share of the reference with diverged copies of a few 300 bp repeat families (synth.add_repeat_families)")
     ap.add_argument("--reads", type=int, default=int(os.environ.get("SMEM_BENCH_READS", 2_000_000)), help="reads per GPU per step")
     ap.add_argument("--read-len", type=int, default=101)
     ap.add_argument("--err", type=float, default=0.01)
@@ -126,6 +127,8 @@ def make_workload(args, rank, device):
     sy = importlib.import_module("bwa-mem-harp2_b200.synth")
     t0 = time.time()
     fwd = sy.make_reference(args.ref_bp, 13, device)
+    if args.repeat_frac > 0:
+        fwd = sy.add_repeat_families(fwd, args.repeat_frac, 17)
     ix = fm.build_index(fwd, sa_intv=32 if getattr(args, 'seeds', False) else 0)
     torch.cuda.synchronize()
     t_index = time.time() - t0
@@ -188,7 +191,7 @@ def main():
     from oracle.binding import SeedOpt as OSeedOpt
     sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    workload = (f"{args.ref_bp / 1e9:.2f} Gbp synthetic reference ({args.contigs} contigs), "
+    workload = (f"{args.ref_bp / 1e9:.2f} Gbp synthetic reference ({args.contigs} contigs{', %.0f%% interspersed 300 bp repeat families' % (100 * args.repeat_frac) if args.repeat_frac > 0 else ''}), "
                 f"{args.reads // 2} simulated {args.read_len}bp read pairs ({args.reads} reads) per GPU per step, "
                 f"{args.err:.0%} substitutions, -k 19 -r 1.5 re-seeding on")
     config = {"workload": workload, "baseline_config": "configs[2]", "ref_bp": args.ref_bp, "reads_per_gpu_per_step": args.reads,

@@ -25,6 +25,33 @@ def make_reference(n_bp: int, seed: int, device: "str | torch.device" = "cpu") -
     return out
 
 
+def add_repeat_families(fwd: torch.Tensor, frac: float, seed: int, n_families: int = 4, unit_len: int = 300,
+                        divergence: float = 0.05) -> torch.Tensor:
+    """Overwrite about ``frac`` of ``fwd`` in place with diverged copies (either strand) of ``n_families`` consensus
+    sequences of ``unit_len`` bases -- a crude model of interspersed repeats (Alu-like) for robustness runs: seeds with
+    thousands of occurrences, many chains per read, a well filled repeat filter."""
+    dev = fwd.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    L = int(fwd.numel())
+    cons = torch.randint(0, 4, (n_families, unit_len), generator=g, device=dev, dtype=torch.uint8)
+    n_ins = int(frac * L / unit_len)
+    ar = torch.arange(unit_len, device=dev, dtype=torch.int64)
+    step = max(1, (1 << 24) // unit_len)
+    for s0 in range(0, n_ins, step):
+        m = min(step, n_ins - s0)
+        pos = (torch.rand(m, generator=g, device=dev, dtype=torch.float64) * (L - unit_len)).to(torch.int64)
+        fam = torch.randint(0, n_families, (m,), generator=g, device=dev)
+        unit = cons[fam]
+        hit = torch.rand((m, unit_len), generator=g, device=dev) < divergence
+        delta = torch.randint(1, 4, (m, unit_len), generator=g, device=dev, dtype=torch.uint8)
+        unit = torch.where(hit, (unit + delta) & 3, unit)
+        rc = torch.rand(m, generator=g, device=dev) < 0.5
+        unit = torch.where(rc[:, None], 3 - unit.flip(1), unit)
+        fwd[(pos[:, None] + ar[None, :]).view(-1)] = unit.reshape(-1)
+    return fwd
+
+
 def simulate_reads(fwd: torch.Tensor, n_reads: int, read_len: int, err: float, seed: int,
                    n_frac: float = 0.0, paired: bool = False, insert_mean: float = 400.0,
                    insert_sd: float = 50.0) -> torch.Tensor:
