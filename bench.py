@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-repeat-filter", action="store_true", help="do not build / use the repeat filter of the re-seeding pass (DESIGN.md section 10)")
     ap.add_argument("--rf-kmer", type=int, default=0)
     ap.add_argument("--rf-log2-bits", type=int, default=0)
+    ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: do not pin each rank to the CPUs local to its GPU")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap[:reuse[:l2_mode]]]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
@@ -167,6 +168,30 @@ def emit(line: str):
     out.flush()
 
 
+def bind_near_gpu(local):
+    """Multi-GPU runs: pin this rank (and the pinned host memory it is about to allocate) to the CPUs NVML reports as local
+    to its GPU.  Without it the ranks of the far socket push their 0.9 GB per step across the socket interconnect and
+    the end-to-end leg of all ranks together stalls at ~100 GB/s.  Returns the CPU list or None."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1} & set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception as e:       # binding is an optimisation, never a requirement
+        log("cpu binding skipped:", repr(e))
+    return None
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -191,6 +216,7 @@ def main():
     from oracle.binding import SeedOpt as OSeedOpt
     sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    cpu_binding = bind_near_gpu(local) if (world > 1 and args.impl == "ours" and not args.no_bind) else None
     workload = (f"{args.ref_bp / 1e9:.2f} Gbp synthetic reference ({args.contigs} contigs{', %.0f%% interspersed 300 bp repeat families' % (100 * args.repeat_frac) if args.repeat_frac > 0 else ''}), "
                 f"{args.reads // 2} simulated {args.read_len}bp read pairs ({args.reads} reads) per GPU per step, "
                 f"{args.err:.0%} substitutions, -k 19 -r 1.5 re-seeding on")
@@ -303,7 +329,7 @@ def main():
         parity = {"reads_checked": ns, "bit_exact": bool(ok), "checker": "oracle/liboracle.so"}
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU intervals differ from the oracle on the bench workload")
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:       # the CPU baseline is a single-GPU-run figure (it would idle the other ranks)
             eng, kind = cpu_engine(ixh)
             probe = cpu_time(eng, seq, offs, min(n, 20_000), ncores, OSeedOpt())
             m = min(n, max(20_000, int(probe["reads_per_s"] * args.cpu_seconds)))
@@ -594,7 +620,7 @@ def main():
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "intervals_per_step_per_gpu": int(total), "overflow_reads": int(overflow), "index_build_s": t_index,
             "blocks_per_sm": g.get_param("blocks_per_sm"), "l2_hot_min_intv": g.get_param("l2_hot_min_intv"),
-            "repeat_filter": rf_info,
+            "repeat_filter": rf_info, "cpu_binding": ("%d cpus local to the GPU (NVML): %d..%d" % (len(cpu_binding), cpu_binding[0], cpu_binding[-1])) if cpu_binding else None,
             "fast_path": dict(fast_info, escaped_reads_per_step=int(escaped), blocks_per_sm=g.get_param("fast_blocks_per_sm")) if fast_info else None,
             "device_ms_per_step": float(np.mean(dev_ms)),
         }
