@@ -4,7 +4,7 @@
 #include "smem_repeat.cuh"
 
 enum { MODE_COLLECT = 0, MODE_SMEM1 = 1, MODE_TRACE = 2 };   // TRACE: COLLECT's walk, but every bwt_smem1 call's raw list is kept
-// hot phases first: the main loop only ever extends in PH_FWD / PH_BWD
+// hot phases first: the main loop only ever extends in PH_FWD / PH_BWD / PH_SPEC
 enum { PH_FWD = 0, PH_BWD = 1, PH_SPEC = 2 /* backward walk of the longest candidate alone */, PH_IDLE = 3, PH_NEED_READ = 4, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
 
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index (TRACE: step*2 + pass) rides in info bits 48..63
