@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--fast-slots", type=int, default=0)
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="smem_gpu_set_param on the device-resident handle (repeatable)")
     ap.add_argument("--no-repeat-filter", action="store_true", help="do not build / use the repeat filter of the re-seeding pass (DESIGN.md section 10)")
+    ap.add_argument("--text-index", action="store_true", help="also build the unique-walk tables (2-bit text, full SA, inverse SA: 16 bytes per text position) and seed with them (DESIGN.md section 10)")
     ap.add_argument("--rf-kmer", type=int, default=0)
     ap.add_argument("--rf-log2-bits", type=int, default=0)
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: do not pin each rank to the CPUs local to its GPU")
@@ -130,13 +131,13 @@ def make_workload(args, rank, device):
     fwd = sy.make_reference(args.ref_bp, 13, device)
     if args.repeat_frac > 0:
         fwd = sy.add_repeat_families(fwd, args.repeat_frac, 17)
-    ix = fm.build_index(fwd, sa_intv=32 if getattr(args, 'seeds', False) else 0)
+    ix = fm.build_index(fwd, sa_intv=32 if (getattr(args, 'seeds', False) or getattr(args, 'text_index', False)) else 0)
     torch.cuda.synchronize()
     t_index = time.time() - t0
     reads = sy.simulate_reads(fwd, args.reads, args.read_len, args.err, seed=1000 + rank, paired=True)
     seq, offs = sy.to_batch(reads)
     sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
-    pac = sg.pack_pac(fwd) if (args.fast or not args.no_repeat_filter) else None          # the reference's .pac layout of the forward text
+    pac = sg.pack_pac(fwd) if (args.fast or args.text_index or not args.no_repeat_filter) else None          # the reference's .pac layout of the forward text
     del fwd, reads
     torch.cuda.empty_cache()
     return ix, seq, offs, t_index, pac
@@ -272,6 +273,14 @@ def main():
         rf_info = {"kmer": g.get_param("rf_kmer"), "log2_bits": g.get_param("rf_log2_bits"), "bytes": 1 << (g.get_param("rf_log2_bits") - 3),
                    "build_s": round(time.time() - tb0, 3)}
         log("repeat filter:", rf_info)
+    uw_info = None
+    if pac is not None and args.text_index:
+        torch.cuda.synchronize()
+        tb0 = time.time()
+        g.upload_sa(ix)
+        g.build_text_index((pac, args.ref_bp))
+        uw_info = {"bytes": 16 * (int(ix.seq_len) + 4) + int(ix.seq_len) // 4, "build_s": round(time.time() - tb0, 3)}
+        log("unique-walk tables:", uw_info)
     if pac is not None and args.fast:
         import ctypes as C
         DL = args.direct_levels
@@ -620,7 +629,7 @@ def main():
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "intervals_per_step_per_gpu": int(total), "overflow_reads": int(overflow), "index_build_s": t_index,
             "blocks_per_sm": g.get_param("blocks_per_sm"), "l2_hot_min_intv": g.get_param("l2_hot_min_intv"),
-            "repeat_filter": rf_info, "cpu_binding": ("%d cpus local to the GPU (NVML): %d..%d" % (len(cpu_binding), cpu_binding[0], cpu_binding[-1])) if cpu_binding else None,
+            "repeat_filter": rf_info, "unique_walk_tables": uw_info, "cpu_binding": ("%d cpus local to the GPU (NVML): %d..%d" % (len(cpu_binding), cpu_binding[0], cpu_binding[-1])) if cpu_binding else None,
             "fast_path": dict(fast_info, escaped_reads_per_step=int(escaped), blocks_per_sm=g.get_param("fast_blocks_per_sm")) if fast_info else None,
             "device_ms_per_step": float(np.mean(dev_ms)),
         }

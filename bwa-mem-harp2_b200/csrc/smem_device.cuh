@@ -61,6 +61,9 @@ struct SeedParams {
 	// repeat filter (smem_repeat.cuh): bit hash(w) is set for every rf_k-mer w that occurs more than once in the indexed text
 	const u32 *qflags;       // per read, per 32 window starts: bit set = that rf_k-mer window is not vouched for (pack_reads_kernel); nullptr = no filter
 	int rf_k;                // k-mer length (<= 32)
+	// unique-walk tables (smem_kernels.cuh PH_UW_*): 2-bit text (32 bases per 64-bit word, first base in the top bits), the
+	// full suffix array (row -> text position) and its inverse; nullptr = off
+	const uint4 *uw_text; const u64 *uw_fsa, *uw_isa;
 	int spec_walk;           // 1 = pass-1 calls that directly follow another walk their longest candidate back alone first (PH_SPEC)
 	int count_skips;         // debug: status[6] counts the re-seeding passes the filter proved void
 	u64 hot_min_intv;        // 0 = off; occ blocks of intervals >= this size are "hot" (shallow levels, re-used across reads)
@@ -178,14 +181,15 @@ struct Ext { u64 a, b, s; };   // a = x[!is_back], b = x[is_back], s = x[2]
 // block as their predecessor, so the gather is skipped when the block number repeats (REUSE).
 template <bool REUSE>
 __device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 pol_hot, u64 pol_cold,
-                                           u32 (&w)[8], u32 (&v)[8], u64 &last_bk, u64 &last_bl)
+                                           u32 (&w)[8], u32 (&v)[8], u64 &last_bk, u64 &last_bl, const uint4 *alt = nullptr)
 {
 	const u64 k = a - 1, l = a - 1 + s;
 	const u64 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);   // '$' is not stored (bwt.c:194)
 	const u64 bk = kk >> 7, bl = ll >> 7;
 	const bool same = bk == bl;
-	const bool need_k = !REUSE || bk != last_bk, need_l = !same && (!REUSE || bl != last_bl);
-	const uint4 *pk = ix.blk + bk * 4 + half * 2, *pl = ix.blk + bl * 4 + half * 2;
+	const bool need_k = !REUSE || alt || bk != last_bk, need_l = !same && (!REUSE || bl != last_bl);
+	// `alt` (unique-walk phases): this lane's gather goes to another table instead; the pair rides on the interval (1,1,1)
+	const uint4 *pk = alt ? alt : ix.blk + bk * 4 + half * 2, *pl = ix.blk + bl * 4 + half * 2;
 	if (hot_min) {                       // uniform branch; ONE load site, the policy is a per-lane operand
 		const u64 policy = s >= hot_min ? pol_hot : pol_cold;
 		if (need_k) ld_sector_hot(w, pk, policy);
@@ -198,7 +202,7 @@ __device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64
 #pragma unroll
 		for (int j = 0; j < 8; ++j) v[j] = w[j];
 	}
-	if (REUSE) { last_bk = bk; last_bl = bl; }
+	if (REUSE) { last_bk = alt ? ~0ull : bk; last_bl = bl; }
 	// symbols 0..kk&127 (inclusive) of the block count; this lane owns symbols 64*half .. 64*half+63
 	const int rk = min(max((int)(kk & 127) + 1 - 64 * half, 0), 64), rl = min(max((int)(ll & 127) + 1 - 64 * half, 0), 64);
 	u32 ck = occ_half(w, rk), cl = occ_half(v, rl);

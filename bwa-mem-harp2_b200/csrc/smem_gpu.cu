@@ -42,6 +42,8 @@ struct DeviceCtx {
 	int64_t escaped = 0;
 	// repeat filter of the re-seeding pass (smem_repeat.cuh)
 	u32 *d_rf = nullptr; bool owns_rf = true; int rf_k = 0, rf_log2 = 0;
+	// unique-walk tables (PH_UW_* of seed_kernel): 2-bit text, full suffix array, inverse suffix array
+	u64 *d_uw_text = nullptr, *d_fsa = nullptr, *d_isa = nullptr; bool owns_uw = true; u64 uw_text_len = 0;
 	u64 rf_text_len = 0;             // length of the text the filter was built from: it is only used with an index of that seq_len
 	int64_t pass2_skipped = 0;
 	uint64_t turn_epoch = 0;         // epoch of the last run in which this lane took part in the kernel turn
@@ -120,6 +122,7 @@ struct smem_gpu {
 	int64_t hot_min_intv = 0;
 	int l2_mode = 0;                 // see SeedParams::l2_mode
 	int repeat_filter = 1;           // use the repeat filter (if built) to skip void re-seeding passes in MODE_COLLECT
+	int unique_walk = 1;             // use the unique-walk tables if smem_gpu_build_text_index built them
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
 	int probe_variant = 0;
@@ -216,6 +219,7 @@ void ctx_free(DeviceCtx &d)
 	if (d.owns_tables && d.has_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
 	cudaFree(d.d_esc);
 	if (d.owns_rf) cudaFree(d.d_rf);
+	if (d.owns_uw) { cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
 	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
 	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
 	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
@@ -341,6 +345,45 @@ int ctx_build_tables(DeviceCtx &d, const uint8_t *pac, int64_t l_pac, int src_de
 	cudaFree(tw); cudaFree(cntK); cudaFree(bsum);
 	d.ft.cnt = cnt; d.ft.cum = cum; d.ft.pyr = pyr; d.ft.top = top; d.ft.DL = DL;
 	d.has_tables = true;
+	return 0;
+}
+
+// Unique-walk tables: the 2-bit text in the layout pack_text_kernel produces, and the full suffix array / inverse suffix
+// array expanded from the samples on the device (fsa_build_kernel).  8 bytes per row each.
+int ctx_build_text_index(DeviceCtx &d, const uint8_t *pac, long long l_pac, int src_device)
+{
+	CK(cudaSetDevice(d.dev));
+	if (d.owns_uw) { cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
+	d.d_uw_text = d.d_fsa = d.d_isa = nullptr; d.owns_uw = true; d.uw_text_len = 0;
+	const long long n = 2 * l_pac;
+	const size_t pac_bytes = (size_t)((l_pac + 3) / 4);
+	uint8_t *d_pac = nullptr;
+	u64 *tw = nullptr, *fsa = nullptr, *isa = nullptr;
+	auto fail = [&](int rc) { cudaFree(d_pac == pac ? nullptr : d_pac); cudaFree(tw); cudaFree(fsa); cudaFree(isa); return rc; };
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); d.err = b_; return fail(e_ == cudaErrorMemoryAllocation ? SMEM_GPU_E_NOMEM : SMEM_GPU_E_CUDA); } } while (0)
+	if (src_device == d.dev) d_pac = const_cast<uint8_t *>(pac);
+	else {
+		CKT(cudaMalloc((void **)&d_pac, pac_bytes));
+		if (src_device < 0) CKT(cudaMemcpyAsync(d_pac, pac, pac_bytes, cudaMemcpyHostToDevice, d.stream));
+		else CKT(cudaMemcpyPeerAsync(d_pac, d.dev, pac, src_device, pac_bytes, d.stream));
+	}
+	const long long n_words = ((n + 31) / 32 + 16 + 3) / 4 * 4;          // whole 32-byte sectors, two spare ones past the end
+	CKT(cudaMalloc((void **)&tw, (size_t)n_words * 8));
+	CKT(cudaMalloc((void **)&fsa, (size_t)(n + 4) * 8));
+	CKT(cudaMalloc((void **)&isa, (size_t)(n + 4) * 8));
+	pack_text_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, tw, n_words);
+	CKT(cudaGetLastError());
+	CKT(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+	const long long n_sa = (long long)d.n_sa;
+	const int grid = (int)std::min<long long>((long long)d.sm_count * 8, (n_sa + 63) / 64);
+	fsa_build_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, n_sa, fsa, isa, d.d_status);
+	CKT(cudaGetLastError());
+	CKT(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CKT(stream_wait(d));
+#undef CKT
+	if (d_pac != pac) cudaFree(d_pac);
+	if (d.h_status[2] != 0) { d.err = "suffix-array walk did not terminate (corrupt index or samples?)"; return fail(SMEM_GPU_E_INTERNAL); }
+	d.d_uw_text = tw; d.d_fsa = fsa; d.d_isa = isa; d.uw_text_len = (u64)n;
 	return 0;
 }
 
@@ -607,6 +650,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	p.l2_mode = h.l2_mode;
 	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf && d.rf_text_len == d.ix.seq_len;   // (a filter of another text is ignored)
 	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips; p.spec_walk = h.spec_walk;
+	const bool use_uw = mode != MODE_SMEM1 && h.unique_walk && d.d_fsa && d.uw_text_len == d.ix.seq_len;
+	p.uw_text = use_uw ? reinterpret_cast<const uint4 *>(d.d_uw_text) : nullptr; p.uw_fsa = d.d_fsa; p.uw_isa = d.d_isa;
 	{
 		const size_t bytes_q = (size_t)d.read_cap * q_stride, bytes = bytes_q + (size_t)d.read_cap * (q_stride >> 4) * 4;   // packed reads | window flags
 		if (bytes > d.qpack_bytes) {
@@ -1175,6 +1220,8 @@ static int upload_all(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device
 	for (auto &d : h->devs) {
 		if (d.d_rf && d.owns_rf) { cudaSetDevice(d.dev); cudaFree(d.d_rf); }
 		d.d_rf = nullptr; d.owns_rf = true; d.rf_k = d.rf_log2 = 0; d.rf_text_len = 0;
+		if (d.owns_uw) { cudaSetDevice(d.dev); cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
+		d.d_uw_text = d.d_fsa = d.d_isa = nullptr; d.owns_uw = true; d.uw_text_len = 0;
 	}
 	int rc = for_each_device(h, [&](DeviceCtx &d) {
 		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
@@ -1221,8 +1268,40 @@ int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src)
 		d.ft = o->ft; d.has_tables = o->has_tables; d.owns_tables = false;
 		if (d.d_rf && d.owns_rf) cudaFree(d.d_rf);
 		d.d_rf = o->d_rf; d.owns_rf = false; d.rf_k = o->rf_k; d.rf_log2 = o->rf_log2; d.rf_text_len = o->rf_text_len;
+		if (d.owns_uw) { cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
+		d.d_uw_text = o->d_uw_text; d.d_fsa = o->d_fsa; d.d_isa = o->d_isa; d.owns_uw = false; d.uw_text_len = o->uw_text_len;
 	}
 	return 0;
+}
+
+int smem_gpu_build_text_index(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device)
+{
+	if (!h || !pac || l_pac < 32) return SMEM_GPU_E_ARG;
+	for (auto &d : h->devs) {
+		if (!d.has_index || d.sa_shift < 0) { h->err = "upload the index and the suffix-array samples first"; return SMEM_GPU_E_NOINDEX; }
+		if (d.ix.seq_len != (u64)(2 * l_pac)) { h->err = "2 * l_pac differs from the seq_len of the uploaded index"; return SMEM_GPU_E_ARG; }
+	}
+	int rc = for_each_device(h, [&](DeviceCtx &d) {
+		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
+		return ctx_build_text_index(d, pac, l_pac, src_device);
+	});
+	if (rc) return rc;
+	for (auto &d : h->devs)
+		for (auto &o : h->devs) {
+			if (&o == &d) break;
+			if (o.dev == d.dev) { d.d_uw_text = o.d_uw_text; d.d_fsa = o.d_fsa; d.d_isa = o.d_isa; d.owns_uw = false; d.uw_text_len = o.uw_text_len; break; }
+		}
+	return 0;
+}
+
+int smem_gpu_get_text_index(smem_gpu_t *h, int which, uint64_t *out, int64_t n_out)
+{
+	if (!h || !out || which < 0 || which > 1) return SMEM_GPU_E_ARG;
+	DeviceCtx &d = h->devs[0];
+	if (!d.d_fsa) { h->err = "no text index built"; return SMEM_GPU_E_NOINDEX; }
+	if (n_out != (int64_t)d.uw_text_len + 1) return SMEM_GPU_E_ARG;
+	cudaSetDevice(d.dev);
+	return cudaMemcpy(out, which ? d.d_isa : d.d_fsa, (size_t)n_out * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : SMEM_GPU_E_CUDA;
 }
 
 int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int kmer_len, int log2_bits)
@@ -1454,6 +1533,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "repeat_filter")) { h->repeat_filter = v != 0; return 0; }
 	if (!strcmp(name, "count_skips")) { h->count_skips = v != 0; return 0; }
 	if (!strcmp(name, "spec_walk")) { h->spec_walk = v != 0; return 0; }
+	if (!strcmp(name, "unique_walk")) { h->unique_walk = v != 0; return 0; }
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
@@ -1485,6 +1565,8 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "repeat_filter")) return h->repeat_filter;
 	if (!strcmp(name, "count_skips")) return h->count_skips;
 	if (!strcmp(name, "spec_walk")) return h->spec_walk;
+	if (!strcmp(name, "unique_walk")) return h->unique_walk;
+	if (!strcmp(name, "has_text_index")) return h->devs[0].d_fsa ? 1 : 0;
 	if (!strcmp(name, "blocking_sync")) return g_blocking_sync ? 1 : 0;
 	if (!strcmp(name, "has_repeat_filter")) return h->devs[0].d_rf ? 1 : 0;
 	if (!strcmp(name, "rf_kmer")) return h->devs[0].rf_k;

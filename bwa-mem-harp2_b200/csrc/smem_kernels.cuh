@@ -5,7 +5,8 @@
 
 enum { MODE_COLLECT = 0, MODE_SMEM1 = 1, MODE_TRACE = 2 };   // TRACE: COLLECT's walk, but every bwt_smem1 call's raw list is kept
 // hot phases first: the main loop only ever extends in PH_FWD / PH_BWD / PH_SPEC
-enum { PH_FWD = 0, PH_BWD = 1, PH_SPEC = 2 /* backward walk of the longest candidate alone */, PH_IDLE = 3, PH_NEED_READ = 4, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
+enum { PH_FWD = 0, PH_BWD = 1, PH_SPEC = 2 /* backward walk of the longest candidate alone */,
+       PH_UW_SA = 3, PH_UW_TEXT = 4, PH_UW_ISA = 5 /* unique forward walk by text comparison */, PH_IDLE = 6, PH_NEED_READ = 7, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
 
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index (TRACE: step*2 + pass) rides in info bits 48..63
 #define AUX_SHIFT 16         // ... and, in TRACE mode, bwt_smem1's return value in bits 16..31 (query positions are < 2^16)
@@ -42,6 +43,7 @@ template <int MODE, int MIN_BLOCKS, bool WIDE, bool REUSE /* keep the last occ s
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
 	const bool SPEC = MODE != MODE_SMEM1 && p.spec_walk;     // speculative longest-only backward walk (PH_SPEC)
+	const bool UW = p.uw_text != nullptr;                      // unique forward walks by text comparison (PH_UW_*)
 	typedef BEntry<WIDE> BE;
 	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, half = lane & 1;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				b = p.ix.L2[c0] + 1;
 				s = p.ix.L2[c0 + 1] - p.ix.L2[c0];
 				end = (u32)(x + 1);
-				i = x + 1; n_curr = 0;
+				i = x + 1; n_curr = 0; j = 0;
 				sts_u16(sc + CS_NMEM, 0); sts_u16(sc + CS_MAXLEN, 0); sts_u16(sc + CS_MAXSTART, 0); sts_u16(sc + CS_MAXEND, 0);
 				sts_i32(sc + CS_MAXS_LO, 0); sts_i32(sc + CS_MAXS_HI, 0);
 				guard = 2 * (len + 2) * (len + 2) + 64;   // > every extend one bwt_smem1 can issue
@@ -302,13 +304,78 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 
 		// ============================================================== one bwt_extend per pair (warp converged)
 		// idle pairs ride along on the interval (1,1,1): its block is hot in L2 and the result is dropped
-		const Ext ok = extend_pair<REUSE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, last_bk, last_bl);
+		// Unique forward walk (PH_UW_*): once the forward sweep of a pass-1 call has extended an interval of size 1 three times,
+		// the rest of the walk is a comparison of the read with the text at the pattern's only occurrence: text position
+		// t = SA[x0] (one gather), the text itself (one gather of 2 x 128 bases), and the reverse-strand row of the longer
+		// pattern = ISA[n - t - length] (one gather; T = forward + reverse complement, so rc(P) sits mirrored); x0 and the size
+		// stay.  The gathers go through extend_pair's own load (same registers); the walk hands back to PH_FWD, whose next
+		// extend fails like the reference's last one.  t rides in last_s, which the forward sweep does not use.
+		const uint4 *alt = nullptr;
+		if (UW && phase >= PH_UW_SA && phase <= PH_UW_ISA) {
+			const u64 plen = (u64)(end - (u32)lds_u16(sc + CS_X));
+			u64 byte;
+			if (phase == PH_UW_SA) byte = (u64)p.uw_fsa + 8 * b;
+			else if (phase == PH_UW_ISA) byte = (u64)p.uw_isa + 8 * (p.ix.seq_len - (last_s + plen));
+			else byte = (u64)p.uw_text + 32 * (((last_s + plen) >> 7) + (u64)half);
+			alt = reinterpret_cast<const uint4 *>(byte & ~31ull);
+		}
+		const Ext ok = extend_pair<REUSE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, last_bk, last_bl, alt);
 		if (phase == PH_IDLE) continue;
 		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 
 		// ============================================================== consume the result, set up the next extend
 		// (forward: bwt.c:794-799, backward: bwt.c:813-824; written once for both so that the warp does not
 		//  run two divergent copies of the push / advance code)
+		if (UW && alt) {
+			const u32 pm2 = 3u << (lane & ~1);
+			if (phase == PH_UW_TEXT) {
+				const int x0q = lds_u16(sc + CS_X);
+				const u64 tp = last_s + (u64)(end - (u32)x0q);          // text position that faces read base i
+				const u64 sec0 = tp >> 7, mysec = sec0 + (u64)half;
+				const u64 lim = min(min(tp + (u64)(len - i), p.ix.seq_len), (sec0 + 2) << 7);   // compare [tp, lim)
+				const u64 rs = max(tp, mysec << 7), re = min((mysec + 1) << 7, lim);
+				u32 cnt = 0;
+				bool full = true;
+				if (re > rs) {
+#pragma unroll
+					for (int wq = 0; wq < 4; ++wq) {
+						const u64 word = (u64)blk_k[2 * wq] | ((u64)blk_k[2 * wq + 1] << 32);
+						const u64 w0 = (mysec << 7) + 32 * wq;                      // text position of the word's first base
+						if (full && re > w0 && rs < w0 + 32) {
+							const int r0 = rs > w0 ? (int)(rs - w0) : 0, r1 = re < w0 + 32 ? (int)(re - w0) : 32;
+							for (int r = r0; r < r1; ++r) {
+								const u32 tb = (u32)(word >> (62 - 2 * r)) & 3u;
+								const u32 rb = qbase(sq, i + (int)(w0 + r - tp));
+								if (rb != tb) { full = false; break; }
+								++cnt;
+							}
+						}
+					}
+				}
+				const u32 c0 = __shfl_sync(pm2, cnt, lane & ~1), c1 = __shfl_sync(pm2, cnt, lane | 1);
+				const bool f0 = __shfl_sync(pm2, (int)full, lane & ~1) != 0, f1 = __shfl_sync(pm2, (int)full, lane | 1) != 0;
+				const u32 m = f0 ? c0 + c1 : c0;
+				i += (int)m; end = (u32)i;
+				// ran through the whole 256-base window without a verdict: another round of text, else the inverse SA
+				if (!(f0 && f1 && tp + m == ((sec0 + 2) << 7) && i < len && tp + m < p.ix.seq_len)) phase = PH_UW_ISA;
+			} else {
+				const u64 byte = phase == PH_UW_SA ? (u64)p.uw_fsa + 8 * b
+				                                   : (u64)p.uw_isa + 8 * (p.ix.seq_len - (last_s + (u64)(end - (u32)lds_u16(sc + CS_X))));
+				const u32 q4 = (u32)(byte & 31u) >> 3;
+				u32 lo = blk_k[0], hi = blk_k[1];
+				if (q4 == 1) { lo = blk_k[2]; hi = blk_k[3]; } else if (q4 == 2) { lo = blk_k[4]; hi = blk_k[5]; } else if (q4 == 3) { lo = blk_k[6]; hi = blk_k[7]; }
+				const u64 val = (u64)lo | ((u64)hi << 32);
+				if (phase == PH_UW_SA) { last_s = val; phase = PH_UW_TEXT; }
+				else {
+					a = val;                                         // x[1] of the longer pattern; x[0] (b) and the size stay
+					j = 0;
+					const u32 qv = i < len ? qbase(sq, i) : 4u;
+					if (qv > 3) phase = PH_FWD_END;
+					else { c = 3 - (int)qv; phase = PH_FWD; }
+				}
+			}
+			continue;
+		}
 		if (SPEC && phase == PH_SPEC) {
 			if (ok.s < min_intv) {                               // died before the limit: the shorter candidates matter after all
 				i = lds_u16(sc + CS_X) - 1; j = 0; n_prev = n0; n_curr = 0;
@@ -343,6 +410,10 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			const u32 qv = i < len ? qbase(sq, i) : 4u;
 			if (qv > 3) phase = PH_FWD_END;
 			else c = 3 - (int)qv;
+			if (UW) {
+				j = (s == 1 && min_intv == 1) ? j + 1 : 0;           // consecutive extends of a unique interval
+				if (j >= 3 && phase == PH_FWD && len - i >= 8) { phase = PH_UW_SA; a = 1; }   // (a is rebuilt from the inverse SA)
+			}
 		} else {
 			if (++j == n_prev) {                             // bwt.c:826-827
 				if (n_curr == 0) { phase = PH_CALL_DONE; continue; }
@@ -603,6 +674,39 @@ __global__ void __launch_bounds__(128) sa_kernel(const DevIndex ix, const u64 *_
 		if (!__any_sync(FULL_MASK, have)) break;
 		const u64 kn = inv_psi_pair(ix, k, half, lane);
 		if (have) { k = kn; if (++steps > (1ull << 24)) { if (!half) atomicAdd(&status[2], 1); k = 0; } }   // guard: corrupt index
+	}
+}
+
+// Full suffix array and its inverse from the samples (unique-walk tables, PH_UW_* of seed_kernel): every sampled row k * intv
+// starts a walk r -> invPsi(r), p -> p - 1 that ends at the next sampled row; the walks partition the rows, so every row
+// r gets fsa[r] = its text position and isa[position] = r exactly once.  Row 0 (the '$' suffix, sa[0] = -1 in the
+// reference, bwt.c:97) is given position seq_len.  Persistent lane pairs, one occ block per step like sa_kernel.
+__global__ void __launch_bounds__(128) fsa_build_kernel(const DevIndex ix, const u64 *__restrict__ sa, int sa_shift, long long n_sa,
+                                                        u64 *__restrict__ fsa, u64 *__restrict__ isa, int *__restrict__ status)
+{
+	const int lane = threadIdx.x & 31, half = lane & 1;
+	const long long npairs = ((long long)gridDim.x * blockDim.x) >> 1;
+	long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+	const u64 mask = (1ull << sa_shift) - 1;
+	bool have = false;
+	u64 r = 0, pos = 0, steps = 0;
+	for (;;) {
+		if (!have && q < n_sa) {
+			r = (u64)q << sa_shift; pos = q ? sa[q] : ix.seq_len; q += npairs;
+			if (!half) { fsa[r] = pos; isa[pos] = r; }
+			have = true; steps = 0;
+		}
+		__syncwarp();
+		if (!__any_sync(FULL_MASK, have)) break;
+		const u64 rn = inv_psi_pair(ix, r, half, lane);
+		if (have) {
+			r = rn; pos -= 1;
+			if ((r & mask) == 0) have = false;
+			else {
+				if (!half) { fsa[r] = pos; isa[pos] = r; }
+				if (++steps > (1ull << 24)) { if (!half) atomicAdd(&status[2], 1); have = false; }   // guard: corrupt index
+			}
+		}
 	}
 }
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_chains", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_kmer_tables", "smem_gpu_get_kmer_table", "smem_gpu_build_repeat_filter", "smem_gpu_get_repeat_filter", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_chains", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_kmer_tables", "smem_gpu_get_kmer_table", "smem_gpu_build_repeat_filter", "smem_gpu_get_repeat_filter", "smem_gpu_build_text_index", "smem_gpu_get_text_index", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -220,6 +220,29 @@ class SmemGpu:
         else:
             a = np.ascontiguousarray(pac.numpy() if hasattr(pac, "numpy") else pac, np.uint8)
             self._check(self.lib.smem_gpu_build_repeat_filter(self.h, C.c_void_p(a.ctypes.data), C.c_int64(l_pac), C.c_int(-1), C.c_int(kmer_len), C.c_int(log2_bits)))
+
+    def build_text_index(self, fwd):
+        """Unique-walk tables (smem_gpu_build_text_index): 2-bit text + full SA + inverse SA; needs upload_index and upload_sa.
+        ``fwd`` as for :meth:`build_repeat_filter`."""
+        if isinstance(fwd, tuple):
+            pac, l_pac = fwd
+        else:
+            pac = pack_pac(fwd)
+            l_pac = int(fwd.numel() if hasattr(fwd, "numel") else fwd.size)
+        if hasattr(pac, "is_cuda") and pac.is_cuda:
+            import torch
+            torch.cuda.synchronize(pac.device)
+            self._check(self.lib.smem_gpu_build_text_index(self.h, C.c_void_p(pac.data_ptr()), C.c_int64(l_pac), C.c_int(pac.device.index or 0)))
+        else:
+            a = np.ascontiguousarray(pac.numpy() if hasattr(pac, "numpy") else pac, np.uint8)
+            self._check(self.lib.smem_gpu_build_text_index(self.h, C.c_void_p(a.ctypes.data), C.c_int64(l_pac), C.c_int(-1)))
+        self._text_len = 2 * l_pac
+
+    def text_index(self, which: int) -> np.ndarray:
+        """Test hook: 0 = full suffix array, 1 = inverse (seq_len + 1 entries)."""
+        out = np.empty(self._text_len + 1, np.uint64)
+        self._check(self.lib.smem_gpu_get_text_index(self.h, C.c_int(which), C.c_void_p(out.ctypes.data), C.c_int64(out.size)))
+        return out
 
     def repeat_filter_bits(self) -> np.ndarray:
         """Test hook: the bit table of device 0 as uint32 words."""

@@ -117,6 +117,18 @@ int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pa
 /* Test hook: the bit table of device 0 (2^(log2_bits - 5) uint32 words; get_param "rf_kmer" / "rf_log2_bits"). */
 int smem_gpu_get_repeat_filter(smem_gpu_t *h, uint32_t *out, int64_t out_words);
 
+/* Unique-walk tables -- optional accelerator tables of smem_gpu_collect / smem_gpu_trace.
+ * Once the forward sweep of bwt_smem1 (bwt.c:790-806) holds an interval of size 1, every further bwt_extend asks whether
+ * the text continues like the read at the pattern's ONLY occurrence.  With the 2-bit text, the full suffix array and its
+ * inverse in HBM (8 bytes per row each: 100 GB at 3.1 Gbp) that walk is one suffix-array lookup, one comparison of the
+ * read with the text and one inverse lookup for the reverse-strand row (T = forward + reverse complement, so the reverse
+ * complement of a pattern at t sits at seq_len - t - length); x[0] and the size do not change.  The tables are expanded on
+ * the device from the suffix-array samples (smem_gpu_upload_sa first) and `pac` / l_pac (as for
+ * smem_gpu_build_repeat_filter); results never depend on them ("unique_walk" switches their use off and on). */
+int smem_gpu_build_text_index(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device);
+/* Test hook: which = 0 full suffix array, 1 inverse; seq_len + 1 entries of device 0. */
+int smem_gpu_get_text_index(smem_gpu_t *h, int which, uint64_t *out, int64_t n_out);
+
 /* Whole-read seeding == the enumeration loop of mem_insert_seed (bwamem.c:453-460):
  * smem_next2 (bwamem.c:244-305: pass 1, 0.7.8 re-seed of the longest SMEM, ordered merge) to
  * exhaustion for every read.  step_out (nullable) receives, per interval, the index of the

@@ -197,3 +197,57 @@ def test_gpu_repeat_filter_of_another_text_is_refused_or_ignored(worlds, synth, 
     want = Oracle(ix2).collect(seq, offs, SeedOpt(), nthreads=2)
     assert np.array_equal(got["intv"], want["intv"]) and np.array_equal(got["read_off"], want["read_off"])
     g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_text_index_and_unique_walk(fm, synth):
+    """Unique-walk tables (full SA / inverse from the samples on the device) against the oracle's bwt_sa, and seeding with
+    the walk on against the oracle: random + repeat-rich text, both strands, junction, N, ragged lengths, TRACE."""
+    sg = pkg("smem_gpu")
+    for name, ref in (("random", synth.make_reference(300_000, 5)), ("repeats", repeat_rich_reference(200_000, 8))):
+        ix = fm.build_index(ref, sa_intv=32)
+        o = Oracle(ix)
+        g = sg.SmemGpu(max_batch_reads=4096, max_read_len=256, devices=[0, 0])
+        g.upload_index(ix); g.upload_sa(ix)
+        g.build_text_index(ref)
+        n = ix.seq_len
+        fsa, isa = g.text_index(0), g.text_index(1)
+        rows = np.arange(1, n + 1, dtype=np.uint64)
+        assert np.array_equal(fsa[1:], o.sa(ix, rows))                    # every row but the '$' row
+        assert int(fsa[0]) == n and int(isa[n]) == 0
+        assert np.array_equal(isa[fsa[1:].astype(np.int64)], rows)        # inverse
+        g.build_repeat_filter(ref, 13, 0)
+        r = ref.numpy()
+        T = np.concatenate([r, (3 - r)[::-1]])
+        rng = np.random.default_rng(4)
+        reads = [np.zeros(0, np.uint8)]
+        for ln in (7, 20, 33, 60, 101, 150, 255, 256):
+            for _ in range(8):
+                p = int(rng.integers(0, len(r) - ln)); q = r[p:p + ln].copy()
+                if rng.random() < 0.5:
+                    q = (3 - q)[::-1].copy()
+                if rng.random() < 0.5 and ln > 30:
+                    q[int(rng.integers(0, ln))] = (q[int(rng.integers(0, ln))] + 1) % 4
+                if rng.random() < 0.2 and ln > 30:
+                    q[int(rng.integers(0, ln))] = 4
+                reads.append(q)
+        for off in (-90, -40, -1, 0, 30):                                 # across the forward / reverse-complement junction
+            reads.append(T[len(r) + off - 100: len(r) + off + 100].copy())
+        reads.append(T[:180].copy()); reads.append(T[-180:].copy())       # the two ends of the text
+        seq1, offs1 = synth.to_batch(reads)
+        sets = [(seq1, offs1, SeedOpt())]
+        for rl, err, opt in SETS:
+            s_, o_ = synth.to_batch(synth.simulate_reads(ref, 2500, rl, err, seed=23, paired=True, n_frac=0.05))
+            sets.append((s_, o_, opt))
+        for seq, offs, opt in sets:
+            want = o.collect(seq, offs, opt, nthreads=4)
+            gopt = sg.SeedOpt(opt.min_seed_len, opt.split_factor, opt.split_width, opt.start_width)
+            got = g.collect(seq, offs, gopt)
+            for k in ("intv", "read_off", "step"):
+                assert np.array_equal(got[k], want[k]), (name, k)
+            tr = g.trace(seq, offs, gopt)
+            g.set_param("unique_walk", 0)
+            tr0 = g.trace(seq, offs, gopt)
+            g.set_param("unique_walk", 1)
+            assert all(np.array_equal(tr[k], tr0[k]) for k in tr0)
+        g.close()
