@@ -57,7 +57,8 @@ def parse():
     ap.add_argument("--fast-slots", type=int, default=0)
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="smem_gpu_set_param on the device-resident handle (repeatable)")
     ap.add_argument("--no-repeat-filter", action="store_true", help="do not build / use the repeat filter of the re-seeding pass (DESIGN.md section 10)")
-    ap.add_argument("--text-index", action="store_true", help="also build the unique-walk tables (2-bit text, full SA, inverse SA: 16 bytes per text position) and seed with them (DESIGN.md section 10)")
+    ap.add_argument("--no-text-index", action="store_true", help="do not build / use the unique-walk tables")
+    ap.add_argument("--text-index", action="store_true", help="(default when HBM has room) "also build the unique-walk tables (text at 4 bits per base, full SA, inverse SA: 16.5 bytes per text position) and seed with them")
     ap.add_argument("--rf-kmer", type=int, default=0)
     ap.add_argument("--rf-log2-bits", type=int, default=0)
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: do not pin each rank to the CPUs local to its GPU")
@@ -225,6 +226,16 @@ def main():
               "read_len": args.read_len, "l2": "inputs larger than L2 (index %.1f GB, reads %.0f MB)" %
               (args.ref_bp / 1e9, args.reads * args.read_len / 1e6), "parallelism": f"replicated index, reads sharded x{args.gpus}"}
 
+    # unique-walk tables: 16.5 bytes per text position next to the index; on unless told otherwise
+    # or the device is too small for them (results never depend on them)
+    uw_need = int(16.5 * 2 * args.ref_bp)
+    uw_room = torch.cuda.get_device_properties(device).total_memory - 8 * 2 * args.ref_bp - (24 << 30)   # index + builder scratch + results
+    if args.impl == "reference" or args.no_text_index or args.fast:
+        args.text_index = False
+    elif not args.text_index:
+        args.text_index = uw_need <= uw_room
+        if not args.text_index:
+            log(f"unique-walk tables skipped: {uw_need / 1e9:.0f} GB needed, {uw_room / 1e9:.0f} GB to spare on this device")
     log(f"rank {rank}/{world}: building workload ({args.ref_bp} bp)")
     ix, seq, offs, t_index, pac = make_workload(args, rank, device)
     log(f"index built on GPU in {t_index:.1f}s: seq_len={ix.seq_len} bwt_size={ix.bwt_size} primary={ix.primary}")
@@ -278,8 +289,11 @@ def main():
         torch.cuda.synchronize()
         tb0 = time.time()
         g.upload_sa(ix)
-        g.build_text_index((pac, args.ref_bp))
-        uw_info = {"bytes": 16 * (int(ix.seq_len) + 4) + int(ix.seq_len) // 4, "build_s": round(time.time() - tb0, 3)}
+        try:
+            g.build_text_index((pac, args.ref_bp))
+            uw_info = {"bytes": 16 * (int(ix.seq_len) + 4) + int(ix.seq_len) // 2, "build_s": round(time.time() - tb0, 3)}
+        except RuntimeError as e:           # optional tables: seeding runs without them (same results, FM extends instead)
+            uw_info = {"skipped": str(e)}
         log("unique-walk tables:", uw_info)
     if pac is not None and args.fast:
         import ctypes as C
@@ -323,14 +337,15 @@ def main():
             # what the kernel's two exact shortcuts leave of that work (oracle MODEL of them, exact window counts instead of
             # the device's hashed bit table): reported next to the algorithmic figure, which stays the reference algorithm's
             import ctypes as C
-            orc.lib.orc_set_skip_kmer(int(rf_info["kmer"])); orc.lib.orc_set_spec_walk(int(g.get_param("spec_walk")))
+            uw_on = bool(uw_info and "bytes" in uw_info and g.get_param("unique_walk"))
+            orc.lib.orc_set_skip_kmer(int(rf_info["kmer"])); orc.lib.orc_set_spec_walk(int(g.get_param("spec_walk"))); orc.lib.orc_set_unique_walk(int(uw_on))
             try:
                 s2 = orc.collect(seq[: int(offs[ns])], offs[: ns + 1], OSeedOpt(), nthreads=ncores, stats=True)["stats"]
             finally:
-                orc.lib.orc_set_skip_kmer(0); orc.lib.orc_set_spec_walk(0)
+                orc.lib.orc_set_skip_kmer(0); orc.lib.orc_set_spec_walk(0); orc.lib.orc_set_unique_walk(0)
             executed = {"extends_per_read": s2["extends"] / ns, "blocks_per_read": s2["blocks"] / ns,
                         "bytes_per_read": (64.0 * s2["blocks"] + 128.0 * ns + 32.0 * s2["intervals"]) / ns,
-                        "note": "same counting rule applied to the extends left after the repeat filter and the speculative walk (oracle model)"}
+                        "note": "same counting rule applied to the extends left after the repeat filter, the speculative walk and" + (" the unique walks, three gathers each" if uw_on else " (not built here) the unique walks") + " (oracle model)"}
             log("executed work per read with the shortcuts (oracle model):", executed)
         got = g.collect(seq[: int(offs[ns])], offs[: ns + 1], opt)
         ok = (np.array_equal(got["read_off"], st["read_off"]) and np.array_equal(got["intv"], st["intv"])
@@ -395,6 +410,8 @@ def main():
     if rf_info:                                          # untimed: how many re-seeding passes the filter proved void
         g.set_param("count_skips", 1); g.run_collect(opt)
         rf_info["pass2_skipped_per_step"] = g.get_param("pass2_skipped")
+        if uw_info is not None and "bytes" in uw_info:
+            uw_info["walks_per_step"] = g.get_param("unique_walks")
         g.set_param("count_skips", 0)
 
     # ---- end-to-end leg: host buffers in, host buffers out, copies inside the timed region.  The public call is

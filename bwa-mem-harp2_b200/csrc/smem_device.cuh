@@ -61,11 +61,12 @@ struct SeedParams {
 	// repeat filter (smem_repeat.cuh): bit hash(w) is set for every rf_k-mer w that occurs more than once in the indexed text
 	const u32 *qflags;       // per read, per 32 window starts: bit set = that rf_k-mer window is not vouched for (pack_reads_kernel); nullptr = no filter
 	int rf_k;                // k-mer length (<= 32)
-	// unique-walk tables (smem_kernels.cuh PH_UW_*): 2-bit text (32 bases per 64-bit word, first base in the top bits), the
+	// unique-walk tables (smem_kernels.cuh PH_UW_*): text at one base per nibble (eight bases per 32-bit word, first base lowest, like the staged reads), the
 	// full suffix array (row -> text position) and its inverse; nullptr = off
 	const uint4 *uw_text; const u64 *uw_fsa, *uw_isa;
+	int uw_min_run, uw_min_left;   // a walk starts after this many extends of an interval of size 1 and with at least this many read bases left (it costs three gathers)
 	int spec_walk;           // 1 = pass-1 calls that directly follow another walk their longest candidate back alone first (PH_SPEC)
-	int count_skips;         // debug: status[6] counts the re-seeding passes the filter proved void
+	int count_skips;         // debug: status[6] counts the re-seeding passes the filter proved void, status[7] the unique walks
 	u64 hot_min_intv;        // 0 = off; occ blocks of intervals >= this size are "hot" (shallow levels, re-used across reads)
 	int l2_mode;             // L2 eviction hints when hot_min_intv != 0: 0 = hot evict_last / cold normal,
 	                         // 1 = hot normal / cold evict_first, 2 = hot evict_last / cold evict_first

@@ -42,10 +42,10 @@ struct DeviceCtx {
 	int64_t escaped = 0;
 	// repeat filter of the re-seeding pass (smem_repeat.cuh)
 	u32 *d_rf = nullptr; bool owns_rf = true; int rf_k = 0, rf_log2 = 0;
-	// unique-walk tables (PH_UW_* of seed_kernel): 2-bit text, full suffix array, inverse suffix array
+	// unique-walk tables (PH_UW_* of seed_kernel): nibble text, full suffix array, inverse suffix array
 	u64 *d_uw_text = nullptr, *d_fsa = nullptr, *d_isa = nullptr; bool owns_uw = true; u64 uw_text_len = 0;
 	u64 rf_text_len = 0;             // length of the text the filter was built from: it is only used with an index of that seq_len
-	int64_t pass2_skipped = 0;
+	int64_t pass2_skipped = 0, uw_walks = 0;
 	uint64_t turn_epoch = 0;         // epoch of the last run in which this lane took part in the kernel turn
 	bool holds_turn = false;         // this lane's seed kernel is part of the call that currently owns the GPU's kernel turn
 	u64 *d_k = nullptr, *d_kout = nullptr; size_t k_cap = 0;
@@ -123,6 +123,7 @@ struct smem_gpu {
 	int l2_mode = 0;                 // see SeedParams::l2_mode
 	int repeat_filter = 1;           // use the repeat filter (if built) to skip void re-seeding passes in MODE_COLLECT
 	int unique_walk = 1;             // use the unique-walk tables if smem_gpu_build_text_index built them
+	int uw_min_left = 8, uw_min_run = 3;   // ... for walks with at least this many read bases left, after this many extends of a unique interval
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
 	int probe_variant = 0;
@@ -348,7 +349,7 @@ int ctx_build_tables(DeviceCtx &d, const uint8_t *pac, int64_t l_pac, int src_de
 	return 0;
 }
 
-// Unique-walk tables: the 2-bit text in the layout pack_text_kernel produces, and the full suffix array / inverse suffix
+// Unique-walk tables: the text, one base per nibble (pack_text_nib_kernel), and the full suffix array / inverse suffix
 // array expanded from the samples on the device (fsa_build_kernel).  8 bytes per row each.
 int ctx_build_text_index(DeviceCtx &d, const uint8_t *pac, long long l_pac, int src_device)
 {
@@ -367,11 +368,11 @@ int ctx_build_text_index(DeviceCtx &d, const uint8_t *pac, long long l_pac, int 
 		if (src_device < 0) CKT(cudaMemcpyAsync(d_pac, pac, pac_bytes, cudaMemcpyHostToDevice, d.stream));
 		else CKT(cudaMemcpyPeerAsync(d_pac, d.dev, pac, src_device, pac_bytes, d.stream));
 	}
-	const long long n_words = ((n + 31) / 32 + 16 + 3) / 4 * 4;          // whole 32-byte sectors, two spare ones past the end
-	CKT(cudaMalloc((void **)&tw, (size_t)n_words * 8));
+	const long long n_words = ((n + 63) / 64 + 2) * 8;                   // 32-bit words of eight bases: whole 32-byte sectors, two spare ones past the end
+	CKT(cudaMalloc((void **)&tw, (size_t)n_words * 4));
 	CKT(cudaMalloc((void **)&fsa, (size_t)(n + 4) * 8));
 	CKT(cudaMalloc((void **)&isa, (size_t)(n + 4) * 8));
-	pack_text_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, tw, n_words);
+	pack_text_nib_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, reinterpret_cast<u32 *>(tw), n_words);
 	CKT(cudaGetLastError());
 	CKT(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	const long long n_sa = (long long)d.n_sa;
@@ -651,7 +652,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf && d.rf_text_len == d.ix.seq_len;   // (a filter of another text is ignored)
 	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips; p.spec_walk = h.spec_walk;
 	const bool use_uw = mode != MODE_SMEM1 && h.unique_walk && d.d_fsa && d.uw_text_len == d.ix.seq_len;
-	p.uw_text = use_uw ? reinterpret_cast<const uint4 *>(d.d_uw_text) : nullptr; p.uw_fsa = d.d_fsa; p.uw_isa = d.d_isa;
+	p.uw_text = use_uw ? reinterpret_cast<const uint4 *>(d.d_uw_text) : nullptr; p.uw_fsa = d.d_fsa; p.uw_isa = d.d_isa; p.uw_min_left = h.uw_min_left; p.uw_min_run = h.uw_min_run;
 	{
 		const size_t bytes_q = (size_t)d.read_cap * q_stride, bytes = bytes_q + (size_t)d.read_cap * (q_stride >> 4) * 4;   // packed reads | window flags
 		if (bytes > d.qpack_bytes) {
@@ -738,13 +739,13 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
 	const auto tt0 = std::chrono::steady_clock::now();
 	auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
-	CK(cudaMemcpyAsync(d.h_status, d.d_status, 7 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 8 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(stream_wait(d));
 	const double t_status = tms();
 	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
 	const int n_over = d.h_status[1];
 	d.overflow = n_over; d.escaped = use_fast ? d.h_status[5] : 0;
-	d.pass2_skipped = d.h_status[6];
+	d.pass2_skipped = d.h_status[6]; d.uw_walks = d.h_status[7];
 	int big_cap = 0;
 	if (n_over > 0) {
 		// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
@@ -1534,6 +1535,8 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "count_skips")) { h->count_skips = v != 0; return 0; }
 	if (!strcmp(name, "spec_walk")) { h->spec_walk = v != 0; return 0; }
 	if (!strcmp(name, "unique_walk")) { h->unique_walk = v != 0; return 0; }
+	if (!strcmp(name, "unique_walk_min_run")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_run = (int)v; return 0; }
+	if (!strcmp(name, "unique_walk_min_left")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_left = (int)v; return 0; }
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
@@ -1572,6 +1575,9 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "rf_kmer")) return h->devs[0].rf_k;
 	if (!strcmp(name, "rf_log2_bits")) return h->devs[0].rf_log2;
 	if (!strcmp(name, "pass2_skipped")) { int64_t t = 0; for (auto &d : h->devs) t += d.pass2_skipped; return t; }
+	if (!strcmp(name, "unique_walks")) { int64_t t = 0; for (auto &d : h->devs) t += d.uw_walks; return t; }
+	if (!strcmp(name, "unique_walk_min_left")) return h->uw_min_left;
+	if (!strcmp(name, "unique_walk_min_run")) return h->uw_min_run;
 	if (!strcmp(name, "chain_kernels_us")) { float m = 0; for (auto &d : h->devs) m = std::max(m, d.chain_ms); return (int64_t)(m * 1000.0f); }
 	if (!strcmp(name, "n_chains")) { int64_t t = 0; for (auto &d : h->devs) t += d.n_chains; return t; }
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;

@@ -306,17 +306,17 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// idle pairs ride along on the interval (1,1,1): its block is hot in L2 and the result is dropped
 		// Unique forward walk (PH_UW_*): once the forward sweep of a pass-1 call has extended an interval of size 1 three times,
 		// the rest of the walk is a comparison of the read with the text at the pattern's only occurrence: text position
-		// t = SA[x0] (one gather), the text itself (one gather of 2 x 128 bases), and the reverse-strand row of the longer
+		// t = SA[x0] (one gather), the text itself (one gather of 2 x 64 bases, a nibble each like the staged read), and the reverse-strand row of the longer
 		// pattern = ISA[n - t - length] (one gather; T = forward + reverse complement, so rc(P) sits mirrored); x0 and the size
-		// stay.  The gathers go through extend_pair's own load (same registers); the walk hands back to PH_FWD, whose next
-		// extend fails like the reference's last one.  t rides in last_s, which the forward sweep does not use.
+		// stay.  The gathers go through extend_pair's own load (same registers); the walk ends where the reference's last
+		// bwt_extend fails.  t rides in last_s, which the forward sweep does not use.
 		const uint4 *alt = nullptr;
 		if (UW && phase >= PH_UW_SA && phase <= PH_UW_ISA) {
 			const u64 plen = (u64)(end - (u32)lds_u16(sc + CS_X));
 			u64 byte;
 			if (phase == PH_UW_SA) byte = (u64)p.uw_fsa + 8 * b;
 			else if (phase == PH_UW_ISA) byte = (u64)p.uw_isa + 8 * (p.ix.seq_len - (last_s + plen));
-			else byte = (u64)p.uw_text + 32 * (((last_s + plen) >> 7) + (u64)half);
+			else byte = (u64)p.uw_text + 32 * (((last_s + plen) >> 6) + (u64)half);
 			alt = reinterpret_cast<const uint4 *>(byte & ~31ull);
 		}
 		const Ext ok = extend_pair<REUSE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, last_bk, last_bl, alt);
@@ -329,35 +329,39 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		if (UW && alt) {
 			const u32 pm2 = 3u << (lane & ~1);
 			if (phase == PH_UW_TEXT) {
-				const int x0q = lds_u16(sc + CS_X);
-				const u64 tp = last_s + (u64)(end - (u32)x0q);          // text position that faces read base i
-				const u64 sec0 = tp >> 7, mysec = sec0 + (u64)half;
-				const u64 lim = min(min(tp + (u64)(len - i), p.ix.seq_len), (sec0 + 2) << 7);   // compare [tp, lim)
-				const u64 rs = max(tp, mysec << 7), re = min((mysec + 1) << 7, lim);
-				u32 cnt = 0;
-				bool full = true;
-				if (re > rs) {
+				// text (pack_text_nib_kernel) and read carry one base per nibble, first base lowest: eight bases per XOR.  This lane
+				// compares the part of [tp, lim) that lies in its 64-base sector; the read word is funnel-shifted into place.
+				const u64 tp = last_s + (u64)(end - (u32)lds_u16(sc + CS_X));   // text position that faces read base i
+				const u64 sec0 = tp >> 6, mybase = (sec0 + (u64)half) << 6;
+				const u64 lim = min(min(tp + (u64)(len - i), p.ix.seq_len), (sec0 + 2) << 6);   // compare [tp, lim)
+				const int r_lo = tp > mybase ? (int)(tp - mybase) : 0, r_hi = lim > mybase ? (int)min(lim - mybase, (u64)64) : 0;
+				int first = 64;
+				if (r_hi > r_lo) {
+					const int base_q = i + (int)((long long)mybase - (long long)tp);   // read index facing the sector's first base (< 0: before i)
+					const int nw1 = (p.q_stride >> 2) - 1, qw = base_q >> 3;
+					const u32 sh = ((u32)base_q & 7u) * 4u;
+					u32 lo = (u32)lds_i32(sq + 4u * (u32)min(max(qw, 0), nw1));   // (clamped words only face masked positions)
 #pragma unroll
-					for (int wq = 0; wq < 4; ++wq) {
-						const u64 word = (u64)blk_k[2 * wq] | ((u64)blk_k[2 * wq + 1] << 32);
-						const u64 w0 = (mysec << 7) + 32 * wq;                      // text position of the word's first base
-						if (full && re > w0 && rs < w0 + 32) {
-							const int r0 = rs > w0 ? (int)(rs - w0) : 0, r1 = re < w0 + 32 ? (int)(re - w0) : 32;
-							for (int r = r0; r < r1; ++r) {
-								const u32 tb = (u32)(word >> (62 - 2 * r)) & 3u;
-								const u32 rb = qbase(sq, i + (int)(w0 + r - tp));
-								if (rb != tb) { full = false; break; }
-								++cnt;
-							}
-						}
+					for (int wq = 0; wq < 8; ++wq) {
+						const u32 hi = (u32)lds_i32(sq + 4u * (u32)min(max(qw + 1 + wq, 0), nw1));
+						u32 d = blk_k[wq] ^ __funnelshift_r(lo, hi, sh);
+						lo = hi;
+						const int a0 = r_lo - 8 * wq, a1 = r_hi - 8 * wq;            // nibbles [a0, a1) of this word take part
+						u32 vm = a0 <= 0 ? 0xffffffffu : (a0 >= 8 ? 0u : 0xffffffffu << (4 * a0));
+						if (a1 < 8) vm &= a1 <= 0 ? 0u : ~(0xffffffffu << (4 * a1));
+						d &= vm;
+						const u32 m = (d | (d >> 1) | (d >> 2)) & 0x11111111u;        // a base differs (an ambiguous read base, 4, always does)
+						if (m && first == 64) first = 8 * wq + ((__ffs((int)m) - 1) >> 2);
 					}
 				}
+				const bool full = first == 64;
+				const u32 cnt = r_hi > r_lo ? (u32)((full ? r_hi : first) - r_lo) : 0u;
 				const u32 c0 = __shfl_sync(pm2, cnt, lane & ~1), c1 = __shfl_sync(pm2, cnt, lane | 1);
 				const bool f0 = __shfl_sync(pm2, (int)full, lane & ~1) != 0, f1 = __shfl_sync(pm2, (int)full, lane | 1) != 0;
 				const u32 m = f0 ? c0 + c1 : c0;
 				i += (int)m; end = (u32)i;
-				// ran through the whole 256-base window without a verdict: another round of text, else the inverse SA
-				if (!(f0 && f1 && tp + m == ((sec0 + 2) << 7) && i < len && tp + m < p.ix.seq_len)) phase = PH_UW_ISA;
+				// ran through the whole 128-base window without a verdict: another round of text, else the inverse SA
+				if (!(f0 && f1 && tp + m == ((sec0 + 2) << 6) && i < len && tp + m < p.ix.seq_len)) phase = PH_UW_ISA;
 			} else {
 				const u64 byte = phase == PH_UW_SA ? (u64)p.uw_fsa + 8 * b
 				                                   : (u64)p.uw_isa + 8 * (p.ix.seq_len - (last_s + (u64)(end - (u32)lds_u16(sc + CS_X))));
@@ -369,9 +373,10 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				else {
 					a = val;                                         // x[1] of the longer pattern; x[0] (b) and the size stay
 					j = 0;
-					const u32 qv = i < len ? qbase(sq, i) : 4u;
-					if (qv > 3) phase = PH_FWD_END;
-					else { c = 3 - (int)qv; phase = PH_FWD; }
+					// The comparison stopped at the end of the read, at an ambiguous base (bwt.c:800-806), at the end of the text or at
+					// a base that differs from the text at the only occurrence: the reference's next bwt_extend finds nothing
+					// (bwt.c:796-798).  Either way the interval is pushed and the forward sweep is over.
+					phase = PH_FWD_END;
 				}
 			}
 			continue;
@@ -412,7 +417,10 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			else c = 3 - (int)qv;
 			if (UW) {
 				j = (s == 1 && min_intv == 1) ? j + 1 : 0;           // consecutive extends of a unique interval
-				if (j >= 3 && phase == PH_FWD && len - i >= 8) { phase = PH_UW_SA; a = 1; }   // (a is rebuilt from the inverse SA)
+				if (j >= p.uw_min_run && phase == PH_FWD && len - i >= p.uw_min_left) {                  // (a is rebuilt from the inverse SA)
+					phase = PH_UW_SA; a = 1;
+					if (p.count_skips && !half) atomicAdd(&p.status[7], 1);
+				}
 			}
 		} else {
 			if (++j == n_prev) {                             // bwt.c:826-827
@@ -675,6 +683,26 @@ __global__ void __launch_bounds__(128) sa_kernel(const DevIndex ix, const u64 *_
 		const u64 kn = inv_psi_pair(ix, k, half, lane);
 		if (have) { k = kn; if (++steps > (1ull << 24)) { if (!half) atomicAdd(&status[2], 1); k = 0; } }   // guard: corrupt index
 	}
+}
+
+// Text T = forward + reverse complement, one base per nibble, eight bases per 32-bit word, first base lowest -- the
+// layout of the staged reads (pack_reads_kernel), so that PH_UW_TEXT compares eight bases with one XOR.  `pac` is the
+// reference's .pac layout of the forward strand (bntseq.c: four bases per byte, first base in the top bits).
+__global__ void __launch_bounds__(256) pack_text_nib_kernel(const uint8_t *__restrict__ pac, long long l_pac, u32 *__restrict__ tw, long long n_words)
+{
+	const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= n_words) return;
+	const long long n = 2 * l_pac;
+	u32 v = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const long long pos = 8 * w + k;
+		u32 base = 0;
+		if (pos < l_pac) base = (pac[pos >> 2] >> ((~pos & 3) << 1)) & 3u;
+		else if (pos < n) { const long long o = n - 1 - pos; base = 3u - ((pac[o >> 2] >> ((~o & 3) << 1)) & 3u); }
+		v |= base << (4 * k);
+	}
+	tw[w] = v;
 }
 
 // Full suffix array and its inverse from the samples (unique-walk tables, PH_UW_* of seed_kernel): every sampled row k * intv

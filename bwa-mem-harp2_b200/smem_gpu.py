@@ -222,7 +222,7 @@ class SmemGpu:
             self._check(self.lib.smem_gpu_build_repeat_filter(self.h, C.c_void_p(a.ctypes.data), C.c_int64(l_pac), C.c_int(-1), C.c_int(kmer_len), C.c_int(log2_bits)))
 
     def build_text_index(self, fwd):
-        """Unique-walk tables (smem_gpu_build_text_index): 2-bit text + full SA + inverse SA; needs upload_index and upload_sa.
+        """Unique-walk tables (smem_gpu_build_text_index): text (4 bits per base) + full SA + inverse SA; needs upload_index and upload_sa.
         ``fwd`` as for :meth:`build_repeat_filter`."""
         if isinstance(fwd, tuple):
             pac, l_pac = fwd

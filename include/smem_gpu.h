@@ -119,7 +119,7 @@ int smem_gpu_get_repeat_filter(smem_gpu_t *h, uint32_t *out, int64_t out_words);
 
 /* Unique-walk tables -- optional accelerator tables of smem_gpu_collect / smem_gpu_trace.
  * Once the forward sweep of bwt_smem1 (bwt.c:790-806) holds an interval of size 1, every further bwt_extend asks whether
- * the text continues like the read at the pattern's ONLY occurrence.  With the 2-bit text, the full suffix array and its
+ * the text continues like the read at the pattern's ONLY occurrence.  With the text (4 bits per base), the full suffix array and its
  * inverse in HBM (8 bytes per row each: 100 GB at 3.1 Gbp) that walk is one suffix-array lookup, one comparison of the
  * read with the text and one inverse lookup for the reverse-strand row (T = forward + reverse complement, so the reverse
  * complement of a pattern at t sits at seq_len - t - length); x[0] and the size do not change.  The tables are expanded on

@@ -93,12 +93,21 @@ void orc_set_spec_walk(int on) { orc_spec_walk = on; orc_spec_hits = orc_spec_mi
 uint64_t orc_get_spec_hits(void) { return orc_spec_hits; }
 uint64_t orc_get_spec_misses(void) { return orc_spec_misses; }
 
+/* COUNTING MODEL of the device kernel's unique forward walk, off unless orc_set_unique_walk(1) -- a
+ * hook of bench.py's `executed` figure; results are untouched.  Once the forward sweep of a pass-1 call (min_intv == 1) has
+ * extended an interval of size 1 `run` times and at least `left` read bases remain, the device replaces the rest of the
+ * sweep by three gathers (suffix array, text, inverse suffix array); they are counted as three extends of one block each
+ * and the extends they replace are not counted (a walk longer than the 128-base text window costs one more gather per
+ * window, which this model leaves out: 101 bp reads never need it). */
+static int orc_uw_model = 0, orc_uw_run = 3, orc_uw_left = 8;
+void orc_set_unique_walk(int on) { orc_uw_model = on; }
+
 /* bwt_smem1, bwt.c:776-835.  Writes the SMEM candidates through x into `mem`, returns ret. */
 static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int min_intv, ivv_t *mem,
                  ivv_t *prev, ivv_t *curr, orc_stats_t *st)
 {
 	iv_t ik, ok[4];
-	int i, j, ret;
+	int i, j, ret, uw_run = 0, uw_walking = 0;
 	ivv_t *t;
 	mem->n = 0;
 	if (q[x] > 3) return x + 1;
@@ -111,12 +120,16 @@ static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int mi
 		int c;
 		if (q[i] > 3) { ivv_push(curr, ik); break; }
 		c = 3 - q[i];
-		extend(ix, &ik, 0, ok, st);
+		extend(ix, &ik, 0, ok, uw_walking ? 0 : st);
 		if (ok[c].x2 != ik.x2) {
 			ivv_push(curr, ik);
 			if (ok[c].x2 < (uint64_t)min_intv) break;
 		}
 		ik = ok[c]; ik.info = (uint64_t)(i + 1);
+		if (orc_uw_model && st && !uw_walking && min_intv == 1) {
+			uw_run = ik.x2 == 1 ? uw_run + 1 : 0;
+			if (uw_run >= orc_uw_run && len - (i + 1) >= orc_uw_left && q[i + 1] <= 3) { uw_walking = 1; st->extends += 3; st->blocks += 3; }
+		}
 	}
 	if (i == len) ivv_push(curr, ik);
 	ivv_reverse(curr); /* longest match first */

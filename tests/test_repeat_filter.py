@@ -242,9 +242,12 @@ def test_gpu_text_index_and_unique_walk(fm, synth):
         for seq, offs, opt in sets:
             want = o.collect(seq, offs, opt, nthreads=4)
             gopt = sg.SeedOpt(opt.min_seed_len, opt.split_factor, opt.split_width, opt.start_width)
-            got = g.collect(seq, offs, gopt)
-            for k in ("intv", "read_off", "step"):
-                assert np.array_equal(got[k], want[k]), (name, k)
+            for run, left in ((3, 8), (1, 1), (2, 40)):                    # when a walk starts: extends of a unique interval, bases left
+                g.set_param("unique_walk_min_run", run); g.set_param("unique_walk_min_left", left)
+                got = g.collect(seq, offs, gopt)
+                for k in ("intv", "read_off", "step"):
+                    assert np.array_equal(got[k], want[k]), (name, k, run, left)
+            g.set_param("unique_walk_min_run", 3); g.set_param("unique_walk_min_left", 8)
             tr = g.trace(seq, offs, gopt)
             g.set_param("unique_walk", 0)
             tr0 = g.trace(seq, offs, gopt)
