@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="smem_gpu_set_param on the device-resident handle (repeatable)")
     ap.add_argument("--no-repeat-filter", action="store_true", help="do not build / use the repeat filter of the re-seeding pass (DESIGN.md section 10)")
     ap.add_argument("--no-text-index", action="store_true", help="do not build / use the unique-walk tables")
-    ap.add_argument("--text-index", action="store_true", help="(default when HBM has room) "also build the unique-walk tables (text at 4 bits per base, full SA, inverse SA: 16.5 bytes per text position) and seed with them")
+    ap.add_argument("--text-index", action="store_true", help="(default when HBM has room) also build the unique-walk tables (text at 4 bits per base, full SA, inverse SA: 16.5 bytes per text position) and seed with them (DESIGN.md section 10)")
     ap.add_argument("--rf-kmer", type=int, default=0)
     ap.add_argument("--rf-log2-bits", type=int, default=0)
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: do not pin each rank to the CPUs local to its GPU")
@@ -612,6 +612,8 @@ def main():
         traffic = None
         try:   # dram__bytes_read + dram__bytes_write of seed_kernel from the committed `ncu --set full` capture of this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "seed_traffic.json")))
+            if not (uw_info and "bytes" in uw_info):
+                tr = tr.get("without_text_index", {})          # the capture of the kernel without the unique-walk tables
             if tr.get("ref_bp") == args.ref_bp and tr.get("reads") == args.reads and tr.get("read_len") == args.read_len:
                 traffic = tr["dram_bytes_per_launch"]
         except Exception:
