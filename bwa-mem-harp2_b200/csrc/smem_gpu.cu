@@ -652,7 +652,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf && d.rf_text_len == d.ix.seq_len;   // (a filter of another text is ignored)
 	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips; p.spec_walk = h.spec_walk;
 	const bool use_uw = mode != MODE_SMEM1 && h.unique_walk && d.d_fsa && d.uw_text_len == d.ix.seq_len;
-	p.uw_text = use_uw ? reinterpret_cast<const uint4 *>(d.d_uw_text) : nullptr; p.uw_fsa = d.d_fsa; p.uw_isa = d.d_isa; p.uw_min_left = h.uw_min_left; p.uw_min_run = h.uw_min_run;
+	p.uw_text = use_uw ? reinterpret_cast<const uint4 *>(d.d_uw_text) : nullptr; p.uw_fsa = d.d_fsa; p.uw_isa = d.d_isa; p.uw_min_left = h.uw_min_left; p.uw_min_run = use_uw ? h.uw_min_run : 0x7fffffff;
 	{
 		const size_t bytes_q = (size_t)d.read_cap * q_stride, bytes = bytes_q + (size_t)d.read_cap * (q_stride >> 4) * 4;   // packed reads | window flags
 		if (bytes > d.qpack_bytes) {

@@ -43,15 +43,15 @@ template <int MODE, int MIN_BLOCKS, bool WIDE, bool REUSE /* keep the last occ s
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
 	const bool SPEC = MODE != MODE_SMEM1 && p.spec_walk;     // speculative longest-only backward walk (PH_SPEC)
-	const bool UW = p.uw_text != nullptr;                      // unique forward walks by text comparison (PH_UW_*)
 	typedef BEntry<WIDE> BE;
 	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, half = lane & 1;
 	const int pair = threadIdx.x >> 1;
 	const u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;   // this pair's shared memory
-	const u32 sb = sp;                                       // B entries first (16-byte aligned)
-	const u32 sc = sp + (u32)p.b_cap * BE::BYTES;            // cold state
-	const u32 sq = sc + COLD_BYTES;                          // query, two bases per byte
+	// cold state first, then B, then the query: the cold-state and B addresses are sp + a compile-time constant
+	const u32 sc = sp;                                       // cold state
+	const u32 sb = sp + COLD_BYTES;                          // B entries (16-byte aligned)
+	const u32 sq = sb + (u32)p.b_cap * BE::BYTES;            // query, two bases per byte
 	Intv *const M1s = p.scratch + (size_t)(blockIdx.x * (SEED_BLOCK / 2) + pair) * 3 * p.scratch_cap;
 	auto scratch_base = [&]() -> Intv * { return M1s; };   // (forcing this out of the main loop with volatile reads cost spills: slower)
 
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// stay.  The gathers go through extend_pair's own load (same registers); the walk ends where the reference's last
 		// bwt_extend fails.  t rides in last_s, which the forward sweep does not use.
 		const uint4 *alt = nullptr;
-		if (UW && phase >= PH_UW_SA && phase <= PH_UW_ISA) {
+		if (phase >= PH_UW_SA && phase <= PH_UW_ISA) {              // (only entered with the tables present)
 			const u64 plen = (u64)(end - (u32)lds_u16(sc + CS_X));
 			u64 byte;
 			if (phase == PH_UW_SA) byte = (u64)p.uw_fsa + 8 * b;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// ============================================================== consume the result, set up the next extend
 		// (forward: bwt.c:794-799, backward: bwt.c:813-824; written once for both so that the warp does not
 		//  run two divergent copies of the push / advance code)
-		if (UW && alt) {
+		if (alt) {
 			const u32 pm2 = 3u << (lane & ~1);
 			if (phase == PH_UW_TEXT) {
 				// text (pack_text_nib_kernel) and read carry one base per nibble, first base lowest: eight bases per XOR.  This lane
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			const u32 qv = i < len ? qbase(sq, i) : 4u;
 			if (qv > 3) phase = PH_FWD_END;
 			else c = 3 - (int)qv;
-			if (UW) {
+			if (MODE != MODE_SMEM1) {                            // (uw_min_run is out of reach without the tables)
 				j = (s == 1 && min_intv == 1) ? j + 1 : 0;           // consecutive extends of a unique interval
 				if (j >= p.uw_min_run && phase == PH_FWD && len - i >= p.uw_min_left) {                  // (a is rebuilt from the inverse SA)
 					phase = PH_UW_SA; a = 1;
