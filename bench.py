@@ -36,7 +36,7 @@ def log(*a):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-bp", type=int, default=int(os.environ.get("SMEM_BENCH_REF_BP", 3_100_000_000)))
@@ -465,8 +465,16 @@ def main():
                 r = e2e_step(0)
             return r
         res = [0] * T
+        nxt = [0]
+        lock = threading.Lock()
         def work(t):
-            for _ in range(t, k_steps, T):
+            # a free worker takes the next step (kt_for_batch hands out batches the same way, kthread_batch.c:20-44): with a
+            # fixed striping the worker that happens to come second can be left with the last two steps, back to back
+            while True:
+                with lock:
+                    k = nxt[0]; nxt[0] += 1
+                if k >= k_steps:
+                    break
                 res[t] = e2e_step(t)
         th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
         for x in th:
