@@ -67,6 +67,23 @@ def test_spec_walk_rule_is_exact_on_cpu(worlds, synth):
         assert hits > 1000
 
 
+def test_unique_walk_counting_model_leaves_results_alone(worlds, synth):
+    """orc_set_unique_walk only changes the oracle's extend / block counts (bench.py's `executed` figure), never a result."""
+    for name, ref, ix, o in worlds:
+        seq, offs = synth.to_batch(synth.simulate_reads(ref, 1500, 101, 0.01, seed=31, paired=True, n_frac=0.05))
+        want = o.collect(seq, offs, SeedOpt(), nthreads=2, stats=True)
+        o.lib.orc_set_unique_walk(1)
+        try:
+            got = o.collect(seq, offs, SeedOpt(), nthreads=2, stats=True)
+        finally:
+            o.lib.orc_set_unique_walk(0)
+        for k in ("intv", "read_off", "step"):
+            assert np.array_equal(got[k], want[k]), (name, k)
+        assert got["stats"]["extends"] <= want["stats"]["extends"] and got["stats"]["intervals"] == want["stats"]["intervals"]
+        if name == "random":
+            assert got["stats"]["extends"] < 0.9 * want["stats"]["extends"]      # long unique matches: the walks are taken
+
+
 def _brute_bits(T, K, log2_bits):
     n = len(T)
     codes = np.zeros(n - K + 1, np.uint64)
