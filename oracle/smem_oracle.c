@@ -102,6 +102,22 @@ uint64_t orc_get_spec_misses(void) { return orc_spec_misses; }
 static int orc_uw_model = 0, orc_uw_run = 3, orc_uw_left = 8;
 void orc_set_unique_walk(int on) { orc_uw_model = on; }
 
+/* EXECUTABLE MODEL of the same rule (tests/test_repeat_filter.py), off unless orc_set_unique_walk_tables is given tables:
+ * text = T = forward + reverse complement, one base per byte, n = seq_len bases; fsa[r] = text position of row r
+ * (fsa[0] = n for the '$' row), isa = its inverse.  With them the rest of a forward sweep that holds an interval of size 1
+ * is computed the way PH_UW_SA / PH_UW_TEXT / PH_UW_ISA of the device kernel do it -- t = fsa[x0], compare the read with
+ * the text behind the match, x1 = isa[n - t - length] -- instead of by bwt_extend. */
+static const uint8_t *orc_uw_text = 0;
+static const uint64_t *orc_uw_fsa = 0, *orc_uw_isa = 0;
+static uint64_t orc_uw_n = 0;
+uint64_t orc_uw_walks = 0;
+void orc_set_unique_walk_tables(const uint8_t *text, const uint64_t *fsa, const uint64_t *isa, uint64_t n, int run, int left)
+{
+	orc_uw_text = text; orc_uw_fsa = fsa; orc_uw_isa = isa; orc_uw_n = n; orc_uw_walks = 0;
+	orc_uw_run = run > 0 ? run : 3; orc_uw_left = left > 0 ? left : 8;
+}
+uint64_t orc_get_unique_walks(void) { return orc_uw_walks; }
+
 /* bwt_smem1, bwt.c:776-835.  Writes the SMEM candidates through x into `mem`, returns ret. */
 static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int min_intv, ivv_t *mem,
                  ivv_t *prev, ivv_t *curr, orc_stats_t *st)
@@ -126,7 +142,23 @@ static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int mi
 			if (ok[c].x2 < (uint64_t)min_intv) break;
 		}
 		ik = ok[c]; ik.info = (uint64_t)(i + 1);
-		if (orc_uw_model && st && !uw_walking && min_intv == 1) {
+		if (orc_uw_text && min_intv == 1) {
+			uw_run = ik.x2 == 1 ? uw_run + 1 : 0;
+			if (uw_run >= orc_uw_run && len - (i + 1) >= orc_uw_left && q[i + 1] <= 3) {
+				const uint64_t t = orc_uw_fsa[ik.x0];                 /* the pattern q[x..i] occurs only here */
+				uint64_t plen = (uint64_t)(i + 1 - x);
+				int e = i + 1;
+				while (e < len && q[e] <= 3 && t + plen < orc_uw_n && orc_uw_text[t + plen] == q[e]) { ++e; ++plen; }
+				ik.x1 = orc_uw_isa[orc_uw_n - (t + plen)];            /* rc(pattern) sits mirrored in T */
+				ik.info = (uint64_t)e;
+				/* read end, ambiguous base, text end or a differing base: the reference's next bwt_extend finds nothing
+				 * (bwt.c:796-798) or the loop ends (bwt.c:800-806); either way ik is pushed and the sweep is over */
+				ivv_push(curr, ik);
+				__sync_fetch_and_add(&orc_uw_walks, 1);
+				i = -2;                                               /* (not len: the push after the loop is skipped) */
+				break;
+			}
+		} else if (orc_uw_model && st && !uw_walking && min_intv == 1) {
 			uw_run = ik.x2 == 1 ? uw_run + 1 : 0;
 			if (uw_run >= orc_uw_run && len - (i + 1) >= orc_uw_left && q[i + 1] <= 3) { uw_walking = 1; st->extends += 3; st->blocks += 3; }
 		}

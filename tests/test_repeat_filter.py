@@ -84,6 +84,69 @@ def test_unique_walk_counting_model_leaves_results_alone(worlds, synth):
             assert got["stats"]["extends"] < 0.9 * want["stats"]["extends"]      # long unique matches: the walks are taken
 
 
+def _text_tables(o, ix, ref):
+    """T = forward + reverse complement (one base per byte), its suffix array from the oracle's bwt_sa, and the inverse."""
+    n = int(ix.seq_len)
+    fsa = np.empty(n + 1, np.uint64)
+    fsa[0] = n                                                            # the '$' row
+    fsa[1:] = o.sa(ix, np.arange(1, n + 1, dtype=np.uint64))
+    isa = np.empty(n + 1, np.uint64)
+    isa[fsa.astype(np.int64)] = np.arange(n + 1, dtype=np.uint64)
+    r = ref.numpy() if hasattr(ref, "numpy") else np.asarray(ref)
+    T = np.ascontiguousarray(np.concatenate([r, (3 - r)[::-1]]), np.uint8)
+    return T, fsa, isa
+
+
+def _edge_reads(ref, T, rng):
+    """Ragged lengths, both strands, one substitution / one N, the forward / reverse-complement junction, the text ends."""
+    r = ref.numpy() if hasattr(ref, "numpy") else np.asarray(ref)
+    reads = [np.zeros(0, np.uint8)]
+    for ln in (7, 20, 33, 60, 101, 150, 255, 256):
+        for _ in range(8):
+            p = int(rng.integers(0, len(r) - ln)); q = r[p:p + ln].copy()
+            if rng.random() < 0.5:
+                q = (3 - q)[::-1].copy()
+            if rng.random() < 0.5 and ln > 30:
+                k = int(rng.integers(0, ln)); q[k] = (q[k] + 1) % 4
+            if rng.random() < 0.2 and ln > 30:
+                q[int(rng.integers(0, ln))] = 4
+            reads.append(q)
+    for off in (-90, -40, -1, 0, 30):
+        reads.append(T[len(r) + off - 100: len(r) + off + 100].copy())
+    reads.append(T[:180].copy()); reads.append(T[-180:].copy())
+    return reads
+
+
+def test_unique_walk_rule_is_exact_on_cpu(fm, synth):
+    """Executable model of PH_UW_* in the oracle (smem_oracle.c, orc_set_unique_walk_tables: suffix array lookup, text
+    comparison, inverse lookup instead of bwt_extend) against the unmodified algorithm: random and repeat-rich texts,
+    every option set, edge reads, both start thresholds."""
+    for name, ref in (("random", synth.make_reference(300_000, 5)), ("repeats", repeat_rich_reference(200_000, 8))):
+        ix = fm.build_index(ref, sa_intv=32)
+        o = Oracle(ix)
+        o.lib.orc_get_unique_walks.restype = C.c_uint64
+        T, fsa, isa = _text_tables(o, ix, ref)
+        n = int(ix.seq_len)
+        assert np.array_equal(np.sort(fsa), np.arange(n + 1, dtype=np.uint64))       # a permutation of the text positions
+        sets = [synth.to_batch(_edge_reads(ref, T, np.random.default_rng(4))) + (SeedOpt(),)]
+        for rl, err, opt in SETS:
+            sets.append(synth.to_batch(synth.simulate_reads(ref, 1200, rl, err, seed=37, paired=True, n_frac=0.05)) + (opt,))
+        walks = 0
+        for seq, offs, opt in sets:
+            want = o.collect(seq, offs, opt, nthreads=2)
+            for run, left in ((3, 8), (1, 1)):
+                o.lib.orc_set_unique_walk_tables(C.c_void_p(T.ctypes.data), C.c_void_p(fsa.ctypes.data), C.c_void_p(isa.ctypes.data),
+                                                 C.c_uint64(n), C.c_int(run), C.c_int(left))
+                try:
+                    got = o.collect(seq, offs, opt, nthreads=2)
+                    walks += o.lib.orc_get_unique_walks()
+                finally:
+                    o.lib.orc_set_unique_walk_tables(None, None, None, C.c_uint64(0), C.c_int(0), C.c_int(0))
+                for k in ("intv", "read_off", "step", "n_steps", "last_start"):
+                    assert np.array_equal(got[k], want[k]), (name, k, run, left)
+        assert walks > 1000                  # the rule fires on these sets
+
+
 def _brute_bits(T, K, log2_bits):
     n = len(T)
     codes = np.zeros(n - K + 1, np.uint64)
