@@ -207,8 +207,8 @@ int smem_gpu_host_free(void *ptr);
 
 /* Measurement hooks (CUDA events on the library's own streams; max over the handle's devices). */
 typedef struct {
-	double seed_kernel_ms;     /* the SMEM kernel(s) of the last run */
-	double total_device_ms;    /* seed kernel + scan + compaction (+ overflow re-run) */
+	double seed_kernel_ms;     /* the SMEM kernel of the last run (first launch; the overflow re-run is not in it) */
+	double total_device_ms;    /* pack pre-pass + seed kernel + scan + compaction (+ overflow re-run) */
 	int64_t kernel_launches;   /* kernels launched by the last run, all devices */
 	int64_t overflow_reads;    /* reads that needed the large-slot re-run */
 	int64_t h2d_bytes, d2h_bytes;  /* bytes copied by the last stage / fetch */
@@ -219,7 +219,10 @@ int smem_gpu_last_timing(const smem_gpu_t *h, smem_gpu_timing_t *t);
  * memory per read), "force_wide" (32-byte entries), "l2_fetch_granularity" (32|64|128, device-wide
  * cudaLimitMaxL2FetchGranularity hint), "probe_variant", "l2_hot_min_intv" (0 = off:
  * occ-block loads for intervals of size >= value carry an L2 evict_last hint), "reuse" (keep the last occ sectors
- * in registers), "spare_sms" / "chain_lanes" (scheduling of several pipeline lanes on one GPU). */
+ * in registers), "spare_sms" / "chain_lanes" (scheduling of several pipeline lanes on one GPU), "repeat_filter" /
+ * "spec_walk" / "unique_walk" (0 = do not use that shortcut of DESIGN.md section 10; results are the same),
+ * "unique_walk_min_run" / "unique_walk_min_left" (a unique walk starts after that many extends of an interval of size 1
+ * and with at least that many read bases left; 3 / 8), "count_skips" (debug counters "pass2_skipped", "unique_walks"). */
 int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t value);
 int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name);
 
