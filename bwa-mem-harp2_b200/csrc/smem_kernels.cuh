@@ -306,10 +306,10 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// idle pairs ride along on the interval (1,1,1): its block is hot in L2 and the result is dropped
 		// Unique forward walk (PH_UW_*): once the forward sweep of a pass-1 call has extended an interval of size 1 three times,
 		// the rest of the walk is a comparison of the read with the text at the pattern's only occurrence: text position
-		// t = SA[x0] (one gather), the text itself (one gather of 2 x 64 bases, a nibble each like the staged read), and the reverse-strand row of the longer
-		// pattern = ISA[n - t - length] (one gather; T = forward + reverse complement, so rc(P) sits mirrored); x0 and the size
-		// stay.  The gathers go through extend_pair's own load (same registers); the walk ends where the reference's last
-		// bwt_extend fails.  t rides in last_s, which the forward sweep does not use.
+		// t = SA[x0] (one gather), the text itself (one gather of 2 x 64 bases, a nibble each like the staged read), and the
+		// reverse-strand row of the longer pattern = ISA[n - t - length] (one gather; T = forward + reverse complement, so
+		// rc(P) sits mirrored); x0 and the size stay.  The gathers go through extend_pair's own load (same registers); the
+		// walk ends where the reference's last bwt_extend fails.  t rides in last_s, which the forward sweep does not use.
 		const uint4 *alt = nullptr;
 		if (phase >= PH_UW_SA && phase <= PH_UW_ISA) {              // (only entered with the tables present)
 			const u64 plen = (u64)(end - (u32)lds_u16(sc + CS_X));
