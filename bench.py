@@ -49,24 +49,21 @@ def parse():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--l2-hot-min-intv", type=int, default=-1)
     ap.add_argument("--lanes", type=int, default=1, help="pipeline lanes per GPU of the end-to-end handle")
-    ap.add_argument("--host-threads", type=int, default=2, help="host worker threads of the end-to-end leg, each with its own handle sharing one index (the reference's -t N pattern)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the end-to-end legs, each with its own handle sharing one index (the reference's -t N pattern); 0 = 3, or 2 when the rank has fewer than 4 cores to itself")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (32-byte end-to-end, seeds / chains end-to-end, unique walks off, configs 4 and 5)")
+    ap.add_argument("--pcie-probe", action="store_true", help="also time the step's copy volumes alone and next to a running seed kernel (on by default in multi-GPU runs)")
+    ap.add_argument("--isa-shift", type=int, default=2, help="the unique-walk tables sample the inverse suffix array every 2^this positions")
     ap.add_argument("--spare-sms", type=int, default=-1)
-    ap.add_argument("--fast", action="store_true", help="EXPERIMENTAL: build the k-mer count pyramid and seed through the table-driven kernel (DESIGN.md section 9)")
-    ap.add_argument("--direct-levels", type=int, default=-1, help="depth of the direct k-mer tables (pyramid reaches +5); -1 = from the text length")
-    ap.add_argument("--fast-blocks-per-sm", type=int, default=0)
-    ap.add_argument("--fast-slots", type=int, default=0)
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="smem_gpu_set_param on the device-resident handle (repeatable)")
     ap.add_argument("--no-repeat-filter", action="store_true", help="do not build / use the repeat filter of the re-seeding pass (DESIGN.md section 10)")
     ap.add_argument("--no-text-index", action="store_true", help="do not build / use the unique-walk tables")
-    ap.add_argument("--text-index", action="store_true", help="(default when HBM has room) also build the unique-walk tables (text at 4 bits per base, full SA, inverse SA: 16.5 bytes per text position) and seed with them (DESIGN.md section 10)")
+    ap.add_argument("--text-index", action="store_true", help="(default when HBM has room) also build the unique-walk tables (text at 4 bits per base, 33-bit suffix array, sampled inverse: 6.2 bytes per text position) and seed with them (DESIGN.md section 10)")
     ap.add_argument("--rf-kmer", type=int, default=0)
     ap.add_argument("--rf-log2-bits", type=int, default=0)
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: do not pin each rank to the CPUs local to its GPU")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap[:reuse[:l2_mode]]]] to time (stderr), e.g. 6,8:16384,9::17")
+    ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap[::l2_mode]]] to time (stderr), e.g. 6,8:16384,9::17")
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
-    ap.add_argument("--batch-sweep", action="store_true", help="BASELINE config 5: latency/throughput of smem_gpu_collect for 64..1M reads per call, L2 hint off/on")
-    ap.add_argument("--seeds", action="store_true", help="also time collect + smem_gpu_seeds (section 8f-1: intervals -> mem_seed_t on device)")
     ap.add_argument("--full-compare", action="store_true", help="compare every interval of the step with the oracle (config 2)")
     return ap.parse_args()
 
@@ -123,7 +120,7 @@ class ClockSampler:
         return out
 
 
-def make_workload(args, rank, device):
+def make_workload(args, rank, device, want_cfg4=False):
     """Reference + index on the GPU, this rank's reads on the host (pinned by the caller)."""
     import torch
     fm = importlib.import_module("bwa-mem-harp2_b200.fmindex")
@@ -132,16 +129,19 @@ def make_workload(args, rank, device):
     fwd = sy.make_reference(args.ref_bp, 13, device)
     if args.repeat_frac > 0:
         fwd = sy.add_repeat_families(fwd, args.repeat_frac, 17)
-    ix = fm.build_index(fwd, sa_intv=32 if (getattr(args, 'seeds', False) or getattr(args, 'text_index', False)) else 0)
+    ix = fm.build_index(fwd, sa_intv=0 if args.impl == 'reference' else 32)
     torch.cuda.synchronize()
     t_index = time.time() - t0
     reads = sy.simulate_reads(fwd, args.reads, args.read_len, args.err, seed=1000 + rank, paired=True)
     seq, offs = sy.to_batch(reads)
+    cfg4 = None
+    if want_cfg4:          # BASELINE configs[3]: 250 bp reads at 2 % errors on the same reference
+        cfg4 = sy.to_batch(sy.simulate_reads(fwd, 500_000, 250, 0.02, seed=4000 + rank))
     sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
-    pac = sg.pack_pac(fwd) if (args.fast or args.text_index or not args.no_repeat_filter) else None          # the reference's .pac layout of the forward text
+    pac = sg.pack_pac(fwd) if (args.text_index or not args.no_repeat_filter) else None          # the reference's .pac layout of the forward text
     del fwd, reads
     torch.cuda.empty_cache()
-    return ix, seq, offs, t_index, pac
+    return ix, seq, offs, t_index, pac, cfg4
 
 
 def cpu_engine(ix_host):
@@ -228,16 +228,17 @@ def main():
 
     # unique-walk tables: 16.5 bytes per text position next to the index; on unless told otherwise
     # or the device is too small for them (results never depend on them)
-    uw_need = int(16.5 * 2 * args.ref_bp)
+    uw_need = int((0.5 + 32 / 7 * (1 + 0.5 ** args.isa_shift)) * 2 * args.ref_bp)
     uw_room = torch.cuda.get_device_properties(device).total_memory - 8 * 2 * args.ref_bp - (24 << 30)   # index + builder scratch + results
-    if args.impl == "reference" or args.no_text_index or args.fast:
+    if args.impl == "reference" or args.no_text_index:
         args.text_index = False
     elif not args.text_index:
         args.text_index = uw_need <= uw_room
         if not args.text_index:
             log(f"unique-walk tables skipped: {uw_need / 1e9:.0f} GB needed, {uw_room / 1e9:.0f} GB to spare on this device")
     log(f"rank {rank}/{world}: building workload ({args.ref_bp} bp)")
-    ix, seq, offs, t_index, pac = make_workload(args, rank, device)
+    want_cfg4 = (args.impl == "ours" and not args.no_extras and world == 1 and args.read_len == 101 and args.reads >= 1_000_000 and args.ref_bp >= 1_000_000_000)
+    ix, seq, offs, t_index, pac, cfg4 = make_workload(args, rank, device, want_cfg4)
     log(f"index built on GPU in {t_index:.1f}s: seq_len={ix.seq_len} bwt_size={ix.bwt_size} primary={ix.primary}")
     n = len(offs) - 1
 
@@ -265,6 +266,7 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm (CUDA through the C ABI)
+    import ctypes as C
     g = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local])
     if args.blocks_per_sm:
         g.set_param("blocks_per_sm", args.blocks_per_sm)
@@ -274,8 +276,8 @@ def main():
     if args.l2_hot_min_intv >= 0:
         g.set_param("l2_hot_min_intv", args.l2_hot_min_intv)
     g.upload_index(ix)                      # device -> device copy of the packed bwt_t into the library's HBM buffer
+    g.upload_sa(ix)                         # suffix-array samples: unique-walk tables, seed-level API
     lib = g.lib
-    fast_info = None
     rf_info = None
     if pac is not None and not args.no_repeat_filter:
         torch.cuda.synchronize()
@@ -288,36 +290,23 @@ def main():
     if pac is not None and args.text_index:
         torch.cuda.synchronize()
         tb0 = time.time()
-        g.upload_sa(ix)
         try:
+            g.set_param("unique_walk_isa_shift", args.isa_shift)
             g.build_text_index((pac, args.ref_bp))
-            uw_info = {"bytes": 16 * (int(ix.seq_len) + 4) + int(ix.seq_len) // 2, "build_s": round(time.time() - tb0, 3)}
+            uw_info = {"bytes": g.get_param("uw_table_bytes"), "isa_shift": args.isa_shift, "build_s": round(time.time() - tb0, 3)}
         except RuntimeError as e:           # optional tables: seeding runs without them (same results, FM extends instead)
             uw_info = {"skipped": str(e)}
         log("unique-walk tables:", uw_info)
-    if pac is not None and args.fast:
-        import ctypes as C
-        DL = args.direct_levels
-        if DL < 0:
-            DL = 2
-            while 4 ** (DL + 5) < 1.3 * ix.seq_len and DL < 13:
-                DL += 1
-        torch.cuda.synchronize()
-        tb0 = time.time()
-        g._check(lib.smem_gpu_build_kmer_tables(g.h, C.c_void_p(pac.data_ptr()), C.c_int64(args.ref_bp), C.c_int(local), C.c_int(DL)))
-        fast_info = {"direct_levels": DL, "deepest_level": DL + 5, "build_s": time.time() - tb0,
-                     "table_bytes": 4 ** (DL + 5) + 4 ** (DL + 4) + (4 ** (DL + 1) - 4) // 3 * 4 + (4 ** (DL + 2) - 4) // 3 * 8}
-        g.set_param("fast", 1)
-        if args.fast_blocks_per_sm:
-            g.set_param("fast_blocks_per_sm", args.fast_blocks_per_sm)
-        if args.fast_slots:
-            g.set_param("fast_slots", args.fast_slots)
-        log("k-mer count pyramid:", fast_info)
+    uw_on = bool(uw_info and "bytes" in uw_info)
     pac = None
     torch.cuda.empty_cache()
-    # pinned host batch + pinned result buffers for the end-to-end leg
+    # the step's batch in pinned host memory, in both forms the C ABI takes: bwa's one byte per base + CSR offsets
+    # (smem_gpu_collect) and the compact wire format (smem_gpu_collect_packed: two bits per base, fixed stride)
     pseq = sg.PinnedArray(lib, (len(seq),), np.uint8); pseq.array[:] = seq
     poffs = sg.PinnedArray(lib, (n + 1,), np.int64); poffs.array[:] = offs
+    tp0 = time.perf_counter()
+    packed = sg.PackedReads(lib, seq, offs, pinned=True, threads=min(ncores, 16))
+    t_pack = time.perf_counter() - tp0
     opt = sg.SeedOpt()
 
     # CPU baseline + full-size parity sample (rank 0 only)
@@ -334,23 +323,24 @@ def main():
         log(f"algorithmic work per read (oracle, {ns} reads): extends={s['extends'] / ns:.1f} blocks={s['blocks'] / ns:.1f} "
             f"intervals={s['intervals'] / ns:.2f} bytes={bytes_per_read:.0f}")
         if rf_info:
-            # what the kernel's two exact shortcuts leave of that work (oracle MODEL of them, exact window counts instead of
+            # what the kernel's exact shortcuts leave of that work (oracle MODEL of them, exact window counts instead of
             # the device's hashed bit table): reported next to the algorithmic figure, which stays the reference algorithm's
-            import ctypes as C
-            uw_on = bool(uw_info and "bytes" in uw_info and g.get_param("unique_walk"))
-            orc.lib.orc_set_skip_kmer(int(rf_info["kmer"])); orc.lib.orc_set_spec_walk(int(g.get_param("spec_walk"))); orc.lib.orc_set_unique_walk(int(uw_on))
+            orc.lib.orc_set_skip_kmer(int(rf_info["kmer"])); orc.lib.orc_set_spec_walk(int(g.get_param("spec_walk"))); orc.lib.orc_set_unique_walk(int(uw_on and g.get_param("unique_walk")))
             try:
                 s2 = orc.collect(seq[: int(offs[ns])], offs[: ns + 1], OSeedOpt(), nthreads=ncores, stats=True)["stats"]
             finally:
                 orc.lib.orc_set_skip_kmer(0); orc.lib.orc_set_spec_walk(0); orc.lib.orc_set_unique_walk(0)
             executed = {"extends_per_read": s2["extends"] / ns, "blocks_per_read": s2["blocks"] / ns,
                         "bytes_per_read": (64.0 * s2["blocks"] + 128.0 * ns + 32.0 * s2["intervals"]) / ns,
-                        "note": "same counting rule applied to the extends left after the repeat filter, the speculative walk and" + (" the unique walks, three gathers each" if uw_on else " (not built here) the unique walks") + " (oracle model)"}
+                        "note": "same counting rule applied to the extends left after the repeat filter, the speculative walk and" + (" the unique walks (three gathers each; the sampled inverse suffix array adds 1.5 extends per walk on average, not counted)" if uw_on else " (not built here) the unique walks") + " (oracle model)"}
             log("executed work per read with the shortcuts (oracle model):", executed)
         got = g.collect(seq[: int(offs[ns])], offs[: ns + 1], opt)
         ok = (np.array_equal(got["read_off"], st["read_off"]) and np.array_equal(got["intv"], st["intv"])
               and np.array_equal(got["step"], st["step"]))
-        parity = {"reads_checked": ns, "bit_exact": bool(ok), "checker": "oracle/liboracle.so"}
+        # ... and the same reads through the compact wire format
+        gp = g.collect_packed(sg.PackedReads(lib, seq[: int(offs[ns])], offs[: ns + 1]), opt)
+        ok = ok and np.array_equal(gp["read_off"], st["read_off"]) and np.array_equal(gp["intv"], st["intv"])
+        parity = {"reads_checked": ns, "bit_exact": bool(ok), "checker": "oracle/liboracle.so", "wire_formats_checked": ["bytes + bwtintv_t", "2-bit reads + 16-byte records"]}
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU intervals differ from the oracle on the bench workload")
         if not args.skip_cpu and world == 1:       # the CPU baseline is a single-GPU-run figure (it would idle the other ranks)
@@ -359,9 +349,9 @@ def main():
             m = min(n, max(20_000, int(probe["reads_per_s"] * args.cpu_seconds)))
             r = cpu_time(eng, seq, offs, m, ncores, OSeedOpt())
             one = cpu_time(eng, seq, offs, min(m, 20_000), 1, OSeedOpt())
-            gk = g.collect(seq[: int(offs[m])], offs[: m + 1], opt, want_step=False)
+            gk = g.collect_packed(sg.PackedReads(lib, seq[: int(offs[m])], offs[: m + 1]), opt)
             ck = orc.checksum(gk["intv"], gk["read_off"])
-            parity.update(reads_checked=m, bit_exact=bool(ok and ck == r["checksum"]), checker=f"oracle + {kind} checksum")
+            parity.update(reads_checked=m, bit_exact=bool(ok and ck == r["checksum"]), checker=f"oracle + {kind} checksum (through the compact wire format)")
             if ck != r["checksum"]:
                 raise SystemExit("PARITY FAILURE: checksum of GPU intervals differs from the CPU arm")
             cpu_baseline = {"value": r["reads_per_s"], "unit": "reads/s", "cores": ncores, "kind": kind,
@@ -377,21 +367,20 @@ def main():
             dist.barrier()
 
     # ---- device-resident leg: inputs staged in HBM before the timed region
-    g.stage(pseq.array, poffs.array)
+    g.stage_packed(packed)
     if args.sweep:
         keep = (g.get_param("blocks_per_sm"), g.get_param("l2_hot_min_intv"), g.get_param("b_cap"))
         for item in args.sweep.split(","):
             f = item.split(":")
             b, hot = f[0], (f[1] if len(f) > 1 and f[1] else "0")
-            g.set_param("reuse", int(f[3]) if len(f) > 3 and f[3] else 0)
             g.set_param("l2_mode", int(f[4]) if len(f) > 4 else 0)
             g.set_param("blocks_per_sm", int(b)); g.set_param("l2_hot_min_intv", int(hot))
             g.set_param("b_cap", int(f[2]) if len(f) > 2 and f[2] else keep[2])
             ms = []
             for _ in range(4):
                 g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
-            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} reuse={g.get_param('reuse')} l2_mode={g.get_param('l2_mode')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
-        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("reuse", 0); g.set_param("l2_mode", 0)
+            log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} l2_mode={g.get_param('l2_mode')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
+        g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("l2_mode", 0)
     for _ in range(max(args.warmup, 3)):
         total = g.run_collect(opt)
     sampler = ClockSampler(local)
@@ -410,142 +399,124 @@ def main():
     if rf_info:                                          # untimed: how many re-seeding passes the filter proved void
         g.set_param("count_skips", 1); g.run_collect(opt)
         rf_info["pass2_skipped_per_step"] = g.get_param("pass2_skipped")
-        if uw_info is not None and "bytes" in uw_info:
+        if uw_on:
             uw_info["walks_per_step"] = g.get_param("unique_walks")
         g.set_param("count_skips", 0)
+    if uw_on and not args.no_extras:                     # untimed: what the tables buy, in kernel time per GB of HBM
+        g.set_param("unique_walk", 0)
+        ms0 = []
+        for _ in range(4):
+            g.run_collect(opt); ms0.append(g.timing()["seed_kernel_ms"])
+        g.set_param("unique_walk", 1)
+        uw_info["seed_kernel_ms_without"] = float(np.mean(ms0[1:]))
+        uw_info["seed_kernel_ms_with"] = float(np.mean(seed_ms))
+        uw_info["ms_gained_per_GB"] = (uw_info["seed_kernel_ms_without"] - uw_info["seed_kernel_ms_with"]) / (uw_info["bytes"] / 1e9)
 
-    # ---- end-to-end leg: host buffers in, host buffers out, copies inside the timed region.  The public call is
-    # smem_gpu_collect on a handle with `--lanes` pipeline lanes on this GPU (shards overlap H2D / kernels / D2H).
-    escaped = g.get_param("escaped_reads")
+    # ---- end-to-end legs: host buffers in, host buffers out, copies inside the timed region, through the public one-call API.
+    # Each of T worker threads owns a handle (sharing the first one's index copy, smem_gpu_share_index -- the reference's
+    # -t N pattern) and its own pinned result buffers, and makes the public call for the steps it is given: one call's
+    # copies overlap another call's kernels (the GPU's kernel turn).
     g_owner = g                             # owns the index and the tables; the end-to-end handles alias them
-    if args.lanes > 1:
-        g = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local] * args.lanes)
-        if args.blocks_per_sm:
-            g.set_param("blocks_per_sm", args.blocks_per_sm)
-        if args.spare_sms >= 0:
-            g.set_param("spare_sms", args.spare_sms)
-        if args.fast_blocks_per_sm:
-            g.set_param("fast_blocks_per_sm", args.fast_blocks_per_sm)
-        g.set_param("fast", 1 if args.fast else 0)
-        g.share_index_from(g_owner)
-    # Each of `--host-threads` worker threads owns a handle (sharing the first one's index copy, smem_gpu_share_index)
-    # and its own pinned result buffers, and makes the public call for the steps it is given: step k's copies overlap
-    # step k+1's kernels.  Every step still copies its inputs H2D and its results D2H inside the timed region.
-    import ctypes as C
-    T = max(1, args.host_threads)
-    workers = [g]
-    for _ in range(1, T):
+    cores_per_rank = max(1, ncores // max(1, world))
+    T = args.host_threads if args.host_threads > 0 else (3 if cores_per_rank >= 4 else 2)
+    workers = []
+    for _ in range(T):
         w = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=[local] * max(1, args.lanes))
         if args.blocks_per_sm:
             w.set_param("blocks_per_sm", args.blocks_per_sm)
-        if args.fast_blocks_per_sm:
-            w.set_param("fast_blocks_per_sm", args.fast_blocks_per_sm)
-        w.set_param("fast", 1 if args.fast else 0)
+        if args.spare_sms >= 0:
+            w.set_param("spare_sms", args.spare_sms)
         w.share_index_from(g_owner)
         workers.append(w)
-    pintvs = [sg.PinnedArray(lib, (total + 1024, 4), np.uint64) for _ in range(T)]
-    proffs = [sg.PinnedArray(lib, (n + 1,), np.int64) for _ in range(T)]
-    pintv, proff = pintvs[0], proffs[0]
+    cap16 = total + total // 16 + 1024
+    prec = [sg.PinnedArray(lib, (cap16, 2), np.uint64) for _ in range(T)]
+    proff32 = [sg.PinnedArray(lib, (n + 1,), np.uint32) for _ in range(T)]
 
-    def e2e_step(t=0):
-        tot = C.c_int64(0)
-        rc = lib.smem_gpu_collect(workers[t].h, C.c_int64(n), pseq.array.ctypes.data_as(C.POINTER(C.c_uint8)),
-                                  poffs.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(opt),
-                                  pintvs[t].array.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(pintvs[t].array.shape[0]),
-                                  proffs[t].array.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(tot))
-        if rc:
-            raise SystemExit(f"smem_gpu_collect failed: {rc} {lib.smem_gpu_last_error(workers[t].h).decode()}")
-        return int(tot.value)
-
-    def e2e_run(k_steps):
-        """k_steps calls of the public API spread over the worker threads; returns the interval count of a step."""
-        if T == 1:
-            r = 0
-            for _ in range(k_steps):
-                r = e2e_step(0)
-            return r
-        res = [0] * T
+    def run_pool(step_fn, k_steps):
+        """k_steps calls spread over the worker threads; a free worker takes the next step (kt_for_batch hands out batches
+        the same way, kthread_batch.c:20-44).  Returns the last result of any worker."""
+        res = [None] * T
         nxt = [0]
         lock = threading.Lock()
+        err = []
         def work(t):
-            # a free worker takes the next step (kt_for_batch hands out batches the same way, kthread_batch.c:20-44): with a
-            # fixed striping the worker that happens to come second can be left with the last two steps, back to back
-            while True:
-                with lock:
-                    k = nxt[0]; nxt[0] += 1
-                if k >= k_steps:
-                    break
-                res[t] = e2e_step(t)
+            try:
+                while True:
+                    with lock:
+                        k = nxt[0]; nxt[0] += 1
+                    if k >= k_steps:
+                        break
+                    res[t] = step_fn(t)
+            except BaseException as e:  # noqa: BLE001
+                err.append(e)
         th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
         for x in th:
             x.start()
         for x in th:
             x.join()
-        return max(res)
+        if err:
+            raise SystemExit(f"end-to-end worker failed: {err[0]!r}")
+        return next((r for r in res if r is not None), None)
 
-    e2e_run(2 * T)
-    sync()
-    t1 = time.perf_counter()
-    tot_e2e = e2e_run(args.steps)
-    sync()
-    dt_e2e = time.perf_counter() - t1
-    te = g.timing()
+    def check_rc(rc, t, what):
+        if rc:
+            raise RuntimeError(f"{what} failed: {rc} {lib.smem_gpu_last_error(workers[t].h).decode()}")
 
-    # ---- optional: the seed-level API (section 8f-1): stage -> collect -> seeds -> D2H of mem_seed_t only
-    seeds_leg = None
-    if args.seeds:
-        g.upload_sa(ix)
-        seed_off = sg.PinnedArray(lib, (n + 1,), np.int64)
-        pseeds = sg.PinnedArray(lib, (8 * n, 2), np.int64)
-        def seeds_step():
-            g.stage(pseq.array, poffs.array)
-            g.run_collect(opt)
-            tot = C.c_int64(0)
-            rc = lib.smem_gpu_seeds(g.h, C.c_int(19), C.c_int64(10000), C.c_void_p(pseeds.array.ctypes.data), C.c_int64(pseeds.array.shape[0]),
-                                    seed_off.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(tot))
-            assert rc == 0, (rc, lib.smem_gpu_last_error(g.h))
-            return int(tot.value)
-        for _ in range(2):
-            seeds_step()
+    def acc_reset():
+        for w in workers:
+            w.set_param("acc_reset", 1)
+
+    def acc_read():
+        """per-call wall time of the stages of the one-call form, averaged over this rank's calls"""
+        c = max(1, sum(w.get_param("acc_calls") for w in workers))
+        f = lambda k: sum(w.get_param(k) for w in workers) / c / 1e3
+        st, fe = f("acc_stage_us"), f("acc_fetch_us")
+        h2d, d2h = sum(w.get_param("acc_h2d_bytes") for w in workers) / c, sum(w.get_param("acc_d2h_bytes") for w in workers) / c
+        return {"h2d_ms": st, "wait_for_kernel_turn_ms": f("acc_turn_us"), "kernels_ms": f("acc_run_us"), "d2h_ms": fe,
+                "h2d_GBps": h2d / max(st, 1e-6) / 1e6, "d2h_GBps": d2h / max(fe, 1e-6) / 1e6}
+
+    def timed_leg(step_fn, k_steps):
+        run_pool(step_fn, 2 * T)
+        acc_reset()
         sync()
-        ts = time.perf_counter()
-        for _ in range(args.steps):
-            n_seeds = seeds_step()
+        t1 = time.perf_counter()
+        r = run_pool(step_fn, k_steps)
         sync()
-        dts = time.perf_counter() - ts
-        seeds_leg = {"value": world * n * args.steps / dts, "unit": "reads/s", "ms_per_step": dts / args.steps * 1e3, "seeds_per_step_per_gpu": n_seeds,
-                     "d2h_bytes_per_step": n_seeds * 16 + (n + 1) * 8, "note": "host reads in -> mem_seed_t {rbeg,qbeg,len} out (min_seed_len 19, max_occ 10000)"}
-        log("seeds leg:", seeds_leg)
-        # ---- section 8f-3: ... -> seeds -> chains (+ mem_chain_flt) on the device, D2H of chains and their seeds
-        chain_off = sg.PinnedArray(lib, (n + 1,), np.int64)
-        pchains = sg.PinnedArray(lib, (4 * n, 3), np.int64)
-        pcseeds = sg.PinnedArray(lib, (8 * n, 2), np.int64)
-        copt = sg.ChainOpt(100, 10000, 19, 0.5, 0.5, 1)
-        def chains_step():
-            g.stage(pseq.array, poffs.array)
-            g.run_collect(opt)
-            tot, nc, ns = C.c_int64(0), C.c_int64(0), C.c_int64(0)
-            rc = lib.smem_gpu_seeds(g.h, C.c_int(19), C.c_int64(10000), None, C.c_int64(0), seed_off.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(tot))
-            assert rc in (0, -5), (rc, lib.smem_gpu_last_error(g.h))          # seeds stay in HBM: only their count comes back
-            rc = lib.smem_gpu_chains(g.h, C.byref(copt), C.c_int64(int(ix.seq_len) // 2), C.c_void_p(pchains.array.ctypes.data), C.c_int64(pchains.array.shape[0]),
-                                     C.c_void_p(pcseeds.array.ctypes.data), C.c_int64(pcseeds.array.shape[0]),
-                                     chain_off.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nc), C.byref(ns))
-            assert rc == 0, (rc, lib.smem_gpu_last_error(g.h))
-            return int(nc.value), int(ns.value)
-        for _ in range(2):
-            chains_step()
-        sync()
-        ts = time.perf_counter()
-        for _ in range(args.steps):
-            n_chains, n_cseeds = chains_step()
-        sync()
-        dts = time.perf_counter() - ts
-        chains_leg = {"value": world * n * args.steps / dts, "unit": "reads/s", "ms_per_step": dts / args.steps * 1e3, "chains_per_step_per_gpu": n_chains,
-                      "chain_seeds_per_step_per_gpu": n_cseeds, "chain_kernels_ms": g.get_param("chain_kernels_us") / 1e3,
-                      "d2h_bytes_per_step": n_chains * 24 + n_cseeds * 16 + (n + 1) * 16,
-                      "note": "host reads in -> mem_chain_t after mem_chain_flt out (w 100, max_chain_gap 10000, mask_level 0.5, chain_drop_ratio 0.5)"}
-        log("chains leg:", chains_leg)
-        seeds_leg["chains"] = chains_leg
+        return time.perf_counter() - t1, r
+
+    def max_over_ranks(x):
+        tt = torch.tensor([x], dtype=torch.float64, device=device)
+        if use_dist:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def gather_ranks(vals):
+        tt = torch.tensor(vals, dtype=torch.float64, device=device)
+        if not use_dist:
+            return [vals]
+        out = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(out, tt)
+        return [[float(v) for v in o.tolist()] for o in out]
+
+    # (1) the headline: compact wire format both ways (SURVEY 8f-4)
+    def step_packed(t):
+        tot = C.c_int64(0)
+        rc = lib.smem_gpu_collect_packed(workers[t].h, C.byref(packed.desc), C.byref(opt), C.c_void_p(prec[t].array.ctypes.data), C.c_int64(cap16),
+                                         C.c_void_p(proff32[t].array.ctypes.data), C.byref(tot))
+        check_rc(rc, t, "smem_gpu_collect_packed")
+        return int(tot.value)
+    dt_e2e, tot_e2e = timed_leg(step_packed, args.steps)
+    te = workers[0].timing()
+    stages = acc_read()
+    stage_keys = list(stages)
+    stages_per_rank = [dict(zip(stage_keys, (round(v, 3) for v in row))) for row in gather_ranks([stages[k] for k in stage_keys])]
+    dt_e2e = max_over_ranks(dt_e2e)
+    e2e_overflow = workers[0].timing()["overflow_reads"]
+    # every worker's last result is the step's result: checksum of rank 0's against the device-resident run
+    if rank == 0:
+        a = g.fetch_packed(total)
+        if not (np.array_equal(a["rec"], prec[0].array[:tot_e2e]) and np.array_equal(a["read_off"], proff32[0].array.astype(np.int64))):
+            raise SystemExit("PARITY FAILURE: end-to-end result differs from the device-resident run")
 
     # ---- optional: every interval of the step against the oracle (BASELINE config 2)
     if args.full_compare and rank == 0:
@@ -554,45 +525,177 @@ def main():
         ixh = fm.BwtIndex(ix.primary, ix.L2, ix.seq_len, ix.bwt_size, ix.words_numpy())
         t0c = time.time()
         want = Oracle(ixh).collect(seq, offs, OSeedOpt(), nthreads=ncores)
-        same = (np.array_equal(want["read_off"], proff.array) and np.array_equal(want["intv"], pintv.array[:tot_e2e]))
+        same = (np.array_equal(want["read_off"], proff32[0].array.astype(np.int64)) and np.array_equal(want["intv"], sg.unpack_intv16(prec[0].array[:tot_e2e])))
         log(f"full compare: {n} reads, {len(want['intv'])} intervals, bit_exact={same} (oracle {time.time() - t0c:.1f}s)")
         parity = dict(parity or {}, full_compare_reads=n, full_compare_intervals=int(len(want["intv"])), full_compare_bit_exact=bool(same))
         if not same:
             raise SystemExit("PARITY FAILURE in --full-compare")
+        del want, ixh
 
-    # ---- optional: batch-size sweep (BASELINE config 5): one smem_gpu_collect call of B reads, host buffers
-    batch_sweep = None
-    if args.batch_sweep and rank == 0:
-        batch_sweep = []
+    extras = {}
+    if not args.no_extras:
+        # (2) bwa's own formats: one byte per base in, bwtintv_t out (the call the link-compatible adapter makes)
+        pintvs = [sg.PinnedArray(lib, (total + 1024, 4), np.uint64) for _ in range(T)]
+        proffs = [sg.PinnedArray(lib, (n + 1,), np.int64) for _ in range(T)]
+        def step_bytes(t):
+            tot = C.c_int64(0)
+            rc = lib.smem_gpu_collect(workers[t].h, C.c_int64(n), pseq.array.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                      poffs.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(opt),
+                                      pintvs[t].array.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(pintvs[t].array.shape[0]),
+                                      proffs[t].array.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(tot))
+            check_rc(rc, t, "smem_gpu_collect")
+            return int(tot.value)
+        d2, _ = timed_leg(step_bytes, args.steps)
+        tb = workers[0].timing(); sb = acc_read()
+        d2 = max_over_ranks(d2)
+        extras["e2e_bwtintv"] = {"value": world * n * args.steps / d2, "unit": "reads/s", "ms_per_step": d2 / args.steps * 1e3, "api": "smem_gpu_collect",
+                                 "h2d_bytes_per_step": int(tb["h2d_bytes"]), "d2h_bytes_per_step": int(tb["d2h_bytes"]), "stages_rank0": {k: round(v, 3) for k, v in sb.items()}}
+        log("e2e, byte reads in / bwtintv_t out:", extras["e2e_bwtintv"])
+        for a_ in pintvs + proffs:
+            a_.free()
+        # (3) compact reads in -> mem_seed_t out (section 8f-1) and (4) -> chains after mem_chain_flt out (section 8f-3)
+        seed_off = [sg.PinnedArray(lib, (n + 1,), np.int64) for _ in range(T)]
+        pseeds = [sg.PinnedArray(lib, (4 * n, 2), np.int64) for _ in range(T)]
+        chain_off = [sg.PinnedArray(lib, (n + 1,), np.int64) for _ in range(T)]
+        pchains = [sg.PinnedArray(lib, (3 * n, 3), np.int64) for _ in range(T)]
+        copt = sg.ChainOpt(100, 10000, 19, 0.5, 0.5, 1)
+        def step_seeds(t, fetch=True):
+            h = workers[t].h
+            check_rc(lib.smem_gpu_stage_reads_packed(h, C.byref(packed.desc)), t, "stage_reads_packed")
+            tot = C.c_int64(0)
+            check_rc(lib.smem_gpu_run_collect(h, C.byref(opt), C.byref(tot)), t, "run_collect")
+            rc = lib.smem_gpu_seeds(h, C.c_int(19), C.c_int64(10000), C.c_void_p(pseeds[t].array.ctypes.data) if fetch else None,
+                                    C.c_int64(pseeds[t].array.shape[0] if fetch else 0), seed_off[t].array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(tot))
+            if rc and not (rc == -5 and not fetch):
+                check_rc(rc, t, "smem_gpu_seeds")
+            return int(tot.value)
+        d3, n_seeds = timed_leg(step_seeds, args.steps)
+        d3 = max_over_ranks(d3)
+        extras["e2e_seeds"] = {"value": world * n * args.steps / d3, "unit": "reads/s", "ms_per_step": d3 / args.steps * 1e3, "api": "smem_gpu_stage_reads_packed + run_collect + seeds",
+                               "seeds_per_step_per_gpu": n_seeds, "h2d_bytes_per_step": packed.h2d_bytes, "d2h_bytes_per_step": n_seeds * 16 + (n + 1) * 8,
+                               "note": "compact reads in -> mem_seed_t {rbeg,qbeg,len} out (min_seed_len 19, max_occ 10000)"}
+        log("e2e, seeds out:", extras["e2e_seeds"])
+        def step_chains(t):
+            step_seeds(t, fetch=False)                   # seeds stay in HBM: only their count comes back
+            nc, ns_ = C.c_int64(0), C.c_int64(0)
+            rc = lib.smem_gpu_chains(workers[t].h, C.byref(copt), C.c_int64(int(ix.seq_len) // 2), C.c_void_p(pchains[t].array.ctypes.data), C.c_int64(pchains[t].array.shape[0]),
+                                     C.c_void_p(pseeds[t].array.ctypes.data), C.c_int64(pseeds[t].array.shape[0]),
+                                     chain_off[t].array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nc), C.byref(ns_))
+            check_rc(rc, t, "smem_gpu_chains")
+            return int(nc.value), int(ns_.value)
+        d4, (n_chains, n_cseeds) = timed_leg(step_chains, args.steps)
+        d4 = max_over_ranks(d4)
+        extras["e2e_chains"] = {"value": world * n * args.steps / d4, "unit": "reads/s", "ms_per_step": d4 / args.steps * 1e3, "api": "... + smem_gpu_chains",
+                                "chains_per_step_per_gpu": n_chains, "chain_seeds_per_step_per_gpu": n_cseeds, "h2d_bytes_per_step": packed.h2d_bytes,
+                                "d2h_bytes_per_step": n_chains * 24 + n_cseeds * 16 + (n + 1) * 16,
+                                "note": "compact reads in -> mem_chain_t after mem_chain_flt out (w 100, max_chain_gap 10000, mask_level 0.5, chain_drop_ratio 0.5)"}
+        log("e2e, chains out:", extras["e2e_chains"])
+        for a_ in seed_off + pseeds + chain_off + pchains:
+            a_.free()
+
+    # ---- where the end-to-end time goes when several GPUs share the host: the copy volumes of a step alone, and next to a running seed kernel
+    pcie = None
+    if args.pcie_probe or world > 1:
+        h_in = torch.empty(packed.h2d_bytes, dtype=torch.uint8).pin_memory(); h_out = torch.empty(16 * tot_e2e + 4 * n, dtype=torch.uint8).pin_memory()
+        d_in = torch.empty_like(h_in, device=device); d_out = torch.empty_like(h_out, device=device)
+        side = torch.cuda.Stream(device)
+        def copies(k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(side):
+                e0.record()
+                for _ in range(k):
+                    d_in.copy_(h_in, non_blocking=True); h_out.copy_(d_out, non_blocking=True)
+                e1.record()
+            return e0, e1
+        sync()
+        e0, e1 = copies(10); e1.synchronize()
+        alone = e0.elapsed_time(e1) / 10
+        sync()
+        stop = [False]
+        def spin():
+            while not stop[0]:
+                g.run_collect(opt)
+        thk = threading.Thread(target=spin); thk.start()
+        time.sleep(0.05)
+        e0, e1 = copies(10); e1.synchronize()
+        stop[0] = True; thk.join()
+        busy = e0.elapsed_time(e1) / 10
+        nb = (h_in.numel() + h_out.numel()) / 1e6
+        rows = gather_ranks([alone, busy])
+        pcie = {"bytes_per_step_MB": nb, "copy_ms_alone_per_rank": [round(r[0], 3) for r in rows], "copy_ms_next_to_seed_kernel_per_rank": [round(r[1], 3) for r in rows],
+                "box_GBps_alone": world * nb / max(r[0] for r in rows), "box_GBps_next_to_seed_kernel": world * nb / max(r[1] for r in rows),
+                "note": "all ranks at once: H2D of a step's compact reads + D2H of its 16-byte records from/to pinned memory on a side stream, 10 rounds; second figure with the device-resident seed kernel looping"}
+        log("pcie probe:", pcie)
+        del h_in, h_out, d_in, d_out
+
+    # ---- BASELINE configs 4 and 5 from the same invocation (single-GPU runs only)
+    if not args.no_extras and world == 1 and rank == 0 and args.read_len == 101 and args.reads >= 1_000_000:
+        # config 5: batch-size sweep, one smem_gpu_collect_packed call of B reads from host buffers, L2 evict_last hint on shallow levels off / on
+        sweep = []
         for hot in (0, 16384):
-            g.set_param("l2_hot_min_intv", hot)
+            workers[0].set_param("l2_hot_min_intv", hot)
             for B in (64, 256, 1024, 4096, 16384, 65536, 262144, 1048576):
-                if B > n:
-                    continue
-                o = poffs.array[: B + 1]
-                s_ = pseq.array[: int(o[-1])]
+                sub = sg.Reads2(B, packed.seq2.ctypes.data, packed.stride, args.read_len, None, None, 0)
                 def call():
                     tot = C.c_int64(0)
-                    rc = lib.smem_gpu_collect(g.h, C.c_int64(B), s_.ctypes.data_as(C.POINTER(C.c_uint8)), o.ctypes.data_as(C.POINTER(C.c_int64)),
-                                              C.byref(opt), pintv.array.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(pintv.array.shape[0]),
-                                              proff.array.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(tot))
+                    rc = lib.smem_gpu_collect_packed(workers[0].h, C.byref(sub), C.byref(opt), C.c_void_p(prec[0].array.ctypes.data), C.c_int64(cap16),
+                                                     C.c_void_p(proff32[0].array.ctypes.data), C.byref(tot))
                     assert rc == 0, rc
                 for _ in range(3):
                     call()
                 reps = 20 if B <= 16384 else 5
-                tb = time.perf_counter()
+                tb_ = time.perf_counter()
                 for _ in range(reps):
                     call()
-                ms = (time.perf_counter() - tb) / reps * 1e3
-                batch_sweep.append({"reads_per_call": B, "l2_hot_min_intv": hot, "latency_ms": round(ms, 3), "reads_per_s": round(B / ms * 1e3)})
-                log(f"batch sweep B={B} l2_hot_min_intv={hot}: {ms:.3f} ms/call -> {B / ms / 1e3:.2f} M reads/s")
-        g.set_param("l2_hot_min_intv", 0)
-
-    # ---- max over ranks
-    times = torch.tensor([dt, dt_e2e, float(np.mean(seed_ms))], dtype=torch.float64, device=device)
-    if use_dist:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e, seed_avg_ms = [float(x) for x in times.tolist()]
+                ms = (time.perf_counter() - tb_) / reps * 1e3
+                sweep.append({"reads_per_call": B, "l2_hot_min_intv": hot, "latency_ms": round(ms, 3), "reads_per_s": round(B / ms * 1e3)})
+        workers[0].set_param("l2_hot_min_intv", 0)
+        extras["config5_batch_sweep"] = {"api": "smem_gpu_collect_packed, one handle, host buffers", "rows": sweep,
+                                         "note": "reads without ambiguous bases only (the sub-batches reuse the step's records without its exception list)" if packed.n_amb else None}
+        log("config 5:", sweep)
+        # config 4: 250 bp reads at 2 % errors on the same index, re-seeding on (-k 19 -r 1.5, split_width 10)
+        if cfg4 is not None:
+            from oracle.binding import Oracle
+            seq4, offs4 = cfg4
+            n4 = len(offs4) - 1
+            g4 = sg.SmemGpu(max_batch_reads=n4, max_read_len=250, devices=[local])
+            g4.share_index_from(g_owner)
+            pk4 = sg.PackedReads(lib, seq4, offs4, pinned=True, threads=min(ncores, 16))
+            fm = importlib.import_module("bwa-mem-harp2_b200.fmindex")
+            ixh = fm.BwtIndex(ix.primary, ix.L2, ix.seq_len, ix.bwt_size, ix.words_numpy())
+            orc = Oracle(ixh)
+            m4 = min(n4, 20_000)
+            tc0 = time.perf_counter()
+            want4 = orc.collect(seq4[: int(offs4[m4])], offs4[: m4 + 1], OSeedOpt(), nthreads=ncores, stats=True)
+            cpu4 = m4 / (time.perf_counter() - tc0)
+            got4 = g4.collect_packed(sg.PackedReads(lib, seq4[: int(offs4[m4])], offs4[: m4 + 1]), opt)
+            ok4 = np.array_equal(got4["intv"], want4["intv"]) and np.array_equal(got4["read_off"], want4["read_off"])
+            if not ok4:
+                raise SystemExit("PARITY FAILURE on the 250 bp configuration")
+            s4 = want4["stats"]
+            g4.stage_packed(pk4)
+            ms4 = []
+            for _ in range(6):
+                tot4 = g4.run_collect(opt); ms4.append(g4.timing()["total_device_ms"])
+            rec4 = sg.PinnedArray(lib, (tot4 + 1024, 2), np.uint64); off4 = sg.PinnedArray(lib, (n4 + 1,), np.uint32)
+            def call4():
+                tot = C.c_int64(0)
+                rc = lib.smem_gpu_collect_packed(g4.h, C.byref(pk4.desc), C.byref(opt), C.c_void_p(rec4.array.ctypes.data), C.c_int64(rec4.array.shape[0]),
+                                                 C.c_void_p(off4.array.ctypes.data), C.byref(tot))
+                assert rc == 0, (rc, lib.smem_gpu_last_error(g4.h))
+            call4()
+            tb_ = time.perf_counter()
+            for _ in range(5):
+                call4()
+            e4 = (time.perf_counter() - tb_) / 5
+            extras["config4_250bp"] = {"workload": f"{n4} simulated 250 bp reads at 2 % substitutions on the same index, -k 19 -r 1.5 (split_len 28, split_width 10)",
+                                       "value": n4 / (float(np.mean(ms4[1:])) * 1e-3), "unit": "reads/s", "device_ms_per_step": float(np.mean(ms4[1:])),
+                                       "e2e_one_handle_reads_per_s": n4 / e4, "intervals_per_read": tot4 / n4, "overflow_reads": int(g4.timing()["overflow_reads"]),
+                                       "algorithmic_bytes_per_read": (64.0 * s4["blocks"] + 128.0 * m4 + 32.0 * s4["intervals"]) / m4,
+                                       "parity": {"reads_checked": m4, "bit_exact": bool(ok4), "checker": "oracle/liboracle.so, entry by entry"},
+                                       "cpu_port_reads_per_s": cpu4, "cpu_cores": ncores}
+            log("config 4:", extras["config4_250bp"])
+            rec4.free(); off4.free(); g4.close(); del orc, ixh
 
     probe = None
     if args.probe and rank == 0:
@@ -602,12 +705,17 @@ def main():
                 probe[f"{bb}B_x{chains}"] = round(g.gather_roofline(bb, 0, chains, 1000), 1)
         log("random-access probe GB/s:", probe)
     rand64 = rand64_split = None
-    e2e_overflow = g.timing()["overflow_reads"]
     if rank == 0:
         # the roofline of the access pattern: dependent 64 B gathers over the whole index, one coalesced request
         # per block (lane pair, 2 x 32 B) -- and, for reference, the same gathers issued as two per-lane requests
         g.set_param("probe_variant", 10); rand64 = g.gather_roofline(64, 0, 2048, 1000)
         g.set_param("probe_variant", 0); rand64_split = g.gather_roofline(64, 0, 2048, 1000)
+
+    # ---- max over ranks
+    times = torch.tensor([dt, float(np.mean(seed_ms))], dtype=torch.float64, device=device)
+    if use_dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt, seed_avg_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
         peaks = {}
@@ -617,23 +725,26 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        traffic = None
+        traffic, traffic_src = None, None
         try:   # dram__bytes_read + dram__bytes_write of seed_kernel from the committed `ncu --set full` capture of this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "seed_traffic.json")))
-            if not (uw_info and "bytes" in uw_info):
+            if not uw_on:
                 tr = tr.get("without_text_index", {})          # the capture of the kernel without the unique-walk tables
             if tr.get("ref_bp") == args.ref_bp and tr.get("reads") == args.reads and tr.get("read_len") == args.read_len:
                 traffic = tr["dram_bytes_per_launch"]
+                traffic_src = "static: profiles/seed_traffic.json (" + tr.get("capture", "ncu --set full capture of this workload") + "), not measured in this run"
         except Exception:
             pass
         value = world * n * args.steps / dt
         achieved = n * bytes_per_read / (seed_avg_ms * 1e-3) / 1e9
+        exec_gbs = n * executed["bytes_per_read"] / (seed_avg_ms * 1e-3) / 1e9 if executed else None
         # the bound that actually holds for this access pattern: DRAM-missing requests per second.
         # requests of the kernel = ncu DRAM bytes / 64 (the sector pairs a lane pair gathers); ceiling = the coalesced 64 B probe
-        request_rate = None
-        if traffic and rand64 and not fast_info:
+        request_rate, frac_req = None, None
+        if traffic and rand64:
             rq = traffic / 64.0 / (seed_avg_ms * 1e-3) / 1e9
-            request_rate = {"achieved_G_per_s": rq, "ceiling_G_per_s": rand64 / 64.0, "frac": rq / (rand64 / 64.0),
+            frac_req = rq / (rand64 / 64.0)
+            request_rate = {"achieved_G_per_s": rq, "ceiling_G_per_s": rand64 / 64.0, "frac": frac_req,
                             "note": "DRAM requests of 64 B per second: ncu dram bytes of the committed capture / 64 / live kernel time, against the coalesced gather probe measured in this run"}
         out = {
             "metric": "smem_seeded_101bp_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -641,13 +752,20 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": world * n * args.steps / dt_e2e, "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
                     "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "pipeline_lanes_per_gpu": args.lanes, "host_threads": T, "intervals": int(tot_e2e)},
+                    "api": "smem_gpu_collect_packed (2-bit reads in, 16-byte interval records out; include/smem_gpu.h)",
+                    "pipeline_lanes_per_gpu": args.lanes, "host_threads": T, "intervals": int(tot_e2e),
+                    "host_pack_s_per_step_untimed": round(t_pack, 4),
+                    "stages_per_rank": stages_per_rank},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic if not fast_info else None, "peak_source": peak_src,
-                         "kernel": "fast_kernel + resolve_kernel (k-mer count pyramid; FM re-run of escaped reads not included)" if fast_info else "seed_kernel<COLLECT>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "frac_executed": exec_gbs / rand64 if (exec_gbs and rand64) else None,
+                         "frac_dram_requests": frac_req,
+                         "frac_notes": "frac = the REFERENCE algorithm's bytes (SURVEY 8d) / kernel time / streaming peak; frac_executed = bytes of the extends the kernel really "
+                                       "executes (oracle model of its exact shortcuts) / kernel time / the coalesced random-gather probe; frac_dram_requests = DRAM requests / s "
+                                       "against the same probe's request rate",
+                         "kernel": "seed_kernel<COLLECT>",
                          "kernel_ms": seed_avg_ms, "algorithmic_bytes_per_read": bytes_per_read, "executed": executed,
-                         "achieved_note": "algorithmic bytes of the REFERENCE algorithm (SURVEY 8d) / kernel time; `executed` and `traffic` show what the kernel really touches",
                          "request_rate": request_rate,
                          "random_access_peak": rand64, "frac_of_random_access": achieved / rand64 if rand64 else None,
                          "random_access_peak_two_requests": rand64_split,
@@ -656,16 +774,15 @@ def main():
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "intervals_per_step_per_gpu": int(total), "overflow_reads": int(overflow), "index_build_s": t_index,
             "blocks_per_sm": g.get_param("blocks_per_sm"), "l2_hot_min_intv": g.get_param("l2_hot_min_intv"),
-            "repeat_filter": rf_info, "unique_walk_tables": uw_info, "cpu_binding": ("%d cpus local to the GPU (NVML): %d..%d" % (len(cpu_binding), cpu_binding[0], cpu_binding[-1])) if cpu_binding else None,
-            "fast_path": dict(fast_info, escaped_reads_per_step=int(escaped), blocks_per_sm=g.get_param("fast_blocks_per_sm")) if fast_info else None,
+            "repeat_filter": rf_info, "unique_walk_tables": uw_info, "hbm_table_bytes": g.get_param("table_bytes"), "hbm_index_bytes": g.get_param("index_bytes"),
+            "cpu_binding": ("%d cpus local to the GPU (NVML): %d..%d" % (len(cpu_binding), cpu_binding[0], cpu_binding[-1])) if cpu_binding else None,
             "device_ms_per_step": float(np.mean(dev_ms)),
         }
+        out.update(extras)
+        if pcie:
+            out["pcie_probe"] = pcie
         if probe:
             out["random_access_probe_gbs"] = probe
-        if batch_sweep:
-            out["batch_sweep"] = batch_sweep
-        if seeds_leg:
-            out["seeds_api"] = seeds_leg
         emit(json.dumps(out))
     if use_dist:
         dist.barrier()

@@ -40,9 +40,8 @@ struct __align__(32) Intv { u64 x0, x1, x2, info; };
 
 struct SeedParams {
 	DevIndex ix;
-	const uint8_t *seq;      // staged reads, one base per byte
-	const long long *offs;   // [n+1]
-	const uint4 *qpack;      // reads re-packed two bases per byte (0..3, else 4; padded with 4), q_stride bytes per read (pack_reads_kernel)
+	const int *rlen;         // [n] read lengths (pack pre-pass)
+	const uint4 *qpack;      // reads re-packed two bases per byte (0..3, > 3 ambiguous; padded with 4), q_stride bytes per read (pack pre-pass)
 	long long n;
 	const int *list;         // optional indirection (overflow re-run): read id = list[k]
 	const int *xs, *min_intvs; // smem1 mode inputs
@@ -62,8 +61,9 @@ struct SeedParams {
 	const u32 *qflags;       // per read, per 32 window starts: bit set = that rf_k-mer window is not vouched for (pack_reads_kernel); nullptr = no filter
 	int rf_k;                // k-mer length (<= 32)
 	// unique-walk tables (smem_kernels.cuh PH_UW_*): text at one base per nibble (eight bases per 32-bit word, first base lowest, like the staged reads), the
-	// full suffix array (row -> text position) and its inverse; nullptr = off
-	const uint4 *uw_text; const u64 *uw_fsa, *uw_isa;
+	// full suffix array (row -> text position) and the inverse sampled every 2^uw_isa_shift positions from the end of the text, both as 33-bit
+	// entries, seven to a 32-byte sector (seven low words + one word of high bits); nullptr = off
+	const uint4 *uw_text; const u32 *uw_fsa, *uw_isa; int uw_isa_shift;
 	int uw_min_run, uw_min_left;   // a walk starts after this many extends of an interval of size 1 and with at least this many read bases left (it costs three gathers)
 	int spec_walk;           // 1 = pass-1 calls that directly follow another walk their longest candidate back alone first (PH_SPEC)
 	int count_skips;         // debug: status[6] counts the re-seeding passes the filter proved void, status[7] the unique walks
@@ -177,33 +177,29 @@ struct Ext { u64 a, b, s; };   // a = x[!is_back], b = x[is_back], s = x[2]
 
 // bwt_extend for one chosen base c, executed by a converged warp of lane pairs (half = lane & 1).
 // in: (a = x[!is_back], b = x[is_back], s = x[2], c) identical in both lanes of a pair; out likewise.
-// w / v hold this lane's sector of the K / L block across calls (last_bk / last_bl = their block numbers): in the
-// backward sweep consecutive prev[] elements are nested intervals, and the small ones sit in the same 128-row
-// block as their predecessor, so the gather is skipped when the block number repeats (REUSE).
-template <bool REUSE>
+// w / v receive this lane's sector of the K / L block.  (Keeping them across calls to skip the gather when the block
+// number repeats was measured: +14 % at equal occupancy, a tie once its registers are paid for -- removed.)
 __device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 pol_hot, u64 pol_cold,
-                                           u32 (&w)[8], u32 (&v)[8], u64 &last_bk, u64 &last_bl, const uint4 *alt = nullptr)
+                                           u32 (&w)[8], u32 (&v)[8], const uint4 *alt = nullptr)
 {
 	const u64 k = a - 1, l = a - 1 + s;
 	const u64 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);   // '$' is not stored (bwt.c:194)
 	const u64 bk = kk >> 7, bl = ll >> 7;
 	const bool same = bk == bl;
-	const bool need_k = !REUSE || alt || bk != last_bk, need_l = !same && (!REUSE || bl != last_bl);
 	// `alt` (unique-walk phases): this lane's gather goes to another table instead; the pair rides on the interval (1,1,1)
 	const uint4 *pk = alt ? alt : ix.blk + bk * 4 + half * 2, *pl = ix.blk + bl * 4 + half * 2;
 	if (hot_min) {                       // uniform branch; ONE load site, the policy is a per-lane operand
 		const u64 policy = s >= hot_min ? pol_hot : pol_cold;
-		if (need_k) ld_sector_hot(w, pk, policy);
-		if (need_l) ld_sector_hot(v, pl, policy);
+		ld_sector_hot(w, pk, policy);
+		if (!same) ld_sector_hot(v, pl, policy);
 	} else {
-		if (need_k) ld_sector(w, pk);
-		if (need_l) ld_sector(v, pl);
+		ld_sector(w, pk);
+		if (!same) ld_sector(v, pl);
 	}
 	if (same) {
 #pragma unroll
 		for (int j = 0; j < 8; ++j) v[j] = w[j];
 	}
-	if (REUSE) { last_bk = alt ? ~0ull : bk; last_bl = bl; }
 	// symbols 0..kk&127 (inclusive) of the block count; this lane owns symbols 64*half .. 64*half+63
 	const int rk = min(max((int)(kk & 127) + 1 - 64 * half, 0), 64), rl = min(max((int)(ll & 127) + 1 - 64 * half, 0), 64);
 	u32 ck = occ_half(w, rk), cl = occ_half(v, rl);

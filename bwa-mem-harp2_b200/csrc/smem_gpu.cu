@@ -7,7 +7,6 @@
 // No CPU fallback exists here: every failure is an error code.
 #include "../../include/smem_gpu.h"
 #include "smem_kernels.cuh"
-#include "smem_fast.cuh"
 #include "smem_chain.cuh"
 #include <algorithm>
 #include <chrono>
@@ -36,14 +35,10 @@ struct DeviceCtx {
 	bool owns_index = true;          // false: d_index aliases the copy of an earlier context on the same GPU
 	// suffix-array samples and the seed-level API (section 8f-1)
 	u64 *d_sa = nullptr; bool owns_sa = true; int sa_shift = -1; u64 n_sa = 0;
-	// k-mer count pyramid of the fast path (smem_fast.cuh)
-	FastTables ft{}; bool has_tables = false, owns_tables = true;
-	int *d_esc = nullptr;
-	int64_t escaped = 0;
 	// repeat filter of the re-seeding pass (smem_repeat.cuh)
 	u32 *d_rf = nullptr; bool owns_rf = true; int rf_k = 0, rf_log2 = 0;
 	// unique-walk tables (PH_UW_* of seed_kernel): nibble text, full suffix array, inverse suffix array
-	u64 *d_uw_text = nullptr, *d_fsa = nullptr, *d_isa = nullptr; bool owns_uw = true; u64 uw_text_len = 0;
+	u64 *d_uw_text = nullptr; u32 *d_fsa = nullptr, *d_isa = nullptr; bool owns_uw = true; u64 uw_text_len = 0; int uw_isa_shift = 2; size_t uw_bytes = 0;
 	u64 rf_text_len = 0;             // length of the text the filter was built from: it is only used with an index of that seq_len
 	int64_t pass2_skipped = 0, uw_walks = 0;
 	uint64_t turn_epoch = 0;         // epoch of the last run in which this lane took part in the kernel turn
@@ -67,9 +62,16 @@ struct DeviceCtx {
 	// batch buffers (capacity fixed at create)
 	int64_t read_cap = 0;
 	size_t seq_cap = 0;
-	uint8_t *d_seq = nullptr;
-	uint4 *d_qpack = nullptr; size_t qpack_bytes = 0;   // reads re-packed two bases per byte (pack_reads_kernel)
+	uint8_t *d_seq = nullptr;        // the caller's reads as they arrived: CSR bytes (in_fmt 0) or 2-bit records (in_fmt 1)
+	uint4 *d_qpack = nullptr; size_t qpack_bytes = 0;   // reads re-packed one base per nibble at a fixed stride (pack pre-pass)
+	int *d_rlen = nullptr;           // read lengths (pack pre-pass)
 	long long *d_offs = nullptr;
+	unsigned short *d_lens = nullptr; AmbEntry *d_amb = nullptr; size_t amb_cap = 0;   // compact wire format: lengths, ambiguous-base list
+	int in_fmt = 0, r2_stride = 0, r2_read_len = 0; bool r2_has_lens = false; long long n_amb = 0;
+	uint4 *d_outp = nullptr; size_t outp_cap = 0; u32 *d_off32 = nullptr;               // 16-byte result records + 32-bit offsets
+	bool want_packed = false, out_valid = false, outp_valid = false;
+	int64_t h2d = 0, d2h = 0;        // bytes of the last stage / fetch of this context
+	double acc_stage_ms = 0, acc_turn_ms = 0, acc_run_ms = 0, acc_fetch_ms = 0; int64_t acc_calls = 0, acc_h2d = 0, acc_d2h = 0;   // wall-time accumulators of the one-call forms
 	int *d_x = nullptr, *d_mi = nullptr, *d_ret = nullptr;
 	int *d_counts = nullptr, *d_overflow = nullptr, *d_status = nullptr;
 	long long *d_off = nullptr;
@@ -123,6 +125,7 @@ struct smem_gpu {
 	int l2_mode = 0;                 // see SeedParams::l2_mode
 	int repeat_filter = 1;           // use the repeat filter (if built) to skip void re-seeding passes in MODE_COLLECT
 	int unique_walk = 1;             // use the unique-walk tables if smem_gpu_build_text_index built them
+	int uw_isa_shift = 2;            // the inverse suffix array of the next smem_gpu_build_text_index is sampled every 2^this positions
 	int uw_min_left = 8, uw_min_run = 3;   // ... for walks with at least this many read bases left, after this many extends of a unique interval
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
@@ -130,11 +133,8 @@ struct smem_gpu {
 	int force_wide = 0;
 	int spare_sms = 0;               // SMs the seed kernel leaves empty when a GPU has several lanes
 	int chain_lanes = 0;             // 1: lane k's seed kernel waits for lane k-1's (no tail overlap)
-	int fast = 0;                    // EXPERIMENTAL, opt-in: use the k-mer count pyramid for MODE_COLLECT when its tables are present
-	                                 // (bit-exact, but measured slower than the FM kernel so far: DESIGN.md section 9)
-	int fast_blocks_per_sm = 4, fast_b_cap = 4, fast_slots = 128;
-	int reuse = 0;                   // keep the last K/L occ sectors in registers and skip the gather when the block repeats:
-	                                 // +14 % at equal occupancy, but the 16 extra registers cost that occupancy (tie) -> off
+	int64_t turn_min_reads = 16384;  // calls with fewer reads per lane do not take the GPU's kernel turn: their few CTAs run next to other calls' kernels
+	bool use_turn = true;
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
 	uint64_t epoch = 0;              // bumped per run; orders the lanes' seed kernels
 	uint64_t stage_epoch = 0;        // bumped per staging; orders the lanes' H2D copies
@@ -162,6 +162,59 @@ template <typename T> int dev_alloc(DeviceCtx &d, T **p, size_t count)
 	return 0;
 }
 
+// Batch buffers of a context: everything whose size follows max_batch_reads / max_read_len (smem_gpu_create, smem_gpu_resize).
+// Device memory per lane: read_cap * (max_len + slot_cap * 32 + 16 * 32 + ~50) bytes of batch buffers plus
+// sm_count * 9 * 64 * 3 * (max_len + 2) * 32 bytes of per-pair list scratch (0.85 GB at 101 bp, 2.1 GB at 250 bp, 8.4 GB at 1024 bp).
+void ctx_free_batch(DeviceCtx &d)
+{
+	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
+	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
+	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
+	cudaFree(d.d_seq); cudaFree(d.d_qpack); cudaFree(d.d_offs); cudaFree(d.d_rlen); cudaFree(d.d_lens); cudaFree(d.d_amb); cudaFree(d.d_outp); cudaFree(d.d_off32);
+	cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
+	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_off); cudaFree(d.d_slots);
+	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_aux); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
+	d.d_k = d.d_kout = nullptr; d.k_cap = 0; d.d_scnt = nullptr; d.d_soff = d.d_sroff = nullptr; d.s_cap = d.sroff_cap = 0; d.d_seeds = nullptr; d.seeds_cap = 0;
+	d.d_cwork = nullptr; d.d_flt = nullptr; d.d_keep = nullptr; d.cwork_cap = 0; d.d_nch = d.d_nkept = nullptr; d.d_coff = d.d_koff = nullptr; d.cread_cap = 0;
+	d.d_chains = nullptr; d.d_cseeds = nullptr; d.chains_cap = 0;
+	d.d_seq = nullptr; d.d_qpack = nullptr; d.qpack_bytes = 0; d.d_offs = nullptr; d.d_rlen = nullptr; d.d_lens = nullptr; d.d_amb = nullptr; d.amb_cap = 0;
+	d.d_outp = nullptr; d.outp_cap = 0; d.d_off32 = nullptr; d.d_x = d.d_mi = d.d_ret = nullptr; d.d_counts = d.d_overflow = nullptr; d.d_off = nullptr;
+	d.d_slots = nullptr; d.slots_cap_alloc = 0; d.d_scratch = nullptr; d.scratch_entries = 0; d.d_out = nullptr; d.d_step = d.d_aux = nullptr; d.out_cap = 0;
+	d.d_tmp = nullptr; d.tmp_bytes = 0; d.d_big = nullptr; d.big_entries = 0; d.d_counts_k = nullptr; d.counts_k_cap = 0;
+	d.read_cap = 0; d.seq_cap = 0; d.n = 0; d.lo = d.hi = 0; d.seeds_valid = d.out_valid = d.outp_valid = false;
+}
+
+int ctx_alloc_batch(DeviceCtx &d, int64_t read_cap, int max_len, int slot_cap)
+{
+	CK(cudaSetDevice(d.dev));
+	d.read_cap = read_cap;
+	d.seq_cap = (size_t)read_cap * (size_t)max_len + 64;
+	int rc;
+	if ((rc = dev_alloc(d, &d.d_seq, d.seq_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_offs, (size_t)read_cap + 1))) return rc;
+	if ((rc = dev_alloc(d, &d.d_rlen, (size_t)read_cap + 1))) return rc;
+	if ((rc = dev_alloc(d, &d.d_x, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_mi, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_ret, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_counts, (size_t)read_cap + 1))) return rc;
+	if ((rc = dev_alloc(d, &d.d_overflow, (size_t)read_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_off, (size_t)read_cap + 1))) return rc;
+	if ((rc = dev_alloc(d, &d.d_slots, (size_t)read_cap * slot_cap))) return rc;
+	d.slots_cap_alloc = slot_cap;
+	d.out_cap = (size_t)read_cap * 16 + 1024;
+	if ((rc = dev_alloc(d, &d.d_out, d.out_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_step, d.out_cap))) return rc;
+	if ((rc = dev_alloc(d, &d.d_aux, d.out_cap))) return rc;
+	// per-pair scratch for the default launch geometry (re-grown in ctx_run if blocks_per_sm is raised): allocating
+	// it lazily would delay the first lane's first kernel by a cudaMalloc
+	d.scratch_entries = (size_t)d.sm_count * 9 * 64 * 3 * (size_t)(max_len + 2);
+	CK(cudaMalloc((void **)&d.d_scratch, d.scratch_entries * sizeof(Intv)));
+	// block sums of the counts -> offsets scan
+	d.tmp_bytes = ((size_t)(read_cap + 1) / SCAN_PER_BLOCK + 2) * sizeof(long long);
+	CK(cudaMalloc(&d.d_tmp, d.tmp_bytes));
+	return 0;
+}
+
 int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int slot_cap)
 {
 	d.dev = dev;
@@ -182,34 +235,10 @@ int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int
 	}
 	CK(cudaEventCreate(&d.ev0)); CK(cudaEventCreate(&d.ev0s)); CK(cudaEventCreate(&d.ev1)); CK(cudaEventCreate(&d.ev2));
 	CK(cudaEventCreateWithFlags(&d.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
-	d.read_cap = read_cap;
-	d.seq_cap = (size_t)read_cap * (size_t)max_len + 64;
 	int rc;
-	if ((rc = dev_alloc(d, &d.d_seq, d.seq_cap))) return rc;
-	if ((rc = dev_alloc(d, &d.d_offs, (size_t)read_cap + 1))) return rc;
-	if ((rc = dev_alloc(d, &d.d_x, (size_t)read_cap))) return rc;
-	if ((rc = dev_alloc(d, &d.d_mi, (size_t)read_cap))) return rc;
-	if ((rc = dev_alloc(d, &d.d_ret, (size_t)read_cap))) return rc;
-	if ((rc = dev_alloc(d, &d.d_counts, (size_t)read_cap + 1))) return rc;
-	if ((rc = dev_alloc(d, &d.d_overflow, (size_t)read_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_status, 8))) return rc;
-	if ((rc = dev_alloc(d, &d.d_esc, (size_t)read_cap))) return rc;
-	if ((rc = dev_alloc(d, &d.d_off, (size_t)read_cap + 1))) return rc;
-	if ((rc = dev_alloc(d, &d.d_slots, (size_t)read_cap * slot_cap))) return rc;
-	d.slots_cap_alloc = slot_cap;
-	d.out_cap = (size_t)read_cap * 16 + 1024;
-	if ((rc = dev_alloc(d, &d.d_out, d.out_cap))) return rc;
-	if ((rc = dev_alloc(d, &d.d_step, d.out_cap))) return rc;
-	if ((rc = dev_alloc(d, &d.d_aux, d.out_cap))) return rc;
 	CK(cudaMallocHost((void **)&d.h_status, 128));
-	// per-pair scratch for the default launch geometry (re-grown in ctx_run if blocks_per_sm is raised): allocating
-	// it lazily would delay the first lane's first kernel by a cudaMalloc
-	d.scratch_entries = (size_t)d.sm_count * 9 * 64 * 3 * (size_t)(max_len + 2);
-	CK(cudaMalloc((void **)&d.d_scratch, d.scratch_entries * sizeof(Intv)));
-	// block sums of the counts -> offsets scan
-	d.tmp_bytes = ((size_t)(read_cap + 1) / SCAN_PER_BLOCK + 2) * sizeof(long long);
-	CK(cudaMalloc(&d.d_tmp, d.tmp_bytes));
-	return 0;
+	return ctx_alloc_batch(d, read_cap, max_len, slot_cap);
 }
 
 void ctx_free(DeviceCtx &d)
@@ -217,16 +246,10 @@ void ctx_free(DeviceCtx &d)
 	cudaSetDevice(d.dev);
 	if (d.owns_index) cudaFree(d.d_index);
 	if (d.owns_sa) cudaFree(d.d_sa);
-	if (d.owns_tables && d.has_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
-	cudaFree(d.d_esc);
 	if (d.owns_rf) cudaFree(d.d_rf);
 	if (d.owns_uw) { cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
-	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
-	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
-	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
-	cudaFree(d.d_seq); cudaFree(d.d_qpack); cudaFree(d.d_offs); cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
-	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_status); cudaFree(d.d_off); cudaFree(d.d_slots);
-	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_aux); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
+	ctx_free_batch(d);
+	cudaFree(d.d_status);
 	if (d.h_status) cudaFreeHost(d.h_status);
 	if (d.ev0) cudaEventDestroy(d.ev0);
 	if (d.ev0s) cudaEventDestroy(d.ev0s);
@@ -274,93 +297,20 @@ int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 }
 
 
-// K-mer count pyramid (smem_fast.cuh) built on the device from the 2-bit forward text (`.pac` of the reference,
-// bntseq.c:268-273 doubles it with its reverse complement).  pac: (l_pac + 3) / 4 bytes on the host (src_device < 0)
-// or on CUDA device src_device.
-int ctx_build_tables(DeviceCtx &d, const uint8_t *pac, int64_t l_pac, int src_device, int DL)
-{
-	CK(cudaSetDevice(d.dev));
-	if (d.has_tables && d.owns_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
-	d.ft = FastTables{}; d.has_tables = false; d.owns_tables = true;
-	const int K = DL + 1, LP = DL + 4, D = DL + 5;
-	const long long n = 2 * l_pac;
-	const size_t pac_bytes = (size_t)((l_pac + 3) / 4);
-	uint8_t *d_pac = nullptr;
-	u64 *tw = nullptr, *bsum = nullptr;
-	u32 *cntK = nullptr, *cnt = nullptr;
-	u64 *cum = nullptr;
-	uint8_t *pyr = nullptr, *top = nullptr;
-	auto fail = [&](int rc) { cudaFree(d_pac == pac ? nullptr : d_pac); cudaFree(tw); cudaFree(bsum); cudaFree(cntK); cudaFree(cnt); cudaFree(cum); cudaFree(pyr); cudaFree(top); return rc; };
-#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); d.err = b_; return fail(e_ == cudaErrorMemoryAllocation ? SMEM_GPU_E_NOMEM : SMEM_GPU_E_CUDA); } } while (0)
-	if (src_device == d.dev) d_pac = const_cast<uint8_t *>(pac);
-	else {
-		CKT(cudaMalloc((void **)&d_pac, pac_bytes));
-		if (src_device < 0) CKT(cudaMemcpyAsync(d_pac, pac, pac_bytes, cudaMemcpyHostToDevice, d.stream));
-		else CKT(cudaMemcpyPeerAsync(d_pac, d.dev, pac, src_device, pac_bytes, d.stream));
-	}
-	// the last D symbols of T are the reverse complement of the first D symbols of the forward text
-	uint8_t head[8] = {0};
-	CKT(cudaMemcpyAsync(head, d_pac, std::min<size_t>(pac_bytes, 8), cudaMemcpyDeviceToHost, d.stream));
-	CKT(stream_wait(d));
-	TailCodes tails{};
-	for (int a = 1; a <= D && a < 20; ++a) {
-		u64 code = 0;
-		for (int k = 0; k < a; ++k) { const int o = a - 1 - k; code = (code << 2) | (u64)(3 - ((head[o >> 2] >> ((~o & 3) << 1)) & 3)); }
-		tails.code[a] = code;
-	}
-	const long long n_words = (n + 31) / 32 + 2;
-	const size_t n_lvl = (size_t)lvl_off(K), n_cum = (size_t)lvl_off(K + 1);       // entries of levels 1..DL / 1..DL+1
-	CKT(cudaMalloc((void **)&tw, (size_t)n_words * 8));
-	CKT(cudaMalloc((void **)&cntK, ((size_t)1 << (2 * K)) * 4));
-	CKT(cudaMalloc((void **)&cnt, n_lvl * 4));
-	CKT(cudaMalloc((void **)&cum, n_cum * 8));
-	CKT(cudaMalloc((void **)&pyr, (size_t)1 << (2 * LP)));
-	CKT(cudaMalloc((void **)&top, (size_t)1 << (2 * D)));
-	const long long nbK = (((long long)1 << (2 * K)) + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK;
-	CKT(cudaMalloc((void **)&bsum, (size_t)(nbK + 2) * 8));
-	CKT(cudaMemsetAsync(cntK, 0, ((size_t)1 << (2 * K)) * 4, d.stream));
-	CKT(cudaMemsetAsync(pyr, 0, (size_t)1 << (2 * LP), d.stream));
-	CKT(cudaMemsetAsync(top, 0, (size_t)1 << (2 * D), d.stream));
-	pack_text_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, tw, n_words);
-	kmer_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(tw, n, DL, cntK, pyr, top);
-	CKT(cudaGetLastError());
-	// levels DL .. 1 by summing children; x[0] of every level by an exclusive scan
-	for (int L = K; L >= 1; --L) {
-		const long long nL = (long long)1 << (2 * L);
-		const u32 *src = L == K ? cntK : cnt + lvl_off(L);
-		if (L > 1) {
-			const long long np = nL / 4;
-			kmer_reduce_kernel<<<(unsigned)((np + 255) / 256), 256, 0, d.stream>>>(src, cnt + lvl_off(L - 1), np, tails.code[L - 1]);
-		}
-		const int nb = (int)((nL + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
-		cum_local_kernel<<<nb, SCAN_TPB, 0, d.stream>>>(src, nL, cum + lvl_off(L), bsum);
-		scan_bsum_kernel<<<1, SCAN_TPB, 0, d.stream>>>((long long *)bsum, nb);
-		cum_add_kernel<<<(unsigned)((nL + 255) / 256), 256, 0, d.stream>>>(cum + lvl_off(L), nL, bsum, L, tails);
-		CKT(cudaGetLastError());
-	}
-	// entries next to a suffix of T shorter than their level: unknown (see bwa-mem-harp2_b200/kmer_tables.py)
-	for (int a = K; a < LP; ++a) CKT(cudaMemsetAsync(pyr + (tails.code[a] << (2 * (LP - a))), 255, (size_t)1 << (2 * (LP - a)), d.stream));
-	CKT(cudaMemsetAsync(top + (tails.code[LP] << 2), 255, 4, d.stream));
-	CKT(stream_wait(d));
-#undef CKT
-	if (d_pac != pac) cudaFree(d_pac);
-	cudaFree(tw); cudaFree(cntK); cudaFree(bsum);
-	d.ft.cnt = cnt; d.ft.cum = cum; d.ft.pyr = pyr; d.ft.top = top; d.ft.DL = DL;
-	d.has_tables = true;
-	return 0;
-}
-
-// Unique-walk tables: the text, one base per nibble (pack_text_nib_kernel), and the full suffix array / inverse suffix
-// array expanded from the samples on the device (fsa_build_kernel).  8 bytes per row each.
-int ctx_build_text_index(DeviceCtx &d, const uint8_t *pac, long long l_pac, int src_device)
+// Unique-walk tables: the text, one base per nibble (pack_text_nib_kernel), the full suffix array and the inverse suffix
+// array sampled every 2^isa_shift positions, expanded from the samples on the device (fsa_build_kernel) as 33-bit entries:
+// 0.5 + 4.57 + 4.57 / 2^isa_shift bytes per text position (3.1 Gbp, shift 2: 3.1 + 28.3 + 7.1 = 38.5 GB).
+int ctx_build_text_index(DeviceCtx &d, const uint8_t *pac, long long l_pac, int src_device, int isa_shift)
 {
 	CK(cudaSetDevice(d.dev));
 	if (d.owns_uw) { cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
-	d.d_uw_text = d.d_fsa = d.d_isa = nullptr; d.owns_uw = true; d.uw_text_len = 0;
+	d.d_uw_text = nullptr; d.d_fsa = d.d_isa = nullptr; d.owns_uw = true; d.uw_text_len = 0; d.uw_bytes = 0;
 	const long long n = 2 * l_pac;
+	if ((unsigned long long)n >= (1ull << 33)) { d.err = "text too long for 33-bit suffix-array entries (seq_len >= 2^33): unique-walk tables not built"; return SMEM_GPU_E_ARG; }
 	const size_t pac_bytes = (size_t)((l_pac + 3) / 4);
 	uint8_t *d_pac = nullptr;
-	u64 *tw = nullptr, *fsa = nullptr, *isa = nullptr;
+	u64 *tw = nullptr;
+	u32 *fsa = nullptr, *isa = nullptr;
 	auto fail = [&](int rc) { cudaFree(d_pac == pac ? nullptr : d_pac); cudaFree(tw); cudaFree(fsa); cudaFree(isa); return rc; };
 #define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[512]; snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); d.err = b_; return fail(e_ == cudaErrorMemoryAllocation ? SMEM_GPU_E_NOMEM : SMEM_GPU_E_CUDA); } } while (0)
 	if (src_device == d.dev) d_pac = const_cast<uint8_t *>(pac);
@@ -370,22 +320,27 @@ int ctx_build_text_index(DeviceCtx &d, const uint8_t *pac, long long l_pac, int 
 		else CKT(cudaMemcpyPeerAsync(d_pac, d.dev, pac, src_device, pac_bytes, d.stream));
 	}
 	const long long n_words = ((n + 63) / 64 + 2) * 8;                   // 32-bit words of eight bases: whole 32-byte sectors, two spare ones past the end
+	const size_t fsa_bytes = ((size_t)(n + 1) / 7 + 2) * 32, isa_bytes = (((size_t)n >> isa_shift) / 7 + 2) * 32;
 	CKT(cudaMalloc((void **)&tw, (size_t)n_words * 4));
-	CKT(cudaMalloc((void **)&fsa, (size_t)(n + 4) * 8));
-	CKT(cudaMalloc((void **)&isa, (size_t)(n + 4) * 8));
+	CKT(cudaMalloc((void **)&fsa, fsa_bytes));
+	CKT(cudaMalloc((void **)&isa, isa_bytes));
+	CKT(cudaMemsetAsync(fsa, 0, fsa_bytes, d.stream));
+	CKT(cudaMemsetAsync(isa, 0, isa_bytes, d.stream));
 	pack_text_nib_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, reinterpret_cast<u32 *>(tw), n_words);
 	CKT(cudaGetLastError());
 	CKT(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	const long long n_sa = (long long)d.n_sa;
 	const int grid = (int)std::min<long long>((long long)d.sm_count * 8, (n_sa + 63) / 64);
-	fsa_build_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, n_sa, fsa, isa, d.d_status);
+	fsa_build_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, n_sa, fsa, isa, isa_shift, d.d_status);
 	CKT(cudaGetLastError());
 	CKT(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CKT(stream_wait(d));
 #undef CKT
 	if (d_pac != pac) cudaFree(d_pac);
+	d_pac = nullptr;
 	if (d.h_status[2] != 0) { d.err = "suffix-array walk did not terminate (corrupt index or samples?)"; return fail(SMEM_GPU_E_INTERNAL); }
-	d.d_uw_text = tw; d.d_fsa = fsa; d.d_isa = isa; d.uw_text_len = (u64)n;
+	d.d_uw_text = tw; d.d_fsa = fsa; d.d_isa = isa; d.uw_text_len = (u64)n; d.uw_isa_shift = isa_shift;
+	d.uw_bytes = (size_t)n_words * 4 + fsa_bytes + isa_bytes;
 	return 0;
 }
 
@@ -455,74 +410,120 @@ int ctx_build_repeat_filter(DeviceCtx &d, const uint8_t *pac, long long l_pac, i
 	return 0;
 }
 
-int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi);
+// What the caller staged: CSR bytes (fmt 0: smem_gpu_collect / smem1 / trace) or the compact wire format (fmt 1: smem_reads2_t).
+struct BatchIn {
+	int fmt = 0;
+	const uint8_t *seq = nullptr; const int64_t *offs = nullptr; const int32_t *x = nullptr, *mi = nullptr;
+	const smem_reads2_t *r2 = nullptr;
+};
+
+int ctx_stage_inner(DeviceCtx &d, const BatchIn &in);
 
 // Lanes of one GPU enqueue their H2D copies in lane order (the copy engine is FIFO), so lane 0's reads land
 // first and the seed kernels become ready in priority order.
-int ctx_stage(DeviceCtx &d, smem_gpu &h, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
+int ctx_stage(DeviceCtx &d, smem_gpu &h, const BatchIn &in)
 {
 	if (d.prev_lane) {
 		std::unique_lock<std::mutex> lk(h.lane_mu);
 		h.lane_cv.wait(lk, [&] { return d.prev_lane->stage_issued == h.stage_epoch; });
 	}
-	const int rc = ctx_stage_inner(d, seq, offs, x, mi);
+	const int rc = ctx_stage_inner(d, in);
 	if (d.stage_issued != h.stage_epoch) { std::lock_guard<std::mutex> lk(h.lane_mu); d.stage_issued = h.stage_epoch; h.lane_cv.notify_all(); }
 	return rc;
 }
 
-int ctx_stage_inner(DeviceCtx &d, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
+// H2D only: nothing here walks the batch on the CPU -- read lengths are validated by the pack pre-pass on the device
+// (status[5], reported by the run).
+int ctx_stage_inner(DeviceCtx &d, const BatchIn &in)
 {
 	CK(cudaSetDevice(d.dev));
 	d.n = d.hi - d.lo;
 	d.total = 0;
+	d.in_fmt = in.fmt;
+	d.h2d = 0;
 	if (d.n == 0) return 0;
-	d.seq_base = offs[d.lo];
-	const size_t nbytes = (size_t)(offs[d.hi] - offs[d.lo]);
-	if (nbytes > d.seq_cap || d.n > d.read_cap) { d.err = "batch exceeds the capacity given to smem_gpu_create"; return SMEM_GPU_E_CAPACITY; }
-	for (int64_t i = d.lo; i < d.hi; ++i) {          // every per-read buffer on the device is sized from max_read_len
-		const int64_t l = offs[i + 1] - offs[i];
-		if (l < 0 || l > d.owner->max_len) { d.err = "a read is longer than max_read_len (or offs is not monotone)"; return l < 0 ? SMEM_GPU_E_ARG : SMEM_GPU_E_CAPACITY; }
-	}
-	if (nbytes) CK(cudaMemcpyAsync(d.d_seq, seq + d.seq_base, nbytes, cudaMemcpyHostToDevice, d.stream));
-	CK(cudaMemcpyAsync(d.d_offs, offs + d.lo, (size_t)(d.n + 1) * 8, cudaMemcpyHostToDevice, d.stream));
-	if (x) {
-		CK(cudaMemcpyAsync(d.d_x, x + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
-		CK(cudaMemcpyAsync(d.d_mi, mi + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
+	if (d.n > d.read_cap) { d.err = "batch exceeds the capacity given to smem_gpu_create"; return SMEM_GPU_E_CAPACITY; }
+	if (in.fmt == 0) {
+		d.seq_base = in.offs[d.lo];
+		const long long span = in.offs[d.hi] - in.offs[d.lo];
+		if (span < 0) { d.err = "offs is not monotone"; return SMEM_GPU_E_ARG; }
+		const size_t nbytes = (size_t)span;
+		if (nbytes > d.seq_cap) { d.err = "batch exceeds the capacity given to smem_gpu_create (a read longer than max_read_len?)"; return SMEM_GPU_E_CAPACITY; }
+		if (nbytes) CK(cudaMemcpyAsync(d.d_seq, in.seq + d.seq_base, nbytes, cudaMemcpyHostToDevice, d.stream));
+		CK(cudaMemcpyAsync(d.d_offs, in.offs + d.lo, (size_t)(d.n + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+		d.h2d = (int64_t)nbytes + (d.n + 1) * 8;
+		if (in.x) {
+			CK(cudaMemcpyAsync(d.d_x, in.x + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
+			CK(cudaMemcpyAsync(d.d_mi, in.mi + d.lo, (size_t)d.n * 4, cudaMemcpyHostToDevice, d.stream));
+			d.h2d += d.n * 8;
+		}
+	} else {
+		const smem_reads2_t &r = *in.r2;
+		const size_t nbytes = (size_t)d.n * (size_t)r.stride;
+		if (nbytes > d.seq_cap) { d.err = "batch exceeds the capacity given to smem_gpu_create"; return SMEM_GPU_E_CAPACITY; }
+		d.seq_base = 0; d.r2_stride = r.stride; d.r2_read_len = r.read_len; d.r2_has_lens = r.lens != nullptr;
+		CK(cudaMemcpyAsync(d.d_seq, r.seq2 + (size_t)d.lo * (size_t)r.stride, nbytes, cudaMemcpyHostToDevice, d.stream));
+		d.h2d = (int64_t)nbytes;
+		if (r.lens) {
+			if (!d.d_lens) CK(cudaMalloc((void **)&d.d_lens, ((size_t)d.read_cap + 1) * sizeof(unsigned short)));
+			CK(cudaMemcpyAsync(d.d_lens, r.lens + d.lo, (size_t)d.n * 2, cudaMemcpyHostToDevice, d.stream));
+			d.h2d += d.n * 2;
+		}
+		// ambiguous bases of this shard: the list is sorted by read, so the shard's entries are one contiguous range
+		const smem_amb_t *a0 = r.amb, *a1 = r.amb + (r.amb ? r.n_amb : 0);
+		if (r.amb && r.n_amb > 0) {
+			a0 = std::lower_bound(r.amb, r.amb + r.n_amb, (uint32_t)d.lo, [](const smem_amb_t &e, uint32_t v) { return e.read < v; });
+			a1 = std::lower_bound(a0, r.amb + r.n_amb, (uint32_t)d.hi, [](const smem_amb_t &e, uint32_t v) { return e.read < v; });
+		}
+		d.n_amb = (long long)(a1 - a0);
+		if (d.n_amb > 0) {
+			if ((size_t)d.n_amb > d.amb_cap) {
+				if (d.d_amb) CK(cudaFree(d.d_amb));
+				d.d_amb = nullptr; d.amb_cap = 0;
+				const size_t cap = (size_t)d.n_amb + (size_t)d.n_amb / 2 + 1024;
+				CK(cudaMalloc((void **)&d.d_amb, cap * sizeof(AmbEntry)));
+				d.amb_cap = cap;
+			}
+			CK(cudaMemcpyAsync(d.d_amb, a0, (size_t)d.n_amb * sizeof(AmbEntry), cudaMemcpyHostToDevice, d.stream));
+			d.h2d += d.n_amb * (int64_t)sizeof(AmbEntry);
+		}
 	}
 	{ std::lock_guard<std::mutex> lk(d.owner->lane_mu); d.stage_issued = d.owner->stage_epoch; d.owner->lane_cv.notify_all(); }
 	CK(stream_wait(d));
 	return 0;
 }
 
-template <int MODE, bool WIDE, bool REUSE>
+// Launch-bounds variants of seed_kernel that are compiled in: the default geometry (9 CTAs of 128 threads per SM, 56
+// registers), one step down (8, 64 registers) and a roomy fallback (6, 80 registers).  make ALL_BOUNDS=1 adds the rest for
+// occupancy sweeps; "blocks_per_sm" only accepts what was compiled.
+#ifdef SMEM_ALL_BOUNDS
+static const int kSeedBounds[] = {3, 4, 5, 6, 7, 8, 9, 10, 12};
+#else
+static const int kSeedBounds[] = {6, 8, 9};
+#endif
+
+template <int MODE, bool WIDE>
 int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem)
 {
-#define LAUNCH(B)                                                                                                                  \
-	do {                                                                                                                           \
-		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-		seed_kernel<MODE, B, WIDE, REUSE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
+#define LAUNCH(B)                                                                                                         \
+	do {                                                                                                                  \
+		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+		seed_kernel<MODE, B, WIDE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
 	} while (0)
-#ifdef SMEM_QUICK_BUILD          /* development builds (make QUICK=1): one launch-bounds variant only */
-	(void)blocks_per_sm;
-	LAUNCH(9);
-#else
 	switch (blocks_per_sm) {
+#ifdef SMEM_ALL_BOUNDS
+	case 3: LAUNCH(3); break;
 	case 4: LAUNCH(4); break;
 	case 5: LAUNCH(5); break;
-	case 6: LAUNCH(6); break;
 	case 7: LAUNCH(7); break;
-	case 8: LAUNCH(8); break;
-	case 9: LAUNCH(9); break;
 	case 10: LAUNCH(10); break;
 	case 12: LAUNCH(12); break;
-#if SEED_BLOCK == 64
-	case 14: LAUNCH(14); break;
-	case 16: LAUNCH(16); break;
-	case 18: LAUNCH(18); break;
 #endif
-	default: LAUNCH(3); break;
+	case 6: LAUNCH(6); break;
+	case 8: LAUNCH(8); break;
+	case 9: LAUNCH(9); break;
+	default: d.err = "blocks_per_sm variant not compiled in"; return SMEM_GPU_E_ARG;
 	}
-#endif
 #undef LAUNCH
 	CK(cudaGetLastError());
 	++d.launches;
@@ -530,10 +531,15 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 }
 
 template <int MODE>
-int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide, bool reuse)
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide)
 {
-	if (reuse) return wide ? launch_seed_w<MODE, true, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, true>(d, p, blocks_per_sm, grid, smem);
-	return wide ? launch_seed_w<MODE, true, false>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false, false>(d, p, blocks_per_sm, grid, smem);
+	return wide ? launch_seed_w<MODE, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false>(d, p, blocks_per_sm, grid, smem);
+}
+
+int launch_seed_mode(DeviceCtx &d, int mode, const SeedParams &p, int bps, int grid, size_t smem, bool wide)
+{
+	return mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide)
+	     : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide) : launch_seed<MODE_TRACE>(d, p, bps, grid, smem, wide);
 }
 
 // Several handles on one GPU (one per host thread, smem_gpu_share_index): the seed kernels of ONE call run as a block.
@@ -545,6 +551,7 @@ DevTurn g_turn[64];
 
 void turn_acquire(DeviceCtx &d, smem_gpu &h)
 {
+	if (!h.use_turn) return;
 	DevTurn &t = g_turn[d.dev & 63];
 	std::unique_lock<std::mutex> lk(t.mu);
 	t.cv.wait(lk, [&] { return t.owner == nullptr || t.owner == &h; });
@@ -589,13 +596,30 @@ int ctx_run(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *opt)
 	return rc;
 }
 
+// 16-byte result records need every SA coordinate < 2^33 and query positions < 2^14 (smem_intv16_t)
+static bool packed_out_ok(const DeviceCtx &d, const smem_gpu &h) { return d.ix.seq_len < (1ull << 33) && h.max_len < (1 << 14); }
+
+int ensure_packed_out(DeviceCtx &d)
+{
+	if (d.outp_cap < d.out_cap) {
+		if (d.d_outp) CK(cudaFree(d.d_outp));
+		d.d_outp = nullptr; d.outp_cap = 0;
+		CK(cudaMalloc((void **)&d.d_outp, d.out_cap * sizeof(uint4)));
+		d.outp_cap = d.out_cap;
+	}
+	if (!d.d_off32) CK(cudaMalloc((void **)&d.d_off32, ((size_t)d.read_cap + 2) * sizeof(u32)));
+	return 0;
+}
+
 int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *opt)
 {
 	CK(cudaSetDevice(d.dev));
 	d.mode = mode; d.launches = 0; d.overflow = 0; d.seed_ms = d.total_ms = 0; d.total = 0;
-	d.seeds_valid = false;
+	d.seeds_valid = false; d.out_valid = d.outp_valid = false;
 	if (d.n == 0) return 0;
 	if (!d.has_index) { d.err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
+	const bool packed_out = d.want_packed;
+	if (packed_out && (mode != MODE_COLLECT || !packed_out_ok(d, h))) { d.err = "16-byte result records need seq_len < 2^33 and max_read_len < 2^14"; return SMEM_GPU_E_ARG; }
 	const int bps = h.blocks_per_sm;
 	// several lanes on this GPU: the persistent seed kernel leaves `spare_sms` SMs empty, so that the finished
 	// lane's scan / compaction kernels run next to the following lane's seed kernel (measured: with every SM
@@ -634,8 +658,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	}
 	SeedParams p{};
 	p.ix = d.ix;
-	p.seq = d.d_seq - d.seq_base;
-	p.offs = d.d_offs;
+	p.rlen = d.d_rlen;
 	p.n = d.n;
 	p.list = nullptr;
 	p.xs = d.d_x; p.min_intvs = d.d_mi; p.ret = d.d_ret;
@@ -653,7 +676,9 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const bool use_rf = mode == MODE_COLLECT && h.repeat_filter && d.d_rf && d.rf_text_len == d.ix.seq_len;   // (a filter of another text is ignored)
 	p.qflags = nullptr; p.rf_k = d.rf_k; p.count_skips = h.count_skips; p.spec_walk = h.spec_walk;
 	const bool use_uw = mode != MODE_SMEM1 && h.unique_walk && d.d_fsa && d.uw_text_len == d.ix.seq_len;
-	p.uw_text = use_uw ? reinterpret_cast<const uint4 *>(d.d_uw_text) : nullptr; p.uw_fsa = d.d_fsa; p.uw_isa = d.d_isa; p.uw_min_left = h.uw_min_left; p.uw_min_run = use_uw ? h.uw_min_run : 0x7fffffff;
+	p.uw_text = use_uw ? reinterpret_cast<const uint4 *>(d.d_uw_text) : nullptr; p.uw_fsa = d.d_fsa; p.uw_isa = d.d_isa; p.uw_isa_shift = d.uw_isa_shift; p.uw_min_left = h.uw_min_left;
+	// (the PH_UW_LF steps read the bases in front of the sampled row from the read: the pattern must be longer than the sampling distance)
+	p.uw_min_run = use_uw ? std::max(h.uw_min_run, (1 << d.uw_isa_shift) - 1) : 0x7fffffff;
 	{
 		const size_t bytes_q = (size_t)d.read_cap * q_stride, bytes = bytes_q + (size_t)d.read_cap * (q_stride >> 4) * 4;   // packed reads | window flags
 		if (bytes > d.qpack_bytes) {
@@ -665,18 +690,39 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		p.qpack = d.d_qpack;
 		if (use_rf) p.qflags = reinterpret_cast<u32 *>(reinterpret_cast<uint8_t *>(d.d_qpack) + bytes_q);
 	}
+	if (packed_out) { const int rc0 = ensure_packed_out(d); if (rc0) return rc0; }
 
-	turn_acquire(d, h);
-	CK(cudaEventRecord(d.ev0, d.stream));
-	{   // reads -> two bases per byte at a fixed stride (the seed kernels stage a read with 16-byte copies)
-		const long long chunks = (long long)d.n * (q_stride >> 4);
-		pack_reads_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, d.stream>>>(p.seq, p.offs, d.n, q_stride >> 4, d.d_qpack,
-		                                                                          d.d_rf, d.rf_k, d.rf_log2, const_cast<u32 *>(p.qflags));
-		CK(cudaGetLastError());
-		++d.launches;
+	{
+		const auto tw0 = std::chrono::steady_clock::now();
+		turn_acquire(d, h);
+		d.acc_turn_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
 	}
+	CK(cudaEventRecord(d.ev0, d.stream));
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
 	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
+	{   // pack pre-pass: the caller's reads -> one base per nibble at a fixed stride + lengths (+ the repeat filter's window flags)
+		const int cpr = q_stride >> 4;
+		const long long chunks = (long long)d.n * cpr;
+		const unsigned gridp = (unsigned)((chunks + 255) / 256);
+		if (d.in_fmt == 0)
+			pack_bytes_kernel<<<gridp, 256, 0, d.stream>>>(d.d_seq - d.seq_base, d.d_offs, d.n, cpr, h.max_len, d.d_qpack, d.d_rlen, d.d_status);
+		else {
+			unpack2_kernel<<<gridp, 256, 0, d.stream>>>(d.d_seq, d.r2_stride, d.r2_has_lens ? d.d_lens : nullptr, d.r2_read_len, d.n, cpr, h.max_len,
+			                                            d.d_qpack, d.d_rlen, d.d_status);
+			if (d.n_amb > 0) {
+				amb_patch_kernel<<<(unsigned)((d.n_amb + 255) / 256), 256, 0, d.stream>>>(d.d_amb, d.n_amb, d.lo, d.n, q_stride,
+				                                                                          reinterpret_cast<u32 *>(d.d_qpack), d.d_rlen, d.d_status);
+				++d.launches;
+			}
+		}
+		CK(cudaGetLastError());
+		++d.launches;
+		if (use_rf) {
+			window_flags_kernel<<<gridp, 256, 0, d.stream>>>(d.d_qpack, d.d_rlen, d.n, cpr, d.d_rf, d.rf_k, d.rf_log2, const_cast<u32 *>(p.qflags));
+			CK(cudaGetLastError());
+			++d.launches;
+		}
+	}
 	if (d.prev_lane && h.chain_lanes) {
 		std::unique_lock<std::mutex> lk(h.lane_mu);
 		h.lane_cv.wait(lk, [&] { return d.prev_lane->seed_issued == h.epoch; });
@@ -684,57 +730,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		CK(cudaStreamWaitEvent(d.stream, d.prev_lane->ev1, 0));
 	}
 	int rc = 0;
-	d.escaped = 0;
 	CK(cudaEventRecord(d.ev0s, d.stream));          // after the pack pre-pass: seed_ms is the seed kernel's own duration
-	const bool use_fast = mode == MODE_COLLECT && h.fast && d.has_tables && !wide && h.max_len < 32768 && d.ft.DL + 5 <= 18;
-	if (use_fast) {
-		// k-mer count pyramid (smem_fast.cuh): the table-driven kernel, then the interval resolution; reads it gives up
-		// on (a table said "unknown") join the overflow list and are seeded by the FM kernel below
-		FastParams fp{};
-		fp.s = p; fp.t = d.ft; fp.esc = d.d_esc;
-		fp.q2_words = (h.max_len + 15) / 16 + 2;
-		fp.esc_cap = std::min(h.slot_cap, 32);
-		fp.s.b_cap = h.fast_b_cap;
-		fp.s.q_stride = (8 * fp.q2_words + 15) / 16 * 16;
-		const int q2_bytes = (4 * fp.q2_words + 15) / 16 * 16;
-		fp.s.pair_stride = (FH_BYTES + fp.s.b_cap * 16 + FS_BYTES + fp.s.q_stride + q2_bytes + 15) / 16 * 16;
-		fp.n_slots = h.fast_slots;
-		const size_t smem_f = FAST_HDR + (size_t)fp.n_slots * fp.s.pair_stride;
-		if (smem_f > smem_budget) { d.err = "read length too large for the shared-memory staging of one CTA"; return SMEM_GPU_E_CAPACITY; }
-		const int fb = h.fast_blocks_per_sm;
-		const int grid_f = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * fb, (d.n + fp.n_slots - 1) / fp.n_slots);
-		const size_t need_f = (size_t)d.sm_count * fb * fp.n_slots * 3 * scratch_cap;
-		if (need_f > d.scratch_entries) {
-			if (d.d_scratch) CK(cudaFree(d.d_scratch));
-			d.d_scratch = nullptr; d.scratch_entries = 0;
-			CK(cudaMalloc((void **)&d.d_scratch, need_f * sizeof(Intv)));
-			d.scratch_entries = need_f;
-			fp.s.scratch = d.d_scratch; p.scratch = d.d_scratch;
-		}
-		CK(cudaMemsetAsync(d.d_esc, 0, (size_t)d.n * sizeof(int), d.stream));
-#define LAUNCH_F(B) do { CK(cudaFuncSetAttribute(fast_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
-		fast_kernel<B><<<grid_f, FAST_TPB, smem_f, d.stream>>>(fp); } while (0)
-#ifdef SMEM_QUICK_BUILD
-		(void)fb; LAUNCH_F(4);
-#else
-		switch (fb) {
-		case 2: LAUNCH_F(2); break;
-		case 4: LAUNCH_F(4); break;
-		case 5: LAUNCH_F(5); break;
-		case 6: LAUNCH_F(6); break;
-		case 8: LAUNCH_F(8); break;
-		default: LAUNCH_F(3); break;
-		}
-#endif
-#undef LAUNCH_F
-		CK(cudaGetLastError());
-		const long long threads = (long long)d.n * 8;
-		resolve_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(fp);
-		CK(cudaGetLastError());
-		d.launches += 2;
-	} else
-		rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, h.reuse != 0)
-		   : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, h.reuse != 0) : launch_seed<MODE_TRACE>(d, p, bps, grid, smem, wide, false);
+	rc = launch_seed_mode(d, mode, p, bps, grid, smem, wide);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
 	lane_mark_issued(d, h);
@@ -744,9 +741,11 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 8 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 	CK(stream_wait(d));
 	const double t_status = tms();
+	if (d.h_status[5] & 1) { d.err = "a read is longer than max_read_len (or offs is not monotone / a length exceeds the record stride)"; return SMEM_GPU_E_CAPACITY; }
+	if (d.h_status[5] & 2) { d.err = "an ambiguous-base entry names a read outside its shard (is the list sorted by read?)"; return SMEM_GPU_E_ARG; }
 	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
 	const int n_over = d.h_status[1];
-	d.overflow = n_over; d.escaped = use_fast ? d.h_status[5] : 0;
+	d.overflow = n_over;
 	d.pass2_skipped = d.h_status[6]; d.uw_walks = d.h_status[7];
 	int big_cap = 0;
 	if (n_over > 0) {
@@ -776,8 +775,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
 			p2.overflow_list = d.d_counts_k + n_over;
 			const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
-			rc = mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p2, bps, grid2, smem, wide, h.reuse != 0)
-			   : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p2, bps, grid2, smem, wide, h.reuse != 0) : launch_seed<MODE_TRACE>(d, p2, bps, grid2, smem, wide, false);
+			rc = launch_seed_mode(d, mode, p2, bps, grid2, smem, wide);
 			if (rc) return rc;
 			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 			CK(stream_wait(d));
@@ -810,18 +808,28 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		CK(cudaMalloc((void **)&d.d_out, d.out_cap * sizeof(Intv)));
 		CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
 		CK(cudaMalloc((void **)&d.d_aux, d.out_cap * sizeof(unsigned short)));
+		if (packed_out) { const int rc0 = ensure_packed_out(d); if (rc0) return rc0; }
 	}
+	if (packed_out && (unsigned long long)d.total >= (1ull << 32)) { d.err = "more than 2^32 intervals in one shard: use the 32-byte form"; return SMEM_GPU_E_CAPACITY; }
 	{
 		const long long threads = (long long)d.n * 8;
-		compact_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
-		                                                                        d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
+		if (packed_out)
+			compact_packed_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
+			                                                                               d.d_outp, d.d_off32);
+		else
+			compact_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
+			                                                                        d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
 		CK(cudaGetLastError());
 		++d.launches;
 	}
 	if (n_over > 0) {
 		const long long threads = (long long)n_over * big_cap;
-		compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
-		                                                                             d.d_off, d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
+		if (packed_out)
+			compact_list_packed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
+			                                                                                    d.d_off, d.d_outp);
+		else
+			compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
+			                                                                             d.d_off, d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
 		CK(cudaGetLastError());
 		++d.launches;
 	}
@@ -830,6 +838,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	// there first would hold every SM and they would wait for it to drain
 	turn_release(d);
 	CK(stream_wait(d));
+	(packed_out ? d.outp_valid : d.out_valid) = true;
 	if (trace) fprintf(stderr, "[smem_gpu trace]   lane %d run: status +%.2f scan +%.2f compact +%.2f ms after the seed launch\n", d.lane, t_status, t_scan, tms());
 	CK(cudaEventElapsedTime(&d.seed_ms, d.ev0s, d.ev1));
 	CK(cudaEventElapsedTime(&d.total_ms, d.ev0, d.ev2));
@@ -839,14 +848,42 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 int ctx_fetch(DeviceCtx &d, smem_intv_t *intv_out, int64_t *read_off, uint16_t *step_out, int32_t *ret, long long base, uint16_t *aux_out = nullptr)
 {
 	CK(cudaSetDevice(d.dev));
+	d.d2h = 0;
 	if (d.n == 0) return 0;
+	if (!d.out_valid) { d.err = "the resident results are in the 16-byte form: fetch them with smem_gpu_fetch_packed"; return SMEM_GPU_E_ARG; }
 	CK(cudaMemcpyAsync(read_off + d.lo, d.d_off, (size_t)d.n * 8, cudaMemcpyDeviceToHost, d.stream));   // read_off[n] is set by the caller
-	if (intv_out && d.total) CK(cudaMemcpyAsync(intv_out + base, d.d_out, (size_t)d.total * sizeof(Intv), cudaMemcpyDeviceToHost, d.stream));
-	if (step_out && d.total) CK(cudaMemcpyAsync(step_out + base, d.d_step, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream));
-	if (aux_out && d.total) CK(cudaMemcpyAsync(aux_out + base, d.d_aux, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream));
-	if (ret) CK(cudaMemcpyAsync(ret + d.lo, d.d_ret, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream));
+	d.d2h = d.n * 8;
+	if (intv_out && d.total) { CK(cudaMemcpyAsync(intv_out + base, d.d_out, (size_t)d.total * sizeof(Intv), cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.total * 32; }
+	if (step_out && d.total) { CK(cudaMemcpyAsync(step_out + base, d.d_step, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.total * 2; }
+	if (aux_out && d.total) { CK(cudaMemcpyAsync(aux_out + base, d.d_aux, (size_t)d.total * 2, cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.total * 2; }
+	if (ret) { CK(cudaMemcpyAsync(ret + d.lo, d.d_ret, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.n * 4; }
 	CK(stream_wait(d));
 	if (base) for (int64_t i = d.lo; i < d.hi; ++i) read_off[i] += base;
+	return 0;
+}
+
+// 16-byte records + 32-bit offsets; results of a run that compacted into the 32-byte form are converted on the device first
+int ctx_fetch_packed(DeviceCtx &d, smem_gpu &h, smem_intv16_t *out, uint32_t *read_off, long long base)
+{
+	CK(cudaSetDevice(d.dev));
+	d.d2h = 0;
+	if (d.n == 0) return 0;
+	if (!d.outp_valid) {
+		if (!d.out_valid || d.mode != MODE_COLLECT || !packed_out_ok(d, h) || (unsigned long long)d.total >= (1ull << 32)) {
+			d.err = "no resident results that fit 16-byte records"; return SMEM_GPU_E_ARG;
+		}
+		const int rc0 = ensure_packed_out(d);
+		if (rc0) return rc0;
+		const long long threads = std::max<long long>(d.total, d.n + 1);
+		intv16_from_dense_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_out, d.total, d.d_off, d.n, d.d_outp, d.d_off32);
+		CK(cudaGetLastError());
+		d.outp_valid = true;
+	}
+	CK(cudaMemcpyAsync(read_off + d.lo, d.d_off32, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream));
+	d.d2h = d.n * 4;
+	if (out && d.total) { CK(cudaMemcpyAsync(out + base, d.d_outp, (size_t)d.total * 16, cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.total * 16; }
+	CK(stream_wait(d));
+	if (base) for (int64_t i = d.lo; i < d.hi; ++i) read_off[i] += (uint32_t)base;
 	return 0;
 }
 
@@ -872,24 +909,41 @@ void shard(smem_gpu *h, int64_t n)
 	}
 }
 
-int do_stage(smem_gpu *h, int64_t n, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi)
+int check_batch(smem_gpu *h, const BatchIn &in, int64_t n)
 {
-	if (!h || n < 0 || (n > 0 && (!seq || !offs))) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
+	if (!h || n < 0) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
+	if (in.fmt == 0) { if (n > 0 && (!in.seq || !in.offs)) { h->err = "bad argument"; return SMEM_GPU_E_ARG; } }
+	else {
+		const smem_reads2_t *r = in.r2;
+		if (!r || r->n_reads != n || (n > 0 && !r->seq2) || r->stride < 1 || (!r->lens && (r->read_len < 0 || r->read_len > 4 * r->stride)) ||
+		    r->n_amb < 0 || (r->n_amb > 0 && !r->amb) || n >= (1ll << 32)) { h->err = "bad smem_reads2_t"; return SMEM_GPU_E_ARG; }
+	}
 	if (n > h->max_batch) { h->err = "batch larger than max_batch_reads"; return SMEM_GPU_E_CAPACITY; }
-	shard(h, n);
-	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->stage_epoch; }
-	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_stage(d, *h, seq, offs, x, mi); });
-	if (rc) return rc;
-	h->staged = n; h->ran = false;
-	h->h2d_bytes = n ? (offs[n] - offs[0]) + (n + (int64_t)h->devs.size()) * 8 + (x ? n * 8 : 0) : 0;
 	return 0;
 }
 
-int do_run(smem_gpu *h, int mode, const smem_seed_opt_t *opt, int64_t *total_out)
+int64_t sum_h2d(const smem_gpu *h) { int64_t t = 0; for (auto &d : h->devs) t += d.h2d; return t; }
+int64_t sum_d2h(const smem_gpu *h) { int64_t t = 0; for (auto &d : h->devs) t += d.d2h; return t; }
+
+int do_stage(smem_gpu *h, int64_t n, const BatchIn &in)
+{
+	int rc = check_batch(h, in, n);
+	if (rc) return rc;
+	shard(h, n);
+	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->stage_epoch; }
+	rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_stage(d, *h, in); });
+	if (rc) return rc;
+	h->staged = n; h->ran = false;
+	h->h2d_bytes = sum_h2d(h);
+	return 0;
+}
+
+int do_run(smem_gpu *h, int mode, const smem_seed_opt_t *opt, int64_t *total_out, bool packed_out = false)
 {
 	if (h->staged < 0) { h->err = "nothing staged"; return SMEM_GPU_E_ARG; }
 	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; }
-	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_run(d, *h, mode, opt); });
+	h->use_turn = h->staged >= h->turn_min_reads * (int64_t)h->devs.size();
+	int rc = for_each_device(h, [&](DeviceCtx &d) { d.want_packed = packed_out; return ctx_run(d, *h, mode, opt); });
 	if (rc) return rc;
 	int64_t tot = 0;
 	for (auto &d : h->devs) tot += d.total;
@@ -914,7 +968,26 @@ int do_fetch(smem_gpu *h, smem_intv_t *intv_out, int64_t cap, int64_t *read_off,
 	});
 	if (rc) return rc;
 	read_off[h->staged] = tot;
-	h->d2h_bytes = (h->staged + (int64_t)h->devs.size()) * 8 + (fits ? tot * (32 + (step_out ? 2 : 0)) : 0) + (ret ? h->staged * 4 : 0);
+	h->d2h_bytes = sum_d2h(h);
+	if (!fits) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	return 0;
+}
+
+int do_fetch_packed(smem_gpu *h, smem_intv16_t *out, int64_t cap, uint32_t *read_off, int64_t *total_out)
+{
+	if (!h->ran) { h->err = "no results: call a run function first"; return SMEM_GPU_E_ARG; }
+	if (!read_off) { h->err = "read_off is required"; return SMEM_GPU_E_ARG; }
+	int64_t tot = 0;
+	std::vector<long long> base(h->devs.size());
+	for (size_t k = 0; k < h->devs.size(); ++k) { base[k] = tot; tot += h->devs[k].total; }
+	if (total_out) *total_out = tot;
+	if (tot >= (1ll << 32)) { h->err = "more than 2^32 intervals: use the 32-byte form"; return SMEM_GPU_E_CAPACITY; }
+	const bool fits = tot <= cap && (out || tot == 0);
+	read_off[0] = 0;
+	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_fetch_packed(d, *h, fits ? out : nullptr, read_off, base[&d - &h->devs[0]]); });
+	if (rc) return rc;
+	read_off[h->staged] = (uint32_t)tot;
+	h->d2h_bytes = sum_d2h(h);
 	if (!fits) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
 	return 0;
 }
@@ -922,29 +995,40 @@ int do_fetch(smem_gpu *h, smem_intv_t *intv_out, int64_t cap, int64_t *read_off,
 // One-call form: every context (GPU, or pipeline lane of a GPU) runs stage -> run -> fetch for its shard on its own
 // host thread, so that one lane's copies overlap another lane's kernels.  A lane needs the interval totals of all
 // lanes before it to know where its results go; those finish first anyway (lanes run in order).
-int do_collect(smem_gpu *h, int mode, int64_t n, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *mi,
-               const smem_seed_opt_t *opt, smem_intv_t *intv_out, int64_t cap, int64_t *read_off, uint16_t *step_out, int32_t *ret,
-               int64_t *total_out, uint16_t *aux_out = nullptr)
+// out16 / read_off32 != nullptr selects the 16-byte result records.
+struct CollectOut {
+	smem_intv_t *intv = nullptr; int64_t *read_off = nullptr; uint16_t *step = nullptr, *aux = nullptr; int32_t *ret = nullptr;
+	smem_intv16_t *intv16 = nullptr; uint32_t *read_off32 = nullptr;
+	int64_t cap = 0; int64_t *total = nullptr;
+};
+
+int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_seed_opt_t *opt, const CollectOut &out)
 {
-	if (!h || n < 0 || (n > 0 && (!seq || !offs)) || !read_off) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
-	if (n > h->max_batch) { h->err = "batch larger than max_batch_reads"; return SMEM_GPU_E_CAPACITY; }
+	const bool packed = out.read_off32 != nullptr;
+	if (!h || (!packed && !out.read_off)) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
+	int rc = check_batch(h, in, n);
+	if (rc) return rc;
 	shard(h, n);
 	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; ++h->stage_epoch; }
 	const size_t G = h->devs.size();
+	h->use_turn = n >= h->turn_min_reads * (int64_t)G;
 	std::vector<long long> totals(G, 0);
 	std::vector<char> ran(G, 0);
 	std::mutex mu;
 	std::condition_variable cv;
 	bool overflow = false;
-	read_off[0] = 0;
+	if (packed) out.read_off32[0] = 0; else out.read_off[0] = 0;
 	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
 	const auto t0 = std::chrono::steady_clock::now();
 	auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
-	int rc = for_each_device(h, [&](DeviceCtx &d) {
+	const bool have_out = packed ? out.intv16 != nullptr : out.intv != nullptr;
+	rc = for_each_device(h, [&](DeviceCtx &d) {
 		const size_t k = &d - &h->devs[0];
 		const double ta = ms();
-		int r = ctx_stage(d, *h, seq, offs, x, mi);
+		d.want_packed = packed;
+		int r = ctx_stage(d, *h, in);
 		const double tb = ms();
+		const double turn0 = d.acc_turn_ms;
 		if (!r) r = ctx_run(d, *h, mode, opt);
 		else if (d.hi > d.lo) { turn_acquire(d, *h); turn_release(d); }    // keep the turn's lane count right
 		const double tc = ms();
@@ -955,24 +1039,32 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const uint8_t *seq, const int64
 			cv.notify_all();
 			cv.wait(lk, [&] { for (size_t j = 0; j < k; ++j) if (!ran[j]) return false; return true; });
 			for (size_t j = 0; j < k; ++j) base += totals[j];
-			if (!r && base + d.total > cap) overflow = true;
+			if (!r && base + d.total > out.cap) overflow = true;
 		}
 		if (r) return r;
-		const bool fits = intv_out && base + d.total <= cap;
-		r = ctx_fetch(d, fits ? intv_out : nullptr, read_off, fits ? step_out : nullptr, ret, base, fits ? aux_out : nullptr);
+		const bool fits = have_out && base + d.total <= out.cap;
+		const double tc2 = ms();
+		if (packed) {
+			if (base + d.total >= (1ll << 32)) { d.err = "more than 2^32 intervals: use the 32-byte form"; return (int)SMEM_GPU_E_CAPACITY; }
+			r = ctx_fetch_packed(d, *h, fits ? out.intv16 : nullptr, out.read_off32, base);
+		} else
+			r = ctx_fetch(d, fits ? out.intv : nullptr, out.read_off, fits ? out.step : nullptr, out.ret, base, fits ? out.aux : nullptr);
+		const double td = ms();
+		d.acc_stage_ms += tb - ta; d.acc_run_ms += (tc - tb) - (d.acc_turn_ms - turn0); d.acc_fetch_ms += td - tc2; d.acc_calls += 1;
+		d.acc_h2d += d.h2d; d.acc_d2h += d.d2h;
 		if (trace) fprintf(stderr, "[smem_gpu trace] lane %zu: start %.2f staged %.2f ran %.2f (seed %.2f ms, dev %.2f ms) fetched %.2f\n", k, ta, tb, tc,
-		                   d.seed_ms, d.total_ms, ms());
+		                   d.seed_ms, d.total_ms, td);
 		return r;
 	});
 	h->staged = n; h->ran = rc == 0;
 	if (rc) return rc;
 	long long tot = 0;
 	for (auto t : totals) tot += t;
-	read_off[n] = tot;
-	if (total_out) *total_out = tot;
-	h->h2d_bytes = n ? (offs[n] - offs[0]) + (n + (int64_t)G) * 8 + (x ? n * 8 : 0) : 0;
-	h->d2h_bytes = n * 8 + (overflow ? 0 : tot * (32 + (step_out ? 2 : 0))) + (ret ? n * 4 : 0);
-	if (overflow || (tot > 0 && !intv_out)) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	if (packed) out.read_off32[n] = (uint32_t)tot; else out.read_off[n] = tot;
+	if (out.total) *out.total = tot;
+	h->h2d_bytes = sum_h2d(h);
+	h->d2h_bytes = sum_d2h(h);
+	if (overflow || (tot > 0 && !have_out)) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
 	return 0;
 }
 
@@ -988,6 +1080,10 @@ int smem_gpu_device_count(void)
 	return n;
 }
 
+// result slots per read of the first pass: 101 bp reads emit 11 intervals on average, 250 bp reads 48; rarer, longer lists take
+// the overflow re-run (ctx_run_inner), so this only trades HBM (read_cap * slot_cap * 32 bytes) against how often that runs
+static int default_slot_cap(int max_read_len) { return std::min(256, std::max(64, (max_read_len / 2 + 31) / 32 * 32)); }
+
 int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int64_t max_batch_reads, int max_read_len)
 {
 	if (!out || n_devices < 1 || n_devices > 64 || max_batch_reads < 1 || max_read_len < 1 || max_read_len > 65535) return SMEM_GPU_E_ARG;
@@ -996,7 +1092,7 @@ int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int6
 	smem_gpu *h = new (std::nothrow) smem_gpu();
 	if (!h) return SMEM_GPU_E_NOMEM;
 	h->max_batch = max_batch_reads; h->max_len = max_read_len;
-	h->slot_cap = std::min(256, std::max(128, (max_read_len + 31) / 32 * 32));   // long reads emit more intervals (250 bp: 48 on average); rarer, longer lists take the re-run
+	h->slot_cap = default_slot_cap(max_read_len);
 	h->devs.resize(n_devices);
 	const int64_t per = (max_batch_reads + n_devices - 1) / n_devices;
 	for (int k = 0; k < n_devices; ++k) {
@@ -1016,6 +1112,25 @@ int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int6
 	}
 	for (auto &d : h->devs) { d.lanes_on_dev = 0; for (auto &o : h->devs) d.lanes_on_dev += o.dev == d.dev; }
 	*out = h;
+	return 0;
+}
+
+// Re-size the batch buffers of a handle in place (index, samples and accelerator tables stay): the adapter grows its
+// handles when a batch or a read arrives that is larger than what they were created for.
+int smem_gpu_resize(smem_gpu_t *h, int64_t max_batch_reads, int max_read_len)
+{
+	if (!h || max_batch_reads < 1 || max_read_len < 1 || max_read_len > 65535) return SMEM_GPU_E_ARG;
+	const int64_t per = (max_batch_reads + (int64_t)h->devs.size() - 1) / (int64_t)h->devs.size();
+	const int slot_cap = default_slot_cap(max_read_len);
+	for (auto &d : h->devs) {
+		cudaSetDevice(d.dev);
+		cudaStreamSynchronize(d.stream);
+		ctx_free_batch(d);
+		const int rc = ctx_alloc_batch(d, per, max_read_len, slot_cap);
+		if (rc) { h->err = "device " + std::to_string(d.dev) + ": " + d.err; h->staged = -1; h->ran = false; return rc; }
+	}
+	h->max_batch = max_batch_reads; h->max_len = max_read_len; h->slot_cap = slot_cap;
+	h->staged = -1; h->ran = false;
 	return 0;
 }
 
@@ -1092,6 +1207,7 @@ int ctx_seeds_run(DeviceCtx &d, int min_seed_len, u64 max_occ)
 	d.seeds_valid = false;
 	if (d.n == 0) { d.seeds_valid = true; return 0; }
 	if (d.sa_shift < 0) { d.err = "suffix-array samples not uploaded"; return SMEM_GPU_E_NOINDEX; }
+	if (!d.out_valid) { d.err = "the resident results are 16-byte records (smem_gpu_collect_packed): run smem_gpu_run_collect for the seed-level API"; return SMEM_GPU_E_ARG; }
 	const long long total = d.total;
 	if ((size_t)total + 1 > d.s_cap) {
 		if (d.d_scnt) CK(cudaFree(d.d_scnt));
@@ -1224,7 +1340,7 @@ static int upload_all(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device
 		if (d.d_rf && d.owns_rf) { cudaSetDevice(d.dev); cudaFree(d.d_rf); }
 		d.d_rf = nullptr; d.owns_rf = true; d.rf_k = d.rf_log2 = 0; d.rf_text_len = 0;
 		if (d.owns_uw) { cudaSetDevice(d.dev); cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
-		d.d_uw_text = d.d_fsa = d.d_isa = nullptr; d.owns_uw = true; d.uw_text_len = 0;
+		d.d_uw_text = nullptr; d.d_fsa = d.d_isa = nullptr; d.owns_uw = true; d.uw_text_len = 0; d.uw_bytes = 0;
 	}
 	int rc = for_each_device(h, [&](DeviceCtx &d) {
 		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
@@ -1267,12 +1383,10 @@ int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src)
 		if (d.d_sa && d.owns_sa) cudaFree(d.d_sa);
 		d.d_index = o->d_index; d.owns_index = false; d.index_bytes = o->index_bytes; d.ix = o->ix; d.has_index = true;
 		d.d_sa = o->d_sa; d.owns_sa = false; d.sa_shift = o->sa_shift; d.n_sa = o->n_sa;
-		if (d.has_tables && d.owns_tables) { cudaFree((void *)d.ft.cnt); cudaFree((void *)d.ft.cum); cudaFree((void *)d.ft.pyr); cudaFree((void *)d.ft.top); }
-		d.ft = o->ft; d.has_tables = o->has_tables; d.owns_tables = false;
 		if (d.d_rf && d.owns_rf) cudaFree(d.d_rf);
 		d.d_rf = o->d_rf; d.owns_rf = false; d.rf_k = o->rf_k; d.rf_log2 = o->rf_log2; d.rf_text_len = o->rf_text_len;
 		if (d.owns_uw) { cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
-		d.d_uw_text = o->d_uw_text; d.d_fsa = o->d_fsa; d.d_isa = o->d_isa; d.owns_uw = false; d.uw_text_len = o->uw_text_len;
+		d.d_uw_text = o->d_uw_text; d.d_fsa = o->d_fsa; d.d_isa = o->d_isa; d.owns_uw = false; d.uw_text_len = o->uw_text_len; d.uw_isa_shift = o->uw_isa_shift; d.uw_bytes = o->uw_bytes;
 	}
 	return 0;
 }
@@ -1286,13 +1400,13 @@ int smem_gpu_build_text_index(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, 
 	}
 	int rc = for_each_device(h, [&](DeviceCtx &d) {
 		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
-		return ctx_build_text_index(d, pac, l_pac, src_device);
+		return ctx_build_text_index(d, pac, l_pac, src_device, h->uw_isa_shift);
 	});
 	if (rc) return rc;
 	for (auto &d : h->devs)
 		for (auto &o : h->devs) {
 			if (&o == &d) break;
-			if (o.dev == d.dev) { d.d_uw_text = o.d_uw_text; d.d_fsa = o.d_fsa; d.d_isa = o.d_isa; d.owns_uw = false; d.uw_text_len = o.uw_text_len; break; }
+			if (o.dev == d.dev) { d.d_uw_text = o.d_uw_text; d.d_fsa = o.d_fsa; d.d_isa = o.d_isa; d.owns_uw = false; d.uw_text_len = o.uw_text_len; d.uw_isa_shift = o.uw_isa_shift; d.uw_bytes = o.uw_bytes; break; }
 		}
 	return 0;
 }
@@ -1302,9 +1416,15 @@ int smem_gpu_get_text_index(smem_gpu_t *h, int which, uint64_t *out, int64_t n_o
 	if (!h || !out || which < 0 || which > 1) return SMEM_GPU_E_ARG;
 	DeviceCtx &d = h->devs[0];
 	if (!d.d_fsa) { h->err = "no text index built"; return SMEM_GPU_E_NOINDEX; }
-	if (n_out != (int64_t)d.uw_text_len + 1) return SMEM_GPU_E_ARG;
+	const int64_t want = which ? (int64_t)(d.uw_text_len >> d.uw_isa_shift) + 1 : (int64_t)d.uw_text_len + 1;
+	if (n_out != want) return SMEM_GPU_E_ARG;
 	cudaSetDevice(d.dev);
-	return cudaMemcpy(out, which ? d.d_isa : d.d_fsa, (size_t)n_out * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : SMEM_GPU_E_CUDA;
+	u64 *tmp = nullptr;
+	if (cudaMalloc((void **)&tmp, (size_t)n_out * 8) != cudaSuccess) return SMEM_GPU_E_NOMEM;
+	uw_unpack_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, d.stream>>>(which ? d.d_isa : d.d_fsa, n_out, tmp);
+	const bool ok = cudaMemcpyAsync(out, tmp, (size_t)n_out * 8, cudaMemcpyDeviceToHost, d.stream) == cudaSuccess && stream_wait(d) == cudaSuccess;
+	cudaFree(tmp);
+	return ok ? 0 : SMEM_GPU_E_CUDA;
 }
 
 int smem_gpu_build_repeat_filter(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int kmer_len, int log2_bits)
@@ -1340,41 +1460,6 @@ int smem_gpu_get_repeat_filter(smem_gpu_t *h, uint32_t *out, int64_t out_words)
 	if (out_words != (int64_t)1 << (d.rf_log2 - 5)) return SMEM_GPU_E_ARG;
 	cudaSetDevice(d.dev);
 	return cudaMemcpy(out, d.d_rf, (size_t)out_words * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : SMEM_GPU_E_CUDA;
-}
-
-int smem_gpu_build_kmer_tables(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int direct_levels)
-{
-	if (!h || !pac || l_pac < 32 || direct_levels < 2 || direct_levels > 13) return SMEM_GPU_E_ARG;
-	if (2 * l_pac <= direct_levels + 6) return SMEM_GPU_E_ARG;
-	int rc = for_each_device(h, [&](DeviceCtx &d) {
-		for (auto &o : h->devs) { if (&o == &d) break; if (o.dev == d.dev) return 0; }     // not the first on its GPU
-		return ctx_build_tables(d, pac, l_pac, src_device, direct_levels);
-	});
-	if (rc) return rc;
-	for (auto &d : h->devs)
-		for (auto &o : h->devs) {
-			if (&o == &d) break;
-			if (o.dev == d.dev) { d.ft = o.ft; d.has_tables = o.has_tables; d.owns_tables = false; break; }
-		}
-	return 0;
-}
-
-int smem_gpu_get_kmer_table(smem_gpu_t *h, int which, int level, void *out, int64_t out_bytes)
-{
-	if (!h || !out) return SMEM_GPU_E_ARG;
-	DeviceCtx &d = h->devs[0];
-	if (!d.has_tables) { h->err = "no k-mer tables built"; return SMEM_GPU_E_NOINDEX; }
-	const int DL = d.ft.DL;
-	const void *src = nullptr;
-	size_t bytes = 0;
-	if (which == 0 && level >= 1 && level <= DL) { src = d.ft.cnt + lvl_off(level); bytes = ((size_t)1 << (2 * level)) * 4; }
-	else if (which == 1 && level >= 1 && level <= DL + 1) { src = d.ft.cum + lvl_off(level); bytes = ((size_t)1 << (2 * level)) * 8; }
-	else if (which == 2) { src = d.ft.pyr; bytes = (size_t)1 << (2 * (DL + 4)); }
-	else if (which == 3) { src = d.ft.top; bytes = (size_t)1 << (2 * (DL + 5)); }
-	else return SMEM_GPU_E_ARG;
-	if ((int64_t)bytes != out_bytes) { h->err = "table size mismatch"; return SMEM_GPU_E_ARG; }
-	cudaSetDevice(d.dev);
-	return cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : SMEM_GPU_E_CUDA;
 }
 
 int smem_gpu_upload_sa(smem_gpu_t *h, int sa_intv, uint64_t n_sa, const uint64_t *sa, int src_device)
@@ -1454,9 +1539,21 @@ int smem_gpu_chains(smem_gpu_t *h, const smem_chain_opt_t *opt, int64_t l_pac, s
 	return 0;
 }
 
+static BatchIn bytes_in(const uint8_t *seq, const int64_t *offs, const int32_t *x = nullptr, const int32_t *mi = nullptr)
+{
+	BatchIn in; in.fmt = 0; in.seq = seq; in.offs = offs; in.x = x; in.mi = mi; return in;
+}
+static BatchIn packed_in(const smem_reads2_t *r) { BatchIn in; in.fmt = 1; in.r2 = r; return in; }
+
 int smem_gpu_stage_reads(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs)
 {
-	return do_stage(h, n_reads, seq, offs, nullptr, nullptr);
+	return do_stage(h, n_reads, bytes_in(seq, offs));
+}
+
+int smem_gpu_stage_reads_packed(smem_gpu_t *h, const smem_reads2_t *reads)
+{
+	if (!h || !reads) return SMEM_GPU_E_ARG;
+	return do_stage(h, reads->n_reads, packed_in(reads));
 }
 
 int smem_gpu_run_collect(smem_gpu_t *h, const smem_seed_opt_t *opt, int64_t *total_out)
@@ -1471,25 +1568,93 @@ int smem_gpu_fetch(smem_gpu_t *h, smem_intv_t *intv_out, int64_t intv_cap, int64
 	return do_fetch(h, intv_out, intv_cap, read_off, step_out, nullptr, total_out);
 }
 
+int smem_gpu_fetch_packed(smem_gpu_t *h, smem_intv16_t *intv_out, int64_t intv_cap, uint32_t *read_off, int64_t *total_out)
+{
+	if (!h) return SMEM_GPU_E_ARG;
+	return do_fetch_packed(h, intv_out, intv_cap, read_off, total_out);
+}
+
 int smem_gpu_collect(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const smem_seed_opt_t *opt,
                      smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, uint16_t *step_out, int64_t *total_out)
 {
 	if (!h || !opt || !read_off) return SMEM_GPU_E_ARG;
-	return do_collect(h, MODE_COLLECT, n_reads, seq, offs, nullptr, nullptr, opt, intv_out, intv_cap, read_off, step_out, nullptr, total_out);
+	CollectOut o; o.intv = intv_out; o.cap = intv_cap; o.read_off = read_off; o.step = step_out; o.total = total_out;
+	return do_collect(h, MODE_COLLECT, n_reads, bytes_in(seq, offs), opt, o);
+}
+
+int smem_gpu_collect_packed(smem_gpu_t *h, const smem_reads2_t *reads, const smem_seed_opt_t *opt, smem_intv16_t *intv_out, int64_t intv_cap,
+                            uint32_t *read_off, int64_t *total_out)
+{
+	if (!h || !reads || !opt || !read_off) return SMEM_GPU_E_ARG;
+	CollectOut o; o.intv16 = intv_out; o.cap = intv_cap; o.read_off32 = read_off; o.total = total_out;
+	return do_collect(h, MODE_COLLECT, reads->n_reads, packed_in(reads), opt, o);
 }
 
 int smem_gpu_trace(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const smem_seed_opt_t *opt,
                    smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, uint16_t *tag_out, uint16_t *ret_out, int64_t *total_out)
 {
 	if (!h || !opt || !read_off || !tag_out || !ret_out) return SMEM_GPU_E_ARG;
-	return do_collect(h, MODE_TRACE, n_reads, seq, offs, nullptr, nullptr, opt, intv_out, intv_cap, read_off, tag_out, nullptr, total_out, ret_out);
+	CollectOut o; o.intv = intv_out; o.cap = intv_cap; o.read_off = read_off; o.step = tag_out; o.aux = ret_out; o.total = total_out;
+	return do_collect(h, MODE_TRACE, n_reads, bytes_in(seq, offs), opt, o);
 }
 
 int smem_gpu_smem1(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const int32_t *x, const int32_t *min_intv,
                    smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off, int32_t *ret, int64_t *total_out)
 {
 	if (!h || !read_off || !ret || (n_reads > 0 && (!x || !min_intv))) return SMEM_GPU_E_ARG;
-	return do_collect(h, MODE_SMEM1, n_reads, seq, offs, x, min_intv, nullptr, intv_out, intv_cap, read_off, nullptr, ret, total_out);
+	CollectOut o; o.intv = intv_out; o.cap = intv_cap; o.read_off = read_off; o.ret = ret; o.total = total_out;
+	return do_collect(h, MODE_SMEM1, n_reads, bytes_in(seq, offs, x, min_intv), nullptr, o);
+}
+
+// Host-side helper of the compact wire format: CSR bytes -> fixed-stride 2-bit records (+ lengths, + the ambiguous-base
+// list, sorted by read because reads are walked in order and the per-thread lists are concatenated in thread order).
+int smem_gpu_pack_reads(int64_t n_reads, const uint8_t *seq, const int64_t *offs, int32_t stride, uint8_t *seq2, uint16_t *lens,
+                        smem_amb_t *amb, int64_t amb_cap, int64_t *n_amb_out, int n_threads)
+{
+	if (n_reads < 0 || (n_reads > 0 && (!seq || !offs || !seq2)) || stride < 1 || n_reads >= (1ll << 32)) return SMEM_GPU_E_ARG;
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_threads < 1 ? 1 : n_threads, 64), (n_reads + 4095) / 4096));
+	std::vector<std::vector<smem_amb_t>> found(T);
+	std::vector<int> bad(T, 0);
+	auto work = [&](int t) {
+		const int64_t lo = n_reads * t / T, hi = n_reads * (t + 1) / T;
+		for (int64_t r = lo; r < hi; ++r) {
+			const int64_t l = offs[r + 1] - offs[r];
+			if (l < 0 || l > 4ll * stride || l > 65535) { bad[t] = 1; return; }
+			if (lens) lens[r] = (uint16_t)l;
+			const uint8_t *q = seq + offs[r];
+			uint8_t *o = seq2 + (size_t)r * (size_t)stride;
+			int64_t i = 0;
+			for (; i + 4 <= l; i += 4) {
+				const uint8_t a = q[i], b = q[i + 1], c = q[i + 2], e = q[i + 3];
+				if ((a | b | c | e) > 3) for (int k = 0; k < 4; ++k) if (q[i + k] > 3) found[t].push_back(smem_amb_t{(uint32_t)r, (uint16_t)(i + k), 0});
+				o[i >> 2] = (uint8_t)(((a & 3) << 6) | ((b & 3) << 4) | ((c & 3) << 2) | (e & 3));
+			}
+			if (i < l) {
+				uint8_t v = 0;
+				for (int k = 0; k < 4; ++k) {
+					const uint8_t a = i + k < l ? q[i + k] : 0;
+					if (a > 3) found[t].push_back(smem_amb_t{(uint32_t)r, (uint16_t)(i + k), 0});
+					v = (uint8_t)((v << 2) | (a & 3));
+				}
+				o[i >> 2] = v; i += 4;
+			}
+			for (int64_t k = i >> 2; k < stride; ++k) o[k] = 0;
+		}
+	};
+	if (T == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (int t = 0; t < T; ++t) th.emplace_back(work, t);
+		for (auto &x : th) x.join();
+	}
+	for (int t = 0; t < T; ++t) if (bad[t]) return SMEM_GPU_E_ARG;
+	int64_t tot = 0;
+	for (auto &v : found) tot += (int64_t)v.size();
+	if (n_amb_out) *n_amb_out = tot;
+	if (tot > amb_cap || (tot > 0 && !amb)) return SMEM_GPU_E_CAPACITY;
+	int64_t k = 0;
+	for (auto &v : found) { if (!v.empty()) memcpy(amb + k, v.data(), v.size() * sizeof(smem_amb_t)); k += (int64_t)v.size(); }
+	return 0;
 }
 
 int smem_gpu_host_alloc(void **ptr, size_t bytes)
@@ -1517,19 +1682,15 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 {
 	if (!h || !name) return SMEM_GPU_E_ARG;
 	if (!strcmp(name, "blocks_per_sm")) {
-		static const int ok[] = {3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 18};
-		for (int k : ok) if (k == v) { h->blocks_per_sm = (int)v; return 0; }
+		for (int k : kSeedBounds) if (k == v) { h->blocks_per_sm = (int)v; return 0; }   // only the variants that were compiled in
+		h->err = "blocks_per_sm: that launch-bounds variant is not compiled in (6, 8, 9; make ALL_BOUNDS=1 for the sweep set)";
 		return SMEM_GPU_E_ARG;
 	}
 	if (!strcmp(name, "slot_cap")) { if (v < 1 || v > 4096) return SMEM_GPU_E_ARG; h->slot_cap = (int)v; return 0; }
 	if (!strcmp(name, "force_wide")) { h->force_wide = v != 0; return 0; }
 	if (!strcmp(name, "spare_sms")) { if (v < 0 || v > 64) return SMEM_GPU_E_ARG; h->spare_sms = (int)v; return 0; }
 	if (!strcmp(name, "chain_lanes")) { h->chain_lanes = v != 0; return 0; }
-	if (!strcmp(name, "reuse")) { h->reuse = v != 0; return 0; }
-	if (!strcmp(name, "fast")) { h->fast = v != 0; return 0; }
-	if (!strcmp(name, "fast_blocks_per_sm")) { if (v < 2 || v > 8 || v == 7) return SMEM_GPU_E_ARG; h->fast_blocks_per_sm = (int)v; return 0; }
-	if (!strcmp(name, "fast_b_cap")) { if (v < 1 || v > 64) return SMEM_GPU_E_ARG; h->fast_b_cap = (int)v; return 0; }
-	if (!strcmp(name, "fast_slots")) { if (v < 16 || v > FAST_MAX_SLOTS) return SMEM_GPU_E_ARG; h->fast_slots = (int)v; return 0; }
+	if (!strcmp(name, "turn_min_reads")) { if (v < 0) return SMEM_GPU_E_ARG; h->turn_min_reads = v; return 0; }
 	if (!strcmp(name, "b_cap")) { if (v < 2 || v > 4096) return SMEM_GPU_E_ARG; h->b_cap = (int)v; return 0; }
 	if (!strcmp(name, "l2_hot_min_intv")) { if (v < 0) return SMEM_GPU_E_ARG; h->hot_min_intv = v; return 0; }
 	if (!strcmp(name, "l2_mode")) { if (v < 0 || v > 2) return SMEM_GPU_E_ARG; h->l2_mode = (int)v; return 0; }
@@ -1539,7 +1700,9 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "unique_walk")) { h->unique_walk = v != 0; return 0; }
 	if (!strcmp(name, "unique_walk_min_run")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_run = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_min_left")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_left = (int)v; return 0; }
+	if (!strcmp(name, "unique_walk_isa_shift")) { if (v < 0 || v > 6) return SMEM_GPU_E_ARG; h->uw_isa_shift = (int)v; return 0; }
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
+	if (!strcmp(name, "acc_reset")) { for (auto &d : h->devs) { d.acc_stage_ms = d.acc_turn_ms = d.acc_run_ms = d.acc_fetch_ms = 0; d.acc_calls = d.acc_h2d = d.acc_d2h = 0; } return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
 		if (v != 32 && v != 64 && v != 128) return SMEM_GPU_E_ARG;
@@ -1558,13 +1721,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "b_cap")) return h->b_cap;
 	if (!strcmp(name, "spare_sms")) return h->spare_sms;
 	if (!strcmp(name, "chain_lanes")) return h->chain_lanes;
-	if (!strcmp(name, "reuse")) return h->reuse;
-	if (!strcmp(name, "fast")) return h->fast;
-	if (!strcmp(name, "fast_blocks_per_sm")) return h->fast_blocks_per_sm;
-	if (!strcmp(name, "fast_b_cap")) return h->fast_b_cap;
-	if (!strcmp(name, "fast_slots")) return h->fast_slots;
-	if (!strcmp(name, "has_kmer_tables")) return h->devs[0].has_tables ? 1 : 0;
-	if (!strcmp(name, "escaped_reads")) { int64_t e = 0; for (auto &d : h->devs) e += d.escaped; return e; }
+	if (!strcmp(name, "turn_min_reads")) return h->turn_min_reads;
 	if (!strcmp(name, "l2_hot_min_intv")) return h->hot_min_intv;
 	if (!strcmp(name, "l2_mode")) return h->l2_mode;
 	if (!strcmp(name, "repeat_filter")) return h->repeat_filter;
@@ -1580,11 +1737,24 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	if (!strcmp(name, "unique_walks")) { int64_t t = 0; for (auto &d : h->devs) t += d.uw_walks; return t; }
 	if (!strcmp(name, "unique_walk_min_left")) return h->uw_min_left;
 	if (!strcmp(name, "unique_walk_min_run")) return h->uw_min_run;
+	if (!strcmp(name, "unique_walk_isa_shift")) return h->devs[0].d_fsa ? h->devs[0].uw_isa_shift : h->uw_isa_shift;
 	if (!strcmp(name, "chain_kernels_us")) { float m = 0; for (auto &d : h->devs) m = std::max(m, d.chain_ms); return (int64_t)(m * 1000.0f); }
 	if (!strcmp(name, "n_chains")) { int64_t t = 0; for (auto &d : h->devs) t += d.n_chains; return t; }
 	if (!strcmp(name, "sm_count")) return h->devs[0].sm_count;
 	if (!strcmp(name, "l2_fetch_granularity")) { size_t g = 0; cudaSetDevice(h->devs[0].dev); cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); return (int64_t)g; }
 	if (!strcmp(name, "n_devices")) return (int64_t)h->devs.size();
+	// wall-time accumulators of the one-call forms (smem_gpu_collect*, trace, smem1), summed over the handle's lanes, in microseconds
+	if (!strcmp(name, "acc_stage_us")) { double t = 0; for (auto &d : h->devs) t += d.acc_stage_ms; return (int64_t)(t * 1000); }
+	if (!strcmp(name, "acc_turn_us")) { double t = 0; for (auto &d : h->devs) t += d.acc_turn_ms; return (int64_t)(t * 1000); }
+	if (!strcmp(name, "acc_run_us")) { double t = 0; for (auto &d : h->devs) t += d.acc_run_ms; return (int64_t)(t * 1000); }
+	if (!strcmp(name, "acc_fetch_us")) { double t = 0; for (auto &d : h->devs) t += d.acc_fetch_ms; return (int64_t)(t * 1000); }
+	if (!strcmp(name, "acc_calls")) { int64_t t = 0; for (auto &d : h->devs) t += d.acc_calls; return t; }
+	if (!strcmp(name, "acc_h2d_bytes")) { int64_t t = 0; for (auto &d : h->devs) t += d.acc_h2d; return t; }
+	if (!strcmp(name, "acc_d2h_bytes")) { int64_t t = 0; for (auto &d : h->devs) t += d.acc_d2h; return t; }
+	// HBM held by the optional accelerator tables of device 0 (repeat filter + unique-walk tables) and by the index itself
+	if (!strcmp(name, "table_bytes")) { const DeviceCtx &d = h->devs[0]; return (int64_t)((d.d_rf ? (size_t)1 << (d.rf_log2 - 3) : 0) + d.uw_bytes); }
+	if (!strcmp(name, "uw_table_bytes")) return (int64_t)h->devs[0].uw_bytes;
+	if (!strcmp(name, "index_bytes")) return (int64_t)h->devs[0].index_bytes;
 	return SMEM_GPU_E_ARG;
 }
 

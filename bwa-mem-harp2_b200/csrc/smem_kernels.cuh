@@ -6,7 +6,7 @@
 enum { MODE_COLLECT = 0, MODE_SMEM1 = 1, MODE_TRACE = 2 };   // TRACE: COLLECT's walk, but every bwt_smem1 call's raw list is kept
 // hot phases first: the main loop only ever extends in PH_FWD / PH_BWD / PH_SPEC
 enum { PH_FWD = 0, PH_BWD = 1, PH_SPEC = 2 /* backward walk of the longest candidate alone */,
-       PH_UW_SA = 3, PH_UW_TEXT = 4, PH_UW_ISA = 5 /* unique forward walk by text comparison */, PH_IDLE = 6, PH_NEED_READ = 7, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
+       PH_UW_SA = 3, PH_UW_TEXT = 4, PH_UW_ISA = 5, PH_UW_LF = 6 /* unique forward walk by text comparison */, PH_IDLE = 7, PH_NEED_READ = 8, PH_NEXT_STEP, PH_INIT_CALL, PH_FWD_END, PH_FWD_DONE, PH_BWD_LAST, PH_CALL_DONE };
 
 #define STEP_SHIFT 48        // inside the slots the smem_next2 step index (TRACE: step*2 + pass) rides in info bits 48..63
 #define AUX_SHIFT 16         // ... and, in TRACE mode, bwt_smem1's return value in bits 16..31 (query positions are < 2^16)
@@ -39,7 +39,7 @@ __device__ __noinline__ Intv bx_get(const Intv *p) { return ld_intv(p); }
 //   global : M1, M2 = `matches` / `sub` of smem_next2 in emission order (descending start), each of
 //            scratch_cap = max_read_len + 2 entries, which bounds every list of bwt.c:776-835.
 //            BX = the entries of B beyond b_cap (only the deepest forward passes reach them).
-template <int MODE, int MIN_BLOCKS, bool WIDE, bool REUSE /* keep the last occ sectors in registers, skip repeated gathers */>
+template <int MODE, int MIN_BLOCKS, bool WIDE>
 __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
 	const bool SPEC = MODE != MODE_SMEM1 && p.spec_walk;     // speculative longest-only backward walk (PH_SPEC)
@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	int i = 0, j = 0, n0 = 0, n_prev = 0, n_curr = 0, len = 0, guard = 0;
 	int max_count = 0;                   // largest per-read interval count this pair produced (sizes the compaction grid)
 	u64 min_intv = 1, last_s = 0;
-	u32 blk_k[8], blk_l[8];              // this lane's sectors of the last K / L occ blocks (see extend_pair)
-	u64 last_bk = ~0ull, last_bl = ~0ull;
+	u32 blk_k[8], blk_l[8];              // this lane's sectors of the K / L occ blocks (see extend_pair)
 #pragma unroll
 	for (int t = 0; t < 8; ++t) blk_k[t] = blk_l[t] = 0;
 
@@ -114,8 +113,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				rk = lds_i32(sc + CS_RK);
 				if ((long long)rk >= p.n) { if (!half && max_count > 0) atomicMax(&p.status[4], max_count); phase = PH_IDLE; break; }
 				const int rid = p.list ? p.list[rk] : rk;
-				const long long o0 = p.offs[rid];
-				len = (int)(p.offs[rid + 1] - o0);
+				len = p.rlen[rid];
 				{                                                            // staged by pack_reads_kernel: 16 bytes (32 bases) per copy
 					const uint4 *src = p.qpack + (size_t)rid * (size_t)(p.q_stride >> 4);
 					for (int t = half; 32 * t < len; t += 2) sts_v4(sq + 16 * t, __ldg(src + t));
@@ -163,7 +161,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				i = x + 1; n_curr = 0; j = 0;
 				sts_u16(sc + CS_NMEM, 0); sts_u16(sc + CS_MAXLEN, 0); sts_u16(sc + CS_MAXSTART, 0); sts_u16(sc + CS_MAXEND, 0);
 				sts_i32(sc + CS_MAXS_LO, 0); sts_i32(sc + CS_MAXS_HI, 0);
-				guard = 2 * (len + 2) * (len + 2) + 64;   // > every extend one bwt_smem1 can issue
+				guard = (int)min(2ll * (len + 2) * (len + 2) + 64, 0x7fffffffll);   // > every extend one bwt_smem1 can issue (saturates for reads beyond 32 k bases)
 				const u32 qv = i < len ? qbase(sq, i) : 4u;
 				if (qv > 3) phase = PH_FWD_END;
 				else { c = 3 - (int)qv; phase = PH_FWD; }     // bwt.c:793: forward extension uses the complement
@@ -307,19 +305,23 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// Unique forward walk (PH_UW_*): once the forward sweep of a pass-1 call has extended an interval of size 1 three times,
 		// the rest of the walk is a comparison of the read with the text at the pattern's only occurrence: text position
 		// t = SA[x0] (one gather), the text itself (one gather of 2 x 64 bases, a nibble each like the staged read), and the
-		// reverse-strand row of the longer pattern = ISA[n - t - length] (one gather; T = forward + reverse complement, so
-		// rc(P) sits mirrored); x0 and the size stay.  The gathers go through extend_pair's own load (same registers); the
-		// walk ends where the reference's last bwt_extend fails.  t rides in last_s, which the forward sweep does not use.
+		// reverse-strand row of the longer pattern = ISA[n - t - length] (T = forward + reverse complement, so rc(P) sits
+		// mirrored); x0 and the size stay.  SA and ISA entries are 33 bits, seven to a 32-byte sector (uw_get33); the ISA is
+		// sampled every 2^uw_isa_shift positions counted from the END of the text, so the row comes from the sample at or above
+		// the position (one gather) plus (t + length) mod 2^shift ordinary backward extends of that single row by the
+		// complemented read bases it is known to be preceded by (PH_UW_LF).  The gathers go through extend_pair's own load (same
+		// registers); the walk ends where the reference's last bwt_extend fails.  t rides in last_s, which the forward sweep
+		// does not use.
 		const uint4 *alt = nullptr;
 		if (phase >= PH_UW_SA && phase <= PH_UW_ISA) {              // (only entered with the tables present)
-			const u64 plen = (u64)(end - (u32)lds_u16(sc + CS_X));
+			const u64 tq = last_s + (u64)(end - (u32)lds_u16(sc + CS_X));    // t + pattern length (PH_UW_SA: unused)
 			u64 byte;
-			if (phase == PH_UW_SA) byte = (u64)p.uw_fsa + 8 * b;
-			else if (phase == PH_UW_ISA) byte = (u64)p.uw_isa + 8 * (p.ix.seq_len - (last_s + plen));
-			else byte = (u64)p.uw_text + 32 * (((last_s + plen) >> 6) + (u64)half);
-			alt = reinterpret_cast<const uint4 *>(byte & ~31ull);
+			if (phase == PH_UW_SA) byte = (u64)p.uw_fsa + 32 * (b / 7);
+			else if (phase == PH_UW_ISA) byte = (u64)p.uw_isa + 32 * ((tq >> p.uw_isa_shift) / 7);
+			else byte = (u64)p.uw_text + 32 * ((tq >> 6) + (u64)half);
+			alt = reinterpret_cast<const uint4 *>(byte);
 		}
-		const Ext ok = extend_pair<REUSE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, last_bk, last_bl, alt);
+		const Ext ok = extend_pair(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
 		if (phase == PH_IDLE) continue;
 		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 
@@ -363,22 +365,32 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				// ran through the whole 128-base window without a verdict: another round of text, else the inverse SA
 				if (!(f0 && f1 && tp + m == ((sec0 + 2) << 6) && i < len && tp + m < p.ix.seq_len)) phase = PH_UW_ISA;
 			} else {
-				const u64 byte = phase == PH_UW_SA ? (u64)p.uw_fsa + 8 * b
-				                                   : (u64)p.uw_isa + 8 * (p.ix.seq_len - (last_s + (u64)(end - (u32)lds_u16(sc + CS_X))));
-				const u32 q4 = (u32)(byte & 31u) >> 3;
-				u32 lo = blk_k[0], hi = blk_k[1];
-				if (q4 == 1) { lo = blk_k[2]; hi = blk_k[3]; } else if (q4 == 2) { lo = blk_k[4]; hi = blk_k[5]; } else if (q4 == 3) { lo = blk_k[6]; hi = blk_k[7]; }
-				const u64 val = (u64)lo | ((u64)hi << 32);
+				const u64 tq = last_s + (u64)(end - (u32)lds_u16(sc + CS_X));
+				const u32 slot = (u32)((phase == PH_UW_SA ? b : tq >> p.uw_isa_shift) % 7);
+				u32 lo = blk_k[0];
+#pragma unroll
+				for (int t = 1; t < 7; ++t) if (slot == (u32)t) lo = blk_k[t];
+				const u64 val = (u64)lo | ((u64)((blk_k[7] >> slot) & 1u) << 32);
 				if (phase == PH_UW_SA) { last_s = val; phase = PH_UW_TEXT; }
 				else {
-					a = val;                                         // x[1] of the longer pattern; x[0] (b) and the size stay
-					j = 0;
 					// The comparison stopped at the end of the read, at an ambiguous base (bwt.c:800-806), at the end of the text or at
 					// a base that differs from the text at the only occurrence: the reference's next bwt_extend finds nothing
-					// (bwt.c:796-798).  Either way the interval is pushed and the forward sweep is over.
-					phase = PH_FWD_END;
+					// (bwt.c:796-798).  Either way the interval is pushed and the forward sweep is over -- once x[1], the row of
+					// rc(pattern), is known: `val` is the row of the sampled suffix j positions above it; each backward extend of
+					// that single row by the base in front of it (the complement of read base i - j, then i - j + 1, ...) moves
+					// one position down.  x[0] (b) and the size stay.
+					a = val;
+					j = (int)(tq & ((1ull << p.uw_isa_shift) - 1));
+					if (j == 0) phase = PH_FWD_END;
+					else { phase = PH_UW_LF; c = 3 - (int)qbase(sq, i - j); }
 				}
 			}
+			continue;
+		}
+		if (phase == PH_UW_LF) {                                 // one position down the sampled inverse suffix array
+			a = ok.a;
+			if (--j == 0) phase = PH_FWD_END;
+			else c = 3 - (int)qbase(sq, i - j);
 			continue;
 		}
 		if (SPEC && phase == PH_SPEC) {
@@ -435,60 +447,147 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	}
 }
 
-// Reads (one base per byte, as the caller hands them over) -> two bases per byte at a fixed stride, so that a lane pair
-// stages its next read with a few 16-byte copies instead of a byte loop inside the divergent cold section.
-// One thread per 16-byte chunk (32 bases).
-__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t *__restrict__ seq, const long long *__restrict__ offs, long long n,
-                                                         int chunks_per_read, uint4 *__restrict__ qpack,
-                                                         const u32 *__restrict__ rf_bits, int K, int log2_bits, u32 *__restrict__ qflags)
+// ---------------------------------------------------------------------------------------------
+// Pack pre-pass: whatever form the caller's reads arrive in, the seed kernel stages a read from `qpack` -- one base per
+// nibble (0..3, > 3 ambiguous, padded with 4), eight bases per 32-bit word, first base lowest, q_stride bytes per read --
+// with a few 16-byte copies, and takes its length from rlen[].  One thread per 16-byte chunk (32 bases).  Reads whose
+// length does not fit the handle set status[5] (checked on the host after the run: no per-read loop on the CPU).
+
+// 32-bit word at an arbitrary byte address: two aligned loads and a funnel shift (reads stay inside the staging buffer:
+// it is allocated with 64 bytes of slack and starts 256-byte aligned)
+__device__ __forceinline__ u32 ld_u32_unaligned(const uint8_t *p)
+{
+	const u32 *q = reinterpret_cast<const u32 *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+	const u32 sh = ((u32)reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+	return __funnelshift_r(__ldg(q), __ldg(q + 1), sh);
+}
+// bases [8k, 8k+8) of a chunk that holds n_valid real bases: everything behind the read's end becomes 4
+__device__ __forceinline__ u32 pad_nibbles(u32 w, int n_valid, int k)
+{
+	const int v = min(max(n_valid - 8 * k, 0), 8);
+	const u32 m = v >= 8 ? 0xffffffffu : ((1u << (4 * v)) - 1u);
+	return (w & m) | (0x44444444u & ~m);
+}
+
+// (a) one base per byte (0..3, > 3 ambiguous; bwamem.c:1403-1406) at CSR offsets -- the layout of smem_gpu_collect
+__global__ void __launch_bounds__(256) pack_bytes_kernel(const uint8_t *__restrict__ seq, const long long *__restrict__ offs, long long n,
+                                                         int chunks_per_read, int max_len, uint4 *__restrict__ qpack, int *__restrict__ rlen,
+                                                         int *__restrict__ status)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long r = t / chunks_per_read;
 	if (r >= n) return;
 	const int ch = (int)(t % chunks_per_read);
-	const long long o0 = offs[r];
-	const int len = (int)(offs[r + 1] - o0), base = 32 * ch;
+	const long long o0 = offs[r], l64 = offs[r + 1] - o0;
+	const bool bad = l64 < 0 || l64 > (long long)max_len;
+	const int len = bad ? 0 : (int)l64, base = 32 * ch;
+	if (ch == 0) { rlen[r] = len; if (bad) atomicOr(&status[5], 1); }
+	const int n_valid = min(max(len - base, 0), 32);
 	u32 w[4];
+	const uint8_t *src = seq + o0 + base;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
-		u32 v = 0;
-#pragma unroll
-		for (int b = 0; b < 8; ++b) {
-			const int pos = base + 8 * k + b;
-			const u32 c = pos < len ? min((u32)seq[o0 + pos], 4u) : 4u;
-			v |= c << (4 * b);
+		u32 v = 0x44444444u;
+		if (8 * k < n_valid) {
+			u32 lo = __vminu4(ld_u32_unaligned(src + 8 * k), 0x04040404u), hi = __vminu4(ld_u32_unaligned(src + 8 * k + 4), 0x04040404u);
+			lo = (lo | (lo >> 4)) & 0x00ff00ffu; lo = (lo | (lo >> 8)) & 0x0000ffffu;      // four bytes -> four nibbles, first base lowest
+			hi = (hi | (hi >> 4)) & 0x00ff00ffu; hi = (hi | (hi >> 8)) & 0x0000ffffu;
+			v = pad_nibbles(lo | (hi << 16), n_valid, k);
 		}
 		w[k] = v;
 	}
 	qpack[t] = make_uint4(w[0], w[1], w[2], w[3]);
-	if (!qflags) return;
-	// repeat-filter flags of the 32 windows that start in this chunk (smem_repeat.cuh): rolling K-mer code, `amb` = bases
-	// until the most recent ambiguous one leaves the window; eight independent table loads per round
+}
+
+// (b) the compact wire format (smem_reads2_t): fixed-stride records of two bits per base, four bases per byte, first base
+// in the top bits (the reference's .pac convention, bntseq.c:_set_pac); lengths from lens[] or one length for all
+__global__ void __launch_bounds__(256) unpack2_kernel(const uint8_t *__restrict__ seq2, int stride, const unsigned short *__restrict__ lens, int read_len,
+                                                      long long n, int chunks_per_read, int max_len, uint4 *__restrict__ qpack, int *__restrict__ rlen,
+                                                      int *__restrict__ status)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long r = t / chunks_per_read;
+	if (r >= n) return;
+	const int ch = (int)(t % chunks_per_read);
+	const int l0 = lens ? (int)lens[r] : read_len;
+	const bool bad = l0 < 0 || l0 > max_len || l0 > 4 * stride;
+	const int len = bad ? 0 : l0, base = 32 * ch;
+	if (ch == 0) { rlen[r] = len; if (bad) atomicOr(&status[5], 1); }
+	const int n_valid = min(max(len - base, 0), 32);
+	u32 w[4];
+	const uint8_t *src = seq2 + (size_t)r * (size_t)stride + 8 * ch;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		u32 v = 0x44444444u;
+		if (8 * k < n_valid) {
+			const u32 two = ld_u32_unaligned(src + 2 * k) & 0xffffu;            // bytes 2k, 2k+1 of the chunk = bases 8k .. 8k+7
+			const u32 b0 = two & 255u, b1 = two >> 8;
+			const u32 n0 = (b0 >> 6) | (b0 & 0x30u) | ((b0 & 0x0cu) << 6) | ((b0 & 3u) << 12);
+			const u32 n1 = (b1 >> 6) | (b1 & 0x30u) | ((b1 & 0x0cu) << 6) | ((b1 & 3u) << 12);
+			v = pad_nibbles(n0 | (n1 << 16), n_valid, k);
+		}
+		w[k] = v;
+	}
+	qpack[t] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ... whose ambiguous bases travel as an exception list {read, pos} (a two-bit code cannot say N): bit 2 of the nibble is set
+struct AmbEntry { u32 read; unsigned short pos, reserved; };
+__global__ void amb_patch_kernel(const AmbEntry *__restrict__ amb, long long n_amb, long long read_lo, long long n, int q_stride,
+                                 u32 *__restrict__ qpack_words, const int *__restrict__ rlen, int *__restrict__ status)
+{
+	const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_amb) return;
+	const long long r = (long long)amb[e].read - read_lo;
+	const int pos = amb[e].pos;
+	if (r < 0 || r >= n) { atomicOr(&status[5], 2); return; }
+	if (pos >= rlen[r]) return;
+	atomicOr(&qpack_words[(size_t)r * (size_t)(q_stride >> 2) + (pos >> 3)], 4u << (4 * (pos & 7)));
+}
+
+// Repeat-filter flags of the 32 windows that start in a chunk (smem_repeat.cuh), from the packed reads: rolling K-mer code,
+// `amb` = bases until the most recent ambiguous one leaves the window; eight independent table loads per round.
+__global__ void __launch_bounds__(256) window_flags_kernel(const uint4 *__restrict__ qpack, const int *__restrict__ rlen, long long n, int chunks_per_read,
+                                                           const u32 *__restrict__ rf_bits, int K, int log2_bits, u32 *__restrict__ qflags)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long r = t / chunks_per_read;
+	if (r >= n) return;
+	const int ch = (int)(t % chunks_per_read);
+	const int len = rlen[r], base = 32 * ch;
+	if (base + K > len) { qflags[t] = 0xffffffffu; return; }            // every window of this chunk runs off the read
+	u32 q[8];
+	{
+		const uint4 c0 = __ldg(qpack + t);
+		uint4 c1 = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);
+		if (ch + 1 < chunks_per_read) c1 = __ldg(qpack + t + 1);
+		q[0] = c0.x; q[1] = c0.y; q[2] = c0.z; q[3] = c0.w; q[4] = c1.x; q[5] = c1.y; q[6] = c1.z; q[7] = c1.w;
+	}
+	// bases base .. base + 63 in order (static register indices): base i is the last base of the window starting at
+	// a = i - (K - 1); windows 0 .. 31 belong to this chunk
 	u32 flags = 0;
 	u64 code = 0;
 	int amb = 0;
 	const u64 kmask = K == 32 ? ~0ull : (1ull << (2 * K)) - 1;
-	for (int k = 0; k < K - 1; ++k) {
-		const int pos = base + k;
-		const u32 c = pos < len ? (u32)seq[o0 + pos] : 4u;
-		code = ((code << 2) | (c & 3u)) & kmask;
-		amb = c > 3u ? K : max(amb - 1, 0);
-	}
-	for (int a0 = 0; a0 < 32; a0 += 8) {
+#pragma unroll
+	for (int w = 0; w < 8; ++w) {
 		u32 wd[8], sh[8], bad[8];
 #pragma unroll
 		for (int k = 0; k < 8; ++k) {
-			const int pos = base + a0 + k + K - 1;                 // last base of the window starting at base + a0 + k
-			const u32 c = pos < len ? (u32)seq[o0 + pos] : 4u;
+			const u32 c = (q[w] >> (4 * k)) & 15u;
 			code = ((code << 2) | (c & 3u)) & kmask;
 			amb = c > 3u ? K : max(amb - 1, 0);
+			const int a0 = 8 * w + k - (K - 1);
 			bad[k] = amb > 0;
 			const u64 b = rf_bit_index(code, log2_bits);
-			wd[k] = bad[k] ? 0u : __ldg(rf_bits + (b >> 5));
+			wd[k] = (bad[k] || a0 < 0 || a0 > 31) ? 0u : __ldg(rf_bits + (b >> 5));
 			sh[k] = (u32)(b & 31);
 		}
 #pragma unroll
-		for (int k = 0; k < 8; ++k) flags |= (bad[k] | ((wd[k] >> sh[k]) & 1u)) << (a0 + k);
+		for (int k = 0; k < 8; ++k) {
+			const int a0 = 8 * w + k - (K - 1);
+			if (a0 >= 0 && a0 <= 31) flags |= (bad[k] | ((wd[k] >> sh[k]) & 1u)) << a0;
+		}
 	}
 	qflags[t] = flags;
 }
@@ -612,6 +711,54 @@ __global__ void __launch_bounds__(128) compact_kernel(const Intv *__restrict__ s
 	}
 }
 
+// The compact result record (smem_intv16_t, include/smem_gpu.h): x0 | x1 << 33 | x2 << 66 | qbeg << 99 | qend << 113 --
+// 127 bits, valid while seq_len < 2^33 and reads are shorter than 2^14 (the host checks both before choosing this form).
+__device__ __forceinline__ uint4 pack_intv16(const Intv &v)
+{
+	const u64 qb = (v.info >> 32) & 0x3fffull, qe = v.info & 0x3fffull;
+	const u64 lo = v.x0 | (v.x1 << 33);
+	const u64 hi = (v.x1 >> 31) | (v.x2 << 2) | (qb << 35) | (qe << 49);
+	return make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+}
+
+// Compaction into the compact wire format: slots -> dense 16-byte records + 32-bit CSR offsets (off32[n] = total).
+__global__ void __launch_bounds__(128) compact_packed_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
+                                                             const long long *__restrict__ off, long long n, uint4 *__restrict__ out,
+                                                             u32 *__restrict__ off32)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long r = t >> 3;
+	if (r >= n) return;
+	const int c = min(counts[r], slot_cap);      // entries beyond slot_cap are filled in by the overflow re-run
+	const long long o0 = off[r];
+	if ((t & 7) == 0) { off32[r] = (u32)o0; if (r == n - 1) off32[n] = (u32)off[n]; }
+	for (int e = (int)(t & 7); e < c; e += 8) {
+		Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
+		v.info &= INFO_MASK;
+		out[o0 + e] = pack_intv16(v);
+	}
+}
+
+// dense 32-byte results of an earlier run -> 16-byte records + 32-bit offsets (smem_gpu_fetch_packed after smem_gpu_run_collect)
+__global__ void intv16_from_dense_kernel(const Intv *__restrict__ in, long long total, const long long *__restrict__ off, long long n,
+                                         uint4 *__restrict__ out, u32 *__restrict__ off32)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < total) out[t] = pack_intv16(ld_intv(&in[t]));
+	if (t <= n) off32[t] = (u32)off[t];
+}
+
+__global__ void compact_list_packed_kernel(const Intv *__restrict__ big_slots, int big_cap, const int *__restrict__ list,
+                                           const int *__restrict__ counts_k, int n_list, const long long *__restrict__ off, uint4 *__restrict__ out)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int k = (int)(t / big_cap), e = (int)(t % big_cap);
+	if (k >= n_list || e >= counts_k[k]) return;
+	Intv v = ld_intv(&big_slots[(size_t)k * big_cap + e]);
+	v.info &= INFO_MASK;
+	out[off[list[k]] + e] = pack_intv16(v);
+}
+
 // Overflow re-run placement: big_slots[k][big_cap] of read list[k] -> dense output at off[list[k]].
 __global__ void compact_list_kernel(const Intv *__restrict__ big_slots, int big_cap, const int *__restrict__ list,
                                     const int *__restrict__ counts_k, int n_list, const long long *__restrict__ off,
@@ -705,23 +852,43 @@ __global__ void __launch_bounds__(256) pack_text_nib_kernel(const uint8_t *__res
 	tw[w] = v;
 }
 
-// Full suffix array and its inverse from the samples (unique-walk tables, PH_UW_* of seed_kernel): every sampled row k * intv
+// 33-bit table entries, seven to a 32-byte sector: words 0..6 = low 32 bits, word 7 = the seven high bits.  One sector is
+// what one lane gathers with one request, so a lookup costs the same as with 8-byte entries at 4.57 bytes per entry.
+__device__ __forceinline__ void uw_put33(u32 *tab, u64 idx, u64 val)          // table zeroed beforehand; entries are written once
+{
+	const u64 sec = idx / 7; const u32 slot = (u32)(idx % 7);
+	tab[sec * 8 + slot] = (u32)val;
+	if (val >> 32) atomicOr(&tab[sec * 8 + 7], 1u << slot);
+}
+__device__ __forceinline__ u64 uw_get33(const u32 *tab, u64 idx)
+{
+	const u64 sec = idx / 7; const u32 slot = (u32)(idx % 7);
+	return (u64)tab[sec * 8 + slot] | ((u64)((tab[sec * 8 + 7] >> slot) & 1u) << 32);
+}
+
+// Full suffix array and sampled inverse from the samples (unique-walk tables, PH_UW_* of seed_kernel): every sampled row k * intv
 // starts a walk r -> invPsi(r), p -> p - 1 that ends at the next sampled row; the walks partition the rows, so every row
-// r gets fsa[r] = its text position and isa[position] = r exactly once.  Row 0 (the '$' suffix, sa[0] = -1 in the
-// reference, bwt.c:97) is given position seq_len.  Persistent lane pairs, one occ block per step like sa_kernel.
+// r gets fsa[r] = its text position exactly once, and every position seq_len - e * 2^isa_shift gets isa[e] = its row.
+// Row 0 (the '$' suffix, sa[0] = -1 in the reference, bwt.c:97) is given position seq_len.  Persistent lane pairs, one occ
+// block per step like sa_kernel.
 __global__ void __launch_bounds__(128) fsa_build_kernel(const DevIndex ix, const u64 *__restrict__ sa, int sa_shift, long long n_sa,
-                                                        u64 *__restrict__ fsa, u64 *__restrict__ isa, int *__restrict__ status)
+                                                        u32 *__restrict__ fsa, u32 *__restrict__ isa, int isa_shift, int *__restrict__ status)
 {
 	const int lane = threadIdx.x & 31, half = lane & 1;
 	const long long npairs = ((long long)gridDim.x * blockDim.x) >> 1;
 	long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-	const u64 mask = (1ull << sa_shift) - 1;
+	const u64 mask = (1ull << sa_shift) - 1, imask = (1ull << isa_shift) - 1;
 	bool have = false;
 	u64 r = 0, pos = 0, steps = 0;
+	auto record = [&]() {
+		uw_put33(fsa, r, pos);
+		const u64 back = ix.seq_len - pos;
+		if ((back & imask) == 0) uw_put33(isa, back >> isa_shift, r);
+	};
 	for (;;) {
 		if (!have && q < n_sa) {
 			r = (u64)q << sa_shift; pos = q ? sa[q] : ix.seq_len; q += npairs;
-			if (!half) { fsa[r] = pos; isa[pos] = r; }
+			if (!half) record();
 			have = true; steps = 0;
 		}
 		__syncwarp();
@@ -731,11 +898,18 @@ __global__ void __launch_bounds__(128) fsa_build_kernel(const DevIndex ix, const
 			r = rn; pos -= 1;
 			if ((r & mask) == 0) have = false;
 			else {
-				if (!half) { fsa[r] = pos; isa[pos] = r; }
+				if (!half) record();
 				if (++steps > (1ull << 24)) { if (!half) atomicAdd(&status[2], 1); have = false; }   // guard: corrupt index
 			}
 		}
 	}
+}
+
+// test hook: 33-bit table -> uint64 array
+__global__ void uw_unpack_kernel(const u32 *__restrict__ tab, long long n, u64 *__restrict__ out)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = uw_get33(tab, (u64)i);
 }
 
 // Intervals -> seeds (bwamem.c:408-421 / 462-476): an interval with seed length >= min_seed_len and x[2] <= max_occ

@@ -26,6 +26,25 @@
 
 __host__ __device__ __forceinline__ u64 rf_bit_index(u64 code, int log2_bits) { return (code * RF_MULT_BIT) >> (64 - log2_bits); }
 
+// T = forward + reverse complement, 32 bases per 64-bit word, first base in the top bits, zero padded -- the builder's view
+// of the text.  `pac` is the reference's .pac layout of the forward strand (bntseq.c: four bases per byte, first base in
+// the top bits); the reverse complement is appended the way bntseq.c:268-273 does.
+__global__ void __launch_bounds__(256) pack_text_kernel(const uint8_t *__restrict__ pac, long long l_pac, u64 *__restrict__ tw, long long n_words)
+{
+	const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= n_words) return;
+	const long long n = 2 * l_pac;
+	u64 v = 0;
+	for (int k = 0; k < 32; ++k) {
+		const long long pos = 32 * w + k;
+		u32 base = 0;
+		if (pos < l_pac) base = (pac[pos >> 2] >> ((~pos & 3) << 1)) & 3u;
+		else if (pos < n) { const long long o = n - 1 - pos; base = 3u - ((pac[o >> 2] >> ((~o & 3) << 1)) & 3u); }
+		v = (v << 2) | base;
+	}
+	tw[w] = v;
+}
+
 // K-mer code at text position pos (tw: 32 bases per 64-bit word, first base in the top bits, zero padded by >= 1 word)
 __device__ __forceinline__ u64 rf_text_code(const u64 *__restrict__ tw, long long pos, int K)
 {

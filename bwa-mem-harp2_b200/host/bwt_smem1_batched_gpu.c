@@ -11,10 +11,22 @@
  *                            itr[i]->start = ret;
  *   pass 2 (is_middle == 1): x = middle of itr[i]->matches->a[max_i[i]], min_intv = that.x[2] + 1;
  *                            results -> itr[i]->sub, start untouched;
- *   reads with done[i] != 0 are not touched; INIT / FREE only manage the reference's thread-local scratch,
- *   of which this adapter has none.
- * Differences by design: no 101 bp limit (bwt.c:575), no 128-read partitions (bwt.c:45), no CPU fallback --
- * a GPU failure aborts with a message, as the reference's own asserts do (fastmap.c:413).
+ *   reads with done[i] != 0 are not touched; INIT / FREE only manage thread-local scratch.
+ *
+ * How the reference's `-t N -b B` calling pattern reaches the GPU:
+ *   * whole-batch cache: the first pass-1 call of a batch computes EVERY round of every read in one smem_gpu_trace launch;
+ *     the reference's later per-round calls (two per round, shrinking active set, bwamem.c:390-393) are served from the
+ *     calling thread's own cache without touching any lock;
+ *   * caller aggregation (what harp_management arbitrates in the reference, fastmap.c:335-420): GPU work goes through a
+ *     combining queue.  A caller posts its request; whoever finds a free service handle becomes the leader, takes every
+ *     compatible pending request (up to the handle's batch limit), runs them as ONE launch, hands the slices back and wakes
+ *     their owners.  With -b 64 and 16 workers a launch carries the reads of all the workers that arrived while the
+ *     previous launches were in flight; SMEM_GPU_ADAPTER_HANDLES (default 4) launches run concurrently on their own streams;
+ *   * staging in pinned memory (smem_gpu_host_alloc), one set per service handle, grown geometrically;
+ *   * handles grow in place (smem_gpu_resize) when a longer read or a larger batch arrives -- no fixed 101 bp / 128-read
+ *     limits (bwt.c:575, bwt.c:45);
+ *   * no CPU fallback and no abort(): a GPU failure is reported once on stderr, recorded (harp_gpu_service_last_error) and
+ *     the affected lists are returned empty; SMEM_GPU_ADAPTER_ABORT=1 restores fail-fast behaviour for batch jobs.
  */
 #include "../../include/bwa_abi.h"
 #include "../../include/smem_gpu.h"
@@ -22,36 +34,101 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
-static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;   /* one handle, one caller at a time */
-static smem_gpu_t *g_h = 0;
+#define MAX_HANDLES 16
+
+typedef struct {
+	smem_gpu_t *h;
+	int dev, busy;
+	int64_t max_batch; int max_len;
+	/* pinned staging, used by the leader that holds the handle */
+	uint8_t *seq; size_t seq_cap;
+	int64_t *offs, *roff; int32_t *x, *mi, *ret; size_t n_cap;
+	smem_intv_t *out; uint16_t *tag, *ret16; size_t out_cap;
+} svc_handle_t;
+
+/* one caller's GPU work: n reads of its batch, either one raw bwt_smem1 each (kind 0) or the whole iterator walk (kind 1) */
+typedef struct req {
+	int kind, start_width;
+	size_t n;
+	harp_smem_i **itr; const int32_t *idx;      /* read k of the request = itr[idx[k]] */
+	const int32_t *x, *mi;                      /* kind 0 */
+	/* results, written by the leader into buffers the requester owns (the requester sleeps meanwhile) */
+	smem_intv_t **intv; uint16_t **tag, **ret16; size_t *cap;   /* grown by the leader */
+	int64_t *roff;                              /* [n + 1] */
+	int32_t *ret;                               /* kind 0: [n] */
+	int done, rc;
+	struct req *next;
+} req_t;
+
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
+static svc_handle_t g_hd[MAX_HANDLES];
+static int g_n_handles = 0;
+static req_t *g_head = 0, *g_tail = 0;
 static const harp_bwt_t *g_bwt = 0;
 static int64_t g_max_batch = 1 << 16;
-static int g_max_len = 1024;
-static uint64_t g_stats[4];   /* GPU calls, reads sent, intervals received, lists served from the batch cache */
+static int g_init_len = 160;
+static int g_last_rc = 0, g_abort_on_error = 0, g_reported = 0, g_start_failed = 0;
+static char g_last_err[512];
+/* GPU calls, reads sent, intervals received, lists served from the batch cache, requests combined into those calls,
+ * nanoseconds inside the GPU calls, nanoseconds inside bwt_smem1_batched (summed over threads) */
+static uint64_t g_stats[8];
+static int g_use_cache = -1, g_split_len = 28, g_split_width = 10;   /* -k 19 -r 1.5 -> (int)(19*1.5+.499), bwamem.c:456; split_width bwamem.c:60 */
 
-/* staging buffers, grown on demand, protected by g_lock */
-static uint8_t *g_seq; static size_t g_seq_cap;
-static int64_t *g_offs, *g_roff; static int32_t *g_x, *g_mi, *g_ret, *g_idx; static size_t g_n_cap;
-static smem_intv_t *g_out; static size_t g_out_cap;
+static uint64_t now_ns(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
+static void stat_add(int k, uint64_t v) { __atomic_fetch_add(&g_stats[k], v, __ATOMIC_RELAXED); }
 
-static void print_stats(void);
-
-static void die(const char *what, int rc)
+static void print_stats(void)
 {
-	fprintf(stderr, "[bwt_smem1_batched/gpu] %s: %s (%d) %s\n", what, smem_gpu_strerror(rc), rc, g_h ? smem_gpu_last_error(g_h) : "");
-	abort();
+	fprintf(stderr, "[bwt_smem1_batched/gpu] gpu_calls=%llu reads_sent=%llu intervals=%llu lists_from_cache=%llu requests=%llu gpu_s=%.3f adapter_s=%.3f handles=%d\n",
+	        (unsigned long long)g_stats[0], (unsigned long long)g_stats[1], (unsigned long long)g_stats[2], (unsigned long long)g_stats[3],
+	        (unsigned long long)g_stats[4], (double)g_stats[5] * 1e-9, (double)g_stats[6] * 1e-9, g_n_handles);
 }
 
-int harp_gpu_service_start(const harp_bwt_t *bwt)
+/* record a failure: message once, code kept for harp_gpu_service_last_error */
+static void fail(const char *what, int rc, smem_gpu_t *h)
 {
-	int devs[64], n_dev = 0, rc;
+	pthread_mutex_lock(&g_mu);
+	g_last_rc = rc;
+	snprintf(g_last_err, sizeof g_last_err, "%s: %s (%d) %s", what, smem_gpu_strerror(rc), rc, h ? smem_gpu_last_error(h) : "");
+	if (!g_reported) { fprintf(stderr, "[bwt_smem1_batched/gpu] %s -- the affected interval lists are returned EMPTY (no CPU fallback)\n", g_last_err); g_reported = 1; }
+	pthread_mutex_unlock(&g_mu);
+	if (g_abort_on_error) abort();
+}
+
+int harp_gpu_service_last_error(const char **msg) { if (msg) *msg = g_last_err; return g_last_rc; }
+
+/* ---- service bring-up: the upload step of bwa_idx_load_bwt (bwa.c:289-291), to HBM instead of the MPF workspace ---- */
+static int service_start_inner(const harp_bwt_t *bwt);
+static int service_start_locked(const harp_bwt_t *bwt)
+{
+	int k;
+	const int rc = service_start_inner(bwt);
+	if (rc) {            /* leave nothing half-built behind, and do not try again on every call */
+		for (k = 0; k < MAX_HANDLES; ++k) if (g_hd[k].h) smem_gpu_destroy(g_hd[k].h);
+		memset(g_hd, 0, sizeof g_hd);
+		g_n_handles = 0; g_start_failed = 1;
+	}
+	return rc;
+}
+
+static int service_start_inner(const harp_bwt_t *bwt)
+{
+	int devs[64], n_dev = 0, rc, k, want = 4;
 	const char *e;
 	smem_index_desc_t ix;
-	if (g_h && g_bwt == bwt) return 0;
-	if (g_h) { smem_gpu_destroy(g_h); g_h = 0; }
+	if (g_n_handles && g_bwt == bwt) return 0;
+	for (k = 0; k < g_n_handles; ++k) { if (g_hd[k].h) smem_gpu_destroy(g_hd[k].h); }
+	memset(g_hd, 0, sizeof g_hd);
+	g_n_handles = 0;
 	if ((e = getenv("SMEM_GPU_MAX_BATCH")) != 0) g_max_batch = atoll(e);
-	if ((e = getenv("SMEM_GPU_MAX_READ_LEN")) != 0) g_max_len = atoi(e);
+	if ((e = getenv("SMEM_GPU_MAX_READ_LEN")) != 0) g_init_len = atoi(e);       /* first size only: handles grow on demand */
+	if ((e = getenv("SMEM_GPU_ADAPTER_HANDLES")) != 0) want = atoi(e);
+	if ((e = getenv("SMEM_GPU_ADAPTER_ABORT")) != 0) g_abort_on_error = atoi(e) != 0;
+	if (g_max_batch < 64) g_max_batch = 64;
+	if (g_init_len < 32) g_init_len = 32;
 	e = getenv("SMEM_GPU_DEVICES");
 	if (e && *e) {
 		char *dup = strdup(e), *tok, *save = 0;
@@ -59,33 +136,248 @@ int harp_gpu_service_start(const harp_bwt_t *bwt)
 		free(dup);
 	}
 	if (n_dev == 0) devs[n_dev++] = 0;
-	if ((rc = smem_gpu_create(&g_h, n_dev, devs, g_max_batch, g_max_len)) != 0) return rc;
-	/* the upload step of bwa_idx_load_bwt (bwa.c:289-291), to HBM instead of the MPF workspace */
+	if (want < n_dev) want = n_dev;
+	if (want > MAX_HANDLES) want = MAX_HANDLES;
 	ix.primary = bwt->primary;
 	memcpy(ix.L2, bwt->L2, sizeof ix.L2);
 	ix.seq_len = bwt->seq_len;
 	ix.bwt_size = bwt->bwt_size;
 	ix.bwt = bwt->bwt;
-	if ((rc = smem_gpu_upload_index(g_h, &ix)) != 0) return rc;
+	for (k = 0; k < want; ++k) {            /* handle k lives on device k mod n_dev; one index copy per GPU */
+		svc_handle_t *s = &g_hd[k];
+		int j;
+		s->dev = devs[k % n_dev]; s->max_batch = g_max_batch; s->max_len = g_init_len;
+		if ((rc = smem_gpu_create(&s->h, 1, &s->dev, s->max_batch, s->max_len)) != 0) return rc;
+		++g_n_handles;
+		for (j = 0; j < k; ++j) if (g_hd[j].dev == s->dev) break;
+		rc = j < k ? smem_gpu_share_index(s->h, g_hd[j].h) : smem_gpu_upload_index(s->h, &ix);
+		if (rc != 0) return rc;
+		smem_gpu_set_param(s->h, "turn_min_reads", 1ll << 40);   /* concurrent small launches: never serialise on the kernel turn */
+	}
 	if (g_bwt == 0 && getenv("SMEM_GPU_ADAPTER_STATS")) atexit(print_stats);
 	g_bwt = bwt;
 	return 0;
 }
 
-void harp_gpu_service_stop(void)
+int harp_gpu_service_start(const harp_bwt_t *bwt)
 {
-	pthread_mutex_lock(&g_lock);
-	if (g_h) smem_gpu_destroy(g_h);
-	g_h = 0; g_bwt = 0;
-	pthread_mutex_unlock(&g_lock);
+	int rc;
+	pthread_mutex_lock(&g_mu);
+	rc = service_start_locked(bwt);
+	pthread_mutex_unlock(&g_mu);
+	return rc;
 }
 
-void harp_gpu_service_stats(uint64_t out[4]) { memcpy(out, g_stats, sizeof g_stats); }
-
-static void print_stats(void)
+void harp_gpu_service_stop(void)
 {
-	fprintf(stderr, "[bwt_smem1_batched/gpu] gpu_calls=%llu reads_sent=%llu intervals=%llu lists_from_cache=%llu\n",
-	        (unsigned long long)g_stats[0], (unsigned long long)g_stats[1], (unsigned long long)g_stats[2], (unsigned long long)g_stats[3]);
+	int k;
+	pthread_mutex_lock(&g_mu);
+	for (k = 0; k < g_n_handles; ++k) {
+		svc_handle_t *s = &g_hd[k];
+		if (s->h) smem_gpu_destroy(s->h);
+		smem_gpu_host_free(s->seq); smem_gpu_host_free(s->offs); smem_gpu_host_free(s->roff); smem_gpu_host_free(s->x); smem_gpu_host_free(s->mi);
+		smem_gpu_host_free(s->ret); smem_gpu_host_free(s->out); smem_gpu_host_free(s->tag); smem_gpu_host_free(s->ret16);
+	}
+	memset(g_hd, 0, sizeof g_hd);
+	g_n_handles = 0; g_bwt = 0;
+	pthread_mutex_unlock(&g_mu);
+}
+
+void harp_gpu_service_stats(uint64_t out[4]) { memcpy(out, g_stats, 4 * sizeof(uint64_t)); }
+void harp_gpu_service_stats8(uint64_t out[8]) { memcpy(out, g_stats, sizeof g_stats); }
+
+/* ---- pinned staging of a service handle ---------------------------------------------------------------------- */
+static int pin_grow(void **p, size_t *cap, size_t need, size_t elem)
+{
+	void *q = 0;
+	size_t c;
+	if (need <= *cap) return 0;
+	c = need + need / 2 + 1024;
+	if (smem_gpu_host_alloc(&q, c * elem) != 0) return SMEM_GPU_E_NOMEM;
+	if (*p) smem_gpu_host_free(*p);
+	*p = q; *cap = c;
+	return 0;
+}
+
+static int stage_grow(svc_handle_t *s, size_t n, size_t nbytes)
+{
+	int rc = 0;
+	size_t c;
+	if (n > s->n_cap) {
+		c = 0; rc |= pin_grow((void **)&s->offs, &c, n + 1, sizeof(int64_t));
+		c = 0; rc |= pin_grow((void **)&s->roff, &c, n + 1, sizeof(int64_t));
+		c = 0; rc |= pin_grow((void **)&s->x, &c, n, sizeof(int32_t));
+		c = 0; rc |= pin_grow((void **)&s->mi, &c, n, sizeof(int32_t));
+		c = 0; rc |= pin_grow((void **)&s->ret, &c, n, sizeof(int32_t));
+		s->n_cap = rc ? 0 : n + n / 2 + 1024;
+	}
+	if (!rc) rc = pin_grow((void **)&s->seq, &s->seq_cap, nbytes + 64, 1);
+	return rc;
+}
+
+static int out_grow(svc_handle_t *s, size_t need)
+{
+	int rc = 0;
+	size_t c;
+	if (need <= s->out_cap) return 0;
+	c = 0; rc |= pin_grow((void **)&s->out, &c, need, sizeof(smem_intv_t));
+	c = 0; rc |= pin_grow((void **)&s->tag, &c, need, sizeof(uint16_t));
+	c = 0; rc |= pin_grow((void **)&s->ret16, &c, need, sizeof(uint16_t));
+	s->out_cap = rc ? 0 : need + need / 2 + 1024;
+	return rc;
+}
+
+/* ---- the leader: every compatible pending request in one launch ----------------------------------------------- */
+static void lead(svc_handle_t *s, req_t *list)
+{
+	req_t *r;
+	size_t n = 0, nbytes = 0, k, pos;
+	int max_len = 0, rc = 0, n_req = 0;
+	int64_t total = 0;
+	const uint64_t t0 = now_ns();
+	for (r = list; r; r = r->next) {
+		++n_req;
+		for (k = 0; k < r->n; ++k) { const int l = r->itr[r->idx[k]]->len; nbytes += (size_t)l; if (l > max_len) max_len = l; }
+		n += r->n;
+	}
+	if (max_len > s->max_len || (int64_t)n > s->max_batch) {    /* grow the handle in place; the index stays */
+		int want_len = s->max_len;
+		int64_t want_batch = s->max_batch;
+		while (want_len < max_len) want_len = want_len * 2 > 65535 ? 65535 : want_len * 2;
+		while (want_batch < (int64_t)n) want_batch *= 2;
+		if (max_len > 65535) rc = SMEM_GPU_E_CAPACITY;
+		else if ((rc = smem_gpu_resize(s->h, want_batch, want_len)) == 0) { s->max_len = want_len; s->max_batch = want_batch; }
+	}
+	if (!rc) rc = stage_grow(s, n, nbytes);
+	if (!rc) rc = out_grow(s, 24 * n + 4096);
+	if (!rc) {
+		for (r = list, pos = 0, nbytes = 0; r; r = r->next)
+			for (k = 0; k < r->n; ++k, ++pos) {
+				const harp_smem_i *it = r->itr[r->idx[k]];
+				s->offs[pos] = (int64_t)nbytes;
+				memcpy(s->seq + nbytes, it->query, (size_t)it->len);
+				nbytes += (size_t)it->len;
+				if (list->kind == 0) { s->x[pos] = r->x[k]; s->mi[pos] = r->mi[k]; }
+			}
+		s->offs[n] = (int64_t)nbytes;
+		for (;;) {
+			if (list->kind == 0)
+				rc = smem_gpu_smem1(s->h, (int64_t)n, s->seq, s->offs, s->x, s->mi, s->out, (int64_t)s->out_cap, s->roff, s->ret, &total);
+			else {
+				smem_seed_opt_t opt;
+				opt.min_seed_len = g_split_len; opt.split_factor = 1.0; opt.split_width = g_split_width; opt.start_width = list->start_width;
+				rc = smem_gpu_trace(s->h, (int64_t)n, s->seq, s->offs, &opt, s->out, (int64_t)s->out_cap, s->roff, s->tag, s->ret16, &total);
+			}
+			if (rc == SMEM_GPU_E_CAPACITY && (size_t)total > s->out_cap) {   /* more intervals than guessed: size exactly and repeat */
+				if ((rc = out_grow(s, (size_t)total)) == 0) continue;
+			}
+			break;
+		}
+	}
+	if (rc) fail(list->kind ? "smem_gpu_trace" : "smem_gpu_smem1", rc, s->h);
+	/* hand the slices back */
+	for (r = list, pos = 0; r; r = r->next) {
+		r->rc = rc;
+		if (!rc) {
+			const int64_t base = s->roff[pos];
+			const size_t cnt = (size_t)(s->roff[pos + r->n] - base);
+			if (cnt > *r->cap) {
+				const size_t c = cnt + cnt / 2 + 256;
+				*r->intv = (smem_intv_t *)realloc(*r->intv, c * sizeof(smem_intv_t));
+				if (r->tag) { *r->tag = (uint16_t *)realloc(*r->tag, c * 2); *r->ret16 = (uint16_t *)realloc(*r->ret16, c * 2); }
+				*r->cap = c;
+			}
+			memcpy(*r->intv, s->out + base, cnt * sizeof(smem_intv_t));
+			if (r->tag) { memcpy(*r->tag, s->tag + base, cnt * 2); memcpy(*r->ret16, s->ret16 + base, cnt * 2); }
+			for (k = 0; k <= r->n; ++k) r->roff[k] = s->roff[pos + k] - base;
+			if (r->ret) memcpy(r->ret, s->ret + pos, r->n * sizeof(int32_t));
+		} else
+			for (k = 0; k <= r->n; ++k) r->roff[k] = 0;
+		pos += r->n;
+	}
+	stat_add(0, 1); stat_add(1, n); stat_add(2, (uint64_t)total); stat_add(4, (uint64_t)n_req); stat_add(5, now_ns() - t0);
+}
+
+/* post a request and wait for it; while waiting, lead launches whenever a service handle is free */
+static int submit(req_t *me)
+{
+	int k;
+	me->done = 0; me->rc = 0; me->next = 0;
+	pthread_mutex_lock(&g_mu);
+	if (g_tail) g_tail->next = me; else g_head = me;
+	g_tail = me;
+	while (!me->done) {
+		svc_handle_t *s = 0;
+		if (g_head) for (k = 0; k < g_n_handles; ++k) if (!g_hd[k].busy) { s = &g_hd[k]; break; }
+		if (s) {
+			/* take the head request and every later one that can share its launch */
+			req_t *list = g_head, *lt = list, **pp, *r;
+			int64_t n = (int64_t)list->n;
+			g_head = list->next; if (!g_head) g_tail = 0;
+			lt->next = 0;
+			for (pp = &g_head, g_tail = 0; (r = *pp) != 0;) {
+				if (r->kind == list->kind && r->start_width == list->start_width && n + (int64_t)r->n <= g_max_batch) {
+					*pp = r->next; r->next = 0; lt->next = r; lt = r; n += (int64_t)r->n;
+				} else { g_tail = r; pp = &r->next; }
+			}
+			s->busy = 1;
+			pthread_mutex_unlock(&g_mu);
+			lead(s, list);
+			pthread_mutex_lock(&g_mu);
+			s->busy = 0;
+			for (r = list; r;) { req_t *nx = r->next; r->next = 0; r->done = 1; r = nx; }   /* (owners may return as soon as done is set) */
+			pthread_cond_broadcast(&g_cv);
+		} else
+			pthread_cond_wait(&g_cv, &g_mu);
+	}
+	pthread_mutex_unlock(&g_mu);
+	return me->rc;
+}
+
+/* ---- thread-local state --------------------------------------------------------------------------------------- */
+typedef struct {
+	/* whole-batch cache: the per-call lists of every round of the batch, from one smem_gpu_trace */
+	int n;
+	const harp_smem_i **itr; const uint8_t **query; int *len;
+	int *next_pos;        /* where the next pass-1 call of the read must start (before skipping N) */
+	int *step;            /* last step served by pass 1, -1 = none */
+	int64_t *cur;         /* cursor into the read's trace entries */
+	int64_t *roff;        /* [n+1] trace CSR, batch order (empty for reads that were done) */
+	smem_intv_t *intv; uint16_t *tag, *ret; size_t cap;
+	size_t n_cap;
+	/* direct path / request scratch */
+	int32_t *list, *lx, *lmi, *lret, *gidx;
+	int64_t *groff;
+	smem_intv_t *dintv; size_t dcap;
+} tls_t;
+static __thread tls_t tc;
+
+static int skip_n(const uint8_t *q, int len, int pos) { while (pos < len && q[pos] > 3) ++pos; return pos; }
+
+static void tls_grow(int n)
+{
+	if ((size_t)n <= tc.n_cap) return;
+	tc.n_cap = (size_t)n + 64;
+	tc.itr = (const harp_smem_i **)realloc((void *)tc.itr, tc.n_cap * sizeof(*tc.itr));
+	tc.query = (const uint8_t **)realloc((void *)tc.query, tc.n_cap * sizeof(*tc.query));
+	tc.len = (int *)realloc(tc.len, tc.n_cap * sizeof(int));
+	tc.next_pos = (int *)realloc(tc.next_pos, tc.n_cap * sizeof(int));
+	tc.step = (int *)realloc(tc.step, tc.n_cap * sizeof(int));
+	tc.cur = (int64_t *)realloc(tc.cur, tc.n_cap * sizeof(int64_t));
+	tc.roff = (int64_t *)realloc(tc.roff, (tc.n_cap + 1) * sizeof(int64_t));
+	tc.groff = (int64_t *)realloc(tc.groff, (tc.n_cap + 1) * sizeof(int64_t));
+	tc.list = (int32_t *)realloc(tc.list, tc.n_cap * sizeof(int32_t));
+	tc.lx = (int32_t *)realloc(tc.lx, tc.n_cap * sizeof(int32_t));
+	tc.lmi = (int32_t *)realloc(tc.lmi, tc.n_cap * sizeof(int32_t));
+	tc.lret = (int32_t *)realloc(tc.lret, tc.n_cap * sizeof(int32_t));
+	tc.gidx = (int32_t *)realloc(tc.gidx, tc.n_cap * sizeof(int32_t));
+}
+
+static void tls_free(void)
+{
+	free((void *)tc.itr); free((void *)tc.query); free(tc.len); free(tc.next_pos); free(tc.step); free(tc.cur); free(tc.roff); free(tc.groff);
+	free(tc.intv); free(tc.tag); free(tc.ret); free(tc.list); free(tc.lx); free(tc.lmi); free(tc.lret); free(tc.gidx); free(tc.dintv);
+	memset(&tc, 0, sizeof tc);
 }
 
 /* copy a list into a caller-owned kvec, growing it the way kv_push does (kvec.h:75-81) */
@@ -101,154 +393,76 @@ static void put_list(harp_bwtintv_v *v, const smem_intv_t *src, size_t cnt)
 	v->n = cnt;
 }
 
-static void grow_n(size_t n)
-{
-	if (n <= g_n_cap) return;
-	g_n_cap = n + n / 2 + 64;
-	g_offs = (int64_t *)realloc(g_offs, (g_n_cap + 1) * sizeof(int64_t));
-	g_roff = (int64_t *)realloc(g_roff, (g_n_cap + 1) * sizeof(int64_t));
-	g_x = (int32_t *)realloc(g_x, g_n_cap * sizeof(int32_t));
-	g_mi = (int32_t *)realloc(g_mi, g_n_cap * sizeof(int32_t));
-	g_ret = (int32_t *)realloc(g_ret, g_n_cap * sizeof(int32_t));
-	g_idx = (int32_t *)realloc(g_idx, g_n_cap * sizeof(int32_t));
-}
-
-/* ---- direct path: one bwt_smem1 per listed read, in one GPU call ------------------------------------------ */
-/* idx[k] = position in the batch; x/mi per listed read.  Results go to matches (pass 1, + start) or sub (pass 2). */
+/* ---- direct path: one bwt_smem1 per listed read ------------------------------------------------------------------
+ * idx[k] = position in the batch; x/mi per listed read.  Results go to matches (pass 1, + start) or sub (pass 2). */
 static void direct_smem1(harp_smem_i **itr, const int32_t *idx, size_t n, const int32_t *x, const int32_t *mi, int is_middle)
 {
-	size_t k, nbytes = 0;
-	int64_t total = 0;
-	int rc;
+	req_t rq;
+	size_t k;
 	if (n == 0) return;
-	grow_n(n);
-	for (k = 0; k < n; ++k) { g_offs[k] = (int64_t)nbytes; nbytes += (size_t)itr[idx[k]]->len; }
-	g_offs[n] = (int64_t)nbytes;
-	if (nbytes > g_seq_cap) { g_seq_cap = nbytes + nbytes / 2 + 4096; g_seq = (uint8_t *)realloc(g_seq, g_seq_cap); }
-	for (k = 0; k < n; ++k) memcpy(g_seq + g_offs[k], itr[idx[k]]->query, (size_t)itr[idx[k]]->len);
-	if (g_out_cap < 32 * n) { g_out_cap = 32 * n + 1024; g_out = (smem_intv_t *)realloc(g_out, g_out_cap * sizeof(smem_intv_t)); }
-	rc = smem_gpu_smem1(g_h, (int64_t)n, g_seq, g_offs, x, mi, g_out, (int64_t)g_out_cap, g_roff, g_ret, &total);
-	if (rc == SMEM_GPU_E_CAPACITY && (size_t)total > g_out_cap) {   /* more intervals than guessed: size exactly and repeat */
-		g_out_cap = (size_t)total + 1024;
-		g_out = (smem_intv_t *)realloc(g_out, g_out_cap * sizeof(smem_intv_t));
-		rc = smem_gpu_smem1(g_h, (int64_t)n, g_seq, g_offs, x, mi, g_out, (int64_t)g_out_cap, g_roff, g_ret, &total);
-	}
-	if (rc != 0) die("smem_gpu_smem1", rc);
-	for (k = 0; k < n; ++k) {   /* scatter into the caller-owned kvecs (bwt.c:719-749) */
+	memset(&rq, 0, sizeof rq);
+	rq.kind = 0; rq.n = n; rq.itr = itr; rq.idx = idx; rq.x = x; rq.mi = mi;
+	rq.intv = &tc.dintv; rq.cap = &tc.dcap; rq.roff = tc.groff; rq.ret = tc.lret;
+	submit(&rq);
+	for (k = 0; k < n; ++k) {   /* scatter into the caller-owned kvecs (bwt.c:719-749); after a failure every list is empty */
 		harp_smem_i *it = itr[idx[k]];
-		put_list(is_middle ? it->sub : it->matches, g_out + g_roff[k], (size_t)(g_roff[k + 1] - g_roff[k]));
-		if (!is_middle) it->start = g_ret[k];
+		put_list(is_middle ? it->sub : it->matches, tc.dintv + tc.groff[k], (size_t)(tc.groff[k + 1] - tc.groff[k]));
+		if (!is_middle) it->start = rq.rc ? it->len : tc.lret[k];
 	}
-	g_stats[0] += 1; g_stats[1] += n; g_stats[2] += (uint64_t)total;
 }
 
-/* ---- whole-batch cache --------------------------------------------------------------
- * The reference calls bwt_smem1_batched twice per iterator round (bwamem.c:172,204) for several rounds with a
- * shrinking active set (bwamem.c:390-393).  On the first pass-1 call of a batch (every active read still at its
- * first position) the adapter computes EVERY round of every read in one smem_gpu_trace launch and keeps the per-call
- * lists; the later calls are served from that cache after checking that the caller is where the trace expects it
- * (same smem_i, same query, same position).  Anything that does not line up (different -r/-s options than assumed,
- * a caller that is mid-way) falls back to the direct path for that read -- never to the CPU. */
-typedef struct {
-	int n;
-	const harp_smem_i **itr; const uint8_t **query; int *len;
-	int *next_pos;        /* where the next pass-1 call of the read must start (before skipping N) */
-	int *step;            /* last step served by pass 1, -1 = none */
-	int64_t *cur;         /* cursor into the read's trace entries */
-	int64_t *roff;        /* [n+1] trace CSR, batch order (empty for reads that were done) */
-	smem_intv_t *intv; uint16_t *tag, *ret; size_t cap;
-	size_t n_cap;
-	int32_t *list, *lx, *lmi; /* scratch for fallbacks */
-} trace_cache_t;
-static __thread trace_cache_t tc;
-static int g_use_cache = -1, g_split_len = 28, g_split_width = 10;   /* -k 19 -r 1.5 -> (int)(19*1.5+.499), bwamem.c:456; split_width bwamem.c:60 */
-
-static int skip_n(const uint8_t *q, int len, int pos) { while (pos < len && q[pos] > 3) ++pos; return pos; }
-
-static void cache_grow(int n)
-{
-	if ((size_t)n <= tc.n_cap) return;
-	tc.n_cap = (size_t)n + 64;
-	tc.itr = (const harp_smem_i **)realloc((void *)tc.itr, tc.n_cap * sizeof(*tc.itr));
-	tc.query = (const uint8_t **)realloc((void *)tc.query, tc.n_cap * sizeof(*tc.query));
-	tc.len = (int *)realloc(tc.len, tc.n_cap * sizeof(int));
-	tc.next_pos = (int *)realloc(tc.next_pos, tc.n_cap * sizeof(int));
-	tc.step = (int *)realloc(tc.step, tc.n_cap * sizeof(int));
-	tc.cur = (int64_t *)realloc(tc.cur, tc.n_cap * sizeof(int64_t));
-	tc.roff = (int64_t *)realloc(tc.roff, (tc.n_cap + 1) * sizeof(int64_t));
-	tc.list = (int32_t *)realloc(tc.list, tc.n_cap * sizeof(int32_t));
-	tc.lx = (int32_t *)realloc(tc.lx, tc.n_cap * sizeof(int32_t));
-	tc.lmi = (int32_t *)realloc(tc.lmi, tc.n_cap * sizeof(int32_t));
-}
-
-static void cache_free(void)
-{
-	free((void *)tc.itr); free((void *)tc.query); free(tc.len); free(tc.next_pos); free(tc.step); free(tc.cur); free(tc.roff);
-	free(tc.intv); free(tc.tag); free(tc.ret); free(tc.list); free(tc.lx); free(tc.lmi);
-	memset(&tc, 0, sizeof tc);
-}
-
-/* all rounds of the active reads of this batch in one launch; must be called with g_lock held */
+/* ---- whole-batch cache: all rounds of the active reads of this batch in one (shared) launch ---------------------- */
 static void cache_fill(harp_smem_i **itr, int batch_size, const int *done, int start_width)
 {
-	size_t n = 0, nbytes = 0, k;
-	int i, rc;
-	int64_t total = 0;
-	smem_seed_opt_t opt;
-	cache_grow(batch_size);
-	grow_n((size_t)batch_size);
+	req_t rq;
+	size_t n = 0, k;
+	int i;
 	for (i = 0; i < batch_size; ++i) {
 		tc.itr[i] = itr[i]; tc.query[i] = done[i] ? 0 : itr[i]->query; tc.len[i] = done[i] ? 0 : itr[i]->len;
 		tc.next_pos[i] = 0; tc.step[i] = -1;
-		if (done[i]) continue;
-		g_idx[n] = i; g_offs[n] = (int64_t)nbytes; nbytes += (size_t)itr[i]->len; ++n;
+		if (!done[i]) tc.gidx[n++] = i;
 	}
-	g_offs[n] = (int64_t)nbytes;
-	if (nbytes > g_seq_cap) { g_seq_cap = nbytes + nbytes / 2 + 4096; g_seq = (uint8_t *)realloc(g_seq, g_seq_cap); }
-	for (k = 0; k < n; ++k) memcpy(g_seq + g_offs[k], itr[g_idx[k]]->query, (size_t)itr[g_idx[k]]->len);
-	opt.min_seed_len = g_split_len; opt.split_factor = 1.0; opt.split_width = g_split_width; opt.start_width = start_width;
-	if (tc.cap < 48 * n + 1024) {
-		tc.cap = 48 * n + 1024;
-		tc.intv = (smem_intv_t *)realloc(tc.intv, tc.cap * sizeof(smem_intv_t));
-		tc.tag = (uint16_t *)realloc(tc.tag, tc.cap * 2); tc.ret = (uint16_t *)realloc(tc.ret, tc.cap * 2);
-	}
-	rc = smem_gpu_trace(g_h, (int64_t)n, g_seq, g_offs, &opt, tc.intv, (int64_t)tc.cap, g_roff, tc.tag, tc.ret, &total);
-	if (rc == SMEM_GPU_E_CAPACITY && (size_t)total > tc.cap) {
-		tc.cap = (size_t)total + 1024;
-		tc.intv = (smem_intv_t *)realloc(tc.intv, tc.cap * sizeof(smem_intv_t));
-		tc.tag = (uint16_t *)realloc(tc.tag, tc.cap * 2); tc.ret = (uint16_t *)realloc(tc.ret, tc.cap * 2);
-		rc = smem_gpu_trace(g_h, (int64_t)n, g_seq, g_offs, &opt, tc.intv, (int64_t)tc.cap, g_roff, tc.tag, tc.ret, &total);
-	}
-	if (rc != 0) die("smem_gpu_trace", rc);
+	memset(&rq, 0, sizeof rq);
+	rq.kind = 1; rq.start_width = start_width; rq.n = n; rq.itr = itr; rq.idx = tc.gidx;
+	rq.intv = &tc.intv; rq.tag = &tc.tag; rq.ret16 = &tc.ret; rq.cap = &tc.cap; rq.roff = tc.groff;
+	if (submit(&rq) != 0) { tc.n = 0; return; }      /* failure: nothing cached, the direct path reports it again and returns empty lists */
 	/* trace CSR is in gathered order; spread it to batch order (reads that were done own an empty range) */
 	for (i = 0, k = 0; i < batch_size; ++i) {
-		tc.roff[i] = g_roff[k]; tc.cur[i] = g_roff[k];
+		tc.roff[i] = tc.groff[k]; tc.cur[i] = tc.groff[k];
 		if (!done[i]) ++k;
 	}
-	tc.roff[batch_size] = total;
+	tc.roff[batch_size] = tc.groff[n];
 	tc.n = batch_size;
-	g_stats[0] += 1; g_stats[1] += n; g_stats[2] += (uint64_t)total;
 }
 
 void bwt_smem1_batched(harp_smem_i **itr, int *ori_start, int *max_i, int start_width, int is_middle,
                        int batch_size, const int *done, int bwt_batched_status)
 {
-	int i, rc;
+	int i;
 	size_t n = 0, nf = 0;
-	if (bwt_batched_status == HARP_BWT_BATCHED_FREE) { cache_free(); return; }
+	uint64_t t0;
+	if (bwt_batched_status == HARP_BWT_BATCHED_FREE) { tls_free(); return; }
 	if (bwt_batched_status != HARP_BWT_BATCHED_DO) return;   /* INIT: nothing thread-local to set up */
 	if (batch_size <= 0) return;
+	t0 = now_ns();
 
-	pthread_mutex_lock(&g_lock);
-	if (g_use_cache < 0) {
-		const char *e = getenv("SMEM_GPU_ADAPTER_CACHE");
-		g_use_cache = e ? atoi(e) != 0 : 1;
-		if ((e = getenv("SMEM_GPU_SPLIT_LEN")) != 0) g_split_len = atoi(e);
-		if ((e = getenv("SMEM_GPU_SPLIT_WIDTH")) != 0) g_split_width = atoi(e);
+	if ((g_n_handles == 0 && !g_start_failed) || g_use_cache < 0) {               /* first call: bring the service up (bwa.c:289-301 has no hook to do it earlier) */
+		int rc = 0;
+		pthread_mutex_lock(&g_mu);
+		if (g_use_cache < 0) {
+			const char *e = getenv("SMEM_GPU_ADAPTER_CACHE");
+			if ((e = getenv("SMEM_GPU_SPLIT_LEN")) != 0) g_split_len = atoi(e);
+			if ((e = getenv("SMEM_GPU_SPLIT_WIDTH")) != 0) g_split_width = atoi(e);
+			e = getenv("SMEM_GPU_ADAPTER_CACHE");
+			g_use_cache = e ? atoi(e) != 0 : 1;
+		}
+		if (!g_start_failed)
+			for (i = 0; i < batch_size; ++i)
+				if (!done[i]) { rc = service_start_locked(itr[i]->bwt); break; }
+		pthread_mutex_unlock(&g_mu);
+		if (rc) fail("service start", rc, 0);
 	}
-	for (i = 0; i < batch_size; ++i)
-		if (!done[i] && (g_h == 0 || g_bwt != itr[i]->bwt)) { if ((rc = harp_gpu_service_start(itr[i]->bwt)) != 0) die("service start", rc); break; }
-	cache_grow(batch_size);
+	tls_grow(batch_size);
 
 	if (!is_middle) {
 		/* pass 1 (bwt.c:514-546): x = ori_start[i], min_intv = max(start_width, 1) */
@@ -258,7 +472,7 @@ void bwt_smem1_batched(harp_smem_i **itr, int *ori_start, int *max_i, int start_
 			++active;
 			fresh += ori_start[i] == skip_n(itr[i]->query, itr[i]->len, 0);
 		}
-		if (g_use_cache && active > 0 && fresh == active) cache_fill(itr, batch_size, done, start_width);   /* first round of a batch */
+		if (g_use_cache && g_n_handles && active > 0 && fresh == active) cache_fill(itr, batch_size, done, start_width);   /* first round of a batch */
 		for (i = 0; i < batch_size; ++i) {
 			harp_smem_i *it;
 			int ok = 0;
@@ -284,7 +498,8 @@ void bwt_smem1_batched(harp_smem_i **itr, int *ori_start, int *max_i, int start_
 				tc.list[n] = i; tc.lx[n] = ori_start[i]; tc.lmi[n] = start_width; ++n;
 			}
 		}
-		direct_smem1(itr, tc.list, n, tc.lx, tc.lmi, 0);
+		if (g_n_handles) direct_smem1(itr, tc.list, n, tc.lx, tc.lmi, 0);
+		else for (i = 0; i < (int)n; ++i) { itr[tc.list[i]]->matches->n = 0; itr[tc.list[i]]->start = itr[tc.list[i]]->len; }
 	} else {
 		/* pass 2 (bwt.c:518-525,541-546): x = middle of matches[max_i], min_intv = its x[2] + 1, results -> sub */
 		for (i = 0; i < batch_size; ++i) {
@@ -307,8 +522,9 @@ void bwt_smem1_batched(harp_smem_i **itr, int *ori_start, int *max_i, int start_
 				++n;
 			}
 		}
-		direct_smem1(itr, tc.list, n, tc.lx, tc.lmi, 1);
+		if (g_n_handles) direct_smem1(itr, tc.list, n, tc.lx, tc.lmi, 1);
+		else for (i = 0; i < (int)n; ++i) itr[tc.list[i]]->sub->n = 0;
 	}
-	g_stats[3] += nf;
-	pthread_mutex_unlock(&g_lock);
+	stat_add(3, nf);
+	stat_add(6, now_ns() - t0);
 }

@@ -111,6 +111,12 @@ static void serve_batch(void)
 		const size_t cnt = (size_t)(roff[r + 1] - roff[r]);
 		size_t k;
 		if (8 + cnt * 4 + 4 >= 1024) { fprintf(stderr, "[harp_shim] %zu intervals do not fit the protocol's output record\n", cnt); abort(); }
+		/* the output carve-out is the LAST megabyte of the workspace (HelloALINLB.cpp:61,410): a request whose records do not
+		 * fit it cannot be answered through this protocol -- stop with a message rather than write past the allocation */
+		if ((size_t)(o - SPL_BWT_output) + 8 + cnt * 4 + 4 > MB(1) / sizeof *o) {
+			fprintf(stderr, "[harp_shim] the %u records of this request do not fit the protocol's 1 MB output region (read %u, %zu intervals)\n", n, r, cnt);
+			abort();
+		}
 		memset(o, 0, 64);
 		o[0] = r; o[1] = cnt; o[2] = (unsigned long int)ret[r];
 		o += 8;

@@ -19,8 +19,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
 
 EXPORTS = [
-    "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
-    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_chains", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_kmer_tables", "smem_gpu_get_kmer_table", "smem_gpu_build_repeat_filter", "smem_gpu_get_repeat_filter", "smem_gpu_build_text_index", "smem_gpu_get_text_index", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_resize", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
+    "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_chains", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_repeat_filter", "smem_gpu_get_repeat_filter", "smem_gpu_build_text_index", "smem_gpu_get_text_index", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
+    "smem_gpu_collect_packed", "smem_gpu_stage_reads_packed", "smem_gpu_fetch_packed", "smem_gpu_pack_reads",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -46,6 +47,67 @@ class Timing(C.Structure):
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Reads2(C.Structure):
+    """smem_reads2_t: the compact read format (two bits per base, fixed stride, ambiguous bases as an exception list)."""
+    _fields_ = [("n_reads", C.c_int64), ("seq2", C.c_void_p), ("stride", C.c_int32), ("read_len", C.c_int32), ("lens", C.c_void_p),
+                ("amb", C.c_void_p), ("n_amb", C.c_int64)]
+
+
+AMB_DTYPE = np.dtype([("read", np.uint32), ("pos", np.uint16), ("reserved", np.uint16)])
+
+
+def unpack_intv16(rec: np.ndarray) -> np.ndarray:
+    """smem_intv16_t records (uint64[n, 2]) -> bwtintv_t rows (uint64[n, 4]); mirrors smem_intv16_unpack of smem_gpu.h."""
+    rec = np.asarray(rec, np.uint64).reshape(-1, 2)
+    w0, w1 = rec[:, 0], rec[:, 1]
+    m33 = np.uint64((1 << 33) - 1)
+    out = np.empty((len(rec), 4), np.uint64)
+    out[:, 0] = w0 & m33
+    out[:, 1] = (w0 >> np.uint64(33)) | ((w1 & np.uint64(3)) << np.uint64(31))
+    out[:, 2] = (w1 >> np.uint64(2)) & m33
+    out[:, 3] = (((w1 >> np.uint64(35)) & np.uint64(0x3fff)) << np.uint64(32)) | ((w1 >> np.uint64(49)) & np.uint64(0x3fff))
+    return out
+
+
+class PackedReads:
+    """Host buffers of one batch in the compact format (optionally pinned) + the smem_reads2_t that describes them."""
+
+    def __init__(self, lib, seq, offs, stride=None, uniform=None, pinned=False, threads=8):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        n = len(offs) - 1
+        lens = np.diff(offs)
+        max_len = int(lens.max()) if n else 0
+        self.stride = int(stride or max(1, (max_len + 3) // 4))
+        if uniform is None:
+            uniform = bool(n == 0 or (lens == lens[0]).all())
+        self.n = n
+        alloc = (lambda shape, dt: PinnedArray(lib, shape, dt)) if pinned else None
+        self._keep = []
+
+        def mk(shape, dt):
+            if alloc:
+                a = alloc(shape, dt); self._keep.append(a); return a.array
+            return np.zeros(shape, dt)
+        self.seq2 = mk((max(n * self.stride, 1),), np.uint8)
+        self.lens = None if uniform else mk((max(n, 1),), np.uint16)
+        n_amb_guess = int(np.count_nonzero(seq > 3))
+        self.amb = mk((max(n_amb_guess, 1),), AMB_DTYPE)
+        n_amb = C.c_int64(0)
+        rc = lib.smem_gpu_pack_reads(C.c_int64(n), _p(seq, C.c_uint8), _p(offs, C.c_int64), C.c_int32(self.stride), C.c_void_p(self.seq2.ctypes.data),
+                                     C.c_void_p(self.lens.ctypes.data) if self.lens is not None else None, C.c_void_p(self.amb.ctypes.data),
+                                     C.c_int64(len(self.amb)), C.byref(n_amb), C.c_int(threads))
+        if rc:
+            raise SmemGpuError(rc, "smem_gpu_pack_reads failed")
+        self.n_amb = int(n_amb.value)
+        self.desc = Reads2(n, self.seq2.ctypes.data, self.stride, int(lens[0]) if (uniform and n) else 0,
+                           self.lens.ctypes.data if self.lens is not None else None, self.amb.ctypes.data if self.n_amb else None, self.n_amb)
+
+    @property
+    def h2d_bytes(self):
+        return self.n * self.stride + (2 * self.n if self.lens is not None else 0) + 8 * self.n_amb
 
 
 class SmemGpuError(RuntimeError):
@@ -189,21 +251,6 @@ class SmemGpu:
         self._check(self.lib.smem_gpu_share_index(self.h, other.h))
         self._shared_from = other        # keep the owner alive
 
-    def build_kmer_tables(self, fwd, direct_levels: int):
-        """K-mer count pyramid of the fast path (smem_gpu_build_kmer_tables) from the forward text ``fwd``
-        (uint8 symbols 0..3, numpy array or torch tensor on any device); packs it to the reference's .pac layout first."""
-        pac = pack_pac(fwd)
-        l_pac = int(fwd.numel() if hasattr(fwd, "numel") else fwd.size)
-        if hasattr(pac, "is_cuda") and pac.is_cuda:
-            import torch
-            torch.cuda.synchronize(pac.device)
-            self._check(self.lib.smem_gpu_build_kmer_tables(self.h, C.c_void_p(pac.data_ptr()), C.c_int64(l_pac), C.c_int(pac.device.index or 0),
-                                                            C.c_int(direct_levels)))
-        else:
-            a = np.ascontiguousarray(pac.numpy() if hasattr(pac, "numpy") else pac, np.uint8)
-            self._check(self.lib.smem_gpu_build_kmer_tables(self.h, C.c_void_p(a.ctypes.data), C.c_int64(l_pac), C.c_int(-1), C.c_int(direct_levels)))
-        self.direct_levels = direct_levels
-
     def build_repeat_filter(self, fwd, kmer_len: int = 0, log2_bits: int = 0):
         """Repeat filter of the re-seeding pass (smem_gpu_build_repeat_filter) from the forward text ``fwd`` (uint8 symbols
         0..3, numpy array or torch tensor on any device, or an already packed .pac given as ``(pac, l_pac)``)."""
@@ -239,8 +286,9 @@ class SmemGpu:
         self._text_len = 2 * l_pac
 
     def text_index(self, which: int) -> np.ndarray:
-        """Test hook: 0 = full suffix array, 1 = inverse (seq_len + 1 entries)."""
-        out = np.empty(self._text_len + 1, np.uint64)
+        """Test hook: 0 = full suffix array (seq_len + 1 rows), 1 = the sampled inverse (entry e = row of the suffix at
+        seq_len - e * 2^unique_walk_isa_shift)."""
+        out = np.empty(self._text_len + 1 if which == 0 else (self._text_len >> self.get_param("unique_walk_isa_shift")) + 1, np.uint64)
         self._check(self.lib.smem_gpu_get_text_index(self.h, C.c_int(which), C.c_void_p(out.ctypes.data), C.c_int64(out.size)))
         return out
 
@@ -248,14 +296,6 @@ class SmemGpu:
         """Test hook: the bit table of device 0 as uint32 words."""
         out = np.empty(1 << (self.get_param("rf_log2_bits") - 5), np.uint32)
         self._check(self.lib.smem_gpu_get_repeat_filter(self.h, C.c_void_p(out.ctypes.data), C.c_int64(out.size)))
-        return out
-
-    def kmer_table(self, which: int, level: int = 0) -> np.ndarray:
-        """Test hook: one table of the pyramid (0 cnt[level], 1 cum[level], 2 pyr, 3 top)."""
-        DL = self.direct_levels
-        n = 4 ** level if which < 2 else 4 ** (DL + 4 + (which == 3))
-        out = np.empty(n, [np.uint32, np.uint64, np.uint8, np.uint8][which])
-        self._check(self.lib.smem_gpu_get_kmer_table(self.h, C.c_int(which), C.c_int(level), C.c_void_p(out.ctypes.data), C.c_int64(out.nbytes)))
         return out
 
     def upload_sa(self, index):
@@ -340,6 +380,38 @@ class SmemGpu:
             self._check(rc)
             t = int(tot.value)
             return dict(intv=intv[:t], read_off=read_off, step=step[:t] if want_step else None)
+
+    def collect_packed(self, reads: "PackedReads", opt: "SeedOpt | None" = None, out=None, read_off=None, unpack=True):
+        """smem_gpu_collect_packed: compact reads in, 16-byte interval records + uint32 CSR offsets out."""
+        opt = opt or SeedOpt()
+        n = reads.n
+        cap = out.shape[0] if out is not None else max(64, 16 * n)
+        read_off = read_off if read_off is not None else np.zeros(n + 1, np.uint32)
+        tot = C.c_int64(0)
+        while True:
+            rec = out if out is not None else np.empty((cap, 2), np.uint64)
+            rc = self.lib.smem_gpu_collect_packed(self.h, C.byref(reads.desc), C.byref(opt), C.c_void_p(rec.ctypes.data), C.c_int64(cap),
+                                                  C.c_void_p(read_off.ctypes.data), C.byref(tot))
+            if rc == -5 and tot.value > cap and out is None:
+                cap = int(tot.value)
+                continue
+            self._check(rc)
+            t = int(tot.value)
+            return dict(rec=rec[:t], intv=unpack_intv16(rec[:t]) if unpack else None, read_off=read_off.astype(np.int64) if unpack else read_off)
+
+    def stage_packed(self, reads: "PackedReads"):
+        self._keep = reads
+        self._n = reads.n
+        self._check(self.lib.smem_gpu_stage_reads_packed(self.h, C.byref(reads.desc)))
+
+    def fetch_packed(self, total: int):
+        n = self._n
+        rec = np.empty((max(total, 1), 2), np.uint64)
+        read_off = np.zeros(n + 1, np.uint32)
+        tot = C.c_int64(0)
+        self._check(self.lib.smem_gpu_fetch_packed(self.h, C.c_void_p(rec.ctypes.data), C.c_int64(rec.shape[0]), C.c_void_p(read_off.ctypes.data), C.byref(tot)))
+        t = int(tot.value)
+        return dict(rec=rec[:t], intv=unpack_intv16(rec[:t]), read_off=read_off.astype(np.int64))
 
     def trace(self, seq, offs, opt: "SeedOpt | None" = None):
         """Per-call raw lists of the whole iterator walk (smem_gpu_trace): intv, read_off, tag (2*step+pass), ret."""

@@ -62,6 +62,15 @@ void harp_gpu_service_stop(void);
  * Environment: SMEM_GPU_ADAPTER_CACHE=0 disables the cache; SMEM_GPU_SPLIT_LEN / SMEM_GPU_SPLIT_WIDTH tell it the
  * caller's re-seeding options (default 28 / 10 = -k 19 -r 1.5); a mismatch only costs speed, never correctness. */
 void harp_gpu_service_stats(uint64_t out[4]);
+/* ... plus: requests combined into those calls, nanoseconds inside the GPU calls, nanoseconds inside bwt_smem1_batched
+ * (summed over the calling threads), reserved.  SMEM_GPU_ADAPTER_STATS=1 prints all of them at exit. */
+void harp_gpu_service_stats8(uint64_t out[8]);
+/* bwt_smem1_batched returns void (bwt.c:444), so a GPU failure cannot be handed to the caller: it is reported once on
+ * stderr, the affected lists come back EMPTY (there is no CPU fallback), and the code of the last failure stays readable here
+ * (0 = none; *msg = its text).  SMEM_GPU_ADAPTER_ABORT=1 makes a failure abort the process instead.
+ * Other environment: SMEM_GPU_ADAPTER_HANDLES (service handles = concurrent launches, default 4), SMEM_GPU_MAX_BATCH (reads
+ * per launch, default 65536), SMEM_GPU_MAX_READ_LEN (first size of the handles; they grow on demand). */
+int harp_gpu_service_last_error(const char **msg);
 
 #ifdef __cplusplus
 }

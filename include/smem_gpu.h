@@ -72,6 +72,12 @@ enum {
  * shards overlap; lanes of one GPU share a single copy of the index. */
 int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int64_t max_batch_reads, int max_read_len);
 int smem_gpu_destroy(smem_gpu_t *h);
+/* Device memory of a handle grows with both limits: per lane read_cap * (max_read_len + ~2.6 KB) bytes of batch buffers plus
+ * sm_count * 9 * 64 * 3 * (max_read_len + 2) * 32 bytes of list scratch (0.85 GB at 101 bp, 2.1 GB at 250 bp, 8.4 GB at
+ * 1024 bp; max_read_len <= 65535 is accepted, but beyond a few thousand bases the scratch alone exhausts HBM and create /
+ * resize return SMEM_GPU_E_NOMEM).  smem_gpu_resize re-sizes the batch buffers in place -- index, samples and accelerator
+ * tables stay -- so a caller can start small and grow when a longer read or a larger batch arrives. */
+int smem_gpu_resize(smem_gpu_t *h, int64_t max_batch_reads, int max_read_len);
 
 /* Replaces the memcpy into SPL_BWT_ref + handshake `2` of bwa_idx_load_bwt (bwa.c:289-301):
  * copies bwt->bwt, primary, L2, seq_len to every GPU of the handle, once. */
@@ -85,20 +91,6 @@ int smem_gpu_upload_index_device(smem_gpu_t *h, const smem_index_desc_t *ix, int
  * handles may run concurrently from different threads, so one thread's copies overlap another thread's kernels. */
 int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src);
 
-/* K-mer count pyramid of the indexed text -- optional accelerator tables of smem_gpu_collect.
- * Most bwt_extend calls of bwt_smem1 (bwt.c:776-835) are made on patterns of at most ~17 bases and only their
- * interval SIZES are looked at (bwt.c:794-799, 813-824); sizes and interval starts of short patterns are functions of
- * the pattern alone and are tabulated here for every k-mer of up to direct_levels + 5 bases (12 + 5 on a 3.1 Gbp
- * index: 25 GB of HBM).  Built on every GPU of the handle from the 2-bit forward text: `pac` is bwaidx_t::pac /
- * the .pac file of the reference (bntseq.c:_get_pac: 4 bases per byte, first base in the top bits; the library appends
- * the reverse complement itself, bntseq.c:268-273), l_pac = bntseq_t::l_pac; src_device < 0: host pointer, else the
- * CUDA device holding it.  Results never depend on the tables: a read whose k-mers hit a saturated or otherwise
- * unknown entry is seeded by the plain FM kernel.  smem_gpu_smem1 / smem_gpu_trace do not use the tables.
- * Choose direct_levels so that 4^(direct_levels + 5) is a small multiple of the text length (3.1 Gbp: 12; 100 Mbp: 9). */
-int smem_gpu_build_kmer_tables(smem_gpu_t *h, const uint8_t *pac, int64_t l_pac, int src_device, int direct_levels);
-/* Test hook: copy one table to the host.  which: 0 = cnt[level] (uint32), 1 = cum[level] (uint64), 2 = pyr, 3 = top (uint8). */
-int smem_gpu_get_kmer_table(smem_gpu_t *h, int which, int level, void *out, int64_t out_bytes);
-
 /* Repeat filter of the re-seeding pass -- optional accelerator table of smem_gpu_collect.
  * smem_next2 re-seeds from the middle x of a long, nearly unique SMEM with min_intv >= 2 (bwamem.c:272-278), and the
  * merge keeps an entry of that pass only if its length is >= max >> 1 (bwamem.c:288,297).  Such an entry is a pattern
@@ -107,7 +99,9 @@ int smem_gpu_get_kmer_table(smem_gpu_t *h, int which, int level, void *out, int6
  * cannot contribute and is skipped (about a third of all bwt_extend calls of a 101 bp read).  The table holds one bit per
  * hash value: set <=> some kmer_len-mer with that hash occurs more than once in T = forward + reverse complement; hash
  * collisions cost a skip, never a wrong one, and results never depend on the table.  Built on every GPU of the handle
- * from the 2-bit forward text (`pac`, l_pac, src_device as for smem_gpu_build_kmer_tables).  kmer_len 0 = from the text
+ * from the 2-bit forward text: `pac` is bwaidx_t::pac / the .pac file of the reference (bntseq.c:_get_pac: 4 bases per byte,
+ * first base in the top bits; the library appends the reverse complement itself, bntseq.c:268-273), l_pac = bntseq_t::l_pac;
+ * src_device < 0: host pointer, else the CUDA device holding it.  kmer_len 0 = from the text
  * length (22 on a 3.1 Gbp index; 4^kmer_len ~ 1000 x the text length), log2_bits 0 = the smallest power of two
  * for which at most 1/256 of the bits are set (found by filling a table of 8 bits per text position and folding it down:
  * 32-128 MB and L2-friendly on a repeat-poor text, gigabytes on a repeat-rich one).  smem_gpu_smem1 / smem_gpu_trace return raw bwt_smem1 lists and never skip.
@@ -201,6 +195,53 @@ int smem_gpu_run_collect(smem_gpu_t *h, const smem_seed_opt_t *opt, int64_t *tot
 int smem_gpu_fetch(smem_gpu_t *h, smem_intv_t *intv_out, int64_t intv_cap, int64_t *read_off,
                    uint16_t *step_out, int64_t *total_out);
 
+/* ---- Compact wire formats (what replaces the reference's 256-byte input record, bwt.c:574-596,
+ * and its 64 + 32 n byte output record, afu_core.v:1931-1960 / bwt.c:719-749).  The interval lists are the same, bit for
+ * bit; only their representation on the PCIe link and in the caller's buffers shrinks: 26 instead of 109 bytes per
+ * 101 bp read going in, 16 instead of 32 bytes per interval and 4 instead of 8 bytes per read coming out.
+ *
+ * Reads: fixed-stride records of two bits per base, four bases per byte, FIRST base in the TOP bits (the reference's .pac
+ * convention, bntseq.c:_set_pac); record i starts at seq2 + i * stride.  Every read has read_len bases unless lens != NULL.
+ * A two-bit code cannot say "ambiguous" (bwamem.c:1403-1406 maps N to 4), so those bases travel as an exception list,
+ * sorted by read; the two bits stored at such a position are ignored. */
+typedef struct { uint32_t read; uint16_t pos; uint16_t reserved; } smem_amb_t;
+typedef struct {
+	int64_t n_reads;
+	const uint8_t *seq2;
+	int32_t stride;          /* bytes per record, >= ceil(longest read / 4) */
+	int32_t read_len;        /* length of every read when lens == NULL */
+	const uint16_t *lens;    /* optional: per-read lengths */
+	const smem_amb_t *amb;   /* optional: ambiguous bases, ascending by read */
+	int64_t n_amb;
+} smem_reads2_t;
+
+/* Result record: bits 0-32 x[0], 33-65 x[1], 66-98 x[2], 99-112 query begin, 113-126 query end (w[0] = low word).
+ * Valid for indices with seq_len < 2^33 (8.5 Gbp of forward + reverse text: any genome up to 4.2 Gbp) and reads shorter
+ * than 2^14 bases; the *_packed entry points return SMEM_GPU_E_ARG otherwise (use the 32-byte form). */
+typedef struct { uint64_t w[2]; } smem_intv16_t;
+static inline void smem_intv16_unpack(const smem_intv16_t *p, smem_intv_t *o)
+{
+	const uint64_t m33 = ((uint64_t)1 << 33) - 1;
+	o->x[0] = p->w[0] & m33;
+	o->x[1] = (p->w[0] >> 33) | ((p->w[1] & 3) << 31);
+	o->x[2] = (p->w[1] >> 2) & m33;
+	o->info = (((p->w[1] >> 35) & 0x3fff) << 32) | ((p->w[1] >> 49) & 0x3fff);
+}
+
+/* smem_gpu_collect with both formats: read_off = uint32[n_reads + 1] (CSR), intv_out in the same order as
+ * smem_gpu_collect's.  On SMEM_GPU_E_CAPACITY read_off and *total_out are valid. */
+int smem_gpu_collect_packed(smem_gpu_t *h, const smem_reads2_t *reads, const smem_seed_opt_t *opt, smem_intv16_t *intv_out,
+                            int64_t intv_cap, uint32_t *read_off, int64_t *total_out);
+/* Split form: compact reads in (then smem_gpu_run_collect, smem_gpu_seeds, smem_gpu_chains as usual) / 16-byte records out
+ * (after any smem_gpu_run_collect or smem_gpu_collect*). */
+int smem_gpu_stage_reads_packed(smem_gpu_t *h, const smem_reads2_t *reads);
+int smem_gpu_fetch_packed(smem_gpu_t *h, smem_intv16_t *intv_out, int64_t intv_cap, uint32_t *read_off, int64_t *total_out);
+/* Host-side packer for callers that hold bwa's one-byte-per-base reads (n_threads host threads; lens and amb may be NULL if
+ * the batch has one length / the caller knows there are no ambiguous bases -- then an ambiguous base is an error).
+ * *n_amb_out = entries written (or needed, with SMEM_GPU_E_CAPACITY). */
+int smem_gpu_pack_reads(int64_t n_reads, const uint8_t *seq, const int64_t *offs, int32_t stride, uint8_t *seq2, uint16_t *lens,
+                        smem_amb_t *amb, int64_t amb_cap, int64_t *n_amb_out, int n_threads);
+
 /* Pinned host memory for the caller's batches (replaces the MPF-VTP workspace buffers). */
 int smem_gpu_host_alloc(void **ptr, size_t bytes);
 int smem_gpu_host_free(void *ptr);
@@ -218,11 +259,14 @@ int smem_gpu_last_timing(const smem_gpu_t *h, smem_gpu_timing_t *t);
 /* Tuning knobs: "blocks_per_sm", "slot_cap", "b_cap" (prev/curr entries kept in shared
  * memory per read), "force_wide" (32-byte entries), "l2_fetch_granularity" (32|64|128, device-wide
  * cudaLimitMaxL2FetchGranularity hint), "probe_variant", "l2_hot_min_intv" (0 = off:
- * occ-block loads for intervals of size >= value carry an L2 evict_last hint), "reuse" (keep the last occ sectors
- * in registers), "spare_sms" / "chain_lanes" (scheduling of several pipeline lanes on one GPU), "repeat_filter" /
+ * occ-block loads for intervals of size >= value carry an L2 evict_last hint), "spare_sms" / "chain_lanes" (scheduling of several pipeline lanes on one GPU), "repeat_filter" /
  * "spec_walk" / "unique_walk" (0 = do not use that shortcut of DESIGN.md section 10; results are the same),
  * "unique_walk_min_run" / "unique_walk_min_left" (a unique walk starts after that many extends of an interval of size 1
- * and with at least that many read bases left; 3 / 8), "count_skips" (debug counters "pass2_skipped", "unique_walks"). */
+ * and with at least that many read bases left; 3 / 8), "count_skips" (debug counters "pass2_skipped", "unique_walks").
+ * "blocks_per_sm" accepts the launch-bounds variants that were compiled in (6, 8, 9).  Read-only: "table_bytes" /
+ * "uw_table_bytes" / "index_bytes" (HBM of device 0), and the wall-time accumulators of the one-call forms, summed over the
+ * handle's lanes: "acc_stage_us" (H2D), "acc_turn_us" (waiting for the GPU's kernel turn), "acc_run_us" (kernels),
+ * "acc_fetch_us" (D2H), "acc_calls", "acc_h2d_bytes", "acc_d2h_bytes"; set "acc_reset" to clear them. */
 int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t value);
 int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name);
 

@@ -118,14 +118,16 @@ def test_slot_overflow_rerun_and_knobs(world, synth):
     seq, offs = synth.to_batch(synth.simulate_reads(ref, 4000, 101, 0.03, seed=31, n_frac=0.05))
     a = o.collect(seq, offs, OSeedOpt(), nthreads=8)
     try:
-        for name, val in [("slot_cap", 2), ("slot_cap", 128), ("blocks_per_sm", 3), ("blocks_per_sm", 12), ("blocks_per_sm", 6),
+        for name, val in [("slot_cap", 2), ("slot_cap", 128), ("blocks_per_sm", 6), ("blocks_per_sm", 9), ("blocks_per_sm", 8),
                           ("b_cap", 2), ("b_cap", 7), ("force_wide", 1), ("b_cap", 19), ("force_wide", 0),
-                          ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0), ("reuse", 1), ("reuse", 0)]:
+                          ("l2_hot_min_intv", 64), ("l2_hot_min_intv", 0)]:
             g.set_param(name, val)
             b = g.collect(seq, offs)
             same_result(a, b, ("read_off", "intv", "step"))
             if name == "slot_cap" and val == 2:
                 assert g.timing()["overflow_reads"] > 0
+        with pytest.raises(pkg("smem_gpu").SmemGpuError):      # only launch-bounds variants that were compiled in are accepted
+            g.set_param("blocks_per_sm", 12)
     finally:
         g.set_param("slot_cap", 128); g.set_param("blocks_per_sm", 8); g.set_param("l2_hot_min_intv", 0)
         g.set_param("b_cap", 19); g.set_param("force_wide", 0)

@@ -284,18 +284,23 @@ def test_gpu_text_index_and_unique_walk(fm, synth):
     """Unique-walk tables (full SA / inverse from the samples on the device) against the oracle's bwt_sa, and seeding with
     the walk on against the oracle: random + repeat-rich text, both strands, junction, N, ragged lengths, TRACE."""
     sg = pkg("smem_gpu")
-    for name, ref in (("random", synth.make_reference(300_000, 5)), ("repeats", repeat_rich_reference(200_000, 8))):
+    for name, ref, shift in (("random", synth.make_reference(300_000, 5), 2), ("repeats", repeat_rich_reference(200_000, 8), 3),
+                             ("random-full-isa", synth.make_reference(120_001, 6), 0)):
         ix = fm.build_index(ref, sa_intv=32)
         o = Oracle(ix)
         g = sg.SmemGpu(max_batch_reads=4096, max_read_len=256, devices=[0, 0])
         g.upload_index(ix); g.upload_sa(ix)
+        g.set_param("unique_walk_isa_shift", shift)                       # sampling distance of the inverse suffix array (PH_UW_LF steps)
         g.build_text_index(ref)
         n = ix.seq_len
-        fsa, isa = g.text_index(0), g.text_index(1)
+        fsa, isa_s = g.text_index(0), g.text_index(1)                     # 33-bit tables, unpacked by the test hook
         rows = np.arange(1, n + 1, dtype=np.uint64)
         assert np.array_equal(fsa[1:], o.sa(ix, rows))                    # every row but the '$' row
-        assert int(fsa[0]) == n and int(isa[n]) == 0
-        assert np.array_equal(isa[fsa[1:].astype(np.int64)], rows)        # inverse
+        assert int(fsa[0]) == n
+        isa = np.empty(n + 1, np.uint64); isa[fsa.astype(np.int64)] = np.arange(n + 1, dtype=np.uint64)   # inverse of the full table
+        k = 1 << g.get_param("unique_walk_isa_shift")                     # samples: position n - e * k for e = 0, 1, ...
+        assert len(isa_s) == n // k + 1 and np.array_equal(isa_s, isa[n - k * np.arange(n // k + 1)])
+        assert g.get_param("uw_table_bytes") < 5.5 * n + 4096             # 0.5 + 4.57 + 4.57 / 4 bytes per text position
         g.build_repeat_filter(ref, 13, 0)
         r = ref.numpy()
         T = np.concatenate([r, (3 - r)[::-1]])

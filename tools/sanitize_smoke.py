@@ -16,7 +16,7 @@ for devices in ([0], [0, 0]):
     g = sg.SmemGpu(max_batch_reads=1024, max_read_len=128, devices=devices)
     g.upload_index(ix); g.upload_sa(ix)
     g.build_repeat_filter(ref, 12, 0)                  # filter + window flags + speculative walk are on from here
-    for name, val in (("slot_cap", 128), ("slot_cap", 3), ("b_cap", 2), ("force_wide", 1), ("blocks_per_sm", 4)):
+    for name, val in (("slot_cap", 128), ("slot_cap", 3), ("b_cap", 2), ("force_wide", 1), ("blocks_per_sm", 6)):
         g.set_param(name, val)
         got = g.collect(seq, offs)
         assert np.array_equal(got["intv"], want["intv"]) and np.array_equal(got["read_off"], want["read_off"]), (devices, name, val)
