@@ -215,6 +215,7 @@ def main():
     if use_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+        host_group = dist.new_group(backend="gloo")       # host-side barrier for the legs in which one rank drives every GPU
     from oracle.binding import SeedOpt as OSeedOpt
     sg = importlib.import_module("bwa-mem-harp2_b200.smem_gpu")
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
@@ -484,19 +485,9 @@ def main():
         sync()
         return time.perf_counter() - t1, r
 
-    def max_over_ranks(x):
-        tt = torch.tensor([x], dtype=torch.float64, device=device)
-        if use_dist:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
-    def gather_ranks(vals):
-        tt = torch.tensor(vals, dtype=torch.float64, device=device)
-        if not use_dist:
-            return [vals]
-        out = [torch.zeros_like(tt) for _ in range(world)]
-        dist.all_gather(out, tt)
-        return [[float(v) for v in o.tolist()] for o in out]
+    sh = importlib.import_module("bwa-mem-harp2_b200.sharding")      # the host-side multi-GPU plumbing: max / gather over ranks
+    max_over_ranks = lambda x: sh.max_over_ranks(x, device)
+    gather_ranks = lambda vals: sh.gather_rows(vals, device)
 
     # (1) the headline: compact wire format both ways
     def step_packed(t):
@@ -592,6 +583,40 @@ def main():
         log("e2e, chains out:", extras["e2e_chains"])
         for a_ in seed_off + pseeds + chain_off + pchains:
             a_.free()
+
+    # ---- the other multi-GPU form of the C ABI: ONE handle spanning all N devices of the box (a C host program's form; the
+    # library shards the batch and stitches the CSR on the host).  Rank 0 drives it while the other ranks wait on the host.
+    if use_dist and not args.no_extras:
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                gs = sg.SmemGpu(max_batch_reads=n, max_read_len=args.read_len, devices=list(range(world)))
+                gs.upload_index(ix)                      # peer copies of the packed bwt_t to every GPU of the handle
+                want_rec, want_off = prec[0].array[:tot_e2e].copy(), proff32[0].array.copy()
+                def call_single():
+                    tot = C.c_int64(0)
+                    rc = lib.smem_gpu_collect_packed(gs.h, C.byref(packed.desc), C.byref(opt), C.c_void_p(prec[0].array.ctypes.data), C.c_int64(cap16),
+                                                     C.c_void_p(proff32[0].array.ctypes.data), C.byref(tot))
+                    if rc:
+                        raise RuntimeError(f"single handle: {rc} {lib.smem_gpu_last_error(gs.h).decode()}")
+                    return int(tot.value)
+                call_single()
+                ts_ = time.perf_counter()
+                for _ in range(3):
+                    tot_s = call_single()
+                dts = (time.perf_counter() - ts_) / 3
+                same = tot_s == tot_e2e and np.array_equal(prec[0].array[:tot_s], want_rec) and np.array_equal(proff32[0].array, want_off)
+                extras["single_handle_all_devices"] = {"devices": world, "reads_per_call": n, "bit_exact_vs_one_gpu_run": bool(same), "ms_per_call": dts * 1e3,
+                                                       "reads_per_s": n / dts, "note": "one smem_gpu_t over all GPUs of the box, one host call (strong scaling of ONE batch; "
+                                                       "index only on the other GPUs, no accelerator tables)"}
+                log("single handle over all devices:", extras["single_handle_all_devices"])
+                if not same:
+                    raise SystemExit("PARITY FAILURE: the N-device handle returns different intervals")
+                gs.close()
+            except RuntimeError as e:
+                extras["single_handle_all_devices"] = {"skipped": str(e)}
+        dist.barrier(group=host_group)
 
     # ---- where the end-to-end time goes when several GPUs share the host: the copy volumes of a step alone, and next to a running seed kernel
     pcie = None
@@ -712,10 +737,7 @@ def main():
         g.set_param("probe_variant", 0); rand64_split = g.gather_roofline(64, 0, 2048, 1000)
 
     # ---- max over ranks
-    times = torch.tensor([dt, float(np.mean(seed_ms))], dtype=torch.float64, device=device)
-    if use_dist:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, seed_avg_ms = [float(x) for x in times.tolist()]
+    dt, seed_avg_ms = max_over_ranks(dt), max_over_ranks(float(np.mean(seed_ms)))
 
     if rank == 0:
         peaks = {}

@@ -15,10 +15,14 @@
 // definition: every seed sees the chains its predecessors made), all lanes do the parts that grow with the number of
 // chains -- the ordered insert (shift of the sorted chain list), the chain weights, the permutation after the sort and
 // the copy-out -- so that a repeat read costs O(n^2 / 32) instead of stalling the grid behind one thread.
-// No B-tree: per read the chains live in a sorted array of chain ids in HBM scratch (a chain's id is the index of its
-// first seed; pos = that seed's rbeg), seeds of a chain are a linked list through s_next in insertion order.
-// Equal keys follow what a kbtree leaf does (kbtree.h __kb_getp_aux finds the FIRST equal key, __kb_putp_aux inserts
-// right after it); the reference's own result for equal keys depends on node splits once a read has more than ~11 chains.
+// A chain's id is the index of its first seed (pos = that seed's rbeg); the seeds of a chain are a linked list through s_next in
+// insertion order.  While a read's chains are being built they live in a B-tree of chain ids with the node capacity, search,
+// pre-emptive split and descent rules of the reference's klib kbtree (bwamem.c:328-331 / kbtree.h: t = 8, at most 15 keys per
+// node): for chains with EQUAL pos -- the same reference segment twice in a read, more than w apart -- which one is found as the
+// lower bound, where the next one goes and the order they leave in depend on the shape of that tree, so a sorted array (round 1)
+// was not enough (oracle/smem_oracle.c bt_*; tests/test_chains.py crafted equal-key reads against the reference's mem_chain).
+// Lane 0 runs the insertion loop -- it is sequential by definition, and O(log n) per seed now; the tree is walked in order into
+// `ord`, from where the filter and the copy-out use all lanes.
 #pragma once
 #include "smem_kernels.cuh"
 
@@ -38,7 +42,8 @@ struct ChainWork {
 	const long long *off;        // [n + 1] interval CSR of the reads (d_off)
 	const long long *soff;       // [total + 1] seed offset of every interval (d_soff): read r owns seeds soff[off[r]] .. soff[off[r+1]]
 	long long n;
-	int *ord, *ord2;             // per seed slot: sorted chain ids / scratch for the permutation
+	int *ord, *ord2;             // per seed slot: chain ids in tree order / scratch for the permutation
+	int *bt;                     // B-tree nodes, BT_INTS ints each; read r owns nodes soff[off[r]] / 7 + 2 r .. (at most n_seeds / 7 + 2 of them)
 	int *c_last, *c_n, *s_next;  // per chain (at its first seed's slot): last seed, seed count; per seed: next seed of its chain
 	FltRec *flt;
 	unsigned char *keep;
@@ -140,6 +145,112 @@ __device__ __noinline__ void flt_introsort(size_t n, FltRec *a)
 	}
 }
 
+// ---- the reference's kbtree over chain ids (see the header; restated from kbtree.h:117-226, 336-361) ----
+#define BT_T 8
+#define BT_MAX (2 * BT_T - 1)
+#define BT_INTS 32           // [0] number of keys | internal << 8, [1..15] keys, [16..31] children
+#define BT_LEAF 0
+#define BT_INTERNAL 256
+struct BTree { int *nd; int n_nodes, root; const Seed *sd; };
+
+__device__ __forceinline__ int *bt_node(const BTree &t, int x) { return t.nd + (size_t)x * BT_INTS; }
+__device__ __forceinline__ int bt_new(BTree &t, int kind)
+{
+	bt_node(t, t.n_nodes)[0] = kind;
+	return t.n_nodes++;
+}
+// __kb_getp_aux: index of the FIRST key equal to pos (r = 0), else of the last smaller key (-1 if none)
+__device__ __forceinline__ int bt_find(const BTree &t, const int *nd, long long pos, int &r)
+{
+	const int n = nd[0] & 255;
+	int lo = 0, hi = n;
+	if (n == 0) return -1;
+	while (lo < hi) { const int mid = (lo + hi) >> 1; if (t.sd[nd[1 + mid]].rbeg < pos) lo = mid + 1; else hi = mid; }
+	if (lo == n) { r = 1; return n - 1; }
+	r = t.sd[nd[1 + lo]].rbeg == pos ? 0 : -1;
+	return r < 0 ? lo - 1 : lo;
+}
+// kb_intervalp's lower bound: an equal key ends the descent at once, otherwise the deepest "last smaller key" on the way down
+__device__ __forceinline__ int bt_lower(const BTree &t, long long pos)
+{
+	int x = t.root, lower = -1, r = 0;
+	for (;;) {
+		const int *nd = bt_node(t, x);
+		const int i = bt_find(t, nd, pos, r);
+		if (i >= 0 && r == 0) return nd[1 + i];
+		if (i >= 0) lower = nd[1 + i];
+		if (!(nd[0] & BT_INTERNAL)) return lower;
+		x = nd[16 + i + 1];
+	}
+}
+// __kb_split: child y = children[i] of x is full; its upper half moves to a new node z, its median up into x
+__device__ __forceinline__ void bt_split(BTree &t, int xi, int i, int yi)
+{
+	int *y = bt_node(t, yi);
+	const int kind = y[0] & BT_INTERNAL;
+	const int zi = bt_new(t, kind);
+	int *x = bt_node(t, xi), *z = bt_node(t, zi);
+	z[0] = kind | (BT_T - 1);
+	for (int k = 0; k < BT_T - 1; ++k) z[1 + k] = y[1 + BT_T + k];
+	if (kind) for (int k = 0; k < BT_T; ++k) z[16 + k] = y[16 + BT_T + k];
+	y[0] = kind | (BT_T - 1);
+	const int xn = x[0] & 255;
+	for (int k = xn; k > i; --k) x[16 + k + 1] = x[16 + k];
+	x[16 + i + 1] = zi;
+	for (int k = xn - 1; k >= i; --k) x[1 + k + 1] = x[1 + k];
+	x[1 + i] = y[1 + BT_T - 1];
+	x[0] = BT_INTERNAL | (xn + 1);
+}
+// kb_putp / __kb_putp_aux: a full root is split first; a full child is split before it is entered and the descent moves
+// right only if pos is GREATER than the median moved up; in a leaf the key goes right behind the slot bt_find names
+__device__ __forceinline__ void bt_put(BTree &t, int id)
+{
+	const long long pos = t.sd[id].rbeg;
+	int x = t.root, r = 0;
+	if ((bt_node(t, x)[0] & 255) == BT_MAX) {
+		const int s = bt_new(t, BT_INTERNAL);
+		bt_node(t, s)[16] = x;
+		bt_split(t, s, 0, x);
+		t.root = x = s;
+	}
+	for (;;) {
+		int *nd = bt_node(t, x);
+		if (!(nd[0] & BT_INTERNAL)) break;
+		int i = bt_find(t, nd, pos, r) + 1;
+		if ((bt_node(t, nd[16 + i])[0] & 255) == BT_MAX) {
+			bt_split(t, x, i, nd[16 + i]);
+			if (pos > t.sd[nd[1 + i]].rbeg) ++i;
+		}
+		x = nd[16 + i];
+	}
+	int *nd = bt_node(t, x);
+	const int n = nd[0] & 255, i = bt_find(t, nd, pos, r);
+	for (int k = n - 1; k > i; --k) nd[1 + k + 1] = nd[1 + k];
+	nd[1 + i + 1] = id;
+	nd[0] = n + 1;                                   // (a leaf)
+}
+// __kb_traverse: in order, iteratively (depth <= 11 for 2^31 keys at >= 8 children per internal node).
+// A frame holds 2 * i + phase: phase 0 = child i is still to be visited, 1 = child i is done and key i comes next.
+__device__ __forceinline__ int bt_walk(const BTree &t, int *out)
+{
+	int sx[12], si[12], top = 0, n = 0;
+	sx[0] = t.root; si[0] = 0;
+	while (top >= 0) {
+		const int *nd = bt_node(t, sx[top]);
+		const int nk = nd[0] & 255;
+		if (!(nd[0] & BT_INTERNAL)) {
+			for (int k = 0; k < nk; ++k) out[n++] = nd[1 + k];
+			--top;
+			continue;
+		}
+		const int i = si[top] >> 1;
+		if (!(si[top] & 1)) { si[top] |= 1; ++top; sx[top] = nd[16 + i]; si[top] = 0; continue; }
+		if (i < nk) { out[n++] = nd[1 + i]; si[top] = 2 * (i + 1); continue; }
+		--top;
+	}
+	return n;
+}
+
 #define CHAIN_TPB 128
 
 __global__ void __launch_bounds__(CHAIN_TPB) chain_build_kernel(const ChainWork cw, const ChainOpt o)
@@ -153,51 +264,37 @@ __global__ void __launch_bounds__(CHAIN_TPB) chain_build_kernel(const ChainWork 
 	int *ord = cw.ord + s0, *ord2 = cw.ord2 + s0, *c_last = cw.c_last + s0, *c_n = cw.c_n + s0, *s_next = cw.s_next + s0;
 	int nch = 0;
 
-	// ---- insertion loop, bwamem.c:478-496 (lane 0 decides, the warp shifts)
-	for (int e = 0; e < ns; ++e) {
-		int ins = -1;
-		if (lane == 0) {
+	// ---- insertion loop, bwamem.c:478-496: sequential by definition (every seed sees the chains its predecessors made) -> lane 0
+	if (lane == 0 && ns > 0) {
+		BTree t;
+		t.nd = cw.bt + ((size_t)(s0 / 7) + 2 * (size_t)r) * BT_INTS; t.n_nodes = 0; t.sd = sd;
+		t.root = bt_new(t, BT_LEAF);
+		for (int e = 0; e < ns; ++e) {
 			const Seed s = ld_seed(&sd[e]);
-			if (!(s.rbeg < o.l_pac && o.l_pac < s.rbeg + s.len)) {                 // not bridging the forward/reverse boundary
-				int lo = 0, hi = nch;
-				while (lo < hi) { const int mid = (lo + hi) >> 1; if (sd[ord[mid]].rbeg < s.rbeg) lo = mid + 1; else hi = mid; }
-				int cand;
-				if (lo < nch && sd[ord[lo]].rbeg == s.rbeg) { cand = lo; ins = lo + 1; }   // first equal key; a new chain goes right after it
-				else { cand = lo - 1; ins = lo; }
-				if (cand >= 0) {
-					// test_and_merge, bwamem.c:334-356
-					const int f = ord[cand], l = c_last[f];
-					const Seed first = ld_seed(&sd[f]), last = ld_seed(&sd[l]);
-					const long long qend = last.qbeg + last.len, rend = last.rbeg + last.len;
-					bool absorbed = false;
-					if (s.qbeg >= first.qbeg && s.qbeg + s.len <= qend && s.rbeg >= first.rbeg && s.rbeg + s.len <= rend) absorbed = true;   // contained
-					else if ((last.rbeg < o.l_pac || first.rbeg < o.l_pac) && s.rbeg >= o.l_pac) absorbed = false;                    // other strand
-					else {
-						const long long x = s.qbeg - last.qbeg, y = s.rbeg - last.rbeg;
-						if (y >= 0 && x - y <= o.w && y - x <= o.w && x - last.len < o.max_chain_gap && y - last.len < o.max_chain_gap) {
-							s_next[l] = e; s_next[e] = -1; c_last[f] = e; c_n[f] += 1;
-							absorbed = true;
-						}
+			if (s.rbeg < o.l_pac && o.l_pac < s.rbeg + s.len) continue;            // bridging the forward/reverse boundary
+			const int f = nch ? bt_lower(t, s.rbeg) : -1;                          // kb_intervalp: the closest chain at or below rbeg
+			if (f >= 0) {
+				// test_and_merge, bwamem.c:334-356
+				const int l = c_last[f];
+				const Seed first = ld_seed(&sd[f]), last = ld_seed(&sd[l]);
+				const long long qend = last.qbeg + last.len, rend = last.rbeg + last.len;
+				if (s.qbeg >= first.qbeg && s.qbeg + s.len <= qend && s.rbeg >= first.rbeg && s.rbeg + s.len <= rend) continue;          // contained
+				if (!((last.rbeg < o.l_pac || first.rbeg < o.l_pac) && s.rbeg >= o.l_pac)) {                                          // same strand
+					const long long x = s.qbeg - last.qbeg, y = s.rbeg - last.rbeg;
+					if (y >= 0 && x - y <= o.w && y - x <= o.w && x - last.len < o.max_chain_gap && y - last.len < o.max_chain_gap) {
+						s_next[l] = e; s_next[e] = -1; c_last[f] = e; c_n[f] += 1;
+						continue;
 					}
-					if (absorbed) ins = -1;
 				}
 			}
+			c_last[e] = e; c_n[e] = 1; s_next[e] = -1;                             // a new chain, keyed by rbeg (bwamem.c:489-494)
+			bt_put(t, e);
+			++nch;
 		}
-		ins = __shfl_sync(FULL_MASK, ins, 0);
-		if (ins < 0) continue;
-		// ord[ins .. nch) moves up by one, top chunk first
-		for (int hi = nch; hi > ins; hi -= 32) {
-			const int idx = hi - 1 - lane;
-			int v = 0;
-			if (idx >= ins) v = ord[idx];
-			__syncwarp();
-			if (idx >= ins) ord[idx + 1] = v;
-			__syncwarp();
-		}
-		if (lane == 0) { ord[ins] = e; c_last[e] = e; c_n[e] = 1; s_next[e] = -1; }
-		++nch;
-		__syncwarp();
+		if (nch) bt_walk(t, ord);                                                  // __kb_traverse, bwamem.c:608-610
 	}
+	nch = __shfl_sync(FULL_MASK, nch, 0);
+	__syncwarp();
 
 	int n_out = nch;
 	if (o.do_flt && nch > 1) {

@@ -50,7 +50,7 @@ struct SeedParams {
 	int slot_cap;
 	int *counts;             // [n] exact interval count per read (even when > slot_cap)
 	int *overflow_list;      // read ids with count > slot_cap
-	int *status;             // [0] work counter, [1] n_overflow, [2] guard trips, [3] largest overflowing count, [4] largest count
+	int *status;             // [0] work counter, [1] n_overflow, [2] guard trips, [3] largest overflowing count, [5] bad-input flags of the pack pre-pass, [6] skipped re-seeding passes, [7] unique walks
 	Intv *scratch;           // per lane pair: M1, M2, BX arrays of scratch_cap entries each (global, L2-resident)
 	int scratch_cap;
 	int b_cap;               // entries of the prev/curr array kept in shared memory per read (rest spills to BX)
@@ -179,6 +179,9 @@ struct Ext { u64 a, b, s; };   // a = x[!is_back], b = x[is_back], s = x[2]
 // in: (a = x[!is_back], b = x[is_back], s = x[2], c) identical in both lanes of a pair; out likewise.
 // w / v receive this lane's sector of the K / L block.  (Keeping them across calls to skip the gather when the block
 // number repeats was measured: +14 % at equal occupancy, a tie once its registers are paid for -- removed.)
+// NARROW: every base occurs fewer than 2^32 times in the text (checked at upload), so occurrence counts and the sizes of
+// the four child intervals are 32-bit quantities: half the shuffles and none of the carries of the general form.
+template <bool NARROW>
 __device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64 s, int c, int half, int lane, u64 hot_min, u64 pol_hot, u64 pol_cold,
                                            u32 (&w)[8], u32 (&v)[8], const uint4 *alt = nullptr)
 {
@@ -207,6 +210,20 @@ __device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64
 	cl += __shfl_xor_sync(FULL_MASK, cl, 1);
 	// this lane owns bases j0 = 2*half and j0 + 1
 	const int j0 = 2 * half;
+	if (NARROW) {
+		const u32 tk0 = w[0] + ((ck >> (8 * j0)) & 0xffu), tk1 = w[2] + ((ck >> (8 * j0 + 8)) & 0xffu);
+		const u32 tl0 = v[0] + ((cl >> (8 * j0)) & 0xffu), tl1 = v[2] + ((cl >> (8 * j0 + 8)) & 0xffu);
+		const u32 sz0 = tl0 - tk0, sz1 = tl1 - tk1;
+		u64 acc = (u64)(j0 > c ? sz0 : 0u) + (u64)(j0 + 1 > c ? sz1 : 0u);
+		acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+		const u32 tkc = (c & 1) ? tk1 : tk0, szc = (c & 1) ? sz1 : sz0;
+		const int owner = (lane & ~1) | (c >> 1);
+		Ext o;
+		o.a = ix.L2[c] + 1 + (u64)__shfl_sync(FULL_MASK, tkc, owner);
+		o.s = (u64)__shfl_sync(FULL_MASK, szc, owner);
+		o.b = b + ((a <= ix.primary && a + s - 1 >= ix.primary) ? 1 : 0) + acc;
+		return o;
+	}
 	const u64 tk0 = ((u64)w[0] | ((u64)w[1] << 32)) + ((ck >> (8 * j0)) & 0xffu), tk1 = ((u64)w[2] | ((u64)w[3] << 32)) + ((ck >> (8 * j0 + 8)) & 0xffu);
 	const u64 tl0 = ((u64)v[0] | ((u64)v[1] << 32)) + ((cl >> (8 * j0)) & 0xffu), tl1 = ((u64)v[2] | ((u64)v[3] << 32)) + ((cl >> (8 * j0 + 8)) & 0xffu);
 	const u64 sz0 = tl0 - tk0, sz1 = tl1 - tk1;

@@ -49,6 +49,7 @@ struct DeviceCtx {
 	bool seeds_valid = false;        // d_seeds / d_soff describe the resident intervals (set by smem_gpu_seeds, cleared by a new run)
 	// chaining (section 8f-3): scratch per seed slot, outputs
 	int *d_cwork = nullptr; FltRec *d_flt = nullptr; unsigned char *d_keep = nullptr; size_t cwork_cap = 0;
+	int *d_bt = nullptr; size_t bt_nodes = 0;   // B-tree nodes of the chain builder (smem_chain.cuh)
 	int *d_nch = nullptr, *d_nkept = nullptr; long long *d_coff = nullptr, *d_koff = nullptr; size_t cread_cap = 0;
 	Chain *d_chains = nullptr; Seed *d_cseeds = nullptr; size_t chains_cap = 0;
 	long long n_chains = 0, n_cseeds = 0;
@@ -168,6 +169,7 @@ template <typename T> int dev_alloc(DeviceCtx &d, T **p, size_t count)
 void ctx_free_batch(DeviceCtx &d)
 {
 	cudaFree(d.d_k); cudaFree(d.d_kout); cudaFree(d.d_scnt); cudaFree(d.d_soff); cudaFree(d.d_sroff); cudaFree(d.d_seeds);
+	cudaFree(d.d_bt); d.d_bt = nullptr; d.bt_nodes = 0;
 	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
 	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
 	cudaFree(d.d_seq); cudaFree(d.d_qpack); cudaFree(d.d_offs); cudaFree(d.d_rlen); cudaFree(d.d_lens); cudaFree(d.d_amb); cudaFree(d.d_outp); cudaFree(d.d_off32);
@@ -201,7 +203,7 @@ int ctx_alloc_batch(DeviceCtx &d, int64_t read_cap, int max_len, int slot_cap)
 	if ((rc = dev_alloc(d, &d.d_off, (size_t)read_cap + 1))) return rc;
 	if ((rc = dev_alloc(d, &d.d_slots, (size_t)read_cap * slot_cap))) return rc;
 	d.slots_cap_alloc = slot_cap;
-	d.out_cap = (size_t)read_cap * 16 + 1024;
+	d.out_cap = (size_t)read_cap * 24 + 1024;      // (grown on demand; TRACE keeps ~19 raw entries per 101 bp read, COLLECT 11)
 	if ((rc = dev_alloc(d, &d.d_out, d.out_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_step, d.out_cap))) return rc;
 	if ((rc = dev_alloc(d, &d.d_aux, d.out_cap))) return rc;
@@ -212,6 +214,11 @@ int ctx_alloc_batch(DeviceCtx &d, int64_t read_cap, int max_len, int slot_cap)
 	// block sums of the counts -> offsets scan
 	d.tmp_bytes = ((size_t)(read_cap + 1) / SCAN_PER_BLOCK + 2) * sizeof(long long);
 	CK(cudaMalloc(&d.d_tmp, d.tmp_bytes));
+	{   // reads re-packed one base per nibble | window flags of the repeat filter (sizes as in ctx_run_inner)
+		const size_t q_stride = (size_t)(((max_len + 1) / 2 + 15) / 16 * 16);
+		d.qpack_bytes = (size_t)read_cap * q_stride + (size_t)read_cap * (q_stride >> 4) * 4;
+		CK(cudaMalloc((void **)&d.d_qpack, std::max<size_t>(d.qpack_bytes, 16)));
+	}
 	return 0;
 }
 
@@ -631,7 +638,9 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const int scratch_cap = h.max_len + 2;
 	const size_t need = (size_t)max_grid * pairs_per_cta * 3 * scratch_cap;
 	// 16-byte packed prev/curr entries need every SA coordinate < 2^36 and read positions < 2^20
-	const bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
+	// ... and the 32-bit occurrence counts of the narrow extend need every base to occur fewer than 2^32 times
+	bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
+	for (int c = 0; c < 4; ++c) if (d.ix.L2[c + 1] - d.ix.L2[c] >= (1ull << 32)) wide = true;
 	const int q_stride = ((h.max_len + 1) / 2 + 15) / 16 * 16;      // two bases per byte; keeps pair_stride a multiple of 16
 	// b_cap is honoured even if that leaves room for fewer CTAs per SM than blocks_per_sm asks for (the
 	// hardware then simply runs fewer); it only shrinks when a single CTA would not fit at all.
@@ -1082,7 +1091,7 @@ int smem_gpu_device_count(void)
 
 // result slots per read of the first pass: 101 bp reads emit 11 intervals on average, 250 bp reads 48; rarer, longer lists take
 // the overflow re-run (ctx_run_inner), so this only trades HBM (read_cap * slot_cap * 32 bytes) against how often that runs
-static int default_slot_cap(int max_read_len) { return std::min(256, std::max(64, (max_read_len / 2 + 31) / 32 * 32)); }
+static int default_slot_cap(int max_read_len) { return std::min(256, std::max(64, (max_read_len * 3 / 4 + 31) / 32 * 32)); }
 
 int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int64_t max_batch_reads, int max_read_len)
 {
@@ -1279,6 +1288,16 @@ int ctx_chains_run(DeviceCtx &d, const ChainOpt &o)
 	}
 	ChainWork cw;
 	cw.seeds = d.d_seeds; cw.off = d.d_off; cw.soff = d.d_soff; cw.n = d.n;
+	{
+		const size_t nodes = (size_t)d.n_seeds / 7 + 2 * ((size_t)d.n + 1) + 4;      // read r owns nodes soff / 7 + 2 r .. : at most n_seeds_r / 7 + 2
+		if (nodes > d.bt_nodes) {
+			cudaFree(d.d_bt); d.d_bt = nullptr; d.bt_nodes = 0;
+			const size_t cap = nodes + nodes / 8 + 64;
+			CK(cudaMalloc((void **)&d.d_bt, cap * BT_INTS * sizeof(int)));
+			d.bt_nodes = cap;
+		}
+	}
+	cw.bt = d.d_bt;
 	cw.ord = d.d_cwork; cw.ord2 = cw.ord + d.cwork_cap; cw.c_last = cw.ord2 + d.cwork_cap; cw.c_n = cw.c_last + d.cwork_cap; cw.s_next = cw.c_n + d.cwork_cap;
 	cw.flt = d.d_flt; cw.keep = d.d_keep; cw.n_chains = d.d_nch; cw.n_kept = d.d_nkept;
 	const unsigned grid = (unsigned)(((d.n + 1) * 32 + CHAIN_TPB - 1) / CHAIN_TPB);

@@ -47,13 +47,22 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	extern __shared__ uint4 smem_raw[];
 	const int lane = threadIdx.x & 31, half = lane & 1;
 	const int pair = threadIdx.x >> 1;
-	const u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;   // this pair's shared memory
+	u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;   // this pair's shared memory
+#ifdef SEED_KEEP_SP
+	asm volatile("" : "+r"(sp));                             // opaque: kept in its register instead of being re-derived from the thread id at every use
+#endif
 	// cold state first, then B, then the query: the cold-state and B addresses are sp + a compile-time constant
 	const u32 sc = sp;                                       // cold state
 	const u32 sb = sp + COLD_BYTES;                          // B entries (16-byte aligned)
 	const u32 sq = sb + (u32)p.b_cap * BE::BYTES;            // query, two bases per byte
+#ifdef SEED_KEEP_GP
+	u32 gp3 = (u32)(blockIdx.x * (SEED_BLOCK / 2) + pair) * 3u;
+	asm volatile("" : "+r"(gp3));                            // opaque, one register: the scratch base is two multiply-adds away instead of a dozen instructions
+	auto scratch_base = [&]() -> Intv * { return p.scratch + (size_t)gp3 * (size_t)p.scratch_cap; };
+#else
 	Intv *const M1s = p.scratch + (size_t)(blockIdx.x * (SEED_BLOCK / 2) + pair) * 3 * p.scratch_cap;
 	auto scratch_base = [&]() -> Intv * { return M1s; };   // (forcing this out of the main loop with volatile reads cost spills: slower)
+#endif
 
 	u64 pol_hot = 0, pol_cold = 0;
 	if (p.hot_min_intv) {
@@ -95,8 +104,8 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	u32 end = 0;                         // info of that interval (query end)
 	int c = 0;                           // base of the pending extend
 	int i = 0, j = 0, n0 = 0, n_prev = 0, n_curr = 0, len = 0, guard = 0;
-	int max_count = 0;                   // largest per-read interval count this pair produced (sizes the compaction grid)
-	u64 min_intv = 1, last_s = 0;
+	u32 min_intv = 1;                    // <= split_width + 1, an int (bwamem.c:272-278), or the caller's int32 (bwt.c:784)
+	u64 last_s = 0;
 	u32 blk_k[8], blk_l[8];              // this lane's sectors of the K / L occ blocks (see extend_pair)
 #pragma unroll
 	for (int t = 0; t < 8; ++t) blk_k[t] = blk_l[t] = 0;
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(sc + CS_RK, rk); }
 				__syncwarp(3u << (lane & ~1));
 				rk = lds_i32(sc + CS_RK);
-				if ((long long)rk >= p.n) { if (!half && max_count > 0) atomicMax(&p.status[4], max_count); phase = PH_IDLE; break; }
+				if ((long long)rk >= p.n) { phase = PH_IDLE; break; }
 				const int rid = p.list ? p.list[rk] : rk;
 				len = p.rlen[rid];
 				{                                                            // staged by pack_reads_kernel: 16 bytes (32 bases) per copy
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					phase = PH_NEXT_STEP;
 				} else {
 					const int x = p.xs[rid], mi = p.min_intvs[rid];
-					min_intv = mi < 1 ? 1 : (u64)mi;                                              // bwt.c:784
+					min_intv = mi < 1 ? 1u : (u32)mi;                                            // bwt.c:784
 					sts_u16(sc + CS_PASS, 0); sts_u16(sc + CS_X, x);
 					if (x < 0 || x >= len || qbase(sq, x) > 3) {                                // bwt.c:783
 						p.ret[rid] = x + 1; p.counts[rk] = 0; phase = PH_NEED_READ;
@@ -141,14 +150,13 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				if (start >= len) {
 					const int rk = lds_i32(sc + CS_RK), n_out = lds_i32(sc + CS_NOUT);
 					p.counts[rk] = n_out;
-					max_count = max(max_count, n_out);
 					if (n_out > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sc + CS_RID); atomicMax(&p.status[3], n_out); }
 					phase = PH_NEED_READ;
 					break;
 				}
 				sts_u16(sc + CS_START, start); sts_u16(sc + CS_ORI, start); sts_u16(sc + CS_X, start); sts_u16(sc + CS_PASS, 0);
 				if (SPEC) sts_u16(sc + CS_KEEP, lim1);       // (CS_KEEP is otherwise only used by the merge after a re-seeding pass)
-				min_intv = p.start_width < 1 ? 1 : (u64)p.start_width;
+				min_intv = p.start_width < 1 ? 1u : (u32)p.start_width;
 				phase = PH_INIT_CALL;
 			} break;
 			case PH_INIT_CALL: {     // bwt_set_intv, bwt.c:788-789, then the head of the forward loop
@@ -205,7 +213,6 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					for (int e = n_mem - 1, o = 0; e >= 0; --e, ++o)             // bwt.c:829: ascending start
 						if (o < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[o], t.x0, t.x1, t.x2, t.info); }
 					p.counts[rk] = n_mem; p.ret[rid] = lds_u16(sc + CS_RET);
-					max_count = max(max_count, n_mem);
 					if (n_mem > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_mem); }
 					phase = PH_NEED_READ;
 					break;
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 						if (n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width) {   // bwamem.c:272
 							sts_u16(sc + CS_PASS, 1);
 							sts_u16(sc + CS_X, (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1);
-							min_intv = max_s + 1;
+							min_intv = (u32)max_s + 1u;
 							phase = PH_INIT_CALL;
 							break;
 						}
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					if (reseed) {
 						sts_u16(sc + CS_NM1, n_mem); sts_u16(sc + CS_KEEP, max_len); sts_u16(sc + CS_PASS, 1);
 						sts_u16(sc + CS_X, (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1);
-						min_intv = max_s + 1;
+						min_intv = (u32)max_s + 1u;
 						phase = PH_INIT_CALL;
 						break;
 					}
@@ -321,7 +328,11 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			else byte = (u64)p.uw_text + 32 * ((tq >> 6) + (u64)half);
 			alt = reinterpret_cast<const uint4 *>(byte);
 		}
-		const Ext ok = extend_pair(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
+#ifdef SEED_NARROW
+		const Ext ok = extend_pair<!WIDE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
+#else
+		const Ext ok = extend_pair<false>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
+#endif
 		if (phase == PH_IDLE) continue;
 		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
 

@@ -65,16 +65,19 @@ typedef struct req {
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
 static svc_handle_t g_hd[MAX_HANDLES];
-static int g_n_handles = 0;
+static int g_n_handles = 0;      /* handles in service (index uploaded) */
+static int g_n_created = 0;      /* handles created (by the preload thread or the first call) */
 static req_t *g_head = 0, *g_tail = 0;
 static const harp_bwt_t *g_bwt = 0;
-static int64_t g_max_batch = 1 << 16;
+static int64_t g_max_batch = 1 << 15;
 static int g_init_len = 160;
 static int g_last_rc = 0, g_abort_on_error = 0, g_reported = 0, g_start_failed = 0;
 static char g_last_err[512];
 /* GPU calls, reads sent, intervals received, lists served from the batch cache, requests combined into those calls,
- * nanoseconds inside the GPU calls, nanoseconds inside bwt_smem1_batched (summed over threads) */
-static uint64_t g_stats[8];
+ * nanoseconds inside the GPU calls, nanoseconds inside bwt_smem1_batched (summed over threads), of which bringing the
+ * service up (index upload, handles) or waiting for the thread that does; [8..11] leader breakdown: gather, launch, hand-back
+ * nanoseconds and handle / buffer growth events */
+static uint64_t g_stats[12];
 static int g_use_cache = -1, g_split_len = 28, g_split_width = 10;   /* -k 19 -r 1.5 -> (int)(19*1.5+.499), bwamem.c:456; split_width bwamem.c:60 */
 
 static uint64_t now_ns(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
@@ -82,9 +85,11 @@ static void stat_add(int k, uint64_t v) { __atomic_fetch_add(&g_stats[k], v, __A
 
 static void print_stats(void)
 {
-	fprintf(stderr, "[bwt_smem1_batched/gpu] gpu_calls=%llu reads_sent=%llu intervals=%llu lists_from_cache=%llu requests=%llu gpu_s=%.3f adapter_s=%.3f handles=%d\n",
+	fprintf(stderr, "[bwt_smem1_batched/gpu] gpu_calls=%llu reads_sent=%llu intervals=%llu lists_from_cache=%llu requests=%llu gpu_s=%.3f adapter_s=%.3f startup_s=%.3f "
+	        "gather_s=%.3f launch_s=%.3f handback_s=%.3f grow_events=%llu handles=%d\n",
 	        (unsigned long long)g_stats[0], (unsigned long long)g_stats[1], (unsigned long long)g_stats[2], (unsigned long long)g_stats[3],
-	        (unsigned long long)g_stats[4], (double)g_stats[5] * 1e-9, (double)g_stats[6] * 1e-9, g_n_handles);
+	        (unsigned long long)g_stats[4], (double)g_stats[5] * 1e-9, (double)(g_stats[6] - g_stats[7]) * 1e-9, (double)g_stats[7] * 1e-9,
+	        (double)g_stats[8] * 1e-9, (double)g_stats[9] * 1e-9, (double)g_stats[10] * 1e-9, (unsigned long long)g_stats[11], g_n_handles);
 }
 
 /* record a failure: message once, code kept for harp_gpu_service_last_error */
@@ -100,29 +105,24 @@ static void fail(const char *what, int rc, smem_gpu_t *h)
 
 int harp_gpu_service_last_error(const char **msg) { if (msg) *msg = g_last_err; return g_last_rc; }
 
-/* ---- service bring-up: the upload step of bwa_idx_load_bwt (bwa.c:289-291), to HBM instead of the MPF workspace ---- */
-static int service_start_inner(const harp_bwt_t *bwt);
-static int service_start_locked(const harp_bwt_t *bwt)
-{
-	int k;
-	const int rc = service_start_inner(bwt);
-	if (rc) {            /* leave nothing half-built behind, and do not try again on every call */
-		for (k = 0; k < MAX_HANDLES; ++k) if (g_hd[k].h) smem_gpu_destroy(g_hd[k].h);
-		memset(g_hd, 0, sizeof g_hd);
-		g_n_handles = 0; g_start_failed = 1;
-	}
-	return rc;
-}
+static int stage_grow(svc_handle_t *s, size_t n, size_t nbytes);
+static int out_grow(svc_handle_t *s, size_t need);
 
-static int service_start_inner(const harp_bwt_t *bwt)
+/* ---- service bring-up ------------------------------------------------------------------------------------------------
+ * Two parts.  (1) Everything that does not need the index -- CUDA context, kernels (CUDA_MODULE_LOADING=EAGER), the service
+ * handles with their device buffers, the pinned staging sized for a full batch -- is created once, by a background thread
+ * started when the host program is loaded with `mem` on its command line, i.e. WHILE bwa reads its index files
+ * (SMEM_GPU_ADAPTER_PRELOAD=0 turns that off; the first call then does it).  First-use allocation inside the worker threads
+ * was measured at 50-750 ms per handle (pinned allocations and cudaFree serialise on the driver while 16 threads wait).
+ * (2) The index upload of bwa_idx_load_bwt (bwa.c:289-291), to HBM instead of the MPF workspace, on the first DO call -- the
+ * reference gives the adapter no earlier hook -- followed by one tiny launch per handle so that no worker pays a first launch. */
+static int g_pre_state = 0;       /* 0 = not started, 1 = running, 2 = done */
+static int g_pre_rc = 0;
+
+static int create_handles(void)
 {
-	int devs[64], n_dev = 0, rc, k, want = 4;
+	int devs[64], n_dev = 0, rc, k, want = 8;
 	const char *e;
-	smem_index_desc_t ix;
-	if (g_n_handles && g_bwt == bwt) return 0;
-	for (k = 0; k < g_n_handles; ++k) { if (g_hd[k].h) smem_gpu_destroy(g_hd[k].h); }
-	memset(g_hd, 0, sizeof g_hd);
-	g_n_handles = 0;
 	if ((e = getenv("SMEM_GPU_MAX_BATCH")) != 0) g_max_batch = atoll(e);
 	if ((e = getenv("SMEM_GPU_MAX_READ_LEN")) != 0) g_init_len = atoi(e);       /* first size only: handles grow on demand */
 	if ((e = getenv("SMEM_GPU_ADAPTER_HANDLES")) != 0) want = atoi(e);
@@ -138,22 +138,87 @@ static int service_start_inner(const harp_bwt_t *bwt)
 	if (n_dev == 0) devs[n_dev++] = 0;
 	if (want < n_dev) want = n_dev;
 	if (want > MAX_HANDLES) want = MAX_HANDLES;
+	for (k = 0; k < want; ++k) {            /* handle k lives on device k mod n_dev */
+		svc_handle_t *s = &g_hd[k];
+		s->dev = devs[k % n_dev]; s->max_batch = g_max_batch; s->max_len = g_init_len;
+		if ((rc = smem_gpu_create(&s->h, 1, &s->dev, s->max_batch, s->max_len)) != 0) return rc;
+		++g_n_created;
+		smem_gpu_set_param(s->h, "turn_min_reads", 1ll << 40);   /* concurrent small launches: never serialise on the kernel turn */
+		if ((rc = stage_grow(s, (size_t)s->max_batch, (size_t)s->max_batch * 110)) != 0) return rc;
+		if ((rc = out_grow(s, 24 * (size_t)s->max_batch + 4096)) != 0) return rc;
+	}
+	return 0;
+}
+
+static void *preload_main(void *arg)
+{
+	int rc;
+	(void)arg;
+	rc = create_handles();
+	pthread_mutex_lock(&g_mu);
+	g_pre_rc = rc; g_pre_state = 2;
+	pthread_cond_broadcast(&g_cv);
+	pthread_mutex_unlock(&g_mu);
+	return 0;
+}
+
+__attribute__((constructor)) static void adapter_preload(int argc, char **argv)
+{
+	const char *e = getenv("SMEM_GPU_ADAPTER_PRELOAD");
+	pthread_t th;
+	int i, is_mem = 0;
+	setenv("CUDA_MODULE_LOADING", "EAGER", 0);          /* load every kernel with the context, not at a worker's first launch */
+	for (i = 1; argv && i < argc && i < 3; ++i) if (argv[i] && strcmp(argv[i], "mem") == 0) is_mem = 1;
+	if (e ? atoi(e) == 0 : !is_mem) return;
+	g_pre_state = 1;
+	if (pthread_create(&th, 0, preload_main, 0) != 0) { g_pre_state = 0; return; }
+	pthread_detach(th);
+}
+
+static int service_start_inner(const harp_bwt_t *bwt);
+static int service_start_locked(const harp_bwt_t *bwt)
+{
+	int k;
+	const int rc = service_start_inner(bwt);
+	if (rc) {            /* leave nothing half-built behind, and do not try again on every call */
+		for (k = 0; k < MAX_HANDLES; ++k) if (g_hd[k].h) smem_gpu_destroy(g_hd[k].h);
+		memset(g_hd, 0, sizeof g_hd);
+		g_n_handles = 0; g_n_created = 0; g_start_failed = 1;
+	}
+	return rc;
+}
+
+static int service_start_inner(const harp_bwt_t *bwt)
+{
+	int rc, k;
+	smem_index_desc_t ix;
+	while (g_pre_state == 1) pthread_cond_wait(&g_cv, &g_mu);       /* the background part, if it is still at it (this releases g_mu: */
+	if (g_n_handles && g_bwt == bwt) return 0;                      /*  another worker may have brought the service up meanwhile) */
+	if (g_pre_state == 2 && g_pre_rc) return g_pre_rc;
+	if (g_n_created == 0 && (rc = create_handles()) != 0) return rc;
 	ix.primary = bwt->primary;
 	memcpy(ix.L2, bwt->L2, sizeof ix.L2);
 	ix.seq_len = bwt->seq_len;
 	ix.bwt_size = bwt->bwt_size;
 	ix.bwt = bwt->bwt;
-	for (k = 0; k < want; ++k) {            /* handle k lives on device k mod n_dev; one index copy per GPU */
+	for (k = 0; k < g_n_created; ++k) {     /* one index copy per GPU */
 		svc_handle_t *s = &g_hd[k];
 		int j;
-		s->dev = devs[k % n_dev]; s->max_batch = g_max_batch; s->max_len = g_init_len;
-		if ((rc = smem_gpu_create(&s->h, 1, &s->dev, s->max_batch, s->max_len)) != 0) return rc;
-		++g_n_handles;
 		for (j = 0; j < k; ++j) if (g_hd[j].dev == s->dev) break;
 		rc = j < k ? smem_gpu_share_index(s->h, g_hd[j].h) : smem_gpu_upload_index(s->h, &ix);
 		if (rc != 0) return rc;
-		smem_gpu_set_param(s->h, "turn_min_reads", 1ll << 40);   /* concurrent small launches: never serialise on the kernel turn */
 	}
+	for (k = 0; k < g_n_created; ++k) {     /* one tiny launch of each kind per handle: nothing is first-time for a worker */
+		svc_handle_t *s = &g_hd[k];
+		smem_seed_opt_t opt;
+		int64_t total = 0;
+		memset(s->seq, 0, 64); s->seq[1] = 1; s->seq[2] = 2; s->seq[3] = 3;
+		s->offs[0] = 0; s->offs[1] = 40; s->x[0] = 0; s->mi[0] = 1;
+		opt.min_seed_len = g_split_len; opt.split_factor = 1.0; opt.split_width = g_split_width; opt.start_width = 1;
+		if ((rc = smem_gpu_trace(s->h, 1, s->seq, s->offs, &opt, s->out, (int64_t)s->out_cap, s->roff, s->tag, s->ret16, &total)) != 0) return rc;
+		if ((rc = smem_gpu_smem1(s->h, 1, s->seq, s->offs, s->x, s->mi, s->out, (int64_t)s->out_cap, s->roff, s->ret, &total)) != 0) return rc;
+	}
+	g_n_handles = g_n_created;
 	if (g_bwt == 0 && getenv("SMEM_GPU_ADAPTER_STATS")) atexit(print_stats);
 	g_bwt = bwt;
 	return 0;
@@ -172,19 +237,20 @@ void harp_gpu_service_stop(void)
 {
 	int k;
 	pthread_mutex_lock(&g_mu);
-	for (k = 0; k < g_n_handles; ++k) {
+	while (g_pre_state == 1) pthread_cond_wait(&g_cv, &g_mu);
+	for (k = 0; k < MAX_HANDLES; ++k) {
 		svc_handle_t *s = &g_hd[k];
 		if (s->h) smem_gpu_destroy(s->h);
 		smem_gpu_host_free(s->seq); smem_gpu_host_free(s->offs); smem_gpu_host_free(s->roff); smem_gpu_host_free(s->x); smem_gpu_host_free(s->mi);
 		smem_gpu_host_free(s->ret); smem_gpu_host_free(s->out); smem_gpu_host_free(s->tag); smem_gpu_host_free(s->ret16);
 	}
 	memset(g_hd, 0, sizeof g_hd);
-	g_n_handles = 0; g_bwt = 0;
+	g_n_handles = 0; g_n_created = 0; g_bwt = 0;
 	pthread_mutex_unlock(&g_mu);
 }
 
 void harp_gpu_service_stats(uint64_t out[4]) { memcpy(out, g_stats, 4 * sizeof(uint64_t)); }
-void harp_gpu_service_stats8(uint64_t out[8]) { memcpy(out, g_stats, sizeof g_stats); }
+void harp_gpu_service_stats8(uint64_t out[8]) { memcpy(out, g_stats, 8 * sizeof(uint64_t)); }
 
 /* ---- pinned staging of a service handle ---------------------------------------------------------------------- */
 static int pin_grow(void **p, size_t *cap, size_t need, size_t elem)
@@ -235,6 +301,9 @@ static void lead(svc_handle_t *s, req_t *list)
 	int max_len = 0, rc = 0, n_req = 0;
 	int64_t total = 0;
 	const uint64_t t0 = now_ns();
+	uint64_t t_back, t_grown = 0, t_launched = 0, t1 = 0;
+	static int trace = -1;
+	if (trace < 0) trace = getenv("SMEM_GPU_ADAPTER_TRACE") != 0;
 	for (r = list; r; r = r->next) {
 		++n_req;
 		for (k = 0; k < r->n; ++k) { const int l = r->itr[r->idx[k]]->len; nbytes += (size_t)l; if (l > max_len) max_len = l; }
@@ -246,10 +315,15 @@ static void lead(svc_handle_t *s, req_t *list)
 		while (want_len < max_len) want_len = want_len * 2 > 65535 ? 65535 : want_len * 2;
 		while (want_batch < (int64_t)n) want_batch *= 2;
 		if (max_len > 65535) rc = SMEM_GPU_E_CAPACITY;
-		else if ((rc = smem_gpu_resize(s->h, want_batch, want_len)) == 0) { s->max_len = want_len; s->max_batch = want_batch; }
+		else if ((rc = smem_gpu_resize(s->h, want_batch, want_len)) == 0) { s->max_len = want_len; s->max_batch = want_batch; stat_add(11, 1); }
 	}
-	if (!rc) rc = stage_grow(s, n, nbytes);
-	if (!rc) rc = out_grow(s, 24 * n + 4096);
+	{
+		const size_t c0 = s->n_cap + s->seq_cap + s->out_cap;
+		if (!rc) rc = stage_grow(s, n, nbytes);
+		if (!rc) rc = out_grow(s, 24 * n + 4096);
+		if (s->n_cap + s->seq_cap + s->out_cap != c0) stat_add(11, 1);
+	}
+	t_grown = now_ns();
 	if (!rc) {
 		for (r = list, pos = 0, nbytes = 0; r; r = r->next)
 			for (k = 0; k < r->n; ++k, ++pos) {
@@ -260,6 +334,7 @@ static void lead(svc_handle_t *s, req_t *list)
 				if (list->kind == 0) { s->x[pos] = r->x[k]; s->mi[pos] = r->mi[k]; }
 			}
 		s->offs[n] = (int64_t)nbytes;
+		t1 = now_ns(); stat_add(8, t1 - t0);
 		for (;;) {
 			if (list->kind == 0)
 				rc = smem_gpu_smem1(s->h, (int64_t)n, s->seq, s->offs, s->x, s->mi, s->out, (int64_t)s->out_cap, s->roff, s->ret, &total);
@@ -269,11 +344,15 @@ static void lead(svc_handle_t *s, req_t *list)
 				rc = smem_gpu_trace(s->h, (int64_t)n, s->seq, s->offs, &opt, s->out, (int64_t)s->out_cap, s->roff, s->tag, s->ret16, &total);
 			}
 			if (rc == SMEM_GPU_E_CAPACITY && (size_t)total > s->out_cap) {   /* more intervals than guessed: size exactly and repeat */
+				stat_add(11, 1);
 				if ((rc = out_grow(s, (size_t)total)) == 0) continue;
 			}
 			break;
 		}
+		t_launched = now_ns();
+		stat_add(9, t_launched - t1);
 	}
+	t_back = now_ns();
 	if (rc) fail(list->kind ? "smem_gpu_trace" : "smem_gpu_smem1", rc, s->h);
 	/* hand the slices back */
 	for (r = list, pos = 0; r; r = r->next) {
@@ -295,7 +374,10 @@ static void lead(svc_handle_t *s, req_t *list)
 			for (k = 0; k <= r->n; ++k) r->roff[k] = 0;
 		pos += r->n;
 	}
-	stat_add(0, 1); stat_add(1, n); stat_add(2, (uint64_t)total); stat_add(4, (uint64_t)n_req); stat_add(5, now_ns() - t0);
+	stat_add(0, 1); stat_add(1, n); stat_add(2, (uint64_t)total); stat_add(4, (uint64_t)n_req); stat_add(5, now_ns() - t0); stat_add(10, now_ns() - t_back);
+	if (trace) fprintf(stderr, "[adapter trace] handle %d kind %d: %d requests, %zu reads, %lld intervals; grow %.2f gather %.2f launch %.2f hand-back %.2f ms\n", (int)(s - g_hd),
+	                   list->kind, n_req, n, (long long)total, (t_grown - t0) * 1e-6, t1 ? (t1 - t_grown) * 1e-6 : 0.0,
+	                   t_launched ? (t_launched - t1) * 1e-6 : 0.0, (now_ns() - t_back) * 1e-6);
 }
 
 /* post a request and wait for it; while waiting, lead launches whenever a service handle is free */
@@ -461,6 +543,7 @@ void bwt_smem1_batched(harp_smem_i **itr, int *ori_start, int *max_i, int start_
 				if (!done[i]) { rc = service_start_locked(itr[i]->bwt); break; }
 		pthread_mutex_unlock(&g_mu);
 		if (rc) fail("service start", rc, 0);
+		stat_add(7, now_ns() - t0);
 	}
 	tls_grow(batch_size);
 

@@ -41,6 +41,16 @@ def sum_over_ranks(value: int, device=None) -> int:
     return int(t.item())
 
 
+def gather_rows(values, device=None) -> "list[list[float]]":
+    """One row of floats per rank, on every rank (per-rank stage times of the end-to-end leg in bench.py)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [[float(v) for v in values]]
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device or "cpu")
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [[float(v) for v in o.tolist()] for o in out]
+
+
 def gather_results(local: dict, dst: int = 0):
     """Gather per-rank CSR results (intv [t,4] uint64, read_off [n+1], optional step) on ``dst`` in rank
     (= read) order.  Returns the merged dict on ``dst`` and None elsewhere."""

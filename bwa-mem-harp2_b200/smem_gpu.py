@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsmem_gpu.so")
+LIB_PATH = os.environ.get("SMEM_GPU_LIB") or os.path.join(HERE, "libsmem_gpu.so")   # (SMEM_GPU_LIB: kernel-variant builds, tools/variants.sh)
 
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_resize", "smem_gpu_upload_index", "smem_gpu_upload_index_device",

@@ -65,7 +65,7 @@ def build_reference() -> "str | None":
     if os.path.isdir(REF_SRC):
         subprocess.run(["make", "-s", "-C", HERE, "ref", "-j8"], check=True)
         if os.path.exists(os.path.join(HERE, "..", "bwa-mem-harp2_b200", "libsmem_gpu.so")):
-            subprocess.run(["make", "-s", "-C", HERE, "gpu", "harp", "-j8"], check=True)   # reference `bwa mem` + GPU adapter / + protocol shim
+            subprocess.run(["make", "-s", "-C", HERE, "gpu", "harp", "timed", "-j8"], check=True)   # reference `bwa mem` + GPU adapter / + protocol shim / timed CPU twin
     return so if os.path.exists(so) else None
 
 

@@ -698,53 +698,161 @@ static int chain_filter(const orc_chain_opt_t *o, int n_chn, const ochain_t *cha
 	return n_out;
 }
 
+/* The chains of a read live in the reference in a klib B-tree keyed by pos (bwamem.c:328-331: KBTREE_INIT(chn, mem_chain_t,
+ * chain_cmp); kb_init(chn, KB_DEFAULT_SIZE = 512) with 24-byte keys and 8-byte pointers gives t = ((512 - 4 - 8) / 32 + 1) >> 1
+ * = 8, i.e. at most 15 keys per node, kbtree.h:55-70).  For chains with EQUAL pos -- the same reference segment twice in a
+ * read, more than `w` apart -- which of them kb_intervalp returns as the lower bound, where kb_putp puts the next one and
+ * the order __kb_traverse leaves them in all depend on the shape of that tree (which node a key was split into), so the
+ * tree is restated here with the same node capacity, search, pre-emptive split and descent rules, over chain ids:
+ *   bt_find   <- __kb_getp_aux (kbtree.h:117-131): lower-bound search in one node; index of the FIRST key equal to pos if there
+ *                is one (*r = 0), else of the last smaller key (-1 if none)
+ *   bt_lower  <- kb_intervalp's `lower` (kbtree.h:151-169): an equal key ends the descent at once; otherwise the deepest
+ *                "last smaller key" seen on the way down
+ *   bt_put    <- kb_putp / __kb_putp_aux / __kb_split (kbtree.h:174-226): a full root is split first; on the way down a full
+ *                child is split before it is entered and the descent moves right only if pos is GREATER than the median
+ *                moved up; in a leaf the key goes right behind the slot bt_find names
+ *   bt_walk   <- __kb_traverse (kbtree.h:336-361): in order */
+#define BT_T 8
+#define BT_MAX (2 * BT_T - 1)
+typedef struct { int n, internal; int key[BT_MAX]; int ptr[BT_MAX + 1]; } btnode_t;
+typedef struct { btnode_t *nd; int n_nodes, cap, root; const ochain_t *ch; } btree_t;
+
+static int bt_new(btree_t *t, int internal)
+{
+	if (t->n_nodes == t->cap) { t->cap = t->cap ? t->cap << 1 : 8; t->nd = (btnode_t *)realloc(t->nd, sizeof(btnode_t) * (size_t)t->cap); }
+	memset(&t->nd[t->n_nodes], 0, sizeof(btnode_t));
+	t->nd[t->n_nodes].internal = internal;
+	return t->n_nodes++;
+}
+
+static int bt_find(const btree_t *t, const btnode_t *x, int64_t pos, int *r)
+{
+	int lo = 0, hi = x->n;
+	if (x->n == 0) return -1;
+	while (lo < hi) { const int mid = (lo + hi) >> 1; if (t->ch[x->key[mid]].pos < pos) lo = mid + 1; else hi = mid; }
+	if (lo == x->n) { *r = 1; return x->n - 1; }
+	*r = t->ch[x->key[lo]].pos == pos ? 0 : -1;
+	return *r < 0 ? lo - 1 : lo;
+}
+
+static int bt_lower(const btree_t *t, int64_t pos)        /* chain id or -1 */
+{
+	int x = t->root, lower = -1, r = 0;
+	for (;;) {
+		const btnode_t *nd = &t->nd[x];
+		const int i = bt_find(t, nd, pos, &r);
+		if (i >= 0 && r == 0) return nd->key[i];
+		if (i >= 0) lower = nd->key[i];
+		if (!nd->internal) return lower;
+		x = nd->ptr[i + 1];
+	}
+}
+
+static void bt_split(btree_t *t, int xi, int i, int yi)   /* child yi = ptr[i] of xi is full */
+{
+	const int zi = bt_new(t, t->nd[yi].internal);       /* (may move t->nd) */
+	btnode_t *x = &t->nd[xi], *y = &t->nd[yi], *z = &t->nd[zi];
+	z->n = BT_T - 1;
+	memcpy(z->key, y->key + BT_T, sizeof(int) * (BT_T - 1));
+	if (y->internal) memcpy(z->ptr, y->ptr + BT_T, sizeof(int) * BT_T);
+	y->n = BT_T - 1;
+	memmove(x->ptr + i + 2, x->ptr + i + 1, sizeof(int) * (size_t)(x->n - i));
+	x->ptr[i + 1] = zi;
+	memmove(x->key + i + 1, x->key + i, sizeof(int) * (size_t)(x->n - i));
+	x->key[i] = y->key[BT_T - 1];
+	++x->n;
+}
+
+static void bt_put(btree_t *t, int id)
+{
+	const int64_t pos = t->ch[id].pos;
+	int x = t->root, r = 0;
+	if (t->nd[x].n == BT_MAX) {
+		const int s = bt_new(t, 1);
+		t->nd[s].ptr[0] = x;
+		bt_split(t, s, 0, x);
+		t->root = x = s;
+	}
+	while (t->nd[x].internal) {
+		int i = bt_find(t, &t->nd[x], pos, &r) + 1;
+		if (t->nd[t->nd[x].ptr[i]].n == BT_MAX) {
+			bt_split(t, x, i, t->nd[x].ptr[i]);
+			if (pos > t->ch[t->nd[x].key[i]].pos) ++i;
+		}
+		x = t->nd[x].ptr[i];
+	}
+	{
+		btnode_t *nd = &t->nd[x];
+		const int i = bt_find(t, nd, pos, &r);
+		if (i != nd->n - 1) memmove(nd->key + i + 2, nd->key + i + 1, sizeof(int) * (size_t)(nd->n - i - 1));
+		nd->key[i + 1] = id;
+		++nd->n;
+	}
+}
+
+static int bt_walk(const btree_t *t, int x, int *out, int n)
+{
+	const btnode_t *nd = &t->nd[x];
+	int i;
+	for (i = 0; i <= nd->n; ++i) {
+		if (nd->internal) n = bt_walk(t, nd->ptr[i], out, n);
+		if (i < nd->n) out[n++] = nd->key[i];
+	}
+	return n;
+}
+
 /* mem_chain (bwamem.c:593-615) from the seed loop on (bwamem.c:478-496): per seed, the closest chain at or below its
  * reference position (kb_intervalp lower bound) absorbs it or a new chain keyed by rbeg is inserted; chains leave in
- * ascending pos (__kb_traverse).  The kbtree is restated as a sorted array; for EQUAL keys it follows what a kbtree
- * leaf does (__kb_getp_aux: the FIRST equal key is found; __kb_putp_aux inserts right after it).  Then, optionally,
- * mem_chain_flt.  Flat result as oracle/ref_harness.c:ref_chains. */
+ * the tree's order (__kb_traverse).  Then, optionally, mem_chain_flt.  Flat result as oracle/ref_harness.c:ref_chains. */
 int64_t orc_chains(int64_t n, const orc_seed_t *seeds, const int64_t *seed_off, int64_t l_pac, const orc_chain_opt_t *o, int do_flt,
                    int64_t *chain_off, int64_t *chain, int64_t chain_cap, orc_seed_t *out_seeds, int64_t seed_cap, int64_t *n_seeds_out)
 {
 	int64_t r, nc = 0, ns = 0;
-	ochain_t *ch = 0;
-	int *order = 0, cap = 0;
+	ochain_t *ch = 0, *sorted = 0;        /* ch: creation order (the tree's keys are indices into it); sorted: traversal order */
+	int *order = 0, *walk = 0, cap = 0;
+	btree_t t;
+	memset(&t, 0, sizeof t);
 	chain_off[0] = 0;
 	for (r = 0; r < n; ++r) {
 		int nch = 0, k, n_out;
 		int64_t e;
+		t.n_nodes = 0; t.root = bt_new(&t, 0);
 		for (e = seed_off[r]; e < seed_off[r + 1]; ++e) {
 			const orc_seed_t *s = &seeds[e];
-			int lo = 0, hi = nch, at;
+			int lower;
 			if (s->rbeg < l_pac && l_pac < s->rbeg + s->len) continue;      /* bridges the forward/reverse boundary, bwamem.c:478 */
-			while (lo < hi) { const int mid = (lo + hi) >> 1; if (ch[mid].pos < s->rbeg) lo = mid + 1; else hi = mid; }
-			at = lo;                                                        /* first chain with pos >= rbeg */
-			if (at < nch && ch[at].pos == s->rbeg) { if (chain_absorbs(o, l_pac, &ch[at], s)) continue; ++at; }
-			else if (at > 0 && chain_absorbs(o, l_pac, &ch[at - 1], s)) continue;
+			t.ch = ch;
+			lower = nch ? bt_lower(&t, s->rbeg) : -1;
+			if (lower >= 0 && chain_absorbs(o, l_pac, &ch[lower], s)) continue;
 			if (nch == cap) {
 				cap = cap ? cap << 1 : 16;
 				ch = (ochain_t *)realloc(ch, sizeof(ochain_t) * (size_t)cap);
+				sorted = (ochain_t *)realloc(sorted, sizeof(ochain_t) * (size_t)cap);
 				order = (int *)realloc(order, sizeof(int) * (size_t)cap);
+				walk = (int *)realloc(walk, sizeof(int) * (size_t)cap);
 			}
-			memmove(&ch[at + 1], &ch[at], sizeof(ochain_t) * (size_t)(nch - at));
-			ch[at].n = 1; ch[at].m = 4; ch[at].pos = s->rbeg;
-			ch[at].seeds = (orc_seed_t *)calloc(4, sizeof(orc_seed_t));
-			ch[at].seeds[0] = *s;
+			ch[nch].n = 1; ch[nch].m = 4; ch[nch].pos = s->rbeg;
+			ch[nch].seeds = (orc_seed_t *)calloc(4, sizeof(orc_seed_t));
+			ch[nch].seeds[0] = *s;
+			t.ch = ch;
+			bt_put(&t, nch);
 			++nch;
 		}
-		if (do_flt) n_out = chain_filter(o, nch, ch, order);
+		if (nch) { k = bt_walk(&t, t.root, walk, 0); (void)k; }
+		for (k = 0; k < nch; ++k) sorted[k] = ch[walk[k]];
+		if (do_flt) n_out = chain_filter(o, nch, sorted, order);
 		else for (n_out = 0; n_out < nch; ++n_out) order[n_out] = n_out;
 		for (k = 0; k < n_out; ++k) {
-			const ochain_t *c = &ch[order[k]];
-			int t;
+			const ochain_t *c = &sorted[order[k]];
+			int q;
 			if (nc < chain_cap) { chain[2 * nc] = c->pos; chain[2 * nc + 1] = c->n; }
 			++nc;
-			for (t = 0; t < c->n; ++t, ++ns) if (ns < seed_cap) out_seeds[ns] = c->seeds[t];
+			for (q = 0; q < c->n; ++q, ++ns) if (ns < seed_cap) out_seeds[ns] = c->seeds[q];
 		}
 		for (k = 0; k < nch; ++k) free(ch[k].seeds);
 		chain_off[r + 1] = nc;
 	}
-	free(ch); free(order);
+	free(ch); free(sorted); free(order); free(walk); free(t.nd);
 	*n_seeds_out = ns;
 	return nc;
 }

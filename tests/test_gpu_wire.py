@@ -91,6 +91,7 @@ def test_lanes_split_forms_and_conversions(world, synth):
     got = g2.collect_packed(pr)
     assert np.array_equal(got["intv"], want["intv"]) and np.array_equal(got["read_off"], want["read_off"])
     # 32-byte fetch of 16-byte resident results is refused, not converted silently
+    g2._n = pr.n
     with pytest.raises(sg.SmemGpuError):
         g2.fetch(len(want["intv"]))
     g2.close()

@@ -300,7 +300,7 @@ def test_gpu_text_index_and_unique_walk(fm, synth):
         isa = np.empty(n + 1, np.uint64); isa[fsa.astype(np.int64)] = np.arange(n + 1, dtype=np.uint64)   # inverse of the full table
         k = 1 << g.get_param("unique_walk_isa_shift")                     # samples: position n - e * k for e = 0, 1, ...
         assert len(isa_s) == n // k + 1 and np.array_equal(isa_s, isa[n - k * np.arange(n // k + 1)])
-        assert g.get_param("uw_table_bytes") < 5.5 * n + 4096             # 0.5 + 4.57 + 4.57 / 4 bytes per text position
+        assert g.get_param("uw_table_bytes") < (0.5 + 4.58 * (1 + 1 / k)) * n + 8192   # text nibbles + 33-bit SA + sampled 33-bit inverse (6.2 bytes per position at k = 4)
         g.build_repeat_filter(ref, 13, 0)
         r = ref.numpy()
         T = np.concatenate([r, (3 - r)[::-1]])

@@ -31,6 +31,7 @@ def _worker(rank, world, port, tmp):
     t = sh.max_over_ranks(1.0 + rank)
     n = sh.sum_over_ranks(hi - lo)
     assert t == float(world) and n == 1001
+    assert sh.gather_rows([rank, 2.5]) == [[0.0, 2.5], [1.0, 2.5]]
     if rank == 0:
         full = Oracle(ix).collect(seq, offs, SeedOpt())
         assert all(np.array_equal(merged[k], full[k]) for k in ("intv", "read_off", "step"))
