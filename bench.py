@@ -729,12 +729,17 @@ def main():
             for chains in (512, 1024, 2048):
                 probe[f"{bb}B_x{chains}"] = round(g.gather_roofline(bb, 0, chains, 1000), 1)
         log("random-access probe GB/s:", probe)
-    rand64 = rand64_split = None
+    rand64 = rand64_split = rand64_bulk = None
     if rank == 0:
         # the roofline of the access pattern: dependent 64 B gathers over the whole index, one coalesced request
         # per block (lane pair, 2 x 32 B) -- and, for reference, the same gathers issued as two per-lane requests
         g.set_param("probe_variant", 10); rand64 = g.gather_roofline(64, 0, 2048, 1000)
         g.set_param("probe_variant", 0); rand64_split = g.gather_roofline(64, 0, 2048, 1000)
+        try:      # the same gathers through the bulk-copy engine: one cp.async.bulk of 64 B per lane into shared memory behind an mbarrier
+            g.set_param("probe_variant", 20); rand64_bulk = g.gather_roofline(64, 0, 2048, 1000)
+        except Exception as e:  # noqa: BLE001
+            rand64_bulk = None; log("bulk-copy probe failed:", e)
+        g.set_param("probe_variant", 0)
 
     # ---- max over ranks
     dt, seed_avg_ms = max_over_ranks(dt), max_over_ranks(float(np.mean(seed_ms)))
@@ -790,7 +795,7 @@ def main():
                          "kernel_ms": seed_avg_ms, "algorithmic_bytes_per_read": bytes_per_read, "executed": executed,
                          "request_rate": request_rate,
                          "random_access_peak": rand64, "frac_of_random_access": achieved / rand64 if rand64 else None,
-                         "random_access_peak_two_requests": rand64_split,
+                         "random_access_peak_two_requests": rand64_split, "random_access_bulk_copy_64B_per_lane": rand64_bulk,
                          "random_access_note": "dependent 64 B gathers over the whole index (smem_gpu_gather_roofline): one coalesced "
                                                "request per block by a lane pair; L2 hits on hot blocks let the kernel exceed it"},
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,

@@ -136,6 +136,7 @@ struct smem_gpu {
 	int chain_lanes = 0;             // 1: lane k's seed kernel waits for lane k-1's (no tail overlap)
 	int64_t turn_min_reads = 16384;  // calls with fewer reads per lane do not take the GPU's kernel turn: their few CTAs run next to other calls' kernels
 	bool use_turn = true;
+	bool stage_wait = true;          // ctx_stage_inner waits for its H2D copies (always in the split form)
 	int64_t h2d_bytes = 0, d2h_bytes = 0;
 	uint64_t epoch = 0;              // bumped per run; orders the lanes' seed kernels
 	uint64_t stage_epoch = 0;        // bumped per staging; orders the lanes' H2D copies
@@ -209,7 +210,7 @@ int ctx_alloc_batch(DeviceCtx &d, int64_t read_cap, int max_len, int slot_cap)
 	if ((rc = dev_alloc(d, &d.d_aux, d.out_cap))) return rc;
 	// per-pair scratch for the default launch geometry (re-grown in ctx_run if blocks_per_sm is raised): allocating
 	// it lazily would delay the first lane's first kernel by a cudaMalloc
-	d.scratch_entries = (size_t)d.sm_count * 9 * 64 * 3 * (size_t)(max_len + 2);
+	d.scratch_entries = (size_t)std::min<int64_t>((int64_t)d.sm_count * 9, (read_cap + 63) / 64 + 1) * 64 * 3 * (size_t)(max_len + 2);   // (a batch never needs more CTAs than it has groups of 64 reads)
 	CK(cudaMalloc((void **)&d.d_scratch, d.scratch_entries * sizeof(Intv)));
 	// block sums of the counts -> offsets scan
 	d.tmp_bytes = ((size_t)(read_cap + 1) / SCAN_PER_BLOCK + 2) * sizeof(long long);
@@ -496,7 +497,10 @@ int ctx_stage_inner(DeviceCtx &d, const BatchIn &in)
 		}
 	}
 	{ std::lock_guard<std::mutex> lk(d.owner->lane_mu); d.stage_issued = d.owner->stage_epoch; d.owner->lane_cv.notify_all(); }
-	CK(stream_wait(d));
+	// Small one-call batches (no kernel turn to hold, see do_collect) leave the copies queued: the kernels follow on the same
+	// stream and the caller's buffers stay valid until the call returns, so the host round trip is saved.  Otherwise the reads
+	// are on the device before the call asks for the GPU's kernel turn (it must not hold the turn while its copy is in flight).
+	if (d.owner->stage_wait) CK(stream_wait(d));
 	return 0;
 }
 
@@ -636,7 +640,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const int pairs_per_cta = SEED_BLOCK / 2;
 	const int grid = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * bps, (d.n + pairs_per_cta - 1) / pairs_per_cta);
 	const int scratch_cap = h.max_len + 2;
-	const size_t need = (size_t)max_grid * pairs_per_cta * 3 * scratch_cap;
+	const size_t need = (size_t)std::min<int64_t>(max_grid, (d.read_cap + pairs_per_cta - 1) / pairs_per_cta + 1) * pairs_per_cta * 3 * scratch_cap;
 	// 16-byte packed prev/curr entries need every SA coordinate < 2^36 and read positions < 2^20
 	// ... and the 32-bit occurrence counts of the narrow extend need every base to occur fewer than 2^32 times
 	bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
@@ -747,57 +751,11 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
 	const auto tt0 = std::chrono::steady_clock::now();
 	auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
-	CK(cudaMemcpyAsync(d.h_status, d.d_status, 8 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-	CK(stream_wait(d));
-	const double t_status = tms();
-	if (d.h_status[5] & 1) { d.err = "a read is longer than max_read_len (or offs is not monotone / a length exceeds the record stride)"; return SMEM_GPU_E_CAPACITY; }
-	if (d.h_status[5] & 2) { d.err = "an ambiguous-base entry names a read outside its shard (is the list sorted by read?)"; return SMEM_GPU_E_ARG; }
-	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
-	const int n_over = d.h_status[1];
-	d.overflow = n_over;
-	d.pass2_skipped = d.h_status[6]; d.uw_walks = d.h_status[7];
-	int big_cap = 0;
-	if (n_over > 0) {
-		// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
-		std::vector<int> list(n_over);
-		CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
-		CK(stream_wait(d));
-		std::sort(list.begin(), list.end());       // deterministic re-run order
-		if ((size_t)n_over > d.counts_k_cap) {
-			if (d.d_counts_k) CK(cudaFree(d.d_counts_k));
-			d.d_counts_k = nullptr; d.counts_k_cap = 0;
-			CK(cudaMalloc((void **)&d.d_counts_k, (size_t)n_over * 2 * 4));       // counts + this pass' overflow list
-			d.counts_k_cap = n_over;
-		}
-		CK(cudaMemcpyAsync(d.d_overflow, list.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, d.stream));
-		big_cap = d.h_status[3];
-		for (int round = 0; round < 3; ++round) {
-			const size_t need_big = (size_t)n_over * big_cap;
-			if (need_big > d.big_entries) {
-				if (d.d_big) CK(cudaFree(d.d_big));
-				d.d_big = nullptr; d.big_entries = 0;
-				CK(cudaMalloc((void **)&d.d_big, need_big * sizeof(Intv)));
-				d.big_entries = need_big;
-			}
-			CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
-			SeedParams p2 = p;
-			p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
-			p2.overflow_list = d.d_counts_k + n_over;
-			const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
-			rc = launch_seed_mode(d, mode, p2, bps, grid2, smem, wide);
-			if (rc) return rc;
-			CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-			CK(stream_wait(d));
-			if (d.h_status[2] != 0) { d.err = "device guard tripped in the overflow re-run"; return SMEM_GPU_E_INTERNAL; }
-			if (d.h_status[1] == 0) break;
-			if (round == 2) { d.err = "overflow re-run did not converge"; return SMEM_GPU_E_INTERNAL; }
-			big_cap = d.h_status[3];               // exact now: nothing was abandoned with B in global memory
-		}
-		scatter_counts_kernel<<<(n_over + 255) / 256, 256, 0, d.stream>>>(d.d_counts_k, d.d_overflow, n_over, d.d_counts);
-		CK(cudaGetLastError());
-		++d.launches;
-	}
-	{
+	// The common case needs ONE host round trip: counts -> offsets (scan), slots -> dense output (compaction) and the copies
+	// of the status words and of the total are all queued behind the seed kernel, then the host waits once.  Only a run with
+	// reads that outgrew their slots, or with more intervals than the output buffers hold, takes the second leg below -- the
+	// offsets come from the exact counts either way, so the entries already placed stay where they are.
+	auto queue_scan = [&]() -> int {
 		const long long n1 = d.n + 1;                  // counts[n] = 0, so off[n] = total
 		const int nb = (int)((n1 + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
 		long long *bsum = (long long *)d.d_tmp;
@@ -806,49 +764,105 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		scan_add_kernel<<<(unsigned)((n1 + SCAN_TPB - 1) / SCAN_TPB), SCAN_TPB, 0, d.stream>>>(d.d_off, n1, bsum);
 		CK(cudaGetLastError());
 		d.launches += 3;
-	}
-	CK(cudaMemcpyAsync(d.h_status + 6, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
-	CK(stream_wait(d));
-	const double t_scan = tms();
-	memcpy(&d.total, d.h_status + 6, 8);
-	if ((size_t)d.total > d.out_cap) {
-		CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); CK(cudaFree(d.d_aux)); d.d_out = nullptr; d.d_step = nullptr; d.d_aux = nullptr;
-		d.out_cap = (size_t)d.total + (size_t)d.total / 8 + 1024;
-		CK(cudaMalloc((void **)&d.d_out, d.out_cap * sizeof(Intv)));
-		CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
-		CK(cudaMalloc((void **)&d.d_aux, d.out_cap * sizeof(unsigned short)));
-		if (packed_out) { const int rc0 = ensure_packed_out(d); if (rc0) return rc0; }
-	}
-	if (packed_out && (unsigned long long)d.total >= (1ull << 32)) { d.err = "more than 2^32 intervals in one shard: use the 32-byte form"; return SMEM_GPU_E_CAPACITY; }
-	{
+		return 0;
+	};
+	auto queue_compact = [&]() -> int {
 		const long long threads = (long long)d.n * 8;
 		if (packed_out)
 			compact_packed_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
-			                                                                               d.d_outp, d.d_off32);
+			                                                                               d.d_outp, d.d_off32, (long long)d.out_cap);
 		else
 			compact_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
-			                                                                        d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
+			                                                                        d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr, (long long)d.out_cap);
 		CK(cudaGetLastError());
 		++d.launches;
-	}
-	if (n_over > 0) {
-		const long long threads = (long long)n_over * big_cap;
-		if (packed_out)
-			compact_list_packed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
-			                                                                                    d.d_off, d.d_outp);
-		else
-			compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
-			                                                                             d.d_off, d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
-		CK(cudaGetLastError());
-		++d.launches;
-	}
+		return 0;
+	};
+	if ((rc = queue_scan())) return rc;
+	if ((rc = queue_compact())) return rc;
+	CK(cudaMemcpyAsync(d.h_status, d.d_status, 8 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+	CK(cudaMemcpyAsync(d.h_status + 8, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaEventRecord(d.ev2, d.stream));
+	CK(stream_wait(d));
+	const double t_first = tms();
+	if (d.h_status[5] & 1) { d.err = "a read is longer than max_read_len (or offs is not monotone / a length exceeds the record stride)"; return SMEM_GPU_E_CAPACITY; }
+	if (d.h_status[5] & 2) { d.err = "an ambiguous-base entry names a read outside its shard (is the list sorted by read?)"; return SMEM_GPU_E_ARG; }
+	if (d.h_status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
+	const int n_over = d.h_status[1];
+	d.overflow = n_over;
+	d.pass2_skipped = d.h_status[6]; d.uw_walks = d.h_status[7];
+	memcpy(&d.total, d.h_status + 8, 8);
+	const bool regrow = (size_t)d.total > d.out_cap;
+	if (packed_out && (unsigned long long)d.total >= (1ull << 32)) { d.err = "more than 2^32 intervals in one shard: use the 32-byte form"; return SMEM_GPU_E_CAPACITY; }
+	if (n_over > 0 || regrow) {
+		int big_cap = 0;
+		if (n_over > 0) {
+			// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
+			std::vector<int> list(n_over);
+			CK(cudaMemcpyAsync(list.data(), d.d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, d.stream));
+			CK(stream_wait(d));
+			std::sort(list.begin(), list.end());       // deterministic re-run order
+			if ((size_t)n_over > d.counts_k_cap) {
+				if (d.d_counts_k) CK(cudaFree(d.d_counts_k));
+				d.d_counts_k = nullptr; d.counts_k_cap = 0;
+				CK(cudaMalloc((void **)&d.d_counts_k, (size_t)n_over * 2 * 4));       // counts + this pass' overflow list
+				d.counts_k_cap = n_over;
+			}
+			CK(cudaMemcpyAsync(d.d_overflow, list.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, d.stream));
+			big_cap = d.h_status[3];
+			for (int round = 0; round < 3; ++round) {
+				const size_t need_big = (size_t)n_over * big_cap;
+				if (need_big > d.big_entries) {
+					if (d.d_big) CK(cudaFree(d.d_big));
+					d.d_big = nullptr; d.big_entries = 0;
+					CK(cudaMalloc((void **)&d.d_big, need_big * sizeof(Intv)));
+					d.big_entries = need_big;
+				}
+				CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+				SeedParams p2 = p;
+				p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
+				p2.overflow_list = d.d_counts_k + n_over;
+				const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
+				rc = launch_seed_mode(d, mode, p2, bps, grid2, smem, wide);
+				if (rc) return rc;
+				CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+				CK(stream_wait(d));
+				if (d.h_status[2] != 0) { d.err = "device guard tripped in the overflow re-run"; return SMEM_GPU_E_INTERNAL; }
+				if (d.h_status[1] == 0) break;
+				if (round == 2) { d.err = "overflow re-run did not converge"; return SMEM_GPU_E_INTERNAL; }
+				big_cap = d.h_status[3];               // exact now: nothing was abandoned with B in global memory
+			}
+			// (the re-run reproduces the counts the first pass measured: the offsets already computed stay valid)
+		}
+		if (regrow) {
+			CK(cudaFree(d.d_out)); CK(cudaFree(d.d_step)); CK(cudaFree(d.d_aux)); d.d_out = nullptr; d.d_step = nullptr; d.d_aux = nullptr;
+			d.out_cap = (size_t)d.total + (size_t)d.total / 8 + 1024;
+			CK(cudaMalloc((void **)&d.d_out, d.out_cap * sizeof(Intv)));
+			CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
+			CK(cudaMalloc((void **)&d.d_aux, d.out_cap * sizeof(unsigned short)));
+			if (packed_out) { const int rc0 = ensure_packed_out(d); if (rc0) return rc0; }
+			if ((rc = queue_compact())) return rc;       // the first compaction stopped at the old capacity
+		}
+		if (n_over > 0) {
+			const long long threads = (long long)n_over * big_cap;
+			if (packed_out)
+				compact_list_packed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
+				                                                                                    d.d_off, d.d_outp);
+			else
+				compact_list_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
+				                                                                             d.d_off, d.d_out, d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr);
+			CK(cudaGetLastError());
+			++d.launches;
+		}
+		CK(cudaEventRecord(d.ev2, d.stream));
+		turn_release(d);
+		CK(stream_wait(d));
+	}
 	// the scan / compaction kernels are queued ahead of whatever the next call launches: a persistent seed kernel that got
 	// there first would hold every SM and they would wait for it to drain
 	turn_release(d);
-	CK(stream_wait(d));
 	(packed_out ? d.outp_valid : d.out_valid) = true;
-	if (trace) fprintf(stderr, "[smem_gpu trace]   lane %d run: status +%.2f scan +%.2f compact +%.2f ms after the seed launch\n", d.lane, t_status, t_scan, tms());
+	if (trace) fprintf(stderr, "[smem_gpu trace]   lane %d run: first round trip +%.2f, done +%.2f ms after the seed launch (%d overflow reads%s)\n", d.lane, t_first, tms(), n_over, regrow ? ", output buffers regrown" : "");
 	CK(cudaEventElapsedTime(&d.seed_ms, d.ev0s, d.ev1));
 	CK(cudaEventElapsedTime(&d.total_ms, d.ev0, d.ev2));
 	return 0;
@@ -940,6 +954,7 @@ int do_stage(smem_gpu *h, int64_t n, const BatchIn &in)
 	if (rc) return rc;
 	shard(h, n);
 	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->stage_epoch; }
+	h->stage_wait = true;
 	rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_stage(d, *h, in); });
 	if (rc) return rc;
 	h->staged = n; h->ran = false;
@@ -1021,6 +1036,7 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_s
 	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; ++h->stage_epoch; }
 	const size_t G = h->devs.size();
 	h->use_turn = n >= h->turn_min_reads * (int64_t)G;
+	h->stage_wait = h->use_turn;
 	std::vector<long long> totals(G, 0);
 	std::vector<char> ran(G, 0);
 	std::mutex mu;
@@ -1722,7 +1738,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "unique_walk_isa_shift")) { if (v < 0 || v > 6) return SMEM_GPU_E_ARG; h->uw_isa_shift = (int)v; return 0; }
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
 	if (!strcmp(name, "acc_reset")) { for (auto &d : h->devs) { d.acc_stage_ms = d.acc_turn_ms = d.acc_run_ms = d.acc_fetch_ms = 0; d.acc_calls = d.acc_h2d = d.acc_d2h = 0; } return 0; }
-	if (!strcmp(name, "probe_variant")) { if (v < 0 || v > 15) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
+	if (!strcmp(name, "probe_variant")) { if (v < 0 || (v > 15 && v != 20)) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
 	if (!strcmp(name, "l2_fetch_granularity")) {   // device-wide hint, cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes)
 		if (v != 32 && v != 64 && v != 128) return SMEM_GPU_E_ARG;
 		for (auto &d : h->devs) { cudaSetDevice(d.dev); if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) != cudaSuccess) return SMEM_GPU_E_CUDA; }
@@ -1800,6 +1816,7 @@ int smem_gpu_gather_roofline(smem_gpu_t *h, int block_bytes, uint64_t span_bytes
 			case 13: COOP(8, 16); break;    // 128 B units
 			case 14: COOP(2, 16); break;    // 32 B units
 			case 15: COOP(8, 32); break;    // 256 B units
+			case 20: gather_probe_bulk_kernel<<<grid, 256, 0, d.stream>>>(d.d_index, span_bytes / 64, steps, sink); break;   // 64 B per lane by cp.async.bulk + mbarrier
 			case 1: PROBE_B(1); break;
 			case 2: PROBE_B(2); break;
 			case 3: PROBE_B(3); break;
@@ -1816,7 +1833,7 @@ int smem_gpu_gather_roofline(smem_gpu_t *h, int block_bytes, uint64_t span_bytes
 		float ms = 0;
 		CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
 		double per_thread = block_bytes;
-		switch (h->probe_variant) { case 10: case 12: case 15: per_thread = 32; break; case 11: case 13: case 14: per_thread = 16; break; default: break; }
+		switch (h->probe_variant) { case 10: case 12: case 15: per_thread = 32; break; case 11: case 13: case 14: per_thread = 16; break; case 20: per_thread = 64; break; default: break; }
 		*gbps_out = (double)grid * 256.0 * steps * per_thread / (ms * 1e-3) / 1e9;
 		return 0;
 	};

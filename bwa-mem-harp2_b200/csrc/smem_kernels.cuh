@@ -603,13 +603,6 @@ __global__ void __launch_bounds__(256) window_flags_kernel(const uint4 *__restri
 	qflags[t] = flags;
 }
 
-// counts of the re-run (list order) -> counts[read id]
-__global__ void scatter_counts_kernel(const int *__restrict__ counts_k, const int *__restrict__ list, int n_list, int *__restrict__ counts)
-{
-	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k < n_list) counts[list[k]] = counts_k[k];
-}
-
 // Upload-time re-pack of bwt_t::bwt (bwtindex.c:128-150: per 128 symbols 4 x uint64 checkpoints + 8 words of
 // 16 two-bit symbols, first symbol in the top bits; last block truncated) into the split bit-plane block
 // described in smem_device.cuh.  One thread per block.
@@ -707,13 +700,14 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_add_kernel(long long *__restric
 // Eight lanes per read, each copying entries lane, lane+8, ... (most reads have <= 16 intervals).
 __global__ void __launch_bounds__(128) compact_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
                                                       const long long *__restrict__ off, long long n, Intv *__restrict__ out,
-                                                      unsigned short *__restrict__ step_out, unsigned short *__restrict__ aux_out)
+                                                      unsigned short *__restrict__ step_out, unsigned short *__restrict__ aux_out, long long out_cap)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long r = t >> 3;
 	if (r >= n) return;
-	const int c = min(counts[r], slot_cap);      // entries beyond slot_cap are filled in by the overflow re-run
 	const long long o0 = off[r];
+	// entries beyond slot_cap are filled in by the overflow re-run; entries beyond the buffer wait for the host to re-size it
+	const int c = (int)min((long long)min(counts[r], slot_cap), max(out_cap - o0, 0ll));
 	for (int e = (int)(t & 7); e < c; e += 8) {
 		const Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
 		st_intv(&out[o0 + e], v.x0, v.x1, v.x2, v.info & INFO_MASK);
@@ -735,13 +729,13 @@ __device__ __forceinline__ uint4 pack_intv16(const Intv &v)
 // Compaction into the compact wire format: slots -> dense 16-byte records + 32-bit CSR offsets (off32[n] = total).
 __global__ void __launch_bounds__(128) compact_packed_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
                                                              const long long *__restrict__ off, long long n, uint4 *__restrict__ out,
-                                                             u32 *__restrict__ off32)
+                                                             u32 *__restrict__ off32, long long out_cap)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long r = t >> 3;
 	if (r >= n) return;
-	const int c = min(counts[r], slot_cap);      // entries beyond slot_cap are filled in by the overflow re-run
 	const long long o0 = off[r];
+	const int c = (int)min((long long)min(counts[r], slot_cap), max(out_cap - o0, 0ll));      // (see compact_kernel)
 	if ((t & 7) == 0) { off32[r] = (u32)o0; if (r == n - 1) off32[n] = (u32)off[n]; }
 	for (int e = (int)(t & 7); e < c; e += 8) {
 		Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
@@ -1054,6 +1048,46 @@ __global__ void __launch_bounds__(256) gather_probe_coop_kernel(const uint4 *__r
 		for (int m = 1; m < LANES; m <<= 1) f ^= __shfl_xor_sync(0xffffffffu, f, m);
 		acc += f;
 		s += f;
+	}
+	if (acc == 0x7fffffffffffffffull) *sink = acc;
+}
+
+// Bulk-copy flavour of the probe ("TMA ... behind an mbarrier"): every lane fetches its 64-byte unit with
+// ONE cp.async.bulk (global -> shared, completion on the warp's mbarrier) instead of LDG, then reads it back from shared
+// memory.  Answers two questions for the seed kernel: does the copy engine path sustain more DRAM-missing requests than
+// 38 G/s, and does a 64-byte unit fetched by a single lane cost one request (a lane pair's LDG.256) or two (a lane's 2 x 32 B)?
+__global__ void __launch_bounds__(256) gather_probe_bulk_kernel(const uint4 *__restrict__ base, u64 n_units, int steps, u64 *sink)
+{
+	__shared__ __align__(128) uint4 buf[256 * 4];                  // 64 bytes per thread
+	__shared__ __align__(8) unsigned long long bar[8];             // one mbarrier per warp
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 bar_a = (u32)__cvta_generic_to_shared(&bar[warp]);
+	const u32 slot_a = (u32)__cvta_generic_to_shared(&buf[threadIdx.x * 4]);
+	if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncwarp();
+	u64 s = (u64)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+	u64 acc = 0;
+	u32 phase = 0;
+	for (int it = 0; it < steps; ++it) {
+		s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
+		const u64 u = __umul64hi(s, n_units);
+		const uint4 *ptr = base + u * 4;
+		if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(32u * 64u) : "memory");
+		__syncwarp();
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];"
+		             :: "r"(slot_a), "l"(ptr), "r"(bar_a) : "memory");
+		u32 done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			             : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+		}
+		phase ^= 1;
+		const uint4 a = buf[threadIdx.x * 4], b = buf[threadIdx.x * 4 + 1], c = buf[threadIdx.x * 4 + 2], d = buf[threadIdx.x * 4 + 3];
+		const u32 f = a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+		acc += f;
+		s += f;
+		__syncwarp();                                               // every lane has read its slot before the next round overwrites it
 	}
 	if (acc == 0x7fffffffffffffffull) *sink = acc;
 }

@@ -69,7 +69,7 @@ static int g_n_handles = 0;      /* handles in service (index uploaded) */
 static int g_n_created = 0;      /* handles created (by the preload thread or the first call) */
 static req_t *g_head = 0, *g_tail = 0;
 static const harp_bwt_t *g_bwt = 0;
-static int64_t g_max_batch = 1 << 15;
+static int64_t g_max_batch = 4096;
 static int g_init_len = 160;
 static int g_last_rc = 0, g_abort_on_error = 0, g_reported = 0, g_start_failed = 0;
 static char g_last_err[512];
@@ -119,11 +119,13 @@ static int out_grow(svc_handle_t *s, size_t need);
 static int g_pre_state = 0;       /* 0 = not started, 1 = running, 2 = done */
 static int g_pre_rc = 0;
 
+#define FIRST_BATCH 4096          /* reads per launch the handles are created for; re-sized from the first batch the reference sends */
+
 static int create_handles(void)
 {
-	int devs[64], n_dev = 0, rc, k, want = 8;
+	int devs[64], n_dev = 0, rc, k, want = MAX_HANDLES;
 	const char *e;
-	if ((e = getenv("SMEM_GPU_MAX_BATCH")) != 0) g_max_batch = atoll(e);
+	g_max_batch = FIRST_BATCH;
 	if ((e = getenv("SMEM_GPU_MAX_READ_LEN")) != 0) g_init_len = atoi(e);       /* first size only: handles grow on demand */
 	if ((e = getenv("SMEM_GPU_ADAPTER_HANDLES")) != 0) want = atoi(e);
 	if ((e = getenv("SMEM_GPU_ADAPTER_ABORT")) != 0) g_abort_on_error = atoi(e) != 0;
@@ -175,11 +177,11 @@ __attribute__((constructor)) static void adapter_preload(int argc, char **argv)
 	pthread_detach(th);
 }
 
-static int service_start_inner(const harp_bwt_t *bwt);
-static int service_start_locked(const harp_bwt_t *bwt)
+static int service_start_inner(const harp_bwt_t *bwt, int first_batch);
+static int service_start_locked(const harp_bwt_t *bwt, int first_batch)
 {
 	int k;
-	const int rc = service_start_inner(bwt);
+	const int rc = service_start_inner(bwt, first_batch);
 	if (rc) {            /* leave nothing half-built behind, and do not try again on every call */
 		for (k = 0; k < MAX_HANDLES; ++k) if (g_hd[k].h) smem_gpu_destroy(g_hd[k].h);
 		memset(g_hd, 0, sizeof g_hd);
@@ -188,7 +190,7 @@ static int service_start_locked(const harp_bwt_t *bwt)
 	return rc;
 }
 
-static int service_start_inner(const harp_bwt_t *bwt)
+static int service_start_inner(const harp_bwt_t *bwt, int first_batch)
 {
 	int rc, k;
 	smem_index_desc_t ix;
@@ -201,6 +203,38 @@ static int service_start_inner(const harp_bwt_t *bwt)
 	ix.seq_len = bwt->seq_len;
 	ix.bwt_size = bwt->bwt_size;
 	ix.bwt = bwt->bwt;
+	{
+		/* How many launches in flight, and how many reads each can carry, follows from the batch size the reference calls with
+		 * (-b, seen here for the first time): tiny batches are latency-bound -- one handle per worker thread keeps every worker's
+		 * wait at one launch latency; large batches fill the GPU by themselves -- a few handles with room to combine four
+		 * requests.  SMEM_GPU_ADAPTER_HANDLES / SMEM_GPU_MAX_BATCH override. */
+		const char *eh = getenv("SMEM_GPU_ADAPTER_HANDLES"), *eb = getenv("SMEM_GPU_MAX_BATCH");
+		int use = first_batch <= 256 ? 16 : first_batch <= 2048 ? 8 : 4;
+		int64_t per = first_batch <= 1024 ? FIRST_BATCH : 4ll * first_batch;
+		if (per > 65536) per = first_batch > 65536 ? first_batch : 65536;
+		if (eb) per = atoll(eb);
+		if (per < first_batch) per = first_batch;
+		if (eh) use = atoi(eh);
+		if (use > g_n_created) use = g_n_created;
+		if (use < 1) use = 1;
+		for (k = use; k < g_n_created; ++k) {          /* surplus handles go (they were cheap: small buffers) */
+			svc_handle_t *s = &g_hd[k];
+			smem_gpu_destroy(s->h);
+			smem_gpu_host_free(s->seq); smem_gpu_host_free(s->offs); smem_gpu_host_free(s->roff); smem_gpu_host_free(s->x); smem_gpu_host_free(s->mi);
+			smem_gpu_host_free(s->ret); smem_gpu_host_free(s->out); smem_gpu_host_free(s->tag); smem_gpu_host_free(s->ret16);
+			memset(s, 0, sizeof *s);
+		}
+		g_n_created = use;
+		g_max_batch = per;
+		if (per > FIRST_BATCH)
+			for (k = 0; k < g_n_created; ++k) {
+				svc_handle_t *s = &g_hd[k];
+				if ((rc = smem_gpu_resize(s->h, per, s->max_len)) != 0) return rc;
+				s->max_batch = per;
+				if ((rc = stage_grow(s, (size_t)per, (size_t)per * 110)) != 0) return rc;
+				if ((rc = out_grow(s, 24 * (size_t)per + 4096)) != 0) return rc;
+			}
+	}
 	for (k = 0; k < g_n_created; ++k) {     /* one index copy per GPU */
 		svc_handle_t *s = &g_hd[k];
 		int j;
@@ -228,7 +262,7 @@ int harp_gpu_service_start(const harp_bwt_t *bwt)
 {
 	int rc;
 	pthread_mutex_lock(&g_mu);
-	rc = service_start_locked(bwt);
+	rc = service_start_locked(bwt, 65536);
 	pthread_mutex_unlock(&g_mu);
 	return rc;
 }
@@ -540,7 +574,7 @@ void bwt_smem1_batched(harp_smem_i **itr, int *ori_start, int *max_i, int start_
 		}
 		if (!g_start_failed)
 			for (i = 0; i < batch_size; ++i)
-				if (!done[i]) { rc = service_start_locked(itr[i]->bwt); break; }
+				if (!done[i]) { rc = service_start_locked(itr[i]->bwt, batch_size); break; }
 		pthread_mutex_unlock(&g_mu);
 		if (rc) fail("service start", rc, 0);
 		stat_add(7, now_ns() - t0);

@@ -73,9 +73,9 @@ enum {
 int smem_gpu_create(smem_gpu_t **out, int n_devices, const int *device_ids, int64_t max_batch_reads, int max_read_len);
 int smem_gpu_destroy(smem_gpu_t *h);
 /* Device memory of a handle grows with both limits: per lane read_cap * (max_read_len + ~2.6 KB) bytes of batch buffers plus
- * sm_count * 9 * 64 * 3 * (max_read_len + 2) * 32 bytes of list scratch (0.85 GB at 101 bp, 2.1 GB at 250 bp, 8.4 GB at
- * 1024 bp; max_read_len <= 65535 is accepted, but beyond a few thousand bases the scratch alone exhausts HBM and create /
- * resize return SMEM_GPU_E_NOMEM).  smem_gpu_resize re-sizes the batch buffers in place -- index, samples and accelerator
+ * min(sm_count * 9, max_batch_reads / 64 + 1) * 64 * 3 * (max_read_len + 2) * 32 bytes of list scratch (for batches that
+ * fill the GPU: 0.85 GB at 101 bp, 2.1 GB at 250 bp, 8.4 GB at 1024 bp; max_read_len <= 65535 is accepted, but beyond a few
+ * thousand bases the scratch of a full-size batch exhausts HBM and create / resize return SMEM_GPU_E_NOMEM).  smem_gpu_resize re-sizes the batch buffers in place -- index, samples and accelerator
  * tables stay -- so a caller can start small and grow when a longer read or a larger batch arrives. */
 int smem_gpu_resize(smem_gpu_t *h, int64_t max_batch_reads, int max_read_len);
 
@@ -127,7 +127,9 @@ int smem_gpu_get_text_index(smem_gpu_t *h, int which, uint64_t *out, int64_t n_o
  * smem_next2 (bwamem.c:244-305: pass 1, 0.7.8 re-seed of the longest SMEM, ordered merge) to
  * exhaustion for every read.  step_out (nullable) receives, per interval, the index of the
  * smem_next2 call that produced it.  *total_out = number of intervals; if it exceeds intv_cap the
- * call returns SMEM_GPU_E_CAPACITY with read_off and *total_out valid and intv_out untouched. */
+ * call returns SMEM_GPU_E_CAPACITY with read_off and *total_out valid; the CONTENT of intv_out is then unspecified (shards
+ * that still fitted may have been copied).  The results stay resident: size the buffer from *total_out and call
+ * smem_gpu_fetch -- there is no need to seed again. */
 int smem_gpu_collect(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs,
                      const smem_seed_opt_t *opt, smem_intv_t *intv_out, int64_t intv_cap,
                      int64_t *read_off, uint16_t *step_out, int64_t *total_out);

@@ -98,7 +98,7 @@ def main():
     ap.add_argument("--paired", action="store_true")
     ap.add_argument("--threads", default="", help="comma list of -t values for the GPU runs (default: 1 and the core count)")
     ap.add_argument("--batches", default="64,1024,16384,65536")
-    ap.add_argument("--handles", default="8", help="comma list of SMEM_GPU_ADAPTER_HANDLES values")
+    ap.add_argument("--handles", default="0", help="comma list of SMEM_GPU_ADAPTER_HANDLES values (0 = the adapter's own choice from the batch size)")
     ap.add_argument("--out", default="")
     ap.add_argument("--tmp", default="/dev/shm" if os.path.isdir("/dev/shm") else None)
     args = ap.parse_args()
@@ -142,11 +142,13 @@ def main():
                 for b in [int(x) for x in args.batches.split(",")]:
                     if t == 1 and b < 1024 and args.reads > 200_000:
                         continue                      # one thread, tiny batches: minutes of latency-bound calls that say nothing new
-                    env = {"SMEM_GPU_ADAPTER_STATS": "1", "SMEM_GPU_ADAPTER_HANDLES": str(handles)}
+                    env = {"SMEM_GPU_ADAPTER_STATS": "1"}
+                    if handles > 0:
+                        env["SMEM_GPU_ADAPTER_HANDLES"] = str(handles)
                     wall, md5, n_l, err = run_mem(GPU, t, b, fa, fqs, env)
                     st = [l for l in err.splitlines() if "lists_from_cache" in l]
                     kv = dict(x.split("=") for x in st[-1].split()[1:]) if st else {}
-                    row = {"impl": "drop-in (bwa_gpu mem: reference + GPU adapter)", "t": t, "b": b, "handles": handles, "wall_s": round(wall, 3),
+                    row = {"impl": "drop-in (bwa_gpu mem: reference + GPU adapter)", "t": t, "b": b, "handles": int(kv.get("handles", handles)), "wall_s": round(wall, 3),
                            "reads_per_s": round(args.reads / wall), "sam_identical_to_cpu_path": md5 == md5_cpu and n_l == n_lines,
                            "seed_s_sum_over_threads": float(kv.get("adapter_s", "nan")), "startup_s_sum_over_threads": float(kv.get("startup_s", "nan")),
                            "gpu_call_s": float(kv.get("gpu_s", "nan")), "leader_gather_s": float(kv.get("gather_s", "nan")), "leader_launch_s": float(kv.get("launch_s", "nan")),
