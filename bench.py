@@ -341,7 +341,10 @@ def main():
         # ... and the same reads through the compact wire format
         gp = g.collect_packed(sg.PackedReads(lib, seq[: int(offs[ns])], offs[: ns + 1]), opt)
         ok = ok and np.array_equal(gp["read_off"], st["read_off"]) and np.array_equal(gp["intv"], st["intv"])
-        parity = {"reads_checked": ns, "bit_exact": bool(ok), "checker": "oracle/liboracle.so", "wire_formats_checked": ["bytes + bwtintv_t", "2-bit reads + 16-byte records"]}
+        gp = g.collect_packed12(sg.PackedReads(lib, seq[: int(offs[ns])], offs[: ns + 1]), opt)
+        ok = ok and np.array_equal(gp["read_off"], st["read_off"]) and np.array_equal(gp["intv"], st["intv"])
+        parity = {"reads_checked": ns, "bit_exact": bool(ok), "checker": "oracle/liboracle.so",
+                  "wire_formats_checked": ["bytes + bwtintv_t", "2-bit reads + 16-byte records", "2-bit reads + 12-byte records"]}
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU intervals differ from the oracle on the bench workload")
         if not args.skip_cpu and world == 1:       # the CPU baseline is a single-GPU-run figure (it would idle the other ranks)
@@ -350,7 +353,7 @@ def main():
             m = min(n, max(20_000, int(probe["reads_per_s"] * args.cpu_seconds)))
             r = cpu_time(eng, seq, offs, m, ncores, OSeedOpt())
             one = cpu_time(eng, seq, offs, min(m, 20_000), 1, OSeedOpt())
-            gk = g.collect_packed(sg.PackedReads(lib, seq[: int(offs[m])], offs[: m + 1]), opt)
+            gk = g.collect_packed12(sg.PackedReads(lib, seq[: int(offs[m])], offs[: m + 1]), opt)
             ck = orc.checksum(gk["intv"], gk["read_off"])
             parity.update(reads_checked=m, bit_exact=bool(ok and ck == r["checksum"]), checker=f"oracle + {kind} checksum (through the compact wire format)")
             if ck != r["checksum"]:
@@ -432,6 +435,9 @@ def main():
     cap16 = total + total // 16 + 1024
     prec = [sg.PinnedArray(lib, (cap16, 2), np.uint64) for _ in range(T)]
     proff32 = [sg.PinnedArray(lib, (n + 1,), np.uint32) for _ in range(T)]
+    prec12 = [sg.PinnedArray(lib, (cap16, 3), np.uint32) for _ in range(T)]          # 12-byte records (smem_intv12_t) + their exception lists
+    exc_cap = max(4096, n // 4)
+    pexc = [sg.PinnedArray(lib, (exc_cap,), sg.EXC_DTYPE) for _ in range(T)]
 
     def run_pool(step_fn, k_steps):
         """k_steps calls spread over the worker threads; a free worker takes the next step (kt_for_batch hands out batches
@@ -489,14 +495,24 @@ def main():
     max_over_ranks = lambda x: sh.max_over_ranks(x, device)
     gather_ranks = lambda vals: sh.gather_rows(vals, device)
 
-    # (1) the headline: compact wire format both ways
+    # (1) the headline: compact wire format both ways: 2-bit reads in, 12-byte interval records out
+    n_exc_last = [0] * T
+    pos_bits = [0]
+    def step_packed12(t):
+        tot, ne, pb = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        rc = lib.smem_gpu_collect_packed12(workers[t].h, C.byref(packed.desc), C.byref(opt), C.c_void_p(prec12[t].array.ctypes.data), C.c_int64(cap16),
+                                           C.c_void_p(proff32[t].array.ctypes.data), C.c_void_p(pexc[t].array.ctypes.data), C.c_int64(exc_cap),
+                                           C.byref(ne), C.byref(pb), C.byref(tot))
+        check_rc(rc, t, "smem_gpu_collect_packed12")
+        n_exc_last[t] = int(ne.value); pos_bits[0] = int(pb.value)
+        return int(tot.value)
     def step_packed(t):
         tot = C.c_int64(0)
         rc = lib.smem_gpu_collect_packed(workers[t].h, C.byref(packed.desc), C.byref(opt), C.c_void_p(prec[t].array.ctypes.data), C.c_int64(cap16),
                                          C.c_void_p(proff32[t].array.ctypes.data), C.byref(tot))
         check_rc(rc, t, "smem_gpu_collect_packed")
         return int(tot.value)
-    dt_e2e, tot_e2e = timed_leg(step_packed, args.steps)
+    dt_e2e, tot_e2e = timed_leg(step_packed12, args.steps)
     te = workers[0].timing()
     stages = acc_read()
     stage_keys = list(stages)
@@ -506,8 +522,10 @@ def main():
     # every worker's last result is the step's result: checksum of rank 0's against the device-resident run
     if rank == 0:
         a = g.fetch_packed(total)
-        if not (np.array_equal(a["rec"], prec[0].array[:tot_e2e]) and np.array_equal(a["read_off"], proff32[0].array.astype(np.int64))):
+        got12 = sg.unpack_intv12(prec12[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]])
+        if not (tot_e2e == total and np.array_equal(a["intv"], got12) and np.array_equal(a["read_off"], proff32[0].array.astype(np.int64))):
             raise SystemExit("PARITY FAILURE: end-to-end result differs from the device-resident run")
+        del got12
 
     # ---- optional: every interval of the step against the oracle (BASELINE config 2)
     if args.full_compare and rank == 0:
@@ -516,7 +534,7 @@ def main():
         ixh = fm.BwtIndex(ix.primary, ix.L2, ix.seq_len, ix.bwt_size, ix.words_numpy())
         t0c = time.time()
         want = Oracle(ixh).collect(seq, offs, OSeedOpt(), nthreads=ncores)
-        same = (np.array_equal(want["read_off"], proff32[0].array.astype(np.int64)) and np.array_equal(want["intv"], sg.unpack_intv16(prec[0].array[:tot_e2e])))
+        same = (np.array_equal(want["read_off"], proff32[0].array.astype(np.int64)) and np.array_equal(want["intv"], sg.unpack_intv12(prec12[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]])))
         log(f"full compare: {n} reads, {len(want['intv'])} intervals, bit_exact={same} (oracle {time.time() - t0c:.1f}s)")
         parity = dict(parity or {}, full_compare_reads=n, full_compare_intervals=int(len(want["intv"])), full_compare_bit_exact=bool(same))
         if not same:
@@ -525,6 +543,16 @@ def main():
 
     extras = {}
     if not args.no_extras:
+        # (1b) the same call with 16-byte records (no exception list; 4 more bytes per interval over the link)
+        d16, tot16 = timed_leg(step_packed, args.steps)
+        t16 = workers[0].timing(); s16 = acc_read()
+        d16 = max_over_ranks(d16)
+        extras["e2e_16byte_records"] = {"value": world * n * args.steps / d16, "unit": "reads/s", "ms_per_step": d16 / args.steps * 1e3, "api": "smem_gpu_collect_packed",
+                                        "h2d_bytes_per_step": int(t16["h2d_bytes"]), "d2h_bytes_per_step": int(t16["d2h_bytes"]),
+                                        "stages_rank0": {k: round(v, 3) for k, v in s16.items()}}
+        log("e2e, 2-bit reads in / 16-byte records out:", extras["e2e_16byte_records"])
+        if rank == 0 and not (tot16 == tot_e2e and np.array_equal(a["rec"], prec[0].array[:tot16])):
+            raise SystemExit("PARITY FAILURE: 16-byte end-to-end result differs from the device-resident run")
         # (2) bwa's own formats: one byte per base in, bwtintv_t out (the call the link-compatible adapter makes)
         pintvs = [sg.PinnedArray(lib, (total + 1024, 4), np.uint64) for _ in range(T)]
         proffs = [sg.PinnedArray(lib, (n + 1,), np.int64) for _ in range(T)]
@@ -779,7 +807,8 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": world * n * args.steps / dt_e2e, "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
                     "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "api": "smem_gpu_collect_packed (2-bit reads in, 16-byte interval records out; include/smem_gpu.h)",
+                    "api": "smem_gpu_collect_packed12 (2-bit reads in, 12-byte interval records + exception list out; include/smem_gpu.h)",
+                    "exceptions_per_step": int(n_exc_last[0]), "record_pos_bits": pos_bits[0],
                     "pipeline_lanes_per_gpu": args.lanes, "host_threads": T, "intervals": int(tot_e2e),
                     "host_pack_s_per_step_untimed": round(t_pack, 4),
                     "stages_per_rank": stages_per_rank},

@@ -69,8 +69,11 @@ struct DeviceCtx {
 	long long *d_offs = nullptr;
 	unsigned short *d_lens = nullptr; AmbEntry *d_amb = nullptr; size_t amb_cap = 0;   // compact wire format: lengths, ambiguous-base list
 	int in_fmt = 0, r2_stride = 0, r2_read_len = 0; bool r2_has_lens = false; long long n_amb = 0;
-	uint4 *d_outp = nullptr; size_t outp_cap = 0; u32 *d_off32 = nullptr;               // 16-byte result records + 32-bit offsets
-	bool want_packed = false, out_valid = false, outp_valid = false;
+	uint4 *d_outp = nullptr; size_t outp_cap = 0; u32 *d_off32 = nullptr;               // 16- or 12-byte result records + 32-bit offsets
+	Exc12 *d_exc = nullptr; size_t exc_cap = 0; long long n_exc = 0; int pos_bits = 0;  // 12-byte records: intervals whose size does not fit the record
+	int want_packed = 0;             // result form of the next run: 0 = 32-byte bwtintv_t, 1 = 16-byte records, 2 = 12-byte records
+	int outp_fmt = 0;                // what d_outp holds (0 = nothing valid)
+	bool out_valid = false;
 	int64_t h2d = 0, d2h = 0;        // bytes of the last stage / fetch of this context
 	double acc_stage_ms = 0, acc_turn_ms = 0, acc_run_ms = 0, acc_fetch_ms = 0; int64_t acc_calls = 0, acc_h2d = 0, acc_d2h = 0;   // wall-time accumulators of the one-call forms
 	int *d_x = nullptr, *d_mi = nullptr, *d_ret = nullptr;
@@ -173,7 +176,7 @@ void ctx_free_batch(DeviceCtx &d)
 	cudaFree(d.d_bt); d.d_bt = nullptr; d.bt_nodes = 0;
 	cudaFree(d.d_cwork); cudaFree(d.d_flt); cudaFree(d.d_keep); cudaFree(d.d_nch); cudaFree(d.d_nkept); cudaFree(d.d_coff); cudaFree(d.d_koff);
 	cudaFree(d.d_chains); cudaFree(d.d_cseeds);
-	cudaFree(d.d_seq); cudaFree(d.d_qpack); cudaFree(d.d_offs); cudaFree(d.d_rlen); cudaFree(d.d_lens); cudaFree(d.d_amb); cudaFree(d.d_outp); cudaFree(d.d_off32);
+	cudaFree(d.d_seq); cudaFree(d.d_qpack); cudaFree(d.d_offs); cudaFree(d.d_rlen); cudaFree(d.d_lens); cudaFree(d.d_amb); cudaFree(d.d_outp); cudaFree(d.d_off32); cudaFree(d.d_exc);
 	cudaFree(d.d_x); cudaFree(d.d_mi); cudaFree(d.d_ret);
 	cudaFree(d.d_counts); cudaFree(d.d_overflow); cudaFree(d.d_off); cudaFree(d.d_slots);
 	cudaFree(d.d_scratch); cudaFree(d.d_out); cudaFree(d.d_step); cudaFree(d.d_aux); cudaFree(d.d_tmp); cudaFree(d.d_big); cudaFree(d.d_counts_k);
@@ -181,10 +184,10 @@ void ctx_free_batch(DeviceCtx &d)
 	d.d_cwork = nullptr; d.d_flt = nullptr; d.d_keep = nullptr; d.cwork_cap = 0; d.d_nch = d.d_nkept = nullptr; d.d_coff = d.d_koff = nullptr; d.cread_cap = 0;
 	d.d_chains = nullptr; d.d_cseeds = nullptr; d.chains_cap = 0;
 	d.d_seq = nullptr; d.d_qpack = nullptr; d.qpack_bytes = 0; d.d_offs = nullptr; d.d_rlen = nullptr; d.d_lens = nullptr; d.d_amb = nullptr; d.amb_cap = 0;
-	d.d_outp = nullptr; d.outp_cap = 0; d.d_off32 = nullptr; d.d_x = d.d_mi = d.d_ret = nullptr; d.d_counts = d.d_overflow = nullptr; d.d_off = nullptr;
+	d.d_outp = nullptr; d.outp_cap = 0; d.d_off32 = nullptr; d.d_exc = nullptr; d.exc_cap = 0; d.d_x = d.d_mi = d.d_ret = nullptr; d.d_counts = d.d_overflow = nullptr; d.d_off = nullptr;
 	d.d_slots = nullptr; d.slots_cap_alloc = 0; d.d_scratch = nullptr; d.scratch_entries = 0; d.d_out = nullptr; d.d_step = d.d_aux = nullptr; d.out_cap = 0;
 	d.d_tmp = nullptr; d.tmp_bytes = 0; d.d_big = nullptr; d.big_entries = 0; d.d_counts_k = nullptr; d.counts_k_cap = 0;
-	d.read_cap = 0; d.seq_cap = 0; d.n = 0; d.lo = d.hi = 0; d.seeds_valid = d.out_valid = d.outp_valid = false;
+	d.read_cap = 0; d.seq_cap = 0; d.n = 0; d.lo = d.hi = 0; d.seeds_valid = d.out_valid = false; d.outp_fmt = 0;
 }
 
 int ctx_alloc_batch(DeviceCtx &d, int64_t read_cap, int max_len, int slot_cap)
@@ -622,15 +625,33 @@ int ensure_packed_out(DeviceCtx &d)
 	return 0;
 }
 
+// 12-byte records: query positions take pos_bits each, what is left of the third word holds the interval size
+static int pos_bits_for(int max_len) { int b = 1; while ((1 << b) < max_len) ++b; return b; }
+static bool packed12_ok(const DeviceCtx &d, const smem_gpu &h) { return d.ix.seq_len < (1ull << 33) && pos_bits_for(h.max_len) <= 13; }
+
+int ensure_exc(DeviceCtx &d, size_t want)
+{
+	static_assert(sizeof(Exc12) == sizeof(smem_x2exc_t) && sizeof(smem_intv12_t) == 12, "12-byte record layout");
+	if (d.exc_cap < want) {
+		if (d.d_exc) CK(cudaFree(d.d_exc));
+		d.d_exc = nullptr; d.exc_cap = 0;
+		CK(cudaMalloc((void **)&d.d_exc, want * sizeof(Exc12)));
+		d.exc_cap = want;
+	}
+	return 0;
+}
+
 int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *opt)
 {
 	CK(cudaSetDevice(d.dev));
 	d.mode = mode; d.launches = 0; d.overflow = 0; d.seed_ms = d.total_ms = 0; d.total = 0;
-	d.seeds_valid = false; d.out_valid = d.outp_valid = false;
+	d.seeds_valid = false; d.out_valid = false; d.outp_fmt = 0; d.n_exc = 0;
 	if (d.n == 0) return 0;
 	if (!d.has_index) { d.err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
-	const bool packed_out = d.want_packed;
+	const bool packed_out = d.want_packed != 0, packed12 = d.want_packed == 2;
 	if (packed_out && (mode != MODE_COLLECT || !packed_out_ok(d, h))) { d.err = "16-byte result records need seq_len < 2^33 and max_read_len < 2^14"; return SMEM_GPU_E_ARG; }
+	if (packed12 && !packed12_ok(d, h)) { d.err = "12-byte result records need seq_len < 2^33 and max_read_len <= 8192"; return SMEM_GPU_E_ARG; }
+	d.pos_bits = pos_bits_for(h.max_len);
 	const int bps = h.blocks_per_sm;
 	// several lanes on this GPU: the persistent seed kernel leaves `spare_sms` SMs empty, so that the finished
 	// lane's scan / compaction kernels run next to the following lane's seed kernel (measured: with every SM
@@ -704,6 +725,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		if (use_rf) p.qflags = reinterpret_cast<u32 *>(reinterpret_cast<uint8_t *>(d.d_qpack) + bytes_q);
 	}
 	if (packed_out) { const int rc0 = ensure_packed_out(d); if (rc0) return rc0; }
+	if (packed12) { const int rc0 = ensure_exc(d, d.out_cap / 16 + 1024); if (rc0) return rc0; }
 
 	{
 		const auto tw0 = std::chrono::steady_clock::now();
@@ -768,7 +790,11 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	};
 	auto queue_compact = [&]() -> int {
 		const long long threads = (long long)d.n * 8;
-		if (packed_out)
+		if (packed12)
+			compact_packed12_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
+			                                                                                 reinterpret_cast<u32 *>(d.d_outp), d.d_off32, (long long)d.out_cap,
+			                                                                                 d.pos_bits, d.d_exc, (long long)d.exc_cap, d.d_status + 4);
+		else if (packed_out)
 			compact_packed_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
 			                                                                               d.d_outp, d.d_off32, (long long)d.out_cap);
 		else
@@ -780,8 +806,9 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	};
 	if ((rc = queue_scan())) return rc;
 	if ((rc = queue_compact())) return rc;
-	CK(cudaMemcpyAsync(d.h_status, d.d_status, 8 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
-	CK(cudaMemcpyAsync(d.h_status + 8, d.d_off + d.n, 8, cudaMemcpyDeviceToHost, d.stream));
+	publish_status_kernel<<<1, 32, 0, d.stream>>>(d.d_status, d.d_off + d.n, d.h_status);     // (h_status is pinned: mapped under unified addressing)
+	CK(cudaGetLastError());
+	++d.launches;
 	CK(cudaEventRecord(d.ev2, d.stream));
 	CK(stream_wait(d));
 	const double t_first = tms();
@@ -793,8 +820,11 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	d.pass2_skipped = d.h_status[6]; d.uw_walks = d.h_status[7];
 	memcpy(&d.total, d.h_status + 8, 8);
 	const bool regrow = (size_t)d.total > d.out_cap;
+	bool exc_grow = packed12 && (size_t)d.h_status[4] > d.exc_cap;       // (counted before any re-compaction)
+	const long long exc_first = d.h_status[4];
+	d.n_exc = exc_first;
 	if (packed_out && (unsigned long long)d.total >= (1ull << 32)) { d.err = "more than 2^32 intervals in one shard: use the 32-byte form"; return SMEM_GPU_E_CAPACITY; }
-	if (n_over > 0 || regrow) {
+	if (n_over > 0 || regrow || exc_grow) {
 		int big_cap = 0;
 		if (n_over > 0) {
 			// Reads that outgrew their result slot are seeded again into slots of the largest count measured.
@@ -841,11 +871,23 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			CK(cudaMalloc((void **)&d.d_step, d.out_cap * sizeof(unsigned short)));
 			CK(cudaMalloc((void **)&d.d_aux, d.out_cap * sizeof(unsigned short)));
 			if (packed_out) { const int rc0 = ensure_packed_out(d); if (rc0) return rc0; }
-			if ((rc = queue_compact())) return rc;       // the first compaction stopped at the old capacity
 		}
+		if (packed12) {
+			// room for the first compaction's entries plus every entry the overflow reads can add (they are placed a second time, whole)
+			const size_t need_exc = (size_t)exc_first + (size_t)n_over * big_cap + 1024;
+			if (need_exc > d.exc_cap) exc_grow = true;         // (a new buffer: the first compaction runs again to fill it)
+			if (regrow || exc_grow) { const int rc0 = ensure_exc(d, std::max(need_exc + need_exc / 8, d.out_cap / 16 + 1024)); if (rc0) return rc0; }
+		}
+		if (packed12) CK(cudaMemsetAsync(d.d_status + 4, 0, sizeof(int), d.stream));   // the re-compaction (or the overflow reads' part) counts again
+		if (regrow || exc_grow) { if ((rc = queue_compact())) return rc; }       // the first compaction stopped at the old capacity
+		else if (packed12) CK(cudaMemcpyAsync(d.d_status + 4, d.h_status + 4, sizeof(int), cudaMemcpyHostToDevice, d.stream));   // keep the first pass' entries
 		if (n_over > 0) {
 			const long long threads = (long long)n_over * big_cap;
-			if (packed_out)
+			if (packed12)
+				compact_list_packed12_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over, d.d_off,
+				                                                                                      reinterpret_cast<u32 *>(d.d_outp), d.pos_bits, d.d_exc,
+				                                                                                      (long long)d.exc_cap, d.d_status + 4);
+			else if (packed_out)
 				compact_list_packed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
 				                                                                                    d.d_off, d.d_outp);
 			else
@@ -854,14 +896,19 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			CK(cudaGetLastError());
 			++d.launches;
 		}
+		if (packed12) { publish_status_kernel<<<1, 32, 0, d.stream>>>(d.d_status, d.d_off + d.n, d.h_status); CK(cudaGetLastError()); }
 		CK(cudaEventRecord(d.ev2, d.stream));
 		turn_release(d);
 		CK(stream_wait(d));
+		if (packed12) {
+			d.n_exc = d.h_status[4];
+			if ((size_t)d.n_exc > d.exc_cap) { d.err = "exception list of the 12-byte records outgrew its buffer twice"; return SMEM_GPU_E_INTERNAL; }
+		}
 	}
 	// the scan / compaction kernels are queued ahead of whatever the next call launches: a persistent seed kernel that got
 	// there first would hold every SM and they would wait for it to drain
 	turn_release(d);
-	(packed_out ? d.outp_valid : d.out_valid) = true;
+	if (packed_out) d.outp_fmt = d.want_packed; else d.out_valid = true;
 	if (trace) fprintf(stderr, "[smem_gpu trace]   lane %d run: first round trip +%.2f, done +%.2f ms after the seed launch (%d overflow reads%s)\n", d.lane, t_first, tms(), n_over, regrow ? ", output buffers regrown" : "");
 	CK(cudaEventElapsedTime(&d.seed_ms, d.ev0s, d.ev1));
 	CK(cudaEventElapsedTime(&d.total_ms, d.ev0, d.ev2));
@@ -886,27 +933,51 @@ int ctx_fetch(DeviceCtx &d, smem_intv_t *intv_out, int64_t *read_off, uint16_t *
 }
 
 // 16-byte records + 32-bit offsets; results of a run that compacted into the 32-byte form are converted on the device first
-int ctx_fetch_packed(DeviceCtx &d, smem_gpu &h, smem_intv16_t *out, uint32_t *read_off, long long base)
+// fmt 2 = 12-byte records: `out` is then a smem_intv12_t array, exc_out (room for exc_room entries from exc_base on) receives the exception list
+int ctx_fetch_packed(DeviceCtx &d, smem_gpu &h, void *out, uint32_t *read_off, long long base, int fmt = 1, smem_x2exc_t *exc_out = nullptr,
+                     long long exc_base = 0, long long exc_room = 0)
 {
 	CK(cudaSetDevice(d.dev));
 	d.d2h = 0;
 	if (d.n == 0) return 0;
-	if (!d.outp_valid) {
-		if (!d.out_valid || d.mode != MODE_COLLECT || !packed_out_ok(d, h) || (unsigned long long)d.total >= (1ull << 32)) {
-			d.err = "no resident results that fit 16-byte records"; return SMEM_GPU_E_ARG;
+	if (d.outp_fmt != fmt) {
+		if (!d.out_valid || d.mode != MODE_COLLECT || !packed_out_ok(d, h) || (unsigned long long)d.total >= (1ull << 32) || (fmt == 2 && !packed12_ok(d, h))) {
+			d.err = "no resident results that fit the compact records (a run that compacted into one compact form keeps only that form)"; return SMEM_GPU_E_ARG;
 		}
 		const int rc0 = ensure_packed_out(d);
 		if (rc0) return rc0;
 		const long long threads = std::max<long long>(d.total, d.n + 1);
-		intv16_from_dense_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_out, d.total, d.d_off, d.n, d.d_outp, d.d_off32);
-		CK(cudaGetLastError());
-		d.outp_valid = true;
+		if (fmt == 2) {
+			d.pos_bits = pos_bits_for(h.max_len);
+			for (int round = 0; round < 2; ++round) {
+				const int rc1 = ensure_exc(d, round == 0 ? d.out_cap / 16 + 1024 : (size_t)d.n_exc + 1024);
+				if (rc1) return rc1;
+				CK(cudaMemsetAsync(d.d_status + 4, 0, sizeof(int), d.stream));
+				intv12_from_dense_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_out, d.total, d.d_off, d.n, reinterpret_cast<u32 *>(d.d_outp),
+				                                                                                 d.d_off32, d.pos_bits, d.d_exc, (long long)d.exc_cap, d.d_status + 4);
+				CK(cudaGetLastError());
+				CK(cudaMemcpyAsync(d.h_status + 4, d.d_status + 4, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+				CK(stream_wait(d));
+				d.n_exc = d.h_status[4];
+				if ((size_t)d.n_exc <= d.exc_cap) break;
+			}
+		} else {
+			intv16_from_dense_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_out, d.total, d.d_off, d.n, d.d_outp, d.d_off32);
+			CK(cudaGetLastError());
+		}
+		d.outp_fmt = fmt;
 	}
+	const size_t rec = fmt == 2 ? 12 : 16;
 	CK(cudaMemcpyAsync(read_off + d.lo, d.d_off32, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream));
 	d.d2h = d.n * 4;
-	if (out && d.total) { CK(cudaMemcpyAsync(out + base, d.d_outp, (size_t)d.total * 16, cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.total * 16; }
+	if (out && d.total) { CK(cudaMemcpyAsync((uint8_t *)out + (size_t)base * rec, d.d_outp, (size_t)d.total * rec, cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.total * rec; }
+	const bool exc_fits = fmt == 2 && exc_out && d.n_exc <= exc_room;
+	if (exc_fits && d.n_exc) { CK(cudaMemcpyAsync(exc_out + exc_base, d.d_exc, (size_t)d.n_exc * sizeof(Exc12), cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.n_exc * (int64_t)sizeof(Exc12); }
 	CK(stream_wait(d));
-	if (base) for (int64_t i = d.lo; i < d.hi; ++i) read_off[i] += (uint32_t)base;
+	if (base) {
+		for (int64_t i = d.lo; i < d.hi; ++i) read_off[i] += (uint32_t)base;
+		if (exc_fits) for (long long k = 0; k < d.n_exc; ++k) exc_out[exc_base + k].index += (uint32_t)base;
+	}
 	return 0;
 }
 
@@ -962,7 +1033,7 @@ int do_stage(smem_gpu *h, int64_t n, const BatchIn &in)
 	return 0;
 }
 
-int do_run(smem_gpu *h, int mode, const smem_seed_opt_t *opt, int64_t *total_out, bool packed_out = false)
+int do_run(smem_gpu *h, int mode, const smem_seed_opt_t *opt, int64_t *total_out, int packed_out = 0)
 {
 	if (h->staged < 0) { h->err = "nothing staged"; return SMEM_GPU_E_ARG; }
 	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; }
@@ -997,7 +1068,9 @@ int do_fetch(smem_gpu *h, smem_intv_t *intv_out, int64_t cap, int64_t *read_off,
 	return 0;
 }
 
-int do_fetch_packed(smem_gpu *h, smem_intv16_t *out, int64_t cap, uint32_t *read_off, int64_t *total_out)
+struct Exc12Out { smem_x2exc_t *exc = nullptr; int64_t cap = 0; int64_t *n_out = nullptr; int32_t *pos_bits_out = nullptr; };
+
+int do_fetch_packed(smem_gpu *h, void *out, int64_t cap, uint32_t *read_off, int64_t *total_out, int fmt = 1, const Exc12Out &xo = Exc12Out())
 {
 	if (!h->ran) { h->err = "no results: call a run function first"; return SMEM_GPU_E_ARG; }
 	if (!read_off) { h->err = "read_off is required"; return SMEM_GPU_E_ARG; }
@@ -1008,11 +1081,27 @@ int do_fetch_packed(smem_gpu *h, smem_intv16_t *out, int64_t cap, uint32_t *read
 	if (tot >= (1ll << 32)) { h->err = "more than 2^32 intervals: use the 32-byte form"; return SMEM_GPU_E_CAPACITY; }
 	const bool fits = tot <= cap && (out || tot == 0);
 	read_off[0] = 0;
-	int rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_fetch_packed(d, *h, fits ? out : nullptr, read_off, base[&d - &h->devs[0]]); });
-	if (rc) return rc;
+	// (exception lists are placed device after device; a device that still has to convert its results learns its count inside ctx_fetch_packed,
+	//  so with several devices the lists are fetched one device at a time)
+	int rc = 0;
+	int64_t n_exc = 0;
+	if (fmt == 2 && h->devs.size() > 1) {
+		for (auto &d : h->devs) {
+			rc = ctx_fetch_packed(d, *h, fits ? out : nullptr, read_off, base[&d - &h->devs[0]], 2, xo.exc, n_exc, std::max<int64_t>(xo.cap - n_exc, 0));
+			if (rc) { h->err = "device " + std::to_string(d.dev) + ": " + d.err; return rc; }
+			n_exc += d.n_exc;
+		}
+	} else {
+		rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_fetch_packed(d, *h, fits ? out : nullptr, read_off, base[&d - &h->devs[0]], fmt, xo.exc, 0, xo.cap); });
+		if (rc) return rc;
+		if (fmt == 2) n_exc = h->devs[0].n_exc;
+	}
 	read_off[h->staged] = (uint32_t)tot;
 	h->d2h_bytes = sum_d2h(h);
+	if (xo.n_out) *xo.n_out = n_exc;
+	if (xo.pos_bits_out) *xo.pos_bits_out = pos_bits_for(h->max_len);
 	if (!fits) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	if (fmt == 2 && (n_exc > xo.cap || (n_exc > 0 && !xo.exc))) { h->err = "exc_cap too small for the exception list"; return SMEM_GPU_E_CAPACITY; }
 	return 0;
 }
 
@@ -1022,7 +1111,8 @@ int do_fetch_packed(smem_gpu *h, smem_intv16_t *out, int64_t cap, uint32_t *read
 // out16 / read_off32 != nullptr selects the 16-byte result records.
 struct CollectOut {
 	smem_intv_t *intv = nullptr; int64_t *read_off = nullptr; uint16_t *step = nullptr, *aux = nullptr; int32_t *ret = nullptr;
-	smem_intv16_t *intv16 = nullptr; uint32_t *read_off32 = nullptr;
+	void *intv16 = nullptr; uint32_t *read_off32 = nullptr;      // compact records: smem_intv16_t (fmt 1) or smem_intv12_t (fmt 2)
+	int fmt = 1; Exc12Out xo;
 	int64_t cap = 0; int64_t *total = nullptr;
 };
 
@@ -1037,8 +1127,10 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_s
 	const size_t G = h->devs.size();
 	h->use_turn = n >= h->turn_min_reads * (int64_t)G;
 	h->stage_wait = h->use_turn;
-	std::vector<long long> totals(G, 0);
+	std::vector<long long> totals(G, 0), excs(G, 0);
 	std::vector<char> ran(G, 0);
+	bool exc_overflow = false;
+	const int want_fmt = packed ? out.fmt : 0;
 	std::mutex mu;
 	std::condition_variable cv;
 	bool overflow = false;
@@ -1050,28 +1142,29 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_s
 	rc = for_each_device(h, [&](DeviceCtx &d) {
 		const size_t k = &d - &h->devs[0];
 		const double ta = ms();
-		d.want_packed = packed;
+		d.want_packed = want_fmt;
 		int r = ctx_stage(d, *h, in);
 		const double tb = ms();
 		const double turn0 = d.acc_turn_ms;
 		if (!r) r = ctx_run(d, *h, mode, opt);
 		else if (d.hi > d.lo) { turn_acquire(d, *h); turn_release(d); }    // keep the turn's lane count right
 		const double tc = ms();
-		long long base = 0;
+		long long base = 0, exc_base = 0;
 		{
 			std::unique_lock<std::mutex> lk(mu);
-			totals[k] = r ? 0 : d.total; ran[k] = 1;
+			totals[k] = r ? 0 : d.total; excs[k] = r ? 0 : d.n_exc; ran[k] = 1;
 			cv.notify_all();
 			cv.wait(lk, [&] { for (size_t j = 0; j < k; ++j) if (!ran[j]) return false; return true; });
-			for (size_t j = 0; j < k; ++j) base += totals[j];
+			for (size_t j = 0; j < k; ++j) { base += totals[j]; exc_base += excs[j]; }
 			if (!r && base + d.total > out.cap) overflow = true;
+			if (!r && want_fmt == 2 && (exc_base + d.n_exc > out.xo.cap || (d.n_exc > 0 && !out.xo.exc))) exc_overflow = true;
 		}
 		if (r) return r;
 		const bool fits = have_out && base + d.total <= out.cap;
 		const double tc2 = ms();
 		if (packed) {
 			if (base + d.total >= (1ll << 32)) { d.err = "more than 2^32 intervals: use the 32-byte form"; return (int)SMEM_GPU_E_CAPACITY; }
-			r = ctx_fetch_packed(d, *h, fits ? out.intv16 : nullptr, out.read_off32, base);
+			r = ctx_fetch_packed(d, *h, fits ? out.intv16 : nullptr, out.read_off32, base, want_fmt, out.xo.exc, exc_base, std::max<int64_t>(out.xo.cap - exc_base, 0));
 		} else
 			r = ctx_fetch(d, fits ? out.intv : nullptr, out.read_off, fits ? out.step : nullptr, out.ret, base, fits ? out.aux : nullptr);
 		const double td = ms();
@@ -1089,7 +1182,14 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_s
 	if (out.total) *out.total = tot;
 	h->h2d_bytes = sum_h2d(h);
 	h->d2h_bytes = sum_d2h(h);
+	if (want_fmt == 2) {
+		long long ne = 0;
+		for (auto e : excs) ne += e;
+		if (out.xo.n_out) *out.xo.n_out = ne;
+		if (out.xo.pos_bits_out) *out.xo.pos_bits_out = pos_bits_for(h->max_len);
+	}
 	if (overflow || (tot > 0 && !have_out)) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	if (exc_overflow) { h->err = "exc_cap too small for the exception list"; return SMEM_GPU_E_CAPACITY; }
 	return 0;
 }
 
@@ -1623,6 +1723,23 @@ int smem_gpu_collect_packed(smem_gpu_t *h, const smem_reads2_t *reads, const sme
 	if (!h || !reads || !opt || !read_off) return SMEM_GPU_E_ARG;
 	CollectOut o; o.intv16 = intv_out; o.cap = intv_cap; o.read_off32 = read_off; o.total = total_out;
 	return do_collect(h, MODE_COLLECT, reads->n_reads, packed_in(reads), opt, o);
+}
+
+int smem_gpu_collect_packed12(smem_gpu_t *h, const smem_reads2_t *reads, const smem_seed_opt_t *opt, smem_intv12_t *intv_out, int64_t intv_cap,
+                              uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap, int64_t *n_exc_out, int32_t *pos_bits_out, int64_t *total_out)
+{
+	if (!h || !reads || !opt || !read_off || exc_cap < 0) return SMEM_GPU_E_ARG;
+	CollectOut o; o.intv16 = intv_out; o.cap = intv_cap; o.read_off32 = read_off; o.total = total_out; o.fmt = 2;
+	o.xo.exc = exc_out; o.xo.cap = exc_cap; o.xo.n_out = n_exc_out; o.xo.pos_bits_out = pos_bits_out;
+	return do_collect(h, MODE_COLLECT, reads->n_reads, packed_in(reads), opt, o);
+}
+
+int smem_gpu_fetch_packed12(smem_gpu_t *h, smem_intv12_t *intv_out, int64_t intv_cap, uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap,
+                            int64_t *n_exc_out, int32_t *pos_bits_out, int64_t *total_out)
+{
+	if (!h || exc_cap < 0) return SMEM_GPU_E_ARG;
+	Exc12Out xo; xo.exc = exc_out; xo.cap = exc_cap; xo.n_out = n_exc_out; xo.pos_bits_out = pos_bits_out;
+	return do_fetch_packed(h, intv_out, intv_cap, read_off, total_out, 2, xo);
 }
 
 int smem_gpu_trace(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const smem_seed_opt_t *opt,

@@ -744,6 +744,77 @@ __global__ void __launch_bounds__(128) compact_packed_kernel(const Intv *__restr
 	}
 }
 
+// The 12-byte result record (smem_intv12_t, include/smem_gpu.h): w[0] = low word of x0, w[1] = low word of x1, w[2] = bit 32 of x0 |
+// bit 32 of x1 << 1 | qbeg << 2 | (qend - 1) << (2 + P) | field << (2 + 2P), P = pos_bits; field = x2 - 1 while that is below
+// the all-ones value of its 30 - 2P bits, else all ones and the interval's x2 travels in the exception list {index, x2}
+// (unordered; status[4] counts them, entries beyond exc_cap are dropped and the host re-runs the compaction with room).
+struct Exc12 { u32 index, x2_lo, x2_hi; };
+__device__ __forceinline__ void put_intv12(u32 *__restrict__ out, long long o, const Intv &v, int pos_bits, Exc12 *__restrict__ exc, long long exc_cap,
+                                           int *__restrict__ n_exc)
+{
+	const u32 qb = (u32)(v.info >> 32) & 0xffffu, qe = (u32)v.info & 0xffffu;
+	const int fbits = 30 - 2 * pos_bits;
+	const u32 esc = (1u << fbits) - 1u;
+	const u64 x2m = v.x2 - 1;
+	const bool is_exc = x2m >= (u64)esc;
+	const u32 w2 = (u32)(v.x0 >> 32 & 1) | ((u32)(v.x1 >> 32 & 1) << 1) | (qb << 2) | ((qe - 1u) << (2 + pos_bits)) | ((is_exc ? esc : (u32)x2m) << (2 + 2 * pos_bits));
+	out[3 * o] = (u32)v.x0; out[3 * o + 1] = (u32)v.x1; out[3 * o + 2] = w2;
+	if (is_exc) {
+		const long long k = atomicAdd(n_exc, 1);
+		if (k < exc_cap) { exc[k].index = (u32)o; exc[k].x2_lo = (u32)v.x2; exc[k].x2_hi = (u32)(v.x2 >> 32); }
+	}
+}
+
+__global__ void __launch_bounds__(128) compact_packed12_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
+                                                               const long long *__restrict__ off, long long n, u32 *__restrict__ out,
+                                                               u32 *__restrict__ off32, long long out_cap, int pos_bits, Exc12 *__restrict__ exc,
+                                                               long long exc_cap, int *__restrict__ n_exc)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long r = t >> 3;
+	if (r >= n) return;
+	const long long o0 = off[r];
+	const int c = (int)min((long long)min(counts[r], slot_cap), max(out_cap - o0, 0ll));      // (see compact_kernel)
+	if ((t & 7) == 0) { off32[r] = (u32)o0; if (r == n - 1) off32[n] = (u32)off[n]; }
+	for (int e = (int)(t & 7); e < c; e += 8) {
+		Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
+		v.info &= INFO_MASK;
+		put_intv12(out, o0 + e, v, pos_bits, exc, exc_cap, n_exc);
+	}
+}
+
+__global__ void compact_list_packed12_kernel(const Intv *__restrict__ big_slots, int big_cap, const int *__restrict__ list,
+                                             const int *__restrict__ counts_k, int n_list, const long long *__restrict__ off, u32 *__restrict__ out,
+                                             int pos_bits, Exc12 *__restrict__ exc, long long exc_cap, int *__restrict__ n_exc)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int k = (int)(t / big_cap), e = (int)(t % big_cap);
+	if (k >= n_list || e >= counts_k[k]) return;
+	Intv v = ld_intv(&big_slots[(size_t)k * big_cap + e]);
+	v.info &= INFO_MASK;
+	put_intv12(out, off[list[k]] + e, v, pos_bits, exc, exc_cap, n_exc);
+}
+
+// dense 32-byte results of an earlier run -> 12-byte records + 32-bit offsets (smem_gpu_fetch_packed12 after smem_gpu_run_collect)
+__global__ void intv12_from_dense_kernel(const Intv *__restrict__ in, long long total, const long long *__restrict__ off, long long n,
+                                         u32 *__restrict__ out, u32 *__restrict__ off32, int pos_bits, Exc12 *__restrict__ exc, long long exc_cap,
+                                         int *__restrict__ n_exc)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < total) put_intv12(out, t, ld_intv(&in[t]), pos_bits, exc, exc_cap, n_exc);
+	if (t <= n) off32[t] = (u32)off[t];
+}
+
+// The run's status words and interval total go to the host by a STORE into mapped pinned memory: a copy would queue on the
+// device-to-host copy engine behind another lane's bulk result transfer and hold the GPU's kernel turn for its duration.
+__global__ void publish_status_kernel(const int *__restrict__ status, const long long *__restrict__ total, int *__restrict__ host)
+{
+	const int t = threadIdx.x;
+	if (t < 8) host[t] = status[t];
+	if (t == 8) { const long long v = *total; host[8] = (int)(u32)v; host[9] = (int)(u32)((unsigned long long)v >> 32); }
+	__threadfence_system();
+}
+
 // dense 32-byte results of an earlier run -> 16-byte records + 32-bit offsets (smem_gpu_fetch_packed after smem_gpu_run_collect)
 __global__ void intv16_from_dense_kernel(const Intv *__restrict__ in, long long total, const long long *__restrict__ off, long long n,
                                          uint4 *__restrict__ out, u32 *__restrict__ off32)

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("SMEM_GPU_LIB") or os.path.join(HERE, "libsmem_gpu.so"
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_resize", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
     "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_chains", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_repeat_filter", "smem_gpu_get_repeat_filter", "smem_gpu_build_text_index", "smem_gpu_get_text_index", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
-    "smem_gpu_collect_packed", "smem_gpu_stage_reads_packed", "smem_gpu_fetch_packed", "smem_gpu_pack_reads",
+    "smem_gpu_collect_packed", "smem_gpu_stage_reads_packed", "smem_gpu_fetch_packed", "smem_gpu_pack_reads", "smem_gpu_collect_packed12", "smem_gpu_fetch_packed12",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -68,6 +68,32 @@ def unpack_intv16(rec: np.ndarray) -> np.ndarray:
     out[:, 1] = (w0 >> np.uint64(33)) | ((w1 & np.uint64(3)) << np.uint64(31))
     out[:, 2] = (w1 >> np.uint64(2)) & m33
     out[:, 3] = (((w1 >> np.uint64(35)) & np.uint64(0x3fff)) << np.uint64(32)) | ((w1 >> np.uint64(49)) & np.uint64(0x3fff))
+    return out
+
+
+EXC_DTYPE = np.dtype([("index", np.uint32), ("x2_lo", np.uint32), ("x2_hi", np.uint32)])
+
+
+def unpack_intv12(rec: np.ndarray, pos_bits: int, exc: "np.ndarray | None" = None) -> np.ndarray:
+    """smem_intv12_t records (uint32[n, 3]) + exception list -> bwtintv_t rows (uint64[n, 4]); mirrors smem_intv12_unpack of smem_gpu.h."""
+    rec = np.asarray(rec, np.uint32).reshape(-1, 3)
+    w2 = rec[:, 2].astype(np.uint64)
+    P = np.uint64(pos_bits)
+    pm = np.uint64((1 << pos_bits) - 1)
+    esc = np.uint64((1 << (30 - 2 * pos_bits)) - 1)
+    f = w2 >> (np.uint64(2) + P + P)
+    out = np.empty((len(rec), 4), np.uint64)
+    out[:, 0] = rec[:, 0].astype(np.uint64) | ((w2 & np.uint64(1)) << np.uint64(32))
+    out[:, 1] = rec[:, 1].astype(np.uint64) | (((w2 >> np.uint64(1)) & np.uint64(1)) << np.uint64(32))
+    out[:, 2] = np.where(f == esc, np.uint64(0), f + np.uint64(1))
+    out[:, 3] = (((w2 >> np.uint64(2)) & pm) << np.uint64(32)) | (((w2 >> (np.uint64(2) + P)) & pm) + np.uint64(1))
+    n_esc = int(np.count_nonzero(f == esc))
+    if n_esc:
+        if exc is None or len(exc) == 0:
+            raise ValueError("records refer to the exception list, which is missing")
+        out[exc["index"], 2] = exc["x2_lo"].astype(np.uint64) | (exc["x2_hi"].astype(np.uint64) << np.uint64(32))
+        if np.any(out[:, 2] == 0):
+            raise ValueError("an escaped record has no entry in the exception list")
     return out
 
 
@@ -398,6 +424,45 @@ class SmemGpu:
             self._check(rc)
             t = int(tot.value)
             return dict(rec=rec[:t], intv=unpack_intv16(rec[:t]) if unpack else None, read_off=read_off.astype(np.int64) if unpack else read_off)
+
+    def collect_packed12(self, reads: "PackedReads", opt: "SeedOpt | None" = None, out=None, read_off=None, exc=None, unpack=True):
+        """smem_gpu_collect_packed12: compact reads in, 12-byte interval records + exception list + uint32 CSR offsets out."""
+        opt = opt or SeedOpt()
+        n = reads.n
+        cap = out.shape[0] if out is not None else max(64, 16 * n)
+        exc_cap = exc.shape[0] if exc is not None else max(64, n)
+        read_off = read_off if read_off is not None else np.zeros(n + 1, np.uint32)
+        tot, n_exc, pb = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        while True:
+            rec = out if out is not None else np.empty((cap, 3), np.uint32)
+            ex = exc if exc is not None else np.empty(exc_cap, EXC_DTYPE)
+            rc = self.lib.smem_gpu_collect_packed12(self.h, C.byref(reads.desc), C.byref(opt), C.c_void_p(rec.ctypes.data), C.c_int64(cap),
+                                                    C.c_void_p(read_off.ctypes.data), C.c_void_p(ex.ctypes.data), C.c_int64(exc_cap), C.byref(n_exc),
+                                                    C.byref(pb), C.byref(tot))
+            if rc == -5 and out is None and exc is None and (tot.value > cap or n_exc.value > exc_cap):
+                cap, exc_cap = max(cap, int(tot.value)), max(exc_cap, int(n_exc.value))
+                continue
+            self._check(rc)
+            t, ne = int(tot.value), int(n_exc.value)
+            return dict(rec=rec[:t], exc=ex[:ne], pos_bits=int(pb.value), intv=unpack_intv12(rec[:t], int(pb.value), ex[:ne]) if unpack else None,
+                        read_off=read_off.astype(np.int64) if unpack else read_off)
+
+    def fetch_packed12(self, total: int):
+        n = self._n
+        read_off = np.zeros(n + 1, np.uint32)
+        tot, n_exc, pb = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        exc_cap = 1024
+        while True:
+            rec = np.empty((max(total, 1), 3), np.uint32)
+            ex = np.empty(exc_cap, EXC_DTYPE)
+            rc = self.lib.smem_gpu_fetch_packed12(self.h, C.c_void_p(rec.ctypes.data), C.c_int64(rec.shape[0]), C.c_void_p(read_off.ctypes.data),
+                                                  C.c_void_p(ex.ctypes.data), C.c_int64(exc_cap), C.byref(n_exc), C.byref(pb), C.byref(tot))
+            if rc == -5 and n_exc.value > exc_cap:
+                exc_cap = int(n_exc.value)
+                continue
+            self._check(rc)
+            t, ne = int(tot.value), int(n_exc.value)
+            return dict(rec=rec[:t], exc=ex[:ne], pos_bits=int(pb.value), intv=unpack_intv12(rec[:t], int(pb.value), ex[:ne]), read_off=read_off.astype(np.int64))
 
     def stage_packed(self, reads: "PackedReads"):
         self._keep = reads

@@ -238,6 +238,32 @@ int smem_gpu_collect_packed(smem_gpu_t *h, const smem_reads2_t *reads, const sme
  * (after any smem_gpu_run_collect or smem_gpu_collect*). */
 int smem_gpu_stage_reads_packed(smem_gpu_t *h, const smem_reads2_t *reads);
 int smem_gpu_fetch_packed(smem_gpu_t *h, smem_intv16_t *intv_out, int64_t intv_cap, uint32_t *read_off, int64_t *total_out);
+/* 12-byte result record, for links where bytes are what limits (eight GPUs behind shared PCIe uplinks):
+ * w[0] = low 32 bits of x[0], w[1] = low 32 bits of x[1], w[2] = bit 32 of x[0] | bit 32 of x[1] << 1 | query begin << 2 |
+ * (query end - 1) << (2 + P) | field << (2 + 2 P), with P = *pos_bits_out = ceil(log2(max_read_len)) of the handle and
+ * field = x[2] - 1 while that is below the all-ones value of the field's 30 - 2 P bits (16 bits = sizes up to 65535 for reads
+ * of up to 128 bases).  An all-ones field says "look it up": such intervals are listed, in no particular order, in the
+ * exception list {index of the record, x[2]}; decoding = unpack every record, then x[2] = exc.x2 at exc.index.  The same
+ * limits as the 16-byte record, plus max_read_len <= 8192.  On SMEM_GPU_E_CAPACITY read_off, *total_out and *n_exc_out are
+ * valid (size both buffers and call smem_gpu_fetch_packed12). */
+typedef struct { uint32_t w[3]; } smem_intv12_t;
+typedef struct { uint32_t index; uint32_t x2_lo; uint32_t x2_hi; } smem_x2exc_t;
+/* returns 1 if x[2] has to come from the exception list (o->x[2] is then 0) */
+static inline int smem_intv12_unpack(const smem_intv12_t *p, int pos_bits, smem_intv_t *o)
+{
+	const uint32_t w2 = p->w[2], pm = ((uint32_t)1 << pos_bits) - 1, esc = ((uint32_t)1 << (30 - 2 * pos_bits)) - 1;
+	const uint32_t f = w2 >> (2 + 2 * pos_bits);
+	o->x[0] = (uint64_t)p->w[0] | ((uint64_t)(w2 & 1) << 32);
+	o->x[1] = (uint64_t)p->w[1] | ((uint64_t)((w2 >> 1) & 1) << 32);
+	o->x[2] = f == esc ? 0 : (uint64_t)f + 1;
+	o->info = ((uint64_t)((w2 >> 2) & pm) << 32) | (uint64_t)(((w2 >> (2 + pos_bits)) & pm) + 1);
+	return f == esc;
+}
+int smem_gpu_collect_packed12(smem_gpu_t *h, const smem_reads2_t *reads, const smem_seed_opt_t *opt, smem_intv12_t *intv_out, int64_t intv_cap,
+                              uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap, int64_t *n_exc_out, int32_t *pos_bits_out,
+                              int64_t *total_out);
+int smem_gpu_fetch_packed12(smem_gpu_t *h, smem_intv12_t *intv_out, int64_t intv_cap, uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap,
+                            int64_t *n_exc_out, int32_t *pos_bits_out, int64_t *total_out);
 /* Host-side packer for callers that hold bwa's one-byte-per-base reads (n_threads host threads; lens and amb may be NULL if
  * the batch has one length / the caller knows there are no ambiguous bases -- then an ambiguous base is an error).
  * *n_amb_out = entries written (or needed, with SMEM_GPU_E_CAPACITY). */

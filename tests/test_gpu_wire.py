@@ -30,6 +30,11 @@ def check(sg, g, o, seq, offs, opt=None, **kw):
     got = g.collect_packed(pr, gopt)
     assert np.array_equal(got["read_off"], want["read_off"])
     assert np.array_equal(got["intv"], want["intv"])
+    got = g.collect_packed12(pr, gopt)                                  # 12-byte records + exception list: the same lists again
+    assert np.array_equal(got["read_off"], want["read_off"])
+    assert np.array_equal(got["intv"], want["intv"])
+    got16 = g.collect_packed(pr, gopt)                                  # (kept last: the d2h byte counts asserted by callers are the 16-byte form's)
+    assert np.array_equal(got16["intv"], want["intv"])
     return pr, want
 
 
@@ -95,6 +100,58 @@ def test_lanes_split_forms_and_conversions(world, synth):
     with pytest.raises(sg.SmemGpuError):
         g2.fetch(len(want["intv"]))
     g2.close()
+
+
+def test_packed12_exception_list(world, synth):
+    """12-byte records (smem_intv12_t): sizes that do not fit the record's field travel in the exception list -- also when that list
+    outgrows its first buffer, when reads outgrow their result slots (overflow re-run), through the split form and on a lane handle."""
+    sg, ref, ix, o, g = world
+    refn = ref.numpy()
+    reads = []
+    for k in range(400):                                                # single bases between Ns: every interval is an exception (x[2] ~ 300 k)
+        q = np.full(260, 4, np.uint8)
+        q[::2] = refn[1000 * k:1000 * k + 130]
+        reads.append(q)
+    reads += synth.simulate_reads(ref, 2000, 101, 0.02, seed=15, n_frac=0.05)
+    for k in range(50):                                                 # short reads: few, large intervals
+        reads.append(refn[5000 * k:5000 * k + 2 + k % 9].copy())
+    seq, offs = synth.to_batch(reads)
+    want = o.collect(seq, offs, OSeedOpt(), nthreads=4)
+    pr = sg.PackedReads(g.lib, seq, offs)
+    got = g.collect_packed12(pr)
+    assert got["pos_bits"] == 9 and len(got["exc"]) > 400 * 130        # (more than the list's first size: 1.5 entries per read of the handle)
+    assert np.array_equal(got["read_off"], want["read_off"]) and np.array_equal(got["intv"], want["intv"])
+    t = g.timing()
+    assert t["d2h_bytes"] == len(offs) * 4 - 4 + 12 * len(want["intv"]) + 12 * len(got["exc"])
+    # reads that outgrow their slots: the first 64 entries are placed by the first compaction, the whole list again by the re-run
+    g.set_param("slot_cap", 64)
+    try:
+        got = g.collect_packed12(pr)
+        assert g.timing()["overflow_reads"] >= 400
+        assert np.array_equal(got["read_off"], want["read_off"]) and np.array_equal(got["intv"], want["intv"])
+    finally:
+        g.set_param("slot_cap", 224)
+    # split form: resident 32-byte results -> 12-byte records; and 16-byte resident results are not converted silently
+    g.stage_packed(pr); tot = g.run_collect()
+    b = g.fetch_packed12(tot)
+    assert np.array_equal(b["intv"], want["intv"]) and np.array_equal(b["read_off"], want["read_off"])
+    g.collect_packed(pr)
+    g._n = pr.n
+    with pytest.raises(sg.SmemGpuError):
+        g.fetch_packed12(len(want["intv"]))
+    # pipeline lanes: exception indices are rebased onto the whole batch
+    g2 = sg.SmemGpu(max_batch_reads=8000, max_read_len=260, devices=[0, 0, 0])
+    g2.share_index_from(g)
+    got = g2.collect_packed12(pr)
+    assert np.array_equal(got["intv"], want["intv"]) and np.array_equal(got["read_off"], want["read_off"])
+    g2.close()
+    # capacity protocol
+    tot, ne, pb = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    roff = np.zeros(pr.n + 1, np.uint32)
+    rec = np.empty((len(want["intv"]), 3), np.uint32)
+    rc = g.lib.smem_gpu_collect_packed12(g.h, C.byref(pr.desc), C.byref(sg.SeedOpt()), C.c_void_p(rec.ctypes.data), C.c_int64(len(rec)),
+                                         C.c_void_p(roff.ctypes.data), None, C.c_int64(0), C.byref(ne), C.byref(pb), C.byref(tot))
+    assert rc == -5 and ne.value == len(got["exc"]) and tot.value == len(rec) and int(roff[-1]) == tot.value
 
 
 def test_errors_are_reported_not_aborted(world, synth):
