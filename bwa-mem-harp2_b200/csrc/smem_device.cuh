@@ -31,6 +31,7 @@ typedef unsigned int u32;
 
 struct DevIndex {
 	const uint4 *blk;   // re-packed 64-byte occ blocks in HBM
+	const uint4 *sec;   // the same index as self-contained 32-byte sectors (one lane per read, see extend_single); nullptr = not built
 	u64 primary;
 	u64 L2[5];
 	u64 seq_len;
@@ -235,6 +236,45 @@ __device__ __forceinline__ Ext extend_pair(const DevIndex &ix, u64 a, u64 b, u64
 	Ext o;
 	o.a = ix.L2[c] + 1 + __shfl_sync(FULL_MASK, tkc, owner);
 	o.s = __shfl_sync(FULL_MASK, szc, owner);
+	o.b = b + ((a <= ix.primary && a + s - 1 >= ix.primary) ? 1 : 0) + acc;
+	return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One LANE per read (seed_kernel<..., LPR = 1>).  Instruction issue, not the DRAM request rate, bounds the lane-pair kernel, and
+// two thirds of its instructions are the per-read state machine that both lanes of a pair execute in duplicate.  When every
+// base occurs fewer than 2^32 times the checkpoints fit 32 bits, and 64 symbols with their own four checkpoints fill exactly
+// one 32-byte sector:
+//   sector m = { uint32 cnt[4]      occurrences of A,C,G,T in symbols [0, 64 m)
+//                uint32 hi[2], lo[2] bit planes of symbols 64 m .. 64 m + 63 (as in the 64-byte block) }
+// (same 0.5 byte per symbol; built from the 64-byte blocks by sectors_from_blocks_kernel).  A lane then computes bwt_occ4 from
+// ONE 32-byte load = one DRAM request -- the request ceiling is per request, not per byte -- with no shuffles, and a warp
+// carries 32 reads instead of 16.
+__device__ __forceinline__ Ext extend_single(const DevIndex &ix, u64 a, u64 b, u64 s, int c, u32 (&w)[8], u32 (&v)[8],
+                                             const uint4 *alt = nullptr, const uint4 *alt2 = nullptr)
+{
+	const u64 k = a - 1, l = a - 1 + s;
+	const u64 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);   // '$' is not stored (bwt.c:194)
+	const u64 mk = kk >> 6, ml = ll >> 6;
+	const bool same = mk == ml && !alt2;
+	// `alt` / `alt2` (unique-walk phases): the gathers go to another table instead; the lane rides on the interval (1,1,1)
+	const uint4 *pk = alt ? alt : ix.sec + mk * 2, *pl = alt2 ? alt2 : ix.sec + ml * 2;
+	ld_sector(w, pk);
+	if (!same) ld_sector(v, pl);
+	if (same) {
+#pragma unroll
+		for (int j = 0; j < 8; ++j) v[j] = w[j];
+	}
+	const u32 ck = occ_half(w, (int)(kk & 63) + 1), cl = occ_half(v, (int)(ll & 63) + 1);   // symbols 0 .. kk & 63 of the sector count
+	const u32 tk0 = w[0] + (ck & 0xffu), tk1 = w[1] + ((ck >> 8) & 0xffu), tk2 = w[2] + ((ck >> 16) & 0xffu), tk3 = w[3] + (ck >> 24);
+	const u32 sz0 = v[0] + (cl & 0xffu) - tk0, sz1 = v[1] + ((cl >> 8) & 0xffu) - tk1, sz2 = v[2] + ((cl >> 16) & 0xffu) - tk2, sz3 = v[3] + (cl >> 24) - tk3;
+	// other strand: bases are laid out T,G,C,A after the optional '$' (bwt.c:425-428): sum the sizes of bases > c
+	const u64 acc = (u64)(c < 1 ? sz1 : 0u) + (u64)(c < 2 ? sz2 : 0u) + (u64)(c < 3 ? sz3 : 0u);
+	const u32 tkc = c == 0 ? tk0 : c == 1 ? tk1 : c == 2 ? tk2 : tk3;
+	const u32 szc = c == 0 ? sz0 : c == 1 ? sz1 : c == 2 ? sz2 : sz3;
+	Ext o;
+	o.a = ix.L2[c] + 1 + (u64)tkc;
+	o.s = (u64)szc;
 	o.b = b + ((a <= ix.primary && a + s - 1 >= ix.primary) ? 1 : 0) + acc;
 	return o;
 }

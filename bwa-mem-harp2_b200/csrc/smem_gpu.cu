@@ -29,6 +29,7 @@ struct DeviceCtx {
 	cudaEvent_t ev_sync = nullptr;   // blocking-sync event: host waits sleep instead of spinning (see stream_wait)
 	// index
 	uint4 *d_index = nullptr;
+	uint4 *d_sec = nullptr;          // the index as 32-byte sectors with 32-bit checkpoints (one lane per read); owned with d_index
 	size_t index_bytes = 0;
 	DevIndex ix{};
 	bool has_index = false;
@@ -132,6 +133,8 @@ struct smem_gpu {
 	int uw_isa_shift = 2;            // the inverse suffix array of the next smem_gpu_build_text_index is sampled every 2^this positions
 	int uw_min_left = 8, uw_min_run = 3;   // ... for walks with at least this many read bases left, after this many extends of a unique interval
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
+	int lanes_per_read = 1;          // 1 = one lane per read on the 32-byte sector index (when it exists), 2 = lane pairs on the 64-byte blocks
+	bool build_sectors = true;       // smem_gpu_upload_index also builds the sector form (when every checkpoint fits 32 bits)
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
 	int probe_variant = 0;
 	int force_wide = 0;
@@ -255,7 +258,7 @@ int ctx_init(DeviceCtx &d, int dev, int lane, int64_t read_cap, int max_len, int
 void ctx_free(DeviceCtx &d)
 {
 	cudaSetDevice(d.dev);
-	if (d.owns_index) cudaFree(d.d_index);
+	if (d.owns_index) { cudaFree(d.d_index); cudaFree(d.d_sec); }
 	if (d.owns_sa) cudaFree(d.d_sa);
 	if (d.owns_rf) cudaFree(d.d_rf);
 	if (d.owns_uw) { cudaFree(d.d_uw_text); cudaFree(d.d_fsa); cudaFree(d.d_isa); }
@@ -280,8 +283,8 @@ int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 	if (ix->seq_len == 0 || ix->bwt_size < (n_blocks - 1) * 16 + 8 + last_words) { d.err = "bwt_size is inconsistent with seq_len"; return SMEM_GPU_E_ARG; }
 	const size_t bytes = (size_t)ix->bwt_size * 4;
 	const size_t out_bytes = (size_t)(n_blocks + 1) * 64;            // one spare block keeps idle lanes in bounds
-	if (d.d_index && d.owns_index) CK(cudaFree(d.d_index));
-	d.d_index = nullptr; d.owns_index = true;
+	if (d.d_index && d.owns_index) { CK(cudaFree(d.d_index)); if (d.d_sec) CK(cudaFree(d.d_sec)); }
+	d.d_index = nullptr; d.d_sec = nullptr; d.owns_index = true;
 	d.has_index = false;
 	CK(cudaMalloc((void **)&d.d_index, out_bytes));
 	CK(cudaMemsetAsync((char *)d.d_index + out_bytes - 64, 0, 64, d.stream));
@@ -299,6 +302,16 @@ int ctx_upload_index(DeviceCtx &d, const smem_index_desc_t *ix, int src_device)
 	CK(stream_wait(d));
 	if (tmp) CK(cudaFree(tmp));
 	d.index_bytes = (size_t)n_blocks * 64;
+	// the sector form for the one-lane-per-read kernel: every checkpoint must fit 32 bits
+	bool narrow = d.owner->build_sectors;
+	for (int c = 0; c < 4; ++c) if (ix->L2[c + 1] - ix->L2[c] >= (1ull << 32)) narrow = false;
+	if (narrow) {
+		CK(cudaMalloc((void **)&d.d_sec, out_bytes));
+		sectors_from_blocks_kernel<<<(unsigned)((n_blocks + 1 + 255) / 256), 256, 0, d.stream>>>(d.d_index, n_blocks + 1, d.d_sec);
+		CK(cudaGetLastError());
+		CK(stream_wait(d));
+	}
+	d.ix.sec = d.d_sec;
 	d.ix.blk = d.d_index;
 	d.ix.primary = ix->primary;
 	for (int i = 0; i < 5; ++i) d.ix.L2[i] = ix->L2[i];
@@ -517,12 +530,32 @@ static const int kSeedBounds[] = {6, 8, 9};
 #endif
 
 template <int MODE, bool WIDE>
-int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem)
+int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, int lpr)
 {
+	if (lpr == 1) {          // one lane per read: 64-thread CTAs, as many as shared memory admits (nine at 101 bp); up to 112 registers
+		if constexpr (WIDE) { d.err = "one lane per read needs 32-bit occurrence counts"; return SMEM_GPU_E_INTERNAL; }
+		else {
+			CK(cudaFuncSetAttribute(seed_kernel<MODE, 9, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			seed_kernel<MODE, 9, false, 1><<<grid, SEED_BLOCK1, smem, d.stream>>>(p);
+			CK(cudaGetLastError());
+			++d.launches;
+			return 0;
+		}
+	}
+	if (lpr == 3) {          // lane pairs, each lane on the 32-byte sector form of the index
+		if constexpr (WIDE) { d.err = "the sector form needs 32-bit occurrence counts"; return SMEM_GPU_E_INTERNAL; }
+		else {
+			CK(cudaFuncSetAttribute(seed_kernel<MODE, 9, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			seed_kernel<MODE, 9, false, 2, true><<<grid, SEED_BLOCK, smem, d.stream>>>(p);
+			CK(cudaGetLastError());
+			++d.launches;
+			return 0;
+		}
+	}
 #define LAUNCH(B)                                                                                                         \
 	do {                                                                                                                  \
-		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-		seed_kernel<MODE, B, WIDE><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
+		CK(cudaFuncSetAttribute(seed_kernel<MODE, B, WIDE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+		seed_kernel<MODE, B, WIDE, 2><<<grid, SEED_BLOCK, smem, d.stream>>>(p);                                             \
 	} while (0)
 	switch (blocks_per_sm) {
 #ifdef SMEM_ALL_BOUNDS
@@ -545,15 +578,15 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 }
 
 template <int MODE>
-int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide)
+int launch_seed(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, bool wide, int lpr)
 {
-	return wide ? launch_seed_w<MODE, true>(d, p, blocks_per_sm, grid, smem) : launch_seed_w<MODE, false>(d, p, blocks_per_sm, grid, smem);
+	return wide ? launch_seed_w<MODE, true>(d, p, blocks_per_sm, grid, smem, 2) : launch_seed_w<MODE, false>(d, p, blocks_per_sm, grid, smem, lpr);
 }
 
-int launch_seed_mode(DeviceCtx &d, int mode, const SeedParams &p, int bps, int grid, size_t smem, bool wide)
+int launch_seed_mode(DeviceCtx &d, int mode, const SeedParams &p, int bps, int grid, size_t smem, bool wide, int lpr)
 {
-	return mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide)
-	     : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide) : launch_seed<MODE_TRACE>(d, p, bps, grid, smem, wide);
+	return mode == MODE_COLLECT ? launch_seed<MODE_COLLECT>(d, p, bps, grid, smem, wide, lpr)
+	     : mode == MODE_SMEM1 ? launch_seed<MODE_SMEM1>(d, p, bps, grid, smem, wide, lpr) : launch_seed<MODE_TRACE>(d, p, bps, grid, smem, wide, lpr);
 }
 
 // Several handles on one GPU (one per host thread, smem_gpu_share_index): the seed kernels of ONE call run as a block.
@@ -657,15 +690,16 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	// lane's scan / compaction kernels run next to the following lane's seed kernel (measured: with every SM
 	// occupied they wait for it to drain, even when CTA slots are free)
 	const int spare = d.lanes_on_dev > 1 ? std::min(h.spare_sms, d.sm_count / 4) : 0;
-	const int max_grid = d.sm_count * bps;
-	const int pairs_per_cta = SEED_BLOCK / 2;
-	const int grid = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * bps, (d.n + pairs_per_cta - 1) / pairs_per_cta);
-	const int scratch_cap = h.max_len + 2;
-	const size_t need = (size_t)std::min<int64_t>(max_grid, (d.read_cap + pairs_per_cta - 1) / pairs_per_cta + 1) * pairs_per_cta * 3 * scratch_cap;
 	// 16-byte packed prev/curr entries need every SA coordinate < 2^36 and read positions < 2^20
 	// ... and the 32-bit occurrence counts of the narrow extend need every base to occur fewer than 2^32 times
 	bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
 	for (int c = 0; c < 4; ++c) if (d.ix.L2[c + 1] - d.ix.L2[c] >= (1ull << 32)) wide = true;
+	const int lpr = (h.lanes_per_read != 2 && !wide && d.ix.sec) ? h.lanes_per_read : 2;      // 3 = lane pairs on the sector index
+	const int pairs_per_cta = lpr == 1 ? SEED_BLOCK1 : SEED_BLOCK / 2;            // reads in flight per CTA
+	const int max_grid = d.sm_count * std::max(bps, 9);                              // (the one-lane kernel runs up to nine CTAs per SM whatever bps says)
+	const int grid = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * (lpr != 2 ? 9 : bps), (d.n + pairs_per_cta - 1) / pairs_per_cta);
+	const int scratch_cap = h.max_len + 2;
+	const size_t need = (size_t)std::min<int64_t>(max_grid, (d.read_cap + pairs_per_cta - 1) / pairs_per_cta + 1) * pairs_per_cta * 3 * scratch_cap;
 	const int q_stride = ((h.max_len + 1) / 2 + 15) / 16 * 16;      // two bases per byte; keeps pair_stride a multiple of 16
 	// b_cap is honoured even if that leaves room for fewer CTAs per SM than blocks_per_sm asks for (the
 	// hardware then simply runs fewer); it only shrinks when a single CTA would not fit at all.
@@ -766,7 +800,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	}
 	int rc = 0;
 	CK(cudaEventRecord(d.ev0s, d.stream));          // after the pack pre-pass: seed_ms is the seed kernel's own duration
-	rc = launch_seed_mode(d, mode, p, bps, grid, smem, wide);
+	rc = launch_seed_mode(d, mode, p, bps, grid, smem, wide, lpr);
 	if (rc) return rc;
 	CK(cudaEventRecord(d.ev1, d.stream));
 	lane_mark_issued(d, h);
@@ -853,7 +887,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 				p2.n = n_over; p2.list = d.d_overflow; p2.slots = d.d_big; p2.slot_cap = big_cap; p2.counts = d.d_counts_k;
 				p2.overflow_list = d.d_counts_k + n_over;
 				const int grid2 = (int)std::min<int64_t>(std::min<int64_t>(max_grid, (int64_t)d.sm_count * 4), (n_over + pairs_per_cta - 1) / pairs_per_cta);
-				rc = launch_seed_mode(d, mode, p2, bps, grid2, smem, wide);
+				rc = launch_seed_mode(d, mode, p2, bps, grid2, smem, wide, lpr);
 				if (rc) return rc;
 				CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 				CK(stream_wait(d));
@@ -1486,8 +1520,8 @@ static int upload_all(smem_gpu_t *h, const smem_index_desc_t *ix, int src_device
 		for (auto &o : h->devs) {
 			if (&o == &d) break;
 			if (o.dev == d.dev) {
-				if (d.d_index && d.owns_index) { cudaSetDevice(d.dev); cudaFree(d.d_index); }
-				d.d_index = o.d_index; d.owns_index = false; d.index_bytes = o.index_bytes; d.ix = o.ix; d.has_index = true;
+				if (d.d_index && d.owns_index) { cudaSetDevice(d.dev); cudaFree(d.d_index); cudaFree(d.d_sec); }
+				d.d_index = o.d_index; d.d_sec = o.d_sec; d.owns_index = false; d.index_bytes = o.index_bytes; d.ix = o.ix; d.has_index = true;
 				break;
 			}
 		}
@@ -1514,9 +1548,9 @@ int smem_gpu_share_index(smem_gpu_t *dst, const smem_gpu_t *src)
 		for (auto &c : src->devs) if (c.dev == d.dev && c.has_index) { o = &c; break; }
 		if (!o) { dst->err = "source handle has no index on device " + std::to_string(d.dev); return SMEM_GPU_E_NOINDEX; }
 		cudaSetDevice(d.dev);
-		if (d.d_index && d.owns_index) cudaFree(d.d_index);
+		if (d.d_index && d.owns_index) { cudaFree(d.d_index); cudaFree(d.d_sec); }
 		if (d.d_sa && d.owns_sa) cudaFree(d.d_sa);
-		d.d_index = o->d_index; d.owns_index = false; d.index_bytes = o->index_bytes; d.ix = o->ix; d.has_index = true;
+		d.d_index = o->d_index; d.d_sec = o->d_sec; d.owns_index = false; d.index_bytes = o->index_bytes; d.ix = o->ix; d.has_index = true;
 		d.d_sa = o->d_sa; d.owns_sa = false; d.sa_shift = o->sa_shift; d.n_sa = o->n_sa;
 		if (d.d_rf && d.owns_rf) cudaFree(d.d_rf);
 		d.d_rf = o->d_rf; d.owns_rf = false; d.rf_k = o->rf_k; d.rf_log2 = o->rf_log2; d.rf_text_len = o->rf_text_len;
@@ -1853,6 +1887,8 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "unique_walk_min_run")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_run = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_min_left")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_left = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_isa_shift")) { if (v < 0 || v > 6) return SMEM_GPU_E_ARG; h->uw_isa_shift = (int)v; return 0; }
+	if (!strcmp(name, "lanes_per_read")) { if (v < 1 || v > 3) return SMEM_GPU_E_ARG; h->lanes_per_read = (int)v; return 0; }
+	if (!strcmp(name, "build_sectors")) { h->build_sectors = v != 0; return 0; }          // takes effect at the next smem_gpu_upload_index
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
 	if (!strcmp(name, "acc_reset")) { for (auto &d : h->devs) { d.acc_stage_ms = d.acc_turn_ms = d.acc_run_ms = d.acc_fetch_ms = 0; d.acc_calls = d.acc_h2d = d.acc_d2h = 0; } return 0; }
 	if (!strcmp(name, "probe_variant")) { if (v < 0 || (v > 15 && v != 20)) return SMEM_GPU_E_ARG; h->probe_variant = (int)v; return 0; }
@@ -1906,7 +1942,7 @@ int64_t smem_gpu_get_param(const smem_gpu_t *h, const char *name)
 	// HBM held by the optional accelerator tables of device 0 (repeat filter + unique-walk tables) and by the index itself
 	if (!strcmp(name, "table_bytes")) { const DeviceCtx &d = h->devs[0]; return (int64_t)((d.d_rf ? (size_t)1 << (d.rf_log2 - 3) : 0) + d.uw_bytes); }
 	if (!strcmp(name, "uw_table_bytes")) return (int64_t)h->devs[0].uw_bytes;
-	if (!strcmp(name, "index_bytes")) return (int64_t)h->devs[0].index_bytes;
+	if (!strcmp(name, "index_bytes")) return (int64_t)h->devs[0].index_bytes * (h->devs[0].d_sec ? 2 : 1);   // (64-byte blocks + the 32-byte sector form)
 	return SMEM_GPU_E_ARG;
 }
 

@@ -12,7 +12,10 @@ enum { PH_FWD = 0, PH_BWD = 1, PH_SPEC = 2 /* backward walk of the longest candi
 #define AUX_SHIFT 16         // ... and, in TRACE mode, bwt_smem1's return value in bits 16..31 (query positions are < 2^16)
 #define INFO_MASK 0x0000ffff0000ffffull
 #ifndef SEED_BLOCK
-#define SEED_BLOCK 128       // threads per CTA of the seeding kernel (= 64 lane pairs = 64 reads in flight)
+#define SEED_BLOCK 128       // threads per CTA of the lane-pair seeding kernel (= 64 lane pairs = 64 reads in flight)
+#endif
+#ifndef SEED_BLOCK1
+#define SEED_BLOCK1 64       // threads per CTA of the one-lane-per-read kernel (= 64 reads in flight; nine CTAs per SM by shared memory)
 #endif
 
 // per-pair shared memory: [B entries | cold state | query, two bases per byte]
@@ -21,7 +24,10 @@ enum { CS_RK = 0, CS_RID = 4, CS_NOUT = 8, CS_MAXS_LO = 12, CS_MAXS_HI = 16,
        CS_START = 20, CS_STEP = 22, CS_ORI = 24, CS_SPLIT = 26, CS_PASS = 28, CS_X = 30, CS_NMEM = 32, CS_LMS = 34, CS_NM1 = 36,
        CS_KEEP = 38, CS_MAXLEN = 40, CS_MAXSTART = 42, CS_MAXEND = 44, CS_RET = 46, COLD_BYTES = 48 };
 
-__device__ __forceinline__ u32 qbase(u32 sq, int i) { return (lds_u8(sq + ((u32)i >> 1)) >> ((i & 1) * 4)) & 15u; }
+// Shared-memory address of byte `off` of a read's private area.  Lane pairs (LPR 2): the area is contiguous at sp.  One lane per
+// read (LPR 1): the 32 areas of a warp are interleaved in 16-byte units (unit u of lane t at warp base + 512 u + 16 t, sp = warp
+// base + 16 t), so that the same unit of 32 reads covers all banks: data-dependent indices differ per lane, the bank does not.
+template <int LPR> __device__ __forceinline__ u32 sh_at(u32 sp, u32 off) { return LPR == 2 ? sp + off : sp + ((off >> 4) << 9) + (off & 15u); }
 __device__ __noinline__ void bx_put(Intv *p, u64 x0, u64 x1, u64 x2, u32 end) { st_intv(p, x0, x1, x2, (u64)end); }
 __device__ __noinline__ Intv bx_get(const Intv *p) { return ld_intv(p); }
 
@@ -39,28 +45,39 @@ __device__ __noinline__ Intv bx_get(const Intv *p) { return ld_intv(p); }
 //   global : M1, M2 = `matches` / `sub` of smem_next2 in emission order (descending start), each of
 //            scratch_cap = max_read_len + 2 entries, which bounds every list of bwt.c:776-835.
 //            BX = the entries of B beyond b_cap (only the deepest forward passes reach them).
-template <int MODE, int MIN_BLOCKS, bool WIDE>
-__global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const SeedParams p)
+//
+// LPR = lanes per read: 2 = the lane pair described above (any index); 1 = one lane per read on the 32-byte sector form of the
+// index (extend_single, smem_device.cuh; needs 32-bit occurrence counts, i.e. !WIDE) -- the same state machine, but a warp
+// carries 32 reads, nothing is executed in duplicate and nothing is shuffled.
+// SEC (LPR 2 only): both lanes of the pair run extend_single on the same 32-byte sector -- identical addresses, still one request --
+// instead of sharing a 64-byte block: no shuffles, a third fewer instructions in the extend.
+template <int MODE, int MIN_BLOCKS, bool WIDE, int LPR, bool SEC = false>
+__global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
+	static_assert((LPR == 2 && !SEC) || !WIDE, "the 32-bit sector form of the index needs 32-bit occurrence counts");
 	const bool SPEC = MODE != MODE_SMEM1 && p.spec_walk;     // speculative longest-only backward walk (PH_SPEC)
 	typedef BEntry<WIDE> BE;
 	extern __shared__ uint4 smem_raw[];
-	const int lane = threadIdx.x & 31, half = lane & 1;
-	const int pair = threadIdx.x >> 1;
-	u32 sp = (u32)__cvta_generic_to_shared(smem_raw) + (u32)pair * (u32)p.pair_stride;   // this pair's shared memory
+	const int lane = threadIdx.x & 31, half = LPR == 2 ? lane & 1 : 0;
+	const int pair = LPR == 2 ? threadIdx.x >> 1 : threadIdx.x;      // the read slot of this CTA the thread works for
+	const u32 pm2 = LPR == 2 ? 3u << (lane & ~1) : 1u << lane;       // the lanes that carry this read
+	u32 sp = (u32)__cvta_generic_to_shared(smem_raw) +
+	         (LPR == 2 ? (u32)pair * (u32)p.pair_stride : (u32)(threadIdx.x >> 5) * 32u * (u32)p.pair_stride + (u32)lane * 16u);   // this read's shared memory (sh_at)
 #ifdef SEED_KEEP_SP
 	asm volatile("" : "+r"(sp));                             // opaque: kept in its register instead of being re-derived from the thread id at every use
 #endif
 	// cold state first, then B, then the query: the cold-state and B addresses are sp + a compile-time constant
-	const u32 sc = sp;                                       // cold state
-	const u32 sb = sp + COLD_BYTES;                          // B entries (16-byte aligned)
-	const u32 sq = sb + (u32)p.b_cap * BE::BYTES;            // query, two bases per byte
+	auto SC = [&](u32 off) -> u32 { return sh_at<LPR>(sp, off); };                             // cold state
+	auto SB = [&](int idx) -> u32 { return LPR == 2 ? sp + COLD_BYTES + (u32)idx * BE::BYTES : sp + ((u32)(COLD_BYTES / 16 + idx) << 9); };   // B entries (16-byte aligned)
+	const u32 sq = sh_at<LPR>(sp, COLD_BYTES + (u32)p.b_cap * BE::BYTES);                      // query, two bases per byte (a multiple of 16 bytes from sp)
+	auto QBYTE = [&](u32 byte) -> u32 { return LPR == 2 ? sq + byte : sq + ((byte >> 4) << 9) + (byte & 15u); };
+	auto qbase = [&](int i) -> u32 { return (lds_u8(QBYTE((u32)i >> 1)) >> ((i & 1) * 4)) & 15u; };
 #ifdef SEED_KEEP_GP
-	u32 gp3 = (u32)(blockIdx.x * (SEED_BLOCK / 2) + pair) * 3u;
+	u32 gp3 = (u32)(blockIdx.x * ((LPR == 2 ? SEED_BLOCK : SEED_BLOCK1) / LPR) + pair) * 3u;
 	asm volatile("" : "+r"(gp3));                            // opaque, one register: the scratch base is two multiply-adds away instead of a dozen instructions
 	auto scratch_base = [&]() -> Intv * { return p.scratch + (size_t)gp3 * (size_t)p.scratch_cap; };
 #else
-	Intv *const M1s = p.scratch + (size_t)(blockIdx.x * (SEED_BLOCK / 2) + pair) * 3 * p.scratch_cap;
+	Intv *const M1s = p.scratch + (size_t)(blockIdx.x * ((LPR == 2 ? SEED_BLOCK : SEED_BLOCK1) / LPR) + pair) * 3 * p.scratch_cap;
 	auto scratch_base = [&]() -> Intv * { return M1s; };   // (forcing this out of the main loop with volatile reads cost spills: slower)
 #endif
 
@@ -75,25 +92,25 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	// B beyond b_cap spills to global memory through an out-of-line slow path: one compare + a branch that is
 	// (almost) never taken on the hot path, and correctness never depends on b_cap
 	auto b_put = [&](int idx, u64 x0, u64 x1, u64 x2, u32 end) {
-		if (__builtin_expect(idx < p.b_cap, 1)) BE::put(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		if (__builtin_expect(idx < p.b_cap, 1)) BE::put(SB(idx), x0, x1, x2, end);
 		else bx_put(scratch_base() + 2 * p.scratch_cap + idx, x0, x1, x2, end);
 	};
 	auto b_get = [&](int idx, u64 &x0, u64 &x1, u64 &x2, u32 &end) {
-		if (__builtin_expect(idx < p.b_cap, 1)) BE::get(sb + (u32)idx * BE::BYTES, x0, x1, x2, end);
+		if (__builtin_expect(idx < p.b_cap, 1)) BE::get(SB(idx), x0, x1, x2, end);
 		else { const Intv t = bx_get(scratch_base() + 2 * p.scratch_cap + idx); x0 = t.x0; x1 = t.x1; x2 = t.x2; end = (u32)t.info; }
 	};
 	// bwt.c:815-820: a hit that cannot be extended is recorded unless a longer match already covers it
 	auto emit = [&](u64 x0, u64 x1, u64 x2, u32 end, int st) {
-		const int n_mem = lds_u16(sc + CS_NMEM);
-		if (n_mem == 0 || st < lds_u16(sc + CS_LMS)) {
-			Intv *M = scratch_base() + (size_t)lds_u16(sc + CS_PASS) * p.scratch_cap;
+		const int n_mem = lds_u16(SC(CS_NMEM));
+		if (n_mem == 0 || st < lds_u16(SC(CS_LMS))) {
+			Intv *M = scratch_base() + (size_t)lds_u16(SC(CS_PASS)) * p.scratch_cap;
 			st_intv(&M[n_mem], x0, x1, x2, (u64)end | ((u64)st << 32));
-			sts_u16(sc + CS_NMEM, n_mem + 1);
-			sts_u16(sc + CS_LMS, st);
+			sts_u16(SC(CS_NMEM), n_mem + 1);
+			sts_u16(SC(CS_LMS), st);
 			const int l = (int)end - st;
-			if (l >= lds_u16(sc + CS_MAXLEN)) {          // ">=": the first maximum in ascending start order wins (bwamem.c:266-270)
-				sts_u16(sc + CS_MAXLEN, l); sts_u16(sc + CS_MAXSTART, st); sts_u16(sc + CS_MAXEND, (int)end);
-				sts_i32(sc + CS_MAXS_LO, (int)(u32)x2); sts_i32(sc + CS_MAXS_HI, (int)(u32)(x2 >> 32));
+			if (l >= lds_u16(SC(CS_MAXLEN))) {          // ">=": the first maximum in ascending start order wins (bwamem.c:266-270)
+				sts_u16(SC(CS_MAXLEN), l); sts_u16(SC(CS_MAXSTART), st); sts_u16(SC(CS_MAXEND), (int)end);
+				sts_i32(SC(CS_MAXS_LO), (int)(u32)x2); sts_i32(SC(CS_MAXS_HI), (int)(u32)(x2 >> 32));
 			}
 		}
 	};
@@ -109,6 +126,13 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 	u32 blk_k[8], blk_l[8];              // this lane's sectors of the K / L occ blocks (see extend_pair)
 #pragma unroll
 	for (int t = 0; t < 8; ++t) blk_k[t] = blk_l[t] = 0;
+	// One lane per read: a warp waits for every global round trip that any of its 32 reads makes in the cold section, so those are
+	// taken off the critical path -- the next read's work index is drawn while the current read is being seeded (rk_pref), a new
+	// read's length, bases and repeat-filter flags arrive in ONE round trip (flags kept in registers), and result lists are copied
+	// four entries per round trip.
+	int rk_pref = 0;
+	u32 qf0 = 0, qf1 = 0, qf2 = 0, qf3 = 0;          // the read's window flags (repeat filter) when they fit four words
+	if (LPR == 1) rk_pref = atomicAdd(&p.status[0], 1);
 
 	for (;;) {
 		__syncwarp();
@@ -117,60 +141,96 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			switch (phase) {
 			case PH_NEED_READ: {
 				int rk = 0;
-				if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(sc + CS_RK, rk); }
-				__syncwarp(3u << (lane & ~1));
-				rk = lds_i32(sc + CS_RK);
-				if ((long long)rk >= p.n) { phase = PH_IDLE; break; }
-				const int rid = p.list ? p.list[rk] : rk;
-				len = p.rlen[rid];
-				{                                                            // staged by pack_reads_kernel: 16 bytes (32 bases) per copy
-					const uint4 *src = p.qpack + (size_t)rid * (size_t)(p.q_stride >> 4);
-					for (int t = half; 32 * t < len; t += 2) sts_v4(sq + 16 * t, __ldg(src + t));
+				if (LPR == 1) { rk = rk_pref; sts_i32(SC(CS_RK), rk); }
+				else {
+					if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(SC(CS_RK), rk); }
+					__syncwarp(pm2); rk = lds_i32(SC(CS_RK));
 				}
-				__syncwarp(3u << (lane & ~1));
-				sts_i32(sc + CS_RID, rid); sts_i32(sc + CS_NOUT, 0); sts_u16(sc + CS_START, 0); sts_u16(sc + CS_STEP, 0);
+				if ((long long)rk >= p.n) { phase = PH_IDLE; break; }
+				if (LPR == 1) rk_pref = atomicAdd(&p.status[0], 1);        // (needed at the next PH_NEED_READ, a few hundred extends from here)
+				const int rid = p.list ? p.list[rk] : rk;
+				if (LPR == 1) {
+					// length, the first 128 bases and the window flags: issued together, one round trip
+					const int cpr = p.q_stride >> 4;
+					const uint4 *src = p.qpack + (size_t)rid * (size_t)cpr;
+					const int len_ = p.rlen[rid];
+					uint4 ch0 = __ldg(src), ch1 = ch0, ch2 = ch0, ch3 = ch0;
+					if (cpr > 1) ch1 = __ldg(src + 1);
+					if (cpr > 2) ch2 = __ldg(src + 2);
+					if (cpr > 3) ch3 = __ldg(src + 3);
+					if (p.qflags && cpr <= 4) {
+						const u32 *fl = p.qflags + (size_t)rid * (size_t)cpr;
+						qf0 = __ldg(fl);
+						if (cpr > 1) qf1 = __ldg(fl + 1);
+						if (cpr > 2) qf2 = __ldg(fl + 2);
+						if (cpr > 3) qf3 = __ldg(fl + 3);
+					}
+					len = len_;
+					sts_v4(sq, ch0);
+					if (len > 32) sts_v4(sq + (1u << 9), ch1);
+					if (len > 64) sts_v4(sq + (2u << 9), ch2);
+					if (len > 96) sts_v4(sq + (3u << 9), ch3);
+					for (int t0 = 4; 32 * t0 < len; t0 += 4) {               // longer reads: four chunks per round trip
+						ch0 = __ldg(src + t0);
+						if (32 * (t0 + 1) < len) ch1 = __ldg(src + t0 + 1);
+						if (32 * (t0 + 2) < len) ch2 = __ldg(src + t0 + 2);
+						if (32 * (t0 + 3) < len) ch3 = __ldg(src + t0 + 3);
+						sts_v4(sq + ((u32)t0 << 9), ch0);
+						if (32 * (t0 + 1) < len) sts_v4(sq + ((u32)(t0 + 1) << 9), ch1);
+						if (32 * (t0 + 2) < len) sts_v4(sq + ((u32)(t0 + 2) << 9), ch2);
+						if (32 * (t0 + 3) < len) sts_v4(sq + ((u32)(t0 + 3) << 9), ch3);
+					}
+				} else {
+					len = p.rlen[rid];
+					{                                                            // staged by pack_reads_kernel: 16 bytes (32 bases) per copy
+						const uint4 *src = p.qpack + (size_t)rid * (size_t)(p.q_stride >> 4);
+						for (int t = half; 32 * t < len; t += 2) sts_v4(sq + 16 * t, __ldg(src + t));
+					}
+					__syncwarp(pm2);
+				}
+				sts_i32(SC(CS_RID), rid); sts_i32(SC(CS_NOUT), 0); sts_u16(SC(CS_START), 0); sts_u16(SC(CS_STEP), 0);
 				if (MODE != MODE_SMEM1) {
-					sts_u16(sc + CS_SPLIT, p.split_len_init < len ? p.split_len_init : len);     // bwamem.c:458
+					sts_u16(SC(CS_SPLIT), p.split_len_init < len ? p.split_len_init : len);     // bwamem.c:458
 					phase = PH_NEXT_STEP;
 				} else {
 					const int x = p.xs[rid], mi = p.min_intvs[rid];
 					min_intv = mi < 1 ? 1u : (u32)mi;                                            // bwt.c:784
-					sts_u16(sc + CS_PASS, 0); sts_u16(sc + CS_X, x);
-					if (x < 0 || x >= len || qbase(sq, x) > 3) {                                // bwt.c:783
+					sts_u16(SC(CS_PASS), 0); sts_u16(SC(CS_X), x);
+					if (x < 0 || x >= len || qbase(x) > 3) {                                // bwt.c:783
 						p.ret[rid] = x + 1; p.counts[rk] = 0; phase = PH_NEED_READ;
 					} else phase = PH_INIT_CALL;
 				}
 			} break;
 			case PH_NEXT_STEP: {     // head of smem_next2, bwamem.c:249-258
-				int start = lds_u16(sc + CS_START);
+				int start = lds_u16(SC(CS_START));
 				// Speculative walk (see PH_FWD_DONE): the previous pass-1 call at CS_ORI ended its forward sweep at `start` because
 				// q[CS_ORI .. start] occurs fewer than start_width times; that bounds the coming backward sweep at CS_ORI.
-				const int lim1 = (SPEC && lds_u16(sc + CS_STEP) > 0 && start < len && qbase(sq, start) <= 3) ? lds_u16(sc + CS_ORI) + 1 : 0;
-				while (start < len && qbase(sq, start) > 3) ++start;
+				const int lim1 = (SPEC && lds_u16(SC(CS_STEP)) > 0 && start < len && qbase(start) <= 3) ? lds_u16(SC(CS_ORI)) + 1 : 0;
+				while (start < len && qbase(start) > 3) ++start;
 				if (start >= len) {
-					const int rk = lds_i32(sc + CS_RK), n_out = lds_i32(sc + CS_NOUT);
+					const int rk = lds_i32(SC(CS_RK)), n_out = lds_i32(SC(CS_NOUT));
 					p.counts[rk] = n_out;
-					if (n_out > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(sc + CS_RID); atomicMax(&p.status[3], n_out); }
+					if (n_out > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = lds_i32(SC(CS_RID)); atomicMax(&p.status[3], n_out); }
 					phase = PH_NEED_READ;
 					break;
 				}
-				sts_u16(sc + CS_START, start); sts_u16(sc + CS_ORI, start); sts_u16(sc + CS_X, start); sts_u16(sc + CS_PASS, 0);
-				if (SPEC) sts_u16(sc + CS_KEEP, lim1);       // (CS_KEEP is otherwise only used by the merge after a re-seeding pass)
+				sts_u16(SC(CS_START), start); sts_u16(SC(CS_ORI), start); sts_u16(SC(CS_X), start); sts_u16(SC(CS_PASS), 0);
+				if (SPEC) sts_u16(SC(CS_KEEP), lim1);       // (CS_KEEP is otherwise only used by the merge after a re-seeding pass)
 				min_intv = p.start_width < 1 ? 1u : (u32)p.start_width;
 				phase = PH_INIT_CALL;
 			} break;
 			case PH_INIT_CALL: {     // bwt_set_intv, bwt.c:788-789, then the head of the forward loop
-				const int x = lds_u16(sc + CS_X);
-				const int c0 = (int)qbase(sq, x);
+				const int x = lds_u16(SC(CS_X));
+				const int c0 = (int)qbase(x);
 				a = p.ix.L2[3 - c0] + 1;             // is_back = 0 walks x[1]
 				b = p.ix.L2[c0] + 1;
 				s = p.ix.L2[c0 + 1] - p.ix.L2[c0];
 				end = (u32)(x + 1);
 				i = x + 1; n_curr = 0; j = 0;
-				sts_u16(sc + CS_NMEM, 0); sts_u16(sc + CS_MAXLEN, 0); sts_u16(sc + CS_MAXSTART, 0); sts_u16(sc + CS_MAXEND, 0);
-				sts_i32(sc + CS_MAXS_LO, 0); sts_i32(sc + CS_MAXS_HI, 0);
+				sts_u16(SC(CS_NMEM), 0); sts_u16(SC(CS_MAXLEN), 0); sts_u16(SC(CS_MAXSTART), 0); sts_u16(SC(CS_MAXEND), 0);
+				sts_i32(SC(CS_MAXS_LO), 0); sts_i32(SC(CS_MAXS_HI), 0);
 				guard = (int)min(2ll * (len + 2) * (len + 2) + 64, 0x7fffffffll);   // > every extend one bwt_smem1 can issue (saturates for reads beyond 32 k bases)
-				const u32 qv = i < len ? qbase(sq, i) : 4u;
+				const u32 qv = i < len ? qbase(i) : 4u;
 				if (qv > 3) phase = PH_FWD_END;
 				else { c = 3 - (int)qv; phase = PH_FWD; }     // bwt.c:793: forward extension uses the complement
 			} break;
@@ -180,20 +240,20 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			} break;
 			case PH_FWD_DONE: {      // bwt.c:807-809: "reverse curr" == address B from its top (n0 - 1 - j)
 				n0 = n_curr; n_prev = n_curr; n_curr = 0;
-				i = lds_u16(sc + CS_X) - 1; j = 0;
-				c = i < 0 ? -1 : (int)qbase(sq, i);
+				i = lds_u16(SC(CS_X)) - 1; j = 0;
+				c = i < 0 ? -1 : (int)qbase(i);
 				if (c > 3) c = -1;
 				b_get(n0 - 1, a, b, s, end);             // prev[0] = the last push; its info is bwt_smem1's return value
-				sts_u16(sc + CS_RET, (int)end);
-				if (MODE != MODE_SMEM1 && lds_u16(sc + CS_PASS) == 0) sts_u16(sc + CS_START, (int)end);   // bwamem.c:262
+				sts_u16(SC(CS_RET), (int)end);
+				if (MODE != MODE_SMEM1 && lds_u16(SC(CS_PASS)) == 0) sts_u16(SC(CS_START), (int)end);   // bwamem.c:262
 				phase = c < 0 ? PH_BWD_LAST : PH_BWD;
 				// Every candidate of this sweep whose start reaches lim = CS_KEEP - 1 contains a pattern known to be too rare, so the
 				// sweep ends there with everything dead; and while the LONGEST candidate (a, b, s) lives nothing is emitted
 				// (bwt.c:815: curr->n != 0).  So walk it back alone: if it lives down to start lim + 1 (or to an ambiguous base /
 				// the read start, where everything dies too) it is the call's only result and the shorter candidates never needed
 				// extending; if it dies earlier the full sweep starts over (PH_SPEC in the main loop).  Model: oracle/smem_oracle.c.
-				if (SPEC && phase == PH_BWD && lds_u16(sc + CS_PASS) == 0 && lds_u16(sc + CS_KEEP) > 0) {
-					if (i < lds_u16(sc + CS_KEEP)) phase = PH_BWD_LAST;      // no round left before the limit: (i + 1, end) is the result
+				if (SPEC && phase == PH_BWD && lds_u16(SC(CS_PASS)) == 0 && lds_u16(SC(CS_KEEP)) > 0) {
+					if (i < lds_u16(SC(CS_KEEP))) phase = PH_BWD_LAST;      // no round left before the limit: (i + 1, end) is the result
 					else phase = PH_SPEC;
 				}
 			} break;
@@ -204,75 +264,100 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 				phase = PH_CALL_DONE;
 			} break;
 			case PH_CALL_DONE: {
-				const int rk = lds_i32(sc + CS_RK), n_mem = lds_u16(sc + CS_NMEM);
+				const int rk = lds_i32(SC(CS_RK)), n_mem = lds_u16(SC(CS_NMEM));
 				Intv *const slot = p.slots + (size_t)rk * p.slot_cap;
 				const Intv *const M1 = scratch_base();
 				const Intv *const M2 = M1 + p.scratch_cap;
 				if (MODE == MODE_SMEM1) {
-					const int rid = lds_i32(sc + CS_RID);
+					const int rid = lds_i32(SC(CS_RID));
 					for (int e = n_mem - 1, o = 0; e >= 0; --e, ++o)             // bwt.c:829: ascending start
 						if (o < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[o], t.x0, t.x1, t.x2, t.info); }
-					p.counts[rk] = n_mem; p.ret[rid] = lds_u16(sc + CS_RET);
+					p.counts[rk] = n_mem; p.ret[rid] = lds_u16(SC(CS_RET));
 					if (n_mem > p.slot_cap && !half) { p.overflow_list[atomicAdd(&p.status[1], 1)] = rid; atomicMax(&p.status[3], n_mem); }
 					phase = PH_NEED_READ;
 					break;
 				}
-				const int step = lds_u16(sc + CS_STEP);
-				int n_out = lds_i32(sc + CS_NOUT);
+				const int step = lds_u16(SC(CS_STEP));
+				int n_out = lds_i32(SC(CS_NOUT));
 				if (MODE == MODE_TRACE) {
 					// what two successive DO calls of bwt_smem1_batched return (bwt.c:719-749): the raw list of this
 					// bwt_smem1 (ascending start) tagged step*2 + pass, with its return value alongside
-					const int pass = lds_u16(sc + CS_PASS);
-					const u64 ttag = ((u64)(step * 2 + pass) << STEP_SHIFT) | ((u64)(u32)lds_u16(sc + CS_RET) << AUX_SHIFT);
+					const int pass = lds_u16(SC(CS_PASS));
+					const u64 ttag = ((u64)(step * 2 + pass) << STEP_SHIFT) | ((u64)(u32)lds_u16(SC(CS_RET)) << AUX_SHIFT);
 					const Intv *const Mp = M1 + (size_t)pass * p.scratch_cap;
 					for (int e = n_mem - 1; e >= 0; --e) {
 						if (n_out < p.slot_cap) { const Intv t = ld_intv(&Mp[e]); st_intv(&slot[n_out], t.x0, t.x1, t.x2, t.info | ttag); }
 						++n_out;
 					}
-					sts_i32(sc + CS_NOUT, n_out);
+					sts_i32(SC(CS_NOUT), n_out);
 					if (pass == 0) {
-						const int max_len = lds_u16(sc + CS_MAXLEN), split_len = lds_u16(sc + CS_SPLIT);
-						const u64 max_s = (u64)(u32)lds_i32(sc + CS_MAXS_LO) | ((u64)(u32)lds_i32(sc + CS_MAXS_HI) << 32);
+						const int max_len = lds_u16(SC(CS_MAXLEN)), split_len = lds_u16(SC(CS_SPLIT));
+						const u64 max_s = (u64)(u32)lds_i32(SC(CS_MAXS_LO)) | ((u64)(u32)lds_i32(SC(CS_MAXS_HI)) << 32);
 						if (n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width) {   // bwamem.c:272
-							sts_u16(sc + CS_PASS, 1);
-							sts_u16(sc + CS_X, (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1);
+							sts_u16(SC(CS_PASS), 1);
+							sts_u16(SC(CS_X), (lds_u16(SC(CS_MAXEND)) + lds_u16(SC(CS_MAXSTART))) >> 1);
 							min_intv = (u32)max_s + 1u;
 							phase = PH_INIT_CALL;
 							break;
 						}
 					}
-					sts_u16(sc + CS_STEP, step + 1);
+					sts_u16(SC(CS_STEP), step + 1);
 					phase = PH_NEXT_STEP;
 					break;
 				}
 				const u64 tag = (u64)step << STEP_SHIFT;
-				if (lds_u16(sc + CS_PASS) == 0) {
-					const int max_len = lds_u16(sc + CS_MAXLEN), split_len = lds_u16(sc + CS_SPLIT);
-					const u64 max_s = (u64)(u32)lds_i32(sc + CS_MAXS_LO) | ((u64)(u32)lds_i32(sc + CS_MAXS_HI) << 32);
+				if (lds_u16(SC(CS_PASS)) == 0) {
+					const int max_len = lds_u16(SC(CS_MAXLEN)), split_len = lds_u16(SC(CS_SPLIT));
+					const u64 max_s = (u64)(u32)lds_i32(SC(CS_MAXS_LO)) | ((u64)(u32)lds_i32(SC(CS_MAXS_HI)) << 32);
 					// bwamem.c:272: re-seed from the middle of the longest SMEM if it is long and (nearly) unique -- unless the
 					// repeat filter proves that the second pass cannot contribute (smem_repeat.cuh)
 					bool reseed = n_mem > 0 && split_len > 0 && max_len >= split_len && max_s <= (u64)p.split_width;
-					if (reseed && p.qflags && (max_len >> 1) >= p.rf_k &&
-					    rf_range_is_clear(p.qflags + (size_t)lds_i32(sc + CS_RID) * (size_t)(p.q_stride >> 4), p.rf_k, len,
-					                      (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1)) {
+					bool rf_clear = false;
+					if (reseed && p.qflags && (max_len >> 1) >= p.rf_k) {
+						const int xm = (lds_u16(SC(CS_MAXEND)) + lds_u16(SC(CS_MAXSTART))) >> 1;
+						if (LPR == 1 && p.q_stride <= 64) {                  // the flags came with the read (rf_range_is_clear on registers)
+							const int lo = max(xm - p.rf_k + 1, 0), hi = min(xm, len - p.rf_k);
+							if (hi >= lo) {
+								const int wl = lo >> 5, wh = hi >> 5;
+								const u32 w0 = wl == 0 ? qf0 : wl == 1 ? qf1 : wl == 2 ? qf2 : qf3, w1 = wh == 0 ? qf0 : wh == 1 ? qf1 : wh == 2 ? qf2 : qf3;
+								const u32 m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - (hi & 31));
+								rf_clear = (wl == wh ? (w0 & m0 & m1) : ((w0 & m0) | (w1 & m1))) == 0;
+							}
+						} else
+							rf_clear = rf_range_is_clear(p.qflags + (size_t)lds_i32(SC(CS_RID)) * (size_t)(p.q_stride >> 4), p.rf_k, len, xm);
+					}
+					if (rf_clear) {
 						reseed = false;
 						if (p.count_skips && !half) atomicAdd(&p.status[6], 1);
 					}
 					if (reseed) {
-						sts_u16(sc + CS_NM1, n_mem); sts_u16(sc + CS_KEEP, max_len); sts_u16(sc + CS_PASS, 1);
-						sts_u16(sc + CS_X, (lds_u16(sc + CS_MAXEND) + lds_u16(sc + CS_MAXSTART)) >> 1);
+						sts_u16(SC(CS_NM1), n_mem); sts_u16(SC(CS_KEEP), max_len); sts_u16(SC(CS_PASS), 1);
+						sts_u16(SC(CS_X), (lds_u16(SC(CS_MAXEND)) + lds_u16(SC(CS_MAXSTART))) >> 1);
 						min_intv = (u32)max_s + 1u;
 						phase = PH_INIT_CALL;
 						break;
 					}
+					if (LPR == 1) {
+						for (int e = n_mem - 1; e >= 0; e -= 4) {        // four loads in flight, then the stores
+							Intv t0 = ld_intv(&M1[e]), t1 = t0, t2 = t0, t3 = t0;
+							if (e >= 1) t1 = ld_intv(&M1[e - 1]);
+							if (e >= 2) t2 = ld_intv(&M1[e - 2]);
+							if (e >= 3) t3 = ld_intv(&M1[e - 3]);
+							if (n_out < p.slot_cap) st_intv(&slot[n_out], t0.x0, t0.x1, t0.x2, t0.info | tag);
+							if (e >= 1 && n_out + 1 < p.slot_cap) st_intv(&slot[n_out + 1], t1.x0, t1.x1, t1.x2, t1.info | tag);
+							if (e >= 2 && n_out + 2 < p.slot_cap) st_intv(&slot[n_out + 2], t2.x0, t2.x1, t2.x2, t2.info | tag);
+							if (e >= 3 && n_out + 3 < p.slot_cap) st_intv(&slot[n_out + 3], t3.x0, t3.x1, t3.x2, t3.info | tag);
+							n_out += min(e + 1, 4);
+						}
+					} else
 					for (int e = n_mem - 1; e >= 0; --e) {
 						if (n_out < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[n_out], t.x0, t.x1, t.x2, t.info | tag); }
 						++n_out;
 					}
 				} else {
 					// ordered merge, bwamem.c:281-301; both lists are walked in ascending start = reverse emission
-					int ia = lds_u16(sc + CS_NM1) - 1, ib = n_mem - 1;
-					const int half_len = lds_u16(sc + CS_KEEP) >> 1, ori_start = lds_u16(sc + CS_ORI);
+					int ia = lds_u16(SC(CS_NM1)) - 1, ib = n_mem - 1;
+					const int half_len = lds_u16(SC(CS_KEEP)) >> 1, ori_start = lds_u16(SC(CS_ORI));
 					Intv va, vb;
 					va.x0 = va.x1 = va.x2 = va.info = 0; vb = va;
 					bool have_a = false, have_b = false;
@@ -298,7 +383,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 						}
 					}
 				}
-				sts_i32(sc + CS_NOUT, n_out); sts_u16(sc + CS_STEP, step + 1);
+				sts_i32(SC(CS_NOUT), n_out); sts_u16(SC(CS_STEP), step + 1);
 				phase = PH_NEXT_STEP;
 			} break;
 			default: break;
@@ -319,64 +404,77 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		// complemented read bases it is known to be preceded by (PH_UW_LF).  The gathers go through extend_pair's own load (same
 		// registers); the walk ends where the reference's last bwt_extend fails.  t rides in last_s, which the forward sweep
 		// does not use.
-		const uint4 *alt = nullptr;
+		const uint4 *alt = nullptr, *alt2 = nullptr;
 		if (phase >= PH_UW_SA && phase <= PH_UW_ISA) {              // (only entered with the tables present)
-			const u64 tq = last_s + (u64)(end - (u32)lds_u16(sc + CS_X));    // t + pattern length (PH_UW_SA: unused)
+			const u64 tq = last_s + (u64)(end - (u32)lds_u16(SC(CS_X)));    // t + pattern length (PH_UW_SA: unused)
 			u64 byte;
 			if (phase == PH_UW_SA) byte = (u64)p.uw_fsa + 32 * (b / 7);
 			else if (phase == PH_UW_ISA) byte = (u64)p.uw_isa + 32 * ((tq >> p.uw_isa_shift) / 7);
-			else byte = (u64)p.uw_text + 32 * ((tq >> 6) + (u64)half);
+			else byte = (u64)p.uw_text + 32 * ((tq >> 6) + (u64)half);       // (SEC: each lane still compares its own 64-base sector)
 			alt = reinterpret_cast<const uint4 *>(byte);
+			if (LPR == 1 && phase == PH_UW_TEXT) alt2 = alt + 2;     // one lane fetches both 64-base sectors of the window
 		}
+		Ext ok;
+		if (LPR == 1 || SEC) ok = extend_single(p.ix, a, b, s, c & 3, blk_k, blk_l, alt, alt2);
+		else {
 #ifdef SEED_NARROW
-		const Ext ok = extend_pair<!WIDE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
+			ok = extend_pair<!WIDE>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
 #else
-		const Ext ok = extend_pair<false>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
+			ok = extend_pair<false>(p.ix, a, b, s, c & 3, half, lane, p.hot_min_intv, pol_hot, pol_cold, blk_k, blk_l, alt);
 #endif
+		}
 		if (phase == PH_IDLE) continue;
-		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(sc + CS_RK)] = 0; phase = PH_NEED_READ; continue; }
+		if (--guard < 0) { if (!half) atomicAdd(&p.status[2], 1); p.counts[lds_i32(SC(CS_RK))] = 0; phase = PH_NEED_READ; continue; }
 
 		// ============================================================== consume the result, set up the next extend
 		// (forward: bwt.c:794-799, backward: bwt.c:813-824; written once for both so that the warp does not
 		//  run two divergent copies of the push / advance code)
 		if (alt) {
-			const u32 pm2 = 3u << (lane & ~1);
 			if (phase == PH_UW_TEXT) {
 				// text (pack_text_nib_kernel) and read carry one base per nibble, first base lowest: eight bases per XOR.  This lane
-				// compares the part of [tp, lim) that lies in its 64-base sector; the read word is funnel-shifted into place.
-				const u64 tp = last_s + (u64)(end - (u32)lds_u16(sc + CS_X));   // text position that faces read base i
+				// compares the part of [tp, lim) that lies in its 64-base sector (LPR 1: in both sectors of the window); the read word is
+				// funnel-shifted into place.
+				constexpr int SPAN = LPR == 2 ? 64 : 128;
+				const u64 tp = last_s + (u64)(end - (u32)lds_u16(SC(CS_X)));   // text position that faces read base i
 				const u64 sec0 = tp >> 6, mybase = (sec0 + (u64)half) << 6;
 				const u64 lim = min(min(tp + (u64)(len - i), p.ix.seq_len), (sec0 + 2) << 6);   // compare [tp, lim)
-				const int r_lo = tp > mybase ? (int)(tp - mybase) : 0, r_hi = lim > mybase ? (int)min(lim - mybase, (u64)64) : 0;
-				int first = 64;
+				const int r_lo = tp > mybase ? (int)(tp - mybase) : 0, r_hi = lim > mybase ? (int)min(lim - mybase, (u64)SPAN) : 0;
+				int first = SPAN;
 				if (r_hi > r_lo) {
 					const int base_q = i + (int)((long long)mybase - (long long)tp);   // read index facing the sector's first base (< 0: before i)
 					const int nw1 = (p.q_stride >> 2) - 1, qw = base_q >> 3;
 					const u32 sh = ((u32)base_q & 7u) * 4u;
-					u32 lo = (u32)lds_i32(sq + 4u * (u32)min(max(qw, 0), nw1));   // (clamped words only face masked positions)
+					u32 lo = (u32)lds_i32(QBYTE(4u * (u32)min(max(qw, 0), nw1)));   // (clamped words only face masked positions)
+					// words w_lo .. w_hi take part; only the first and the last of them partially
+					const int w_lo = r_lo >> 3, w_hi = (r_hi - 1) >> 3, rh = r_hi - 8 * w_hi;
+					const u32 m_lo = 0xffffffffu << (4 * (r_lo & 7)), m_hi = rh >= 8 ? 0xffffffffu : ~(0xffffffffu << (4 * rh));
 #pragma unroll
-					for (int wq = 0; wq < 8; ++wq) {
-						const u32 hi = (u32)lds_i32(sq + 4u * (u32)min(max(qw + 1 + wq, 0), nw1));
-						u32 d = blk_k[wq] ^ __funnelshift_r(lo, hi, sh);
+					for (int wq = 0; wq < SPAN / 8; ++wq) {
+						const u32 hi = (u32)lds_i32(QBYTE(4u * (u32)min(max(qw + 1 + wq, 0), nw1)));
+						u32 d = (wq < 8 ? blk_k[wq & 7] : blk_l[wq & 7]) ^ __funnelshift_r(lo, hi, sh);
 						lo = hi;
-						const int a0 = r_lo - 8 * wq, a1 = r_hi - 8 * wq;            // nibbles [a0, a1) of this word take part
-						u32 vm = a0 <= 0 ? 0xffffffffu : (a0 >= 8 ? 0u : 0xffffffffu << (4 * a0));
-						if (a1 < 8) vm &= a1 <= 0 ? 0u : ~(0xffffffffu << (4 * a1));
+						u32 vm = (wq >= w_lo && wq <= w_hi) ? 0xffffffffu : 0u;
+						if (wq == w_lo) vm &= m_lo;
+						if (wq == w_hi) vm &= m_hi;
 						d &= vm;
 						const u32 m = (d | (d >> 1) | (d >> 2)) & 0x11111111u;        // a base differs (an ambiguous read base, 4, always does)
-						if (m && first == 64) first = 8 * wq + ((__ffs((int)m) - 1) >> 2);
+						if (m && first == SPAN) first = 8 * wq + ((__ffs((int)m) - 1) >> 2);
 					}
 				}
-				const bool full = first == 64;
+				const bool full = first == SPAN;
 				const u32 cnt = r_hi > r_lo ? (u32)((full ? r_hi : first) - r_lo) : 0u;
-				const u32 c0 = __shfl_sync(pm2, cnt, lane & ~1), c1 = __shfl_sync(pm2, cnt, lane | 1);
-				const bool f0 = __shfl_sync(pm2, (int)full, lane & ~1) != 0, f1 = __shfl_sync(pm2, (int)full, lane | 1) != 0;
+				u32 c0 = cnt, c1 = 0;
+				bool f0 = full, f1 = true;
+				if (LPR == 2) {
+					c0 = __shfl_sync(pm2, cnt, lane & ~1); c1 = __shfl_sync(pm2, cnt, lane | 1);
+					f0 = __shfl_sync(pm2, (int)full, lane & ~1) != 0; f1 = __shfl_sync(pm2, (int)full, lane | 1) != 0;
+				}
 				const u32 m = f0 ? c0 + c1 : c0;
 				i += (int)m; end = (u32)i;
 				// ran through the whole 128-base window without a verdict: another round of text, else the inverse SA
 				if (!(f0 && f1 && tp + m == ((sec0 + 2) << 6) && i < len && tp + m < p.ix.seq_len)) phase = PH_UW_ISA;
 			} else {
-				const u64 tq = last_s + (u64)(end - (u32)lds_u16(sc + CS_X));
+				const u64 tq = last_s + (u64)(end - (u32)lds_u16(SC(CS_X)));
 				const u32 slot = (u32)((phase == PH_UW_SA ? b : tq >> p.uw_isa_shift) % 7);
 				u32 lo = blk_k[0];
 #pragma unroll
@@ -393,7 +491,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 					a = val;
 					j = (int)(tq & ((1ull << p.uw_isa_shift) - 1));
 					if (j == 0) phase = PH_FWD_END;
-					else { phase = PH_UW_LF; c = 3 - (int)qbase(sq, i - j); }
+					else { phase = PH_UW_LF; c = 3 - (int)qbase(i - j); }
 				}
 			}
 			continue;
@@ -401,22 +499,22 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 		if (phase == PH_UW_LF) {                                 // one position down the sampled inverse suffix array
 			a = ok.a;
 			if (--j == 0) phase = PH_FWD_END;
-			else c = 3 - (int)qbase(sq, i - j);
+			else c = 3 - (int)qbase(i - j);
 			continue;
 		}
 		if (SPEC && phase == PH_SPEC) {
 			if (ok.s < min_intv) {                               // died before the limit: the shorter candidates matter after all
-				i = lds_u16(sc + CS_X) - 1; j = 0; n_prev = n0; n_curr = 0;
-				c = (int)qbase(sq, i);                           // (valid: the walk started with it)
+				i = lds_u16(SC(CS_X)) - 1; j = 0; n_prev = n0; n_curr = 0;
+				c = (int)qbase(i);                           // (valid: the walk started with it)
 				b_get(n0 - 1, a, b, s, end);
 				phase = PH_BWD;
 				continue;
 			}
 			a = ok.a; b = ok.b; s = ok.s;
 			--i;
-			c = i < 0 ? -1 : (int)qbase(sq, i);
+			c = i < 0 ? -1 : (int)qbase(i);
 			if (c > 3) c = -1;
-			if (c < 0 || i < lds_u16(sc + CS_KEEP)) phase = PH_BWD_LAST;   // everything dies at the next round: emit (i + 1, end)
+			if (c < 0 || i < lds_u16(SC(CS_KEEP))) phase = PH_BWD_LAST;   // everything dies at the next round: emit (i + 1, end)
 			continue;
 		}
 		const bool fwd = phase == PH_FWD;
@@ -435,7 +533,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			if (diff && small) { phase = PH_FWD_DONE; continue; }
 			a = ok.a; b = ok.b; s = ok.s; end = (u32)(i + 1);
 			++i;
-			const u32 qv = i < len ? qbase(sq, i) : 4u;
+			const u32 qv = i < len ? qbase(i) : 4u;
 			if (qv > 3) phase = PH_FWD_END;
 			else c = 3 - (int)qv;
 			if (MODE != MODE_SMEM1) {                            // (uw_min_run is out of reach without the tables)
@@ -449,7 +547,7 @@ __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS) seed_kernel(const Seed
 			if (++j == n_prev) {                             // bwt.c:826-827
 				if (n_curr == 0) { phase = PH_CALL_DONE; continue; }
 				n_prev = n_curr; n_curr = 0; j = 0; --i;
-				c = i < 0 ? -1 : (int)qbase(sq, i);
+				c = i < 0 ? -1 : (int)qbase(i);
 				if (c > 3) c = -1;
 				if (c < 0) phase = PH_BWD_LAST;
 			}
@@ -630,6 +728,20 @@ __global__ void repack_kernel(const u32 *__restrict__ src, u64 n_blocks, u64 seq
 	d[1] = make_uint4(hi[0], hi[1], lo[0], lo[1]);                 //           planes of symbols 0..63
 	d[2] = make_uint4(cnt[4], cnt[5], cnt[6], cnt[7]);             // sector 1: checkpoints G, T
 	d[3] = make_uint4(hi[2], hi[3], lo[2], lo[3]);                 //           planes of symbols 64..127
+}
+
+// 64-byte blocks -> 32-byte sectors with their own 32-bit checkpoints (smem_device.cuh, extend_single).  One thread per block;
+// the second sector's checkpoints are the block's plus the symbol counts of its first half.
+__global__ void sectors_from_blocks_kernel(const uint4 *__restrict__ blk, u64 n_blocks, uint4 *__restrict__ sec)
+{
+	const u64 bidx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (bidx >= n_blocks) return;
+	const uint4 c01 = blk[bidx * 4], p0 = blk[bidx * 4 + 1], c23 = blk[bidx * 4 + 2], p1 = blk[bidx * 4 + 3];
+	const u32 nh = __popc(p0.x) + __popc(p0.y), nl = __popc(p0.z) + __popc(p0.w), nt = __popc(p0.x & p0.z) + __popc(p0.y & p0.w);
+	sec[bidx * 4] = make_uint4(c01.x, c01.z, c23.x, c23.z);                  // low words of the A, C, G, T checkpoints
+	sec[bidx * 4 + 1] = p0;
+	sec[bidx * 4 + 2] = make_uint4(c01.x + (64u - nh - nl + nt), c01.z + (nl - nt), c23.x + (nh - nt), c23.z + nt);
+	sec[bidx * 4 + 3] = p1;
 }
 
 // ---------------------------------------------------------------------------------------------
