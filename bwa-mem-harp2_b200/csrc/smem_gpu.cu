@@ -133,8 +133,8 @@ struct smem_gpu {
 	int uw_isa_shift = 2;            // the inverse suffix array of the next smem_gpu_build_text_index is sampled every 2^this positions
 	int uw_min_left = 8, uw_min_run = 3;   // ... for walks with at least this many read bases left, after this many extends of a unique interval
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
-	int lanes_per_read = 1;          // 1 = one lane per read on the 32-byte sector index (when it exists), 2 = lane pairs on the 64-byte blocks
-	bool build_sectors = true;       // smem_gpu_upload_index also builds the sector form (when every checkpoint fits 32 bits)
+	int lanes_per_read = 2;          // 2 = lane pairs on the 64-byte blocks, 3 = lane pairs on the 32-byte sector index, 1 = one lane per read on the sector index
+	bool build_sectors = false;      // smem_gpu_upload_index also builds the sector form (when every checkpoint fits 32 bits); set by lanes_per_read != 2
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
 	int probe_variant = 0;
 	int force_wide = 0;
@@ -694,7 +694,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	// ... and the 32-bit occurrence counts of the narrow extend need every base to occur fewer than 2^32 times
 	bool wide = h.force_wide || d.ix.seq_len >= (1ull << 36) || h.max_len >= (1 << 20);
 	for (int c = 0; c < 4; ++c) if (d.ix.L2[c + 1] - d.ix.L2[c] >= (1ull << 32)) wide = true;
-	const int lpr = (h.lanes_per_read != 2 && !wide && d.ix.sec) ? h.lanes_per_read : 2;      // 3 = lane pairs on the sector index
+	if (h.lanes_per_read != 2 && !wide && !d.ix.sec) { d.err = "lanes_per_read 1 / 3 need the sector form of the index: set the parameter before smem_gpu_upload_index"; return SMEM_GPU_E_ARG; }
+	const int lpr = (h.lanes_per_read != 2 && !wide) ? h.lanes_per_read : 2;      // 3 = lane pairs on the sector index; wide indices always take the lane-pair kernel
 	const int pairs_per_cta = lpr == 1 ? SEED_BLOCK1 : SEED_BLOCK / 2;            // reads in flight per CTA
 	const int max_grid = d.sm_count * std::max(bps, 9);                              // (the one-lane kernel runs up to nine CTAs per SM whatever bps says)
 	const int grid = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * (lpr != 2 ? 9 : bps), (d.n + pairs_per_cta - 1) / pairs_per_cta);
@@ -1887,7 +1888,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "unique_walk_min_run")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_run = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_min_left")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_left = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_isa_shift")) { if (v < 0 || v > 6) return SMEM_GPU_E_ARG; h->uw_isa_shift = (int)v; return 0; }
-	if (!strcmp(name, "lanes_per_read")) { if (v < 1 || v > 3) return SMEM_GPU_E_ARG; h->lanes_per_read = (int)v; return 0; }
+	if (!strcmp(name, "lanes_per_read")) { if (v < 1 || v > 3) return SMEM_GPU_E_ARG; h->lanes_per_read = (int)v; if (v != 2) h->build_sectors = true; return 0; }
 	if (!strcmp(name, "build_sectors")) { h->build_sectors = v != 0; return 0; }          // takes effect at the next smem_gpu_upload_index
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
 	if (!strcmp(name, "acc_reset")) { for (auto &d : h->devs) { d.acc_stage_ms = d.acc_turn_ms = d.acc_run_ms = d.acc_fetch_ms = 0; d.acc_calls = d.acc_h2d = d.acc_d2h = 0; } return 0; }
