@@ -94,6 +94,13 @@ struct DeviceCtx {
 	int *d_counts_k = nullptr;
 	size_t counts_k_cap = 0;
 	int *h_status = nullptr;          // pinned: [0..4] status, [6..7] int64 total
+	// latency path of small one-call batches (TINY_MAX reads, do_collect): ONE H2D copy of a pinned blob, three launches, results
+	// stored into a pinned arena by the last kernel -- 7 driver calls per batch instead of 25 (with 16 host threads calling at
+	// once the driver's serialisation of those calls, not the GPU, set the latency)
+	bool tiny = false, status_dirty = true;
+	uint8_t *h_tiny_in = nullptr, *d_tiny_in = nullptr; size_t tiny_in_bytes = 0;
+	uint8_t *h_arena = nullptr; size_t arena_entries = 0, arena_reads = 0;
+	size_t tiny_o_x = 0, tiny_o_mi = 0, tiny_o_seq = 0;
 	// current shard
 	int64_t lo = 0, hi = 0, n = 0;
 	long long seq_base = 0;
@@ -133,6 +140,7 @@ struct smem_gpu {
 	int uw_isa_shift = 2;            // the inverse suffix array of the next smem_gpu_build_text_index is sampled every 2^this positions
 	int uw_min_left = 8, uw_min_run = 3;   // ... for walks with at least this many read bases left, after this many extends of a unique interval
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
+	int tiny_path = 1;               // batches of up to TINY_MAX reads through the one-call forms take the latency path (DeviceCtx::tiny)
 	int lanes_per_read = 2;          // 2 = lane pairs on the 64-byte blocks, 3 = lane pairs on the 32-byte sector index, 1 = one lane per read on the sector index
 	bool build_sectors = false;      // smem_gpu_upload_index also builds the sector form (when every checkpoint fits 32 bits); set by lanes_per_read != 2
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
@@ -265,6 +273,10 @@ void ctx_free(DeviceCtx &d)
 	ctx_free_batch(d);
 	cudaFree(d.d_status);
 	if (d.h_status) cudaFreeHost(d.h_status);
+	if (d.h_tiny_in) cudaFreeHost(d.h_tiny_in);
+	if (d.h_arena) cudaFreeHost(d.h_arena);
+	if (d.d_tiny_in) cudaFree(d.d_tiny_in);
+	d.h_tiny_in = d.h_arena = d.d_tiny_in = nullptr; d.tiny_in_bytes = 0; d.arena_entries = d.arena_reads = 0;
 	if (d.ev0) cudaEventDestroy(d.ev0);
 	if (d.ev0s) cudaEventDestroy(d.ev0s);
 	if (d.ev1) cudaEventDestroy(d.ev1);
@@ -456,6 +468,46 @@ int ctx_stage(DeviceCtx &d, smem_gpu &h, const BatchIn &in)
 	return rc;
 }
 
+enum { TINY_FALLBACK = 1000 };      // internal: the latency path could not finish the batch, take the ordinary one
+
+// pinned blob + device twin for the reads of a small batch, pinned arena for its results (sizes follow the handle's limits)
+int ensure_tiny(DeviceCtx &d, int max_len)
+{
+	const size_t reads = (size_t)std::min<int64_t>(d.read_cap, TINY_MAX);
+	const size_t in_bytes = (reads + 1) * 8 + reads * 8 + 512 + reads * (size_t)max_len + 128;
+	if (in_bytes > d.tiny_in_bytes) {
+		if (d.h_tiny_in) CK(cudaFreeHost(d.h_tiny_in));
+		if (d.d_tiny_in) CK(cudaFree(d.d_tiny_in));
+		d.h_tiny_in = d.d_tiny_in = nullptr; d.tiny_in_bytes = 0;
+		CK(cudaMallocHost((void **)&d.h_tiny_in, in_bytes));
+		CK(cudaMalloc((void **)&d.d_tiny_in, in_bytes));
+		d.tiny_in_bytes = in_bytes;
+	}
+	const size_t entries = reads * 48 + 1024;
+	if (entries > d.arena_entries || reads > d.arena_reads) {
+		if (d.h_arena) CK(cudaFreeHost(d.h_arena));
+		d.h_arena = nullptr; d.arena_entries = d.arena_reads = 0;
+		CK(cudaMallocHost((void **)&d.h_arena, 64 + (reads + 1) * 8 + reads * 4 + 64 + entries * 36 + 64));
+		d.arena_entries = entries; d.arena_reads = reads;
+	}
+	return 0;
+}
+
+struct ArenaView { int *status; long long *off; int *ret; Intv *intv; unsigned short *step, *aux; };
+static ArenaView arena_view(const DeviceCtx &d, int64_t n)
+{
+	ArenaView v;
+	uint8_t *p = d.h_arena;
+	v.status = reinterpret_cast<int *>(p); p += 64;
+	v.off = reinterpret_cast<long long *>(p); p += (size_t)(n + 1) * 8;
+	v.ret = reinterpret_cast<int *>(p); p += (size_t)n * 4;
+	p = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p) + 31) & ~(uintptr_t)31);
+	v.intv = reinterpret_cast<Intv *>(p); p += d.arena_entries * 32;
+	v.step = reinterpret_cast<unsigned short *>(p); p += d.arena_entries * 2;
+	v.aux = reinterpret_cast<unsigned short *>(p);
+	return v;
+}
+
 // H2D only: nothing here walks the batch on the CPU -- read lengths are validated by the pack pre-pass on the device
 // (status[5], reported by the run).
 int ctx_stage_inner(DeviceCtx &d, const BatchIn &in)
@@ -467,6 +519,21 @@ int ctx_stage_inner(DeviceCtx &d, const BatchIn &in)
 	d.h2d = 0;
 	if (d.n == 0) return 0;
 	if (d.n > d.read_cap) { d.err = "batch exceeds the capacity given to smem_gpu_create"; return SMEM_GPU_E_CAPACITY; }
+	if (d.tiny) {
+		// latency path: offsets, raw-call arguments and bases gathered into one pinned blob, ONE copy
+		d.seq_base = in.offs[d.lo];
+		const long long span = in.offs[d.hi] - in.offs[d.lo];
+		if (span < 0) { d.err = "offs is not monotone"; return SMEM_GPU_E_ARG; }
+		const size_t nbytes = (size_t)span, n = (size_t)d.n;
+		d.tiny_o_x = (n + 1) * 8; d.tiny_o_mi = d.tiny_o_x + n * 4; d.tiny_o_seq = (d.tiny_o_mi + n * 4 + 255) & ~(size_t)255;
+		if (nbytes > d.seq_cap || d.tiny_o_seq + nbytes + 64 > d.tiny_in_bytes) { d.err = "batch exceeds the capacity given to smem_gpu_create (a read longer than max_read_len?)"; return SMEM_GPU_E_CAPACITY; }
+		memcpy(d.h_tiny_in, in.offs + d.lo, (n + 1) * 8);
+		if (in.x) { memcpy(d.h_tiny_in + d.tiny_o_x, in.x + d.lo, n * 4); memcpy(d.h_tiny_in + d.tiny_o_mi, in.mi + d.lo, n * 4); }
+		memcpy(d.h_tiny_in + d.tiny_o_seq, in.seq + d.seq_base, nbytes);
+		CK(cudaMemcpyAsync(d.d_tiny_in, d.h_tiny_in, d.tiny_o_seq + nbytes, cudaMemcpyHostToDevice, d.stream));
+		d.h2d = (int64_t)(d.tiny_o_seq + nbytes);
+		return 0;
+	}
 	if (in.fmt == 0) {
 		d.seq_base = in.offs[d.lo];
 		const long long span = in.offs[d.hi] - in.offs[d.lo];
@@ -767,14 +834,24 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		turn_acquire(d, h);
 		d.acc_turn_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
 	}
-	CK(cudaEventRecord(d.ev0, d.stream));
-	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
-	CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
+	const bool tiny = d.tiny;
+	if (tiny) {
+		if (d.status_dirty) CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));    // (the latency path's last kernel leaves them zeroed)
+		p.xs = reinterpret_cast<const int *>(d.d_tiny_in + d.tiny_o_x); p.min_intvs = reinterpret_cast<const int *>(d.d_tiny_in + d.tiny_o_mi);
+	} else {
+		CK(cudaEventRecord(d.ev0, d.stream));
+		CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+		CK(cudaMemsetAsync(d.d_counts + d.n, 0, sizeof(int), d.stream));
+	}
+	d.status_dirty = true;
 	{   // pack pre-pass: the caller's reads -> one base per nibble at a fixed stride + lengths (+ the repeat filter's window flags)
 		const int cpr = q_stride >> 4;
 		const long long chunks = (long long)d.n * cpr;
 		const unsigned gridp = (unsigned)((chunks + 255) / 256);
-		if (d.in_fmt == 0)
+		if (tiny)
+			pack_bytes_kernel<<<gridp, 256, 0, d.stream>>>(d.d_tiny_in + d.tiny_o_seq - d.seq_base, reinterpret_cast<const long long *>(d.d_tiny_in), d.n, cpr, h.max_len,
+			                                               d.d_qpack, d.d_rlen, d.d_status);
+		else if (d.in_fmt == 0)
 			pack_bytes_kernel<<<gridp, 256, 0, d.stream>>>(d.d_seq - d.seq_base, d.d_offs, d.n, cpr, h.max_len, d.d_qpack, d.d_rlen, d.d_status);
 		else {
 			unpack2_kernel<<<gridp, 256, 0, d.stream>>>(d.d_seq, d.r2_stride, d.r2_has_lens ? d.d_lens : nullptr, d.r2_read_len, d.n, cpr, h.max_len,
@@ -800,11 +877,31 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		CK(cudaStreamWaitEvent(d.stream, d.prev_lane->ev1, 0));
 	}
 	int rc = 0;
-	CK(cudaEventRecord(d.ev0s, d.stream));          // after the pack pre-pass: seed_ms is the seed kernel's own duration
+	if (!tiny) CK(cudaEventRecord(d.ev0s, d.stream));          // after the pack pre-pass: seed_ms is the seed kernel's own duration
 	rc = launch_seed_mode(d, mode, p, bps, grid, smem, wide, lpr);
 	if (rc) return rc;
-	CK(cudaEventRecord(d.ev1, d.stream));
+	if (!tiny) CK(cudaEventRecord(d.ev1, d.stream));
 	lane_mark_issued(d, h);
+	if (tiny) {
+		const ArenaView av = arena_view(d, d.n);
+		tiny_tail_kernel<<<1, TINY_TPB, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, (int)d.n, d.d_status, mode == MODE_SMEM1 ? d.d_ret : nullptr, d.d_off, d.d_out,
+		                                               d.d_step, mode == MODE_TRACE ? d.d_aux : nullptr, (long long)d.out_cap, av.status, av.off,
+		                                               mode == MODE_SMEM1 ? av.ret : nullptr, av.intv, av.step, mode == MODE_TRACE ? av.aux : nullptr,
+		                                               (long long)d.arena_entries);
+		CK(cudaGetLastError());
+		++d.launches;
+		turn_release(d);
+		CK(stream_wait(d));
+		d.status_dirty = false;
+		if (av.status[5] & 1) { d.err = "a read is longer than max_read_len (or offs is not monotone / a length exceeds the record stride)"; return SMEM_GPU_E_CAPACITY; }
+		if (av.status[2] != 0) { d.err = "device guard tripped (extend budget exceeded)"; return SMEM_GPU_E_INTERNAL; }
+		if (!av.status[11]) return TINY_FALLBACK;          // slots outgrown or more intervals than the buffers hold: the ordinary path sorts that out
+		d.overflow = 0; d.pass2_skipped = av.status[6]; d.uw_walks = av.status[7];
+		d.total = (long long)((unsigned long long)(u32)av.status[8] | ((unsigned long long)(u32)av.status[9] << 32));
+		d.out_valid = true;
+		d.seed_ms = d.total_ms = 0;                         // (no events on this path: they are four driver calls)
+		return 0;
+	}
 	static const bool trace = getenv("SMEM_GPU_TRACE") != nullptr;
 	const auto tt0 = std::chrono::steady_clock::now();
 	auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
@@ -1151,12 +1248,58 @@ struct CollectOut {
 	int64_t cap = 0; int64_t *total = nullptr;
 };
 
+// Latency path (see DeviceCtx::tiny): one context, byte reads, 32-byte results, at most TINY_MAX reads.
+int tiny_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_seed_opt_t *opt, const CollectOut &out)
+{
+	DeviceCtx &d = h->devs[0];
+	CK(cudaSetDevice(d.dev));
+	int rc = ensure_tiny(d, h->max_len);
+	if (rc) return rc;
+	shard(h, n);
+	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; ++h->stage_epoch; }
+	h->use_turn = false; h->stage_wait = false;
+	d.want_packed = 0;
+	d.tiny = true;
+	rc = ctx_stage(d, *h, in);
+	if (!rc) rc = ctx_run(d, *h, mode, opt);
+	d.tiny = false;
+	h->staged = n; h->ran = rc == 0;
+	if (rc) return rc;
+	const ArenaView av = arena_view(d, n);
+	h->h2d_bytes = d.h2d;
+	if (out.total) *out.total = d.total;
+	if (!av.status[10]) {                          // more intervals than the arena holds: fetch them the ordinary way
+		out.read_off[0] = 0;
+		const bool fits = out.intv && d.total <= out.cap;
+		rc = ctx_fetch(d, fits ? out.intv : nullptr, out.read_off, fits ? out.step : nullptr, out.ret, 0, fits ? out.aux : nullptr);
+		if (rc) return rc;
+		out.read_off[n] = d.total;
+		h->d2h_bytes = d.d2h;
+		if (!fits && d.total > 0) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+		return 0;
+	}
+	memcpy(out.read_off, av.off, (size_t)(n + 1) * 8);
+	if (out.ret) memcpy(out.ret, av.ret, (size_t)n * 4);
+	d.d2h = 64 + (n + 1) * 8 + (out.ret ? n * 4 : 0);
+	if (d.total > 0 && (!out.intv || d.total > out.cap)) { h->d2h_bytes = d.d2h; h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
+	memcpy(out.intv, av.intv, (size_t)d.total * 32);
+	if (out.step) memcpy(out.step, av.step, (size_t)d.total * 2);
+	if (out.aux) memcpy(out.aux, av.aux, (size_t)d.total * 2);
+	d.d2h += d.total * (32 + 2 + (mode == MODE_TRACE ? 2 : 0));
+	h->d2h_bytes = d.d2h;
+	return 0;
+}
+
 int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_seed_opt_t *opt, const CollectOut &out)
 {
 	const bool packed = out.read_off32 != nullptr;
 	if (!h || (!packed && !out.read_off)) { if (h) h->err = "bad argument"; return SMEM_GPU_E_ARG; }
 	int rc = check_batch(h, in, n);
 	if (rc) return rc;
+	if (h->tiny_path && h->devs.size() == 1 && !packed && in.fmt == 0 && n > 0 && n <= TINY_MAX) {
+		rc = tiny_collect(h, mode, n, in, opt, out);
+		if (rc != TINY_FALLBACK) return rc;
+	}
 	shard(h, n);
 	{ std::lock_guard<std::mutex> lk(h->lane_mu); ++h->epoch; ++h->stage_epoch; }
 	const size_t G = h->devs.size();
@@ -1888,6 +2031,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "unique_walk_min_run")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_run = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_min_left")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_left = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_isa_shift")) { if (v < 0 || v > 6) return SMEM_GPU_E_ARG; h->uw_isa_shift = (int)v; return 0; }
+	if (!strcmp(name, "tiny_path")) { h->tiny_path = v != 0; return 0; }
 	if (!strcmp(name, "lanes_per_read")) { if (v < 1 || v > 3) return SMEM_GPU_E_ARG; h->lanes_per_read = (int)v; if (v != 2) h->build_sectors = true; return 0; }
 	if (!strcmp(name, "build_sectors")) { h->build_sectors = v != 0; return 0; }          // takes effect at the next smem_gpu_upload_index
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide

@@ -744,6 +744,65 @@ __global__ void sectors_from_blocks_kernel(const uint4 *__restrict__ blk, u64 n_
 	sec[bidx * 4 + 3] = p1;
 }
 
+// Latency path of small batches (n <= TINY_MAX reads): ONE CTA does what scan_*_kernel + compact_kernel + publish_status_kernel do for
+// large ones -- counts -> offsets, slots -> dense output -- and also stores the results into a pinned host arena, so that the host
+// needs a single wait and no further copy: arena = [status 16 x int | off (n + 1) x int64 | ret n x int | intv | step | aux] with the
+// last three sized arena_cap entries.  Reads that outgrew their slots, or a total beyond the capacities, are only reported
+// (status[1] / the total): the host then takes the ordinary path.  Leaves the status words zeroed for the next run.
+#define TINY_MAX 2048
+#define TINY_TPB 256
+__global__ void __launch_bounds__(TINY_TPB) tiny_tail_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts, int n, int *__restrict__ status,
+                                                             const int *__restrict__ ret, long long *__restrict__ off, Intv *__restrict__ out,
+                                                             unsigned short *__restrict__ step_out, unsigned short *__restrict__ aux_out, long long out_cap,
+                                                             int *__restrict__ h_status, long long *__restrict__ h_off, int *__restrict__ h_ret,
+                                                             Intv *__restrict__ h_out, unsigned short *__restrict__ h_step, unsigned short *__restrict__ h_aux,
+                                                             long long arena_cap)
+{
+	__shared__ long long wsum[TINY_TPB / 32];
+	__shared__ long long s_off[TINY_MAX + 1];
+	const int t = threadIdx.x, per = (n + TINY_TPB - 1) / TINY_TPB;
+	const int r0 = t * per, r1 = min(r0 + per, n);
+	long long sum = 0;
+	for (int r = r0; r < r1; ++r) sum += counts[r];
+	long long incl = sum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const long long o = __shfl_up_sync(FULL_MASK, incl, d); if ((t & 31) >= d) incl += o; }
+	if ((t & 31) == 31) wsum[t >> 5] = incl;
+	__syncthreads();
+	long long base = incl - sum, total = 0;
+#pragma unroll
+	for (int w = 0; w < TINY_TPB / 32; ++w) { if (w < (t >> 5)) base += wsum[w]; total += wsum[w]; }
+	for (int r = r0; r < r1; ++r) { s_off[r] = base; off[r] = base; h_off[r] = base; if (h_ret) h_ret[r] = ret[r]; base += counts[r]; }
+	if (t == 0) { s_off[n] = total; off[n] = total; h_off[n] = total; }
+	__syncthreads();
+	const bool ok = status[1] == 0 && total <= out_cap;          // (else: the ordinary path's overflow re-run / buffer growth)
+	const bool to_host = ok && total <= arena_cap;
+	if (ok) {
+		for (int r = t >> 5; r < n; r += TINY_TPB / 32) {
+			const long long o0 = s_off[r];
+			const int c = (int)(s_off[r + 1] - o0);
+			for (int e = t & 31; e < c; e += 32) {
+				const Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
+				const unsigned short st = (unsigned short)(v.info >> STEP_SHIFT), ax = (unsigned short)(v.info >> AUX_SHIFT);
+				st_intv(&out[o0 + e], v.x0, v.x1, v.x2, v.info & INFO_MASK);
+				step_out[o0 + e] = st;
+				if (aux_out) aux_out[o0 + e] = ax;
+				if (to_host) {
+					st_intv(&h_out[o0 + e], v.x0, v.x1, v.x2, v.info & INFO_MASK);
+					h_step[o0 + e] = st;
+					if (h_aux) h_aux[o0 + e] = ax;
+				}
+			}
+		}
+	}
+	__syncthreads();
+	if (t < 8) { h_status[t] = status[t]; }
+	if (t == 8) { h_status[8] = (int)(u32)total; h_status[9] = (int)(u32)((unsigned long long)total >> 32); h_status[10] = to_host ? 1 : 0; h_status[11] = ok ? 1 : 0; }
+	__threadfence_system();
+	__syncthreads();
+	if (t < 8) status[t] = 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // counts -> CSR offsets: a small three-kernel exclusive scan (int counts -> int64 offsets).  Hand-written
 // rather than a library scan so that its CTAs (128 threads, few registers, 32 B of shared memory) fit into

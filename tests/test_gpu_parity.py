@@ -268,3 +268,53 @@ def test_trace_replays_to_collect_and_matches_raw_calls(world, synth):
         assert np.array_equal(raw["intv"][raw["read_off"][k]:raw["read_off"][k + 1]], c[3]), k
         if c[4] is not None:
             assert int(raw["ret"][k]) == c[4]
+
+
+def test_latency_path_of_small_batches(world, synth, sg):
+    """Batches of up to 2048 reads through the one-call forms take the latency path (one H2D copy, three launches, results stored
+    into a pinned arena by the last kernel): same lists as the ordinary path and the oracle; slot overflow and an arena that is
+    too small fall back to the ordinary path / the ordinary fetch."""
+    ref, ix, o, g = world
+    refn = ref.numpy()
+    for n, L in ((1, 101), (64, 101), (700, 150), (2048, 101)):
+        seq, offs = synth.to_batch(synth.simulate_reads(ref, n, L, 0.02, seed=n, n_frac=0.05))
+        a = o.collect(seq, offs, OSeedOpt(), nthreads=4)
+        same_result(a, g.collect(seq, offs), ("read_off", "intv", "step"))
+        assert g.timing()["kernel_launches"] == 3                    # pack, seed, tail
+        rng = np.random.default_rng(n)
+        x = rng.integers(0, L, n).astype(np.int32); mi = rng.integers(0, 4, n).astype(np.int32)
+        same_result(o.smem1(seq, offs, x, mi), g.smem1(seq, offs, x, mi), ("read_off", "intv", "ret"))
+        t1 = g.trace(seq, offs)
+        g.set_param("tiny_path", 0)
+        try:
+            t0 = g.trace(seq, offs)
+            same_result(a, g.collect(seq, offs), ("read_off", "intv", "step"))
+        finally:
+            g.set_param("tiny_path", 1)
+        for k in ("read_off", "intv", "tag", "ret"):
+            assert np.array_equal(t0[k], t1[k]), k
+    # reads that outgrow their slots: the latency path hands over to the ordinary one
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 500, 101, 0.03, seed=3))
+    a = o.collect(seq, offs, OSeedOpt(), nthreads=4)
+    g.set_param("slot_cap", 2)
+    try:
+        same_result(a, g.collect(seq, offs), ("read_off", "intv", "step"))
+        assert g.timing()["overflow_reads"] > 0
+    finally:
+        g.set_param("slot_cap", 128)
+    # more intervals than the arena of a small handle holds (64 x 48 + 1024): ordinary fetch of the resident results
+    g2 = sg.SmemGpu(max_batch_reads=64, max_read_len=260)
+    g2.share_index_from(g)
+    reads = []
+    for k in range(64):
+        q = np.full(260, 4, np.uint8); q[::2] = refn[1000 * k:1000 * k + 130]; reads.append(q)
+    seq, offs = synth.to_batch(reads)
+    a = o.collect(seq, offs, OSeedOpt(), nthreads=4)
+    assert len(a["intv"]) > 64 * 48 + 1024
+    same_result(a, g2.collect(seq, offs), ("read_off", "intv", "step"))
+    # errors are reported, the handle stays usable
+    bad, boffs = synth.to_batch([refn[:300].copy()])
+    with pytest.raises(sg.SmemGpuError):
+        g2.collect(bad, boffs)
+    same_result(a, g2.collect(seq, offs), ("read_off", "intv", "step"))
+    g2.close()
