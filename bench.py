@@ -835,6 +835,21 @@ def main():
             "device_ms_per_step": float(np.mean(dev_ms)),
         }
         out.update(extras)
+        # throughput through the link-compatible bwt_smem1_batched (reference `bwa mem -t T -b B` with only that symbol swapped):
+        # measured by tools/dropin_bench.py on a GPU box (it runs the reference binaries, which this benchmark does not), committed
+        dropin_rows = []
+        for f in ("r2_dropin_small_batches.json", "r2_dropin_100Mbp.json"):
+            try:
+                dj = json.load(open(os.path.join(ROOT, "profiles", f)))
+                for r in dj["rows"]:
+                    if r.get("impl", "").startswith("drop-in") and not any(x["b"] == r["b"] and x["t"] == r["t"] for x in dropin_rows):
+                        dropin_rows.append({k: r[k] for k in ("t", "b", "handles", "reads_per_s", "gpu_calls", "seeding_speedup_vs_cpu_path", "wall_speedup_vs_cpu_path",
+                                                            "sam_identical_to_cpu_path") if k in r})
+            except (OSError, ValueError, KeyError):
+                pass
+        if dropin_rows:
+            out["dropin"] = {"source": "static: profiles/r2_dropin_small_batches.json, profiles/r2_dropin_100Mbp.json (tools/dropin_bench.py, 100 Mbp reference, 101 bp reads, "
+                                       "16 host cores); not measured in this run", "rows": sorted(dropin_rows, key=lambda r: r["b"])}
         if pcie:
             out["pcie_probe"] = pcie
         if probe:
