@@ -701,7 +701,23 @@ def main():
                 for _ in range(reps):
                     call()
                 ms = (time.perf_counter() - tb_) / reps * 1e3
-                sweep.append({"reads_per_call": B, "l2_hot_min_intv": hot, "latency_ms": round(ms, 3), "reads_per_s": round(B / ms * 1e3)})
+                row = {"reads_per_call": B, "l2_hot_min_intv": hot, "latency_ms": round(ms, 3), "reads_per_s": round(B / ms * 1e3)}
+                if hot == 0 and B <= 2048:
+                    # the call the link-compatible adapter makes (bytes in, bwtintv_t out): batches this small take the library's latency path
+                    li = np.empty((B * 32 + 1024, 4), np.uint64); lo_ = np.zeros(B + 1, np.int64); ls = np.empty(B * 32 + 1024, np.uint16)
+                    def call_b():
+                        tot = C.c_int64(0)
+                        rc = lib.smem_gpu_collect(workers[0].h, C.c_int64(B), pseq.array.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                  poffs.array.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(opt), li.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                  C.c_int64(li.shape[0]), lo_.ctypes.data_as(C.POINTER(C.c_int64)), ls.ctypes.data_as(C.POINTER(C.c_uint16)), C.byref(tot))
+                        assert rc == 0, rc
+                    for _ in range(3):
+                        call_b()
+                    tb_ = time.perf_counter()
+                    for _ in range(20):
+                        call_b()
+                    row["latency_ms_byte_api_latency_path"] = round((time.perf_counter() - tb_) / 20 * 1e3, 3)
+                sweep.append(row)
         workers[0].set_param("l2_hot_min_intv", 0)
         extras["config5_batch_sweep"] = {"api": "smem_gpu_collect_packed, one handle, host buffers", "rows": sweep,
                                          "note": "reads without ambiguous bases only (the sub-batches reuse the step's records without its exception list)" if packed.n_amb else None}
