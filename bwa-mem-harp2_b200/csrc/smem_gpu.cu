@@ -140,6 +140,7 @@ struct smem_gpu {
 	int uw_isa_shift = 2;            // the inverse suffix array of the next smem_gpu_build_text_index is sampled every 2^this positions
 	int uw_min_left = 8, uw_min_run = 3;   // ... for walks with at least this many read bases left, after this many extends of a unique interval
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
+	int sa_from_tables = 1;          // bwt_sa from the full suffix array of the unique-walk tables when they are resident (one gather instead of a walk)
 	int tiny_path = 1;               // batches of up to TINY_MAX reads through the one-call forms take the latency path (DeviceCtx::tiny)
 	int lanes_per_read = 2;          // 2 = lane pairs on the 64-byte blocks, 3 = lane pairs on the 32-byte sector index, 1 = one lane per read on the sector index
 	bool build_sectors = false;      // smem_gpu_upload_index also builds the sector form (when every checkpoint fits 32 bits); set by lanes_per_read != 2
@@ -365,6 +366,7 @@ int ctx_build_text_index(DeviceCtx &d, const uint8_t *pac, long long l_pac, int 
 	pack_text_nib_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, d.stream>>>(d_pac, l_pac, reinterpret_cast<u32 *>(tw), n_words);
 	CKT(cudaGetLastError());
 	CKT(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+	d.status_dirty = true;
 	const long long n_sa = (long long)d.n_sa;
 	const int grid = (int)std::min<long long>((long long)d.sm_count * 8, (n_sa + 63) / 64);
 	fsa_build_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, n_sa, fsa, isa, isa_shift, d.d_status);
@@ -1085,6 +1087,7 @@ int ctx_fetch_packed(DeviceCtx &d, smem_gpu &h, void *out, uint32_t *read_off, l
 				const int rc1 = ensure_exc(d, round == 0 ? d.out_cap / 16 + 1024 : (size_t)d.n_exc + 1024);
 				if (rc1) return rc1;
 				CK(cudaMemsetAsync(d.d_status + 4, 0, sizeof(int), d.stream));
+				d.status_dirty = true;
 				intv12_from_dense_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_out, d.total, d.d_off, d.n, reinterpret_cast<u32 *>(d.d_outp),
 				                                                                                 d.d_off32, d.pos_bits, d.d_exc, (long long)d.exc_cap, d.d_status + 4);
 				CK(cudaGetLastError());
@@ -1474,8 +1477,13 @@ int ctx_sa(DeviceCtx &d, const uint64_t *k, uint64_t *out)
 	}
 	CK(cudaMemcpyAsync(d.d_k, k + d.lo, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
-	const int grid = (int)std::min<int64_t>((int64_t)d.sm_count * 8, (n + 63) / 64);
-	sa_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, n, d.d_k, d.d_kout, d.d_status);
+	d.status_dirty = true;
+	if (d.owner->sa_from_tables && d.d_fsa && d.uw_text_len == d.ix.seq_len)
+		sa_from_fsa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(d.d_fsa, n, d.d_k, d.d_kout);
+	else {
+		const int grid = (int)std::min<int64_t>((int64_t)d.sm_count * 8, (n + 63) / 64);
+		sa_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, n, d.d_k, d.d_kout, d.d_status);
+	}
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(out + d.lo, d.d_kout, (size_t)n * 8, cudaMemcpyDeviceToHost, d.stream));
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
@@ -1541,9 +1549,14 @@ int ctx_seeds_run(DeviceCtx &d, int min_seed_len, u64 max_occ)
 		d.seeds_cap = cap;
 	}
 	CK(cudaMemsetAsync(d.d_status, 0, 8 * sizeof(int), d.stream));
+	d.status_dirty = true;
 	if (d.n_seeds > 0 && total > 0) {
-		const int grid = (int)std::min<int64_t>((int64_t)d.sm_count * 8, (d.n_seeds + 63) / 64);
-		seed_expand_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, d.d_out, total, d.d_soff, d.n_seeds, d.d_seeds, d.d_status);
+		if (d.owner->sa_from_tables && d.d_fsa && d.uw_text_len == d.ix.seq_len)
+			seed_expand_fsa_kernel<<<(unsigned)((d.n_seeds + 255) / 256), 256, 0, d.stream>>>(d.d_fsa, d.d_out, total, d.d_soff, d.n_seeds, d.d_seeds);
+		else {
+			const int grid = (int)std::min<int64_t>((int64_t)d.sm_count * 8, (d.n_seeds + 63) / 64);
+			seed_expand_kernel<<<grid, 128, 0, d.stream>>>(d.ix, d.d_sa, d.sa_shift, d.d_out, total, d.d_soff, d.n_seeds, d.d_seeds, d.d_status);
+		}
 		CK(cudaGetLastError());
 	}
 	CK(cudaMemcpyAsync(d.h_status, d.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
@@ -2031,6 +2044,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "unique_walk_min_run")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_run = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_min_left")) { if (v < 1 || v > 65535) return SMEM_GPU_E_ARG; h->uw_min_left = (int)v; return 0; }
 	if (!strcmp(name, "unique_walk_isa_shift")) { if (v < 0 || v > 6) return SMEM_GPU_E_ARG; h->uw_isa_shift = (int)v; return 0; }
+	if (!strcmp(name, "sa_from_tables")) { h->sa_from_tables = v != 0; return 0; }
 	if (!strcmp(name, "tiny_path")) { h->tiny_path = v != 0; return 0; }
 	if (!strcmp(name, "lanes_per_read")) { if (v < 1 || v > 3) return SMEM_GPU_E_ARG; h->lanes_per_read = (int)v; if (v != 2) h->build_sectors = true; return 0; }
 	if (!strcmp(name, "build_sectors")) { h->build_sectors = v != 0; return 0; }          // takes effect at the next smem_gpu_upload_index

@@ -1210,6 +1210,29 @@ __global__ void __launch_bounds__(128) seed_expand_kernel(const DevIndex ix, con
 	}
 }
 
+// The same expansion when the unique-walk tables are resident: bwt_sa(k) is ONE gather from the full suffix array (33-bit entries,
+// uw_get33) instead of a walk of sa_intv / 2 bwt_invPsi steps on average.  One thread per seed.
+__global__ void __launch_bounds__(256) seed_expand_fsa_kernel(const u32 *__restrict__ fsa, const Intv *__restrict__ iv, long long total,
+                                                              const long long *__restrict__ soff, long long n_seeds, Seed *__restrict__ out)
+{
+	const long long cur = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (cur >= n_seeds) return;
+	long long lo = 0, hi = total - 1;               // interval of seed `cur`: last i with soff[i] <= cur
+	while (lo < hi) { const long long mid = (lo + hi + 1) >> 1; if (soff[mid] <= cur) lo = mid; else hi = mid - 1; }
+	const Intv v = ld_intv(&iv[lo]);
+	Seed sd;
+	sd.rbeg = (long long)uw_get33(fsa, v.x0 + (u64)(cur - soff[lo]));       // bwamem.c:420: bwt_sa(bwt, p->x[0] + k)
+	sd.qbeg = (int)(v.info >> 32); sd.len = (int)(u32)v.info - sd.qbeg;
+	out[cur] = sd;
+}
+
+// bwt_sa for a batch of rows from the full suffix array (row 0, the '$' suffix, is -1 in the reference, bwt.c:97)
+__global__ void sa_from_fsa_kernel(const u32 *__restrict__ fsa, long long n, const u64 *__restrict__ k, u64 *__restrict__ out)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = k[i] == 0 ? ~0ull : uw_get33(fsa, k[i]);
+}
+
 __global__ void seed_read_off_kernel(const long long *__restrict__ off, const long long *__restrict__ soff, long long n, long long base,
                                      long long *__restrict__ seed_off)
 {

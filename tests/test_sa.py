@@ -95,3 +95,29 @@ def test_gpu_seeds_vs_oracle(world_sa, synth):
         assert np.array_equal(got["seeds"]["rbeg"], rbeg)
         assert np.array_equal(got["seeds"]["qbeg"], np.array(qb, np.int32)) and np.array_equal(got["seeds"]["len"], np.array(ln, np.int32))
         g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sa_and_seeds_from_the_full_suffix_array(world_sa, synth):
+    """With the unique-walk tables resident bwt_sa is one gather from the full suffix array (seed_expand_fsa_kernel,
+    sa_from_fsa_kernel) instead of a walk of bwt_invPsi steps: same positions, row 0 included (sa[0] = -1, bwt.c:97)."""
+    sg = pkg("smem_gpu")
+    ref, ix, o = world_sa
+    g = sg.SmemGpu(max_batch_reads=8192, max_read_len=128)
+    g.upload_index(ix); g.upload_sa(ix)
+    g.build_text_index(ref)
+    k = np.concatenate([_rows(ix, 40000, 3), np.array([0, 1, ix.seq_len], np.uint64)])
+    want = o.sa(ix, k)
+    assert np.array_equal(g.sa(k), want)
+    g.set_param("sa_from_tables", 0)
+    assert np.array_equal(g.sa(k), want)                       # the walk, for comparison
+    seq, offs = synth.to_batch(synth.simulate_reads(ref, 5000, 101, 0.02, seed=12, n_frac=0.05))
+    g.collect(seq, offs)
+    a = g.seeds(len(offs) - 1, 19, 10000)
+    g.set_param("sa_from_tables", 1)
+    g.collect(seq, offs)
+    b = g.seeds(len(offs) - 1, 19, 10000)
+    assert np.array_equal(a["seed_off"], b["seed_off"])
+    for f in ("rbeg", "qbeg", "len"):
+        assert np.array_equal(a["seeds"][f], b["seeds"][f]), f
+    g.close()
