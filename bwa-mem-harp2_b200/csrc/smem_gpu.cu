@@ -142,8 +142,9 @@ struct smem_gpu {
 	int spec_walk = 1;               // speculative longest-only backward walk in pass-1 calls (smem_kernels.cuh PH_SPEC)
 	int sa_from_tables = 1;          // bwt_sa from the full suffix array of the unique-walk tables when they are resident (one gather instead of a walk)
 	int tiny_path = 1;               // batches of up to TINY_MAX reads through the one-call forms take the latency path (DeviceCtx::tiny)
-	int lanes_per_read = 2;          // 2 = lane pairs on the 64-byte blocks, 3 = lane pairs on the 32-byte sector index, 1 = one lane per read on the sector index
-	bool build_sectors = false;      // smem_gpu_upload_index also builds the sector form (when every checkpoint fits 32 bits); set by lanes_per_read != 2
+	int lanes_per_read = 4;          // 4 = lane pairs on the 32-byte sector index, backward sweep split over the two lanes (default; wide indices take 2);
+	                                 // 2 = lane pairs on the 64-byte blocks, 3 = lane pairs on the sector index, 1 = one lane per read on the sector index
+	bool build_sectors = true;       // smem_gpu_upload_index also builds the sector form (when every checkpoint fits 32 bits); "lanes_per_read" = 2 before the upload turns it off
 	int count_skips = 0;             // debug: count the skipped passes (one atomic each)
 	int probe_variant = 0;
 	int force_wide = 0;
@@ -611,11 +612,16 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 			return 0;
 		}
 	}
-	if (lpr == 3) {          // lane pairs, each lane on the 32-byte sector form of the index
+	if (lpr == 3 || lpr == 4) {          // lane pairs, each lane on the 32-byte sector form of the index; 4: the backward sweep split over the two lanes
 		if constexpr (WIDE) { d.err = "the sector form needs 32-bit occurrence counts"; return SMEM_GPU_E_INTERNAL; }
 		else {
-			CK(cudaFuncSetAttribute(seed_kernel<MODE, 9, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			seed_kernel<MODE, 9, false, 2, true><<<grid, SEED_BLOCK, smem, d.stream>>>(p);
+			if (lpr == 3) {
+				CK(cudaFuncSetAttribute(seed_kernel<MODE, 9, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				seed_kernel<MODE, 9, false, 2, true><<<grid, SEED_BLOCK, smem, d.stream>>>(p);
+			} else {
+				CK(cudaFuncSetAttribute(seed_kernel<MODE, 9, false, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				seed_kernel<MODE, 9, false, 2, true, true><<<grid, SEED_BLOCK, smem, d.stream>>>(p);
+			}
 			CK(cudaGetLastError());
 			++d.launches;
 			return 0;
@@ -2046,7 +2052,7 @@ int smem_gpu_set_param(smem_gpu_t *h, const char *name, int64_t v)
 	if (!strcmp(name, "unique_walk_isa_shift")) { if (v < 0 || v > 6) return SMEM_GPU_E_ARG; h->uw_isa_shift = (int)v; return 0; }
 	if (!strcmp(name, "sa_from_tables")) { h->sa_from_tables = v != 0; return 0; }
 	if (!strcmp(name, "tiny_path")) { h->tiny_path = v != 0; return 0; }
-	if (!strcmp(name, "lanes_per_read")) { if (v < 1 || v > 3) return SMEM_GPU_E_ARG; h->lanes_per_read = (int)v; if (v != 2) h->build_sectors = true; return 0; }
+	if (!strcmp(name, "lanes_per_read")) { if (v < 1 || v > 4) return SMEM_GPU_E_ARG; h->lanes_per_read = (int)v; h->build_sectors = v != 2; return 0; }
 	if (!strcmp(name, "build_sectors")) { h->build_sectors = v != 0; return 0; }          // takes effect at the next smem_gpu_upload_index
 	if (!strcmp(name, "blocking_sync")) { g_blocking_sync = v != 0; return 0; }          // process-wide
 	if (!strcmp(name, "acc_reset")) { for (auto &d : h->devs) { d.acc_stage_ms = d.acc_turn_ms = d.acc_run_ms = d.acc_fetch_ms = 0; d.acc_calls = d.acc_h2d = d.acc_d2h = 0; } return 0; }

@@ -51,10 +51,16 @@ __device__ __noinline__ Intv bx_get(const Intv *p) { return ld_intv(p); }
 // carries 32 reads, nothing is executed in duplicate and nothing is shuffled.
 // SEC (LPR 2 only): both lanes of the pair run extend_single on the same 32-byte sector -- identical addresses, still one request --
 // instead of sharing a 64-byte block: no shuffles, a third fewer instructions in the extend.
-template <int MODE, int MIN_BLOCKS, bool WIDE, int LPR, bool SEC = false>
+// SPLIT (with SEC): in the backward sweep the two lanes of a pair extend TWO DIFFERENT entries of prev[] in the same trip (lane 0
+// prev[j], lane 1 prev[j + 1]; each lane can compute a whole bwt_extend by itself on the sector form).  The entries of one round are
+// independent of each other (bwt.c:812-825 only looks at the previous entry's SIZE to de-duplicate), so the pair exchanges the two
+// sizes, both lanes replay the two push / emit decisions in order on identical state, and each lane stores its own entry.  Half the
+// trips in the triangular sweeps at error positions, which are 40 % of all extends.
+template <int MODE, int MIN_BLOCKS, bool WIDE, int LPR, bool SEC = false, bool SPLIT = false>
 __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCKS) seed_kernel(const SeedParams p)
 {
 	static_assert((LPR == 2 && !SEC) || !WIDE, "the 32-bit sector form of the index needs 32-bit occurrence counts");
+	static_assert(!SPLIT || (SEC && LPR == 2), "splitting the backward sweep needs lane pairs on the sector form");
 	const bool SPEC = MODE != MODE_SMEM1 && p.spec_walk;     // speculative longest-only backward walk (PH_SPEC)
 	typedef BEntry<WIDE> BE;
 	extern __shared__ uint4 smem_raw[];
@@ -133,6 +139,14 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 	int rk_pref = 0;
 	u32 qf0 = 0, qf1 = 0, qf2 = 0, qf3 = 0;          // the read's window flags (repeat filter) when they fit four words
 	if (LPR == 1) rk_pref = atomicAdd(&p.status[0], 1);
+	// the entry of prev[] this lane extends next: prev[j] -- or, SPLIT in the backward sweep proper, prev[j + half] (a lane without an
+	// entry rides on the interval (1,1,1)); every other phase needs prev[0] in both lanes
+	auto load_prev = [&]() {
+		if (SPLIT && phase == PH_BWD) {
+			const int jj = j + half;
+			if (jj < n_prev) b_get(n0 - 1 - jj, a, b, s, end); else { a = 1; b = 1; s = 1; }
+		} else b_get(n0 - 1 - j, a, b, s, end);
+	};
 
 	for (;;) {
 		__syncwarp();
@@ -256,6 +270,7 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 					if (i < lds_u16(SC(CS_KEEP))) phase = PH_BWD_LAST;      // no round left before the limit: (i + 1, end) is the result
 					else phase = PH_SPEC;
 				}
+				if (SPLIT && phase == PH_BWD && half) load_prev();          // lane 1 starts the sweep with prev[1]
 			} break;
 			case PH_BWD_LAST: {
 				// bwt.c:815-821 with c == -1 (read start or ambiguous base): nothing can enter curr and only
@@ -506,8 +521,8 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 			if (ok.s < min_intv) {                               // died before the limit: the shorter candidates matter after all
 				i = lds_u16(SC(CS_X)) - 1; j = 0; n_prev = n0; n_curr = 0;
 				c = (int)qbase(i);                           // (valid: the walk started with it)
-				b_get(n0 - 1, a, b, s, end);
 				phase = PH_BWD;
+				load_prev();
 				continue;
 			}
 			a = ok.a; b = ok.b; s = ok.s;
@@ -515,6 +530,34 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 			c = i < 0 ? -1 : (int)qbase(i);
 			if (c > 3) c = -1;
 			if (c < 0 || i < lds_u16(SC(CS_KEEP))) phase = PH_BWD_LAST;   // everything dies at the next round: emit (i + 1, end)
+			continue;
+		}
+		if (SPLIT && phase == PH_BWD) {
+			// two entries of the round at once: A = prev[j] in lane 0, B = prev[j + 1] in lane 1 (if there is one)
+			const bool two = j + 1 < n_prev;
+			const u32 sA = __shfl_sync(pm2, (u32)ok.s, lane & ~1), sB = __shfl_sync(pm2, (u32)ok.s, lane | 1);
+			const bool smallA = sA < min_intv, smallB = sB < min_intv;
+			const bool emitA = smallA && n_curr == 0;
+			const bool pushA = !smallA && (n_curr == 0 || (u64)sA != last_s);
+			const int idxA = n0 - 1 - n_curr;
+			if (pushA) { ++n_curr; last_s = sA; }
+			const bool emitB = two && !emitA && smallB && n_curr == 0;        // (a second emission of the same round never passes bwt.c:815's test)
+			const bool pushB = two && !smallB && (n_curr == 0 || (u64)sB != last_s);
+			const int idxB = n0 - 1 - n_curr;
+			if (pushB) { ++n_curr; last_s = sB; }
+			// each lane stores its own entry; the emission updates the pair's cold state, which the other lane reads after the sync
+			if (half ? emitB : emitA) emit(a, b, s, end, i + 1);
+			if (half ? pushB : pushA) b_put(half ? idxB : idxA, ok.a, ok.b, ok.s, end);
+			__syncwarp(pm2);
+			j += two ? 2 : 1;
+			if (j >= n_prev) {                               // bwt.c:826-827
+				if (n_curr == 0) { phase = PH_CALL_DONE; continue; }
+				n_prev = n_curr; n_curr = 0; j = 0; --i;
+				c = i < 0 ? -1 : (int)qbase(i);
+				if (c > 3) c = -1;
+				if (c < 0) phase = PH_BWD_LAST;
+			}
+			load_prev();
 			continue;
 		}
 		const bool fwd = phase == PH_FWD;
@@ -551,7 +594,7 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 				if (c > 3) c = -1;
 				if (c < 0) phase = PH_BWD_LAST;
 			}
-			b_get(n0 - 1 - j, a, b, s, end);
+			load_prev();
 		}
 	}
 }

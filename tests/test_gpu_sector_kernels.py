@@ -1,5 +1,6 @@
-"""The two kernel variants on the 32-byte sector form of the index (lanes_per_read 1 and 3, smem_device.cuh extend_single) must give
-the lists of the lane-pair kernel / the oracle, bit for bit: collect, raw bwt_smem1 calls, the trace, every shortcut, spills."""
+"""Every variant of the seed kernel -- lane pairs on the 64-byte blocks (lanes_per_read 2), lane pairs on the 32-byte sector form
+with the backward sweep split over the two lanes (4, the default) or not (3), one lane per read on the sector form (1; smem_device.cuh
+extend_single) -- must give the oracle's lists bit for bit: collect, raw bwt_smem1 calls, the trace, every shortcut, spills."""
 import numpy as np
 import pytest
 
@@ -9,7 +10,7 @@ from oracle.binding import Oracle, SeedOpt as OSeedOpt
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[1, 3])
+@pytest.fixture(scope="module", params=[1, 2, 3, 4])
 def world(request, fm, synth):
     sg = pkg("smem_gpu")
     ref = synth.make_reference(800_000, 17)
@@ -80,6 +81,7 @@ def test_smem1_and_trace(world, synth):
     mi = rng.integers(0, 5, n).astype(np.int32)
     same_result(o.smem1(seq, offs, x, mi), g.smem1(seq, offs, x, mi), ("read_off", "intv", "ret"))
     g2 = sg.SmemGpu(max_batch_reads=30_000, max_read_len=260)      # the lane-pair kernel on the 64-byte blocks
+    g2.set_param("lanes_per_read", 2)
     g2.upload_index(ix)
     ta, tb = g2.trace(seq, offs), g.trace(seq, offs)
     for k in ("read_off", "intv", "tag", "ret"):
