@@ -138,7 +138,14 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 	// four entries per round trip.
 	int rk_pref = 0;
 	u32 qf0 = 0, qf1 = 0, qf2 = 0, qf3 = 0;          // the read's window flags (repeat filter) when they fit four words
-	if (LPR == 1) rk_pref = atomicAdd(&p.status[0], 1);
+	// (drawing the work index ahead was also tried for the lane pairs: one more live register in the 56-register kernel, 18.8 -> 20.1 ms)
+	constexpr bool PREF = LPR == 1;
+#ifdef SEED_NO_SPLIT_COPY
+	constexpr bool PCOPY = false;
+#else
+	constexpr bool PCOPY = SPLIT;
+#endif
+	if (PREF && !half) rk_pref = atomicAdd(&p.status[0], 1);
 	// the entry of prev[] this lane extends next: prev[j] -- or, SPLIT in the backward sweep proper, prev[j + half] (a lane without an
 	// entry rides on the interval (1,1,1)); every other phase needs prev[0] in both lanes
 	auto load_prev = [&]() {
@@ -156,12 +163,13 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 			case PH_NEED_READ: {
 				int rk = 0;
 				if (LPR == 1) { rk = rk_pref; sts_i32(SC(CS_RK), rk); }
+				else if (PREF) { rk = __shfl_sync(pm2, rk_pref, lane & ~1); if (!half) sts_i32(SC(CS_RK), rk); __syncwarp(pm2); }
 				else {
 					if (!half) { rk = atomicAdd(&p.status[0], 1); sts_i32(SC(CS_RK), rk); }
 					__syncwarp(pm2); rk = lds_i32(SC(CS_RK));
 				}
 				if ((long long)rk >= p.n) { phase = PH_IDLE; break; }
-				if (LPR == 1) rk_pref = atomicAdd(&p.status[0], 1);        // (needed at the next PH_NEED_READ, a few hundred extends from here)
+				if (PREF && !half) rk_pref = atomicAdd(&p.status[0], 1);   // (needed at the next PH_NEED_READ, a few hundred extends from here)
 				const int rid = p.list ? p.list[rk] : rk;
 				if (LPR == 1) {
 					// length, the first 128 bases and the window flags: issued together, one round trip
@@ -364,6 +372,12 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 							if (e >= 3 && n_out + 3 < p.slot_cap) st_intv(&slot[n_out + 3], t3.x0, t3.x1, t3.x2, t3.info | tag);
 							n_out += min(e + 1, 4);
 						}
+					} else if (PCOPY) {                                  // the two lanes of the pair copy alternate entries: two round trips in flight
+						for (int e = n_mem - 1 - half; e >= 0; e -= 2) {
+							const int o = n_out + (n_mem - 1 - e);
+							if (o < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[o], t.x0, t.x1, t.x2, t.info | tag); }
+						}
+						n_out += n_mem;
 					} else
 					for (int e = n_mem - 1; e >= 0; --e) {
 						if (n_out < p.slot_cap) { const Intv t = ld_intv(&M1[e]); st_intv(&slot[n_out], t.x0, t.x1, t.x2, t.info | tag); }

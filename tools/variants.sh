@@ -2,7 +2,8 @@
 # time each through bench.py (SMEM_GPU_LIB selects the library).  usage: bash tools/variants.sh build|run [bench flags]
 set -e
 cd "$(dirname "$0")/.."
-V="base: sp:-DSEED_KEEP_SP spgp:-DSEED_KEEP_SP,-DSEED_KEEP_GP spgpn:-DSEED_KEEP_SP,-DSEED_KEEP_GP,-DSEED_NARROW ${EXTRA_VARIANTS}"
+B=-DSEED_KEEP_SP,-DSEED_KEEP_GP,-DSEED_NARROW        # the shipped switches (csrc/Makefile SEED_FLAGS)
+V="${VARIANTS:-shipped:$B nosplitcopy:$B,-DSEED_NO_SPLIT_COPY}"
 if [ "$1" = build ]; then
   mkdir -p bwa-mem-harp2_b200/variants
   for v in $V; do
