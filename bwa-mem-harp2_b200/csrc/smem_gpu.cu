@@ -599,6 +599,10 @@ static const int kSeedBounds[] = {3, 4, 5, 6, 7, 8, 9, 10, 12};
 static const int kSeedBounds[] = {6, 8, 9};
 #endif
 
+#ifndef SEED_SPLIT_BLOCKS
+#define SEED_SPLIT_BLOCKS 9      // CTAs per SM the default kernel is compiled for (56 registers)
+#endif
+
 template <int MODE, bool WIDE>
 int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid, size_t smem, int lpr)
 {
@@ -619,8 +623,8 @@ int launch_seed_w(DeviceCtx &d, const SeedParams &p, int blocks_per_sm, int grid
 				CK(cudaFuncSetAttribute(seed_kernel<MODE, 9, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 				seed_kernel<MODE, 9, false, 2, true><<<grid, SEED_BLOCK, smem, d.stream>>>(p);
 			} else {
-				CK(cudaFuncSetAttribute(seed_kernel<MODE, 9, false, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-				seed_kernel<MODE, 9, false, 2, true, true><<<grid, SEED_BLOCK, smem, d.stream>>>(p);
+				CK(cudaFuncSetAttribute(seed_kernel<MODE, SEED_SPLIT_BLOCKS, false, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				seed_kernel<MODE, SEED_SPLIT_BLOCKS, false, 2, true, true><<<grid, SEED_BLOCK, smem, d.stream>>>(p);
 			}
 			CK(cudaGetLastError());
 			++d.launches;
@@ -773,7 +777,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	const int lpr = (h.lanes_per_read != 2 && !wide) ? h.lanes_per_read : 2;      // 3 = lane pairs on the sector index; wide indices always take the lane-pair kernel
 	const int pairs_per_cta = lpr == 1 ? SEED_BLOCK1 : SEED_BLOCK / 2;            // reads in flight per CTA
 	const int max_grid = d.sm_count * std::max(bps, 9);                              // (the one-lane kernel runs up to nine CTAs per SM whatever bps says)
-	const int grid = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * (lpr != 2 ? 9 : bps), (d.n + pairs_per_cta - 1) / pairs_per_cta);
+	const int grid = (int)std::min<int64_t>((int64_t)(d.sm_count - spare) * (lpr == 4 ? SEED_SPLIT_BLOCKS : lpr != 2 ? 9 : bps), (d.n + pairs_per_cta - 1) / pairs_per_cta);
 	const int scratch_cap = h.max_len + 2;
 	const size_t need = (size_t)std::min<int64_t>(max_grid, (d.read_cap + pairs_per_cta - 1) / pairs_per_cta + 1) * pairs_per_cta * 3 * scratch_cap;
 	const int q_stride = ((h.max_len + 1) / 2 + 15) / 16 * 16;      // two bases per byte; keeps pair_stride a multiple of 16

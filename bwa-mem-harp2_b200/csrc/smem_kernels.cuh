@@ -203,8 +203,9 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 						if (32 * (t0 + 3) < len) sts_v4(sq + ((u32)(t0 + 3) << 9), ch3);
 					}
 				} else {
-					len = p.rlen[rid];
-					{                                                            // staged by pack_reads_kernel: 16 bytes (32 bases) per copy
+					{
+						len = p.rlen[rid];
+						// staged by pack_reads_kernel: 16 bytes (32 bases) per copy
 						const uint4 *src = p.qpack + (size_t)rid * (size_t)(p.q_stride >> 4);
 						for (int t = half; 32 * t < len; t += 2) sts_v4(sq + 16 * t, __ldg(src + t));
 					}
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(LPR == 2 ? SEED_BLOCK : SEED_BLOCK1, MIN_BLOCK
 			load_prev();
 			continue;
 		}
-		const bool fwd = phase == PH_FWD;
+		const bool fwd = SPLIT ? true : phase == PH_FWD;     // (SPLIT: the backward sweep never gets here; 18.3 -> 17.9 ms for the dead code alone)
 		const bool small = ok.s < min_intv;
 		const bool diff = ok.s != (fwd ? s : last_s);
 		const bool push = fwd ? diff : (!small && (n_curr == 0 || diff));
