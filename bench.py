@@ -854,7 +854,7 @@ def main():
         # throughput through the link-compatible bwt_smem1_batched (reference `bwa mem -t T -b B` with only that symbol swapped):
         # measured by tools/dropin_bench.py on a GPU box (it runs the reference binaries, which this benchmark does not), committed
         dropin_rows = []
-        for f in ("r2_dropin_small_batches.json", "r2_dropin_100Mbp.json"):
+        for f in ("r2_dropin_100Mbp.json",):
             try:
                 dj = json.load(open(os.path.join(ROOT, "profiles", f)))
                 for r in dj["rows"]:
@@ -864,8 +864,8 @@ def main():
             except (OSError, ValueError, KeyError):
                 pass
         if dropin_rows:
-            out["dropin"] = {"source": "static: profiles/r2_dropin_small_batches.json, profiles/r2_dropin_100Mbp.json (tools/dropin_bench.py, 100 Mbp reference, 101 bp reads, "
-                                       "16 host cores); not measured in this run", "rows": sorted(dropin_rows, key=lambda r: r["b"])}
+            out["dropin"] = {"source": "static: profiles/r2_dropin_100Mbp.json (tools/dropin_bench.py, 100 Mbp reference, 2 M x 101 bp reads, 16 host cores); "
+                                       "not measured in this run", "rows": sorted(dropin_rows, key=lambda r: r["b"])}
         if pcie:
             out["pcie_probe"] = pcie
         if probe:

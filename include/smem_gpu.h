@@ -291,10 +291,12 @@ int smem_gpu_last_timing(const smem_gpu_t *h, smem_gpu_timing_t *t);
  * "spec_walk" / "unique_walk" (0 = do not use that shortcut of DESIGN.md section 10; results are the same),
  * "unique_walk_min_run" / "unique_walk_min_left" (a unique walk starts after that many extends of an interval of size 1
  * and with at least that many read bases left; 3 / 8), "count_skips" (debug counters "pass2_skipped", "unique_walks").
- * "lanes_per_read" (set BEFORE smem_gpu_upload_index when not 2: the upload then also builds the index as 32-byte sectors with
- * 32-bit checkpoints, + 0.5 byte per symbol): 2 = a lane pair per read on the 64-byte blocks (default; the fastest on a
- * B200), 3 = a lane pair per read, each lane on the sector form, 1 = one lane per read on the sector form (a third fewer
- * instructions, but half the warps: slower); results are identical.
+ * "lanes_per_read" -- the kernel variant (DESIGN.md sections 4 and 11; results are identical): 4 = a lane pair per read on the
+ * 32-byte sector form of the index, the backward sweep split over the two lanes (default; indices with >= 2^32 occurrences of a
+ * base take 2), 2 = a lane pair per read sharing 64-byte blocks (set BEFORE smem_gpu_upload_index to skip building the sector
+ * form, + 0.5 byte per symbol of HBM), 3 = lane pairs on the sector form without the split, 1 = one lane per read on the sector
+ * form; "sa_from_tables" (1 = seed positions from the full suffix array of the unique-walk tables when they are resident),
+ * "tiny_path" (1 = batches of up to 2048 reads through smem_gpu_collect / _smem1 / _trace take the latency path).
  * "blocks_per_sm" accepts the launch-bounds variants that were compiled in (6, 8, 9).  Read-only: "table_bytes" /
  * "uw_table_bytes" / "index_bytes" (HBM of device 0), and the wall-time accumulators of the one-call forms, summed over the
  * handle's lanes: "acc_stage_us" (H2D), "acc_turn_us" (waiting for the GPU's kernel turn), "acc_run_us" (kernels),
