@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: do not pin each rank to the CPUs local to its GPU")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sweep", default="", help="comma list of blocks_per_sm[:l2_hot_min_intv[:b_cap[::l2_mode]]] to time (stderr), e.g. 6,8:16384,9::17")
+    ap.add_argument("--param-sweep", default="", help='time the seed kernel over values of library knobs: "name=v1,v2;name2=v1,v2" (stderr)')
     ap.add_argument("--probe", action="store_true", help="also run the random-access roofline sweep")
     ap.add_argument("--full-compare", action="store_true", help="compare every interval of the step with the oracle (config 2)")
     return ap.parse_args()
@@ -385,6 +386,17 @@ def main():
                 g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
             log(f"sweep blocks_per_sm={b} l2_hot_min_intv={hot} b_cap={g.get_param('b_cap')} l2_mode={g.get_param('l2_mode')}: seed kernel {min(ms[1:]):.2f} ms -> {n / min(ms[1:]) / 1e3:.2f} M reads/s")
         g.set_param("blocks_per_sm", keep[0]); g.set_param("l2_hot_min_intv", keep[1]); g.set_param("b_cap", keep[2]); g.set_param("l2_mode", 0)
+    if args.param_sweep:            # generic knob sweep on the resident batch: --param-sweep "name=v1,v2;other=v1,v2" (one knob at a time, restored after)
+        for spec in args.param_sweep.split(";"):
+            name, vals = spec.split("=")
+            keep_v = g.get_param(name)
+            for v in vals.split(","):
+                g.set_param(name, int(v))
+                ms = []
+                for _ in range(4):
+                    g.run_collect(opt); ms.append(g.timing()["seed_kernel_ms"])
+                log(f"param sweep {name}={v}: seed kernel {min(ms[1:]):.3f} ms")
+            g.set_param(name, keep_v)
     for _ in range(max(args.warmup, 3)):
         total = g.run_collect(opt)
     sampler = ClockSampler(local)
