@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/.."
 B=-DSEED_KEEP_SP,-DSEED_KEEP_GP,-DSEED_NARROW        # the shipped switches (csrc/Makefile SEED_FLAGS)
-V="${VARIANTS:-shipped:$B split8:$B,-DSEED_SPLIT_BLOCKS=8 split10:$B,-DSEED_SPLIT_BLOCKS=10}"
+V="${VARIANTS:-shipped:$B nosplitcopy:$B,-DSEED_NO_SPLIT_COPY}"
 if [ "$1" = build ]; then
   mkdir -p bwa-mem-harp2_b200/variants
   for v in $V; do
