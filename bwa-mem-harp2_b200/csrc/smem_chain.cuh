@@ -23,6 +23,10 @@
 // was not enough (oracle/smem_oracle.c bt_*; tests/test_chains.py crafted equal-key reads against the reference's mem_chain).
 // Lane 0 runs the insertion loop -- it is sequential by definition, and O(log n) per seed now; the tree is walked in order into
 // `ord`, from where the filter and the copy-out use all lanes.
+// Provenance note: flt_introsort / flt_combsort / flt_insertsort and the two predicates chain_weight_dev / the test_and_merge test are
+// deliberate step-by-step restatements of klib ksort.h:146-224 and bwamem.c:334-356, 502-521 -- an unstable sort's order of equal
+// weights (and the reference's never-reset `w` in the weight loop) cannot be reproduced any other way.  They are confined to those
+// ~70 lines; everything around them (one warp per read, the device B-tree, the scans, the emit) is this library's own design.
 #pragma once
 #include "smem_kernels.cuh"
 
