@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-repeat-filter", action="store_true", help="do not build / use the repeat filter of the re-seeding pass (DESIGN.md section 10)")
     ap.add_argument("--no-text-index", action="store_true", help="do not build / use the unique-walk tables")
     ap.add_argument("--text-index", action="store_true", help="(default when HBM has room) also build the unique-walk tables (text at 4 bits per base, 33-bit suffix array, sampled inverse: 6.2 bytes per text position) and seed with them (DESIGN.md section 10)")
+    ap.add_argument("--record-bytes", type=int, default=0, help="interval records of the headline end-to-end leg: 11 or 12 bytes (0 = 12 unless a copy probe shows the link to be the limit)")
     ap.add_argument("--rf-kmer", type=int, default=0)
     ap.add_argument("--rf-log2-bits", type=int, default=0)
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: do not pin each rank to the CPUs local to its GPU")
@@ -344,8 +345,11 @@ def main():
         ok = ok and np.array_equal(gp["read_off"], st["read_off"]) and np.array_equal(gp["intv"], st["intv"])
         gp = g.collect_packed12(sg.PackedReads(lib, seq[: int(offs[ns])], offs[: ns + 1]), opt)
         ok = ok and np.array_equal(gp["read_off"], st["read_off"]) and np.array_equal(gp["intv"], st["intv"])
+        if args.read_len <= 512:
+            gp = g.collect_packed11(sg.PackedReads(lib, seq[: int(offs[ns])], offs[: ns + 1]), opt)
+            ok = ok and np.array_equal(gp["read_off"], st["read_off"]) and np.array_equal(gp["intv"], st["intv"])
         parity = {"reads_checked": ns, "bit_exact": bool(ok), "checker": "oracle/liboracle.so",
-                  "wire_formats_checked": ["bytes + bwtintv_t", "2-bit reads + 16-byte records", "2-bit reads + 12-byte records"]}
+                  "wire_formats_checked": ["bytes + bwtintv_t", "2-bit reads + 16-byte records", "2-bit reads + 12-byte records"] + (["2-bit reads + 11-byte records"] if args.read_len <= 512 else [])}
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU intervals differ from the oracle on the bench workload")
         if not args.skip_cpu and world == 1:       # the CPU baseline is a single-GPU-run figure (it would idle the other ranks)
@@ -354,7 +358,7 @@ def main():
             m = min(n, max(20_000, int(probe["reads_per_s"] * args.cpu_seconds)))
             r = cpu_time(eng, seq, offs, m, ncores, OSeedOpt())
             one = cpu_time(eng, seq, offs, min(m, 20_000), 1, OSeedOpt())
-            gk = g.collect_packed12(sg.PackedReads(lib, seq[: int(offs[m])], offs[: m + 1]), opt)
+            gk = (g.collect_packed11 if args.read_len <= 512 else g.collect_packed12)(sg.PackedReads(lib, seq[: int(offs[m])], offs[: m + 1]), opt)
             ck = orc.checksum(gk["intv"], gk["read_off"])
             parity.update(reads_checked=m, bit_exact=bool(ok and ck == r["checksum"]), checker=f"oracle + {kind} checksum (through the compact wire format)")
             if ck != r["checksum"]:
@@ -448,6 +452,7 @@ def main():
     prec = [sg.PinnedArray(lib, (cap16, 2), np.uint64) for _ in range(T)]
     proff32 = [sg.PinnedArray(lib, (n + 1,), np.uint32) for _ in range(T)]
     prec12 = [sg.PinnedArray(lib, (cap16, 3), np.uint32) for _ in range(T)]          # 12-byte records (smem_intv12_t) + their exception lists
+    prec11 = [sg.PinnedArray(lib, (cap16, 11), np.uint8) for _ in range(T)]          # 11-byte records (smem_intv11_t)
     exc_cap = max(4096, n // 4)
     pexc = [sg.PinnedArray(lib, (exc_cap,), sg.EXC_DTYPE) for _ in range(T)]
 
@@ -507,24 +512,54 @@ def main():
     max_over_ranks = lambda x: sh.max_over_ranks(x, device)
     gather_ranks = lambda vals: sh.gather_rows(vals, device)
 
-    # (1) the headline: compact wire format both ways: 2-bit reads in, 12-byte interval records out
+    # (1) the headline: compact wire format both ways: 2-bit reads in, 11-byte interval records out
     n_exc_last = [0] * T
     pos_bits = [0]
-    def step_packed12(t):
+    def step_packed_small(t, fn, bufs, what):
         tot, ne, pb = C.c_int64(0), C.c_int64(0), C.c_int32(0)
-        rc = lib.smem_gpu_collect_packed12(workers[t].h, C.byref(packed.desc), C.byref(opt), C.c_void_p(prec12[t].array.ctypes.data), C.c_int64(cap16),
-                                           C.c_void_p(proff32[t].array.ctypes.data), C.c_void_p(pexc[t].array.ctypes.data), C.c_int64(exc_cap),
-                                           C.byref(ne), C.byref(pb), C.byref(tot))
-        check_rc(rc, t, "smem_gpu_collect_packed12")
+        rc = fn(workers[t].h, C.byref(packed.desc), C.byref(opt), C.c_void_p(bufs[t].array.ctypes.data), C.c_int64(cap16),
+                C.c_void_p(proff32[t].array.ctypes.data), C.c_void_p(pexc[t].array.ctypes.data), C.c_int64(exc_cap), C.byref(ne), C.byref(pb), C.byref(tot))
+        check_rc(rc, t, what)
         n_exc_last[t] = int(ne.value); pos_bits[0] = int(pb.value)
         return int(tot.value)
+    # Which record size: the 12-byte form costs the GPU 0.15 ms less per step (no squeeze pass), the 11-byte form costs the link 8 % less.
+    # So: 12 bytes unless the link is what limits -- all ranks copy one step's 12-byte volume at once from / to pinned memory, and if
+    # the slowest rank needs longer for that than the GPU needs for the step, the 11-byte form is used (--record-bytes overrides).
+    record_choice = {"record_bytes": 12, "why": "--record-bytes" if args.record_bytes else "one GPU: the link is not shared"}
+    if args.record_bytes in (11, 12):
+        record_choice["record_bytes"] = args.record_bytes
+    elif world > 1 and args.read_len <= 512:
+        h_in = torch.empty(packed.h2d_bytes, dtype=torch.uint8).pin_memory(); h_out = torch.empty(12 * total + 4 * n, dtype=torch.uint8).pin_memory()
+        d_in = torch.empty_like(h_in, device=device); d_out = torch.empty_like(h_out, device=device)
+        side = torch.cuda.Stream(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        with torch.cuda.stream(side):
+            d_in.copy_(h_in, non_blocking=True); h_out.copy_(d_out, non_blocking=True)      # (warm-up)
+            e0.record()
+            for _ in range(4):
+                d_in.copy_(h_in, non_blocking=True); h_out.copy_(d_out, non_blocking=True)
+            e1.record()
+        e1.synchronize()
+        copy_ms = max_over_ranks(e0.elapsed_time(e1) / 4)
+        step_ms = max_over_ranks(float(np.mean(dev_ms)))
+        record_choice = {"record_bytes": 11 if copy_ms > 0.97 * step_ms else 12, "copy_ms_of_a_12_byte_step_all_ranks_at_once": round(copy_ms, 3),
+                         "device_ms_per_step": round(step_ms, 3), "why": "the slowest rank's link time for a step of 12-byte records against the GPU's time for the step"}
+        del h_in, h_out, d_in, d_out
+        sync()
+    use11 = record_choice["record_bytes"] == 11 and args.read_len <= 512      # (the 11-byte form needs query positions of <= 9 bits)
+    log("record size of the end-to-end leg:", record_choice)
+    def step_packed11(t):
+        return step_packed_small(t, lib.smem_gpu_collect_packed11, prec11, "smem_gpu_collect_packed11")
+    def step_packed12(t):
+        return step_packed_small(t, lib.smem_gpu_collect_packed12, prec12, "smem_gpu_collect_packed12")
     def step_packed(t):
         tot = C.c_int64(0)
         rc = lib.smem_gpu_collect_packed(workers[t].h, C.byref(packed.desc), C.byref(opt), C.c_void_p(prec[t].array.ctypes.data), C.c_int64(cap16),
                                          C.c_void_p(proff32[t].array.ctypes.data), C.byref(tot))
         check_rc(rc, t, "smem_gpu_collect_packed")
         return int(tot.value)
-    dt_e2e, tot_e2e = timed_leg(step_packed12, args.steps)
+    dt_e2e, tot_e2e = timed_leg(step_packed11 if use11 else step_packed12, args.steps)
     te = workers[0].timing()
     stages = acc_read()
     stage_keys = list(stages)
@@ -534,7 +569,8 @@ def main():
     # every worker's last result is the step's result: checksum of rank 0's against the device-resident run
     if rank == 0:
         a = g.fetch_packed(total)
-        got12 = sg.unpack_intv12(prec12[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]])
+        got12 = (sg.unpack_intv11(prec11[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]]) if use11 else
+                 sg.unpack_intv12(prec12[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]]))
         if not (tot_e2e == total and np.array_equal(a["intv"], got12) and np.array_equal(a["read_off"], proff32[0].array.astype(np.int64))):
             raise SystemExit("PARITY FAILURE: end-to-end result differs from the device-resident run")
         del got12
@@ -546,15 +582,37 @@ def main():
         ixh = fm.BwtIndex(ix.primary, ix.L2, ix.seq_len, ix.bwt_size, ix.words_numpy())
         t0c = time.time()
         want = Oracle(ixh).collect(seq, offs, OSeedOpt(), nthreads=ncores)
-        same = (np.array_equal(want["read_off"], proff32[0].array.astype(np.int64)) and np.array_equal(want["intv"], sg.unpack_intv12(prec12[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]])))
+        same = (np.array_equal(want["read_off"], proff32[0].array.astype(np.int64)) and np.array_equal(want["intv"], (sg.unpack_intv11(prec11[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]]) if use11 else
+                                               sg.unpack_intv12(prec12[0].array[:tot_e2e], pos_bits[0], pexc[0].array[:n_exc_last[0]]))))
         log(f"full compare: {n} reads, {len(want['intv'])} intervals, bit_exact={same} (oracle {time.time() - t0c:.1f}s)")
         parity = dict(parity or {}, full_compare_reads=n, full_compare_intervals=int(len(want["intv"])), full_compare_bit_exact=bool(same))
         if not same:
             raise SystemExit("PARITY FAILURE in --full-compare")
         del want, ixh
 
+    exc_e2e = int(n_exc_last[0])
     extras = {}
     if not args.no_extras:
+        if not use11 and args.read_len <= 512:       # (1a) the same call with 11-byte records (8 % fewer bytes over the link, one more pass on the GPU)
+            d11, tot11 = timed_leg(step_packed11, args.steps)
+            t11 = workers[0].timing(); s11 = acc_read()
+            d11 = max_over_ranks(d11)
+            extras["e2e_11byte_records"] = {"value": world * n * args.steps / d11, "unit": "reads/s", "ms_per_step": d11 / args.steps * 1e3, "api": "smem_gpu_collect_packed11",
+                                            "h2d_bytes_per_step": int(t11["h2d_bytes"]), "d2h_bytes_per_step": int(t11["d2h_bytes"]),
+                                            "stages_rank0": {k: round(v, 3) for k, v in s11.items()}}
+            log("e2e, 2-bit reads in / 11-byte records out:", extras["e2e_11byte_records"])
+            if rank == 0 and not (tot11 == tot_e2e and np.array_equal(a["intv"], sg.unpack_intv11(prec11[0].array[:tot11], pos_bits[0], pexc[0].array[:n_exc_last[0]]))):
+                raise SystemExit("PARITY FAILURE: 11-byte end-to-end result differs from the device-resident run")
+        if use11:       # (1a) the same call with 12-byte records
+            d12, tot12 = timed_leg(step_packed12, args.steps)
+            t12 = workers[0].timing(); s12 = acc_read()
+            d12 = max_over_ranks(d12)
+            extras["e2e_12byte_records"] = {"value": world * n * args.steps / d12, "unit": "reads/s", "ms_per_step": d12 / args.steps * 1e3, "api": "smem_gpu_collect_packed12",
+                                            "h2d_bytes_per_step": int(t12["h2d_bytes"]), "d2h_bytes_per_step": int(t12["d2h_bytes"]),
+                                            "stages_rank0": {k: round(v, 3) for k, v in s12.items()}}
+            log("e2e, 2-bit reads in / 12-byte records out:", extras["e2e_12byte_records"])
+            if rank == 0 and not (tot12 == tot_e2e and np.array_equal(a["intv"], sg.unpack_intv12(prec12[0].array[:tot12], pos_bits[0], pexc[0].array[:n_exc_last[0]]))):
+                raise SystemExit("PARITY FAILURE: 12-byte end-to-end result differs from the device-resident run")
         # (1b) the same call with 16-byte records (no exception list; 4 more bytes per interval over the link)
         d16, tot16 = timed_leg(step_packed, args.steps)
         t16 = workers[0].timing(); s16 = acc_read()
@@ -835,8 +893,9 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": world * n * args.steps / dt_e2e, "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
                     "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "api": "smem_gpu_collect_packed12 (2-bit reads in, 12-byte interval records + exception list out; include/smem_gpu.h)",
-                    "exceptions_per_step": int(n_exc_last[0]), "record_pos_bits": pos_bits[0],
+                    "api": ("smem_gpu_collect_packed11 (2-bit reads in, 11-byte interval records + exception list out; include/smem_gpu.h)" if use11 else
+                            "smem_gpu_collect_packed12 (2-bit reads in, 12-byte interval records + exception list out; include/smem_gpu.h)"),
+                    "exceptions_per_step": exc_e2e, "record_pos_bits": pos_bits[0], "record_choice": record_choice,
                     "pipeline_lanes_per_gpu": args.lanes, "host_threads": T, "intervals": int(tot_e2e),
                     "host_pack_s_per_step_untimed": round(t_pack, 4),
                     "stages_per_rank": stages_per_rank},

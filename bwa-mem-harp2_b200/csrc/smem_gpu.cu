@@ -739,11 +739,11 @@ int ensure_packed_out(DeviceCtx &d)
 
 // 12-byte records: query positions take pos_bits each, what is left of the third word holds the interval size
 static int pos_bits_for(int max_len) { int b = 1; while ((1 << b) < max_len) ++b; return b; }
-static bool packed12_ok(const DeviceCtx &d, const smem_gpu &h) { return d.ix.seq_len < (1ull << 33) && pos_bits_for(h.max_len) <= 13; }
+static bool packed12_ok(const DeviceCtx &d, const smem_gpu &h, int fmt = 2) { return d.ix.seq_len < (1ull << 33) && pos_bits_for(h.max_len) <= (fmt == 3 ? 9 : 13); }
 
 int ensure_exc(DeviceCtx &d, size_t want)
 {
-	static_assert(sizeof(Exc12) == sizeof(smem_x2exc_t) && sizeof(smem_intv12_t) == 12, "12-byte record layout");
+	static_assert(sizeof(Exc12) == sizeof(smem_x2exc_t) && sizeof(smem_intv12_t) == 12 && sizeof(smem_intv11_t) == 11, "compact record layouts");
 	if (d.exc_cap < want) {
 		if (d.d_exc) CK(cudaFree(d.d_exc));
 		d.d_exc = nullptr; d.exc_cap = 0;
@@ -760,9 +760,11 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	d.seeds_valid = false; d.out_valid = false; d.outp_fmt = 0; d.n_exc = 0;
 	if (d.n == 0) return 0;
 	if (!d.has_index) { d.err = "no index uploaded"; return SMEM_GPU_E_NOINDEX; }
-	const bool packed_out = d.want_packed != 0, packed12 = d.want_packed == 2;
+	const bool packed_out = d.want_packed != 0, packed12 = d.want_packed >= 2;      // (2 = 12-byte records, 3 = 11-byte records: same machinery)
+	const int rec_bytes = d.want_packed == 3 ? -11 : 12;       // (11-byte records are laid out as 12 in d_out first, then squeezed)
+	auto rec_dst = [&]() -> u32 * { return d.want_packed == 3 ? reinterpret_cast<u32 *>(d.d_out) : reinterpret_cast<u32 *>(d.d_outp); };   // (both may be re-sized below)
 	if (packed_out && (mode != MODE_COLLECT || !packed_out_ok(d, h))) { d.err = "16-byte result records need seq_len < 2^33 and max_read_len < 2^14"; return SMEM_GPU_E_ARG; }
-	if (packed12 && !packed12_ok(d, h)) { d.err = "12-byte result records need seq_len < 2^33 and max_read_len <= 8192"; return SMEM_GPU_E_ARG; }
+	if (packed12 && !packed12_ok(d, h, d.want_packed)) { d.err = "12-byte result records need seq_len < 2^33 and max_read_len <= 8192 (11-byte records: <= 512)"; return SMEM_GPU_E_ARG; }
 	d.pos_bits = pos_bits_for(h.max_len);
 	const int bps = h.blocks_per_sm;
 	// several lanes on this GPU: the persistent seed kernel leaves `spare_sms` SMs empty, so that the finished
@@ -936,8 +938,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 		const long long threads = (long long)d.n * 8;
 		if (packed12)
 			compact_packed12_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
-			                                                                                 reinterpret_cast<u32 *>(d.d_outp), d.d_off32, (long long)d.out_cap,
-			                                                                                 d.pos_bits, d.d_exc, (long long)d.exc_cap, d.d_status + 4);
+			                                                                                 rec_dst(), d.d_off32, (long long)d.out_cap,
+			                                                                                 d.pos_bits, d.d_exc, (long long)d.exc_cap, d.d_status + 4, rec_bytes);
 		else if (packed_out)
 			compact_packed_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, d.stream>>>(d.d_slots, h.slot_cap, d.d_counts, d.d_off, d.n,
 			                                                                               d.d_outp, d.d_off32, (long long)d.out_cap);
@@ -950,6 +952,14 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 	};
 	if ((rc = queue_scan())) return rc;
 	if ((rc = queue_compact())) return rc;
+	auto queue_squeeze = [&]() -> int {          // 11-byte records: the 12-byte layout in d_out -> byte-packed records in d_outp
+		if (d.want_packed != 3) return 0;
+		squeeze11_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(reinterpret_cast<const u32 *>(d.d_out), d.d_off + d.n, reinterpret_cast<u32 *>(d.d_outp));
+		CK(cudaGetLastError());
+		++d.launches;
+		return 0;
+	};
+	if ((rc = queue_squeeze())) return rc;
 	publish_status_kernel<<<1, 32, 0, d.stream>>>(d.d_status, d.d_off + d.n, d.h_status);     // (h_status is pinned: mapped under unified addressing)
 	CK(cudaGetLastError());
 	++d.launches;
@@ -1029,8 +1039,8 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			const long long threads = (long long)n_over * big_cap;
 			if (packed12)
 				compact_list_packed12_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over, d.d_off,
-				                                                                                      reinterpret_cast<u32 *>(d.d_outp), d.pos_bits, d.d_exc,
-				                                                                                      (long long)d.exc_cap, d.d_status + 4);
+				                                                                                      rec_dst(), d.pos_bits, d.d_exc,
+				                                                                                      (long long)d.exc_cap, d.d_status + 4, rec_bytes);
 			else if (packed_out)
 				compact_list_packed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_big, big_cap, d.d_overflow, d.d_counts_k, n_over,
 				                                                                                    d.d_off, d.d_outp);
@@ -1040,6 +1050,7 @@ int ctx_run_inner(DeviceCtx &d, smem_gpu &h, int mode, const smem_seed_opt_t *op
 			CK(cudaGetLastError());
 			++d.launches;
 		}
+		if ((rc = queue_squeeze())) return rc;
 		if (packed12) { publish_status_kernel<<<1, 32, 0, d.stream>>>(d.d_status, d.d_off + d.n, d.h_status); CK(cudaGetLastError()); }
 		CK(cudaEventRecord(d.ev2, d.stream));
 		turn_release(d);
@@ -1085,13 +1096,14 @@ int ctx_fetch_packed(DeviceCtx &d, smem_gpu &h, void *out, uint32_t *read_off, l
 	d.d2h = 0;
 	if (d.n == 0) return 0;
 	if (d.outp_fmt != fmt) {
-		if (!d.out_valid || d.mode != MODE_COLLECT || !packed_out_ok(d, h) || (unsigned long long)d.total >= (1ull << 32) || (fmt == 2 && !packed12_ok(d, h))) {
+		if (!d.out_valid || d.mode != MODE_COLLECT || !packed_out_ok(d, h) || (unsigned long long)d.total >= (1ull << 32) || (fmt >= 2 && !packed12_ok(d, h, fmt))) {
 			d.err = "no resident results that fit the compact records (a run that compacted into one compact form keeps only that form)"; return SMEM_GPU_E_ARG;
 		}
 		const int rc0 = ensure_packed_out(d);
 		if (rc0) return rc0;
 		const long long threads = std::max<long long>(d.total, d.n + 1);
-		if (fmt == 2) {
+		if (fmt >= 2) {
+			const int rec_bytes = fmt == 3 ? 11 : 12;
 			d.pos_bits = pos_bits_for(h.max_len);
 			for (int round = 0; round < 2; ++round) {
 				const int rc1 = ensure_exc(d, round == 0 ? d.out_cap / 16 + 1024 : (size_t)d.n_exc + 1024);
@@ -1099,7 +1111,7 @@ int ctx_fetch_packed(DeviceCtx &d, smem_gpu &h, void *out, uint32_t *read_off, l
 				CK(cudaMemsetAsync(d.d_status + 4, 0, sizeof(int), d.stream));
 				d.status_dirty = true;
 				intv12_from_dense_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, d.stream>>>(d.d_out, d.total, d.d_off, d.n, reinterpret_cast<u32 *>(d.d_outp),
-				                                                                                 d.d_off32, d.pos_bits, d.d_exc, (long long)d.exc_cap, d.d_status + 4);
+				                                                                                 d.d_off32, d.pos_bits, d.d_exc, (long long)d.exc_cap, d.d_status + 4, rec_bytes);
 				CK(cudaGetLastError());
 				CK(cudaMemcpyAsync(d.h_status + 4, d.d_status + 4, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
 				CK(stream_wait(d));
@@ -1112,11 +1124,11 @@ int ctx_fetch_packed(DeviceCtx &d, smem_gpu &h, void *out, uint32_t *read_off, l
 		}
 		d.outp_fmt = fmt;
 	}
-	const size_t rec = fmt == 2 ? 12 : 16;
+	const size_t rec = fmt == 3 ? 11 : fmt == 2 ? 12 : 16;
 	CK(cudaMemcpyAsync(read_off + d.lo, d.d_off32, (size_t)d.n * 4, cudaMemcpyDeviceToHost, d.stream));
 	d.d2h = d.n * 4;
 	if (out && d.total) { CK(cudaMemcpyAsync((uint8_t *)out + (size_t)base * rec, d.d_outp, (size_t)d.total * rec, cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.total * rec; }
-	const bool exc_fits = fmt == 2 && exc_out && d.n_exc <= exc_room;
+	const bool exc_fits = fmt >= 2 && exc_out && d.n_exc <= exc_room;
 	if (exc_fits && d.n_exc) { CK(cudaMemcpyAsync(exc_out + exc_base, d.d_exc, (size_t)d.n_exc * sizeof(Exc12), cudaMemcpyDeviceToHost, d.stream)); d.d2h += d.n_exc * (int64_t)sizeof(Exc12); }
 	CK(stream_wait(d));
 	if (base) {
@@ -1230,23 +1242,23 @@ int do_fetch_packed(smem_gpu *h, void *out, int64_t cap, uint32_t *read_off, int
 	//  so with several devices the lists are fetched one device at a time)
 	int rc = 0;
 	int64_t n_exc = 0;
-	if (fmt == 2 && h->devs.size() > 1) {
+	if (fmt >= 2 && h->devs.size() > 1) {
 		for (auto &d : h->devs) {
-			rc = ctx_fetch_packed(d, *h, fits ? out : nullptr, read_off, base[&d - &h->devs[0]], 2, xo.exc, n_exc, std::max<int64_t>(xo.cap - n_exc, 0));
+			rc = ctx_fetch_packed(d, *h, fits ? out : nullptr, read_off, base[&d - &h->devs[0]], fmt, xo.exc, n_exc, std::max<int64_t>(xo.cap - n_exc, 0));
 			if (rc) { h->err = "device " + std::to_string(d.dev) + ": " + d.err; return rc; }
 			n_exc += d.n_exc;
 		}
 	} else {
 		rc = for_each_device(h, [&](DeviceCtx &d) { return ctx_fetch_packed(d, *h, fits ? out : nullptr, read_off, base[&d - &h->devs[0]], fmt, xo.exc, 0, xo.cap); });
 		if (rc) return rc;
-		if (fmt == 2) n_exc = h->devs[0].n_exc;
+		if (fmt >= 2) n_exc = h->devs[0].n_exc;
 	}
 	read_off[h->staged] = (uint32_t)tot;
 	h->d2h_bytes = sum_d2h(h);
 	if (xo.n_out) *xo.n_out = n_exc;
 	if (xo.pos_bits_out) *xo.pos_bits_out = pos_bits_for(h->max_len);
 	if (!fits) { h->err = "intv_cap too small for the result"; return SMEM_GPU_E_CAPACITY; }
-	if (fmt == 2 && (n_exc > xo.cap || (n_exc > 0 && !xo.exc))) { h->err = "exc_cap too small for the exception list"; return SMEM_GPU_E_CAPACITY; }
+	if (fmt >= 2 && (n_exc > xo.cap || (n_exc > 0 && !xo.exc))) { h->err = "exc_cap too small for the exception list"; return SMEM_GPU_E_CAPACITY; }
 	return 0;
 }
 
@@ -1348,7 +1360,7 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_s
 			cv.wait(lk, [&] { for (size_t j = 0; j < k; ++j) if (!ran[j]) return false; return true; });
 			for (size_t j = 0; j < k; ++j) { base += totals[j]; exc_base += excs[j]; }
 			if (!r && base + d.total > out.cap) overflow = true;
-			if (!r && want_fmt == 2 && (exc_base + d.n_exc > out.xo.cap || (d.n_exc > 0 && !out.xo.exc))) exc_overflow = true;
+			if (!r && want_fmt >= 2 && (exc_base + d.n_exc > out.xo.cap || (d.n_exc > 0 && !out.xo.exc))) exc_overflow = true;
 		}
 		if (r) return r;
 		const bool fits = have_out && base + d.total <= out.cap;
@@ -1373,7 +1385,7 @@ int do_collect(smem_gpu *h, int mode, int64_t n, const BatchIn &in, const smem_s
 	if (out.total) *out.total = tot;
 	h->h2d_bytes = sum_h2d(h);
 	h->d2h_bytes = sum_d2h(h);
-	if (want_fmt == 2) {
+	if (want_fmt >= 2) {
 		long long ne = 0;
 		for (auto e : excs) ne += e;
 		if (out.xo.n_out) *out.xo.n_out = ne;
@@ -1941,6 +1953,23 @@ int smem_gpu_fetch_packed12(smem_gpu_t *h, smem_intv12_t *intv_out, int64_t intv
 	if (!h || exc_cap < 0) return SMEM_GPU_E_ARG;
 	Exc12Out xo; xo.exc = exc_out; xo.cap = exc_cap; xo.n_out = n_exc_out; xo.pos_bits_out = pos_bits_out;
 	return do_fetch_packed(h, intv_out, intv_cap, read_off, total_out, 2, xo);
+}
+
+int smem_gpu_collect_packed11(smem_gpu_t *h, const smem_reads2_t *reads, const smem_seed_opt_t *opt, smem_intv11_t *intv_out, int64_t intv_cap,
+                              uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap, int64_t *n_exc_out, int32_t *pos_bits_out, int64_t *total_out)
+{
+	if (!h || !reads || !opt || !read_off || exc_cap < 0) return SMEM_GPU_E_ARG;
+	CollectOut o; o.intv16 = intv_out; o.cap = intv_cap; o.read_off32 = read_off; o.total = total_out; o.fmt = 3;
+	o.xo.exc = exc_out; o.xo.cap = exc_cap; o.xo.n_out = n_exc_out; o.xo.pos_bits_out = pos_bits_out;
+	return do_collect(h, MODE_COLLECT, reads->n_reads, packed_in(reads), opt, o);
+}
+
+int smem_gpu_fetch_packed11(smem_gpu_t *h, smem_intv11_t *intv_out, int64_t intv_cap, uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap,
+                            int64_t *n_exc_out, int32_t *pos_bits_out, int64_t *total_out)
+{
+	if (!h || exc_cap < 0) return SMEM_GPU_E_ARG;
+	Exc12Out xo; xo.exc = exc_out; xo.cap = exc_cap; xo.n_out = n_exc_out; xo.pos_bits_out = pos_bits_out;
+	return do_fetch_packed(h, intv_out, intv_cap, read_off, total_out, 3, xo);
 }
 
 int smem_gpu_trace(smem_gpu_t *h, int64_t n_reads, const uint8_t *seq, const int64_t *offs, const smem_seed_opt_t *opt,

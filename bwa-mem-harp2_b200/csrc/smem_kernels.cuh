@@ -985,16 +985,26 @@ __global__ void __launch_bounds__(128) compact_packed_kernel(const Intv *__restr
 // the all-ones value of its 30 - 2P bits, else all ones and the interval's x2 travels in the exception list {index, x2}
 // (unordered; status[4] counts them, entries beyond exc_cap are dropped and the host re-runs the compaction with room).
 struct Exc12 { u32 index, x2_lo, x2_hi; };
+// rec_bytes = 12: three 32-bit words.  rec_bytes = 11 (smem_intv11_t): the third word shrinks to 24 bits -- the size field keeps
+// 22 - 2P bits (8 for reads up to 128 bases) -- and the records are byte-packed.  rec_bytes = -11: the 11-byte record's content in the
+// 12-byte layout (aligned word stores); squeeze11_kernel then drops every twelfth byte with coalesced word traffic.
 __device__ __forceinline__ void put_intv12(u32 *__restrict__ out, long long o, const Intv &v, int pos_bits, Exc12 *__restrict__ exc, long long exc_cap,
-                                           int *__restrict__ n_exc)
+                                           int *__restrict__ n_exc, int rec_bytes = 12)
 {
 	const u32 qb = (u32)(v.info >> 32) & 0xffffu, qe = (u32)v.info & 0xffffu;
-	const int fbits = 30 - 2 * pos_bits;
+	const int fbits = (rec_bytes == 12 ? 30 : 22) - 2 * pos_bits;
 	const u32 esc = (1u << fbits) - 1u;
 	const u64 x2m = v.x2 - 1;
 	const bool is_exc = x2m >= (u64)esc;
 	const u32 w2 = (u32)(v.x0 >> 32 & 1) | ((u32)(v.x1 >> 32 & 1) << 1) | (qb << 2) | ((qe - 1u) << (2 + pos_bits)) | ((is_exc ? esc : (u32)x2m) << (2 + 2 * pos_bits));
-	out[3 * o] = (u32)v.x0; out[3 * o + 1] = (u32)v.x1; out[3 * o + 2] = w2;
+	if (rec_bytes != 11) { out[3 * o] = (u32)v.x0; out[3 * o + 1] = (u32)v.x1; out[3 * o + 2] = w2; }
+	else {
+		uint8_t *b = reinterpret_cast<uint8_t *>(out) + 11 * o;
+		const u32 w0 = (u32)v.x0, w1 = (u32)v.x1;
+		b[0] = (uint8_t)w0; b[1] = (uint8_t)(w0 >> 8); b[2] = (uint8_t)(w0 >> 16); b[3] = (uint8_t)(w0 >> 24);
+		b[4] = (uint8_t)w1; b[5] = (uint8_t)(w1 >> 8); b[6] = (uint8_t)(w1 >> 16); b[7] = (uint8_t)(w1 >> 24);
+		b[8] = (uint8_t)w2; b[9] = (uint8_t)(w2 >> 8); b[10] = (uint8_t)(w2 >> 16);
+	}
 	if (is_exc) {
 		const long long k = atomicAdd(n_exc, 1);
 		if (k < exc_cap) { exc[k].index = (u32)o; exc[k].x2_lo = (u32)v.x2; exc[k].x2_hi = (u32)(v.x2 >> 32); }
@@ -1004,7 +1014,7 @@ __device__ __forceinline__ void put_intv12(u32 *__restrict__ out, long long o, c
 __global__ void __launch_bounds__(128) compact_packed12_kernel(const Intv *__restrict__ slots, int slot_cap, const int *__restrict__ counts,
                                                                const long long *__restrict__ off, long long n, u32 *__restrict__ out,
                                                                u32 *__restrict__ off32, long long out_cap, int pos_bits, Exc12 *__restrict__ exc,
-                                                               long long exc_cap, int *__restrict__ n_exc)
+                                                               long long exc_cap, int *__restrict__ n_exc, int rec_bytes)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long r = t >> 3;
@@ -1015,29 +1025,51 @@ __global__ void __launch_bounds__(128) compact_packed12_kernel(const Intv *__res
 	for (int e = (int)(t & 7); e < c; e += 8) {
 		Intv v = ld_intv(&slots[(size_t)r * slot_cap + e]);
 		v.info &= INFO_MASK;
-		put_intv12(out, o0 + e, v, pos_bits, exc, exc_cap, n_exc);
+		put_intv12(out, o0 + e, v, pos_bits, exc, exc_cap, n_exc, rec_bytes);
 	}
 }
 
 __global__ void compact_list_packed12_kernel(const Intv *__restrict__ big_slots, int big_cap, const int *__restrict__ list,
                                              const int *__restrict__ counts_k, int n_list, const long long *__restrict__ off, u32 *__restrict__ out,
-                                             int pos_bits, Exc12 *__restrict__ exc, long long exc_cap, int *__restrict__ n_exc)
+                                             int pos_bits, Exc12 *__restrict__ exc, long long exc_cap, int *__restrict__ n_exc, int rec_bytes)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const int k = (int)(t / big_cap), e = (int)(t % big_cap);
 	if (k >= n_list || e >= counts_k[k]) return;
 	Intv v = ld_intv(&big_slots[(size_t)k * big_cap + e]);
 	v.info &= INFO_MASK;
-	put_intv12(out, off[list[k]] + e, v, pos_bits, exc, exc_cap, n_exc);
+	put_intv12(out, off[list[k]] + e, v, pos_bits, exc, exc_cap, n_exc, rec_bytes);
+}
+
+// 12-byte layout with 24-bit third words -> byte-packed 11-byte records: four records (twelve words) in, eleven words out per thread
+__global__ void __launch_bounds__(256) squeeze11_kernel(const u32 *__restrict__ in, const long long *__restrict__ total_ptr, u32 *__restrict__ out)
+{
+	const long long groups = (*total_ptr + 3) >> 2;
+	for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+		const uint4 a = reinterpret_cast<const uint4 *>(in)[3 * g], b = reinterpret_cast<const uint4 *>(in)[3 * g + 1], c = reinterpret_cast<const uint4 *>(in)[3 * g + 2];
+		const u32 w0 = a.x, w1 = a.y, w2 = a.z & 0xffffffu, w3 = a.w, w4 = b.x, w5 = b.y & 0xffffffu, w6 = b.z, w7 = b.w, w8 = c.x & 0xffffffu, w9 = c.y, w10 = c.z,
+		          w11 = c.w & 0xffffffu;
+		u32 *o = out + 11 * g;
+		o[0] = w0; o[1] = w1;
+		o[2] = w2 | (w3 << 24);
+		o[3] = (w3 >> 8) | (w4 << 24);
+		o[4] = (w4 >> 8) | (w5 << 24);
+		o[5] = (w5 >> 8) | (w6 << 16);
+		o[6] = (w6 >> 16) | (w7 << 16);
+		o[7] = (w7 >> 16) | (w8 << 16);
+		o[8] = (w8 >> 16) | (w9 << 8);
+		o[9] = (w9 >> 24) | (w10 << 8);
+		o[10] = (w10 >> 24) | (w11 << 8);
+	}
 }
 
 // dense 32-byte results of an earlier run -> 12-byte records + 32-bit offsets (smem_gpu_fetch_packed12 after smem_gpu_run_collect)
 __global__ void intv12_from_dense_kernel(const Intv *__restrict__ in, long long total, const long long *__restrict__ off, long long n,
                                          u32 *__restrict__ out, u32 *__restrict__ off32, int pos_bits, Exc12 *__restrict__ exc, long long exc_cap,
-                                         int *__restrict__ n_exc)
+                                         int *__restrict__ n_exc, int rec_bytes)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < total) put_intv12(out, t, ld_intv(&in[t]), pos_bits, exc, exc_cap, n_exc);
+	if (t < total) put_intv12(out, t, ld_intv(&in[t]), pos_bits, exc, exc_cap, n_exc, rec_bytes);
 	if (t <= n) off32[t] = (u32)off[t];
 }
 

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("SMEM_GPU_LIB") or os.path.join(HERE, "libsmem_gpu.so"
 EXPORTS = [
     "smem_gpu_create", "smem_gpu_destroy", "smem_gpu_resize", "smem_gpu_upload_index", "smem_gpu_upload_index_device",
     "smem_gpu_collect", "smem_gpu_smem1", "smem_gpu_upload_sa", "smem_gpu_sa", "smem_gpu_seeds", "smem_gpu_chains", "smem_gpu_trace", "smem_gpu_share_index", "smem_gpu_build_repeat_filter", "smem_gpu_get_repeat_filter", "smem_gpu_build_text_index", "smem_gpu_get_text_index", "smem_gpu_stage_reads", "smem_gpu_run_collect", "smem_gpu_fetch",
-    "smem_gpu_collect_packed", "smem_gpu_stage_reads_packed", "smem_gpu_fetch_packed", "smem_gpu_pack_reads", "smem_gpu_collect_packed12", "smem_gpu_fetch_packed12",
+    "smem_gpu_collect_packed", "smem_gpu_stage_reads_packed", "smem_gpu_fetch_packed", "smem_gpu_pack_reads", "smem_gpu_collect_packed12", "smem_gpu_fetch_packed12", "smem_gpu_collect_packed11", "smem_gpu_fetch_packed11",
     "smem_gpu_host_alloc", "smem_gpu_host_free", "smem_gpu_last_timing", "smem_gpu_set_param",
     "smem_gpu_get_param", "smem_gpu_gather_roofline", "smem_gpu_strerror", "smem_gpu_last_error",
     "smem_gpu_device_count",
@@ -95,6 +95,21 @@ def unpack_intv12(rec: np.ndarray, pos_bits: int, exc: "np.ndarray | None" = Non
         if np.any(out[:, 2] == 0):
             raise ValueError("an escaped record has no entry in the exception list")
     return out
+
+
+def unpack_intv11(rec: np.ndarray, pos_bits: int, exc: "np.ndarray | None" = None) -> np.ndarray:
+    """smem_intv11_t records (uint8[n, 11]) + exception list -> bwtintv_t rows; mirrors smem_intv11_unpack of smem_gpu.h."""
+    b = np.asarray(rec, np.uint8).reshape(-1, 11).astype(np.uint32)
+    w = np.empty((len(b), 3), np.uint32)
+    w[:, 0] = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16) | (b[:, 3] << 24)
+    w[:, 1] = b[:, 4] | (b[:, 5] << 8) | (b[:, 6] << 16) | (b[:, 7] << 24)
+    w2 = b[:, 8] | (b[:, 9] << 8) | (b[:, 10] << 16)
+    # the third word of the 12-byte record with a size field of 22 - 2P instead of 30 - 2P bits: widen an all-ones field
+    fbits = 22 - 2 * pos_bits
+    f = w2 >> (2 + 2 * pos_bits)
+    wide = np.where(f == (1 << fbits) - 1, np.uint32((1 << (30 - 2 * pos_bits)) - 1), f)
+    w[:, 2] = (w2 & np.uint32((1 << (2 + 2 * pos_bits)) - 1)) | (wide.astype(np.uint32) << np.uint32(2 + 2 * pos_bits))
+    return unpack_intv12(w, pos_bits, exc)
 
 
 class PackedReads:
@@ -425,18 +440,24 @@ class SmemGpu:
             t = int(tot.value)
             return dict(rec=rec[:t], intv=unpack_intv16(rec[:t]) if unpack else None, read_off=read_off.astype(np.int64) if unpack else read_off)
 
-    def collect_packed12(self, reads: "PackedReads", opt: "SeedOpt | None" = None, out=None, read_off=None, exc=None, unpack=True):
+    def collect_packed11(self, reads: "PackedReads", opt: "SeedOpt | None" = None, **kw):
+        """smem_gpu_collect_packed11: like collect_packed12 with byte-packed 11-byte records."""
+        return self.collect_packed12(reads, opt, rec_bytes=11, **kw)
+
+    def collect_packed12(self, reads: "PackedReads", opt: "SeedOpt | None" = None, out=None, read_off=None, exc=None, unpack=True, rec_bytes=12):
         """smem_gpu_collect_packed12: compact reads in, 12-byte interval records + exception list + uint32 CSR offsets out."""
         opt = opt or SeedOpt()
+        fn = self.lib.smem_gpu_collect_packed12 if rec_bytes == 12 else self.lib.smem_gpu_collect_packed11
+        shape, dt, unp = ((3,), np.uint32, unpack_intv12) if rec_bytes == 12 else ((11,), np.uint8, unpack_intv11)
         n = reads.n
         cap = out.shape[0] if out is not None else max(64, 16 * n)
         exc_cap = exc.shape[0] if exc is not None else max(64, n)
         read_off = read_off if read_off is not None else np.zeros(n + 1, np.uint32)
         tot, n_exc, pb = C.c_int64(0), C.c_int64(0), C.c_int32(0)
         while True:
-            rec = out if out is not None else np.empty((cap, 3), np.uint32)
+            rec = out if out is not None else np.empty((cap,) + shape, dt)
             ex = exc if exc is not None else np.empty(exc_cap, EXC_DTYPE)
-            rc = self.lib.smem_gpu_collect_packed12(self.h, C.byref(reads.desc), C.byref(opt), C.c_void_p(rec.ctypes.data), C.c_int64(cap),
+            rc = fn(self.h, C.byref(reads.desc), C.byref(opt), C.c_void_p(rec.ctypes.data), C.c_int64(cap),
                                                     C.c_void_p(read_off.ctypes.data), C.c_void_p(ex.ctypes.data), C.c_int64(exc_cap), C.byref(n_exc),
                                                     C.byref(pb), C.byref(tot))
             if rc == -5 and out is None and exc is None and (tot.value > cap or n_exc.value > exc_cap):
@@ -444,25 +465,30 @@ class SmemGpu:
                 continue
             self._check(rc)
             t, ne = int(tot.value), int(n_exc.value)
-            return dict(rec=rec[:t], exc=ex[:ne], pos_bits=int(pb.value), intv=unpack_intv12(rec[:t], int(pb.value), ex[:ne]) if unpack else None,
+            return dict(rec=rec[:t], exc=ex[:ne], pos_bits=int(pb.value), intv=unp(rec[:t], int(pb.value), ex[:ne]) if unpack else None,
                         read_off=read_off.astype(np.int64) if unpack else read_off)
 
-    def fetch_packed12(self, total: int):
+    def fetch_packed11(self, total: int):
+        return self.fetch_packed12(total, rec_bytes=11)
+
+    def fetch_packed12(self, total: int, rec_bytes=12):
         n = self._n
+        fn = self.lib.smem_gpu_fetch_packed12 if rec_bytes == 12 else self.lib.smem_gpu_fetch_packed11
+        shape, dt, unp = ((3,), np.uint32, unpack_intv12) if rec_bytes == 12 else ((11,), np.uint8, unpack_intv11)
         read_off = np.zeros(n + 1, np.uint32)
         tot, n_exc, pb = C.c_int64(0), C.c_int64(0), C.c_int32(0)
         exc_cap = 1024
         while True:
-            rec = np.empty((max(total, 1), 3), np.uint32)
+            rec = np.empty((max(total, 1),) + shape, dt)
             ex = np.empty(exc_cap, EXC_DTYPE)
-            rc = self.lib.smem_gpu_fetch_packed12(self.h, C.c_void_p(rec.ctypes.data), C.c_int64(rec.shape[0]), C.c_void_p(read_off.ctypes.data),
+            rc = fn(self.h, C.c_void_p(rec.ctypes.data), C.c_int64(rec.shape[0]), C.c_void_p(read_off.ctypes.data),
                                                   C.c_void_p(ex.ctypes.data), C.c_int64(exc_cap), C.byref(n_exc), C.byref(pb), C.byref(tot))
             if rc == -5 and n_exc.value > exc_cap:
                 exc_cap = int(n_exc.value)
                 continue
             self._check(rc)
             t, ne = int(tot.value), int(n_exc.value)
-            return dict(rec=rec[:t], exc=ex[:ne], pos_bits=int(pb.value), intv=unpack_intv12(rec[:t], int(pb.value), ex[:ne]), read_off=read_off.astype(np.int64))
+            return dict(rec=rec[:t], exc=ex[:ne], pos_bits=int(pb.value), intv=unp(rec[:t], int(pb.value), ex[:ne]), read_off=read_off.astype(np.int64))
 
     def stage_packed(self, reads: "PackedReads"):
         self._keep = reads

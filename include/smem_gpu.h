@@ -264,6 +264,28 @@ int smem_gpu_collect_packed12(smem_gpu_t *h, const smem_reads2_t *reads, const s
                               int64_t *total_out);
 int smem_gpu_fetch_packed12(smem_gpu_t *h, smem_intv12_t *intv_out, int64_t intv_cap, uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap,
                             int64_t *n_exc_out, int32_t *pos_bits_out, int64_t *total_out);
+/* The same record squeezed into 11 bytes, byte-packed (for reads of up to 512 bases): b[0..3] = low word of x[0], b[4..7] = low word
+ * of x[1] (little endian), b[8..10] = the third word of smem_intv12_t with its size field cut to 22 - 2 P bits (8 bits = sizes up to
+ * 255 for reads of up to 128 bases; larger ones go to the same exception list).  What it is for: the last 8 % of the link. */
+typedef struct { uint8_t b[11]; } smem_intv11_t;
+static inline int smem_intv11_unpack(const smem_intv11_t *p, int pos_bits, smem_intv_t *o)
+{
+	const uint32_t w0 = (uint32_t)p->b[0] | ((uint32_t)p->b[1] << 8) | ((uint32_t)p->b[2] << 16) | ((uint32_t)p->b[3] << 24);
+	const uint32_t w1 = (uint32_t)p->b[4] | ((uint32_t)p->b[5] << 8) | ((uint32_t)p->b[6] << 16) | ((uint32_t)p->b[7] << 24);
+	const uint32_t w2 = (uint32_t)p->b[8] | ((uint32_t)p->b[9] << 8) | ((uint32_t)p->b[10] << 16);
+	const uint32_t pm = ((uint32_t)1 << pos_bits) - 1, esc = ((uint32_t)1 << (22 - 2 * pos_bits)) - 1;
+	const uint32_t f = w2 >> (2 + 2 * pos_bits);
+	o->x[0] = (uint64_t)w0 | ((uint64_t)(w2 & 1) << 32);
+	o->x[1] = (uint64_t)w1 | ((uint64_t)((w2 >> 1) & 1) << 32);
+	o->x[2] = f == esc ? 0 : (uint64_t)f + 1;
+	o->info = ((uint64_t)((w2 >> 2) & pm) << 32) | (uint64_t)(((w2 >> (2 + pos_bits)) & pm) + 1);
+	return f == esc;
+}
+int smem_gpu_collect_packed11(smem_gpu_t *h, const smem_reads2_t *reads, const smem_seed_opt_t *opt, smem_intv11_t *intv_out, int64_t intv_cap,
+                              uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap, int64_t *n_exc_out, int32_t *pos_bits_out,
+                              int64_t *total_out);
+int smem_gpu_fetch_packed11(smem_gpu_t *h, smem_intv11_t *intv_out, int64_t intv_cap, uint32_t *read_off, smem_x2exc_t *exc_out, int64_t exc_cap,
+                            int64_t *n_exc_out, int32_t *pos_bits_out, int64_t *total_out);
 /* Host-side packer for callers that hold bwa's one-byte-per-base reads (n_threads host threads; lens and amb may be NULL if
  * the batch has one length / the caller knows there are no ambiguous bases -- then an ambiguous base is an error).
  * *n_amb_out = entries written (or needed, with SMEM_GPU_E_CAPACITY). */

@@ -33,6 +33,9 @@ def check(sg, g, o, seq, offs, opt=None, **kw):
     got = g.collect_packed12(pr, gopt)                                  # 12-byte records + exception list: the same lists again
     assert np.array_equal(got["read_off"], want["read_off"])
     assert np.array_equal(got["intv"], want["intv"])
+    got = g.collect_packed11(pr, gopt)                                  # ... byte-packed 11-byte records (the handle's 260-base limit leaves 4 bits of size)
+    assert np.array_equal(got["read_off"], want["read_off"])
+    assert np.array_equal(got["intv"], want["intv"])
     got16 = g.collect_packed(pr, gopt)                                  # (kept last: the d2h byte counts asserted by callers are the 16-byte form's)
     assert np.array_equal(got16["intv"], want["intv"])
     return pr, want
@@ -123,17 +126,25 @@ def test_packed12_exception_list(world, synth):
     assert np.array_equal(got["read_off"], want["read_off"]) and np.array_equal(got["intv"], want["intv"])
     t = g.timing()
     assert t["d2h_bytes"] == len(offs) * 4 - 4 + 12 * len(want["intv"]) + 12 * len(got["exc"])
+    got11 = g.collect_packed11(pr)
+    assert np.array_equal(got11["read_off"], want["read_off"]) and np.array_equal(got11["intv"], want["intv"]) and len(got11["exc"]) >= len(got["exc"])
+    assert g.timing()["d2h_bytes"] == len(offs) * 4 - 4 + 11 * len(want["intv"]) + 12 * len(got11["exc"])
     # reads that outgrow their slots: the first 64 entries are placed by the first compaction, the whole list again by the re-run
     g.set_param("slot_cap", 64)
     try:
         got = g.collect_packed12(pr)
         assert g.timing()["overflow_reads"] >= 400
         assert np.array_equal(got["read_off"], want["read_off"]) and np.array_equal(got["intv"], want["intv"])
+        got = g.collect_packed11(pr)
+        assert np.array_equal(got["read_off"], want["read_off"]) and np.array_equal(got["intv"], want["intv"])
     finally:
         g.set_param("slot_cap", 224)
     # split form: resident 32-byte results -> 12-byte records; and 16-byte resident results are not converted silently
     g.stage_packed(pr); tot = g.run_collect()
     b = g.fetch_packed12(tot)
+    assert np.array_equal(b["intv"], want["intv"]) and np.array_equal(b["read_off"], want["read_off"])
+    g.stage_packed(pr); tot = g.run_collect()
+    b = g.fetch_packed11(tot)
     assert np.array_equal(b["intv"], want["intv"]) and np.array_equal(b["read_off"], want["read_off"])
     g.collect_packed(pr)
     g._n = pr.n
