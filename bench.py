@@ -548,7 +548,8 @@ def main():
         del h_in, h_out, d_in, d_out
         sync()
     use11 = record_choice["record_bytes"] == 11 and args.read_len <= 512      # (the 11-byte form needs query positions of <= 9 bits)
-    log("record size of the end-to-end leg:", record_choice)
+    if rank == 0:
+        log("record size of the end-to-end leg:", record_choice)
     def step_packed11(t):
         return step_packed_small(t, lib.smem_gpu_collect_packed11, prec11, "smem_gpu_collect_packed11")
     def step_packed12(t):
