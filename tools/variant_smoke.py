@@ -49,4 +49,4 @@ for lpr, devices in ((4, [0]), (4, [0, 0]), (2, [0]), (3, [0]), (1, [0])):
     k = np.random.default_rng(2).integers(0, ix.seq_len + 1, 2000).astype(np.uint64)
     assert np.array_equal(g.sa(k), o.sa(ix, k))
     g.close()
-print("sanitize smoke ok")
+print("variant smoke ok")
