@@ -118,6 +118,18 @@ void orc_set_unique_walk_tables(const uint8_t *text, const uint64_t *fsa, const 
 }
 uint64_t orc_get_unique_walks(void) { return orc_uw_walks; }
 
+/* MODEL of the device kernel's split backward sweep, off unless orc_set_split_pairs(1) -- a test hook.  The
+ * entries of one backward round are independent but for two things: an entry whose new size equals the last KEPT entry's is
+ * dropped, and the first entry to die while nothing has been kept yet may be recorded.  The device therefore extends prev[j] and
+ * prev[j + 1] in the same trip (one lane each), exchanges the two new sizes and replays both decisions in order.  This model does
+ * exactly that on the CPU -- both extends first, from the untouched entries, then the decisions from the sizes alone, the second
+ * emission of a pair suppressed the way the device suppresses it -- so that the suite checks the rule against the sequential loop of
+ * bwt.c:812-825 without a GPU. */
+static int orc_split_pairs = 0;
+uint64_t orc_split_trips = 0;
+void orc_set_split_pairs(int on) { orc_split_pairs = on; orc_split_trips = 0; }
+uint64_t orc_get_split_trips(void) { return orc_split_trips; }
+
 /* bwt_smem1, bwt.c:776-835.  Writes the SMEM candidates through x into `mem`, returns ret. */
 static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int min_intv, ivv_t *mem,
                  ivv_t *prev, ivv_t *curr, orc_stats_t *st)
@@ -189,6 +201,32 @@ static int smem1(const orc_index_t *ix, int len, const uint8_t *q, int x, int mi
 	for (i = x - 1; i >= -1; --i) { /* backward */
 		int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
 		curr->n = 0;
+		if (orc_split_pairs && c >= 0) {
+			uint64_t last_s = 0;
+			for (j = 0; j < prev->n; j += 2) {
+				const int two = j + 1 < prev->n;
+				iv_t okA[4], okB[4], *pA = &prev->a[j], *pB = two ? &prev->a[j + 1] : 0;
+				uint64_t sA, sB = 0;
+				int smallA, smallB = 0, emitA, pushA, emitB, pushB;
+				extend(ix, pA, 1, okA, st);
+				if (two) extend(ix, pB, 1, okB, st);
+				__sync_fetch_and_add(&orc_split_trips, 1);
+				sA = okA[c].x2; if (two) sB = okB[c].x2;
+				smallA = sA < (uint64_t)min_intv; smallB = two && sB < (uint64_t)min_intv;
+				emitA = smallA && curr->n == 0;
+				pushA = !smallA && (curr->n == 0 || sA != last_s);
+				if (emitA && (mem->n == 0 || (uint64_t)(i + 1) < (mem->a[mem->n - 1].info >> 32))) {
+					iv_t e = *pA; e.info |= (uint64_t)(i + 1) << 32; ivv_push(mem, e);
+				}
+				if (pushA) { okA[c].info = pA->info; ivv_push(curr, okA[c]); last_s = sA; }
+				emitB = two && !emitA && smallB && curr->n == 0;
+				pushB = two && !(sB < (uint64_t)min_intv) && (curr->n == 0 || sB != last_s);
+				if (emitB && (mem->n == 0 || (uint64_t)(i + 1) < (mem->a[mem->n - 1].info >> 32))) {
+					iv_t e = *pB; e.info |= (uint64_t)(i + 1) << 32; ivv_push(mem, e);
+				}
+				if (pushB) { okB[c].info = pB->info; ivv_push(curr, okB[c]); last_s = sB; }
+			}
+		} else
 		for (j = 0; j < prev->n; ++j) {
 			iv_t *p = &prev->a[j];
 			extend(ix, p, 1, ok, st);

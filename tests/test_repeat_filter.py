@@ -67,6 +67,41 @@ def test_spec_walk_rule_is_exact_on_cpu(worlds, synth):
         assert hits > 1000
 
 
+def test_split_backward_sweep_rule_is_exact_on_cpu(worlds, synth):
+    """Model of the device kernel's split backward sweep (smem_oracle.c, orc_set_split_pairs): the entries of a
+    backward round extended two at a time, the push / emit decisions replayed in order from the two new sizes -- against the
+    sequential loop of bwt.c:812-825, alone and together with the other shortcuts' models, on random and repeat-rich texts."""
+    for name, ref, ix, o in worlds:
+        o.lib.orc_get_split_trips.restype = C.c_uint64
+        trips = 0
+        for rl, err, opt in SETS:
+            seq, offs = synth.to_batch(synth.simulate_reads(ref, 1200, rl, err, seed=31, paired=True, n_frac=0.05))
+            o.lib.orc_set_skip_kmer(0); o.lib.orc_set_spec_walk(0); o.lib.orc_set_split_pairs(0)
+            want = o.collect(seq, offs, opt, nthreads=2)
+            for K, spec in ((0, 0), (15, 1)):
+                o.lib.orc_set_skip_kmer(K); o.lib.orc_set_spec_walk(spec); o.lib.orc_set_split_pairs(1)
+                try:
+                    got = o.collect(seq, offs, opt, nthreads=2)
+                    trips += o.lib.orc_get_split_trips()
+                finally:
+                    o.lib.orc_set_skip_kmer(0); o.lib.orc_set_spec_walk(0); o.lib.orc_set_split_pairs(0)
+                for k in ("intv", "read_off", "step", "n_steps", "last_start"):
+                    assert np.array_equal(got[k], want[k]), (name, rl, K, k)
+            # raw calls too (every x, several min_intv)
+            n = len(offs) - 1
+            rng = np.random.default_rng(rl)
+            x = rng.integers(0, rl, n).astype(np.int32); mi = rng.integers(0, 5, n).astype(np.int32)
+            w1 = o.smem1(seq, offs, x, mi)
+            o.lib.orc_set_split_pairs(1)
+            try:
+                g1 = o.smem1(seq, offs, x, mi)
+            finally:
+                o.lib.orc_set_split_pairs(0)
+            for k in ("intv", "read_off", "ret"):
+                assert np.array_equal(g1[k], w1[k]), (name, rl, k)
+        assert trips > 100_000
+
+
 def test_unique_walk_counting_model_leaves_results_alone(worlds, synth):
     """orc_set_unique_walk only changes the oracle's extend / block counts (bench.py's `executed` figure), never a result."""
     for name, ref, ix, o in worlds:
